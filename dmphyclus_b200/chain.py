@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's MCMC driver (`/root/reference/R/DMphyClusSource.R`) over a
+pluggable likelihood backend.
+
+The reference's driver is R and stays R in a drop-in deployment; R is absent from this
+image, so this module restates `.performStepPhylo` and the five Metropolis-Hastings moves with the same
+move order, the same calls into the eleven entry points and the same RNG *draw order*, so that
+
+  * "identical cluster-indicator trajectories for a fixed seed" is testable (CUDA engine vs oracle under
+    the same numpy stream), and
+  * `MCMC iterations/sec` can be measured.
+
+R's own Mersenne-Twister stream (`sample.int`, `sample`, `runif`) is replaced by `numpy.random.Generator`
+— the draw ORDER is the reference's, the VALUES are numpy's.  A backend is any object with the eleven
+entry points under the reference's names (`dmphyclus_b200.engine.Engine`; the tests plug in the oracle).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .phylo import Phylo, cluster_mrcas
+
+
+# ---------------------------------------------------------------- priors (R/DMphyClusInterface.R:147-162)
+def _log_big_b(x) -> float:                       # .logBigB, DMphyClusSource.R:329-333
+    x = np.asarray(x, dtype=np.float64)
+    return float(sum(math.lgamma(v) for v in x) - math.lgamma(float(x.sum())))
+
+
+def clusIndLogPrior(clusInd, alpha, k=None) -> float:
+    """Dirichlet-multinomial log-prior of a cluster assignment vector (clusIndLogPrior, R API)."""
+    counts = np.bincount(np.unique(np.asarray(clusInd), return_inverse=True)[1]).astype(np.float64)
+    if k is None:
+        k = len(counts)
+    alpha_vec = np.full(k, float(alpha)) if np.ndim(alpha) == 0 else np.asarray(alpha, dtype=np.float64)
+    if len(counts) < k:
+        counts = np.concatenate([counts, np.zeros(k - len(counts))])
+    n = len(np.asarray(clusInd))
+    return (math.lgamma(n + 1) - sum(math.lgamma(c + 1) for c in counts)
+            + _log_big_b(alpha_vec + counts) - _log_big_b(alpha_vec))
+
+
+def _dgamma_log(x, shape, scale) -> float:
+    if x <= 0:
+        return -math.inf if not (x == 0 and shape == 1) else -math.log(scale)
+    return (shape - 1) * math.log(x) - x / scale - math.lgamma(shape) - shape * math.log(scale)
+
+
+def _dpois_log(k, lam) -> float:
+    return k * math.log(lam) - lam - math.lgamma(k + 1)
+
+
+def _relabel(x):                                   # .relabel, DMphyClusSource.R:322-327
+    x = np.asarray(x)
+    _, inv = np.unique(x, return_inverse=True)
+    return inv + 1
+
+
+# ---------------------------------------------------------------- state
+@dataclass
+class ChainSettings:
+    limProbs: np.ndarray
+    withinTransMatAll: np.ndarray          # [n_within][R][4][4]
+    betweenTransMatAll: np.ndarray         # [n_between][R][4][4]
+    shapeForAlpha: float
+    scaleForAlpha: float
+    alphaMin: float = 0.0
+    poisRateNumClus: float = 1.0
+    numMovesNNIbetween: int = 1
+    numMovesNNIwithin: int = 1
+    numLikThreads: int = 1
+    clusPhyloUpdateProp: float = 1.0
+    numSplitMergeMoves: int = 1
+    togglePhyloUpdates: bool = True
+    maxMapSize: float | None = None
+    cullProportion: float | None = None
+
+
+@dataclass
+class ChainState:
+    edge: np.ndarray                       # paraValues$phylogeny$edge
+    n_tips: int
+    clusInd: np.ndarray                    # paraValues$clusInd, in tip order
+    alpha: float
+    withinMatListIndex: int
+    betweenMatListIndex: int
+    clusterNodeIndices: list
+    logLik: float = 0.0
+    logPostProb: float = 0.0
+    extPointer: object = None
+    clusterCounts: dict = field(default_factory=dict)   # names(clusterCounts) -> count
+    n_loglik_calls: int = 0
+
+
+def init_current_value(backend, alignmentBin, edge, clusInd, alpha, st: ChainSettings,
+                       withinMatListIndex=None, betweenMatListIndex=None) -> ChainState:
+    """.initCurrentValue (DMphyClusSource.R:54-98)."""
+    n, s = alignmentBin.shape
+    if betweenMatListIndex is None:
+        betweenMatListIndex = math.ceil(len(st.betweenTransMatAll) / 2)
+    if withinMatListIndex is None:
+        withinMatListIndex = math.ceil(len(st.withinTransMatAll) / 2)
+    phy = Phylo(edge, n)
+    clusInd = np.asarray(clusInd, dtype=np.int64)
+    mrcas = cluster_mrcas(phy, clusInd)
+    res = backend.logLikCpp(edge, mrcas, st.limProbs, st.withinTransMatAll[withinMatListIndex - 1],
+                            st.betweenTransMatAll[betweenMatListIndex - 1], st.numLikThreads, alignmentBin, n, s,
+                            withinMatListIndex, betweenMatListIndex)
+    cv = ChainState(edge=np.array(edge, dtype=np.int32), n_tips=n, clusInd=clusInd, alpha=float(alpha),
+                    withinMatListIndex=withinMatListIndex, betweenMatListIndex=betweenMatListIndex,
+                    clusterNodeIndices=list(mrcas), logLik=res["logLik"], extPointer=res["solutionPointer"])
+    cv.clusterCounts = {k: int((clusInd == k).sum()) for k in range(1, int(clusInd.max()) + 1)}
+    cv.logPostProb = (cv.logLik + clusIndLogPrior(clusInd, cv.alpha)
+                      + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+                      + _dpois_log(int(clusInd.max()), st.poisRateNumClus))
+    cv.n_loglik_calls = 1
+    return cv
+
+
+# ---------------------------------------------------------------- moves
+def _update_trans_matrix(backend, cv: ChainState, st: ChainSettings, rng, between: bool):
+    """.updateTransMatrix (DMphyClusSource.R:216-255)."""
+    all_list = st.betweenTransMatAll if between else st.withinTransMatAll
+    new_index = int(rng.integers(1, len(all_list) + 1))           # sample.int(n, 1)
+    if between:
+        new_ll = backend.newBetweenTransProbsLogLik(cv.extPointer, st.withinTransMatAll[cv.withinMatListIndex - 1],
+                                                    all_list[new_index - 1], st.numLikThreads, new_index, st.limProbs)
+    else:
+        new_ll = backend.newWithinTransProbsLogLik(cv.extPointer, all_list[new_index - 1],
+                                                   st.betweenTransMatAll[cv.betweenMatListIndex - 1],
+                                                   st.numLikThreads, new_index, st.limProbs)
+    cv.n_loglik_calls += 1
+    if rng.random() < _exp(new_ll - cv.logLik):
+        if between:
+            cv.betweenMatListIndex = new_index
+        else:
+            cv.withinMatListIndex = new_index
+        cv.logPostProb = new_ll + (cv.logPostProb - cv.logLik)
+        cv.logLik = new_ll
+    else:
+        backend.RestorePreviousConfig(cv.extPointer, np.zeros((1, 2), np.int32), cv.withinMatListIndex,
+                                      cv.betweenMatListIndex, False, cv.clusterNodeIndices, False)
+
+
+def _exp(x: float) -> float:
+    return math.inf if x > 700 else math.exp(x)
+
+
+def _nni_update(backend, cv, st, rng, call):
+    res = call()
+    cv.n_loglik_calls += 1
+    new_ll = res["logLik"]
+    if rng.random() < _exp(new_ll - cv.logLik):
+        cv.logPostProb = cv.logPostProb - cv.logLik + new_ll
+        cv.logLik = new_ll
+        cv.edge = np.array(res["edge"], dtype=np.int32)
+    else:
+        backend.RestorePreviousConfig(cv.extPointer, cv.edge, cv.withinMatListIndex, cv.betweenMatListIndex, True,
+                                      cv.clusterNodeIndices, False)
+
+
+def _update_between_phylo(backend, cv, st, rng):
+    """.updateBetweenPhylo (DMphyClusSource.R:335-351)."""
+    w = st.withinTransMatAll[cv.withinMatListIndex - 1]
+    b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+    _nni_update(backend, cv, st, rng, lambda: backend.betweenClusNNIlogLik(
+        cv.extPointer, w, b, cv.clusterNodeIndices, st.numMovesNNIbetween, st.numLikThreads, st.limProbs))
+
+
+def _update_cluster_phylos(backend, cv, st, rng):
+    """.updateClusterPhylos (DMphyClusSource.R:371-415)."""
+    if st.clusPhyloUpdateProp < 1:
+        k = math.ceil(len(cv.clusterNodeIndices) * st.clusPhyloUpdateProp)
+        select = [cv.clusterNodeIndices[i] for i in rng.choice(len(cv.clusterNodeIndices), size=k, replace=False)]
+    else:
+        select = list(cv.clusterNodeIndices)
+    original = Phylo(cv.edge, cv.n_tips)
+    for mrca in select:
+        if len(original.descendants(mrca)) < 3:
+            continue
+        w = st.withinTransMatAll[cv.withinMatListIndex - 1]
+        b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+        _nni_update(backend, cv, st, rng, lambda: backend.withinClusNNIlogLik(
+            cv.extPointer, w, b, mrca, st.numMovesNNIwithin, st.numLikThreads, st.limProbs))
+
+
+def _pairs_and_splits(phy: Phylo, mrcas, counts_gt1):
+    """Sibling cluster pairs (mergeable) grouped by parent in increasing parent id, as
+    split(clusterNodeIndices, f = parent) orders its factor levels (DMphyClusSource.R:157-165)."""
+    groups = {}
+    for m in mrcas:
+        groups.setdefault(int(phy.parent[m]), []).append(m)
+    pairs = [groups[p] for p in sorted(groups) if len(groups[p]) > 1]
+    return pairs, counts_gt1
+
+
+def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
+    """.splitJoinClusterMove / .performSplit / .performMerge (DMphyClusSource.R:100-214)."""
+    phy = Phylo(cv.edge, cv.n_tips)
+    pairs = _pairs_and_splits(phy, cv.clusterNodeIndices, None)[0] if len(cv.clusterNodeIndices) > 1 else []
+    to_split = [k for k, c in cv.clusterCounts.items() if c > 1]
+    num_moves = len(pairs) + len(to_split)
+    if num_moves == 0:
+        raise RuntimeError("No possible move. This is an error. Exiting...")
+    selected = int(rng.integers(1, num_moves + 1))                # sample(1:numMoves, 1)
+    split_move = selected > len(pairs)
+    w = st.withinTransMatAll[cv.withinMatListIndex - 1]
+    b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+    if split_move:
+        clus_number = to_split[selected - len(pairs) - 1]
+        node = cv.clusterNodeIndices[clus_number - 1]
+        if node <= cv.n_tips:
+            raise RuntimeError("split of a cluster whose stored MRCA is a tip (single-cluster start): "
+                               "the reference dereferences a null child here (AugTree.cpp:332)")
+        new_nodes = phy.children[node]
+        new_mrcas = list(cv.clusterNodeIndices)
+        new_mrcas[clus_number - 1] = new_nodes[0]
+        new_mrcas += new_nodes[1:]
+        new_ll = backend.clusSplitMergeLogLik(cv.extPointer, w, b, [node], st.numLikThreads, st.limProbs)
+        new_clus = cv.clusInd.copy()
+        numbers = [clus_number] + list(range(len(cv.clusterNodeIndices) + 1, len(new_mrcas) + 1))
+        for nd, num in zip(new_nodes, numbers):
+            new_clus[phy.descendants(nd) - 1] = num
+    else:
+        to_merge = pairs[selected - 1]
+        new_mrca = int(phy.parent[to_merge[0]])                   # phangorn::mrca.phylo of siblings
+        numbers = [cv.clusterNodeIndices.index(m) + 1 for m in to_merge]
+        replaced = list(cv.clusterNodeIndices)
+        for k in numbers:
+            replaced[k - 1] = new_mrca
+        new_mrcas = list(dict.fromkeys(replaced))                 # unique(), first occurrence kept
+        new_ll = backend.clusSplitMergeLogLik(cv.extPointer, w, b, to_merge, st.numLikThreads, st.limProbs)
+        new_clus = cv.clusInd.copy()
+        new_clus[np.isin(new_clus, numbers)] = min(numbers)
+    cv.n_loglik_calls += 1
+    labels, cnt = np.unique(new_clus, return_counts=True)
+    new_counts = {int(l): int(c) for l, c in zip(labels, cnt)}
+    new_lpp = (new_ll + clusIndLogPrior(new_clus, cv.alpha)
+               + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+               + _dpois_log(int(new_clus.max()), st.poisRateNumClus))
+    groups = {}
+    for m in new_mrcas:
+        groups.setdefault(int(phy.parent[m]), []).append(m)
+    num_pairs_new = sum(1 for g in groups.values() if len(g) > 1)
+    num_splits_new = sum(1 for c in new_counts.values() if c > 1)
+    ratio = num_moves / (num_pairs_new + num_splits_new)
+    mh = ratio * _exp(new_lpp - cv.logPostProb)
+    if rng.random() < mh:
+        cv.logLik, cv.logPostProb = new_ll, new_lpp
+        cv.clusInd, cv.clusterCounts, cv.clusterNodeIndices = new_clus, new_counts, new_mrcas
+        if not split_move:
+            keys = _relabel(np.array(sorted(cv.clusterCounts)))
+            cv.clusterCounts = {int(k): cv.clusterCounts[o] for k, o in zip(keys, sorted(cv.clusterCounts))}
+            cv.clusInd = _relabel(cv.clusInd)
+    else:
+        backend.RestorePreviousConfig(cv.extPointer, np.zeros((1, 2), np.int32), cv.withinMatListIndex,
+                                      cv.betweenMatListIndex, False, cv.clusterNodeIndices, True)
+
+
+def _update_alpha(cv: ChainState, st: ChainSettings, rng):
+    """.updateAlpha (DMphyClusSource.R:38-52)."""
+    new_alpha = cv.alpha + (rng.random() - 0.5)
+    new_alpha = new_alpha + abs(new_alpha - st.alphaMin) * (new_alpha < st.alphaMin)
+    new_lp = clusIndLogPrior(cv.clusInd, new_alpha) + _dgamma_log(new_alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+    cur_lp = clusIndLogPrior(cv.clusInd, cv.alpha) + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+    pois = cv.logPostProb - cur_lp - cv.logLik
+    if rng.random() < _exp(new_lp - cur_lp):
+        cv.alpha = new_alpha
+        cv.logPostProb = cv.logLik + new_lp + pois
+
+
+def perform_step_phylo(backend, cv: ChainState, st: ChainSettings, rng) -> ChainState:
+    """One MCMC iteration: .performStepPhylo (DMphyClusSource.R:1-26)."""
+    if cv.clusInd.max() > 1:
+        _update_trans_matrix(backend, cv, st, rng, between=True)
+    _update_trans_matrix(backend, cv, st, rng, between=False)
+    if st.togglePhyloUpdates:
+        if cv.clusInd.max() > 2:
+            _update_between_phylo(backend, cv, st, rng)
+        _update_cluster_phylos(backend, cv, st, rng)
+    for _ in range(st.numSplitMergeMoves):
+        _split_join_cluster_move(backend, cv, st, rng)
+    _update_alpha(cv, st, rng)
+    if st.maxMapSize is not None:
+        backend.checkAndCullMap(cv.extPointer, st.maxMapSize, st.cullProportion,
+                                st.withinTransMatAll[cv.withinMatListIndex - 1],
+                                st.betweenTransMatAll[cv.betweenMatListIndex - 1], st.limProbs)
+    return cv
+
+
+def run_chain(backend, alignmentBin, edge, clusInd, alpha, st: ChainSettings, n_iter: int, seed: int = 0,
+              withinMatListIndex=None, betweenMatListIndex=None, on_iter=None):
+    """.DMphyClusCore (DMphyClusSource.R:257-313): returns the per-iteration samples."""
+    rng = np.random.default_rng(seed)
+    cv = init_current_value(backend, alignmentBin, edge, clusInd, alpha, st, withinMatListIndex, betweenMatListIndex)
+    out = []
+    try:
+        for it in range(n_iter):
+            perform_step_phylo(backend, cv, st, rng)
+            out.append({"clusInd": cv.clusInd.copy(), "edge": cv.edge.copy(), "alpha": cv.alpha,
+                        "withinMatListIndex": cv.withinMatListIndex, "betweenMatListIndex": cv.betweenMatListIndex,
+                        "clusterNodeIndices": list(cv.clusterNodeIndices), "logPostProb": cv.logPostProb,
+                        "logLik": cv.logLik})
+            if on_iter is not None:
+                on_iter(it, cv)
+    finally:
+        backend.finalDeallocate(cv.extPointer)
+    return out, cv.n_loglik_calls

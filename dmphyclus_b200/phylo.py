@@ -1,0 +1,108 @@
+"""Edge-matrix tree utilities: the few `ape` / `phangorn` functions the reference's R driver leans on
+(`ape::getMRCA`, `phangorn::Children`, `Descendants`, `Ancestors(type="parent")`;
+`/root/reference/R/DMphyClusSource.R:78-88,104,112,146,159,380-386`), restated on the `phylo$edge`
+convention the C++ side consumes (`/root/reference/src/AugTree.cpp:59-86`): int matrix [E][2], 1-based,
+parents in column 0, tips are 1..N, the root is N+1.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Phylo:
+    """Read-only view of an edge matrix with O(1) parent/children lookups (all ids 1-based)."""
+
+    def __init__(self, edge, n_tips: int):
+        self.edge = np.ascontiguousarray(edge, dtype=np.int64)
+        self.n_tips = int(n_tips)
+        n_nodes = int(self.edge.max())
+        self.parent = np.zeros(n_nodes + 1, np.int64)
+        self.parent[self.edge[:, 1]] = self.edge[:, 0]
+        self.children = [[] for _ in range(n_nodes + 1)]
+        for p, c in self.edge:          # row order = child order (AddChild appends)
+            self.children[p].append(int(c))
+        self.root = self.n_tips + 1
+
+    def is_tip(self, v: int) -> bool:
+        return v <= self.n_tips
+
+    def descendants(self, v: int) -> np.ndarray:
+        """Tip ids under v (phangorn::Descendants(type='tips')), in traversal order."""
+        out, stack = [], [v]
+        while stack:
+            x = stack.pop()
+            if x <= self.n_tips:
+                out.append(x)
+            else:
+                stack.extend(reversed(self.children[x]))
+        return np.array(out, dtype=np.int64)
+
+    def subtree_sizes(self) -> np.ndarray:
+        """Number of tips under every node."""
+        size = np.zeros(len(self.parent), np.int64)
+        size[1:self.n_tips + 1] = 1
+        for v in self.postorder():
+            if v > self.n_tips:
+                size[v] = sum(size[c] for c in self.children[v])
+        return size
+
+    def postorder(self):
+        out, stack = [], [(self.root, False)]
+        while stack:
+            v, done = stack.pop()
+            if done or v <= self.n_tips:
+                out.append(v)
+            else:
+                stack.append((v, True))
+                for c in reversed(self.children[v]):
+                    stack.append((c, False))
+        return out
+
+    def depth(self) -> np.ndarray:
+        d = np.zeros(len(self.parent), np.int64)
+        for v in reversed(self.postorder()):
+            if v != self.root:
+                d[v] = d[self.parent[v]] + 1
+        return d
+
+    def mrca(self, tips) -> int:
+        """ape::getMRCA for a set of tip (or node) ids."""
+        tips = list(tips)
+        path = []
+        v = tips[0]
+        while v:
+            path.append(v)
+            v = int(self.parent[v])
+        pos = {v: i for i, v in enumerate(path)}
+        best = 0
+        for t in tips[1:]:
+            v = t
+            while v not in pos:
+                v = int(self.parent[v])
+            best = max(best, pos[v])
+        return path[best]
+
+
+def cluster_mrcas(phy: Phylo, clus_ind) -> list[int]:
+    """clusterNodeIndices as `.initCurrentValue` builds them (DMphyClusSource.R:78-88): for cluster
+    k = 1..max: the MRCA of its tips, or the tip id itself for a singleton.  With a single cluster the
+    reference stores `Ntip` (a tip id!), so the whole tree is evaluated with between-cluster matrices."""
+    clus_ind = np.asarray(clus_ind)
+    k_max = int(clus_ind.max())
+    if k_max == 1:
+        return [phy.n_tips]
+    out = []
+    for k in range(1, k_max + 1):
+        tips = np.nonzero(clus_ind == k)[0] + 1
+        out.append(int(tips[0]) if len(tips) == 1 else phy.mrca(tips))
+    return out
+
+
+def check_clades(phy: Phylo, clus_ind) -> bool:
+    """`.checkInput` / logLikFromClusInd's clade test (DMphyClusInterface.R:228-249)."""
+    clus_ind = np.asarray(clus_ind)
+    for k in np.unique(clus_ind):
+        tips = np.nonzero(clus_ind == k)[0] + 1
+        if len(tips) > 1 and set(phy.descendants(phy.mrca(tips))) != set(tips):
+            return False
+    return True
