@@ -1,0 +1,36 @@
+"""In-tree build of the CUDA engine: `dmphyclus_b200/libdmpc.so` (sm_100a only).
+
+    python -m dmphyclus_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the built .so travels to the GPU box with the repo snapshot."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("dmpc_engine.cu", "kernels.cuh", "host_tree.hpp")]
+HDR = os.path.join(ROOT, "include", "dmpc.h")
+LIB = os.path.join(HERE, "libdmpc.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    deps = SRC + [HDR]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

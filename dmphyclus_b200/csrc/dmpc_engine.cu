@@ -1,0 +1,681 @@
+// dmpc_engine.cu — C-ABI implementation (include/dmpc.h) of the B200-native likelihood engine.
+//
+// Each entry point mirrors one Rcpp-exported function of the reference
+// (/root/reference/src/clusterFunArmadillo.cpp:36-332): same call sequence
+// (NegateAllUpdateFlags -> mutate topology/flags -> ComputeLoglik), but the state lives in flat host arrays
+// (host_tree.hpp) plus dense HBM buffers, and ComputeLoglik is a level schedule of CUDA launches
+// (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
+#include "../../include/dmpc.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_tree.hpp"
+#include "kernels.cuh"
+
+using namespace dmpc;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(DMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+struct HostResult { double ll; int overflow; int badCells; };
+
+}  // namespace
+
+struct dmpc_tree {
+  HostTree ht;
+  int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nChunks = 0;
+  bool quirk = true, deferred = false, alive = true;
+  int device = 0, siteBegin = 0, sitesTotal = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  DevView dv{};
+  RootView rv{};
+  uint8_t* d_tipmask = nullptr;
+  double* d_lut = nullptr;
+  Task* d_tasks = nullptr;
+  Task* h_tasks = nullptr;       // pinned
+  int32_t* d_curList = nullptr;
+  int32_t* h_curList = nullptr;  // pinned
+  HostResult* h_res = nullptr;   // pinned
+  double hP[2][RMAX][16];
+  double hPi[4];
+  bool constantsValid = false;
+  std::vector<void*> allocs;
+  dmpc_stats st{};
+  std::vector<int> order, levelStart;
+  std::vector<int> lastTouched;  // internal indices the pending proposal flipped
+
+  template <class Tp>
+  int alloc(Tp** p, size_t n) {
+    void* q = nullptr;
+    CUDA_TRY(cudaMallocAsync(&q, n * sizeof(Tp), stream));
+    allocs.push_back(q);
+    st.device_bytes += n * sizeof(Tp);
+    *p = (Tp*)q;
+    return DMPC_OK;
+  }
+};
+
+namespace {
+
+int ensureDevice(dmpc_tree* t) {
+  CUDA_TRY(cudaSetDevice(t->device));
+  return DMPC_OK;
+}
+
+int allocSlot(dmpc_tree* t, int slot) {
+  if (t->dv.part[slot]) return DMPC_OK;
+  int rc;
+  const size_t n = (size_t)t->nInt * t->R * t->Sp;
+  if ((rc = t->alloc(&t->dv.part[slot], n * 4))) return rc;
+  if ((rc = t->alloc(&t->dv.expo[slot], n))) return rc;
+  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->R * t->T * t->nInt))) return rc;
+  return DMPC_OK;
+}
+
+int allocElist(dmpc_tree* t, int kcap) {
+  // the previous list (if any) stays in the pool until the handle dies; growth is rare and geometric
+  t->rv.Kcap = kcap;
+  t->rv.Q = std::max(512, kcap);
+  t->st.exponent_capacity = kcap;
+  return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
+}
+
+// matrices arrive column-major from R (P(i,j) at [i + 4j]); constants hold them row-major
+int uploadConstants(dmpc_tree* t, const double* within, const double* between, const double* pi) {
+  double P[2][RMAX][16];
+  std::memset(P, 0, sizeof P);
+  for (int r = 0; r < t->R; r++)
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        P[0][r][i * 4 + j] = between[16 * r + i + 4 * j];
+        P[1][r][i * 4 + j] = within[16 * r + i + 4 * j];
+      }
+  if (t->constantsValid && !std::memcmp(P, t->hP, sizeof P) && !std::memcmp(pi, t->hPi, sizeof t->hPi)) return DMPC_OK;
+  std::memcpy(t->hP, P, sizeof P);
+  std::memcpy(t->hPi, pi, sizeof t->hPi);
+  // tip lookup: P * indicator(mask), summed in gemv_emul_tinysq order (adding +0.0 terms is exact)
+  std::vector<double> lut((size_t)2 * t->R * 64);
+  for (int set = 0; set < 2; set++)
+    for (int r = 0; r < t->R; r++)
+      for (int m = 0; m < 16; m++)
+        for (int i = 0; i < 4; i++) {
+          const double* Pi = &P[set][r][i * 4];
+          const double x0 = m & 1 ? 1.0 : 0.0, x1 = m & 2 ? 1.0 : 0.0, x2 = m & 4 ? 1.0 : 0.0, x3 = m & 8 ? 1.0 : 0.0;
+          volatile double a = Pi[0] * x0, b = Pi[1] * x1, c = Pi[2] * x2, d = Pi[3] * x3;
+          volatile double s = a + b; s = s + c; s = s + d;
+          lut[((size_t)(set * t->R + r) * 16 + m) * 4 + i] = s;
+        }
+  // stream-ordered: kernels of earlier evaluations on this stream have been issued before these copies
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, P, sizeof P, 0, cudaMemcpyHostToDevice, t->stream));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_pi, pi, 4 * sizeof(double), 0, cudaMemcpyHostToDevice, t->stream));
+  CUDA_TRY(cudaMemcpyAsync(t->d_lut, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+  CUDA_TRY(cudaStreamSynchronize(t->stream));   // lut / P are stack/heap temporaries
+  t->constantsValid = true;
+  return DMPC_OK;
+}
+
+// constants are per-module: a second handle on the same device may have overwritten them
+std::mutex g_constMutex;
+dmpc_tree* g_constOwner[64] = {nullptr};
+
+int rootStage(dmpc_tree* t, double* ll);
+
+// ComputeLoglik (AugTree.cpp:289-326): prune the dirty levels, then reduce at the root.
+int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll) {
+  int rc;
+  if ((rc = ensureDevice(t))) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_constMutex);
+    if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
+  }
+  if ((rc = uploadConstants(t, within, between, pi))) return rc;
+  HostTree& ht = t->ht;
+  ht.schedule(t->order, t->levelStart);
+  const int nTasks = (int)t->order.size();
+  const int N = t->N;
+  for (int i = 0; i < nTasks; i++) {
+    const int v = t->order[i];
+    const int outSlot = ht.cur[v] ? 0 : 1;
+    if ((rc = allocSlot(t, outSlot))) return rc;
+    const int c0 = ht.kids[2 * v], c1 = ht.kids[2 * v + 1];
+    Task k;
+    k.out = v - N;
+    k.flags = outSlot ? TF_OUTSLOT : 0;
+    if (c0 < N) { k.c0 = c0; k.flags |= TF_C0TIP; } else { k.c0 = c0 - N; if (ht.cur[c0]) k.flags |= TF_C0SLOT; }
+    if (c1 < N) { k.c1 = c1; k.flags |= TF_C1TIP; } else { k.c1 = c1 - N; if (ht.cur[c1]) k.flags |= TF_C1SLOT; }
+    if (ht.within[c0]) k.flags |= TF_WITHIN;        // AugTree.cpp:125: the FIRST child's flag picks the matrix set
+    t->h_tasks[i] = k;
+    ht.cur[v] = (uint8_t)outSlot;                   // ComputeSolutions: _previousIterVec <- current (:28) ...
+    ht.touched[v] = 1;                              // ... _updateFlag = true (:34)
+    ht.solved[v] = 1;                               // ... _isSolved = true (:33)
+  }
+  CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
+  if (nTasks) {
+    CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, (size_t)nTasks * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
+    const int nLevels = (int)t->levelStart.size() - 1;
+    for (int l = 0; l < nLevels; l++) {
+      const int n = t->levelStart[l + 1] - t->levelStart[l];
+      const long long blocks = (long long)n * t->R * t->T;
+      if (blocks > 2147483647LL) return fail(DMPC_ERR_ARG, "level too wide for one launch");
+      k_prune_level<<<(unsigned)blocks, TILE, 0, t->stream>>>(t->dv, t->d_tasks + t->levelStart[l]);
+      t->st.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    t->st.last_levels = nLevels;
+    t->st.last_prune_launches = nLevels;
+  } else {
+    t->st.last_levels = 0;
+    t->st.last_prune_launches = 0;
+  }
+  CUDA_TRY(cudaEventRecord(t->ev[1], t->stream));
+  t->st.last_updates = (unsigned long long)nTasks * t->S * t->R;
+  t->st.updates += t->st.last_updates;
+  t->st.evaluations++;
+  return rootStage(t, ll);
+}
+
+int launchGather(dmpc_tree* t) {
+  k_root_gather<<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
+  t->st.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
+}
+
+size_t chainSmem(const dmpc_tree* t) { return (size_t)64 * t->rv.Q * (t->rv.RP / 4) + 8 * ((size_t)t->rv.Q + 1); }
+
+int launchChain(dmpc_tree* t) {
+  const size_t smem = chainSmem(t);
+  if (smem > 220 * 1024) return fail(DMPC_ERR_ARG, "rescale list too deep for the chain kernel's staging buffers");
+  if (t->rv.RP == 4) {
+    CUDA_TRY(cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain<4><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_chain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain<8><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  }
+  t->st.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
+}
+
+int launchFinal(dmpc_tree* t, int mode, int reduceAll) {
+  k_final<<<t->nChunks, CHUNK, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll);
+  t->st.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
+}
+
+int gatherWithGrowth(dmpc_tree* t) {
+  for (int attempt = 0; attempt < 8; attempt++) {
+    int rc;
+    if ((rc = launchGather(t))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    if (t->h_res->overflow <= t->rv.Kcap) return DMPC_OK;
+    int k = t->rv.Kcap;
+    while (k < t->h_res->overflow) k *= 2;
+    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, sizeof(int), t->stream));
+    if ((rc = allocElist(t, k))) return rc;
+  }
+  return fail(DMPC_ERR_CUDA, "rescale list kept overflowing");
+}
+
+int rootStage(dmpc_tree* t, double* ll) {
+  int rc;
+  const bool chain = t->quirk && t->R > 1;
+  if (t->deferred) {
+    if ((rc = gatherWithGrowth(t))) return rc;
+    *ll = NAN;
+    return DMPC_OK;
+  }
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if ((rc = launchGather(t))) return rc;
+    if (chain && (rc = launchChain(t))) return rc;
+    if ((rc = launchFinal(t, chain ? 1 : 0, 1))) return rc;
+    CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->ll, t->rv.result, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    if (t->h_res->overflow <= t->rv.Kcap) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+      cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
+      *ll = t->h_res->ll;
+      return DMPC_OK;
+    }
+    int k = t->rv.Kcap;
+    while (k < t->h_res->overflow) k *= 2;
+    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, sizeof(int), t->stream));
+    if ((rc = allocElist(t, k))) return rc;
+  }
+  return fail(DMPC_ERR_CUDA, "rescale list kept overflowing");
+}
+
+void destroy(dmpc_tree* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  if (t->stream) cudaStreamSynchronize(t->stream);
+  for (void* p : t->allocs) cudaFreeAsync(p, t->stream);
+  if (t->stream) cudaStreamSynchronize(t->stream);
+  if (t->h_tasks) cudaFreeHost(t->h_tasks);
+  if (t->h_curList) cudaFreeHost(t->h_curList);
+  if (t->h_res) cudaFreeHost(t->h_res);
+  for (auto& e : t->ev) if (e) cudaEventDestroy(e);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_constMutex);
+    if (g_constOwner[t->device & 63] == t) g_constOwner[t->device & 63] = nullptr;
+  }
+  delete t;
+}
+
+int checkHandle(dmpc_tree* t) {
+  if (!t) return fail(DMPC_ERR_ARG, "pointer is null.");   // clusterFunArmadillo.cpp:136
+  if (!t->alive) return fail(DMPC_ERR_STATE, "tree handle used after dmpc_final_deallocate");
+  return DMPC_OK;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+void dmpc_default_options(dmpc_options* o) {
+  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0;
+}
+
+const char* dmpc_last_error(void) { return g_err.c_str(); }
+const char* dmpc_version(void) { return "dmphyclus_b200 0.1 (sm_100a)"; }
+
+long dmpc_convert_alignment(const char* chars, long nCells, const char* states, uint8_t* maskOut) {
+  if (!chars || !states || !maskOut) { g_err = "null pointer"; return -1; }
+  uint8_t map[256];
+  std::memset(map, 0, sizeof map);
+  for (int j = 0; j < 4; j++) map[(unsigned char)states[j]] = (uint8_t)(1u << j);
+  // IUPAC unions are keyed on the literal labels a,t,c,g (clusterFunArmadillo.cpp:75-91)
+  const uint8_t a = map['a'], tt = map['t'], c = map['c'], g = map['g'];
+  map['r'] = a | g; map['y'] = c | tt; map['s'] = c | g; map['w'] = a | tt; map['k'] = g | tt; map['m'] = a | c;
+  map['b'] = c | g | tt; map['d'] = a | g | tt; map['h'] = a | c | tt; map['v'] = a | c | g;
+  map['-'] = map['n'] = map['.'] = a | tt | c | g;
+  long bad = 0;
+  for (long i = 0; i < nCells; i++) { const uint8_t m = map[(unsigned char)chars[i]]; maskOut[i] = m; bad += m == 0; }
+  return bad;
+}
+
+int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
+                       const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
+                       int numRateCats, const uint8_t* alignmentBin, int numTips, int numLoci,
+                       int withinMatListIndex, int betweenMatListIndex, const dmpc_options* opts,
+                       dmpc_tree** treeOut, double* logLikOut) {
+  if (!edge || !limProbs || !withinTransMats || !betweenTransMats || !alignmentBin || !treeOut || !logLikOut ||
+      (nClusterMRCAs > 0 && !clusterMRCAs))
+    return fail(DMPC_ERR_ARG, "null pointer");
+  if (numRateCats < 1 || numRateCats > RMAX) return fail(DMPC_ERR_ARG, "numRateCats must be in 1..8");
+  if (numTips < 2 || numLoci < 1) return fail(DMPC_ERR_ARG, "need at least 2 tips and 1 locus");
+  dmpc_options o;
+  dmpc_default_options(&o);
+  if (opts) o = *opts;
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return fail(DMPC_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+  dmpc_tree* t = new dmpc_tree;
+  if (o.device < 0) { if (cudaGetDevice(&t->device) != cudaSuccess) t->device = 0; } else t->device = o.device;
+  if (!t->ht.build(edge, nEdgeRows, numTips)) { std::string e = t->ht.err; delete t; return fail(DMPC_ERR_ARG, e); }
+  t->ht.associate(clusterMRCAs, nClusterMRCAs);
+  t->ht.withinIdx = withinMatListIndex; t->ht.betweenIdx = betweenMatListIndex;
+  t->N = numTips; t->S = numLoci; t->R = numRateCats; t->nInt = numTips - 1;
+  t->Sp = (numLoci + TILE - 1) / TILE * TILE;
+  t->T = t->Sp / TILE;
+  t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
+  t->quirk = o.quirk_carry != 0;
+  t->siteBegin = o.site_begin; t->sitesTotal = o.sites_total ? o.sites_total : numLoci;
+  t->rv.RP = numRateCats <= 4 ? 4 : 8;
+
+  int rc = DMPC_OK;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaSetDevice(t->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, t->device));
+    if (prop.major < 10) return fail(DMPC_ERR_CUDA, "device is not sm_100-class; kernels are built for sm_100a only");
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, t->device));
+    unsigned long long keep = ~0ULL;                      // keep freed HBM cached in the pool between handles
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    for (auto& e : t->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaHostAlloc((void**)&t->h_tasks, (size_t)t->nInt * sizeof(Task), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&t->h_curList, (size_t)t->nInt * sizeof(int32_t), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&t->h_res, sizeof(HostResult), cudaHostAllocDefault));
+    int r2;
+    if ((r2 = t->alloc(&t->d_tipmask, (size_t)t->N * t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->d_lut, (size_t)2 * t->R * 64))) return r2;
+    if ((r2 = t->alloc(&t->d_tasks, (size_t)t->nInt))) return r2;
+    if ((r2 = t->alloc(&t->d_curList, (size_t)t->nInt))) return r2;
+    if ((r2 = t->alloc(&t->dv.cur, (size_t)t->nInt))) return r2;
+    if ((r2 = t->alloc(&t->rv.kmax, (size_t)t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.rootdot, (size_t)t->R * t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.act, (size_t)t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.rowoff, (size_t)t->Sp + 1))) return r2;
+    if ((r2 = t->alloc(&t->rv.posIncl, (size_t)t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.chunkStart, (size_t)t->Sp + 2))) return r2;
+    if ((r2 = t->alloc(&t->rv.cout, (size_t)t->Sp * t->rv.RP))) return r2;
+    if ((r2 = t->alloc(&t->rv.mxo, (size_t)t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.carryIn, (size_t)RMAX))) return r2;
+    if ((r2 = t->alloc(&t->rv.carryOut, (size_t)RMAX))) return r2;
+    if ((r2 = t->alloc(&t->rv.sitell, (size_t)t->Sp))) return r2;
+    if ((r2 = t->alloc(&t->rv.chunk, (size_t)t->nChunks))) return r2;
+    if ((r2 = t->alloc(&t->rv.ticket, (size_t)1))) return r2;
+    if ((r2 = t->alloc(&t->rv.overflow, (size_t)2))) return r2;
+    if ((r2 = t->alloc(&t->rv.result, (size_t)1))) return r2;
+    if ((r2 = allocElist(t, 8))) return r2;
+    CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->rv.ticket, 0, sizeof(unsigned), t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, 2 * sizeof(int), t->stream));
+    t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
+    t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt;
+    // alignment: [N][S] host rows -> [N][Sp] device rows; pad sites get the all-ones mask
+    CUDA_TRY(cudaMemcpy2DAsync(t->d_tipmask, t->Sp, alignmentBin, t->S, t->S, t->N, cudaMemcpyHostToDevice, t->stream));
+    {
+      const size_t n = (size_t)t->N * t->Sp;
+      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->d_tipmask, t->N, t->S, t->Sp, t->rv.overflow + 1);
+      t->st.kernel_launches++;
+      CUDA_TRY(cudaMemcpyAsync(&t->h_res->badCells, t->rv.overflow + 1, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+      CUDA_TRY(cudaStreamSynchronize(t->stream));
+      if (t->h_res->badCells)
+        return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
+                                      " alignment cells hold no state (unknown symbol; clusterFunArmadillo.cpp:109)");
+    }
+    return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+  };
+  rc = body();
+  if (rc != DMPC_OK) { std::string keepMsg = g_err; destroy(t); g_err = keepMsg; return rc; }
+  t->ht.negateAllUpdateFlags();   // nothing to roll back to before the first proposal
+  *treeOut = t;
+  return DMPC_OK;
+}
+
+int dmpc_new_between_transprobs_loglik(dmpc_tree* t, const double* withinTransMats, const double* newBetweenTransMats,
+                                       int newBetweenMatListIndex, const double* limProbs, double* logLikOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!withinTransMats || !newBetweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  t->ht.negateAllUpdateFlags();
+  t->ht.betweenIdx = newBetweenMatListIndex;
+  t->ht.invalidateBetween();
+  return evaluate(t, withinTransMats, newBetweenTransMats, limProbs, logLikOut);
+}
+
+int dmpc_new_within_transprobs_loglik(dmpc_tree* t, const double* newWithinTransMats, const double* betweenTransMats,
+                                      int newWithinMatListIndex, const double* limProbs, double* logLikOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!newWithinTransMats || !betweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  t->ht.negateAllUpdateFlags();
+  t->ht.withinIdx = newWithinMatListIndex;
+  t->ht.invalidateAll();
+  return evaluate(t, newWithinTransMats, betweenTransMats, limProbs, logLikOut);
+}
+
+static int nniCommon(dmpc_tree* t, const double* w, const double* b, int origin, const std::vector<long>* mrcas,
+                     int numMoves, const double* pi, double* ll, int32_t* edgeOut) {
+  t->ht.negateAllUpdateFlags();
+  std::vector<int> cand;
+  t->ht.nniCandidates(origin, mrcas, cand);
+  if (cand.empty())
+    return fail(DMPC_ERR_NO_MOVE, "no vertex admits a nearest-neighbour interchange here (the reference calls "
+                                  "gsl_rng_uniform_int(r, 0), clusterFunArmadillo.cpp:187)");
+  for (int m = 0; m < numMoves; m++) {
+    const int root = cand[t->ht.rng.uniform_int(cand.size())];
+    int two[2];
+    t->ht.twoVerticesForNNI(root, mrcas, two);
+    t->ht.rearrangeNNI(two[0], two[1]);
+  }
+  int rc = evaluate(t, w, b, pi, ll);
+  if (rc == DMPC_OK) t->ht.exportEdges(edgeOut);
+  return rc;
+}
+
+int dmpc_within_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                int mrcaOfClusForNNI, int numMovesNNI, const double* limProbs, double* logLikOut,
+                                int32_t* edgeOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !edgeOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (mrcaOfClusForNNI < 1 || mrcaOfClusForNNI > t->ht.numVerts) return fail(DMPC_ERR_ARG, "MRCAofClusForNNI out of range");
+  return nniCommon(t, withinTransMats, betweenTransMats, mrcaOfClusForNNI - 1, nullptr, numMovesNNI, limProbs, logLikOut, edgeOut);
+}
+
+int dmpc_between_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                 const double* clusterMRCAs, int nClusterMRCAs, int numMovesNNI,
+                                 const double* limProbs, double* logLikOut, int32_t* edgeOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !edgeOut || (nClusterMRCAs > 0 && !clusterMRCAs))
+    return fail(DMPC_ERR_ARG, "null pointer");
+  std::vector<long> m(nClusterMRCAs);
+  for (int i = 0; i < nClusterMRCAs; i++) m[i] = (long)clusterMRCAs[i];
+  return nniCommon(t, withinTransMats, betweenTransMats, t->ht.root(), &m, numMovesNNI, limProbs, logLikOut, edgeOut);
+}
+
+int dmpc_clus_split_merge_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                 const int32_t* mrcas, int n, const double* limProbs, double* logLikOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !mrcas || n < 1) return fail(DMPC_ERR_ARG, "null pointer");
+  HostTree& ht = t->ht;
+  for (int i = 0; i < n; i++)
+    if (mrcas[i] < 1 || mrcas[i] > ht.numVerts) return fail(DMPC_ERR_ARG, "cluster MRCA out of range");
+  if (n == 1 && mrcas[0] <= ht.numTips)
+    return fail(DMPC_ERR_ARG, "cannot split a tip (the reference dereferences a null child, AugTree.cpp:332)");
+  if (n > 1 && ht.parent[mrcas[0] - 1] < 0) return fail(DMPC_ERR_ARG, "cannot merge the root");
+  ht.negateAllUpdateFlags();
+  if (n == 1) {                                   // HandleSplit, AugTree.cpp:328-336
+    const int m = mrcas[0] - 1;
+    ht.invalidateSolution(m);
+    ht.within[ht.kids[2 * m]] = 0; ht.within[ht.kids[2 * m + 1]] = 0;
+  } else {                                        // HandleMerge, AugTree.cpp:338-346
+    ht.invalidateSolution(ht.parent[mrcas[0] - 1]);
+    for (int i = 0; i < n; i++) ht.within[mrcas[i] - 1] = 1;
+  }
+  return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+}
+
+int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRows, int withinMatListIndex,
+                                 int betweenMatListIndex, int nniMove, const int32_t* clusterMRCAs,
+                                 int nClusterMRCAs, int splitMergeMove) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  HostTree& ht = t->ht;
+  ht.withinIdx = withinMatListIndex; ht.betweenIdx = betweenMatListIndex;
+  if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
+    if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
+    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
+  }
+  int n = 0;                                      // RestoreIterVecAndExp, IntermediateNode.h:26-33
+  for (int v = ht.numTips; v < ht.numVerts; v++)
+    if (ht.touched[v]) {
+      ht.cur[v] ^= 1;
+      ht.touched[v] = 0;
+      t->h_curList[n++] = ((v - ht.numTips) << 1) | ht.cur[v];
+    }
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(t->d_curList, t->h_curList, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+    k_set_cur<<<(n + 255) / 256, 256, 0, t->stream>>>(t->dv.cur, t->d_curList, n);
+    t->st.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(t->stream));   // h_curList is reused by the next rollback
+  }
+  if (splitMergeMove) {
+    if (nClusterMRCAs > 0 && !clusterMRCAs) return fail(DMPC_ERR_ARG, "null pointer");
+    ht.associate(clusterMRCAs, nClusterMRCAs);
+  }
+  return DMPC_OK;
+}
+
+int dmpc_final_deallocate(dmpc_tree* t) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  destroy(t);
+  return DMPC_OK;
+}
+
+double dmpc_get_max_map_size_estimate(double allowedSizeInMegs, unsigned numRateCats) {
+  // sizeof(S) = 32 and sizeof(mapContentType) = 24 on LP64/libstdc++ (clusterFunArmadillo.cpp:300)
+  return std::floor((allowedSizeInMegs * 1e6) / (32.0 + 24.0 * numRateCats + 16.0));
+}
+
+int dmpc_check_and_cull_map(dmpc_tree* t, unsigned, float, const double*, const double*, const double*) {
+  return checkHandle(t);   // dense HBM storage: nothing to cull, results never depend on culling
+}
+
+int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                       const double* limProbs, double* logLikOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  t->ht.negateAllUpdateFlags();
+  t->ht.invalidateAll();
+  return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+}
+
+int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!out) return fail(DMPC_ERR_ARG, "null pointer");
+  *out = t->st;
+  return DMPC_OK;
+}
+
+int dmpc_timer_begin(dmpc_tree* t) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  CUDA_TRY(cudaEventRecord(t->ev[3], t->stream));
+  return DMPC_OK;
+}
+
+int dmpc_timer_end(dmpc_tree* t, double* msOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  if (!msOut) return fail(DMPC_ERR_ARG, "null pointer");
+  CUDA_TRY(cudaEventRecord(t->ev[4], t->stream));
+  CUDA_TRY(cudaEventSynchronize(t->ev[4]));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, t->ev[3], t->ev[4]));
+  *msOut = ms;
+  return DMPC_OK;
+}
+
+int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  if (vertex < t->N || vertex >= t->ht.numVerts || !sol || !expo) return fail(DMPC_ERR_ARG, "vertex must be internal");
+  const int slot = t->ht.cur[vertex], idx = vertex - t->N;
+  const size_t n = (size_t)t->R * t->Sp;
+  std::vector<double> hs(n * 4);
+  std::vector<float> he(n);
+  std::vector<uint8_t> hf((size_t)t->R * t->T);
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[slot] + (size_t)idx * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(he.data(), t->dv.expo[slot] + (size_t)idx * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < t->R * t->T; b++)
+    CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nInt + idx, 1, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < t->S; s++)
+    for (int r = 0; r < t->R; r++) {
+      for (int k = 0; k < 4; k++) sol[((size_t)s * t->R + r) * 4 + k] = hs[((size_t)r * t->Sp + s) * 4 + k];
+      expo[(size_t)s * t->R + r] = hf[r * t->T + s / TILE] ? he[(size_t)r * t->Sp + s] : 0.0f;
+    }
+  return DMPC_OK;
+}
+
+int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* child1, int32_t* within) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  for (int v = 0; v < t->ht.numVerts; v++) {
+    parent[v] = t->ht.parent[v];
+    child0[v] = t->ht.kids[2 * v]; child1[v] = t->ht.kids[2 * v + 1];
+    within[v] = t->ht.within[v];
+  }
+  return DMPC_OK;
+}
+
+int dmpc_get_site_logliks(dmpc_tree* t, double* out) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  CUDA_TRY(cudaMemcpy(out, t->rv.sitell, (size_t)t->S * sizeof(double), cudaMemcpyDeviceToHost));
+  return DMPC_OK;
+}
+
+int dmpc_set_deferred(dmpc_tree* t, int on) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  t->deferred = on != 0;
+  return DMPC_OK;
+}
+
+int dmpc_shard_chain(dmpc_tree* t, const float* carryIn, float* carryOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  if (!carryIn || !carryOut) return fail(DMPC_ERR_ARG, "null pointer");
+  const bool chain = t->quirk && t->R > 1;
+  if (!chain) { for (int r = 0; r < t->R; r++) carryOut[r] = 0.0f; return DMPC_OK; }
+  float in[RMAX] = {0};
+  for (int r = 0; r < t->R; r++) in[r] = carryIn[r];
+  CUDA_TRY(cudaMemcpyAsync(t->rv.carryIn, in, sizeof in, cudaMemcpyHostToDevice, t->stream));
+  if ((rc = launchChain(t))) return rc;
+  float out[RMAX];
+  CUDA_TRY(cudaMemcpyAsync(out, t->rv.carryOut, sizeof out, cudaMemcpyDeviceToHost, t->stream));
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  for (int r = 0; r < t->R; r++) carryOut[r] = out[r];
+  return DMPC_OK;
+}
+
+int dmpc_shard_num_chunks(dmpc_tree* t) { return checkHandle(t) ? -1 : t->nChunks; }
+
+int dmpc_shard_finish(dmpc_tree* t, double* chunkSums) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  if (!chunkSums) return fail(DMPC_ERR_ARG, "null pointer");
+  const bool chain = t->quirk && t->R > 1;
+  if ((rc = launchFinal(t, chain ? 1 : 0, 0))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(chunkSums, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  return DMPC_OK;
+}
+
+double dmpc_reduce_chunks(const double* chunkSums, int n) {
+  volatile double acc[CHUNK];
+  for (int tI = 0; tI < CHUNK; tI++) {
+    double a = 0.0;
+    for (int c = tI; c < n; c += CHUNK) { volatile double x = a + chunkSums[c]; a = x; }
+    acc[tI] = a;
+  }
+  for (int d = CHUNK / 2; d > 0; d >>= 1)
+    for (int tI = 0; tI < d; tI++) acc[tI] = acc[tI] + acc[tI + d];
+  return acc[0];
+}
+
+}  // extern "C"

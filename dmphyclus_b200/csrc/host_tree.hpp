@@ -1,0 +1,232 @@
+// host_tree.hpp — host-side topology and proposal state machine of the likelihood engine.
+//
+// The reference keeps a pointer graph of TreeNode objects (src/TreeNode.h:80-125,
+// src/IntermediateNode.h:6-53) and walks it recursively.  Here the same state is a handful of flat
+// arrays indexed by vertex id (tips 0..N-1, internal N..2N-2, root = N — AugTree.cpp:59-86), and what
+// the reference expresses as "unsolved nodes reached from the root" (AugTree::TrySolve,
+// AugTree.cpp:114-134) becomes a LEVEL SCHEDULE: the dirty nodes bucketed by height above the clean
+// frontier, one batched kernel launch per bucket.  No arithmetic happens here.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace dmpc {
+
+// GSL's gsl_rng_taus (rng/taus.c) with gsl_rng_alloc's default seed and gsl_rng_uniform_int's rejection
+// loop (rng/rng.c): the reference draws its NNI picks from this stream and never seeds it
+// (clusterFunArmadillo.cpp:51,187,227; AugTree.cpp:266), so reproducing it is part of trajectory parity.
+struct TausRng {
+  uint32_t s1 = 0, s2 = 0, s3 = 0;
+  static uint32_t step(uint32_t s, int a, int b, uint32_t c, int d) { return ((s & c) << d) ^ (((s << a) ^ s) >> b); }
+  uint32_t next() {
+    s1 = step(s1, 13, 19, 4294967294u, 12);
+    s2 = step(s2, 2, 25, 4294967288u, 4);
+    s3 = step(s3, 3, 11, 4294967280u, 17);
+    return s1 ^ s2 ^ s3;
+  }
+  void seed(unsigned long s) {
+    if (s == 0) s = 1;
+    s1 = 69069u * (uint32_t)s;
+    s2 = 69069u * s1;
+    s3 = 69069u * s2;
+    for (int i = 0; i < 6; i++) next();
+  }
+  unsigned long uniform_int(unsigned long n) {   // caller guarantees n > 0
+    const unsigned long scale = 0xffffffffUL / n;
+    unsigned long k;
+    do { k = next() / scale; } while (k >= n);
+    return k;
+  }
+};
+
+struct HostTree {
+  int numTips = 0, numVerts = 0;
+  std::vector<int32_t> parent;           // -1 for the root
+  std::vector<int32_t> kids;             // [2*v + i]: ordered children (-1 = absent); order = the reference's _children
+  std::vector<uint8_t> nkids;
+  std::vector<uint8_t> within;           // _withinParentBranch
+  std::vector<uint8_t> solved;           // _isSolved (tips: always 1)
+  std::vector<uint8_t> touched;          // _updateFlag
+  std::vector<uint8_t> cur;              // which of the two HBM slots holds the vertex's current partial
+  int withinIdx = 0, betweenIdx = 0;
+  TausRng rng;
+  std::string err;
+
+  bool isTip(int v) const { return v < numTips; }
+  int internalIndex(int v) const { return v - numTips; }
+  int root() const { return numTips; }
+
+  void addChild(int p, int c) {          // IntermediateNode::AddChild: push_back
+    if (nkids[p] < 2) kids[2 * p + nkids[p]] = c;
+    nkids[p]++;
+  }
+  void removeChild(int p, int c) {       // IntermediateNode::RemoveChild (IntermediateNode.cpp:73-84): erase first match
+    for (int i = 0; i < std::min<int>(nkids[p], 2); i++)
+      if (kids[2 * p + i] == c) {
+        if (i == 0) kids[2 * p] = kids[2 * p + 1];
+        kids[2 * p + 1] = -1;
+        nkids[p]--;
+        return;
+      }
+  }
+
+  // AugTree::BuildTree / BuildTreeNoAssign (AugTree.cpp:59-101): edge is column-major, 1-based.
+  bool link(const int32_t* edge, int nEdgeRows) {
+    std::fill(kids.begin(), kids.end(), -1);
+    std::fill(nkids.begin(), nkids.end(), 0);
+    for (int k = 0; k < nEdgeRows; k++) {
+      int p = edge[k] - 1, c = edge[k + nEdgeRows] - 1;
+      if (p < numTips || p >= numVerts || c < 0 || c >= numVerts || c == p) { err = "edge matrix entry out of range"; return false; }
+      addChild(p, c);
+      parent[c] = p;
+    }
+    for (int v = numTips; v < numVerts; v++)
+      if (nkids[v] != 2) { err = "the tree is not strictly bifurcating (IntermediateNode.cpp:59)"; return false; }
+    return true;
+  }
+
+  bool build(const int32_t* edge, int nEdgeRows, int nTips) {
+    numTips = nTips;
+    numVerts = nEdgeRows + 1;
+    if (numVerts != 2 * numTips - 1) { err = "edge matrix must have 2*numTips-2 rows"; return false; }
+    parent.assign(numVerts, -1);
+    kids.assign(2 * (size_t)numVerts, -1);
+    nkids.assign(numVerts, 0);
+    within.assign(numVerts, 0);
+    solved.assign(numVerts, 0);
+    touched.assign(numVerts, 0);
+    cur.assign(numVerts, 1);             // first evaluation writes slot 0
+    for (int v = 0; v < numTips; v++) solved[v] = 1;
+    rng.seed(0);
+    if (!link(edge, nEdgeRows)) return false;
+    if (parent[root()] != -1) { err = "vertex numTips+1 must be the root"; return false; }
+    // every vertex must hang below the root
+    std::vector<int> stack(1, root());
+    int seen = 0;
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back(); seen++;
+      if (!isTip(v)) { stack.push_back(kids[2 * v]); stack.push_back(kids[2 * v + 1]); }
+    }
+    if (seen != numVerts) { err = "edge matrix is not a single rooted tree"; return false; }
+    return true;
+  }
+
+  // AugTree::AssociateTransProbMatrices + BindMatrix (AugTree.cpp:30-57)
+  template <class T>
+  void associate(const T* mrcas, int n) {
+    std::fill(within.begin(), within.end(), 0);
+    std::vector<int> stack;
+    for (int i = 0; i < n; i++) {
+      long m = (long)mrcas[i];
+      if (m > numTips && m <= numVerts) {
+        stack.push_back(kids[2 * (m - 1)]); stack.push_back(kids[2 * (m - 1) + 1]);
+        while (!stack.empty()) {
+          int v = stack.back(); stack.pop_back();
+          within[v] = 1;
+          if (!isTip(v)) { stack.push_back(kids[2 * v]); stack.push_back(kids[2 * v + 1]); }
+        }
+      }
+    }
+  }
+
+  void negateAllUpdateFlags() { std::fill(touched.begin(), touched.end(), 0); }          // AugTree.cpp:368-374
+  void invalidateSolution(int v) { for (; v != -1; v = parent[v]) solved[v] = 0; }        // IntermediateNode.cpp:5-13
+  void invalidateAll() { for (int v = numTips; v < numVerts; v++) solved[v] = 0; }        // AugTree.cpp:136-142
+  void invalidateBetween() {                                                              // AugTree.cpp:273-287
+    std::vector<int> stack(1, root());
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      if (isTip(v) || within[kids[2 * v]]) continue;
+      solved[v] = 0;
+      stack.push_back(kids[2 * v]); stack.push_back(kids[2 * v + 1]);
+    }
+  }
+
+  bool inList(const std::vector<long>& l, long id1) const { return std::find(l.begin(), l.end(), id1) != l.end(); }
+
+  // GetNNIverticesWithin / Between (AugTree.cpp:144-209): pre-order list of vertices that have at least one
+  // internal child (which, for the between variant, is not a cluster MRCA; the walk stops at cluster MRCAs).
+  void nniCandidates(int origin, const std::vector<long>* mrcas, std::vector<int>& out) const {
+    std::vector<int> stack(1, origin);
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      if (isTip(v) || (mrcas && inList(*mrcas, v + 1))) continue;
+      bool possible = false;
+      for (int i = 0; i < 2 && !possible; i++) {
+        int c = kids[2 * v + i];
+        possible = !isTip(c) && !(mrcas && inList(*mrcas, c + 1));
+      }
+      if (possible) {
+        out.push_back(v);
+        stack.push_back(kids[2 * v + 1]);   // pushed second-first so that child 0's subtree is listed first
+        stack.push_back(kids[2 * v]);
+      }
+    }
+  }
+
+  // GetTwoVerticesForNNI (AugTree.cpp:253-271)
+  void twoVerticesForNNI(int subtreeRoot, const std::vector<long>* mrcas, int out[2]) {
+    for (int i = 0; i < 2; i++) {
+      int c = kids[2 * subtreeRoot + i];
+      if (isTip(c) || (mrcas && inList(*mrcas, c + 1))) out[i] = c;
+      else out[i] = kids[2 * c + (int)rng.uniform_int(2)];
+    }
+  }
+
+  // RearrangeTreeNNI (AugTree.cpp:211-226)
+  void rearrangeNNI(int a, int b) {
+    removeChild(parent[a], a); addChild(parent[a], b);
+    removeChild(parent[b], b); addChild(parent[b], a);
+    std::swap(parent[a], parent[b]);
+    invalidateSolution(parent[a]);
+    invalidateSolution(parent[b]);
+  }
+
+  // BuildEdgeMatrix (AugTree.cpp:228-251): pre-order, column-major, 1-based
+  void exportEdges(int32_t* out) const {
+    const int nRows = numVerts - 1;
+    int line = 0;
+    std::vector<int> stack(1, root());
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      if (parent[v] != -1) { out[line] = parent[v] + 1; out[line + nRows] = v + 1; line++; }
+      if (!isTip(v)) { stack.push_back(kids[2 * v + 1]); stack.push_back(kids[2 * v]); }
+    }
+  }
+
+  // The dirty set of the pending evaluation as a level schedule.  Mirrors TrySolve: only unsolved vertices
+  // reachable from the root through unsolved vertices are recomputed.  order[] lists them level by level
+  // (children strictly before parents), levelStart[] delimits the levels.
+  void schedule(std::vector<int>& order, std::vector<int>& levelStart) const {
+    order.clear(); levelStart.clear();
+    if (solved[root()]) { levelStart.push_back(0); return; }
+    std::vector<int> pre;
+    std::vector<int> stack(1, root());
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      pre.push_back(v);
+      for (int i = 0; i < 2; i++) { int c = kids[2 * v + i]; if (!isTip(c) && !solved[c]) stack.push_back(c); }
+    }
+    std::vector<int> level(numVerts, 0);   // height above the clean frontier; clean vertices and tips = 0
+    int maxLevel = 0;
+    for (size_t i = pre.size(); i-- > 0;) {   // reverse pre-order visits children before parents
+      int v = pre[i];
+      int l = 1 + std::max(level[kids[2 * v]], level[kids[2 * v + 1]]);
+      level[v] = l;
+      maxLevel = std::max(maxLevel, l);
+    }
+    std::vector<int> cnt(maxLevel + 1, 0);
+    for (int v : pre) cnt[level[v]]++;
+    levelStart.assign(maxLevel + 1, 0);   // level l (1-based) = order[levelStart[l-1] .. levelStart[l])
+    int acc = 0;
+    for (int l = 1; l <= maxLevel; l++) { levelStart[l - 1] = acc; acc += cnt[l]; }
+    levelStart[maxLevel] = acc;
+    std::vector<int> fill(levelStart.begin(), levelStart.end());
+    order.resize(pre.size());
+    for (int v : pre) order[fill[level[v] - 1]++] = v;
+  }
+};
+
+}  // namespace dmpc

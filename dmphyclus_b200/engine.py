@@ -1,0 +1,278 @@
+"""Host binding of the CUDA engine (`libdmpc.so`, C-ABI in `include/dmpc.h`) under the reference's own
+entry-point names (`/root/reference/R/RcppExports.R:4-46`, `src/clusterFunArmadillo.cpp:36-332`).
+
+This is the product path: it loads the hand-written sm_100a library and nothing else — no oracle, no CPU
+fallback.  A missing library or a machine without a B200-class GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdmpc.so")
+_dbl_p = C.POINTER(C.c_double)
+_i32_p = C.POINTER(C.c_int32)
+_u8_p = C.POINTER(C.c_uint8)
+_f32_p = C.POINTER(C.c_float)
+
+
+class DmpcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdmpc status {code}: {msg}")
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("updates", C.c_ulonglong), ("kernel_launches", C.c_ulonglong), ("evaluations", C.c_ulonglong),
+                ("last_eval_ms", C.c_double), ("last_prune_ms", C.c_double), ("last_updates", C.c_ulonglong),
+                ("last_prune_launches", C.c_ulonglong), ("last_levels", C.c_int), ("exponent_capacity", C.c_int),
+                ("device_bytes", C.c_ulonglong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/dmpc.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+ABI = {
+    "dmpc_default_options": (None, [C.POINTER(Options)]),
+    "dmpc_last_error": (C.c_char_p, []),
+    "dmpc_version": (C.c_char_p, []),
+    "dmpc_convert_alignment": (C.c_long, [C.c_char_p, C.c_long, C.c_char_p, _u8_p]),
+    "dmpc_loglik_create": (C.c_int, [_i32_p, C.c_int, _dbl_p, C.c_int, _dbl_p, _dbl_p, _dbl_p, C.c_int, _u8_p, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(_P), _dbl_p]),
+    "dmpc_new_between_transprobs_loglik": (C.c_int, [_P, _dbl_p, _dbl_p, C.c_int, _dbl_p, _dbl_p]),
+    "dmpc_new_within_transprobs_loglik": (C.c_int, [_P, _dbl_p, _dbl_p, C.c_int, _dbl_p, _dbl_p]),
+    "dmpc_within_clus_nni_loglik": (C.c_int, [_P, _dbl_p, _dbl_p, C.c_int, C.c_int, _dbl_p, _dbl_p, _i32_p]),
+    "dmpc_between_clus_nni_loglik": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, C.c_int, C.c_int, _dbl_p, _dbl_p, _i32_p]),
+    "dmpc_clus_split_merge_loglik": (C.c_int, [_P, _dbl_p, _dbl_p, _i32_p, C.c_int, _dbl_p, _dbl_p]),
+    "dmpc_restore_previous_config": (C.c_int, [_P, _i32_p, C.c_int, C.c_int, C.c_int, C.c_int, _i32_p, C.c_int, C.c_int]),
+    "dmpc_final_deallocate": (C.c_int, [_P]),
+    "dmpc_get_max_map_size_estimate": (C.c_double, [C.c_double, C.c_uint]),
+    "dmpc_check_and_cull_map": (C.c_int, [_P, C.c_uint, C.c_float, _dbl_p, _dbl_p, _dbl_p]),
+    "dmpc_recompute_all": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, _dbl_p]),
+    "dmpc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "dmpc_timer_begin": (C.c_int, [_P]),
+    "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
+    "dmpc_get_partial": (C.c_int, [_P, C.c_int, _dbl_p, _f32_p]),
+    "dmpc_get_topology": (C.c_int, [_P, _i32_p, _i32_p, _i32_p, _i32_p]),
+    "dmpc_get_site_logliks": (C.c_int, [_P, _dbl_p]),
+    "dmpc_set_deferred": (C.c_int, [_P, C.c_int]),
+    "dmpc_shard_chain": (C.c_int, [_P, _f32_p, _f32_p]),
+    "dmpc_shard_num_chunks": (C.c_int, [_P]),
+    "dmpc_shard_finish": (C.c_int, [_P, _dbl_p]),
+    "dmpc_reduce_chunks": (C.c_double, [_dbl_p, C.c_int]),
+}
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing: build it with `python -m dmphyclus_b200.build` "
+                                "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _mats(m) -> np.ndarray:
+    m = np.asarray(m, dtype=np.float64)
+    if m.ndim != 3 or m.shape[1:] != (4, 4):
+        raise ValueError(f"transition matrix list must be [R][4][4], got {m.shape}")
+    return np.ascontiguousarray(m.transpose(0, 2, 1)).ravel()      # column-major per matrix, as R passes them
+
+
+def _edge(e) -> np.ndarray:
+    e = np.asarray(e)
+    if e.ndim != 2 or e.shape[1] != 2:
+        raise ValueError("edge matrix must be [E][2]")
+    return np.ascontiguousarray(e.T, dtype=np.int32).ravel()
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Engine:
+    """The eleven entry points of the reference, evaluated on the GPU."""
+
+    name = "cuda"
+
+    def __init__(self, device: int = -1, quirk_carry: bool = True, site_begin: int = 0, sites_total: int = 0):
+        self.lib = load_library()
+        self.opts = Options()
+        self.lib.dmpc_default_options(C.byref(self.opts))
+        self.opts.device = device
+        self.opts.quirk_carry = int(quirk_carry)
+        self.opts.site_begin, self.opts.sites_total = site_begin, sites_total
+        self._shape = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DmpcError(rc, self.lib.dmpc_last_error().decode())
+
+    # ------------------------------------------------------------------ the 11 entry points
+    def getConvertedAlignment(self, equivVector, alignmentAlphaMat) -> np.ndarray:
+        a = np.asarray(alignmentAlphaMat)
+        if a.dtype != np.uint8:
+            a = np.char.encode(a.astype(str), "ascii").view(np.uint8).reshape(a.shape)
+        a = np.ascontiguousarray(a)
+        states = "".join(equivVector).encode()
+        if len(states) != 4:
+            raise ValueError("4-state DNA only (names(limProbs) must have 4 entries)")
+        out = np.empty(a.shape, np.uint8)
+        bad = self.lib.dmpc_convert_alignment(a.ctypes.data_as(C.c_char_p), a.size, states, _p(out, _u8_p))
+        if bad:
+            raise ValueError(f"{bad} alignment cells hold a symbol outside the DNA/IUPAC alphabet")
+        return out
+
+    def logLikCpp(self, edgeMat, clusterMRCAs, limProbsVec, withinTransMatList, betweenTransMatList, numOpenMP,
+                  alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex):
+        e = _edge(edgeMat)
+        m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
+        pi = np.ascontiguousarray(limProbsVec, dtype=np.float64)
+        w, b = _mats(withinTransMatList), _mats(betweenTransMatList)
+        al = np.ascontiguousarray(alignmentBin, dtype=np.uint8)
+        if al.shape != (numTips, numLoci) or len(w) != len(b) or len(pi) != 4:
+            raise ValueError("alignmentBin must be [numTips][numLoci]; matrix lists must have equal length")
+        h, ll = _P(), C.c_double()
+        self._check(self.lib.dmpc_loglik_create(_p(e, _i32_p), len(e) // 2, _p(m, _dbl_p), len(m), _p(pi, _dbl_p),
+                                                _p(w, _dbl_p), _p(b, _dbl_p), len(w) // 16, _p(al, _u8_p), numTips,
+                                                numLoci, int(withinMatListIndex), int(betweenMatListIndex),
+                                                C.byref(self.opts), C.byref(h), C.byref(ll)))
+        self._shape[h.value] = (numTips, numLoci, len(w) // 16)
+        return {"logLik": ll.value, "solutionPointer": h.value, "alignmentBinPointer": None}
+
+    def newBetweenTransProbsLogLik(self, ptr, withinTransProbs, newBetweenTransProbs, numOpenMP,
+                                   newBetweenMatListIndex, limProbs) -> float:
+        w, b, pi = _mats(withinTransProbs), _mats(newBetweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_new_between_transprobs_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p),
+                                                                int(newBetweenMatListIndex), _p(pi, _dbl_p), C.byref(ll)))
+        return ll.value
+
+    def newWithinTransProbsLogLik(self, ptr, newWithinTransProbs, betweenTransProbs, numOpenMP,
+                                  newWithinMatListIndex, limProbs) -> float:
+        w, b, pi = _mats(newWithinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_new_within_transprobs_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p),
+                                                               int(newWithinMatListIndex), _p(pi, _dbl_p), C.byref(ll)))
+        return ll.value
+
+    def withinClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, MRCAofClusForNNI, numMovesNNI,
+                            numOpenMP, limProbs):
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        n = self._shape[ptr][0]
+        edge = np.zeros(2 * (2 * n - 2), np.int32)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_within_clus_nni_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), int(MRCAofClusForNNI),
+                                                         int(numMovesNNI), _p(pi, _dbl_p), C.byref(ll), _p(edge, _i32_p)))
+        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
+
+    def betweenClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, clusterMRCAs, numMovesNNI,
+                             numOpenMP, limProbs):
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
+        n = self._shape[ptr][0]
+        edge = np.zeros(2 * (2 * n - 2), np.int32)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(m, _dbl_p), len(m),
+                                                          int(numMovesNNI), _p(pi, _dbl_p), C.byref(ll), _p(edge, _i32_p)))
+        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
+
+    def clusSplitMergeLogLik(self, ptr, withinTransProbs, betweenTransProbs, clusMRCAsToSplitOrMerge, numOpenMP,
+                             limProbs) -> float:
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        m = np.ascontiguousarray(np.asarray(clusMRCAsToSplitOrMerge).ravel(), dtype=np.int32)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_clus_split_merge_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(m, _i32_p), len(m),
+                                                          _p(pi, _dbl_p), C.byref(ll)))
+        return ll.value
+
+    def RestorePreviousConfig(self, ptr, edgeMat, withinMatListIndex, betweenMatListIndex, NNImove, clusterMRCAs,
+                              splitMergeMove) -> None:
+        e = _edge(edgeMat)
+        m = np.ascontiguousarray(np.asarray(clusterMRCAs).ravel(), dtype=np.int32)
+        self._check(self.lib.dmpc_restore_previous_config(ptr, _p(e, _i32_p), len(e) // 2, int(withinMatListIndex),
+                                                          int(betweenMatListIndex), int(bool(NNImove)), _p(m, _i32_p),
+                                                          len(m), int(bool(splitMergeMove))))
+
+    def finalDeallocate(self, ptr) -> None:
+        self._shape.pop(ptr, None)
+        self._check(self.lib.dmpc_final_deallocate(ptr))
+
+    def getMaxMapSizeEstimate(self, allowedSizeInMegs, numRateCats) -> float:
+        return self.lib.dmpc_get_max_map_size_estimate(float(allowedSizeInMegs), int(numRateCats))
+
+    def checkAndCullMap(self, ptr, allowedNumberOfElements, cullProportion, withinTransProbs, betweenTransProbs,
+                        limProbs) -> None:
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        self._check(self.lib.dmpc_check_and_cull_map(ptr, int(allowedNumberOfElements), float(cullProportion),
+                                                     _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p)))
+
+    # ------------------------------------------------------------------ beyond the reference
+    def recomputeAll(self, ptr, withinTransProbs, betweenTransProbs, limProbs) -> float:
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        ll = C.c_double()
+        self._check(self.lib.dmpc_recompute_all(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p), C.byref(ll)))
+        return ll.value
+
+    def stats(self, ptr) -> dict:
+        s = Stats()
+        self._check(self.lib.dmpc_get_stats(ptr, C.byref(s)))
+        return s.as_dict()
+
+    def timer_begin(self, ptr) -> None:
+        self._check(self.lib.dmpc_timer_begin(ptr))
+
+    def timer_end(self, ptr) -> float:
+        ms = C.c_double()
+        self._check(self.lib.dmpc_timer_end(ptr, C.byref(ms)))
+        return ms.value
+
+    def partial(self, ptr, node):
+        n, s, r = self._shape[ptr]
+        sol = np.empty((s, r, 4), np.float64)
+        ex = np.empty((s, r), np.float32)
+        self._check(self.lib.dmpc_get_partial(ptr, int(node), _p(sol, _dbl_p), _p(ex, _f32_p)))
+        return sol, ex
+
+    def topology(self, ptr):
+        n = 2 * self._shape[ptr][0] - 1
+        arrs = [np.empty(n, np.int32) for _ in range(4)]
+        self._check(self.lib.dmpc_get_topology(ptr, *[_p(a, _i32_p) for a in arrs]))
+        return dict(zip(("parent", "child0", "child1", "within"), arrs))
+
+    def site_logliks(self, ptr) -> np.ndarray:
+        out = np.empty(self._shape[ptr][1], np.float64)
+        self._check(self.lib.dmpc_get_site_logliks(ptr, _p(out, _dbl_p)))
+        return out
+
+    # multi-GPU site sharding (see dmphyclus_b200/sharded.py)
+    def set_deferred(self, ptr, on: bool) -> None:
+        self._check(self.lib.dmpc_set_deferred(ptr, int(on)))
+
+    def shard_chain(self, ptr, carry_in) -> np.ndarray:
+        r = self._shape[ptr][2]
+        cin = np.zeros(8, np.float32)
+        cin[:r] = np.asarray(carry_in, np.float32)[:r]
+        cout = np.zeros(8, np.float32)
+        self._check(self.lib.dmpc_shard_chain(ptr, _p(cin, _f32_p), _p(cout, _f32_p)))
+        return cout[:r].copy()
+
+    def shard_finish(self, ptr) -> np.ndarray:
+        n = self.lib.dmpc_shard_num_chunks(ptr)
+        out = np.empty(n, np.float64)
+        self._check(self.lib.dmpc_shard_finish(ptr, _p(out, _dbl_p)))
+        return out
+
+    def reduce_chunks(self, chunks) -> float:
+        c = np.ascontiguousarray(chunks, dtype=np.float64)
+        return self.lib.dmpc_reduce_chunks(_p(c, _dbl_p), len(c))

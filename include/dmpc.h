@@ -1,0 +1,155 @@
+/* dmpc.h — C-ABI of the B200-native Felsenstein-pruning likelihood engine (libdmpc.so).
+ *
+ * Drop-in boundary for the ONE hot path of villandre/DMphyClus: the likelihood that
+ * `DMphyClusChain` / `logLikFromClusInd` evaluate over the AugTree.  Each entry point replaces one
+ * Rcpp-exported function of the reference (`src/clusterFunArmadillo.cpp`, registered in
+ * `src/RcppExports.cpp:179-192`, called from `R/RcppExports.R:4-46`); the citation beside each
+ * declaration is the reference interface it stands in for.  INTEGRATION.md shows the Rcpp shim a
+ * maintainer adds so that the R API stays unchanged.
+ *
+ * Conventions (all taken from what R hands the reference):
+ *   - node ids, matrix-list indices and edge matrices are R 1-BASED;
+ *   - an edge matrix is int32 [2*nEdgeRows], COLUMN-major (parents first, then children), nEdgeRows = 2N-2;
+ *   - a transition-matrix list is double [R*16]: R column-major 4x4 matrices, P(i,j) = Pr(parent i -> child j),
+ *     used as P * v (IntermediateNode.cpp:57);
+ *   - limProbs is double [4] in the same state order as the matrices (names(limProbs));
+ *   - the alignment is the packed form of getConvertedAlignment's result: uint8 [numTips*numLoci], row-major
+ *     by tip, bit j of a cell set when state j is compatible with the observed symbol.
+ * Everything is plain pointers and sizes; no C++/torch types cross the boundary.  All calls are synchronous:
+ * on return the log-likelihood has been computed on the GPU and copied back.  There is no CPU fallback: every
+ * entry point fails with DMPC_ERR_CUDA if no sm_100-class device is usable.
+ *
+ * Errors: functions return DMPC_OK (0) or a negative status; dmpc_last_error() gives the message for the calling
+ * thread.  The Rcpp shim turns a non-zero status into Rcpp::stop() (the reference throws Rcpp::exception,
+ * clusterFunArmadillo.cpp:136).
+ */
+#ifndef DMPC_H
+#define DMPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmpc_tree dmpc_tree; /* opaque; replaces XPtr<AugTree> (clusterFunArmadillo.cpp:57) */
+
+enum {
+  DMPC_OK = 0,
+  DMPC_ERR_ARG = -1,     /* malformed input (edge matrix, sizes, null pointer, unknown symbol) */
+  DMPC_ERR_CUDA = -2,    /* CUDA runtime/driver failure, or no usable device */
+  DMPC_ERR_NO_MOVE = -3, /* no NNI candidate exists (the reference aborts inside GSL here) */
+  DMPC_ERR_STATE = -4    /* call sequence error (e.g. use after dmpc_final_deallocate) */
+};
+
+/* Options fixed at handle creation (the R signature has no room for them; the shim reads env vars). */
+typedef struct dmpc_options {
+  int device;        /* CUDA device ordinal; -1 = current device */
+  int quirk_carry;   /* 1 (default): reproduce AugTree.cpp:306 — the fp32 exponent vector is NOT reset between
+                        loci, so sites are coupled through a sequential fp32 chain.  0: textbook per-site reduction */
+  int site_begin;    /* this handle evaluates global sites [site_begin, site_begin + numLoci) of an alignment of */
+  int sites_total;   /* sites_total sites (multi-GPU site sharding); single GPU: 0 and numLoci */
+} dmpc_options;
+void dmpc_default_options(dmpc_options* o);
+
+const char* dmpc_last_error(void);
+const char* dmpc_version(void);
+
+/* getConvertedAlignment (clusterFunArmadillo.cpp:64-113): chars [numTips*numLoci] row-major, lower-case
+ * DNA/IUPAC; states = the 4 names(limProbs).  Returns the number of cells holding an unknown symbol
+ * (their mask is 0; dmpc_loglik_create rejects such alignments). */
+long dmpc_convert_alignment(const char* chars, long nCells, const char* states, uint8_t* maskOut);
+
+/* logLikCpp (clusterFunArmadillo.cpp:36-62): builds the tree, uploads the alignment, evaluates. */
+int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
+                       const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
+                       int numRateCats, const uint8_t* alignmentBin, int numTips, int numLoci,
+                       int withinMatListIndex, int betweenMatListIndex, const dmpc_options* opts,
+                       dmpc_tree** treeOut, double* logLikOut);
+
+/* newBetweenTransProbsLogLik (clusterFunArmadillo.cpp:117-138) */
+int dmpc_new_between_transprobs_loglik(dmpc_tree* t, const double* withinTransMats, const double* newBetweenTransMats,
+                                       int newBetweenMatListIndex, const double* limProbs, double* logLikOut);
+/* newWithinTransProbsLogLik (clusterFunArmadillo.cpp:142-164) */
+int dmpc_new_within_transprobs_loglik(dmpc_tree* t, const double* newWithinTransMats, const double* betweenTransMats,
+                                      int newWithinMatListIndex, const double* limProbs, double* logLikOut);
+/* withinClusNNIlogLik (clusterFunArmadillo.cpp:168-203); edgeOut: int32 [2*(2N-2)] column-major, pre-order */
+int dmpc_within_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                int mrcaOfClusForNNI, int numMovesNNI, const double* limProbs, double* logLikOut,
+                                int32_t* edgeOut);
+/* betweenClusNNIlogLik (clusterFunArmadillo.cpp:207-242) */
+int dmpc_between_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                 const double* clusterMRCAs, int nClusterMRCAs, int numMovesNNI,
+                                 const double* limProbs, double* logLikOut, int32_t* edgeOut);
+/* clusSplitMergeLogLik (clusterFunArmadillo.cpp:246-276): n == 1 splits that cluster MRCA, n > 1 merges */
+int dmpc_clus_split_merge_loglik(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                                 const int32_t* clusMRCAsToSplitOrMerge, int n, const double* limProbs,
+                                 double* logLikOut);
+/* RestorePreviousConfig (clusterFunArmadillo.cpp:280-284; AugTree.cpp:348-366).  edge is read only when nniMove. */
+int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRows, int withinMatListIndex,
+                                 int betweenMatListIndex, int nniMove, const int32_t* clusterMRCAs,
+                                 int nClusterMRCAs, int splitMergeMove);
+/* finalDeallocate (clusterFunArmadillo.cpp:288-294) — also frees the tree itself, which the reference leaks */
+int dmpc_final_deallocate(dmpc_tree* t);
+/* getMaxMapSizeEstimate (clusterFunArmadillo.cpp:298-302): same arithmetic, kept for signature parity */
+double dmpc_get_max_map_size_estimate(double allowedSizeInMegs, unsigned numRateCats);
+/* checkAndCullMap (clusterFunArmadillo.cpp:305-332): the dense HBM layout has no dictionary to cull; no-op */
+int dmpc_check_and_cull_map(dmpc_tree* t, unsigned allowedNumberOfElements, float cullProportion,
+                            const double* withinTransMats, const double* betweenTransMats, const double* limProbs);
+
+/* ---------------------------------------------------------------- beyond the reference's 11 entry points */
+
+/* Re-evaluate everything with the current topology/flags/matrices (InvalidateAll + ComputeLoglik); the bench's
+ * device-resident "step".  Does not touch the rollback state of the last proposal. */
+int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                       const double* limProbs, double* logLikOut);
+
+/* Counters since creation: node-site-rate partial updates performed, kernels launched, seconds of device time of
+ * the last evaluation (CUDA events on the engine's stream). */
+typedef struct dmpc_stats {
+  unsigned long long updates;
+  unsigned long long kernel_launches;
+  unsigned long long evaluations;
+  double last_eval_ms;      /* whole evaluation: prune levels + root reduction */
+  double last_prune_ms;     /* the prune_level launches only */
+  unsigned long long last_updates;   /* updates of the last evaluation */
+  unsigned long long last_prune_launches;
+  int last_levels;
+  int exponent_capacity;    /* rows of the per-site rescale list (grows on demand) */
+  unsigned long long device_bytes;   /* bytes of HBM held by this handle */
+} dmpc_stats;
+int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
+/* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
+ * torch.cuda.Event cannot see).  end returns the elapsed milliseconds between the two records. */
+int dmpc_timer_begin(dmpc_tree* t);
+int dmpc_timer_end(dmpc_tree* t, double* msOut);
+
+/* Introspection for parity tests: the committed partial of a vertex (0-based id >= numTips) as
+ * sol [numLoci][R][4] and expo [numLoci][R] (the oracle's layout), and the topology/flags. */
+int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo);
+int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* child1, int32_t* within);
+/* per-site terms of the last evaluation: rateAveragedLogLiks (AugTree.cpp:322), [numLoci] */
+int dmpc_get_site_logliks(dmpc_tree* t, double* out);
+
+/* Multi-GPU site sharding (one handle per rank, contiguous site blocks).  With quirk_carry and R > 1 the
+ * fp32 exponent chain crosses shard boundaries: a rank's chain starts from the previous rank's carry.
+ *   dmpc_shard_begin:  runs the dirty-node pruning and the per-site gather for the pending evaluation of the
+ *                      LAST entry-point call made with deferred reduction (see dmpc_set_deferred);
+ *   dmpc_shard_chain:  runs this shard's chain from carryIn[R] (fp32) and returns carryOut[R];
+ *   dmpc_shard_finish: returns the deterministic partial sums of this shard's sites in fixed 256-site chunks
+ *                      (chunkSums[nChunks]); the caller all-gathers them and adds them in chunk order, so the
+ *                      total is bit-identical for any number of ranks.
+ * With deferral on, the entry points above return logLik = NaN and leave the reduction to these calls. */
+int dmpc_set_deferred(dmpc_tree* t, int on);
+int dmpc_shard_chain(dmpc_tree* t, const float* carryIn, float* carryOut);
+int dmpc_shard_num_chunks(dmpc_tree* t);
+int dmpc_shard_finish(dmpc_tree* t, double* chunkSums);
+/* Host-side twin of the device's final reduction: adds n chunk sums in the same fixed order as the single-GPU
+ * kernel (256 strided accumulators, then a binary tree), so 1-GPU and N-GPU totals agree bit for bit. */
+double dmpc_reduce_chunks(const double* chunkSums, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMPC_H */
