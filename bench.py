@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the Felsenstein-pruning likelihood path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2] [--data evolved|iid]
+
+One "step" = one full evaluation of the likelihood (InvalidateAll + ComputeLoglik: every internal vertex of the
+tree re-pruned at every site and rate category, then the root reduction) on one batch of synthetic input.  The
+metric is BASELINE.json's: node-site partial updates/sec, one update = one 4-state conditional-likelihood vector
+for one (internal vertex, site, rate category).
+
+  value      device-resident: the alignment, tree and buffers already live in HBM; K x dmpc_recompute_all, timed
+             with CUDA events on the engine's own stream, max over ranks.
+  e2e        the same evaluation through the reference-facing call (`logLikCpp` = dmpc_loglik_create, then
+             `finalDeallocate`) from pinned HOST buffers: tree build, alignment upload, pruning, reduction and
+             the read-back of the log-likelihood all inside the timed region (wall clock around synchronous calls).
+  roofline   k_prune_level (the dominant kernel): algorithmic bytes of the timed launches / their device time
+             (CUDA events around the level launches of every evaluation), against MEASURED_PEAKS.json's HBM copy rate.
+  cpu_baseline  the reference's own translation units (oracle/_ref, single-threaded — its OpenMP is commented
+             out) on a bounded sample of the same alignment, on this box's host cores.
+
+N > 1 (launched by torchrun, one rank per GPU): sites are sharded, every rank holds `sites` columns (weak scaling);
+the ranks meet only in the root reduction (dmphyclus_b200/sharded.py).
+
+`--impl reference` times the reference's CPU implementation (oracle/_ref/libref.so, else the oracle port) on the
+same workload and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "node-site partial updates/sec"
+UNIT = "updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--data", default="evolved", choices=["evolved", "iid"])
+    ap.add_argument("--tree", default="random", choices=["random", "balanced", "caterpillar"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 20))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
+    ap.add_argument("--seed", type=int, default=2001)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n, s, r):
+    """per full evaluation, S*R*[(N-2)*32 + (N-1)*36] + S*N bytes (~68 B per update)."""
+    return s * r * ((n - 2) * 32 + (n - 1) * 36) + s * n
+
+
+def make_problem(args, world):
+    from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
+    n, s, k, r = CONFIGS[args.workload]
+    # weak scaling: every rank holds `s` sites of an alignment of s * world sites
+    return Problem(load_packaged(), n, s * world, k, r, args.data, args.tree, seed=args.seed), (n, s, k, r)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled through NVML while the GPU works."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag, self.ok = device, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # the number is still reported; the record says why clocks are missing
+            self.err = repr(e)
+        self.mark = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((time.perf_counter(), sm, rs, util, self.mark))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable: " + self.err}
+        timed = [x for x in self.samples if x[4] == "timed"] or [x for x in self.samples if x[4] is not None]
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        bits = 0
+        for x in timed:
+            bits |= x[2]
+        bits &= ~0x1
+        return {"sm_mhz": float(np.median([x[1] for x in timed])) if timed else None, "sm_max_mhz": float(self.max_sm),
+                "reasons": [v for k, v in names.items() if bits & k], "samples": len(timed)}
+
+
+def cpu_reference_backend():
+    from oracle.oracle import Oracle, Reference
+    try:
+        return Reference(), "reference"
+    except Exception:
+        return Oracle(), "port"
+
+
+def time_cpu(be, p, n_sites, reps=1):
+    """One logLikCpp (tree build, dictionary fill, pruning, reduction) on the first n_sites columns."""
+    from dmphyclus_b200 import synth
+    al = be.getConvertedAlignment(list(synth.STATES), p.chars[:, :n_sites])
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        res = be.logLikCpp(p.edge, p.mrcas, p.pi, p.W[p.w_idx - 1], p.B[p.b_idx - 1], 1, al, p.n, n_sites, p.w_idx, p.b_idx)
+        dt = time.perf_counter() - t0
+        be.finalDeallocate(res["solutionPointer"])
+        best = dt if best is None else min(best, dt)
+    return best, res["logLik"]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    p, (n, s, k, r) = make_problem(args, 1)
+    be, kind = cpu_reference_backend()
+    # calibrate, then size the per-step sample so that the whole run stays within ~90 s
+    t_probe, _ = time_cpu(be, p, 64)
+    per_site = t_probe / 64
+    budget = 90.0 / max(1, args.steps + args.warmup)
+    ns = int(max(64, min(s, budget / per_site / 1.5)))      # /1.5: std::map lookups slow down as it grows
+    for _ in range(args.warmup):
+        time_cpu(be, p, ns)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, ll = time_cpu(be, p, ns)
+    dt = time.perf_counter() - t0
+    upd = (n - 1) * ns * r
+    val = upd * args.steps / dt
+    sample = f"first {ns} of {s} sites, all {n} tips, one logLikCpp per step (tree build + dictionary fill + pruning + reduction)"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(args, n, s, k, r, 1),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                            "host_cores": os.cpu_count(),
+                            "note": "the reference's likelihood is single-threaded (OpenMP commented out, "
+                                    "clusterFunArmadillo.cpp:4,38); it cannot use more host threads"},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(args, n, s, k, r, world):
+    return {"workload": f"{args.workload}: logLikFromClusInd-style full evaluation, {n} seqs x {s} sites per GPU, "
+                        f"{k} clusters, {r} rate categories",
+            "tips": n, "sites_per_gpu": s, "sites_total": s * world, "clusters": k, "rate_categories": r,
+            "alignment": args.data, "tree": args.tree, "seed": args.seed,
+            "matrices": "packaged withinClusTransProbs[[5]] / betweenClusTransProbs[[5]]",
+            "l2": "inputs larger than L2 (partials of one evaluation >> 126 MB); no explicit flush",
+            "parallelism": f"site-sharded x{world}" if world > 1 else "single GPU"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from dmphyclus_b200 import build, synth
+    from dmphyclus_b200.engine import Engine
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the likelihood engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p, (n, s, k, r) = make_problem(args, world)
+    S_total = s * world
+    W, B = p.W[p.w_idx - 1], p.B[p.b_idx - 1]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    if world > 1:
+        from dmphyclus_b200.sharded import ShardedEngine, shard_range
+        local = Engine(device=local_rank, site_begin=shard_range(S_total, rank, world)[0], sites_total=S_total)
+        eng = ShardedEngine(local, S_total, device=torch.device("cuda", local_rank))
+        b0, b1 = eng.begin, eng.end
+    else:
+        local = eng = Engine(device=local_rank)
+        b0, b1 = 0, S_total
+    s_local = b1 - b0
+    # this rank's alignment block in pinned host memory (the e2e leg uploads it every step)
+    masks = local.getConvertedAlignment(list(synth.STATES), p.chars[:, b0:b1])
+    pinned = torch.empty(masks.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = masks
+    al = pinned.numpy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- device-resident leg
+    res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+    h, ll0 = res["solutionPointer"], res["logLik"]
+    sampler.mark = "warm"
+    for _ in range(max(3, args.warmup)):
+        ll = eng.recomputeAll(h, W, B, p.pi)
+    assert ll == ll0, (ll, ll0)          # a full re-evaluation is deterministic
+    st0 = local.stats(h)
+    prune_ms = 0.0
+    barrier()
+    sampler.mark = "timed"
+    local.timer_begin(h)
+    for _ in range(args.steps):
+        eng.recomputeAll(h, W, B, p.pi)
+        prune_ms += local.stats(h)["last_prune_ms"]
+    ms = local.timer_end(h)
+    barrier()
+    sampler.mark = "after"
+    ms = max_over_ranks(ms)
+    st1 = local.stats(h)
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    prune_launches = st1["last_prune_launches"] * args.steps
+    updates_step = (n - 1) * S_total * r
+    value = updates_step * args.steps / (ms * 1e-3)
+    peak, peak_src = peaks()
+    bytes_eval = algorithmic_bytes(n, s_local, r)
+    achieved = bytes_eval * args.steps / (prune_ms * 1e-3) / 1e9
+    dev_bytes = st1["device_bytes"]
+    eng.finalDeallocate(h)
+
+    # ---------------------------------------------------------------- end-to-end leg (host buffers in, scalar out)
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    for _ in range(3):
+        res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        eng.finalDeallocate(res["solutionPointer"])
+    barrier()
+    sampler.mark = "e2e"
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        eng.finalDeallocate(res["solutionPointer"])
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.mark = "after"
+    assert res["logLik"] == ll0, (res["logLik"], ll0)
+    e2e_value = updates_step * e2e_steps / (e2e_ms * 1e-3)
+    h2d = al.nbytes + 2 * (2 * n - 2) * 4 + 2 * r * 16 * 8 + 4 * 8 + 8 * len(p.mrcas) + (n - 1) * 16
+    d2h = 8 + 4 + 4
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        extras = extra_legs(args, eng, p, al, n, s, k, r)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(p, n, s, r)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": config_dict(args, n, s, k, r, world),
+               "clocks": sampler.summary(),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                       "call": "Engine.logLikCpp (dmpc_loglik_create) + finalDeallocate, alignment in pinned host memory"},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "k_prune_level", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": bytes_eval / max(1, st1["last_prune_launches"]),
+                            "launches_per_step": int(st1["last_prune_launches"]),
+                            "kernel_ms_per_step": prune_ms / args.steps,
+                            "kernel_share_of_step": prune_ms / ms, "frac_of_8000_spec": achieved / 8000.0},
+               "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
+               "levels": int(st1["last_levels"])}
+        out.update(extras)
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extra_legs(args, eng, p, al, n, s, k, r):
+    """Secondary numbers (not the headline): the rescale-stress alignment and MCMC iterations/sec."""
+    from dmphyclus_b200 import chain, synth
+    from dmphyclus_b200.workloads import Problem, load_packaged
+    out = {}
+    other = "iid" if args.data == "evolved" else "evolved"
+    q = Problem(load_packaged(), n, s, k, r, other, args.tree, seed=args.seed)
+    alq = eng.getConvertedAlignment(list(synth.STATES), q.chars)
+    res = eng.logLikCpp(q.edge, q.mrcas, q.pi, q.W[4], q.B[4], 1, alq, q.n, s, 5, 5)
+    h = res["solutionPointer"]
+    for _ in range(3):
+        eng.recomputeAll(h, q.W[4], q.B[4], q.pi)
+    steps = max(5, min(args.steps, 50))
+    eng.timer_begin(h)
+    pr = 0.0
+    for _ in range(steps):
+        eng.recomputeAll(h, q.W[4], q.B[4], q.pi)
+        pr += eng.stats(h)["last_prune_ms"]
+    ms = eng.timer_end(h)
+    st = eng.stats(h)
+    out[f"extra_{other}"] = {"value": (n - 1) * s * r * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                             "prune_ms_per_step": pr / steps, "rescale_rows": st["exponent_capacity"],
+                             "logLik": res["logLik"]}
+    eng.finalDeallocate(h)
+    # MCMC iterations/sec: the reference's move schedule (.performStepPhylo) driven from the host mirror
+    cs = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
+                             scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
+    iters = 5
+    t0 = time.perf_counter()
+    _, calls = chain.run_chain(eng, al, p.edge, p.clus, 100.0, cs, iters, seed=args.seed)
+    dt = time.perf_counter() - t0
+    out["mcmc"] = {"iterations_per_sec": iters / dt, "iterations": iters, "likelihood_calls": calls,
+                   "note": "host driver = Python mirror of .performStepPhylo (R in a deployment); includes the initial logLikCpp"}
+    return out
+
+
+def cpu_baseline(p, n, s, r):
+    from oracle.oracle import Oracle
+    be, kind = cpu_reference_backend()
+    ns = min(s, 5000)
+    dt, _ = time_cpu(be, p, ns)
+    out = {"value": (n - 1) * ns * r / dt, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"first {ns} of {s} sites, all {n} tips, one logLikCpp ({dt:.1f} s of CPU work)",
+           "host_cores": os.cpu_count()}
+    # the dense oracle port: 1 thread, and OpenMP over sites on every host core (what numLikThreads advertised)
+    dt1, _ = time_cpu(Oracle(threads=1), p, s)
+    nthr = os.cpu_count() or 1
+    dtn, _ = time_cpu(Oracle(threads=nthr), p, s)
+    out["port_dense_1thread"] = {"value": (n - 1) * s * r / dt1, "unit": UNIT, "cores": 1, "sample": f"all {s} sites"}
+    out["port_dense_openmp"] = {"value": (n - 1) * s * r / dtn, "unit": UNIT, "cores": nthr, "sample": f"all {s} sites"}
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -239,7 +239,9 @@ int rootStage(dmpc_tree* t, double* ll) {
   int rc;
   const bool chain = t->quirk && t->R > 1;
   if (t->deferred) {
-    if ((rc = gatherWithGrowth(t))) return rc;
+    if ((rc = gatherWithGrowth(t))) return rc;      // synchronises the stream: ev[0], ev[1] have completed
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms; t->st.last_eval_ms = ms;
     *ll = NAN;
     return DMPC_OK;
   }
@@ -296,7 +298,7 @@ int checkHandle(dmpc_tree* t) {
 extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
-  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0;
+  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0;
 }
 
 const char* dmpc_last_error(void) { return g_err.c_str(); }
@@ -343,6 +345,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->T = t->Sp / TILE;
   t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
   t->quirk = o.quirk_carry != 0;
+  t->deferred = o.deferred != 0;
   t->siteBegin = o.site_begin; t->sitesTotal = o.sites_total ? o.sites_total : numLoci;
   t->rv.RP = numRateCats <= 4 ? 4 : 8;
 

@@ -25,7 +25,8 @@ class DmpcError(RuntimeError):
 
 
 class Options(C.Structure):
-    _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int)]
+    _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int),
+                ("deferred", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -112,6 +113,7 @@ class Engine:
         self.opts.device = device
         self.opts.quirk_carry = int(quirk_carry)
         self.opts.site_begin, self.opts.sites_total = site_begin, sites_total
+        self.quirk_carry = bool(quirk_carry)
         self._shape = {}
 
     def _check(self, rc):
@@ -134,7 +136,7 @@ class Engine:
         return out
 
     def logLikCpp(self, edgeMat, clusterMRCAs, limProbsVec, withinTransMatList, betweenTransMatList, numOpenMP,
-                  alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex):
+                  alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex, deferred=False):
         e = _edge(edgeMat)
         m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
         pi = np.ascontiguousarray(limProbsVec, dtype=np.float64)
@@ -143,6 +145,7 @@ class Engine:
         if al.shape != (numTips, numLoci) or len(w) != len(b) or len(pi) != 4:
             raise ValueError("alignmentBin must be [numTips][numLoci]; matrix lists must have equal length")
         h, ll = _P(), C.c_double()
+        self.opts.deferred = int(deferred)
         self._check(self.lib.dmpc_loglik_create(_p(e, _i32_p), len(e) // 2, _p(m, _dbl_p), len(m), _p(pi, _dbl_p),
                                                 _p(w, _dbl_p), _p(b, _dbl_p), len(w) // 16, _p(al, _u8_p), numTips,
                                                 numLoci, int(withinMatListIndex), int(betweenMatListIndex),

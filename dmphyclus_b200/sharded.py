@@ -1,0 +1,147 @@
+"""Site-sharded evaluation across the GPUs of one box: one process per GPU (`torch.distributed`), each rank
+owning one contiguous block of alignment columns behind its own `libdmpc` handle.
+
+Every per-(vertex, site) quantity of the likelihood is independent across sites, so pruning needs no
+data-path collective.  The root reduction is where ranks meet:
+
+  * the reference never resets its fp32 exponent vector between loci (`/root/reference/src/AugTree.cpp:306`;
+    SURVEY.md §0.2), so with more than one rate category the per-site terms form ONE sequential fp32 chain over
+    all loci.  The chain therefore hops from rank to rank in site order: rank r runs its block's chain from the
+    carry rank r-1 broadcast (R floats), then broadcasts its own;
+  * each rank then reduces its sites to per-256-site chunk sums; the chunk sums are all-gathered and added in a
+    fixed order (`dmpc_reduce_chunks`), so the total is bit-identical for 1, 2, 4 or 8 ranks — which is what
+    keeps MCMC trajectories identical across GPU counts.
+
+All ranks run the same driver with the same RNG stream and make the same entry-point calls (SPMD); every
+rank gets the same log-likelihood back.  `torch.distributed` is plumbing only: payloads are R floats and
+S/256 doubles per evaluation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+CHUNK = 256   # sites per deterministic reduction chunk (dmphyclus_b200/csrc/kernels.cuh)
+
+
+def shard_range(sites_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous site block [begin, end) of `rank`; block sizes are multiples of CHUNK so that chunk
+    boundaries — and hence the summation tree — do not depend on the number of ranks."""
+    per = -(-sites_total // world)
+    per = -(-per // CHUNK) * CHUNK
+    b = min(sites_total, rank * per)
+    return b, min(sites_total, b + per)
+
+
+class ShardedEngine:
+    """The reference's entry points (same names as `engine.Engine`) over a process group.
+
+    `backend` is this rank's local evaluator: an `engine.Engine` built with `site_begin`/`sites_total`
+    (tests plug in a CPU stand-in with the same shard methods to exercise the exchange under gloo)."""
+
+    name = "cuda-sharded"
+
+    def __init__(self, backend, sites_total: int, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.be, self.group = backend, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.sites_total = sites_total
+        self.begin, self.end = shard_range(sites_total, self.rank, self.world)
+        if self.end <= self.begin:
+            raise ValueError(f"rank {self.rank} owns no site: {sites_total} sites over {self.world} ranks "
+                             f"(blocks are multiples of {CHUNK})")
+        self.device = device if device is not None else torch.device("cpu")
+        self._chunks_per_rank = [-(-(e - b) // CHUNK) for b, e in
+                                 (shard_range(sites_total, r, self.world) for r in range(self.world))]
+        self._R = {}
+        self.collectives = 0
+
+    # ------------------------------------------------------------------ the exchange
+    def _reduce(self, ptr) -> float:
+        torch, dist = self.torch, self.dist
+        R = self._R[ptr]
+        carry = np.zeros(R, np.float32)
+        if R > 1 and getattr(self.be, "quirk_carry", True):
+            buf = torch.zeros(R, dtype=torch.float32, device=self.device)
+            for r in range(self.world):               # the fp32 chain crosses the blocks in site order
+                if r == self.rank:
+                    carry = self.be.shard_chain(ptr, carry)
+                    buf.copy_(torch.from_numpy(carry))
+                if r + 1 < self.world:
+                    dist.broadcast(buf, src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
+                    self.collectives += 1
+                    if r + 1 == self.rank:
+                        carry = buf.cpu().numpy().copy()
+        mine = self.be.shard_finish(ptr)
+        width = max(self._chunks_per_rank)
+        send = torch.zeros(width, dtype=torch.float64, device=self.device)
+        send[:len(mine)] = torch.from_numpy(mine)
+        recv = torch.empty(width * self.world, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        self.collectives += 1
+        allc = recv.cpu().numpy().reshape(self.world, width)
+        chunks = np.concatenate([allc[r, :n] for r, n in enumerate(self._chunks_per_rank)])
+        return float(self.be.reduce_chunks(chunks))
+
+    # ------------------------------------------------------------------ entry points
+    def getConvertedAlignment(self, equivVector, alignmentAlphaMat):
+        return self.be.getConvertedAlignment(equivVector, alignmentAlphaMat)
+
+    def logLikCpp(self, edgeMat, clusterMRCAs, limProbsVec, withinTransMatList, betweenTransMatList, numOpenMP,
+                  alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex):
+        """`alignmentBin` is the FULL [numTips][numLoci] matrix or this rank's block [numTips][end-begin]."""
+        al = np.asarray(alignmentBin)
+        if al.shape[1] == self.sites_total:
+            al = al[:, self.begin:self.end]
+        if al.shape[1] != self.end - self.begin:
+            raise ValueError("alignmentBin must hold all sites or exactly this rank's block")
+        res = self.be.logLikCpp(edgeMat, clusterMRCAs, limProbsVec, withinTransMatList, betweenTransMatList,
+                                numOpenMP, al, numTips, al.shape[1], withinMatListIndex, betweenMatListIndex,
+                                deferred=True)
+        ptr = res["solutionPointer"]
+        self._R[ptr] = len(np.asarray(withinTransMatList))
+        res["logLik"] = self._reduce(ptr)
+        return res
+
+    def newBetweenTransProbsLogLik(self, ptr, *a):
+        self.be.newBetweenTransProbsLogLik(ptr, *a)
+        return self._reduce(ptr)
+
+    def newWithinTransProbsLogLik(self, ptr, *a):
+        self.be.newWithinTransProbsLogLik(ptr, *a)
+        return self._reduce(ptr)
+
+    def withinClusNNIlogLik(self, ptr, *a):
+        res = self.be.withinClusNNIlogLik(ptr, *a)
+        res["logLik"] = self._reduce(ptr)
+        return res
+
+    def betweenClusNNIlogLik(self, ptr, *a):
+        res = self.be.betweenClusNNIlogLik(ptr, *a)
+        res["logLik"] = self._reduce(ptr)
+        return res
+
+    def clusSplitMergeLogLik(self, ptr, *a):
+        self.be.clusSplitMergeLogLik(ptr, *a)
+        return self._reduce(ptr)
+
+    def recomputeAll(self, ptr, *a):
+        self.be.recomputeAll(ptr, *a)
+        return self._reduce(ptr)
+
+    def RestorePreviousConfig(self, ptr, *a):
+        self.be.RestorePreviousConfig(ptr, *a)
+
+    def finalDeallocate(self, ptr):
+        self._R.pop(ptr, None)
+        self.be.finalDeallocate(ptr)
+
+    def getMaxMapSizeEstimate(self, *a):
+        return self.be.getMaxMapSizeEstimate(*a)
+
+    def checkAndCullMap(self, ptr, *a):
+        self.be.checkAndCullMap(ptr, *a)
+
+    def stats(self, ptr):
+        return self.be.stats(ptr)

@@ -50,6 +50,8 @@ typedef struct dmpc_options {
                         loci, so sites are coupled through a sequential fp32 chain.  0: textbook per-site reduction */
   int site_begin;    /* this handle evaluates global sites [site_begin, site_begin + numLoci) of an alignment of */
   int sites_total;   /* sites_total sites (multi-GPU site sharding); single GPU: 0 and numLoci */
+  int deferred;      /* 1: start in deferred-reduction mode (see dmpc_set_deferred): dmpc_loglik_create prunes and
+                        gathers but leaves the root reduction to dmpc_shard_chain / dmpc_shard_finish */
 } dmpc_options;
 void dmpc_default_options(dmpc_options* o);
 

@@ -1,42 +1,49 @@
-"""Shared builders for the parity tests: seeded synthetic problems in the reference's input conventions."""
-import numpy as np
-
-from dmphyclus_b200 import synth
-
-
-class Problem:
-    def __init__(self, packaged, n, n_sites, k, n_rates, kind="iid", shape="random", seed=0, w_idx=5, b_idx=5):
-        rng = np.random.default_rng(seed)
-        self.n, self.S, self.R = n, n_sites, n_rates
-        self.W = packaged["within"][:, :n_rates].copy()
-        self.B = packaged["between"][:, :n_rates].copy()
-        if kind == "diverged":
-            # longer branches (powers of the packaged between-cluster matrices): sites then differ in which rate
-            # category dominates, which is what makes the reference's cross-locus exponent carry visible
-            #  and exercises the sequential fp32 chain
-            def power(m, k):
-                out = np.stack([[np.linalg.matrix_power(m[i, r], k) for r in range(n_rates)] for i in range(len(m))])
-                return out / out.sum(-1, keepdims=True)
-            self.W, self.B = power(self.B, 4), power(self.B, 8)
-        self.pi = synth.LIM_PROBS.copy()
-        self.edge = synth.random_tree(n, rng, shape)
-        self.mrcas, self.clus = synth.pick_clusters(self.edge, n, k)
-        if kind == "iid":
-            self.chars = synth.iid_alignment(n, n_sites, rng)
-        elif kind == "diverged":
-            self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[9], self.B[9], self.mrcas, self.pi, rng)
-        elif kind == "evolved":
-            self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[4], self.B[9], self.mrcas, self.pi, rng)
-        else:
-            raise ValueError(kind)
-        self.w_idx, self.b_idx = w_idx, b_idx
-
-    def create(self, backend):
-        al = backend.getConvertedAlignment(list(synth.STATES), self.chars)
-        res = backend.logLikCpp(self.edge, self.mrcas, self.pi, self.W[self.w_idx - 1], self.B[self.b_idx - 1], 1, al,
-                                self.n, self.S, self.w_idx, self.b_idx)
-        return res["solutionPointer"], res["logLik"]
+"""Shared helpers of the parity tests."""
+from dmphyclus_b200.workloads import Problem  # noqa: F401
 
 
 def rel(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
+
+
+class GoldenCase:
+    """A case of tests/golden/ref_vectors.npz: the stored inputs in `Problem`'s shape plus the reference's outputs."""
+
+    def __init__(self, data, name):
+        import numpy as np
+        from dmphyclus_b200 import synth
+        g = {k.split("/", 1)[1]: data[k] for k in data.files if k.startswith(name + "/")}
+        self.edge, self.mrcas, self.chars = g["in_edge"], [int(x) for x in g["in_mrcas"]], g["in_chars"]
+        self.W, self.B = g["in_W"], g["in_B"]
+        self.n, self.S = self.chars.shape
+        self.R = self.W.shape[1]
+        self.pi = synth.LIM_PROBS.copy()
+        self.w_idx = self.b_idx = 5
+        self.expected = {k: v for k, v in g.items() if not k.startswith("in_")}
+        self.np = np
+
+
+def load_golden():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+
+
+def compare_to_golden(got, expected, ll_tol, exact_partials=True):
+    """Integer outputs bit-exact; log-likelihoods within ll_tol relative; partial vectors bit-exact (or 1e-13
+    relative) and fp32 exponents to their last bit (glibc vs CUDA log differ by <= 1 ulp before the float rounding)."""
+    import numpy as np
+    for k, e in expected.items():
+        g = got[k]
+        if k == "logliks":
+            assert g.shape == e.shape
+            assert np.all(np.abs(g - e) <= ll_tol * np.abs(e)), (k, g, e)
+        elif k.startswith("sol_"):
+            if exact_partials:
+                assert np.array_equal(g, e), k
+            else:
+                assert np.allclose(g, e, rtol=1e-13, atol=0), k
+        elif k.startswith("exp_"):
+            assert np.allclose(g, e, rtol=2e-7, atol=0), k
+        else:
+            assert np.array_equal(g, e), k

@@ -129,3 +129,114 @@ def test_error_paths(packaged, engine):
     with pytest.raises(DmpcError):   # a tip has no NNI candidate: error, not the reference's GSL abort
         engine.withinClusNNIlogLik(h, p.W[4], p.B[4], 1, 1, 1, p.pi)
     engine.finalDeallocate(h)
+
+
+# ---------------------------------------------------------------------------------------------- golden fixtures
+from helpers import GoldenCase, compare_to_golden, load_golden  # noqa: E402
+from script import GOLDEN_CASES, VIGNETTE_CASES, run_script, vignette_loglik  # noqa: E402
+
+
+@pytest.mark.parametrize("name", [c[0] for c in GOLDEN_CASES])
+def test_golden_script_on_gpu(engine, name):
+    """The scripted sequence over all entry points against what the reference's own TUs produced
+    (tests/golden/ref_vectors.npz): integers and partial vectors bit-exact, log-likelihoods within 1e-9."""
+    case = GoldenCase(load_golden(), name)
+    compare_to_golden(run_script(engine, case), case.expected, ll_tol=TOL, exact_partials=True)
+
+
+def test_golden_vignette_on_gpu(engine, packaged):
+    for (m, wi, bi), want in zip(VIGNETTE_CASES, load_golden()["vignette/logliks"]):
+        assert rel(vignette_loglik(engine, packaged, m, wi, bi), want) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- site sharding
+@pytest.mark.parametrize("n,S,k,R,kind,parts", [(700, 1300, 6, 3, "iid", 2), (1024, 2100, 6, 3, "diverged", 4),
+                                                 (300, 900, 4, 1, "iid", 3), (64, 700, 4, 3, "evolved", 2)])
+def test_site_shards_reproduce_single_handle_bitwise(packaged, engine, n, S, k, R, kind, parts):
+    """The multi-GPU protocol with every shard on this one GPU: contiguous CHUNK-aligned site blocks, the fp32
+    chain handed from block to block, chunk sums added in the fixed order -> the SAME BITS as one handle."""
+    from dmphyclus_b200.engine import Engine
+    from dmphyclus_b200.sharded import CHUNK
+    p = Problem(packaged, n, S, k, R, kind, seed=S)
+    al = engine.getConvertedAlignment(list("atcg"), p.chars)
+    h, want = p.create(engine)
+    per = -(-(-(-S // parts)) // CHUNK) * CHUNK
+    shards = []
+    for i in range(parts):
+        b0, b1 = min(S, i * per), min(S, (i + 1) * per)
+        if b1 > b0:
+            e = Engine(site_begin=b0, sites_total=S)
+            r = e.logLikCpp(p.edge, p.mrcas, p.pi, p.W[4], p.B[4], 1, al[:, b0:b1], n, b1 - b0, 5, 5, deferred=True)
+            assert np.isnan(r["logLik"])
+            shards.append((e, r["solutionPointer"]))
+
+    def reduce():
+        carry = np.zeros(R, np.float32)
+        chunks = []
+        for e, hh in shards:
+            carry = e.shard_chain(hh, carry)
+        for e, hh in shards:
+            chunks.append(e.shard_finish(hh))
+        return engine.reduce_chunks(np.concatenate(chunks))
+
+    assert reduce() == want
+    # a proposal on every shard, then the same exchange
+    want2 = engine.newBetweenTransProbsLogLik(h, p.W[4], p.B[7], 1, 8, p.pi)
+    for e, hh in shards:
+        e.newBetweenTransProbsLogLik(hh, p.W[4], p.B[7], 1, 8, p.pi)
+    assert reduce() == want2
+    assert np.array_equal(np.concatenate([e.site_logliks(hh) for e, hh in shards]), engine.site_logliks(h))
+    for e, hh in shards:
+        e.finalDeallocate(hh)
+    engine.finalDeallocate(h)
+
+
+# ---------------------------------------------------------------------------------------------- full size
+@pytest.mark.parametrize("kind", ["evolved", "iid"])
+def test_config2_full_size_against_oracle(packaged, engine, kind):
+    """BASELINE.json config 2 at its full size (1,000 seqs x 10,000 sites, 20 clusters, R = 3): the dense CPU
+    oracle still finishes in seconds there, so this is a direct comparison, plus size-independent properties."""
+    from oracle.oracle import Oracle
+    p = Problem(packaged, 1000, 10000, 20, 3, kind, seed=2001)
+    orc = Oracle(threads=4)
+    hg, lg = p.create(engine)
+    ho, lo = p.create(orc)
+    assert rel(lg, lo) < TOL, (lg, lo)
+    sg, eg = engine.partial(hg, p.n)
+    so, eo = orc.partial(ho, p.n)
+    assert np.array_equal(sg, so)
+    assert np.allclose(eg, eo, rtol=2e-7, atol=0)
+    site = engine.site_logliks(hg)
+    assert abs(site.sum() - lg) <= 1e-12 * abs(lg)              # the total is the sum of the per-site terms
+    assert engine.recomputeAll(hg, p.W[4], p.B[4], p.pi) == lg   # idempotent and deterministic
+    # a proposal that is rolled back leaves the value unchanged; one that is kept matches the oracle
+    a = engine.newWithinTransProbsLogLik(hg, p.W[1], p.B[4], 1, 2, p.pi)
+    b = orc.newWithinTransProbsLogLik(ho, p.W[1], p.B[4], 1, 2, p.pi)
+    assert rel(a, b) < TOL
+    engine.RestorePreviousConfig(hg, np.zeros((1, 2), np.int32), 5, 5, False, p.mrcas, False)
+    assert engine.recomputeAll(hg, p.W[4], p.B[4], p.pi) == lg
+    engine.finalDeallocate(hg)
+    orc.finalDeallocate(ho)
+
+
+def test_site_order_and_duplication_properties(packaged):
+    """Textbook reduction (no cross-locus carry): per-site terms are a function of the site column alone, so
+    permuting the columns permutes them and duplicating the alignment doubles the total."""
+    from dmphyclus_b200.engine import Engine
+    eng = Engine(quirk_carry=False)
+    p = Problem(packaged, 2000, 3000, 10, 3, "iid", seed=77)
+    al = eng.getConvertedAlignment(list("atcg"), p.chars)
+    perm = np.random.default_rng(1).permutation(p.S)
+
+    def run(a):
+        r = eng.logLikCpp(p.edge, p.mrcas, p.pi, p.W[4], p.B[4], 1, a, p.n, a.shape[1], 5, 5)
+        s = eng.site_logliks(r["solutionPointer"])
+        eng.finalDeallocate(r["solutionPointer"])
+        return r["logLik"], s
+
+    l0, s0 = run(al)
+    l1, s1 = run(np.ascontiguousarray(al[:, perm]))
+    assert np.array_equal(s1, s0[perm])
+    l2, s2 = run(np.concatenate([al, al], axis=1))
+    assert np.array_equal(s2[:p.S], s0) and np.array_equal(s2[p.S:], s0)
+    assert rel(l2, 2 * l0) < 1e-13 and rel(l1, l0) < 1e-13

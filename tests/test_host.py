@@ -1,0 +1,81 @@
+"""Host-side logic that needs no GPU: tree utilities, synthetic generators, the restated MCMC driver (over the
+oracle), priors."""
+import math
+
+import numpy as np
+import pytest
+
+from dmphyclus_b200 import chain, synth
+from dmphyclus_b200.phylo import Phylo, check_clades, cluster_mrcas
+from dmphyclus_b200.workloads import Problem
+
+
+@pytest.mark.parametrize("shape", ["random", "balanced", "caterpillar"])
+@pytest.mark.parametrize("n", [2, 3, 17, 256])
+def test_random_tree_is_ape_style(n, shape):
+    e = synth.random_tree(n, np.random.default_rng(n), shape)
+    assert e.shape == (2 * n - 2, 2) and e[0, 0] == n + 1
+    assert sorted(e[:, 1]) == [v for v in range(1, 2 * n) if v != n + 1]          # every non-root vertex has one parent
+    assert np.all(np.bincount(e[:, 0])[n + 1:] == 2) and np.all(e[:, 0] > n)     # strictly bifurcating
+    phy = Phylo(e, n)
+    assert sorted(phy.descendants(phy.root)) == list(range(1, n + 1))
+    if shape == "caterpillar":
+        assert phy.depth().max() == n - 1
+
+
+def test_clusters_are_disjoint_clades():
+    n, k = 200, 9
+    e = synth.random_tree(n, np.random.default_rng(5))
+    mrcas, clus = synth.pick_clusters(e, n, k)
+    phy = Phylo(e, n)
+    assert len(mrcas) == k and set(clus) == set(range(1, k + 1)) and check_clades(phy, clus)
+    assert cluster_mrcas(phy, clus) == mrcas
+    assert cluster_mrcas(phy, np.ones(n, int)) == [n]        # the reference's single-cluster quirk (DMphyClusSource.R:78-80)
+
+
+def test_alignments(packaged):
+    rng = np.random.default_rng(3)
+    a = synth.iid_alignment(50, 4000, rng)
+    assert set(np.unique(a)) <= set(b"atcgnryswkm")
+    assert 0.005 < (a == ord("n")).mean() < 0.02
+    e = synth.random_tree(30, rng)
+    mrcas, _ = synth.pick_clusters(e, 30, 3)
+    b = synth.evolve_alignment(e, 30, 500, packaged["within"][4], packaged["between"][4], mrcas, synth.LIM_PROBS, rng)
+    assert b.shape == (30, 500) and set(np.unique(b)) <= set(b"atcg")
+    assert (b == b[0]).all(0).mean() > 0.5        # short branches: most columns are constant
+
+
+def test_clus_ind_log_prior():
+    """clusIndLogPrior (DMphyClusInterface.R:147-162) against the closed form for two clusters."""
+    c = np.array([1, 1, 1, 2, 2])
+    a = 2.5
+    want = (math.lgamma(6) - math.lgamma(4) - math.lgamma(3)
+            + math.lgamma(a + 3) + math.lgamma(a + 2) - math.lgamma(2 * a + 5) - (2 * math.lgamma(a) - math.lgamma(2 * a)))
+    assert abs(chain.clusIndLogPrior(c, a) - want) < 1e-12
+    assert chain.clusIndLogPrior(np.array([7, 7, 7, 9, 9]), a) == chain.clusIndLogPrior(c, a)
+
+
+def test_chain_runs_and_is_reproducible(oracle, packaged):
+    p = Problem(packaged, 30, 80, 4, 3, "evolved", seed=8)
+    st = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
+                             scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
+    al = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    a, calls = chain.run_chain(oracle, al, p.edge, p.clus, 100.0, st, 12, seed=4)
+    b, _ = chain.run_chain(oracle, al, p.edge, p.clus, 100.0, st, 12, seed=4)
+    assert calls >= 12 * 6
+    for x, y in zip(a, b):
+        assert np.array_equal(x["clusInd"], y["clusInd"]) and x["logLik"] == y["logLik"]
+    for x in a:       # every sample is a valid clade partition of the sampled tree, and its logLik is the true one
+        assert check_clades(Phylo(x["edge"], p.n), x["clusInd"])
+    last = a[-1]
+    phy = Phylo(last["edge"], p.n)
+    r = oracle.logLikCpp(last["edge"], last["clusterNodeIndices"], p.pi, p.W[last["withinMatListIndex"] - 1],
+                         p.B[last["betweenMatListIndex"] - 1], 1, al, p.n, p.S, 1, 1)
+    oracle.finalDeallocate(r["solutionPointer"])
+    assert abs(r["logLik"] - last["logLik"]) <= 1e-12 * abs(last["logLik"])
+
+
+def test_workload_shapes_match_baseline():
+    from dmphyclus_b200.workloads import CONFIGS
+    assert CONFIGS["config2"] == (1000, 10000, 20, 3) and CONFIGS["config3"] == (10000, 30000, 100, 3)
+    assert CONFIGS["config4"][:2] == (5000, 5000) and CONFIGS["config5"][:2] == (100000, 1500)
