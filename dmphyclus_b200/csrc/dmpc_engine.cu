@@ -31,7 +31,25 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(DMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
   } while (0)
 
-struct HostResult { double ll; int overflow; int badCells; };
+struct HostResult { double ll; int overflow; int badCells; int nact; };
+
+// Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
+// and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
+// a logLikFromClusInd-style create/evaluate/destroy cycle; handles borrow a pack and give it back.
+struct ResPack {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  Task* h_tasks = nullptr;       // pinned
+  int32_t* h_curList = nullptr;  // pinned
+  HostResult* h_res = nullptr;   // pinned
+  size_t cap = 0;                // internal vertices the pinned buffers can hold
+};
+struct DeviceCtx {
+  bool checked = false;
+  std::vector<ResPack> freePacks;
+};
+std::mutex g_ctxMutex;
+DeviceCtx g_ctx[64];
 
 }  // namespace
 
@@ -40,7 +58,8 @@ struct dmpc_tree {
   int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nChunks = 0;
   bool quirk = true, deferred = false, alive = true;
   int device = 0, siteBegin = 0, sitesTotal = 0;
-  cudaStream_t stream = nullptr;
+  ResPack pack;
+  cudaStream_t stream = nullptr;                       // = pack.stream
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevView dv{};
   RootView rv{};
@@ -72,6 +91,51 @@ struct dmpc_tree {
 
 namespace {
 
+int acquirePack(dmpc_tree* t) {
+  DeviceCtx& cx = g_ctx[t->device & 63];
+  {
+    std::lock_guard<std::mutex> lk(g_ctxMutex);
+    if (!cx.checked) {
+      int major = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, t->device));
+      if (major < 10) return fail(DMPC_ERR_CUDA, "device is not sm_100-class; kernels are built for sm_100a only");
+      cudaMemPool_t pool;
+      CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, t->device));
+      unsigned long long keep = ~0ULL;                    // keep freed HBM cached in the pool between handles
+      CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      cx.checked = true;
+    }
+    if (!cx.freePacks.empty()) { t->pack = cx.freePacks.back(); cx.freePacks.pop_back(); }
+  }
+  ResPack& p = t->pack;
+  if (!p.stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    for (auto& e : p.ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_res, sizeof(HostResult), cudaHostAllocDefault));
+  }
+  if (p.cap < (size_t)t->nInt) {
+    if (p.h_tasks) cudaFreeHost(p.h_tasks);
+    if (p.h_curList) cudaFreeHost(p.h_curList);
+    p.h_tasks = nullptr; p.h_curList = nullptr; p.cap = 0;
+    const size_t cap = std::max<size_t>(1024, (size_t)t->nInt * 5 / 4);
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_curList, cap * sizeof(int32_t), cudaHostAllocDefault));
+    p.cap = cap;
+  }
+  t->stream = p.stream;
+  for (int i = 0; i < 5; i++) t->ev[i] = p.ev[i];
+  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res;
+  return DMPC_OK;
+}
+
+void releasePack(dmpc_tree* t) {
+  if (!t->pack.stream) return;
+  std::lock_guard<std::mutex> lk(g_ctxMutex);
+  g_ctx[t->device & 63].freePacks.push_back(t->pack);
+  t->pack = ResPack{};
+  t->stream = nullptr;
+}
+
 int ensureDevice(dmpc_tree* t) {
   CUDA_TRY(cudaSetDevice(t->device));
   return DMPC_OK;
@@ -83,7 +147,7 @@ int allocSlot(dmpc_tree* t, int slot) {
   const size_t n = (size_t)t->nInt * t->R * t->Sp;
   if ((rc = t->alloc(&t->dv.part[slot], n * 4))) return rc;
   if ((rc = t->alloc(&t->dv.expo[slot], n))) return rc;
-  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->R * t->T * t->nInt))) return rc;
+  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->T * t->nInt))) return rc;
   return DMPC_OK;
 }
 
@@ -170,9 +234,16 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     const int nLevels = (int)t->levelStart.size() - 1;
     for (int l = 0; l < nLevels; l++) {
       const int n = t->levelStart[l + 1] - t->levelStart[l];
-      const long long blocks = (long long)n * t->R * t->T;
-      if (blocks > 2147483647LL) return fail(DMPC_ERR_ARG, "level too wide for one launch");
-      k_prune_level<<<(unsigned)blocks, TILE, 0, t->stream>>>(t->dv, t->d_tasks + t->levelStart[l]);
+      if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
+      const dim3 grid((unsigned)n, (unsigned)t->T);
+      const Task* lt = t->d_tasks + t->levelStart[l];
+      switch (t->R) {
+        case 1: k_prune_level<1><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 2: k_prune_level<2><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 3: k_prune_level<3><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 4: k_prune_level<4><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        default: k_prune_level<0><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+      }
       t->st.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -190,13 +261,18 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
 }
 
 int launchGather(dmpc_tree* t) {
-  k_root_gather<<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
+  CUDA_TRY(cudaMemsetAsync(t->rv.nact, 0, sizeof(int), t->stream));
+  if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
+  else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
   t->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
 }
 
-size_t chainSmem(const dmpc_tree* t) { return (size_t)64 * t->rv.Q * (t->rv.RP / 4) + 8 * ((size_t)t->rv.Q + 1); }
+size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 4) rows of RP floats + 1 marker byte per row
+  const size_t cap = 2 * (size_t)t->rv.Q + 4;
+  return 2 * cap * t->rv.RP * sizeof(float) + 2 * cap;
+}
 
 int launchChain(dmpc_tree* t) {
   const size_t smem = chainSmem(t);
@@ -225,7 +301,9 @@ int gatherWithGrowth(dmpc_tree* t) {
     int rc;
     if ((rc = launchGather(t))) return rc;
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
+    t->st.last_active_tiles = t->h_res->nact;
     if (t->h_res->overflow <= t->rv.Kcap) return DMPC_OK;
     int k = t->rv.Kcap;
     while (k < t->h_res->overflow) k *= 2;
@@ -252,7 +330,9 @@ int rootStage(dmpc_tree* t, double* ll) {
     CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->ll, t->rv.result, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
+    t->st.last_active_tiles = t->h_res->nact;
     if (t->h_res->overflow <= t->rv.Kcap) {
       float ms = 0;
       cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
@@ -271,14 +351,11 @@ int rootStage(dmpc_tree* t, double* ll) {
 void destroy(dmpc_tree* t) {
   if (!t) return;
   cudaSetDevice(t->device);
-  if (t->stream) cudaStreamSynchronize(t->stream);
-  for (void* p : t->allocs) cudaFreeAsync(p, t->stream);
-  if (t->stream) cudaStreamSynchronize(t->stream);
-  if (t->h_tasks) cudaFreeHost(t->h_tasks);
-  if (t->h_curList) cudaFreeHost(t->h_curList);
-  if (t->h_res) cudaFreeHost(t->h_res);
-  for (auto& e : t->ev) if (e) cudaEventDestroy(e);
-  if (t->stream) cudaStreamDestroy(t->stream);
+  if (t->stream) {
+    for (void* p : t->allocs) cudaFreeAsync(p, t->stream);
+    cudaStreamSynchronize(t->stream);                  // the pack (stream, pinned buffers) goes back idle
+  }
+  releasePack(t);
   {
     std::lock_guard<std::mutex> lk(g_constMutex);
     if (g_constOwner[t->device & 63] == t) g_constOwner[t->device & 63] = nullptr;
@@ -352,19 +429,8 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   int rc = DMPC_OK;
   auto body = [&]() -> int {
     CUDA_TRY(cudaSetDevice(t->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, t->device));
-    if (prop.major < 10) return fail(DMPC_ERR_CUDA, "device is not sm_100-class; kernels are built for sm_100a only");
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, t->device));
-    unsigned long long keep = ~0ULL;                      // keep freed HBM cached in the pool between handles
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
-    for (auto& e : t->ev) CUDA_TRY(cudaEventCreate(&e));
-    CUDA_TRY(cudaHostAlloc((void**)&t->h_tasks, (size_t)t->nInt * sizeof(Task), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc((void**)&t->h_curList, (size_t)t->nInt * sizeof(int32_t), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc((void**)&t->h_res, sizeof(HostResult), cudaHostAllocDefault));
     int r2;
+    if ((r2 = acquirePack(t))) return r2;
     if ((r2 = t->alloc(&t->d_tipmask, (size_t)t->N * t->Sp))) return r2;
     if ((r2 = t->alloc(&t->d_lut, (size_t)2 * t->R * 64))) return r2;
     if ((r2 = t->alloc(&t->d_tasks, (size_t)t->nInt))) return r2;
@@ -384,6 +450,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     if ((r2 = t->alloc(&t->rv.chunk, (size_t)t->nChunks))) return r2;
     if ((r2 = t->alloc(&t->rv.ticket, (size_t)1))) return r2;
     if ((r2 = t->alloc(&t->rv.overflow, (size_t)2))) return r2;
+    if ((r2 = t->alloc(&t->rv.nact, (size_t)1))) return r2;
     if ((r2 = t->alloc(&t->rv.result, (size_t)1))) return r2;
     if ((r2 = allocElist(t, 8))) return r2;
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
@@ -596,16 +663,16 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   const size_t n = (size_t)t->R * t->Sp;
   std::vector<double> hs(n * 4);
   std::vector<float> he(n);
-  std::vector<uint8_t> hf((size_t)t->R * t->T);
+  std::vector<uint8_t> hf((size_t)t->T);
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[slot] + (size_t)idx * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(he.data(), t->dv.expo[slot] + (size_t)idx * n, n * sizeof(float), cudaMemcpyDeviceToHost));
-  for (int b = 0; b < t->R * t->T; b++)
+  for (int b = 0; b < t->T; b++)
     CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nInt + idx, 1, cudaMemcpyDeviceToHost));
   for (int s = 0; s < t->S; s++)
     for (int r = 0; r < t->R; r++) {
       for (int k = 0; k < 4; k++) sol[((size_t)s * t->R + r) * 4 + k] = hs[((size_t)r * t->Sp + s) * 4 + k];
-      expo[(size_t)s * t->R + r] = hf[r * t->T + s / TILE] ? he[(size_t)r * t->Sp + s] : 0.0f;
+      expo[(size_t)s * t->R + r] = hf[s / TILE] ? he[(size_t)r * t->Sp + s] : 0.0f;
     }
   return DMPC_OK;
 }

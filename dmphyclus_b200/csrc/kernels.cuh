@@ -6,9 +6,9 @@
 //                                           (internal vertex, rate, site); two slots s = 0,1 so that a
 //                                           rejected proposal rolls back by flipping a per-vertex slot bit
 //   expo[s]  f32    [N-1][R][Sp]            per-vertex rescale exponents (IntermediateNode.cpp:63: a FLOAT)
-//   flag[s]  u8     [R*T][N-1]              1 when any site of the 128-site tile rescaled at that vertex;
-//                                           expo tiles whose flag is 0 are never written nor read
-// One thread owns one (site, rate) of one vertex: its two child loads are 256-bit (LDG.E.256), consecutive
+//   flag[s]  u8     [T][N-1]                1 when any (site, rate) of the 128-site tile rescaled at that vertex;
+//                                           expo tiles whose flag is 0 are never read (and, for R <= 4, never written)
+// One thread owns one site of one vertex for all R rates: its child loads are 256-bit (LDG.E.256), consecutive
 // threads touch consecutive 32-byte elements, so every warp request is 1 KB fully coalesced.  Per update the
 // compulsory traffic is 2 x 32 B read (internal children; 1 B for a tip) + 32 B written: 68-96 B, against
 // ~70 fp64 operations — HBM-bound, no tensor cores (a 4x4 mat-vec has nothing to tile).
@@ -62,6 +62,7 @@ struct RootView {
   double* chunk;                // [nChunks] sums of CHUNK consecutive sites
   unsigned* ticket;
   int* overflow;
+  int* nact;                    // number of site tiles holding a rescaled site (set by root_gather)
   double* result;
   int Kcap, RP, Q;              // Q = rows per chain staging chunk
 };
@@ -82,65 +83,117 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
                    __dmul_rn(Pi[3], x3));
 }
 
-// IntermediateNode.cpp:58-64: if max < 1e-150, divide by it and OVERWRITE the exponent with (float)log(max)
-__device__ __forceinline__ void rescale(double& s0, double& s1, double& s2, double& s3, float& e) {
-  double m = fmax(fmax(s0, s1), fmax(s2, s3));
-  if (m < 1e-150) {
-    s0 = s0 / m; s1 = s1 / m; s2 = s2 / m; s3 = s3 / m;
+// ------------------------------------------------------------------------------------------------
+// K2 prune_level: all dirty vertices of one level x all sites; one thread owns one site of one vertex for
+// ALL rate categories (the tip masks and the task descriptor are shared by the categories, and R x 2 x 32 B
+// of child loads are in flight per thread before the first use).
+// Replaces IntermediateNode::ComputeSolutions/ComputeSolution (IntermediateNode.cpp:26-71) driven by
+// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, site tiles), 128 threads.
+// RT = compile-time number of rate categories (1..4); RT = 0 handles any R <= RMAX one category at a time.
+
+// one category of one (vertex, site): sol = (P*c0) % (P*c1) with the reference's two rescale checks.
+// "max(sol) < 1e-150" is tested as "every entry < 1e-150" (no NaNs on this path), the max itself is only
+// needed inside the rare branch.
+__device__ __forceinline__ void node_update(const double* __restrict__ P, const double* __restrict__ lutr, bool tip0,
+                                            bool tip1, unsigned ma, unsigned mb, const double (&a)[4],
+                                            const double (&b)[4], double (&s)[4], float& e) {
+  if (tip0) {
+    const double2 u = *reinterpret_cast<const double2*>(lutr + 4 * ma), w = *reinterpret_cast<const double2*>(lutr + 4 * ma + 2);
+    s[0] = u.x; s[1] = u.y; s[2] = w.x; s[3] = w.y;               // ones % y == y exactly
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[i] = row4(P + 4 * i, a[0], a[1], a[2], a[3]);
+  }
+  if (s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150) {   // after child 0 (IntermediateNode.cpp:58-64)
+    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
+    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
+    e = (float)log(m);
+  }
+  if (tip1) {
+    const double2 u = *reinterpret_cast<const double2*>(lutr + 4 * mb), w = *reinterpret_cast<const double2*>(lutr + 4 * mb + 2);
+    s[0] = __dmul_rn(s[0], u.x); s[1] = __dmul_rn(s[1], u.y); s[2] = __dmul_rn(s[2], w.x); s[3] = __dmul_rn(s[3], w.y);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[i] = __dmul_rn(s[i], row4(P + 4 * i, b[0], b[1], b[2], b[3]));
+  }
+  if (s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150) {   // after child 1: OVERWRITES the exponent
+    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
+    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
     e = (float)log(m);
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2 prune_level: all dirty vertices of one level x all (rate, site) pairs.
-// Replaces IntermediateNode::ComputeSolutions/ComputeSolution (IntermediateNode.cpp:26-71) driven by
-// AugTree::TrySolve (AugTree.cpp:114-134).  grid = tasks * R * T blocks of 128 threads.
+template <int RT>
 __global__ void __launch_bounds__(TILE) k_prune_level(DevView v, const Task* __restrict__ tasks) {
-  __shared__ double s_lut[64];
-  const int RT = v.R * v.T;
-  const int task = blockIdx.x / RT;
-  const int blk = blockIdx.x - task * RT;
-  const int r = blk / v.T;
-  const int tile = blk - r * v.T;
-  const Task t = tasks[task];
-  const int set = (t.flags & TF_WITHIN) ? 1 : 0;
-  if (t.flags & (TF_C0TIP | TF_C1TIP)) {
-    if (threadIdx.x < 64) s_lut[threadIdx.x] = v.lut[(size_t)(set * v.R + r) * 64 + threadIdx.x];
+  constexpr int RB = RT > 0 ? RT : 1;                         // categories whose loads are batched
+  __shared__ __align__(16) double s_lut[(RT > 0 ? RT : RMAX) * 64];
+  const int R = RT > 0 ? RT : v.R;
+  const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks) + blockIdx.x);   // Task {out, c0, c1, flags}
+  const int fl = tk.w;
+  const int tile = blockIdx.y;
+  const int site = tile * TILE + threadIdx.x;
+  const int set = (fl & TF_WITHIN) ? 1 : 0;
+  const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
+  const size_t Sp = (size_t)v.Sp, rstride = Sp * 4;            // doubles between consecutive categories
+  unsigned ma = 0, mb = 0;
+  if (tip0) ma = v.tipmask[(size_t)tk.y * Sp + site];
+  if (tip1) mb = v.tipmask[(size_t)tk.z * Sp + site];
+  const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk.y * R * Sp + site) * 4;
+  const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk.z * R * Sp + site) * 4;
+  const int os = (fl & TF_OUTSLOT) ? 1 : 0;
+  const size_t o = (size_t)tk.x * R * Sp + site;
+  double* po = v.partOf(os) + o * 4;
+  float* pe = v.expoOf(os) + o;
+
+  double a[RB][4], b[RB][4];
+  if (RT > 0) {                                                // every child load is issued before any arithmetic
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
+      if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
+    }
+  }
+  if (tip0 | tip1) {
+    for (int i = threadIdx.x; i < R * 64; i += TILE) s_lut[i] = v.lut[(size_t)set * R * 64 + i];
     __syncthreads();
   }
-  const int site = tile * TILE + threadIdx.x;
-  const double* P = c_P[set][r];
-
-  // issue both children's loads before any arithmetic
-  double a0, a1, a2, a3, b0, b1, b2, b3;
-  unsigned ma = 0, mb = 0;
-  if (t.flags & TF_C0TIP) ma = v.tipmask[(size_t)t.c0 * v.Sp + site];
-  else ld256(v.partOf(t.flags & TF_C0SLOT) + (((size_t)t.c0 * v.R + r) * v.Sp + site) * 4, a0, a1, a2, a3);
-  if (t.flags & TF_C1TIP) mb = v.tipmask[(size_t)t.c1 * v.Sp + site];
-  else ld256(v.partOf(t.flags & TF_C1SLOT) + (((size_t)t.c1 * v.R + r) * v.Sp + site) * 4, b0, b1, b2, b3);
-
-  double s0, s1, s2, s3;
-  float e = 0.0f;
-  if (t.flags & TF_C0TIP) { const double* y = s_lut + 4 * ma; s0 = y[0]; s1 = y[1]; s2 = y[2]; s3 = y[3]; }
-  else { s0 = row4(P, a0, a1, a2, a3); s1 = row4(P + 4, a0, a1, a2, a3); s2 = row4(P + 8, a0, a1, a2, a3); s3 = row4(P + 12, a0, a1, a2, a3); }
-  rescale(s0, s1, s2, s3, e);                                   // after child 0 (ones % y == y exactly)
-  if (t.flags & TF_C1TIP) {
-    const double* y = s_lut + 4 * mb;
-    s0 = __dmul_rn(s0, y[0]); s1 = __dmul_rn(s1, y[1]); s2 = __dmul_rn(s2, y[2]); s3 = __dmul_rn(s3, y[3]);
+  bool rescaled = false;
+  if (RT > 0) {
+    float e[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      double s[4];
+      e[r] = 0.0f;
+      node_update(c_P[set][r], s_lut + 64 * r, tip0, tip1, ma, mb, a[r], b[r], s, e[r]);
+      st256(po + r * rstride, s[0], s[1], s[2], s[3]);
+      rescaled |= e[r] != 0.0f;
+    }
+    const int any = __syncthreads_or(rescaled);
+    if (any) {
+#pragma unroll
+      for (int r = 0; r < RB; r++) pe[r * Sp] = e[r];
+    }
+    if (threadIdx.x == 0) {
+      v.flagOf(os)[(size_t)tile * v.nInt + tk.x] = (uint8_t)(any != 0);
+      if (tile == 0) v.cur[tk.x] = (uint8_t)os;
+    }
   } else {
-    s0 = __dmul_rn(s0, row4(P, b0, b1, b2, b3)); s1 = __dmul_rn(s1, row4(P + 4, b0, b1, b2, b3));
-    s2 = __dmul_rn(s2, row4(P + 8, b0, b1, b2, b3)); s3 = __dmul_rn(s3, row4(P + 12, b0, b1, b2, b3));
-  }
-  rescale(s0, s1, s2, s3, e);                                   // after child 1: overwrites
-
-  const int os = (t.flags & TF_OUTSLOT) ? 1 : 0;
-  const size_t o = ((size_t)t.out * v.R + r) * v.Sp + site;
-  st256(v.partOf(os) + o * 4, s0, s1, s2, s3);
-  const int any = __syncthreads_or(e != 0.0f);
-  if (any) v.expoOf(os)[o] = e;
-  if (threadIdx.x == 0) {
-    v.flagOf(os)[(size_t)blk * v.nInt + t.out] = (uint8_t)(any != 0);
-    if (blk == 0) v.cur[t.out] = (uint8_t)os;
+#pragma unroll 1
+    for (int r = 0; r < R; r++) {
+      double s[4];
+      float e = 0.0f;
+      if (!tip0) ld256(pa + r * rstride, a[0][0], a[0][1], a[0][2], a[0][3]);
+      if (!tip1) ld256(pb + r * rstride, b[0][0], b[0][1], b[0][2], b[0][3]);
+      node_update(c_P[set][r], s_lut + 64 * r, tip0, tip1, ma, mb, a[0], b[0], s, e);
+      st256(po + r * rstride, s[0], s[1], s[2], s[3]);
+      pe[r * Sp] = e;                                          // generic path: exponents always written
+      rescaled |= e != 0.0f;
+    }
+    const int any = __syncthreads_or(rescaled);
+    if (threadIdx.x == 0) {
+      v.flagOf(os)[(size_t)tile * v.nInt + tk.x] = (uint8_t)(any != 0);
+      if (tile == 0) v.cur[tk.x] = (uint8_t)os;
+    }
   }
 }
 
@@ -161,68 +214,91 @@ __global__ void k_prepare_masks(uint8_t* mask, int N, int S, int Sp, int* bad) {
 
 // ------------------------------------------------------------------------------------------------
 // K4a root_gather: per site tile, dot(root, limProbs) and the per-site list of non-zero rescale exponents in
-// vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read.
+// vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
+// the flagged vertices of each 128-vertex window are compacted (in id order) into shared memory, then visited
+// four at a time so that their exponent loads overlap.
+template <int RP>
 __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
-  __shared__ unsigned s_ballot[TILE / 32];
-  __shared__ int s_cnt[RMAX][TILE];
-  const int tile = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_list[TILE];
+  __shared__ int s_wcnt[TILE / 32];
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int site = tile * TILE + tid;
   const bool valid = site < v.S;
+  const int R = v.R;
+  const size_t Sp = (size_t)v.Sp;
   const int rootSlot = v.cur[0];
-  for (int r = 0; r < v.R; r++) {
-    double a0, a1, a2, a3;
-    ld256(v.partOf(rootSlot) + ((size_t)r * v.Sp + site) * 4, a0, a1, a2, a3);
-    // arma::dot (op_dot::direct_dot_arma): two interleaved accumulators
-    rv.rootdot[(size_t)r * v.Sp + site] =
-        __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
+#pragma unroll
+  for (int r = 0; r < RP; r++)
+    if (r < R) {
+      double a0, a1, a2, a3;
+      ld256(v.partOf(rootSlot) + ((size_t)r * Sp + site) * 4, a0, a1, a2, a3);
+      // arma::dot (op_dot::direct_dot_arma): two interleaved accumulators
+      rv.rootdot[(size_t)r * Sp + site] =
+          __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
+    }
+  int k[RP];
+#pragma unroll
+  for (int r = 0; r < RP; r++) k[r] = 0;
+  float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
+  const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nInt : nullptr;
+  const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nInt : nullptr;
+  for (int base = 0; base < v.nInt; base += TILE) {
+    const int nd = base + tid;
+    bool f = false;
+    int slot = 0;
+    if (nd < v.nInt) { slot = v.cur[nd]; f = (slot ? f1[nd] : f0[nd]) != 0; }
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int off = __popc(bal & ((1u << lane) - 1)), n = 0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
+    if (f) s_list[off] = (nd << 1) | slot;
+    __syncthreads();
+    for (int i = 0; i < n; i += 4) {
+      float e[4][RP];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int ent = s_list[min(i + j, n - 1)];
+        const float* src = v.expoOf(ent & 1) + (size_t)(ent >> 1) * R * Sp + site;
+#pragma unroll
+        for (int r = 0; r < RP; r++) e[j][r] = (r < R && i + j < n) ? src[r * Sp] : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int r = 0; r < RP; r++)
+          if (e[j][r] != 0.0f) {
+            if (k[r] < rv.Kcap && valid) myList[(size_t)k[r] * RP + r] = e[j][r];
+            k[r]++;
+          }
+    }
+    __syncthreads();
   }
   int kmax = 0;
-  for (int r = 0; r < v.R; r++) {
-    int k = 0;
-    const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)(r * v.T + tile) * v.nInt : nullptr;
-    const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)(r * v.T + tile) * v.nInt : nullptr;
-    for (int base = 0; base < v.nInt; base += TILE) {
-      const int nd = base + tid;
-      bool f = false;
-      if (nd < v.nInt) f = (v.cur[nd] ? f1[nd] : f0[nd]) != 0;
-      const unsigned b = __ballot_sync(0xffffffffu, f);
-      if ((tid & 31) == 0) s_ballot[tid >> 5] = b;
-      __syncthreads();
-      for (int w = 0; w < TILE / 32; w++) {
-        unsigned bits = s_ballot[w];
-        while (bits) {
-          const int node = base + 32 * w + __ffs(bits) - 1;
-          bits &= bits - 1;
-          const float e = v.expoOf(v.cur[node])[((size_t)node * v.R + r) * v.Sp + site];
-          if (e != 0.0f) {
-            if (k < rv.Kcap && valid) rv.elist[((size_t)site * rv.Kcap + k) * rv.RP + r] = e;
-            k++;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    s_cnt[r][tid] = k;
-    kmax = max(kmax, k);
-  }
+#pragma unroll
+  for (int r = 0; r < RP; r++) kmax = max(kmax, k[r]);
   if (valid) {
     const int kk = min(kmax, rv.Kcap);
-    for (int r = 0; r < rv.RP; r++) {
-      const int kr = r < v.R ? min(s_cnt[r][tid], rv.Kcap) : 0;
-      for (int j = kr; j < kk; j++) rv.elist[((size_t)site * rv.Kcap + j) * rv.RP + r] = 0.0f;
-    }
+#pragma unroll
+    for (int r = 0; r < RP; r++)
+      for (int j = min(k[r], rv.Kcap); j < kk; j++) myList[(size_t)j * RP + r] = 0.0f;   // zero padding: x + 0.0f == x
     rv.kmax[site] = kmax;
     if (kmax > rv.Kcap) atomicMax(rv.overflow, kmax);
   } else {
     rv.kmax[site] = 0;
   }
+  const int anyActive = __syncthreads_or(valid && kmax > 0);
+  if (tid == 0 && anyActive) atomicAdd(rv.nact, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4b chain: AugTree.cpp:306-318 keeps ONE fp32 exponent vector across all loci (it is never reset), so the
 // per-site values depend on the site order through a sequential chain of fp32 additions whose rounding has to
-// be reproduced bit for bit.  One block: every thread compacts the active sites, then
-// thread 0 walks them in order while the other warps stage the next chunk of exponent rows in shared memory.
+// be reproduced bit for bit.  One block: every thread compacts the active sites (those
+// that rescaled anywhere), then thread 0 walks their exponent rows as ONE flat stream while the other warps
+// stage the next chunk of rows (and the end-of-site markers) in shared memory.  Categories beyond R ride along
+// as -inf so that the hot loop needs no guards.  When no site rescaled the kernel returns at once.
 template <int RP>
 __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   extern __shared__ float4 s_dyn[];
@@ -231,6 +307,10 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   __shared__ int s_total[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nth = blockDim.x;
   const int S = v.S, Q = rv.Q;
+  if (*rv.nact == 0) {                            // nothing rescaled: the vector never leaves its entry value
+    if (tid < RMAX) rv.carryOut[tid] = rv.carryIn[tid];
+    return;
+  }
 
   // phase A: ordered compaction of the sites that rescaled anywhere (kmax > 0) + row prefix
   int baseCnt = 0, baseRows = 0;
@@ -276,66 +356,84 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   if (tid == 0) rv.chunkStart[nchunks] = nact;
   __syncthreads();
 
-  // phase B
-  float4* const buf0 = s_dyn;                                     // 2 staging buffers of 2Q rows each
-  int* const offs0 = reinterpret_cast<int*>(s_dyn + (size_t)4 * Q * V);   // 2 x (Q+1) row offsets
+  // phase B.  Shared memory: 2 buffers of (2Q + 4) rows, then 2 x (2Q + 4) end-of-site markers (1 byte per row)
+  const int cap = 2 * Q + 4;
+  float4* const buf0 = s_dyn;
+  unsigned char* const end0 = reinterpret_cast<unsigned char*>(s_dyn + (size_t)2 * cap * V);
   float c[RP];
 #pragma unroll
-  for (int r = 0; r < RP; r++) c[r] = r < v.R ? rv.carryIn[r] : 0.0f;
+  for (int r = 0; r < RP; r++) c[r] = r < v.R ? rv.carryIn[r] : -INFINITY;
 
-  auto stage = [&](int ch, int ltid, int nld, int b, bool loadersOnly) {
-    float4* const bufb = buf0 + (size_t)b * 2 * Q * V;
-    int* const offb = offs0 + b * (Q + 1);
+  auto stage = [&](int ch, int ltid, int nld, int b) {
+    float4* const bufb = buf0 + (size_t)b * cap * V;
+    unsigned char* const endb = end0 + (size_t)b * cap;
     const int i0 = rv.chunkStart[ch], i1 = rv.chunkStart[ch + 1];
     const int r0 = rv.rowoff[i0], nrows = rv.rowoff[i1] - r0, ns = i1 - i0;
-    for (int k = ltid; k <= ns; k += nld) offb[k] = rv.rowoff[i0 + k] - r0;
-    if (loadersOnly) asm volatile("bar.sync 1, %0;" ::"r"(nld)); else __syncthreads();
-    for (int q = ltid; q < nrows; q += nld) {
-      int lo = 0, hi = ns;                        // last k with offs[k] <= q
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offb[mid] <= q) lo = mid; else hi = mid; }
-      const int site = rv.act[i0 + lo], j = q - offb[lo];
+    const int padded = (nrows + 3) & ~3;                      // the walker consumes rows four at a time
+    for (int q = ltid; q < padded; q += nld) {
+      if (q >= nrows) {
+#pragma unroll
+        for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        endb[q] = 0;
+        continue;
+      }
+      int lo = 0, hi = ns;                        // last k with rowoff[i0 + k] - r0 <= q
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rv.rowoff[i0 + mid] - r0 <= q) lo = mid; else hi = mid; }
+      const int site = rv.act[i0 + lo], j = q - (rv.rowoff[i0 + lo] - r0);
       const float4* src = reinterpret_cast<const float4*>(rv.elist + ((size_t)site * rv.Kcap + j) * RP);
 #pragma unroll
       for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = src[u];
+      endb[q] = (unsigned char)(q + 1 == rv.rowoff[i0 + lo + 1] - r0);
     }
   };
 
-  if (nchunks > 0) stage(0, tid, nth, 0, false);
+  if (nchunks > 0) stage(0, tid, nth, 0);
   __syncthreads();
+  int outIdx = 0;
   for (int ch = 0; ch < nchunks; ch++) {
     const int b = ch & 1;
     if (wid > 0) {
-      if (ch + 1 < nchunks) stage(ch + 1, tid - 32, nth - 32, b ^ 1, true);
+      if (ch + 1 < nchunks) stage(ch + 1, tid - 32, nth - 32, b ^ 1);
     } else if (tid == 0) {
-      const int i0 = rv.chunkStart[ch], ns = rv.chunkStart[ch + 1] - i0;
-      const float4* const bufb = buf0 + (size_t)b * 2 * Q * V;
-      const int* const offb = offs0 + b * (Q + 1);
-      for (int k = 0; k < ns; k++) {
-        const int o0 = offb[k], o1 = offb[k + 1];
-        for (int q = o0; q < o1; q++) {
+      const int i0 = rv.chunkStart[ch], i1 = rv.chunkStart[ch + 1];
+      const int nrows = rv.rowoff[i1] - rv.rowoff[i0];
+      const float4* const bufb = buf0 + (size_t)b * cap * V;
+      const unsigned* const endw = reinterpret_cast<const unsigned*>(end0 + (size_t)b * cap);
+      outIdx = i0;
+      for (int q = 0; q < nrows; q += 4) {
+        float4 x[4][V];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)(q + j) * V + u];
+        const unsigned mk = endw[q >> 2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
 #pragma unroll
           for (int u = 0; u < V; u++) {
-            const float4 x = bufb[(size_t)q * V + u];
-            c[4 * u + 0] = __fadd_rn(c[4 * u + 0], x.x); c[4 * u + 1] = __fadd_rn(c[4 * u + 1], x.y);
-            c[4 * u + 2] = __fadd_rn(c[4 * u + 2], x.z); c[4 * u + 3] = __fadd_rn(c[4 * u + 3], x.w);
+            c[4 * u + 0] = __fadd_rn(c[4 * u + 0], x[j][u].x); c[4 * u + 1] = __fadd_rn(c[4 * u + 1], x[j][u].y);
+            c[4 * u + 2] = __fadd_rn(c[4 * u + 2], x[j][u].z); c[4 * u + 3] = __fadd_rn(c[4 * u + 3], x[j][u].w);
+          }
+          if ((mk >> (8 * j)) & 0xffu) {          // last row of a site: maxExponent, exponentVec -= maxExponent
+            float m = c[0];
+#pragma unroll
+            for (int r = 1; r < RP; r++) m = fmaxf(m, c[r]);
+#pragma unroll
+            for (int r = 0; r < RP; r++) c[r] = __fsub_rn(c[r], m);
+            float4* co = reinterpret_cast<float4*>(rv.cout + (size_t)outIdx * RP);
+#pragma unroll
+            for (int u = 0; u < V; u++) co[u] = make_float4(c[4 * u], c[4 * u + 1], c[4 * u + 2], c[4 * u + 3]);
+            rv.mxo[outIdx] = m;
+            outIdx++;
           }
         }
-        float m = c[0];
-#pragma unroll
-        for (int r = 1; r < RP; r++) if (r < v.R) m = fmaxf(m, c[r]);
-#pragma unroll
-        for (int r = 0; r < RP; r++) c[r] = r < v.R ? __fsub_rn(c[r], m) : 0.0f;
-        float4* co = reinterpret_cast<float4*>(rv.cout + (size_t)(i0 + k) * RP);
-#pragma unroll
-        for (int u = 0; u < V; u++) co[u] = make_float4(c[4 * u], c[4 * u + 1], c[4 * u + 2], c[4 * u + 3]);
-        rv.mxo[i0 + k] = m;
       }
     }
     __syncthreads();
   }
   if (tid == 0) {
 #pragma unroll
-    for (int r = 0; r < RP; r++) rv.carryOut[r] = c[r];
+    for (int r = 0; r < RP; r++) rv.carryOut[r] = r < v.R ? c[r] : 0.0f;
   }
 }
 
@@ -365,7 +463,10 @@ __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mod
     float ev[RMAX];
     float mx = 0.0f;
     const int km = min(rv.kmax[s], rv.Kcap);
-    if (mode == 1) {
+    if (mode == 1 && *rv.nact == 0) {               // the chain kernel returned early: no site rescaled
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = rv.carryIn[r];
+    } else if (mode == 1) {
       const int p = rv.posIncl[s];
 #pragma unroll
       for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = p ? rv.cout[(size_t)(p - 1) * rv.RP + r] : rv.carryIn[r];

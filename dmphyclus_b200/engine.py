@@ -33,7 +33,7 @@ class Stats(C.Structure):
     _fields_ = [("updates", C.c_ulonglong), ("kernel_launches", C.c_ulonglong), ("evaluations", C.c_ulonglong),
                 ("last_eval_ms", C.c_double), ("last_prune_ms", C.c_double), ("last_updates", C.c_ulonglong),
                 ("last_prune_launches", C.c_ulonglong), ("last_levels", C.c_int), ("exponent_capacity", C.c_int),
-                ("device_bytes", C.c_ulonglong)]
+                ("device_bytes", C.c_ulonglong), ("last_active_tiles", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -269,6 +269,10 @@ class Engine:
         cout = np.zeros(8, np.float32)
         self._check(self.lib.dmpc_shard_chain(ptr, _p(cin, _f32_p), _p(cout, _f32_p)))
         return cout[:r].copy()
+
+    def shard_active(self, ptr) -> bool:
+        """True when a site of this handle rescaled in the last evaluation (its chain is not the identity)."""
+        return self.stats(ptr)["last_active_tiles"] > 0
 
     def shard_finish(self, ptr) -> np.ndarray:
         n = self.lib.dmpc_shard_num_chunks(ptr)

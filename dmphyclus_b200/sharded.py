@@ -6,8 +6,11 @@ data-path collective.  The root reduction is where ranks meet:
 
   * the reference never resets its fp32 exponent vector between loci (`/root/reference/src/AugTree.cpp:306`;
     SURVEY.md §0.2), so with more than one rate category the per-site terms form ONE sequential fp32 chain over
-    all loci.  The chain therefore hops from rank to rank in site order: rank r runs its block's chain from the
-    carry rank r-1 broadcast (R floats), then broadcasts its own;
+    all loci.  The vector only moves at sites that rescaled somewhere in the tree; a rank whose block holds no such
+    site passes it through unchanged.  Every rank first evaluates its block as if the vector entered as zeros and
+    the ranks all-gather (has-rescaled-site flag, chunk sums) in ONE collective; only when a rank before the last
+    reports a rescaled site does the chain hop through those ranks in site order (one R-float broadcast per hop)
+    before a second all-gather;
   * each rank then reduces its sites to per-256-site chunk sums; the chunk sums are all-gathered and added in a
     fixed order (`dmpc_reduce_chunks`), so the total is bit-identical for 1, 2, 4 or 8 ranks — which is what
     keeps MCMC trajectories identical across GPU counts.
@@ -58,30 +61,51 @@ class ShardedEngine:
         self.collectives = 0
 
     # ------------------------------------------------------------------ the exchange
-    def _reduce(self, ptr) -> float:
+    def _gather(self, active: bool, mine: np.ndarray):
+        """One all-gather of every rank's (active flag, chunk sums)."""
         torch, dist = self.torch, self.dist
-        R = self._R[ptr]
-        carry = np.zeros(R, np.float32)
-        if R > 1 and getattr(self.be, "quirk_carry", True):
-            buf = torch.zeros(R, dtype=torch.float32, device=self.device)
-            for r in range(self.world):               # the fp32 chain crosses the blocks in site order
-                if r == self.rank:
-                    carry = self.be.shard_chain(ptr, carry)
-                    buf.copy_(torch.from_numpy(carry))
-                if r + 1 < self.world:
-                    dist.broadcast(buf, src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
-                    self.collectives += 1
-                    if r + 1 == self.rank:
-                        carry = buf.cpu().numpy().copy()
-        mine = self.be.shard_finish(ptr)
-        width = max(self._chunks_per_rank)
-        send = torch.zeros(width, dtype=torch.float64, device=self.device)
-        send[:len(mine)] = torch.from_numpy(mine)
+        width = max(self._chunks_per_rank) + 1
+        send = torch.zeros(width, dtype=torch.float64)
+        send[0] = float(active)
+        send[1:1 + len(mine)] = torch.from_numpy(mine)
+        send = send.to(self.device)
         recv = torch.empty(width * self.world, dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         self.collectives += 1
         allc = recv.cpu().numpy().reshape(self.world, width)
-        chunks = np.concatenate([allc[r, :n] for r, n in enumerate(self._chunks_per_rank)])
+        flags = [bool(allc[r, 0]) for r in range(self.world)]
+        chunks = np.concatenate([allc[r, 1:1 + n] for r, n in enumerate(self._chunks_per_rank)])
+        return flags, chunks
+
+    def _reduce(self, ptr) -> float:
+        torch, dist = self.torch, self.dist
+        R = self._R[ptr]
+        chain = R > 1 and getattr(self.be, "quirk_carry", True)
+        zero = np.zeros(R, np.float32)
+        # optimistic pass: every rank assumes the exponent vector enters its block as zeros.  That is exact
+        # unless an EARLIER rank holds a rescaled site (then the chain has to hop through the ranks in order).
+        active = False
+        if chain:
+            self.be.shard_chain(ptr, zero)
+            active = self.be.shard_active(ptr)
+        flags, chunks = self._gather(active, self.be.shard_finish(ptr))
+        if chain and any(flags[:-1]):
+            carry = zero
+            ran = False
+            buf = torch.zeros(R, dtype=torch.float32, device=self.device)
+            for a in [r for r in range(self.world) if flags[r]]:
+                if a == self.rank:
+                    out = self.be.shard_chain(ptr, carry)
+                    ran = True
+                    buf.copy_(torch.from_numpy(out))
+                if a + 1 < self.world:
+                    dist.broadcast(buf, src=dist.get_global_rank(self.group, a) if self.group else a, group=self.group)
+                    self.collectives += 1
+                    if self.rank > a:
+                        carry = buf.cpu().numpy().copy()
+            if not ran:
+                self.be.shard_chain(ptr, carry)        # no rescaled site here: the vector passes through unchanged
+            flags, chunks = self._gather(True, self.be.shard_finish(ptr))
         return float(self.be.reduce_chunks(chunks))
 
     # ------------------------------------------------------------------ entry points

@@ -46,6 +46,10 @@ class OracleShard:
         self._site[ptr] = ll
         return ev
 
+    def shard_active(self, ptr):
+        _, expo = self._per_site(ptr)
+        return bool((expo != 0).any())
+
     def shard_finish(self, ptr):
         if ptr not in self._site:         # one rate category or textbook mode: no chain ran
             self.shard_chain_reset(ptr)
