@@ -629,6 +629,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   if ((rc = checkHandle(t))) return rc;
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
   *out = t->st;
+  out->num_tips = t->N; out->num_loci = t->S; out->num_rate_cats = t->R;
   return DMPC_OK;
 }
 

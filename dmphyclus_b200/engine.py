@@ -33,7 +33,8 @@ class Stats(C.Structure):
     _fields_ = [("updates", C.c_ulonglong), ("kernel_launches", C.c_ulonglong), ("evaluations", C.c_ulonglong),
                 ("last_eval_ms", C.c_double), ("last_prune_ms", C.c_double), ("last_updates", C.c_ulonglong),
                 ("last_prune_launches", C.c_ulonglong), ("last_levels", C.c_int), ("exponent_capacity", C.c_int),
-                ("device_bytes", C.c_ulonglong), ("last_active_tiles", C.c_int)]
+                ("device_bytes", C.c_ulonglong), ("last_active_tiles", C.c_int),
+                ("num_tips", C.c_int), ("num_loci", C.c_int), ("num_rate_cats", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

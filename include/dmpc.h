@@ -122,6 +122,7 @@ typedef struct dmpc_stats {
   unsigned long long device_bytes;   /* bytes of HBM held by this handle */
   int last_active_tiles;    /* 128-site tiles that held a rescaled site in the last evaluation (0: the fp32
                                exponent chain is the identity on this handle's sites) */
+  int num_tips, num_loci, num_rate_cats;   /* shape of the handle (the shim sizes edge outputs from it) */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
