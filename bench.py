@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
+    ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
     ap.add_argument("--seed", type=int, default=2001)
     return ap.parse_args()
 
@@ -211,11 +212,12 @@ def run_ours(args, rank, world, local_rank):
 
     if world > 1:
         from dmphyclus_b200.sharded import ShardedEngine, shard_range
-        local = Engine(device=local_rank, site_begin=shard_range(S_total, rank, world)[0], sites_total=S_total)
+        local = Engine(device=local_rank, site_begin=shard_range(S_total, rank, world)[0], sites_total=S_total,
+                       fuse_tips=args.fuse)
         eng = ShardedEngine(local, S_total, device=torch.device("cuda", local_rank))
         b0, b1 = eng.begin, eng.end
     else:
-        local = eng = Engine(device=local_rank)
+        local = eng = Engine(device=local_rank, fuse_tips=args.fuse)
         b0, b1 = 0, S_total
     s_local = b1 - b0
     # this rank's alignment block in pinned host memory (the e2e leg uploads it every step)
@@ -261,9 +263,13 @@ def run_ours(args, rank, world, local_rank):
     updates_step = (n - 1) * S_total * r
     value = updates_step * args.steps / (ms * 1e-3)
     peak, peak_src = peaks()
-    bytes_eval = algorithmic_bytes(n, s_local, r)
+    # compulsory HBM bytes of one evaluation's pruning as the engine counted them for the plan it ran (stored
+    # partials written and read, mask bytes); with small-clade fusion this is far below the unfused 68 B/update
+    bytes_eval = st1["last_algorithmic_bytes"]
+    bytes_unfused = algorithmic_bytes(n, s_local, r)
     achieved = bytes_eval * args.steps / (prune_ms * 1e-3) / 1e9
     dev_bytes = st1["device_bytes"]
+    kernel_name = "k_prune_fused" if st1["last_fused_vertices"] else "k_prune_level"
     eng.finalDeallocate(h)
 
     # ---------------------------------------------------------------- end-to-end leg (host buffers in, scalar out)
@@ -305,12 +311,16 @@ def run_ours(args, rank, world, local_rank):
                        "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                        "call": "Engine.logLikCpp (dmpc_loglik_create) + finalDeallocate, alignment in pinned host memory"},
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "k_prune_level", "achieved": achieved, "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": bytes_eval / max(1, st1["last_prune_launches"]),
                             "launches_per_step": int(st1["last_prune_launches"]),
                             "kernel_ms_per_step": prune_ms / args.steps,
-                            "kernel_share_of_step": prune_ms / ms, "frac_of_8000_spec": achieved / 8000.0},
+                            "kernel_share_of_step": prune_ms / ms, "frac_of_8000_spec": achieved / 8000.0,
+                            "stored_vertices": int(st1["last_stored_vertices"]), "fused_vertices": int(st1["last_fused_vertices"]),
+                            "bytes_per_update": bytes_eval / ((n - 1) * s_local * r),
+                            "unfused_bytes_per_step": bytes_unfused,
+                            "unfused_equivalent_gbs": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9},
                "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
                "levels": int(st1["last_levels"])}
         out.update(extras)

@@ -31,7 +31,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(DMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
   } while (0)
 
-struct HostResult { double ll; int overflow; int badCells; int nact; };
+struct HostResult { double ll; int overflow; int badCells; int nact; int violation; };
 
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
 // and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
@@ -41,6 +41,7 @@ struct ResPack {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   Task* h_tasks = nullptr;       // pinned
   int32_t* h_curList = nullptr;  // pinned
+  Token* h_tokens = nullptr;     // pinned
   HostResult* h_res = nullptr;   // pinned
   size_t cap = 0;                // internal vertices the pinned buffers can hold
 };
@@ -55,7 +56,7 @@ DeviceCtx g_ctx[64];
 
 struct dmpc_tree {
   HostTree ht;
-  int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nChunks = 0;
+  int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nReal = 0, nChunks = 0;
   bool quirk = true, deferred = false, alive = true;
   int device = 0, siteBegin = 0, sitesTotal = 0;
   ResPack pack;
@@ -75,7 +76,11 @@ struct dmpc_tree {
   bool constantsValid = false;
   std::vector<void*> allocs;
   dmpc_stats st{};
-  std::vector<int> order, levelStart;
+  HostTree::Plan plan;
+  bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
+  bool smemSet[2] = {false, false};
+  Token* d_tokens = nullptr;
+  Token* h_tokens = nullptr;     // pinned
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
   template <class Tp>
@@ -116,15 +121,17 @@ int acquirePack(dmpc_tree* t) {
   if (p.cap < (size_t)t->nInt) {
     if (p.h_tasks) cudaFreeHost(p.h_tasks);
     if (p.h_curList) cudaFreeHost(p.h_curList);
-    p.h_tasks = nullptr; p.h_curList = nullptr; p.cap = 0;
+    if (p.h_tokens) cudaFreeHost(p.h_tokens);
+    p.h_tasks = nullptr; p.h_curList = nullptr; p.h_tokens = nullptr; p.cap = 0;
     const size_t cap = std::max<size_t>(1024, (size_t)t->nInt * 5 / 4);
     CUDA_TRY(cudaHostAlloc((void**)&p.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_curList, cap * sizeof(int32_t), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_tokens, 2 * cap * sizeof(Token), cudaHostAllocDefault));
     p.cap = cap;
   }
   t->stream = p.stream;
   for (int i = 0; i < 5; i++) t->ev[i] = p.ev[i];
-  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res;
+  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens;
   return DMPC_OK;
 }
 
@@ -199,6 +206,58 @@ dmpc_tree* g_constOwner[64] = {nullptr};
 
 int rootStage(dmpc_tree* t, double* ll);
 
+size_t fusedSmem(int R) { return (size_t)(2 * R * 64 + FUSE_DEPTH * R * 4 * TILE) * sizeof(double) + 2 * R * 16; }
+
+template <int RT>
+int launchFusedLevel(dmpc_tree* t, dim3 grid, const Task* lt) {
+  const size_t smem = fusedSmem(RT);
+  if (t->exact) {
+    if (!t->smemSet[1]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[1] = true; }
+    k_prune_fused<RT, true><<<grid, TILE, smem, t->stream>>>(t->dv, lt, t->d_tokens, t->rv.overflow + 2);
+  } else {
+    if (!t->smemSet[0]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[0] = true; }
+    k_prune_fused<RT, false><<<grid, TILE, smem, t->stream>>>(t->dv, lt, t->d_tokens, t->rv.overflow + 2);
+  }
+  return DMPC_OK;
+}
+
+// the level launches of the current plan (tasks and tokens are already on the device)
+int runPlan(dmpc_tree* t) {
+  const HostTree::Plan& p = t->plan;
+  const int nLevels = (int)p.levelStart.size() - 1;
+  if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
+  CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
+  for (int l = 0; l < nLevels; l++) {
+    const int n = p.levelStart[l + 1] - p.levelStart[l];
+    const dim3 grid((unsigned)n, (unsigned)t->T);
+    const Task* lt = t->d_tasks + p.levelStart[l];
+    int rc = DMPC_OK;
+    if (t->ht.fuseTips > 1) {
+      switch (t->R) {
+        case 1: rc = launchFusedLevel<1>(t, grid, lt); break;
+        case 2: rc = launchFusedLevel<2>(t, grid, lt); break;
+        case 3: rc = launchFusedLevel<3>(t, grid, lt); break;
+        default: rc = launchFusedLevel<4>(t, grid, lt); break;
+      }
+      if (rc) return rc;
+    } else {
+      switch (t->R) {
+        case 1: k_prune_level<1><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 2: k_prune_level<2><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 3: k_prune_level<3><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        case 4: k_prune_level<4><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+        default: k_prune_level<0><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
+      }
+    }
+    t->st.kernel_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(t->ev[1], t->stream));
+  t->st.last_levels = nLevels;
+  t->st.last_prune_launches = nLevels;
+  return DMPC_OK;
+}
+
 // ComputeLoglik (AugTree.cpp:289-326): prune the dirty levels, then reduce at the root.
 int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll) {
   int rc;
@@ -209,55 +268,40 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   }
   if ((rc = uploadConstants(t, within, between, pi))) return rc;
   HostTree& ht = t->ht;
-  ht.schedule(t->order, t->levelStart);
-  const int nTasks = (int)t->order.size();
-  const int N = t->N;
-  for (int i = 0; i < nTasks; i++) {
-    const int v = t->order[i];
-    const int outSlot = ht.cur[v] ? 0 : 1;
-    if ((rc = allocSlot(t, outSlot))) return rc;
-    const int c0 = ht.kids[2 * v], c1 = ht.kids[2 * v + 1];
-    Task k;
-    k.out = v - N;
-    k.flags = outSlot ? TF_OUTSLOT : 0;
-    if (c0 < N) { k.c0 = c0; k.flags |= TF_C0TIP; } else { k.c0 = c0 - N; if (ht.cur[c0]) k.flags |= TF_C0SLOT; }
-    if (c1 < N) { k.c1 = c1; k.flags |= TF_C1TIP; } else { k.c1 = c1 - N; if (ht.cur[c1]) k.flags |= TF_C1SLOT; }
-    if (ht.within[c0]) k.flags |= TF_WITHIN;        // AugTree.cpp:125: the FIRST child's flag picks the matrix set
-    t->h_tasks[i] = k;
-    ht.cur[v] = (uint8_t)outSlot;                   // ComputeSolutions: _previousIterVec <- current (:28) ...
-    ht.touched[v] = 1;                              // ... _updateFlag = true (:34)
-    ht.solved[v] = 1;                               // ... _isSolved = true (:33)
-  }
-  CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
+  HostTree::Plan& p = t->plan;
+  ht.plan(p);
+  const int nTasks = (int)p.tasks.size(), nTok = (int)p.tokens.size();
   if (nTasks) {
+    for (int sl = 0; sl < 2; sl++)
+      if (p.uses[sl] && (rc = allocSlot(t, sl))) return rc;
+    std::memcpy(t->h_tasks, p.tasks.data(), (size_t)nTasks * sizeof(Task));
     CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, (size_t)nTasks * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
-    const int nLevels = (int)t->levelStart.size() - 1;
-    for (int l = 0; l < nLevels; l++) {
-      const int n = t->levelStart[l + 1] - t->levelStart[l];
-      if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
-      const dim3 grid((unsigned)n, (unsigned)t->T);
-      const Task* lt = t->d_tasks + t->levelStart[l];
-      switch (t->R) {
-        case 1: k_prune_level<1><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 2: k_prune_level<2><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 3: k_prune_level<3><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 4: k_prune_level<4><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        default: k_prune_level<0><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-      }
-      t->st.kernel_launches++;
+    if (nTok) {
+      std::memcpy(t->h_tokens, p.tokens.data(), (size_t)nTok * sizeof(Token));
+      CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, (size_t)nTok * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
     }
-    CUDA_TRY(cudaGetLastError());
-    t->st.last_levels = nLevels;
-    t->st.last_prune_launches = nLevels;
-  } else {
-    t->st.last_levels = 0;
-    t->st.last_prune_launches = 0;
   }
-  CUDA_TRY(cudaEventRecord(t->ev[1], t->stream));
-  t->st.last_updates = (unsigned long long)nTasks * t->S * t->R;
+  if ((rc = runPlan(t))) return rc;
+  t->st.last_updates = (unsigned long long)(nTasks + p.fusedOps) * t->S * t->R;
   t->st.updates += t->st.last_updates;
   t->st.evaluations++;
-  return rootStage(t, ll);
+  // compulsory HBM traffic of this evaluation: stored partials written (32 B) and read (32 B per stored operand),
+  // one mask byte per tip operand; exponents move only where something rescaled (not counted)
+  t->st.last_algorithmic_bytes = (unsigned long long)t->S * t->R * 32ull * (unsigned long long)(nTasks + p.storedReads) +
+                                 (unsigned long long)t->S * (unsigned long long)p.tipReads;
+  t->st.last_stored_vertices = nTasks;
+  t->st.last_fused_vertices = (int)p.fusedOps;
+  if ((rc = rootStage(t, ll))) return rc;
+  if (!t->exact && t->h_res->violation) {
+    // a fused clade may have rescaled: redo the same plan with the exact kernel (same tasks, same slots) and
+    // keep that mode for the life of the handle
+    t->exact = true;
+    CUDA_TRY(cudaMemsetAsync(t->rv.overflow + 2, 0, sizeof(int), t->stream));
+    if ((rc = runPlan(t))) return rc;
+    t->st.exact_mode = 1;
+    return rootStage(t, ll);
+  }
+  return DMPC_OK;
 }
 
 int launchGather(dmpc_tree* t) {
@@ -302,6 +346,7 @@ int gatherWithGrowth(dmpc_tree* t) {
     if ((rc = launchGather(t))) return rc;
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->violation, t->rv.overflow + 2, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     t->st.last_active_tiles = t->h_res->nact;
     if (t->h_res->overflow <= t->rv.Kcap) return DMPC_OK;
@@ -331,6 +376,7 @@ int rootStage(dmpc_tree* t, double* ll) {
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->ll, t->rv.result, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(&t->h_res->violation, t->rv.overflow + 2, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     t->st.last_active_tiles = t->h_res->nact;
     if (t->h_res->overflow <= t->rv.Kcap) {
@@ -375,7 +421,7 @@ int checkHandle(dmpc_tree* t) {
 extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
-  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0;
+  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 8; o->fuse_exact = 0;
 }
 
 const char* dmpc_last_error(void) { return g_err.c_str(); }
@@ -417,7 +463,10 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   if (!t->ht.build(edge, nEdgeRows, numTips)) { std::string e = t->ht.err; delete t; return fail(DMPC_ERR_ARG, e); }
   t->ht.associate(clusterMRCAs, nClusterMRCAs);
   t->ht.withinIdx = withinMatListIndex; t->ht.betweenIdx = betweenMatListIndex;
-  t->N = numTips; t->S = numLoci; t->R = numRateCats; t->nInt = numTips - 1;
+  t->N = numTips; t->S = numLoci; t->R = numRateCats;
+  t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
+  t->ht.fuseTips = numRateCats > 4 ? 1 : std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
+  t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
   t->T = t->Sp / TILE;
   t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
@@ -434,6 +483,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     if ((r2 = t->alloc(&t->d_tipmask, (size_t)t->N * t->Sp))) return r2;
     if ((r2 = t->alloc(&t->d_lut, (size_t)2 * t->R * 64))) return r2;
     if ((r2 = t->alloc(&t->d_tasks, (size_t)t->nInt))) return r2;
+    if ((r2 = t->alloc(&t->d_tokens, (size_t)2 * t->nInt))) return r2;
     if ((r2 = t->alloc(&t->d_curList, (size_t)t->nInt))) return r2;
     if ((r2 = t->alloc(&t->dv.cur, (size_t)t->nInt))) return r2;
     if ((r2 = t->alloc(&t->rv.kmax, (size_t)t->Sp))) return r2;
@@ -449,15 +499,15 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     if ((r2 = t->alloc(&t->rv.sitell, (size_t)t->Sp))) return r2;
     if ((r2 = t->alloc(&t->rv.chunk, (size_t)t->nChunks))) return r2;
     if ((r2 = t->alloc(&t->rv.ticket, (size_t)1))) return r2;
-    if ((r2 = t->alloc(&t->rv.overflow, (size_t)2))) return r2;
+    if ((r2 = t->alloc(&t->rv.overflow, (size_t)4))) return r2;      // [0] list overflow, [1] bad cells, [2] fused-clade violation
     if ((r2 = t->alloc(&t->rv.nact, (size_t)1))) return r2;
     if ((r2 = t->alloc(&t->rv.result, (size_t)1))) return r2;
     if ((r2 = allocElist(t, 8))) return r2;
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
     CUDA_TRY(cudaMemsetAsync(t->rv.ticket, 0, sizeof(unsigned), t->stream));
-    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, 2 * sizeof(int), t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, 4 * sizeof(int), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
-    t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt;
+    t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal;
     // alignment: [N][S] host rows -> [N][Sp] device rows; pad sites get the all-ones mask
     CUDA_TRY(cudaMemcpy2DAsync(t->d_tipmask, t->Sp, alignmentBin, t->S, t->S, t->N, cudaMemcpyHostToDevice, t->stream));
     {
@@ -660,13 +710,37 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   if ((rc = checkHandle(t))) return rc;
   if ((rc = ensureDevice(t))) return rc;
   if (vertex < t->N || vertex >= t->ht.numVerts || !sol || !expo) return fail(DMPC_ERR_ARG, "vertex must be internal");
-  const int slot = t->ht.cur[vertex], idx = vertex - t->N;
+  HostTree& ht = t->ht;
+  const int slot = ht.cur[vertex], idx = vertex - t->N;
+  int partSlot = slot, partRow = idx;
+  ht.computeTips();
+  if (ht.fused(vertex)) {
+    // a fused vertex has no stored partial: replay its program (read-only) into the scratch row
+    HostTree::Plan rp;
+    const Task k = ht.makeTask(vertex, t->nReal, 0, rp, false);
+    t->h_tasks[0] = k;
+    CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, sizeof(Task), cudaMemcpyHostToDevice, t->stream));
+    if (!rp.tokens.empty()) {
+      std::memcpy(t->h_tokens, rp.tokens.data(), rp.tokens.size() * sizeof(Token));
+      CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, rp.tokens.size() * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+    }
+    const dim3 grid(1, (unsigned)t->T);
+    switch (t->R) {
+      case 1: rc = launchFusedLevel<1>(t, grid, t->d_tasks); break;
+      case 2: rc = launchFusedLevel<2>(t, grid, t->d_tasks); break;
+      case 3: rc = launchFusedLevel<3>(t, grid, t->d_tasks); break;
+      default: rc = launchFusedLevel<4>(t, grid, t->d_tasks); break;
+    }
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    partSlot = 0; partRow = t->nReal;
+  }
   const size_t n = (size_t)t->R * t->Sp;
   std::vector<double> hs(n * 4);
   std::vector<float> he(n);
   std::vector<uint8_t> hf((size_t)t->T);
   CUDA_TRY(cudaStreamSynchronize(t->stream));
-  CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[slot] + (size_t)idx * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[partSlot] + (size_t)partRow * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(he.data(), t->dv.expo[slot] + (size_t)idx * n, n * sizeof(float), cudaMemcpyDeviceToHost));
   for (int b = 0; b < t->T; b++)
     CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nInt + idx, 1, cudaMemcpyDeviceToHost));

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include "task.hpp"
+
 namespace dmpc {
 
 // GSL's gsl_rng_taus (rng/taus.c) with gsl_rng_alloc's default seed and gsl_rng_uniform_int's rejection
@@ -53,6 +55,11 @@ struct HostTree {
   int withinIdx = 0, betweenIdx = 0;
   TausRng rng;
   std::string err;
+  // small-clade fusion: a vertex with at most fuseTips tips below it (and not the root) is never stored; it is
+  // recomputed from the tip masks inside the task of its nearest stored ancestor.  1 = every vertex is stored.
+  int fuseTips = 1;
+  std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
+  bool tipsValid = false;
 
   bool isTip(int v) const { return v < numTips; }
   int internalIndex(int v) const { return v - numTips; }
@@ -74,6 +81,7 @@ struct HostTree {
 
   // AugTree::BuildTree / BuildTreeNoAssign (AugTree.cpp:59-101): edge is column-major, 1-based.
   bool link(const int32_t* edge, int nEdgeRows) {
+    tipsValid = false;
     std::fill(kids.begin(), kids.end(), -1);
     std::fill(nkids.begin(), nkids.end(), 0);
     for (int k = 0; k < nEdgeRows; k++) {
@@ -177,6 +185,7 @@ struct HostTree {
 
   // RearrangeTreeNNI (AugTree.cpp:211-226)
   void rearrangeNNI(int a, int b) {
+    tipsValid = false;
     removeChild(parent[a], a); addChild(parent[a], b);
     removeChild(parent[b], b); addChild(parent[b], a);
     std::swap(parent[a], parent[b]);
@@ -196,20 +205,107 @@ struct HostTree {
     }
   }
 
-  // The dirty set of the pending evaluation as a level schedule.  Mirrors TrySolve: only unsolved vertices
-  // reachable from the root through unsolved vertices are recomputed.  order[] lists them level by level
-  // (children strictly before parents), levelStart[] delimits the levels.
-  void schedule(std::vector<int>& order, std::vector<int>& levelStart) const {
-    order.clear(); levelStart.clear();
-    if (solved[root()]) { levelStart.push_back(0); return; }
+  void computeTips() {
+    if (tipsValid) return;
+    tips.assign(numVerts, 1);
     std::vector<int> pre;
+    pre.reserve(numVerts);
     std::vector<int> stack(1, root());
     while (!stack.empty()) {
       int v = stack.back(); stack.pop_back();
       pre.push_back(v);
-      for (int i = 0; i < 2; i++) { int c = kids[2 * v + i]; if (!isTip(c) && !solved[c]) stack.push_back(c); }
+      if (!isTip(v)) { stack.push_back(kids[2 * v]); stack.push_back(kids[2 * v + 1]); }
     }
-    std::vector<int> level(numVerts, 0);   // height above the clean frontier; clean vertices and tips = 0
+    for (size_t i = pre.size(); i-- > 0;) { int v = pre[i]; if (!isTip(v)) tips[v] = tips[kids[2 * v]] + tips[kids[2 * v + 1]]; }
+    tipsValid = true;
+  }
+  bool fused(int v) const { return v >= numTips && v != numTips && tips[v] <= fuseTips; }
+
+  // The pending evaluation as launchable work: the dirty STORED vertices level by level (children strictly
+  // before parents), each with its operands; fused operands come with their token programs.  Mirrors TrySolve:
+  // only unsolved vertices reachable from the root through unsolved vertices are recomputed — plus the fused
+  // clades hanging off them, which are recomputed whenever their stored ancestor is.  Updates cur/touched/solved
+  // the way ComputeSolutions does (IntermediateNode.cpp:28-34).
+  struct Plan {
+    std::vector<Task> tasks;
+    std::vector<Token> tokens;
+    std::vector<int> levelStart;
+    long long storedReads = 0, tipReads = 0, fusedOps = 0;
+    bool uses[2] = {false, false};               // slots this plan writes
+    std::vector<int> pre, level, cnt, fill;      // scratch
+  };
+
+  // mutate = false: introspection replay — tokens address the CURRENT slots and no state changes
+  void emitClade(int u, Plan& p, bool mutate = true) {
+    const int k0 = kids[2 * u], k1 = kids[2 * u + 1];
+    Token t;
+    t.a = t.b = 0;
+    if (isTip(k0) && isTip(k1)) {
+      t.op = OP_CHERRY; t.a = k0; t.b = k1;
+      p.tipReads += 2;
+    } else if (isTip(k0) || isTip(k1)) {
+      emitClade(isTip(k0) ? k1 : k0, p, mutate);
+      t.op = OP_REGTIP | (isTip(k0) ? TOK_FIRST : 0);
+      t.b = isTip(k0) ? k0 : k1;
+      p.tipReads += 1;
+    } else {
+      const int h = tips[k0] >= tips[k1] ? k0 : k1, o = h == k0 ? k1 : k0;   // heavier side first: stack depth <= log2
+      emitClade(h, p, mutate);
+      Token sp; sp.op = OP_SPILL; sp.a = sp.b = 0; sp.vertex = 0;
+      p.tokens.push_back(sp);
+      emitClade(o, p, mutate);
+      t.op = OP_SLOTREG | (h == k0 ? TOK_FIRST : 0);
+    }
+    const int slot = mutate ? cur[u] ^ 1 : cur[u];
+    if (within[k0]) t.op |= TOK_SET;                  // AugTree.cpp:125: the first child's flag picks the matrix set
+    if (slot) t.op |= TOK_SLOT;
+    t.vertex = u - numTips;
+    p.tokens.push_back(t);
+    p.fusedOps++;
+    p.uses[slot] = true;
+    if (mutate) { cur[u] = (uint8_t)slot; touched[u] = 1; solved[u] = 1; }
+  }
+
+  // the task of vertex v written to row `outRow`, slot `outSlot`; appends the programs of fused operands to p.tokens
+  Task makeTask(int v, int outRow, int outSlot, Plan& p, bool mutate) {
+    Task k;
+    k.out = outRow;
+    k.flags = outSlot ? TF_OUTSLOT : 0;
+    k.prog0 = k.n0 = k.prog1 = k.n1 = 0;
+    for (int j = 0; j < 2; j++) {
+      const int c = kids[2 * v + j];
+      int32_t& ref = j ? k.c1 : k.c0;
+      if (isTip(c)) {
+        ref = c; k.flags |= j ? TF_C1TIP : TF_C0TIP; p.tipReads++;
+      } else if (fused(c)) {
+        ref = c - numTips; k.flags |= j ? TF_C1FUSED : TF_C0FUSED;
+        const int off = (int)p.tokens.size();
+        emitClade(c, p, mutate);
+        if (j) { k.prog1 = off; k.n1 = (int)p.tokens.size() - off; } else { k.prog0 = off; k.n0 = (int)p.tokens.size() - off; }
+      } else {
+        ref = c - numTips; if (cur[c]) k.flags |= j ? TF_C1SLOT : TF_C0SLOT; p.storedReads++;
+      }
+    }
+    if (within[kids[2 * v]]) k.flags |= TF_WITHIN;      // AugTree.cpp:125: the FIRST child's flag picks the matrix set
+    return k;
+  }
+
+  void plan(Plan& p) {
+    p.tasks.clear(); p.tokens.clear(); p.levelStart.clear();
+    p.storedReads = p.tipReads = p.fusedOps = 0;
+    p.uses[0] = p.uses[1] = false;
+    if (solved[root()]) { p.levelStart.push_back(0); return; }
+    computeTips();
+    std::vector<int>& pre = p.pre;
+    pre.clear();
+    std::vector<int> stack(1, root());
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      pre.push_back(v);
+      for (int i = 0; i < 2; i++) { int c = kids[2 * v + i]; if (!isTip(c) && !fused(c) && !solved[c]) stack.push_back(c); }
+    }
+    std::vector<int>& level = p.level;
+    level.assign(numVerts, 0);             // height above the clean frontier; clean, fused vertices and tips = 0
     int maxLevel = 0;
     for (size_t i = pre.size(); i-- > 0;) {   // reverse pre-order visits children before parents
       int v = pre[i];
@@ -217,15 +313,26 @@ struct HostTree {
       level[v] = l;
       maxLevel = std::max(maxLevel, l);
     }
-    std::vector<int> cnt(maxLevel + 1, 0);
-    for (int v : pre) cnt[level[v]]++;
-    levelStart.assign(maxLevel + 1, 0);   // level l (1-based) = order[levelStart[l-1] .. levelStart[l])
+    p.cnt.assign(maxLevel + 1, 0);
+    for (int v : pre) p.cnt[level[v]]++;
+    p.levelStart.assign(maxLevel + 1, 0);   // level l (1-based) = tasks[levelStart[l-1] .. levelStart[l])
     int acc = 0;
-    for (int l = 1; l <= maxLevel; l++) { levelStart[l - 1] = acc; acc += cnt[l]; }
-    levelStart[maxLevel] = acc;
-    std::vector<int> fill(levelStart.begin(), levelStart.end());
-    order.resize(pre.size());
-    for (int v : pre) order[fill[level[v] - 1]++] = v;
+    for (int l = 1; l <= maxLevel; l++) { p.levelStart[l - 1] = acc; acc += p.cnt[l]; }
+    p.levelStart[maxLevel] = acc;
+    p.fill.assign(p.levelStart.begin(), p.levelStart.end());
+    std::vector<int> order(pre.size());
+    for (int v : pre) order[p.fill[level[v] - 1]++] = v;
+    p.tasks.resize(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+      const int v = order[i];
+      const int outSlot = cur[v] ^ 1;
+      Task k = makeTask(v, v - numTips, outSlot, p, true);
+      p.tasks[i] = k;
+      p.uses[outSlot] = true;
+      cur[v] = (uint8_t)outSlot;                      // ComputeSolutions: _previousIterVec <- current (:28) ...
+      touched[v] = 1;                                 // ... _updateFlag = true (:34)
+      solved[v] = 1;                                  // ... _isSolved = true (:33)
+    }
   }
 };
 

@@ -19,18 +19,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "task.hpp"
+
 namespace dmpc {
 
 constexpr int RMAX = 8;         // rate categories supported (the packaged data uses 3)
 constexpr int TILE = 128;       // sites per block of the pruning kernel = flag granularity
 constexpr int CHUNK = 256;      // sites per deterministic reduction chunk
-
-struct Task {                   // one dirty vertex of one level
-  int32_t out;                  // internal index (vertex id - N) to write
-  int32_t c0, c1;               // children: tip index, or internal index
-  int32_t flags;
-};
-enum : int32_t { TF_OUTSLOT = 1, TF_C0TIP = 2, TF_C1TIP = 4, TF_C0SLOT = 8, TF_C1SLOT = 16, TF_WITHIN = 32 };
 
 struct DevView {
   double* part[2];
@@ -39,7 +34,8 @@ struct DevView {
   const uint8_t* tipmask;
   uint8_t* cur;                 // [N-1] slot of each internal vertex, as seen by the root reduction
   const double* lut;            // [2][R][16][4]: P * indicator(mask) for every 4-bit mask (tips)
-  int N, S, Sp, R, T, nInt;
+  int N, S, Sp, R, T, nInt;      // nInt = rows of the per-vertex arrays: the N-1 internal vertices + 1 scratch row
+  int nReal;                    // N-1: what the root reduction scans
   // select instead of dynamic indexing: indexing a by-value kernel parameter array would spill it to local memory
   __device__ __forceinline__ double* partOf(int slot) const { return slot ? part[1] : part[0]; }
   __device__ __forceinline__ float* expoOf(int slot) const { return slot ? expo[1] : expo[0]; }
@@ -197,6 +193,238 @@ __global__ void __launch_bounds__(TILE) k_prune_level(DevView v, const Task* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2f prune_fused: K2 with small-clade fusion.  An operand of a task may be a FUSED clade (<= 15 tips): its
+// vertices are never stored; the thread recomputes them for its site from the tip masks by running the clade's
+// token program (task.hpp) on a register accumulator + a shared-memory stack, then feeds the result into the
+// stored vertex's update.  HBM traffic drops from ~68 B per update to the stored vertices only (about a fifth
+// of the vertices of a random tree for fuseTips = 8), which moves the kernel off the HBM roof.
+//
+// Rescaling inside a fused clade is legal but needs per-vertex exponents and tile flags.  FAST mode (EXACT =
+// false) assumes it does not happen, clears the fused vertices' flags, and raises *violation when a thread
+// sees a value that could have triggered it (conservative high-word test); the host then re-runs the
+// evaluation with EXACT = true, where every fused vertex gets the reference's full two-check treatment, a
+// block vote, and exponent rows — and keeps that mode for the handle.
+__device__ __forceinline__ void matvec4(const double* __restrict__ P, const double (&x)[4], double (&y)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) y[i] = row4(P + 4 * i, x[0], x[1], x[2], x[3]);
+}
+__device__ __forceinline__ bool below4(const double (&s)[4]) {            // exact: max(s) < 1e-150
+  return s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150;
+}
+__device__ __forceinline__ bool maybeBelow4(const double (&s)[4]) {       // conservative, integer pipe only
+  constexpr int H = 0x20CA2FE8;                                           // > high word of 1e-150 (0x20CA2FE7)
+  return __double2hiint(s[0]) < H && __double2hiint(s[1]) < H && __double2hiint(s[2]) < H && __double2hiint(s[3]) < H;
+}
+// IntermediateNode.cpp:53-66 for one category: first child, check, second child, check (the second OVERWRITES)
+__device__ __forceinline__ void combineExact(const double (&first)[4], const double (&second)[4], double (&s)[4], float& e) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[i] = first[i];
+  if (below4(s)) {
+    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
+    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
+    e = (float)log(m);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[i] = __dmul_rn(s[i], second[i]);
+  if (below4(s)) {
+    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
+    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
+    e = (float)log(m);
+  }
+}
+
+template <int RT, bool EXACT>
+__global__ void __launch_bounds__(TILE) k_prune_fused(DevView v, const Task* __restrict__ tasks,
+                                                      const Token* __restrict__ prog, int* violation) {
+  extern __shared__ __align__(16) double s_mem[];
+  double* const s_lut = s_mem;                                  // [2][RT][16][4]
+  double* const s_stack = s_mem + 2 * RT * 64;                  // [FUSE_DEPTH][RT][4][TILE]
+  unsigned char* const s_below = reinterpret_cast<unsigned char*>(s_stack + FUSE_DEPTH * RT * 4 * TILE);   // [2*RT*16]
+  const int tid = threadIdx.x;
+  const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x));
+  const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x) + 1);
+  const int fl = tk0.w;
+  const int tile = blockIdx.y;
+  const int site = tile * TILE + tid;
+  const int set = (fl & TF_WITHIN) ? 1 : 0;
+  const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
+  const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
+  const size_t Sp = (size_t)v.Sp, rstride = Sp * 4;
+  const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk0.y * RT * Sp + site) * 4;
+  const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk0.z * RT * Sp + site) * 4;
+  unsigned ma = 0, mb = 0;
+  if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site];
+  if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site];
+  double a[RT][4], b[RT][4];
+  const bool early = !(fus0 | fus1);           // plain task: every child load is issued before any arithmetic
+  if (early) {
+#pragma unroll
+    for (int r = 0; r < RT; r++) {
+      if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
+      if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
+    }
+  }
+  if (!early || tip0 || tip1) {
+    for (int i = tid; i < 2 * RT * 64; i += TILE) s_lut[i] = v.lut[i];
+    if (tid < 2 * RT * 16) {
+      const double* q = v.lut + 4 * tid;
+      s_below[tid] = (unsigned char)(q[0] < 1e-150 && q[1] < 1e-150 && q[2] < 1e-150 && q[3] < 1e-150);
+    }
+    __syncthreads();
+  }
+
+  double reg[RT][4];
+  bool trig = false;
+  // ---- the fused operands' programs
+  auto run = [&](int off, int n, int sp) {
+    for (int i = 0; i < n; i++) {
+      const int4 t4 = __ldg(reinterpret_cast<const int4*>(prog + off + i));
+      const int op = t4.x & 7;
+      if (op == OP_SPILL) {
+#pragma unroll
+        for (int r = 0; r < RT; r++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) s_stack[((sp * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
+        sp++;
+        continue;
+      }
+      const int tset = (t4.x & TOK_SET) ? 1 : 0, tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+      const bool firstFlag = (t4.x & TOK_FIRST) != 0;
+      unsigned m0 = 0, m1 = 0;
+      if (op == OP_CHERRY) { m0 = v.tipmask[(size_t)t4.y * Sp + site]; m1 = v.tipmask[(size_t)t4.z * Sp + site]; }
+      else if (op == OP_REGTIP) m1 = v.tipmask[(size_t)t4.z * Sp + site];
+      else sp--;
+      float e[RT];
+      bool resc = false;
+#pragma unroll
+      for (int r = 0; r < RT; r++) {
+        const double* P = c_P[tset][r];
+        const double* lutr = s_lut + (tset * RT + r) * 64;
+        double x[4], y[4];                     // x = term of the operand listed first in the token, y = the other
+        bool xTipBelow = false, yTipBelow = false;
+        if (op == OP_CHERRY) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
+          xTipBelow = s_below[(tset * RT + r) * 16 + m0]; yTipBelow = s_below[(tset * RT + r) * 16 + m1];
+        } else if (op == OP_REGTIP) {
+          matvec4(P, reg[r], x);
+#pragma unroll
+          for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
+          yTipBelow = s_below[(tset * RT + r) * 16 + m1];
+        } else {
+          double z[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) z[k] = s_stack[((sp * RT + r) * 4 + k) * TILE + tid];
+          matvec4(P, z, x);
+          matvec4(P, reg[r], y);
+        }
+        // child order: CHERRY lists the first child first; for the other two firstFlag says whether the operand
+        // listed second (REGTIP: the tip) resp. first (SLOTREG: the popped one) is the reference's first child
+        const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
+        if (EXACT) {
+          e[r] = 0.0f;
+          double s[4];
+          if (xFirst) combineExact(x, y, s, e[r]); else combineExact(y, x, s, e[r]);
+#pragma unroll
+          for (int k = 0; k < 4; k++) reg[r][k] = s[k];
+          resc |= e[r] != 0.0f;
+        } else {
+          // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
+          // notice that one of them COULD have fired
+          if (op == OP_CHERRY) trig |= xTipBelow;
+          else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
+          else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
+#pragma unroll
+          for (int k = 0; k < 4; k++) reg[r][k] = __dmul_rn(x[k], y[k]);
+          trig |= maybeBelow4(reg[r]);
+        }
+      }
+      const size_t frow = (size_t)tile * v.nInt + t4.w;
+      if (EXACT) {
+        const int any = __syncthreads_or(resc);
+        if (any) {
+          float* pe = v.expoOf(tslot) + (size_t)t4.w * RT * Sp + site;
+#pragma unroll
+          for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
+        }
+        if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0) v.cur[t4.w] = (uint8_t)tslot; }
+      } else if (tid == 0) {
+        v.flagOf(tslot)[frow] = 0;
+        if (tile == 0) v.cur[t4.w] = (uint8_t)tslot;
+      }
+    }
+  };
+  if (fus0) {
+    run(tk1.x, tk1.y, 0);
+    if (fus1) {
+#pragma unroll
+      for (int r = 0; r < RT; r++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) s_stack[((0 * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
+    }
+  }
+  if (fus1) run(tk1.z, tk1.w, 1);
+  if (!early) {
+#pragma unroll
+    for (int r = 0; r < RT; r++) {
+      if (!tip0 && !fus0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
+      if (!tip1 && !fus1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
+    }
+  }
+
+  // ---- the stored vertex itself: exact semantics always
+  const int os = (fl & TF_OUTSLOT) ? 1 : 0;
+  const size_t o = (size_t)tk0.x * RT * Sp + site;
+  double* po = v.partOf(os) + o * 4;
+  float* pe = v.expoOf(os) + o;
+  float e[RT];
+  bool rescaled = false;
+#pragma unroll
+  for (int r = 0; r < RT; r++) {
+    const double* P = c_P[set][r];
+    const double* lutr = s_lut + (set * RT + r) * 64;
+    double first[4], second[4], s[4];
+    if (tip0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
+    } else if (fus0) {
+      if (fus1) {
+        double z[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) z[k] = s_stack[((0 * RT + r) * 4 + k) * TILE + tid];
+        matvec4(P, z, first);
+      } else {
+        matvec4(P, reg[r], first);
+      }
+    } else {
+      matvec4(P, a[r], first);
+    }
+    if (tip1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
+    } else if (fus1) {
+      matvec4(P, reg[r], second);
+    } else {
+      matvec4(P, b[r], second);
+    }
+    e[r] = 0.0f;
+    combineExact(first, second, s, e[r]);
+    st256(po + r * rstride, s[0], s[1], s[2], s[3]);
+    rescaled |= e[r] != 0.0f;
+  }
+  const int any = __syncthreads_or(rescaled);
+  if (any) {
+#pragma unroll
+    for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
+  }
+  if (tid == 0) {
+    v.flagOf(os)[(size_t)tile * v.nInt + tk0.x] = (uint8_t)(any != 0);
+    if (tile == 0) v.cur[tk0.x] = (uint8_t)os;
+  }
+  if (!EXACT && trig) *violation = 1;
+}
+
 // rollback: flip the slot bits of the vertices a rejected proposal touched (IntermediateNode.h:26-33)
 __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,11 +470,11 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
   float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
   const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nInt : nullptr;
   const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nInt : nullptr;
-  for (int base = 0; base < v.nInt; base += TILE) {
+  for (int base = 0; base < v.nReal; base += TILE) {
     const int nd = base + tid;
     bool f = false;
     int slot = 0;
-    if (nd < v.nInt) { slot = v.cur[nd]; f = (slot ? f1[nd] : f0[nd]) != 0; }
+    if (nd < v.nReal) { slot = v.cur[nd]; f = (slot ? f1[nd] : f0[nd]) != 0; }
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) s_wcnt[wid] = __popc(bal);
     __syncthreads();

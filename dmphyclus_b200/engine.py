@@ -26,7 +26,7 @@ class DmpcError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int),
-                ("deferred", C.c_int)]
+                ("fuse_tips", C.c_int), ("fuse_exact", C.c_int), ("deferred", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -34,7 +34,9 @@ class Stats(C.Structure):
                 ("last_eval_ms", C.c_double), ("last_prune_ms", C.c_double), ("last_updates", C.c_ulonglong),
                 ("last_prune_launches", C.c_ulonglong), ("last_levels", C.c_int), ("exponent_capacity", C.c_int),
                 ("device_bytes", C.c_ulonglong), ("last_active_tiles", C.c_int),
-                ("num_tips", C.c_int), ("num_loci", C.c_int), ("num_rate_cats", C.c_int)]
+                ("num_tips", C.c_int), ("num_loci", C.c_int), ("num_rate_cats", C.c_int),
+                ("last_algorithmic_bytes", C.c_ulonglong), ("last_stored_vertices", C.c_int),
+                ("last_fused_vertices", C.c_int), ("exact_mode", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -107,7 +109,8 @@ class Engine:
 
     name = "cuda"
 
-    def __init__(self, device: int = -1, quirk_carry: bool = True, site_begin: int = 0, sites_total: int = 0):
+    def __init__(self, device: int = -1, quirk_carry: bool = True, site_begin: int = 0, sites_total: int = 0,
+                 fuse_tips: int | None = None, fuse_exact: bool = False):
         self.lib = load_library()
         self.opts = Options()
         self.lib.dmpc_default_options(C.byref(self.opts))
@@ -115,6 +118,9 @@ class Engine:
         self.opts.quirk_carry = int(quirk_carry)
         self.opts.site_begin, self.opts.sites_total = site_begin, sites_total
         self.quirk_carry = bool(quirk_carry)
+        if fuse_tips is not None:
+            self.opts.fuse_tips = int(fuse_tips)
+        self.opts.fuse_exact = int(fuse_exact)
         self._shape = {}
 
     def _check(self, rc):

@@ -40,10 +40,21 @@ class Problem:
                 out = np.stack([[np.linalg.matrix_power(m[i, r], k) for r in range(n_rates)] for i in range(len(m))])
                 return out / out.sum(-1, keepdims=True)
             self.W, self.B = power(self.B, 4), power(self.B, 8)
+        if kind == "tiny":
+            # near-identity matrices with 1e-80 off-diagonals: three different bases under a vertex already push its
+            # partial below 1e-150, so even the smallest clades rescale (exercises the exact mode of fused clades)
+            def tiny(m, eps):
+                out = np.empty_like(m)
+                out[...] = eps
+                idx = np.arange(4)
+                out[..., idx, idx] = 1.0
+                return out
+            self.W = np.stack([tiny(self.W[i], 10.0 ** -(80 + i)) for i in range(len(self.W))])
+            self.B = np.stack([tiny(self.B[i], 10.0 ** -(70 + i)) for i in range(len(self.B))])
         self.pi = synth.LIM_PROBS.copy()
         self.edge = synth.random_tree(n, rng, shape)
         self.mrcas, self.clus = synth.pick_clusters(self.edge, n, k)
-        if kind == "iid":
+        if kind in ("iid", "tiny"):
             self.chars = synth.iid_alignment(n, n_sites, rng)
         elif kind == "diverged":
             self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[9], self.B[9], self.mrcas, self.pi, rng)

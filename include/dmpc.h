@@ -50,6 +50,11 @@ typedef struct dmpc_options {
                         loci, so sites are coupled through a sequential fp32 chain.  0: textbook per-site reduction */
   int site_begin;    /* this handle evaluates global sites [site_begin, site_begin + numLoci) of an alignment of */
   int sites_total;   /* sites_total sites (multi-GPU site sharding); single GPU: 0 and numLoci */
+  int fuse_tips;     /* small-clade fusion: vertices with at most this many tips below them are never written to
+                        HBM but recomputed from the tip masks by their nearest stored ancestor (default 8, max 15;
+                        <= 1 stores every vertex).  Results do not depend on it */
+  int fuse_exact;    /* 1: fused clades keep full per-vertex rescale bookkeeping from the start (the engine switches
+                        to it by itself the first time a fused clade could have rescaled) */
   int deferred;      /* 1: start in deferred-reduction mode (see dmpc_set_deferred): dmpc_loglik_create prunes and
                         gathers but leaves the root reduction to dmpc_shard_chain / dmpc_shard_finish */
 } dmpc_options;
@@ -123,6 +128,10 @@ typedef struct dmpc_stats {
   int last_active_tiles;    /* 128-site tiles that held a rescaled site in the last evaluation (0: the fp32
                                exponent chain is the identity on this handle's sites) */
   int num_tips, num_loci, num_rate_cats;   /* shape of the handle (the shim sizes edge outputs from it) */
+  unsigned long long last_algorithmic_bytes;   /* compulsory HBM bytes of the last evaluation's pruning: stored
+                               partials written + stored operands read (32 B each) + 1 B per tip operand */
+  int last_stored_vertices, last_fused_vertices;   /* vertices written to HBM / recomputed in registers */
+  int exact_mode;           /* 1 once fused clades run with full rescale bookkeeping */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which

@@ -240,3 +240,53 @@ def test_site_order_and_duplication_properties(packaged):
     l2, s2 = run(np.concatenate([al, al], axis=1))
     assert np.array_equal(s2[:p.S], s0) and np.array_equal(s2[p.S:], s0)
     assert rel(l2, 2 * l0) < 1e-13 and rel(l1, l0) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- small-clade fusion
+@pytest.mark.parametrize("fuse", [1, 2, 3, 8, 15])
+@pytest.mark.parametrize("n,S,k,R,kind,shape", [(300, 140, 5, 3, "evolved", "random"), (700, 130, 8, 3, "iid", "random"),
+                                                 (257, 70, 4, 1, "iid", "balanced"), (120, 60, 4, 4, "iid", "caterpillar"),
+                                                 (9, 40, 2, 2, "evolved", "random")])
+def test_fusion_does_not_change_results(packaged, oracle, fuse, n, S, k, R, kind, shape):
+    """Vertices with <= fuse_tips tips below them are recomputed in registers instead of stored: every setting gives
+    the same partials (bit for bit), exponents, topology and log-likelihoods over the whole scripted call sequence."""
+    from dmphyclus_b200.engine import Engine
+    if R > 3:
+        packaged = dict(packaged)
+        packaged["within"] = np.concatenate([packaged["within"]] * 2, axis=1)[:, :R]
+        packaged["between"] = np.concatenate([packaged["between"], np.roll(packaged["between"], 1, axis=0)], axis=1)[:, :R]
+    p = Problem(packaged, n, S, k, R, kind, shape, seed=n + fuse)
+    got, want = run_script(Engine(fuse_tips=fuse), p), run_script(oracle, p)
+    compare_to_golden(got, want, ll_tol=TOL, exact_partials=True)
+
+
+@pytest.mark.parametrize("start_exact", [False, True])
+def test_fused_clades_that_rescale(packaged, oracle, start_exact):
+    """Matrices with 1e-80 off-diagonals make three-tip clades rescale.  The fast fused path must notice (violation
+    flag), re-run the evaluation in exact mode and from then on keep per-vertex exponents for fused vertices."""
+    from dmphyclus_b200.engine import Engine
+    p = Problem(packaged, 400, 150, 6, 3, "tiny", seed=5)
+    eng = Engine(fuse_tips=8, fuse_exact=start_exact)
+    got, want = run_script(eng, p), run_script(oracle, p)
+    compare_to_golden(got, want, ll_tol=TOL, exact_partials=True)
+    hg, lg = p.create(eng)
+    ho, lo = p.create(oracle)
+    assert eng.stats(hg)["exact_mode"] == 1 and eng.stats(hg)["last_fused_vertices"] > 0
+    assert rel(lg, lo) < TOL
+    for v in range(p.n, 2 * p.n - 1, 37):                 # stored and fused vertices alike
+        (sg, eg), (so, eo) = eng.partial(hg, v), oracle.partial(ho, v)
+        assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=2e-7, atol=0), v
+    eng.finalDeallocate(hg); oracle.finalDeallocate(ho)
+
+
+def test_fused_vertices_are_readable(packaged, engine, oracle):
+    """dmpc_get_partial of a vertex that is never stored replays its clade program."""
+    p = Problem(packaged, 200, 90, 5, 3, "evolved", seed=3)
+    hg, _ = p.create(engine)
+    ho, _ = p.create(oracle)
+    st = engine.stats(hg)
+    assert st["last_fused_vertices"] > st["last_stored_vertices"] > 0
+    assert st["last_fused_vertices"] + st["last_stored_vertices"] == p.n - 1
+    for v in range(p.n, 2 * p.n - 1):
+        assert np.array_equal(engine.partial(hg, v)[0], oracle.partial(ho, v)[0]), v
+    engine.finalDeallocate(hg); oracle.finalDeallocate(ho)
