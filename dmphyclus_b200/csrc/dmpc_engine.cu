@@ -42,6 +42,7 @@ struct ResPack {
   Task* h_tasks = nullptr;       // pinned
   int32_t* h_curList = nullptr;  // pinned
   Token* h_tokens = nullptr;     // pinned
+  int32_t* h_tipList = nullptr;  // pinned
   HostResult* h_res = nullptr;   // pinned
   size_t cap = 0;                // internal vertices the pinned buffers can hold
 };
@@ -81,6 +82,8 @@ struct dmpc_tree {
   bool smemSet[2] = {false, false};
   Token* d_tokens = nullptr;
   Token* h_tokens = nullptr;     // pinned
+  int32_t* d_tipList = nullptr;
+  int32_t* h_tipList = nullptr;  // pinned
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
   template <class Tp>
@@ -122,16 +125,18 @@ int acquirePack(dmpc_tree* t) {
     if (p.h_tasks) cudaFreeHost(p.h_tasks);
     if (p.h_curList) cudaFreeHost(p.h_curList);
     if (p.h_tokens) cudaFreeHost(p.h_tokens);
-    p.h_tasks = nullptr; p.h_curList = nullptr; p.h_tokens = nullptr; p.cap = 0;
+    if (p.h_tipList) cudaFreeHost(p.h_tipList);
+    p.h_tasks = nullptr; p.h_curList = nullptr; p.h_tokens = nullptr; p.h_tipList = nullptr; p.cap = 0;
     const size_t cap = std::max<size_t>(1024, (size_t)t->nInt * 5 / 4);
     CUDA_TRY(cudaHostAlloc((void**)&p.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_curList, cap * sizeof(int32_t), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_tokens, 2 * cap * sizeof(Token), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_tipList, 2 * cap * sizeof(int32_t), cudaHostAllocDefault));
     p.cap = cap;
   }
   t->stream = p.stream;
   for (int i = 0; i < 5; i++) t->ev[i] = p.ev[i];
-  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens;
+  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens; t->h_tipList = p.h_tipList;
   return DMPC_OK;
 }
 
@@ -161,7 +166,7 @@ int allocSlot(dmpc_tree* t, int slot) {
 int allocElist(dmpc_tree* t, int kcap) {
   // the previous list (if any) stays in the pool until the handle dies; growth is rare and geometric
   t->rv.Kcap = kcap;
-  t->rv.Q = std::max(512, kcap);
+  t->rv.Q = std::max(512, (kcap + 3) & ~3);
   t->st.exponent_capacity = kcap;
   return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
 }
@@ -206,17 +211,21 @@ dmpc_tree* g_constOwner[64] = {nullptr};
 
 int rootStage(dmpc_tree* t, double* ll);
 
-size_t fusedSmem(int R) { return (size_t)(2 * R * 64 + FUSE_DEPTH * R * 4 * TILE) * sizeof(double) + 2 * R * 16; }
+constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
+
+size_t fusedSmem(int R) {
+  return (size_t)(2 * R * 64 + FUSE_DEPTH * R * 4 * TILE) * sizeof(double) + 2 * FUSE_MAX_TIPS * TILE + 2 * R * 16;
+}
 
 template <int RT>
-int launchFusedLevel(dmpc_tree* t, dim3 grid, const Task* lt) {
+int launchFusedLevel(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
   const size_t smem = fusedSmem(RT);
   if (t->exact) {
     if (!t->smemSet[1]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[1] = true; }
-    k_prune_fused<RT, true><<<grid, TILE, smem, t->stream>>>(t->dv, lt, t->d_tokens, t->rv.overflow + 2);
+    k_prune_fused<RT, true><<<grid, TILE, smem, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
   } else {
     if (!t->smemSet[0]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[0] = true; }
-    k_prune_fused<RT, false><<<grid, TILE, smem, t->stream>>>(t->dv, lt, t->d_tokens, t->rv.overflow + 2);
+    k_prune_fused<RT, false><<<grid, TILE, smem, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
   }
   return DMPC_OK;
 }
@@ -227,20 +236,28 @@ int runPlan(dmpc_tree* t) {
   const int nLevels = (int)p.levelStart.size() - 1;
   if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
   CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
-  for (int l = 0; l < nLevels; l++) {
-    const int n = p.levelStart[l + 1] - p.levelStart[l];
-    const dim3 grid((unsigned)n, (unsigned)t->T);
+  int launches = 0;
+  for (int l = 0; l < nLevels;) {
+    int n = p.levelStart[l + 1] - p.levelStart[l];
     const Task* lt = t->d_tasks + p.levelStart[l];
     int rc = DMPC_OK;
     if (t->ht.fuseTips > 1) {
+      // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.x == 1)
+      int l2 = l + 1;
+      bool run = n <= NARROW_LEVEL;
+      if (run) while (l2 < nLevels && p.levelStart[l2 + 1] - p.levelStart[l2] <= NARROW_LEVEL) l2++;
+      if (run && l2 > l + 1) n = p.levelStart[l2] - p.levelStart[l]; else { run = false; l2 = l + 1; }
+      const dim3 grid(run ? 1u : (unsigned)n, (unsigned)t->T);
       switch (t->R) {
-        case 1: rc = launchFusedLevel<1>(t, grid, lt); break;
-        case 2: rc = launchFusedLevel<2>(t, grid, lt); break;
-        case 3: rc = launchFusedLevel<3>(t, grid, lt); break;
-        default: rc = launchFusedLevel<4>(t, grid, lt); break;
+        case 1: rc = launchFusedLevel<1>(t, grid, lt, n); break;
+        case 2: rc = launchFusedLevel<2>(t, grid, lt, n); break;
+        case 3: rc = launchFusedLevel<3>(t, grid, lt, n); break;
+        default: rc = launchFusedLevel<4>(t, grid, lt, n); break;
       }
       if (rc) return rc;
+      l = l2;
     } else {
+      const dim3 grid((unsigned)n, (unsigned)t->T);
       switch (t->R) {
         case 1: k_prune_level<1><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
         case 2: k_prune_level<2><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
@@ -248,13 +265,15 @@ int runPlan(dmpc_tree* t) {
         case 4: k_prune_level<4><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
         default: k_prune_level<0><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
       }
+      l++;
     }
     t->st.kernel_launches++;
+    launches++;
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(t->ev[1], t->stream));
   t->st.last_levels = nLevels;
-  t->st.last_prune_launches = nLevels;
+  t->st.last_prune_launches = launches;
   return DMPC_OK;
 }
 
@@ -279,6 +298,8 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     if (nTok) {
       std::memcpy(t->h_tokens, p.tokens.data(), (size_t)nTok * sizeof(Token));
       CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, (size_t)nTok * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+      std::memcpy(t->h_tipList, p.tipList.data(), p.tipList.size() * sizeof(int32_t));
+      CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
     }
   }
   if ((rc = runPlan(t))) return rc;
@@ -313,21 +334,32 @@ int launchGather(dmpc_tree* t) {
   return DMPC_OK;
 }
 
-size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 4) rows of RP floats + 1 marker byte per row
-  const size_t cap = 2 * (size_t)t->rv.Q + 4;
-  return 2 * cap * t->rv.RP * sizeof(float) + 2 * cap;
+size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 8) rows of RP floats, 1 marker byte per group of 4 rows, metadata
+  const size_t cap = 2 * (size_t)t->rv.Q + 8;
+  return 2 * cap * t->rv.RP * sizeof(float) + 2 * (cap / 4) + 4 * sizeof(int) + 16;
+}
+
+template <int RP, int RC>
+int launchChainT(dmpc_tree* t, size_t smem) {
+  CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chain<RP, RC><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  return DMPC_OK;
 }
 
 int launchChain(dmpc_tree* t) {
   const size_t smem = chainSmem(t);
   if (smem > 220 * 1024) return fail(DMPC_ERR_ARG, "rescale list too deep for the chain kernel's staging buffers");
-  if (t->rv.RP == 4) {
-    CUDA_TRY(cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_chain<4><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(k_chain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_chain<8><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  int rc = DMPC_OK;
+  switch (t->R) {
+    case 2: rc = launchChainT<4, 2>(t, smem); break;
+    case 3: rc = launchChainT<4, 3>(t, smem); break;
+    case 4: rc = launchChainT<4, 4>(t, smem); break;
+    case 5: rc = launchChainT<8, 5>(t, smem); break;
+    case 6: rc = launchChainT<8, 6>(t, smem); break;
+    case 7: rc = launchChainT<8, 7>(t, smem); break;
+    default: rc = launchChainT<8, 8>(t, smem); break;
   }
+  if (rc) return rc;
   t->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -484,6 +516,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     if ((r2 = t->alloc(&t->d_lut, (size_t)2 * t->R * 64))) return r2;
     if ((r2 = t->alloc(&t->d_tasks, (size_t)t->nInt))) return r2;
     if ((r2 = t->alloc(&t->d_tokens, (size_t)2 * t->nInt))) return r2;
+    if ((r2 = t->alloc(&t->d_tipList, (size_t)2 * t->nInt))) return r2;
     if ((r2 = t->alloc(&t->d_curList, (size_t)t->nInt))) return r2;
     if ((r2 = t->alloc(&t->dv.cur, (size_t)t->nInt))) return r2;
     if ((r2 = t->alloc(&t->rv.kmax, (size_t)t->Sp))) return r2;
@@ -723,13 +756,15 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
     if (!rp.tokens.empty()) {
       std::memcpy(t->h_tokens, rp.tokens.data(), rp.tokens.size() * sizeof(Token));
       CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, rp.tokens.size() * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+      std::memcpy(t->h_tipList, rp.tipList.data(), rp.tipList.size() * sizeof(int32_t));
+      CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, rp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
     }
     const dim3 grid(1, (unsigned)t->T);
     switch (t->R) {
-      case 1: rc = launchFusedLevel<1>(t, grid, t->d_tasks); break;
-      case 2: rc = launchFusedLevel<2>(t, grid, t->d_tasks); break;
-      case 3: rc = launchFusedLevel<3>(t, grid, t->d_tasks); break;
-      default: rc = launchFusedLevel<4>(t, grid, t->d_tasks); break;
+      case 1: rc = launchFusedLevel<1>(t, grid, t->d_tasks, 1); break;
+      case 2: rc = launchFusedLevel<2>(t, grid, t->d_tasks, 1); break;
+      case 3: rc = launchFusedLevel<3>(t, grid, t->d_tasks, 1); break;
+      default: rc = launchFusedLevel<4>(t, grid, t->d_tasks, 1); break;
     }
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());

@@ -229,6 +229,7 @@ struct HostTree {
   struct Plan {
     std::vector<Task> tasks;
     std::vector<Token> tokens;
+    std::vector<int32_t> tipList;                // tips read by the fused programs, task by task
     std::vector<int> levelStart;
     long long storedReads = 0, tipReads = 0, fusedOps = 0;
     bool uses[2] = {false, false};               // slots this plan writes
@@ -236,24 +237,26 @@ struct HostTree {
   };
 
   // mutate = false: introspection replay — tokens address the CURRENT slots and no state changes
-  void emitClade(int u, Plan& p, bool mutate = true) {
+  void emitClade(int u, Plan& p, int tipBase, bool mutate = true) {
     const int k0 = kids[2 * u], k1 = kids[2 * u + 1];
     Token t;
     t.a = t.b = 0;
     if (isTip(k0) && isTip(k1)) {
-      t.op = OP_CHERRY; t.a = k0; t.b = k1;
+      t.op = OP_CHERRY;
+      t.a = (int)p.tipList.size() - tipBase; p.tipList.push_back(k0);
+      t.b = (int)p.tipList.size() - tipBase; p.tipList.push_back(k1);
       p.tipReads += 2;
     } else if (isTip(k0) || isTip(k1)) {
-      emitClade(isTip(k0) ? k1 : k0, p, mutate);
+      emitClade(isTip(k0) ? k1 : k0, p, tipBase, mutate);
       t.op = OP_REGTIP | (isTip(k0) ? TOK_FIRST : 0);
-      t.b = isTip(k0) ? k0 : k1;
+      t.b = (int)p.tipList.size() - tipBase; p.tipList.push_back(isTip(k0) ? k0 : k1);
       p.tipReads += 1;
     } else {
       const int h = tips[k0] >= tips[k1] ? k0 : k1, o = h == k0 ? k1 : k0;   // heavier side first: stack depth <= log2
-      emitClade(h, p, mutate);
+      emitClade(h, p, tipBase, mutate);
       Token sp; sp.op = OP_SPILL; sp.a = sp.b = 0; sp.vertex = 0;
       p.tokens.push_back(sp);
-      emitClade(o, p, mutate);
+      emitClade(o, p, tipBase, mutate);
       t.op = OP_SLOTREG | (h == k0 ? TOK_FIRST : 0);
     }
     const int slot = mutate ? cur[u] ^ 1 : cur[u];
@@ -271,7 +274,8 @@ struct HostTree {
     Task k;
     k.out = outRow;
     k.flags = outSlot ? TF_OUTSLOT : 0;
-    k.prog0 = k.n0 = k.prog1 = k.n1 = 0;
+    k.prog = (int)p.tokens.size(); k.ntok = 0;
+    k.tipOff = (int)p.tipList.size(); k.nTips = 0;
     for (int j = 0; j < 2; j++) {
       const int c = kids[2 * v + j];
       int32_t& ref = j ? k.c1 : k.c0;
@@ -280,18 +284,19 @@ struct HostTree {
       } else if (fused(c)) {
         ref = c - numTips; k.flags |= j ? TF_C1FUSED : TF_C0FUSED;
         const int off = (int)p.tokens.size();
-        emitClade(c, p, mutate);
-        if (j) { k.prog1 = off; k.n1 = (int)p.tokens.size() - off; } else { k.prog0 = off; k.n0 = (int)p.tokens.size() - off; }
+        emitClade(c, p, k.tipOff, mutate);
+        k.ntok |= ((int)p.tokens.size() - off) << (16 * j);
       } else {
         ref = c - numTips; if (cur[c]) k.flags |= j ? TF_C1SLOT : TF_C0SLOT; p.storedReads++;
       }
     }
+    k.nTips = (int)p.tipList.size() - k.tipOff;
     if (within[kids[2 * v]]) k.flags |= TF_WITHIN;      // AugTree.cpp:125: the FIRST child's flag picks the matrix set
     return k;
   }
 
   void plan(Plan& p) {
-    p.tasks.clear(); p.tokens.clear(); p.levelStart.clear();
+    p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
     p.storedReads = p.tipReads = p.fusedOps = 0;
     p.uses[0] = p.uses[1] = false;
     if (solved[root()]) { p.levelStart.push_back(0); return; }

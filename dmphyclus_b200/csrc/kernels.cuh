@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TILE) k_prune_level(DevView v, const Task* __r
   constexpr int RB = RT > 0 ? RT : 1;                         // categories whose loads are batched
   __shared__ __align__(16) double s_lut[(RT > 0 ? RT : RMAX) * 64];
   const int R = RT > 0 ? RT : v.R;
-  const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks) + blockIdx.x);   // Task {out, c0, c1, flags}
+  const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x));   // Task {out, c0, c1, flags, ...}
   const int fl = tk.w;
   const int tile = blockIdx.y;
   const int site = tile * TILE + threadIdx.x;
@@ -235,192 +235,221 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
 }
 
 template <int RT, bool EXACT>
-__global__ void __launch_bounds__(TILE) k_prune_fused(DevView v, const Task* __restrict__ tasks,
-                                                      const Token* __restrict__ prog, int* violation) {
+__global__ void __launch_bounds__(TILE, 4) k_prune_fused(DevView v, const Task* __restrict__ tasks, int nTasks,
+                                                      const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
+                                                      int* violation) {
   extern __shared__ __align__(16) double s_mem[];
   double* const s_lut = s_mem;                                  // [2][RT][16][4]
   double* const s_stack = s_mem + 2 * RT * 64;                  // [FUSE_DEPTH][RT][4][TILE]
-  unsigned char* const s_below = reinterpret_cast<unsigned char*>(s_stack + FUSE_DEPTH * RT * 4 * TILE);   // [2*RT*16]
-  const int tid = threadIdx.x;
-  const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x));
-  const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x) + 1);
-  const int fl = tk0.w;
+  unsigned char* const s_mask = reinterpret_cast<unsigned char*>(s_stack + FUSE_DEPTH * RT * 4 * TILE);   // [2*FUSE_MAX_TIPS][TILE]
+  unsigned char* const s_below = s_mask + 2 * FUSE_MAX_TIPS * TILE;                                        // [2*RT*16]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile = blockIdx.y;
   const int site = tile * TILE + tid;
-  const int set = (fl & TF_WITHIN) ? 1 : 0;
-  const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
-  const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
   const size_t Sp = (size_t)v.Sp, rstride = Sp * 4;
-  const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk0.y * RT * Sp + site) * 4;
-  const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk0.z * RT * Sp + site) * 4;
-  unsigned ma = 0, mb = 0;
-  if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site];
-  if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site];
-  double a[RT][4], b[RT][4];
-  const bool early = !(fus0 | fus1);           // plain task: every child load is issued before any arithmetic
-  if (early) {
-#pragma unroll
-    for (int r = 0; r < RT; r++) {
-      if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
-      if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
-    }
-  }
-  if (!early || tip0 || tip1) {
-    for (int i = tid; i < 2 * RT * 64; i += TILE) s_lut[i] = v.lut[i];
-    if (tid < 2 * RT * 16) {
-      const double* q = v.lut + 4 * tid;
-      s_below[tid] = (unsigned char)(q[0] < 1e-150 && q[1] < 1e-150 && q[2] < 1e-150 && q[3] < 1e-150);
-    }
-    __syncthreads();
-  }
+  bool lutLoaded = false, trig = false;
 
-  double reg[RT][4];
-  bool trig = false;
-  // ---- the fused operands' programs
-  auto run = [&](int off, int n, int sp) {
-    for (int i = 0; i < n; i++) {
-      const int4 t4 = __ldg(reinterpret_cast<const int4*>(prog + off + i));
-      const int op = t4.x & 7;
-      if (op == OP_SPILL) {
+  // a launch covers one level (gridDim.x = its tasks, one per block) or, with gridDim.x == 1, a run of narrow
+  // levels whose tasks the block walks in order: a thread only ever reads partials of its own site, so the
+  // child -> parent dependencies inside the run are plain program order
+  for (int ti = blockIdx.x; ti < nTasks; ti += gridDim.x) {
+    const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
+    const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
+    const int fl = tk0.w;
+    const int set = (fl & TF_WITHIN) ? 1 : 0;
+    const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
+    const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
+    const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk0.y * RT * Sp + site) * 4;
+    const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk0.z * RT * Sp + site) * 4;
+    const bool early = !(fus0 | fus1);           // plain task: every child load is issued before any arithmetic
+    unsigned ma = 0, mb = 0;
+    if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site];
+    if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site];
+    double a[RT][4], b[RT][4];
+    if (early) {
+#pragma unroll
+      for (int r = 0; r < RT; r++) {
+        if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
+        if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
+      }
+    } else {
+      // the masks of every tip the programs read, fetched asynchronously in one go (4 sites per lane, one tip per
+      // warp and round); the stored operand, if any, is pulled into L2 meanwhile
+      const int nTips = tk1.w;
+      for (int j = wid; j < nTips; j += TILE / 32) {
+        const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + j) * Sp + tile * TILE + 4 * lane;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + j * TILE + 4 * lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < RT; r++) {
+        if (!tip0 && !fus0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + r * rstride));
+        if (!tip1 && !fus1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + r * rstride));
+      }
+    }
+    if (!lutLoaded && (!early || tip0 || tip1)) {
+      for (int i = tid; i < 2 * RT * 64; i += TILE) s_lut[i] = v.lut[i];
+      if (tid < 2 * RT * 16) {
+        const double* q = v.lut + 4 * tid;
+        s_below[tid] = (unsigned char)(q[0] < 1e-150 && q[1] < 1e-150 && q[2] < 1e-150 && q[3] < 1e-150);
+      }
+      lutLoaded = true;
+      if (early) __syncthreads();
+    }
+    if (!early) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+
+    double reg[RT][4];
+    // ---- the fused operands' programs
+    auto run = [&](int off, int n, int sp) {
+      for (int i = 0; i < n; i++) {
+        const int4 t4 = __ldg(reinterpret_cast<const int4*>(prog + off + i));
+        const int op = t4.x & 7;
+        if (op == OP_SPILL) {
+#pragma unroll
+          for (int r = 0; r < RT; r++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) s_stack[((sp * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
+          sp++;
+          continue;
+        }
+        const int tset = (t4.x & TOK_SET) ? 1 : 0, tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+        const bool firstFlag = (t4.x & TOK_FIRST) != 0;
+        unsigned m0 = 0, m1 = 0;
+        if (op == OP_CHERRY) { m0 = s_mask[t4.y * TILE + tid]; m1 = s_mask[t4.z * TILE + tid]; }
+        else if (op == OP_REGTIP) m1 = s_mask[t4.z * TILE + tid];
+        else sp--;
+        float e[RT];
+        bool resc = false;
+#pragma unroll
+        for (int r = 0; r < RT; r++) {
+          const double* P = c_P[tset][r];
+          const double* lutr = s_lut + (tset * RT + r) * 64;
+          double x[4], y[4];                     // x = term of the operand listed first in the token, y = the other
+          bool xTipBelow = false, yTipBelow = false;
+          if (op == OP_CHERRY) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
+            xTipBelow = s_below[(tset * RT + r) * 16 + m0]; yTipBelow = s_below[(tset * RT + r) * 16 + m1];
+          } else if (op == OP_REGTIP) {
+            matvec4(P, reg[r], x);
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
+            yTipBelow = s_below[(tset * RT + r) * 16 + m1];
+          } else {
+            double z[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) z[k] = s_stack[((sp * RT + r) * 4 + k) * TILE + tid];
+            matvec4(P, z, x);
+            matvec4(P, reg[r], y);
+          }
+          // child order: CHERRY lists the first child first; REGTIP's firstFlag says the tip (y) is the reference's
+          // first child, SLOTREG's that the popped operand (x) is
+          const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
+          if (EXACT) {
+            e[r] = 0.0f;
+            double s4[4];
+            if (xFirst) combineExact(x, y, s4, e[r]); else combineExact(y, x, s4, e[r]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) reg[r][k] = s4[k];
+            resc |= e[r] != 0.0f;
+          } else {
+            // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
+            // notice that one of them COULD have fired
+            if (op == OP_CHERRY) trig |= xTipBelow;
+            else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
+            else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
+#pragma unroll
+            for (int k = 0; k < 4; k++) reg[r][k] = __dmul_rn(x[k], y[k]);
+            trig |= maybeBelow4(reg[r]);
+          }
+        }
+        const size_t frow = (size_t)tile * v.nInt + t4.w;
+        if (EXACT) {
+          const int any = __syncthreads_or(resc);
+          if (any) {
+            float* pe = v.expoOf(tslot) + (size_t)t4.w * RT * Sp + site;
+#pragma unroll
+            for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
+          }
+          if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0) v.cur[t4.w] = (uint8_t)tslot; }
+        } else if (tid == 0) {
+          v.flagOf(tslot)[frow] = 0;
+          if (tile == 0) v.cur[t4.w] = (uint8_t)tslot;
+        }
+      }
+    };
+    const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff;
+    if (fus0) {
+      run(tk1.x, n0, 0);
+      if (fus1) {
 #pragma unroll
         for (int r = 0; r < RT; r++)
 #pragma unroll
-          for (int k = 0; k < 4; k++) s_stack[((sp * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
-        sp++;
-        continue;
+          for (int k = 0; k < 4; k++) s_stack[((0 * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
       }
-      const int tset = (t4.x & TOK_SET) ? 1 : 0, tslot = (t4.x & TOK_SLOT) ? 1 : 0;
-      const bool firstFlag = (t4.x & TOK_FIRST) != 0;
-      unsigned m0 = 0, m1 = 0;
-      if (op == OP_CHERRY) { m0 = v.tipmask[(size_t)t4.y * Sp + site]; m1 = v.tipmask[(size_t)t4.z * Sp + site]; }
-      else if (op == OP_REGTIP) m1 = v.tipmask[(size_t)t4.z * Sp + site];
-      else sp--;
-      float e[RT];
-      bool resc = false;
+    }
+    if (fus1) run(tk1.x + n0, n1, 1);
+    if (!early) {
 #pragma unroll
       for (int r = 0; r < RT; r++) {
-        const double* P = c_P[tset][r];
-        const double* lutr = s_lut + (tset * RT + r) * 64;
-        double x[4], y[4];                     // x = term of the operand listed first in the token, y = the other
-        bool xTipBelow = false, yTipBelow = false;
-        if (op == OP_CHERRY) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
-          xTipBelow = s_below[(tset * RT + r) * 16 + m0]; yTipBelow = s_below[(tset * RT + r) * 16 + m1];
-        } else if (op == OP_REGTIP) {
-          matvec4(P, reg[r], x);
-#pragma unroll
-          for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
-          yTipBelow = s_below[(tset * RT + r) * 16 + m1];
-        } else {
-          double z[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) z[k] = s_stack[((sp * RT + r) * 4 + k) * TILE + tid];
-          matvec4(P, z, x);
-          matvec4(P, reg[r], y);
-        }
-        // child order: CHERRY lists the first child first; for the other two firstFlag says whether the operand
-        // listed second (REGTIP: the tip) resp. first (SLOTREG: the popped one) is the reference's first child
-        const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
-        if (EXACT) {
-          e[r] = 0.0f;
-          double s[4];
-          if (xFirst) combineExact(x, y, s, e[r]); else combineExact(y, x, s, e[r]);
-#pragma unroll
-          for (int k = 0; k < 4; k++) reg[r][k] = s[k];
-          resc |= e[r] != 0.0f;
-        } else {
-          // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
-          // notice that one of them COULD have fired
-          if (op == OP_CHERRY) trig |= xTipBelow;
-          else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
-          else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
-#pragma unroll
-          for (int k = 0; k < 4; k++) reg[r][k] = __dmul_rn(x[k], y[k]);
-          trig |= maybeBelow4(reg[r]);
-        }
-      }
-      const size_t frow = (size_t)tile * v.nInt + t4.w;
-      if (EXACT) {
-        const int any = __syncthreads_or(resc);
-        if (any) {
-          float* pe = v.expoOf(tslot) + (size_t)t4.w * RT * Sp + site;
-#pragma unroll
-          for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
-        }
-        if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0) v.cur[t4.w] = (uint8_t)tslot; }
-      } else if (tid == 0) {
-        v.flagOf(tslot)[frow] = 0;
-        if (tile == 0) v.cur[t4.w] = (uint8_t)tslot;
+        if (!tip0 && !fus0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
+        if (!tip1 && !fus1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
       }
     }
-  };
-  if (fus0) {
-    run(tk1.x, tk1.y, 0);
-    if (fus1) {
-#pragma unroll
-      for (int r = 0; r < RT; r++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) s_stack[((0 * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
-    }
-  }
-  if (fus1) run(tk1.z, tk1.w, 1);
-  if (!early) {
+
+    // ---- the stored vertex itself: exact semantics always
+    const int os = (fl & TF_OUTSLOT) ? 1 : 0;
+    const size_t o = (size_t)tk0.x * RT * Sp + site;
+    double* po = v.partOf(os) + o * 4;
+    float* pe = v.expoOf(os) + o;
+    float e[RT];
+    bool rescaled = false;
 #pragma unroll
     for (int r = 0; r < RT; r++) {
-      if (!tip0 && !fus0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
-      if (!tip1 && !fus1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
-    }
-  }
-
-  // ---- the stored vertex itself: exact semantics always
-  const int os = (fl & TF_OUTSLOT) ? 1 : 0;
-  const size_t o = (size_t)tk0.x * RT * Sp + site;
-  double* po = v.partOf(os) + o * 4;
-  float* pe = v.expoOf(os) + o;
-  float e[RT];
-  bool rescaled = false;
+      const double* P = c_P[set][r];
+      const double* lutr = s_lut + (set * RT + r) * 64;
+      double first[4], second[4], s4[4];
+      if (tip0) {
 #pragma unroll
-  for (int r = 0; r < RT; r++) {
-    const double* P = c_P[set][r];
-    const double* lutr = s_lut + (set * RT + r) * 64;
-    double first[4], second[4], s[4];
-    if (tip0) {
+        for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
+      } else if (fus0) {
+        if (fus1) {
+          double z[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
-    } else if (fus0) {
-      if (fus1) {
-        double z[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) z[k] = s_stack[((0 * RT + r) * 4 + k) * TILE + tid];
-        matvec4(P, z, first);
+          for (int k = 0; k < 4; k++) z[k] = s_stack[((0 * RT + r) * 4 + k) * TILE + tid];
+          matvec4(P, z, first);
+        } else {
+          matvec4(P, reg[r], first);
+        }
       } else {
-        matvec4(P, reg[r], first);
+        matvec4(P, a[r], first);
       }
-    } else {
-      matvec4(P, a[r], first);
-    }
-    if (tip1) {
+      if (tip1) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
-    } else if (fus1) {
-      matvec4(P, reg[r], second);
-    } else {
-      matvec4(P, b[r], second);
+        for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
+      } else if (fus1) {
+        matvec4(P, reg[r], second);
+      } else {
+        matvec4(P, b[r], second);
+      }
+      e[r] = 0.0f;
+      combineExact(first, second, s4, e[r]);
+      st256(po + r * rstride, s4[0], s4[1], s4[2], s4[3]);
+      rescaled |= e[r] != 0.0f;
     }
-    e[r] = 0.0f;
-    combineExact(first, second, s, e[r]);
-    st256(po + r * rstride, s[0], s[1], s[2], s[3]);
-    rescaled |= e[r] != 0.0f;
-  }
-  const int any = __syncthreads_or(rescaled);
-  if (any) {
+    const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_stack reuse by the next task of a run
+    if (any) {
 #pragma unroll
-    for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
-  }
-  if (tid == 0) {
-    v.flagOf(os)[(size_t)tile * v.nInt + tk0.x] = (uint8_t)(any != 0);
-    if (tile == 0) v.cur[tk0.x] = (uint8_t)os;
+      for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
+    }
+    if (tid == 0) {
+      v.flagOf(os)[(size_t)tile * v.nInt + tk0.x] = (uint8_t)(any != 0);
+      if (tile == 0) v.cur[tk0.x] = (uint8_t)os;
+    }
   }
   if (!EXACT && trig) *violation = 1;
 }
@@ -527,7 +556,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
 // that rescaled anywhere), then thread 0 walks their exponent rows as ONE flat stream while the other warps
 // stage the next chunk of rows (and the end-of-site markers) in shared memory.  Categories beyond R ride along
 // as -inf so that the hot loop needs no guards.  When no site rescaled the kernel returns at once.
-template <int RP>
+template <int RP, int RC>
 __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   extern __shared__ float4 s_dyn[];
   constexpr int V = RP / 4;                       // float4 per row
@@ -540,11 +569,13 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
     return;
   }
 
-  // phase A: ordered compaction of the sites that rescaled anywhere (kmax > 0) + row prefix
+  // phase A: ordered compaction of the sites that rescaled anywhere (kmax > 0) + prefix of their row counts.
+  // A site's rows are padded to a multiple of 4 with zero rows (x + 0.0f == x), so that the walker consumes
+  // whole groups of 4 and a site can only end at a group boundary.
   int baseCnt = 0, baseRows = 0;
   for (int start = 0; start < S; start += nth) {
     const int s = start + tid;
-    const int km = s < S ? min(rv.kmax[s], rv.Kcap) : 0;
+    const int km = s < S ? (min(rv.kmax[s], rv.Kcap) + 3) & ~3 : 0;
     const int actv = km > 0;
     int ic = actv, ir = km;                        // inclusive warp scans
 #pragma unroll
@@ -575,7 +606,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   const int nact = baseCnt;
   if (tid == 0) rv.rowoff[nact] = baseRows;
   __syncthreads();
-  // staging chunks: chunk c = active sites whose row offset lies in [cQ, (c+1)Q); Q >= Kcap so no chunk is empty
+  // staging chunks: chunk c = active sites whose row offset lies in [cQ, (c+1)Q); Q >= padded Kcap so no chunk is empty
   const int nchunks = nact ? rv.rowoff[nact - 1] / Q + 1 : 0;
   for (int i = tid; i < nact; i += nth) {
     const int c = rv.rowoff[i] / Q;
@@ -584,84 +615,100 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   if (tid == 0) rv.chunkStart[nchunks] = nact;
   __syncthreads();
 
-  // phase B.  Shared memory: 2 buffers of (2Q + 4) rows, then 2 x (2Q + 4) end-of-site markers (1 byte per row)
-  const int cap = 2 * Q + 4;
+  // phase B.  Shared memory: 2 buffers of cap rows (+ one spare group the walker may prefetch), then one
+  // end-of-site marker per group of 4 rows, then per-buffer {first active index, rows}
+  const int cap = 2 * Q + 8;
   float4* const buf0 = s_dyn;
   unsigned char* const end0 = reinterpret_cast<unsigned char*>(s_dyn + (size_t)2 * cap * V);
-  float c[RP];
+  int* const meta0 = reinterpret_cast<int*>(end0 + 2 * (cap / 4));
+  float c[RC];
 #pragma unroll
-  for (int r = 0; r < RP; r++) c[r] = r < v.R ? rv.carryIn[r] : -INFINITY;
+  for (int r = 0; r < RC; r++) c[r] = rv.carryIn[r];
 
   auto stage = [&](int ch, int ltid, int nld, int b) {
     float4* const bufb = buf0 + (size_t)b * cap * V;
-    unsigned char* const endb = end0 + (size_t)b * cap;
+    unsigned char* const endb = end0 + (size_t)b * (cap / 4);
     const int i0 = rv.chunkStart[ch], i1 = rv.chunkStart[ch + 1];
     const int r0 = rv.rowoff[i0], nrows = rv.rowoff[i1] - r0, ns = i1 - i0;
-    const int padded = (nrows + 3) & ~3;                      // the walker consumes rows four at a time
-    for (int q = ltid; q < padded; q += nld) {
-      if (q >= nrows) {
+    if (ltid == 0) { meta0[2 * b] = i0; meta0[2 * b + 1] = nrows; }
+    for (int q = ltid; q < nrows + 4; q += nld) {
+      if (q >= nrows) {                           // the spare group: zeros, never an end
 #pragma unroll
         for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        endb[q] = 0;
+        if ((q & 3) == 0) endb[q >> 2] = 0;
         continue;
       }
       int lo = 0, hi = ns;                        // last k with rowoff[i0 + k] - r0 <= q
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rv.rowoff[i0 + mid] - r0 <= q) lo = mid; else hi = mid; }
       const int site = rv.act[i0 + lo], j = q - (rv.rowoff[i0 + lo] - r0);
+      const int km = min(rv.kmax[site], rv.Kcap);
       const float4* src = reinterpret_cast<const float4*>(rv.elist + ((size_t)site * rv.Kcap + j) * RP);
 #pragma unroll
-      for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = src[u];
-      endb[q] = (unsigned char)(q + 1 == rv.rowoff[i0 + lo + 1] - r0);
+      for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = j < km ? src[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((q & 3) == 0) endb[q >> 2] = (unsigned char)(q + 4 == rv.rowoff[i0 + lo + 1] - r0);
     }
   };
 
   if (nchunks > 0) stage(0, tid, nth, 0);
   __syncthreads();
-  int outIdx = 0;
   for (int ch = 0; ch < nchunks; ch++) {
     const int b = ch & 1;
     if (wid > 0) {
       if (ch + 1 < nchunks) stage(ch + 1, tid - 32, nth - 32, b ^ 1);
     } else if (tid == 0) {
-      const int i0 = rv.chunkStart[ch], i1 = rv.chunkStart[ch + 1];
-      const int nrows = rv.rowoff[i1] - rv.rowoff[i0];
       const float4* const bufb = buf0 + (size_t)b * cap * V;
-      const unsigned* const endw = reinterpret_cast<const unsigned*>(end0 + (size_t)b * cap);
-      outIdx = i0;
-      for (int q = 0; q < nrows; q += 4) {
-        float4 x[4][V];
+      const unsigned char* const endb = end0 + (size_t)b * (cap / 4);
+      int outIdx = meta0[2 * b];
+      const int nrows = meta0[2 * b + 1];
+      float4 x[4][V], y[4][V];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)j * V + u];
+      unsigned fx = endb[0], fy;
+      // two groups per trip: while one group is being added, the next one is already on its way from shared memory
+      auto addGroup = [&](const float4 (&g)[4][V], unsigned flag) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-          for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)(q + j) * V + u];
-        const unsigned mk = endw[q >> 2];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-          for (int u = 0; u < V; u++) {
-            c[4 * u + 0] = __fadd_rn(c[4 * u + 0], x[j][u].x); c[4 * u + 1] = __fadd_rn(c[4 * u + 1], x[j][u].y);
-            c[4 * u + 2] = __fadd_rn(c[4 * u + 2], x[j][u].z); c[4 * u + 3] = __fadd_rn(c[4 * u + 3], x[j][u].w);
+          for (int r = 0; r < RC; r++) {
+            const float4 w = g[j][r >> 2];
+            c[r] = __fadd_rn(c[r], (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w);
           }
-          if ((mk >> (8 * j)) & 0xffu) {          // last row of a site: maxExponent, exponentVec -= maxExponent
-            float m = c[0];
+        if (flag) {                               // last group of a site: maxExponent, exponentVec -= maxExponent
+          float m = c[0];
 #pragma unroll
-            for (int r = 1; r < RP; r++) m = fmaxf(m, c[r]);
+          for (int r = 1; r < RC; r++) m = fmaxf(m, c[r]);
 #pragma unroll
-            for (int r = 0; r < RP; r++) c[r] = __fsub_rn(c[r], m);
-            float4* co = reinterpret_cast<float4*>(rv.cout + (size_t)outIdx * RP);
+          for (int r = 0; r < RC; r++) c[r] = __fsub_rn(c[r], m);
+          float* co = rv.cout + (size_t)outIdx * RP;
 #pragma unroll
-            for (int u = 0; u < V; u++) co[u] = make_float4(c[4 * u], c[4 * u + 1], c[4 * u + 2], c[4 * u + 3]);
-            rv.mxo[outIdx] = m;
-            outIdx++;
-          }
+          for (int r = 0; r < RC; r++) co[r] = c[r];
+          rv.mxo[outIdx] = m;
+          outIdx++;
         }
+      };
+      for (int q = 0; q < nrows; q += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int u = 0; u < V; u++) y[j][u] = bufb[(size_t)(q + 4 + j) * V + u];
+        fy = endb[(q >> 2) + 1];
+        addGroup(x, fx);
+        if (q + 4 >= nrows) break;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)(q + 8 + j) * V + u];
+        fx = endb[(q >> 2) + 2];
+        addGroup(y, fy);
       }
     }
     __syncthreads();
   }
   if (tid == 0) {
 #pragma unroll
-    for (int r = 0; r < RP; r++) rv.carryOut[r] = r < v.R ? c[r] : 0.0f;
+    for (int r = 0; r < RMAX; r++) if (r < RC) rv.carryOut[r] = c[r];
   }
 }
 

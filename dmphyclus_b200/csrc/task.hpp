@@ -11,8 +11,9 @@ struct Task {
   int32_t out;            // internal index (vertex id - N) to write
   int32_t c0, c1;         // children in the reference's order: tip index, internal index, or root of a fused clade
   int32_t flags;
-  int32_t prog0, n0;      // token program of a fused child 0: offset into the token array, token count
-  int32_t prog1, n1;
+  int32_t prog;           // first token of this task's fused-operand programs (child 0's, then child 1's)
+  int32_t ntok;           // tokens of child 0's program | tokens of child 1's program << 16
+  int32_t tipOff, nTips;  // the tips those programs read: slice of the tip list; tokens name them by local index
 };
 enum : int32_t {
   TF_OUTSLOT = 1, TF_C0TIP = 2, TF_C1TIP = 4, TF_C0SLOT = 8, TF_C1SLOT = 16,
@@ -24,7 +25,7 @@ enum : int32_t {
 // partial of the vertex computed last, the stack lives in shared memory.
 struct Token {
   int32_t op;             // opcode | set << 3 | slot << 4 | firstFlag << 5
-  int32_t a, b;           // tip indices
+  int32_t a, b;           // tips, as indices into the task's slice of the tip list
   int32_t vertex;         // internal index of the vertex this token computes
 };
 enum : int32_t {
