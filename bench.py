@@ -269,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
     bytes_unfused = algorithmic_bytes(n, s_local, r)
     achieved = bytes_eval * args.steps / (prune_ms * 1e-3) / 1e9
     dev_bytes = st1["device_bytes"]
-    kernel_name = "k_prune_fused" if st1["last_fused_vertices"] else "k_prune_level"
+    kernel_name = "k_prune"
     eng.finalDeallocate(h)
 
     # ---------------------------------------------------------------- end-to-end leg (host buffers in, scalar out)

@@ -79,7 +79,6 @@ struct dmpc_tree {
   dmpc_stats st{};
   HostTree::Plan plan;
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
-  bool smemSet[2] = {false, false};
   Token* d_tokens = nullptr;
   Token* h_tokens = nullptr;     // pinned
   int32_t* d_tipList = nullptr;
@@ -159,7 +158,7 @@ int allocSlot(dmpc_tree* t, int slot) {
   const size_t n = (size_t)t->nInt * t->R * t->Sp;
   if ((rc = t->alloc(&t->dv.part[slot], n * 4))) return rc;
   if ((rc = t->alloc(&t->dv.expo[slot], n))) return rc;
-  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->T * t->nInt))) return rc;
+  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->R * t->T * t->nInt))) return rc;
   return DMPC_OK;
 }
 
@@ -213,24 +212,13 @@ int rootStage(dmpc_tree* t, double* ll);
 
 constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
 
-size_t fusedSmem(int R) {
-  return (size_t)(2 * R * 64 + FUSE_DEPTH * R * 4 * TILE) * sizeof(double) + 2 * FUSE_MAX_TIPS * TILE + 2 * R * 16;
-}
-
-template <int RT>
-int launchFusedLevel(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
-  const size_t smem = fusedSmem(RT);
-  if (t->exact) {
-    if (!t->smemSet[1]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[1] = true; }
-    k_prune_fused<RT, true><<<grid, TILE, smem, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
-  } else {
-    if (!t->smemSet[0]) { CUDA_TRY(cudaFuncSetAttribute(k_prune_fused<RT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); t->smemSet[0] = true; }
-    k_prune_fused<RT, false><<<grid, TILE, smem, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
-  }
+int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
+  if (t->exact) k_prune<true><<<grid, TILE, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
+  else k_prune<false><<<grid, TILE, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
   return DMPC_OK;
 }
 
-// the level launches of the current plan (tasks and tokens are already on the device)
+// the level launches of the current plan (tasks, tokens and tip lists are already on the device)
 int runPlan(dmpc_tree* t) {
   const HostTree::Plan& p = t->plan;
   const int nLevels = (int)p.levelStart.size() - 1;
@@ -240,33 +228,15 @@ int runPlan(dmpc_tree* t) {
   for (int l = 0; l < nLevels;) {
     int n = p.levelStart[l + 1] - p.levelStart[l];
     const Task* lt = t->d_tasks + p.levelStart[l];
-    int rc = DMPC_OK;
-    if (t->ht.fuseTips > 1) {
-      // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.x == 1)
-      int l2 = l + 1;
-      bool run = n <= NARROW_LEVEL;
-      if (run) while (l2 < nLevels && p.levelStart[l2 + 1] - p.levelStart[l2] <= NARROW_LEVEL) l2++;
-      if (run && l2 > l + 1) n = p.levelStart[l2] - p.levelStart[l]; else { run = false; l2 = l + 1; }
-      const dim3 grid(run ? 1u : (unsigned)n, (unsigned)t->T);
-      switch (t->R) {
-        case 1: rc = launchFusedLevel<1>(t, grid, lt, n); break;
-        case 2: rc = launchFusedLevel<2>(t, grid, lt, n); break;
-        case 3: rc = launchFusedLevel<3>(t, grid, lt, n); break;
-        default: rc = launchFusedLevel<4>(t, grid, lt, n); break;
-      }
-      if (rc) return rc;
-      l = l2;
-    } else {
-      const dim3 grid((unsigned)n, (unsigned)t->T);
-      switch (t->R) {
-        case 1: k_prune_level<1><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 2: k_prune_level<2><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 3: k_prune_level<3><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        case 4: k_prune_level<4><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-        default: k_prune_level<0><<<grid, TILE, 0, t->stream>>>(t->dv, lt); break;
-      }
-      l++;
-    }
+    // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.x == 1)
+    int l2 = l + 1;
+    bool run = n <= NARROW_LEVEL;
+    if (run) while (l2 < nLevels && p.levelStart[l2 + 1] - p.levelStart[l2] <= NARROW_LEVEL) l2++;
+    if (run && l2 > l + 1) n = p.levelStart[l2] - p.levelStart[l]; else { run = false; l2 = l + 1; }
+    const dim3 grid(run ? 1u : (unsigned)n, (unsigned)t->T, (unsigned)t->R);
+    int rc = launchPrune(t, grid, lt, n);
+    if (rc) return rc;
+    l = l2;
     t->st.kernel_launches++;
     launches++;
   }
@@ -497,7 +467,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->ht.withinIdx = withinMatListIndex; t->ht.betweenIdx = betweenMatListIndex;
   t->N = numTips; t->S = numLoci; t->R = numRateCats;
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
-  t->ht.fuseTips = numRateCats > 4 ? 1 : std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
+  t->ht.fuseTips = std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
   t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
   t->T = t->Sp / TILE;
@@ -712,6 +682,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   if ((rc = checkHandle(t))) return rc;
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
   *out = t->st;
+  out->exact_mode = t->exact ? 1 : 0;
   out->num_tips = t->N; out->num_loci = t->S; out->num_rate_cats = t->R;
   return DMPC_OK;
 }
@@ -759,13 +730,8 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
       std::memcpy(t->h_tipList, rp.tipList.data(), rp.tipList.size() * sizeof(int32_t));
       CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, rp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
     }
-    const dim3 grid(1, (unsigned)t->T);
-    switch (t->R) {
-      case 1: rc = launchFusedLevel<1>(t, grid, t->d_tasks, 1); break;
-      case 2: rc = launchFusedLevel<2>(t, grid, t->d_tasks, 1); break;
-      case 3: rc = launchFusedLevel<3>(t, grid, t->d_tasks, 1); break;
-      default: rc = launchFusedLevel<4>(t, grid, t->d_tasks, 1); break;
-    }
+    const dim3 grid(1, (unsigned)t->T, (unsigned)t->R);
+    rc = launchPrune(t, grid, t->d_tasks, 1);
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
     partSlot = 0; partRow = t->nReal;
@@ -773,16 +739,16 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   const size_t n = (size_t)t->R * t->Sp;
   std::vector<double> hs(n * 4);
   std::vector<float> he(n);
-  std::vector<uint8_t> hf((size_t)t->T);
+  std::vector<uint8_t> hf((size_t)t->R * t->T);
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[partSlot] + (size_t)partRow * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(he.data(), t->dv.expo[slot] + (size_t)idx * n, n * sizeof(float), cudaMemcpyDeviceToHost));
-  for (int b = 0; b < t->T; b++)
+  for (int b = 0; b < t->R * t->T; b++)
     CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nInt + idx, 1, cudaMemcpyDeviceToHost));
   for (int s = 0; s < t->S; s++)
     for (int r = 0; r < t->R; r++) {
       for (int k = 0; k < 4; k++) sol[((size_t)s * t->R + r) * 4 + k] = hs[((size_t)r * t->Sp + s) * 4 + k];
-      expo[(size_t)s * t->R + r] = hf[s / TILE] ? he[(size_t)r * t->Sp + s] : 0.0f;
+      expo[(size_t)s * t->R + r] = hf[r * t->T + s / TILE] ? he[(size_t)r * t->Sp + s] : 0.0f;
     }
   return DMPC_OK;
 }

@@ -6,8 +6,8 @@
 //                                           (internal vertex, rate, site); two slots s = 0,1 so that a
 //                                           rejected proposal rolls back by flipping a per-vertex slot bit
 //   expo[s]  f32    [N-1][R][Sp]            per-vertex rescale exponents (IntermediateNode.cpp:63: a FLOAT)
-//   flag[s]  u8     [T][N-1]                1 when any (site, rate) of the 128-site tile rescaled at that vertex;
-//                                           expo tiles whose flag is 0 are never read (and, for R <= 4, never written)
+//   flag[s]  u8     [R][T][N]               1 when any site of the 128-site tile rescaled at that vertex for that rate;
+//                                           expo tiles whose flag is 0 are never written nor read
 // One thread owns one site of one vertex for all R rates: its child loads are 256-bit (LDG.E.256), consecutive
 // threads touch consecutive 32-byte elements, so every warp request is 1 KB fully coalesced.  Per update the
 // compulsory traffic is 2 x 32 B read (internal children; 1 B for a tip) + 32 B written: 68-96 B, against
@@ -80,136 +80,34 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 prune_level: all dirty vertices of one level x all sites; one thread owns one site of one vertex for
-// ALL rate categories (the tip masks and the task descriptor are shared by the categories, and R x 2 x 32 B
-// of child loads are in flight per thread before the first use).
+// K2 prune: the dirty STORED vertices of one level x all sites x all rate categories.
 // Replaces IntermediateNode::ComputeSolutions/ComputeSolution (IntermediateNode.cpp:26-71) driven by
-// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, site tiles), 128 threads.
-// RT = compile-time number of rate categories (1..4); RT = 0 handles any R <= RMAX one category at a time.
-
-// one category of one (vertex, site): sol = (P*c0) % (P*c1) with the reference's two rescale checks.
-// "max(sol) < 1e-150" is tested as "every entry < 1e-150" (no NaNs on this path), the max itself is only
-// needed inside the rare branch.
-__device__ __forceinline__ void node_update(const double* __restrict__ P, const double* __restrict__ lutr, bool tip0,
-                                            bool tip1, unsigned ma, unsigned mb, const double (&a)[4],
-                                            const double (&b)[4], double (&s)[4], float& e) {
-  if (tip0) {
-    const double2 u = *reinterpret_cast<const double2*>(lutr + 4 * ma), w = *reinterpret_cast<const double2*>(lutr + 4 * ma + 2);
-    s[0] = u.x; s[1] = u.y; s[2] = w.x; s[3] = w.y;               // ones % y == y exactly
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = row4(P + 4 * i, a[0], a[1], a[2], a[3]);
-  }
-  if (s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150) {   // after child 0 (IntermediateNode.cpp:58-64)
-    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
-    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
-    e = (float)log(m);
-  }
-  if (tip1) {
-    const double2 u = *reinterpret_cast<const double2*>(lutr + 4 * mb), w = *reinterpret_cast<const double2*>(lutr + 4 * mb + 2);
-    s[0] = __dmul_rn(s[0], u.x); s[1] = __dmul_rn(s[1], u.y); s[2] = __dmul_rn(s[2], w.x); s[3] = __dmul_rn(s[3], w.y);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = __dmul_rn(s[i], row4(P + 4 * i, b[0], b[1], b[2], b[3]));
-  }
-  if (s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150) {   // after child 1: OVERWRITES the exponent
-    const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
-    s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
-    e = (float)log(m);
-  }
-}
-
-template <int RT>
-__global__ void __launch_bounds__(TILE) k_prune_level(DevView v, const Task* __restrict__ tasks) {
-  constexpr int RB = RT > 0 ? RT : 1;                         // categories whose loads are batched
-  __shared__ __align__(16) double s_lut[(RT > 0 ? RT : RMAX) * 64];
-  const int R = RT > 0 ? RT : v.R;
-  const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks + blockIdx.x));   // Task {out, c0, c1, flags, ...}
-  const int fl = tk.w;
-  const int tile = blockIdx.y;
-  const int site = tile * TILE + threadIdx.x;
-  const int set = (fl & TF_WITHIN) ? 1 : 0;
-  const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
-  const size_t Sp = (size_t)v.Sp, rstride = Sp * 4;            // doubles between consecutive categories
-  unsigned ma = 0, mb = 0;
-  if (tip0) ma = v.tipmask[(size_t)tk.y * Sp + site];
-  if (tip1) mb = v.tipmask[(size_t)tk.z * Sp + site];
-  const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk.y * R * Sp + site) * 4;
-  const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk.z * R * Sp + site) * 4;
-  const int os = (fl & TF_OUTSLOT) ? 1 : 0;
-  const size_t o = (size_t)tk.x * R * Sp + site;
-  double* po = v.partOf(os) + o * 4;
-  float* pe = v.expoOf(os) + o;
-
-  double a[RB][4], b[RB][4];
-  if (RT > 0) {                                                // every child load is issued before any arithmetic
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-      if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
-      if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
-    }
-  }
-  if (tip0 | tip1) {
-    for (int i = threadIdx.x; i < R * 64; i += TILE) s_lut[i] = v.lut[(size_t)set * R * 64 + i];
-    __syncthreads();
-  }
-  bool rescaled = false;
-  if (RT > 0) {
-    float e[RB];
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-      double s[4];
-      e[r] = 0.0f;
-      node_update(c_P[set][r], s_lut + 64 * r, tip0, tip1, ma, mb, a[r], b[r], s, e[r]);
-      st256(po + r * rstride, s[0], s[1], s[2], s[3]);
-      rescaled |= e[r] != 0.0f;
-    }
-    const int any = __syncthreads_or(rescaled);
-    if (any) {
-#pragma unroll
-      for (int r = 0; r < RB; r++) pe[r * Sp] = e[r];
-    }
-    if (threadIdx.x == 0) {
-      v.flagOf(os)[(size_t)tile * v.nInt + tk.x] = (uint8_t)(any != 0);
-      if (tile == 0) v.cur[tk.x] = (uint8_t)os;
-    }
-  } else {
-#pragma unroll 1
-    for (int r = 0; r < R; r++) {
-      double s[4];
-      float e = 0.0f;
-      if (!tip0) ld256(pa + r * rstride, a[0][0], a[0][1], a[0][2], a[0][3]);
-      if (!tip1) ld256(pb + r * rstride, b[0][0], b[0][1], b[0][2], b[0][3]);
-      node_update(c_P[set][r], s_lut + 64 * r, tip0, tip1, ma, mb, a[0], b[0], s, e);
-      st256(po + r * rstride, s[0], s[1], s[2], s[3]);
-      pe[r * Sp] = e;                                          // generic path: exponents always written
-      rescaled |= e != 0.0f;
-    }
-    const int any = __syncthreads_or(rescaled);
-    if (threadIdx.x == 0) {
-      v.flagOf(os)[(size_t)tile * v.nInt + tk.x] = (uint8_t)(any != 0);
-      if (tile == 0) v.cur[tk.x] = (uint8_t)os;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2f prune_fused: K2 with small-clade fusion.  An operand of a task may be a FUSED clade (<= 15 tips): its
-// vertices are never stored; the thread recomputes them for its site from the tip masks by running the clade's
-// token program (task.hpp) on a register accumulator + a shared-memory stack, then feeds the result into the
-// stored vertex's update.  HBM traffic drops from ~68 B per update to the stored vertices only (about a fifth
-// of the vertices of a random tree for fuseTips = 8), which moves the kernel off the HBM roof.
+// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, site tiles, R), 128 threads; one thread
+// owns one (site, rate) of its task: two 256-bit child loads (or mask bytes), `sol = (P c0) % (P c1)` with
+// products and sums rounded separately in Armadillo's order, the reference's two rescale checks, one 256-bit
+// store.  ~60 registers, so 8 CTAs (32 warps) per SM keep enough loads and fp64 chains in flight.
+//
+// Small-clade fusion.  An operand of a task may be a FUSED clade (<= 15 tips): its vertices are never stored;
+// the thread recomputes them for its (site, rate) from the tip masks by running the clade's token program
+// (task.hpp) on a register accumulator + a shared-memory stack, then feeds the result into the stored vertex's
+// update.  The masks of all tips a task's programs read are fetched with cp.async in one go.  HBM traffic drops
+// from ~68 B per update to the stored vertices only (about a fifth of the vertices of a random tree for
+// fuseTips = 8), which moves the kernel off the HBM roof towards the fp64 pipe.
 //
 // Rescaling inside a fused clade is legal but needs per-vertex exponents and tile flags.  FAST mode (EXACT =
 // false) assumes it does not happen, clears the fused vertices' flags, and raises *violation when a thread
 // sees a value that could have triggered it (conservative high-word test); the host then re-runs the
 // evaluation with EXACT = true, where every fused vertex gets the reference's full two-check treatment, a
 // block vote, and exponent rows — and keeps that mode for the handle.
+//
+// A launch covers one level (gridDim.x = its tasks) or, with gridDim.x == 1, a run of narrow levels whose tasks
+// each block walks in order: a thread only ever reads partials of its own (site, rate), so the child -> parent
+// dependencies inside the run are plain program order.
 __device__ __forceinline__ void matvec4(const double* __restrict__ P, const double (&x)[4], double (&y)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) y[i] = row4(P + 4 * i, x[0], x[1], x[2], x[3]);
 }
-__device__ __forceinline__ bool below4(const double (&s)[4]) {            // exact: max(s) < 1e-150
+__device__ __forceinline__ bool below4(const double (&s)[4]) {            // exact: max(s) < 1e-150 (no NaNs here)
   return s[0] < 1e-150 && s[1] < 1e-150 && s[2] < 1e-150 && s[3] < 1e-150;
 }
 __device__ __forceinline__ bool maybeBelow4(const double (&s)[4]) {       // conservative, integer pipe only
@@ -219,7 +117,7 @@ __device__ __forceinline__ bool maybeBelow4(const double (&s)[4]) {       // con
 // IntermediateNode.cpp:53-66 for one category: first child, check, second child, check (the second OVERWRITES)
 __device__ __forceinline__ void combineExact(const double (&first)[4], const double (&second)[4], double (&s)[4], float& e) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) s[i] = first[i];
+  for (int i = 0; i < 4; i++) s[i] = first[i];                  // ones % y == y exactly
   if (below4(s)) {
     const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
     s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
@@ -234,24 +132,23 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
   }
 }
 
-template <int RT, bool EXACT>
-__global__ void __launch_bounds__(TILE, 4) k_prune_fused(DevView v, const Task* __restrict__ tasks, int nTasks,
-                                                      const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                      int* violation) {
-  extern __shared__ __align__(16) double s_mem[];
-  double* const s_lut = s_mem;                                  // [2][RT][16][4]
-  double* const s_stack = s_mem + 2 * RT * 64;                  // [FUSE_DEPTH][RT][4][TILE]
-  unsigned char* const s_mask = reinterpret_cast<unsigned char*>(s_stack + FUSE_DEPTH * RT * 4 * TILE);   // [2*FUSE_MAX_TIPS][TILE]
-  unsigned char* const s_below = s_mask + 2 * FUSE_MAX_TIPS * TILE;                                        // [2*RT*16]
+constexpr int PRUNE_SMEM = (2 * 64 + FUSE_DEPTH * 4 * TILE) * 8 + 2 * FUSE_MAX_TIPS * TILE + 32;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(TILE, 8) k_prune(DevView v, const Task* __restrict__ tasks, int nTasks,
+                                                   const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
+                                                   int* violation) {
+  __shared__ __align__(16) double s_lut[2 * 64];                 // [set][mask][4] of this block's rate
+  __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
+  __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
+  __shared__ unsigned char s_below[32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int tile = blockIdx.y;
+  const int tile = blockIdx.y, r = blockIdx.z, R = v.R;
   const int site = tile * TILE + tid;
-  const size_t Sp = (size_t)v.Sp, rstride = Sp * 4;
+  const size_t Sp = (size_t)v.Sp;
+  const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
   bool lutLoaded = false, trig = false;
 
-  // a launch covers one level (gridDim.x = its tasks, one per block) or, with gridDim.x == 1, a run of narrow
-  // levels whose tasks the block walks in order: a thread only ever reads partials of its own site, so the
-  // child -> parent dependencies inside the run are plain program order
   for (int ti = blockIdx.x; ti < nTasks; ti += gridDim.x) {
     const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
     const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
@@ -259,50 +156,38 @@ __global__ void __launch_bounds__(TILE, 4) k_prune_fused(DevView v, const Task* 
     const int set = (fl & TF_WITHIN) ? 1 : 0;
     const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
     const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
-    const double* pa = v.partOf(fl & TF_C0SLOT) + ((size_t)tk0.y * RT * Sp + site) * 4;
-    const double* pb = v.partOf(fl & TF_C1SLOT) + ((size_t)tk0.z * RT * Sp + site) * 4;
-    const bool early = !(fus0 | fus1);           // plain task: every child load is issued before any arithmetic
+    const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site) * 4;
+    const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site) * 4;
+    const bool plain = !(fus0 | fus1);
     unsigned ma = 0, mb = 0;
-    if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site];
-    if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site];
-    double a[RT][4], b[RT][4];
-    if (early) {
-#pragma unroll
-      for (int r = 0; r < RT; r++) {
-        if (!tip0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
-        if (!tip1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
-      }
-    } else {
-      // the masks of every tip the programs read, fetched asynchronously in one go (4 sites per lane, one tip per
-      // warp and round); the stored operand, if any, is pulled into L2 meanwhile
-      const int nTips = tk1.w;
+    double a[4], b[4];
+    // every load this thread needs from HBM is issued here, before any arithmetic
+    if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site]; else if (!fus0) ld256(pa, a[0], a[1], a[2], a[3]);
+    if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site]; else if (!fus1) ld256(pb, b[0], b[1], b[2], b[3]);
+    if (!plain) {
+      const int nTips = tk1.w;                    // masks of every tip the programs read: 4 sites per lane, one tip per warp
       for (int j = wid; j < nTips; j += TILE / 32) {
         const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + j) * Sp + tile * TILE + 4 * lane;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + j * TILE + 4 * lane);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-      for (int r = 0; r < RT; r++) {
-        if (!tip0 && !fus0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + r * rstride));
-        if (!tip1 && !fus1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + r * rstride));
-      }
     }
-    if (!lutLoaded && (!early || tip0 || tip1)) {
-      for (int i = tid; i < 2 * RT * 64; i += TILE) s_lut[i] = v.lut[i];
-      if (tid < 2 * RT * 16) {
-        const double* q = v.lut + 4 * tid;
+    if (!lutLoaded && (!plain || tip0 || tip1)) {
+      if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
+      if (tid < 32) {
+        const double* q = v.lut + (size_t)((tid >> 4) * R + r) * 64 + 4 * (tid & 15);
         s_below[tid] = (unsigned char)(q[0] < 1e-150 && q[1] < 1e-150 && q[2] < 1e-150 && q[3] < 1e-150);
       }
       lutLoaded = true;
-      if (early) __syncthreads();
+      if (plain) __syncthreads();
     }
-    if (!early) {
+    if (!plain) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
     }
 
-    double reg[RT][4];
+    double reg[4];
     // ---- the fused operands' programs
     auto run = [&](int off, int n, int sp) {
       for (int i = 0; i < n; i++) {
@@ -310,75 +195,58 @@ __global__ void __launch_bounds__(TILE, 4) k_prune_fused(DevView v, const Task* 
         const int op = t4.x & 7;
         if (op == OP_SPILL) {
 #pragma unroll
-          for (int r = 0; r < RT; r++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) s_stack[((sp * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
+          for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid] = reg[k];
           sp++;
           continue;
         }
         const int tset = (t4.x & TOK_SET) ? 1 : 0, tslot = (t4.x & TOK_SLOT) ? 1 : 0;
         const bool firstFlag = (t4.x & TOK_FIRST) != 0;
-        unsigned m0 = 0, m1 = 0;
-        if (op == OP_CHERRY) { m0 = s_mask[t4.y * TILE + tid]; m1 = s_mask[t4.z * TILE + tid]; }
-        else if (op == OP_REGTIP) m1 = s_mask[t4.z * TILE + tid];
-        else sp--;
-        float e[RT];
-        bool resc = false;
+        const double* P = c_P[tset][r];
+        const double* lutr = s_lut + tset * 64;
+        double x[4], y[4];                       // x = term of the operand the token lists first, y = the other
+        bool xTipBelow = false, yTipBelow = false;
+        if (op == OP_CHERRY) {
+          const unsigned m0 = s_mask[t4.y * TILE + tid], m1 = s_mask[t4.z * TILE + tid];
 #pragma unroll
-        for (int r = 0; r < RT; r++) {
-          const double* P = c_P[tset][r];
-          const double* lutr = s_lut + (tset * RT + r) * 64;
-          double x[4], y[4];                     // x = term of the operand listed first in the token, y = the other
-          bool xTipBelow = false, yTipBelow = false;
-          if (op == OP_CHERRY) {
+          for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
+          xTipBelow = s_below[tset * 16 + m0]; yTipBelow = s_below[tset * 16 + m1];
+        } else if (op == OP_REGTIP) {
+          const unsigned m1 = s_mask[t4.z * TILE + tid];
+          matvec4(P, reg, x);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
-            xTipBelow = s_below[(tset * RT + r) * 16 + m0]; yTipBelow = s_below[(tset * RT + r) * 16 + m1];
-          } else if (op == OP_REGTIP) {
-            matvec4(P, reg[r], x);
+          for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
+          yTipBelow = s_below[tset * 16 + m1];
+        } else {
+          sp--;
+          double z[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
-            yTipBelow = s_below[(tset * RT + r) * 16 + m1];
-          } else {
-            double z[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) z[k] = s_stack[((sp * RT + r) * 4 + k) * TILE + tid];
-            matvec4(P, z, x);
-            matvec4(P, reg[r], y);
-          }
-          // child order: CHERRY lists the first child first; REGTIP's firstFlag says the tip (y) is the reference's
-          // first child, SLOTREG's that the popped operand (x) is
-          const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
-          if (EXACT) {
-            e[r] = 0.0f;
-            double s4[4];
-            if (xFirst) combineExact(x, y, s4, e[r]); else combineExact(y, x, s4, e[r]);
-#pragma unroll
-            for (int k = 0; k < 4; k++) reg[r][k] = s4[k];
-            resc |= e[r] != 0.0f;
-          } else {
-            // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
-            // notice that one of them COULD have fired
-            if (op == OP_CHERRY) trig |= xTipBelow;
-            else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
-            else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
-#pragma unroll
-            for (int k = 0; k < 4; k++) reg[r][k] = __dmul_rn(x[k], y[k]);
-            trig |= maybeBelow4(reg[r]);
-          }
+          for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid];
+          matvec4(P, z, x);
+          matvec4(P, reg, y);
         }
-        const size_t frow = (size_t)tile * v.nInt + t4.w;
+        // child order: CHERRY lists the first child first; REGTIP's firstFlag says the tip (y) is the reference's
+        // first child, SLOTREG's that the popped operand (x) is
+        const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
+        const size_t frow = flagRow + t4.w;
         if (EXACT) {
-          const int any = __syncthreads_or(resc);
-          if (any) {
-            float* pe = v.expoOf(tslot) + (size_t)t4.w * RT * Sp + site;
+          float e = 0.0f;
+          double s4[4];
+          if (xFirst) combineExact(x, y, s4, e); else combineExact(y, x, s4, e);
 #pragma unroll
-            for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
-          }
-          if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0) v.cur[t4.w] = (uint8_t)tslot; }
-        } else if (tid == 0) {
-          v.flagOf(tslot)[frow] = 0;
-          if (tile == 0) v.cur[t4.w] = (uint8_t)tslot;
+          for (int k = 0; k < 4; k++) reg[k] = s4[k];
+          const int any = __syncthreads_or(e != 0.0f);
+          if (any) v.expoOf(tslot)[((size_t)t4.w * R + r) * Sp + site] = e;
+          if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot; }
+        } else {
+          // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
+          // notice that one of them COULD have fired
+          if (op == OP_CHERRY) trig |= xTipBelow;
+          else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
+          else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
+#pragma unroll
+          for (int k = 0; k < 4; k++) reg[k] = __dmul_rn(x[k], y[k]);
+          trig |= maybeBelow4(reg);
+          if (tid == 0) { v.flagOf(tslot)[frow] = 0; if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot; }
         }
       }
     };
@@ -387,68 +255,48 @@ __global__ void __launch_bounds__(TILE, 4) k_prune_fused(DevView v, const Task* 
       run(tk1.x, n0, 0);
       if (fus1) {
 #pragma unroll
-        for (int r = 0; r < RT; r++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) s_stack[((0 * RT + r) * 4 + k) * TILE + tid] = reg[r][k];
+        for (int k = 0; k < 4; k++) s_stack[k * TILE + tid] = reg[k];
       }
     }
     if (fus1) run(tk1.x + n0, n1, 1);
-    if (!early) {
-#pragma unroll
-      for (int r = 0; r < RT; r++) {
-        if (!tip0 && !fus0) ld256(pa + r * rstride, a[r][0], a[r][1], a[r][2], a[r][3]);
-        if (!tip1 && !fus1) ld256(pb + r * rstride, b[r][0], b[r][1], b[r][2], b[r][3]);
-      }
-    }
 
     // ---- the stored vertex itself: exact semantics always
+    const double* P = c_P[set][r];
+    const double* lutr = s_lut + set * 64;
+    double first[4], second[4], s4[4];
+    if (tip0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
+    } else if (fus0) {
+      if (fus1) {
+        double z[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid];
+        matvec4(P, z, first);
+      } else {
+        matvec4(P, reg, first);
+      }
+    } else {
+      matvec4(P, a, first);
+    }
+    if (tip1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
+    } else if (fus1) {
+      matvec4(P, reg, second);
+    } else {
+      matvec4(P, b, second);
+    }
+    float e = 0.0f;
+    combineExact(first, second, s4, e);
     const int os = (fl & TF_OUTSLOT) ? 1 : 0;
-    const size_t o = (size_t)tk0.x * RT * Sp + site;
-    double* po = v.partOf(os) + o * 4;
-    float* pe = v.expoOf(os) + o;
-    float e[RT];
-    bool rescaled = false;
-#pragma unroll
-    for (int r = 0; r < RT; r++) {
-      const double* P = c_P[set][r];
-      const double* lutr = s_lut + (set * RT + r) * 64;
-      double first[4], second[4], s4[4];
-      if (tip0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
-      } else if (fus0) {
-        if (fus1) {
-          double z[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) z[k] = s_stack[((0 * RT + r) * 4 + k) * TILE + tid];
-          matvec4(P, z, first);
-        } else {
-          matvec4(P, reg[r], first);
-        }
-      } else {
-        matvec4(P, a[r], first);
-      }
-      if (tip1) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
-      } else if (fus1) {
-        matvec4(P, reg[r], second);
-      } else {
-        matvec4(P, b[r], second);
-      }
-      e[r] = 0.0f;
-      combineExact(first, second, s4, e[r]);
-      st256(po + r * rstride, s4[0], s4[1], s4[2], s4[3]);
-      rescaled |= e[r] != 0.0f;
-    }
-    const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_stack reuse by the next task of a run
-    if (any) {
-#pragma unroll
-      for (int r = 0; r < RT; r++) pe[r * Sp] = e[r];
-    }
+    const size_t o = ((size_t)tk0.x * R + r) * Sp + site;
+    st256(v.partOf(os) + o * 4, s4[0], s4[1], s4[2], s4[3]);
+    const int any = __syncthreads_or(e != 0.0f);     // also fences s_mask / s_stack reuse by the next task of a run
+    if (any) v.expoOf(os)[o] = e;
     if (tid == 0) {
-      v.flagOf(os)[(size_t)tile * v.nInt + tk0.x] = (uint8_t)(any != 0);
-      if (tile == 0) v.cur[tk0.x] = (uint8_t)os;
+      v.flagOf(os)[flagRow + tk0.x] = (uint8_t)(any != 0);
+      if (tile == 0 && r == 0) v.cur[tk0.x] = (uint8_t)os;
     }
   }
   if (!EXACT && trig) *violation = 1;
@@ -497,13 +345,18 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
 #pragma unroll
   for (int r = 0; r < RP; r++) k[r] = 0;
   float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
+  const size_t fstride = (size_t)v.T * v.nInt;                  // between the flag planes of consecutive rates
   const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nInt : nullptr;
   const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nInt : nullptr;
   for (int base = 0; base < v.nReal; base += TILE) {
     const int nd = base + tid;
     bool f = false;
     int slot = 0;
-    if (nd < v.nReal) { slot = v.cur[nd]; f = (slot ? f1[nd] : f0[nd]) != 0; }
+    if (nd < v.nReal) {
+      slot = v.cur[nd];
+      const uint8_t* fp = (slot ? f1 : f0) + nd;
+      for (int r = 0; r < R; r++) f |= fp[r * fstride] != 0;
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) s_wcnt[wid] = __popc(bal);
     __syncthreads();
