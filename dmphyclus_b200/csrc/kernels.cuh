@@ -350,29 +350,29 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
   const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nInt : nullptr;
   for (int base = 0; base < v.nReal; base += TILE) {
     const int nd = base + tid;
-    bool f = false;
-    int slot = 0;
+    int slot = 0, rbits = 0;                     // rates for which this vertex rescaled somewhere in the tile
     if (nd < v.nReal) {
       slot = v.cur[nd];
       const uint8_t* fp = (slot ? f1 : f0) + nd;
-      for (int r = 0; r < R; r++) f |= fp[r * fstride] != 0;
+      for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
     }
+    const bool f = rbits != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     if (lane == 0) s_wcnt[wid] = __popc(bal);
     __syncthreads();
     int off = __popc(bal & ((1u << lane) - 1)), n = 0;
 #pragma unroll
     for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
-    if (f) s_list[off] = (nd << 1) | slot;
+    if (f) s_list[off] = (nd << 9) | (slot << 8) | rbits;
     __syncthreads();
     for (int i = 0; i < n; i += 4) {
       float e[4][RP];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int ent = s_list[min(i + j, n - 1)];
-        const float* src = v.expoOf(ent & 1) + (size_t)(ent >> 1) * R * Sp + site;
+        const float* src = v.expoOf((ent >> 8) & 1) + (size_t)(ent >> 9) * R * Sp + site;
 #pragma unroll
-        for (int r = 0; r < RP; r++) e[j][r] = (r < R && i + j < n) ? src[r * Sp] : 0.0f;
+        for (int r = 0; r < RP; r++) e[j][r] = (((ent >> r) & 1) && i + j < n) ? src[r * Sp] : 0.0f;   // unflagged rows were never written
       }
 #pragma unroll
       for (int j = 0; j < 4; j++)
