@@ -181,6 +181,15 @@ int uploadConstants(dmpc_tree* t, const double* within, const double* between, c
         P[1][r][i * 4 + j] = within[16 * r + i + 4 * j];
       }
   if (t->constantsValid && !std::memcmp(P, t->hP, sizeof P) && !std::memcmp(pi, t->hPi, sizeof t->hPi)) return DMPC_OK;
+  // the fast fused path tests only the product of the two child terms for a possible rescale, which is sound when no
+  // term can exceed 1: entries in [0, 1] and row sums <= 1 (up to rounding).  Anything else -> exact mode for good.
+  for (int set = 0; set < 2 && !t->exact; set++)
+    for (int r = 0; r < t->R && !t->exact; r++)
+      for (int i = 0; i < 4; i++) {
+        double row = 0.0;
+        for (int j = 0; j < 4; j++) { const double x = P[set][r][i * 4 + j]; if (!(x >= 0.0 && x <= 1.0)) t->exact = true; row += x; }
+        if (!(row <= 1.0 + 1e-9)) t->exact = true;
+      }
   std::memcpy(t->hP, P, sizeof P);
   std::memcpy(t->hPi, pi, sizeof t->hPi);
   // tip lookup: P * indicator(mask), summed in gemv_emul_tinysq order (adding +0.0 terms is exact)
@@ -213,8 +222,8 @@ int rootStage(dmpc_tree* t, double* ll);
 constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
-  if (t->exact) k_prune<true><<<grid, TILE, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
-  else k_prune<false><<<grid, TILE, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
+  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
+  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
   return DMPC_OK;
 }
 

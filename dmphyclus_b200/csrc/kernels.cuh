@@ -24,7 +24,9 @@
 namespace dmpc {
 
 constexpr int RMAX = 8;         // rate categories supported (the packaged data uses 3)
-constexpr int TILE = 128;       // sites per block of the pruning kernel = flag granularity
+constexpr int TILE = 256;       // sites per block of the pruning kernel = flag granularity
+constexpr int PT = 128;         // threads of a pruning block
+constexpr int SPT = TILE / PT;  // sites per pruning thread
 constexpr int CHUNK = 256;      // sites per deterministic reduction chunk
 
 struct DevView {
@@ -82,21 +84,20 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
 // ------------------------------------------------------------------------------------------------
 // K2 prune: the dirty STORED vertices of one level x all sites x all rate categories.
 // Replaces IntermediateNode::ComputeSolutions/ComputeSolution (IntermediateNode.cpp:26-71) driven by
-// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, site tiles, R), 128 threads; one thread
-// owns one (site, rate) of its task: two 256-bit child loads (or mask bytes), `sol = (P c0) % (P c1)` with
-// products and sums rounded separately in Armadillo's order, the reference's two rescale checks, one 256-bit
-// store.  ~60 registers, so 8 CTAs (32 warps) per SM keep enough loads and fp64 chains in flight.
+// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, 256-site tiles, R), 128 threads; one
+// thread owns two sites of one rate of its task: 256-bit child loads (or mask bytes), `sol = (P c0) % (P c1)` with
+// products and sums rounded separately in Armadillo's order, the reference's two rescale checks, 256-bit stores.
 //
 // Small-clade fusion.  An operand of a task may be a FUSED clade (<= 15 tips): its vertices are never stored;
 // the thread recomputes them for its (site, rate) from the tip masks by running the clade's token program
 // (task.hpp) on a register accumulator + a shared-memory stack, then feeds the result into the stored vertex's
-// update.  The masks of all tips a task's programs read are fetched with cp.async in one go.  HBM traffic drops
+// update.  The masks of all tips a task's programs read, and the tokens, are staged in shared memory in one go.  HBM traffic drops
 // from ~68 B per update to the stored vertices only (about a fifth of the vertices of a random tree for
 // fuseTips = 8), which moves the kernel off the HBM roof towards the fp64 pipe.
 //
 // Rescaling inside a fused clade is legal but needs per-vertex exponents and tile flags.  FAST mode (EXACT =
 // false) assumes it does not happen, clears the fused vertices' flags, and raises *violation when a thread
-// sees a value that could have triggered it (conservative high-word test); the host then re-runs the
+// sees a product that could have triggered it (conservative high-word test); the host then re-runs the
 // evaluation with EXACT = true, where every fused vertex gets the reference's full two-check treatment, a
 // block vote, and exponent rows — and keeps that mode for the handle.
 //
@@ -132,19 +133,19 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
   }
 }
 
-constexpr int PRUNE_SMEM = (2 * 64 + FUSE_DEPTH * 4 * TILE) * 8 + 2 * FUSE_MAX_TIPS * TILE + 32;
-
 template <bool EXACT>
-__global__ void __launch_bounds__(TILE, 8) k_prune(DevView v, const Task* __restrict__ tasks, int nTasks,
-                                                   const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                   int* violation) {
+__global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restrict__ tasks, int nTasks,
+                                                 const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
+                                                 int* violation) {
+  // one thread = SPT sites (tid, tid + PT, ...) of one rate: what is uniform across the block — token decoding, the
+  // P matrix elements, addresses — is paid once per SPT updates
   __shared__ __align__(16) double s_lut[2 * 64];                 // [set][mask][4] of this block's rate
   __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
   __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
-  __shared__ unsigned char s_below[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ __align__(16) int4 s_tok[3 * FUSE_MAX_TIPS + 4];
+  const int tid = threadIdx.x;
   const int tile = blockIdx.y, r = blockIdx.z, R = v.R;
-  const int site = tile * TILE + tid;
+  const int site0 = tile * TILE + tid;
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
   bool lutLoaded = false, trig = false;
@@ -156,29 +157,34 @@ __global__ void __launch_bounds__(TILE, 8) k_prune(DevView v, const Task* __rest
     const int set = (fl & TF_WITHIN) ? 1 : 0;
     const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
     const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
-    const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site) * 4;
-    const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site) * 4;
+    const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site0) * 4;
+    const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site0) * 4;
     const bool plain = !(fus0 | fus1);
-    unsigned ma = 0, mb = 0;
-    double a[4], b[4];
+    const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff, ntok = n0 + n1;
+    unsigned ma[SPT], mb[SPT];
+    double a[SPT][4], b[SPT][4];
     // every load this thread needs from HBM is issued here, before any arithmetic
-    if (tip0) ma = v.tipmask[(size_t)tk0.y * Sp + site]; else if (!fus0) ld256(pa, a[0], a[1], a[2], a[3]);
-    if (tip1) mb = v.tipmask[(size_t)tk0.z * Sp + site]; else if (!fus1) ld256(pb, b[0], b[1], b[2], b[3]);
+#pragma unroll
+    for (int u = 0; u < SPT; u++) {
+      if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT];
+      else if (!fus0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
+      if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT];
+      else if (!fus1) ld256(pb + (size_t)u * PT * 4, b[u][0], b[u][1], b[u][2], b[u][3]);
+    }
     if (!plain) {
-      const int nTips = tk1.w;                    // masks of every tip the programs read: 4 sites per lane, one tip per warp
-      for (int j = wid; j < nTips; j += TILE / 32) {
-        const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + j) * Sp + tile * TILE + 4 * lane;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + j * TILE + 4 * lane);
+      // the masks of every tip the programs read (4 sites per cp.async) and the tokens themselves, into shared memory
+      const int nTips = tk1.w;
+      for (int j = tid; j < nTips * (TILE / 4); j += PT) {
+        const int tipIdx = j / (TILE / 4), q = j - tipIdx * (TILE / 4);
+        const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + tipIdx) * Sp + tile * TILE + 4 * q;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + tipIdx * TILE + 4 * q);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (tid < ntok) s_tok[tid] = __ldg(reinterpret_cast<const int4*>(prog + tk1.x + tid));
     }
     if (!lutLoaded && (!plain || tip0 || tip1)) {
-      if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
-      if (tid < 32) {
-        const double* q = v.lut + (size_t)((tid >> 4) * R + r) * 64 + 4 * (tid & 15);
-        s_below[tid] = (unsigned char)(q[0] < 1e-150 && q[1] < 1e-150 && q[2] < 1e-150 && q[3] < 1e-150);
-      }
+      s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];       // PT == 2 * 64
       lutLoaded = true;
       if (plain) __syncthreads();
     }
@@ -187,113 +193,140 @@ __global__ void __launch_bounds__(TILE, 8) k_prune(DevView v, const Task* __rest
       __syncthreads();
     }
 
-    double reg[4];
+    double reg[SPT][4];
     // ---- the fused operands' programs
-    auto run = [&](int off, int n, int sp) {
-      for (int i = 0; i < n; i++) {
-        const int4 t4 = __ldg(reinterpret_cast<const int4*>(prog + off + i));
+    auto run = [&](int first, int n, int sp) {
+      for (int i = first; i < first + n; i++) {
+        const int4 t4 = s_tok[i];
         const int op = t4.x & 7;
         if (op == OP_SPILL) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid] = reg[k];
+          for (int u = 0; u < SPT; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid + u * PT] = reg[u][k];
           sp++;
           continue;
         }
-        const int tset = (t4.x & TOK_SET) ? 1 : 0, tslot = (t4.x & TOK_SLOT) ? 1 : 0;
-        const bool firstFlag = (t4.x & TOK_FIRST) != 0;
+        const int tset = (t4.x & TOK_SET) ? 1 : 0;
         const double* P = c_P[tset][r];
         const double* lutr = s_lut + tset * 64;
-        double x[4], y[4];                       // x = term of the operand the token lists first, y = the other
-        bool xTipBelow = false, yTipBelow = false;
-        if (op == OP_CHERRY) {
-          const unsigned m0 = s_mask[t4.y * TILE + tid], m1 = s_mask[t4.z * TILE + tid];
+        if (op == OP_SLOTREG) sp--;
+        float e[SPT];
 #pragma unroll
-          for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
-          xTipBelow = s_below[tset * 16 + m0]; yTipBelow = s_below[tset * 16 + m1];
-        } else if (op == OP_REGTIP) {
-          const unsigned m1 = s_mask[t4.z * TILE + tid];
-          matvec4(P, reg, x);
+        for (int u = 0; u < SPT; u++) {
+          double x[4], y[4];                     // x = term of the operand the token lists first, y = the other
+          if (op == OP_CHERRY) {
+            const unsigned m0 = s_mask[t4.y * TILE + tid + u * PT], m1 = s_mask[t4.z * TILE + tid + u * PT];
 #pragma unroll
-          for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
-          yTipBelow = s_below[tset * 16 + m1];
-        } else {
-          sp--;
-          double z[4];
+            for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
+          } else if (op == OP_REGTIP) {
+            const unsigned m1 = s_mask[t4.z * TILE + tid + u * PT];
+            matvec4(P, reg[u], x);
 #pragma unroll
-          for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid];
-          matvec4(P, z, x);
-          matvec4(P, reg, y);
+            for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
+          } else {
+            double z[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid + u * PT];
+            matvec4(P, z, x);
+            matvec4(P, reg[u], y);
+          }
+          if (EXACT) {
+            // child order: CHERRY lists the first child first; REGTIP's flag says the tip (y) is the reference's
+            // first child, SLOTREG's that the popped operand (x) is
+            const bool firstFlag = (t4.x & TOK_FIRST) != 0;
+            const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
+            e[u] = 0.0f;
+            double s4[4];
+            if (xFirst) combineExact(x, y, s4, e[u]); else combineExact(y, x, s4, e[u]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) reg[u][k] = s4[k];
+          } else {
+            // products commute bit for bit, so the child order only matters for the rescale checks.  With transition
+            // probabilities <= 1 (the host verified it, else the handle starts in exact mode) no term exceeds 1, so a
+            // first term below 1e-150 drags the product below it too: one conservative test of the product suffices
+#pragma unroll
+            for (int k = 0; k < 4; k++) reg[u][k] = __dmul_rn(x[k], y[k]);
+            trig |= maybeBelow4(reg[u]);
+          }
         }
-        // child order: CHERRY lists the first child first; REGTIP's firstFlag says the tip (y) is the reference's
-        // first child, SLOTREG's that the popped operand (x) is
-        const bool xFirst = op == OP_CHERRY ? true : op == OP_REGTIP ? !firstFlag : firstFlag;
-        const size_t frow = flagRow + t4.w;
         if (EXACT) {
-          float e = 0.0f;
-          double s4[4];
-          if (xFirst) combineExact(x, y, s4, e); else combineExact(y, x, s4, e);
+          const int tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+          bool resc = false;
 #pragma unroll
-          for (int k = 0; k < 4; k++) reg[k] = s4[k];
-          const int any = __syncthreads_or(e != 0.0f);
-          if (any) v.expoOf(tslot)[((size_t)t4.w * R + r) * Sp + site] = e;
-          if (tid == 0) { v.flagOf(tslot)[frow] = (uint8_t)(any != 0); if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot; }
-        } else {
-          // products commute bit for bit; only the rescale checks depend on the order, and FAST mode just has to
-          // notice that one of them COULD have fired
-          if (op == OP_CHERRY) trig |= xTipBelow;
-          else if (op == OP_REGTIP) trig |= xFirst ? maybeBelow4(x) : yTipBelow;
-          else trig |= xFirst ? maybeBelow4(x) : maybeBelow4(y);
+          for (int u = 0; u < SPT; u++) resc |= e[u] != 0.0f;
+          const int any = __syncthreads_or(resc);
+          if (any) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) reg[k] = __dmul_rn(x[k], y[k]);
-          trig |= maybeBelow4(reg);
-          if (tid == 0) { v.flagOf(tslot)[frow] = 0; if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot; }
+            for (int u = 0; u < SPT; u++) v.expoOf(tslot)[((size_t)t4.w * R + r) * Sp + site0 + u * PT] = e[u];
+          }
+          if (tid == 0) v.flagOf(tslot)[flagRow + t4.w] = (uint8_t)(any != 0);
         }
       }
     };
-    const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff;
     if (fus0) {
-      run(tk1.x, n0, 0);
+      run(0, n0, 0);
       if (fus1) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) s_stack[k * TILE + tid] = reg[k];
+        for (int u = 0; u < SPT; u++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) s_stack[k * TILE + tid + u * PT] = reg[u][k];
       }
     }
-    if (fus1) run(tk1.x + n0, n1, 1);
+    if (fus1) run(n0, n1, 1);
+    if (!plain && tid < ntok) {
+      // bookkeeping of the fused vertices, one token per thread: current slot, and (fast mode) "nothing rescaled"
+      const int4 t4 = s_tok[tid];
+      if ((t4.x & 7) != OP_SPILL) {
+        const int tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+        if (!EXACT) v.flagOf(tslot)[flagRow + t4.w] = 0;
+        if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot;
+      }
+    }
 
     // ---- the stored vertex itself: exact semantics always
     const double* P = c_P[set][r];
     const double* lutr = s_lut + set * 64;
-    double first[4], second[4], s4[4];
-    if (tip0) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma + k];
-    } else if (fus0) {
-      if (fus1) {
-        double z[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid];
-        matvec4(P, z, first);
-      } else {
-        matvec4(P, reg, first);
-      }
-    } else {
-      matvec4(P, a, first);
-    }
-    if (tip1) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb + k];
-    } else if (fus1) {
-      matvec4(P, reg, second);
-    } else {
-      matvec4(P, b, second);
-    }
-    float e = 0.0f;
-    combineExact(first, second, s4, e);
     const int os = (fl & TF_OUTSLOT) ? 1 : 0;
-    const size_t o = ((size_t)tk0.x * R + r) * Sp + site;
-    st256(v.partOf(os) + o * 4, s4[0], s4[1], s4[2], s4[3]);
-    const int any = __syncthreads_or(e != 0.0f);     // also fences s_mask / s_stack reuse by the next task of a run
-    if (any) v.expoOf(os)[o] = e;
+    const size_t o = ((size_t)tk0.x * R + r) * Sp + site0;
+    float e[SPT];
+    bool rescaled = false;
+#pragma unroll
+    for (int u = 0; u < SPT; u++) {
+      double first[4], second[4], s4[4];
+      if (tip0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma[u] + k];
+      } else if (fus0) {
+        if (fus1) {
+          double z[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid + u * PT];
+          matvec4(P, z, first);
+        } else {
+          matvec4(P, reg[u], first);
+        }
+      } else {
+        matvec4(P, a[u], first);
+      }
+      if (tip1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb[u] + k];
+      } else if (fus1) {
+        matvec4(P, reg[u], second);
+      } else {
+        matvec4(P, b[u], second);
+      }
+      e[u] = 0.0f;
+      combineExact(first, second, s4, e[u]);
+      st256(v.partOf(os) + (o + (size_t)u * PT) * 4, s4[0], s4[1], s4[2], s4[3]);
+      rescaled |= e[u] != 0.0f;
+    }
+    const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_tok / s_stack reuse by the next task of a run
+    if (any) {
+#pragma unroll
+      for (int u = 0; u < SPT; u++) v.expoOf(os)[o + (size_t)u * PT] = e[u];
+    }
     if (tid == 0) {
       v.flagOf(os)[flagRow + tk0.x] = (uint8_t)(any != 0);
       if (tile == 0 && r == 0) v.cur[tk0.x] = (uint8_t)os;
