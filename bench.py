@@ -250,10 +250,14 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.mark = "timed"
     local.timer_begin(h)
+    host_us = np.zeros(3)
     for _ in range(args.steps):
         eng.recomputeAll(h, W, B, p.pi)
-        prune_ms += local.stats(h)["last_prune_ms"]
+        sti = local.stats(h)
+        prune_ms += sti["last_prune_ms"]
+        host_us += (sti["last_host_plan_us"], sti["last_host_submit_us"], sti["last_host_total_us"])
     ms = local.timer_end(h)
+    host_us /= args.steps
     barrier()
     sampler.mark = "after"
     ms = max_over_ranks(ms)
@@ -321,6 +325,7 @@ def run_ours(args, rank, world, local_rank):
                             "bytes_per_update": bytes_eval / ((n - 1) * s_local * r),
                             "unfused_bytes_per_step": bytes_unfused,
                             "unfused_equivalent_gbs": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9},
+               "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
                "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
                "levels": int(st1["last_levels"])}
         out.update(extras)

@@ -7,6 +7,7 @@
 // (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
 #include "../../include/dmpc.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -31,7 +32,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(DMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
   } while (0)
 
-struct HostResult { double ll; int overflow; int badCells; int nact; int violation; };
+typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status block
 
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
 // and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
@@ -44,7 +45,9 @@ struct ResPack {
   Token* h_tokens = nullptr;     // pinned
   int32_t* h_tipList = nullptr;  // pinned
   HostResult* h_res = nullptr;   // pinned
+  double* h_chunks = nullptr;    // pinned
   size_t cap = 0;                // internal vertices the pinned buffers can hold
+  size_t chunkCap = 0;
 };
 struct DeviceCtx {
   bool checked = false;
@@ -83,6 +86,10 @@ struct dmpc_tree {
   Token* h_tokens = nullptr;     // pinned
   int32_t* d_tipList = nullptr;
   int32_t* h_tipList = nullptr;  // pinned
+  double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
+  bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
+  bool carryIsZero = true;
+  int lastNact = 0;
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
   template <class Tp>
@@ -133,6 +140,14 @@ int acquirePack(dmpc_tree* t) {
     CUDA_TRY(cudaHostAlloc((void**)&p.h_tipList, 2 * cap * sizeof(int32_t), cudaHostAllocDefault));
     p.cap = cap;
   }
+  if (p.chunkCap < (size_t)t->nChunks) {
+    if (p.h_chunks) cudaFreeHost(p.h_chunks);
+    p.h_chunks = nullptr; p.chunkCap = 0;
+    const size_t cc = std::max<size_t>(256, (size_t)t->nChunks * 5 / 4);
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_chunks, cc * sizeof(double), cudaHostAllocDefault));
+    p.chunkCap = cc;
+  }
+  t->h_chunks = p.h_chunks;
   t->stream = p.stream;
   for (int i = 0; i < 5; i++) t->ev[i] = p.ev[i];
   t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens; t->h_tipList = p.h_tipList;
@@ -222,8 +237,8 @@ int rootStage(dmpc_tree* t, double* ll);
 constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
-  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
-  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, t->rv.overflow + 2);
+  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, &t->rv.st->violation);
+  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, &t->rv.st->violation);
   return DMPC_OK;
 }
 
@@ -264,10 +279,15 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     std::lock_guard<std::mutex> lk(g_constMutex);
     if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
   }
+  const auto h0 = std::chrono::steady_clock::now();
+  auto usSince = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count();
+  };
   if ((rc = uploadConstants(t, within, between, pi))) return rc;
   HostTree& ht = t->ht;
   HostTree::Plan& p = t->plan;
   ht.plan(p);
+  t->st.last_host_plan_us = usSince(h0);
   const int nTasks = (int)p.tasks.size(), nTok = (int)p.tokens.size();
   if (nTasks) {
     for (int sl = 0; sl < 2; sl++)
@@ -291,12 +311,16 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
                                  (unsigned long long)t->S * (unsigned long long)p.tipReads;
   t->st.last_stored_vertices = nTasks;
   t->st.last_fused_vertices = (int)p.fusedOps;
-  if ((rc = rootStage(t, ll))) return rc;
+  const auto h1 = std::chrono::steady_clock::now();
+  rc = rootStage(t, ll);
+  t->st.last_host_submit_us = std::chrono::duration<double, std::micro>(h1 - h0).count() - t->st.last_host_plan_us;
+  t->st.last_host_total_us = usSince(h0);
+  if (rc) return rc;
   if (!t->exact && t->h_res->violation) {
     // a fused clade may have rescaled: redo the same plan with the exact kernel (same tasks, same slots) and
     // keep that mode for the life of the handle
     t->exact = true;
-    CUDA_TRY(cudaMemsetAsync(t->rv.overflow + 2, 0, sizeof(int), t->stream));
+    CUDA_TRY(cudaMemsetAsync(&t->rv.st->violation, 0, sizeof(int), t->stream));
     if ((rc = runPlan(t))) return rc;
     t->st.exact_mode = 1;
     return rootStage(t, ll);
@@ -304,10 +328,10 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   return DMPC_OK;
 }
 
-int launchGather(dmpc_tree* t) {
-  CUDA_TRY(cudaMemsetAsync(t->rv.nact, 0, sizeof(int), t->stream));
-  if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
-  else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv);
+int launchGather(dmpc_tree* t, int mode) {
+  CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
+  if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
+  else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   t->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -351,56 +375,57 @@ int launchFinal(dmpc_tree* t, int mode, int reduceAll) {
   return DMPC_OK;
 }
 
-int gatherWithGrowth(dmpc_tree* t) {
-  for (int attempt = 0; attempt < 8; attempt++) {
-    int rc;
-    if ((rc = launchGather(t))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->violation, t->rv.overflow + 2, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaStreamSynchronize(t->stream));
-    t->st.last_active_tiles = t->h_res->nact;
-    if (t->h_res->overflow <= t->rv.Kcap) return DMPC_OK;
-    int k = t->rv.Kcap;
-    while (k < t->h_res->overflow) k *= 2;
-    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, sizeof(int), t->stream));
-    if ((rc = allocElist(t, k))) return rc;
-  }
-  return fail(DMPC_ERR_CUDA, "rescale list kept overflowing");
+// one D2H copy of everything the host needs after a batch of kernels, then the only synchronisation point
+int readStatus(dmpc_tree* t, bool withChunks) {
+  CUDA_TRY(cudaMemcpyAsync(t->h_res, t->rv.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
+  if (withChunks)
+    CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  t->st.last_active_tiles = t->h_res->nact;
+  t->lastNact = t->h_res->nact;
+  return DMPC_OK;
 }
 
+// ComputeLoglik's reduction (AugTree.cpp:296-325).  k_root_gather finishes the evaluation by itself when no site
+// rescaled anywhere (the usual case); only otherwise do the chain and the final kernel run.
+// Deferred (site-sharded) mode: stops after the gather; the chunk sums it produced — valid when this shard holds no
+// rescaled site and the exponent vector enters as zeros — are already on the host for dmpc_shard_finish.
 int rootStage(dmpc_tree* t, double* ll) {
   int rc;
   const bool chain = t->quirk && t->R > 1;
-  if (t->deferred) {
-    if ((rc = gatherWithGrowth(t))) return rc;      // synchronises the stream: ev[0], ev[1] have completed
-    float ms = 0;
-    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms; t->st.last_eval_ms = ms;
-    *ll = NAN;
-    return DMPC_OK;
+  const int mode = chain ? 1 : 0;
+  if (t->deferred && chain) {
+    CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));   // optimistic: vector enters as zeros
+    t->carryIsZero = true;
   }
   for (int attempt = 0; attempt < 8; attempt++) {
-    if ((rc = launchGather(t))) return rc;
-    if (chain && (rc = launchChain(t))) return rc;
-    if ((rc = launchFinal(t, chain ? 1 : 0, 1))) return rc;
+    if ((rc = launchGather(t, mode))) return rc;
     CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->ll, t->rv.result, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->overflow, t->rv.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->nact, t->rv.nact, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaMemcpyAsync(&t->h_res->violation, t->rv.overflow + 2, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-    CUDA_TRY(cudaStreamSynchronize(t->stream));
-    t->st.last_active_tiles = t->h_res->nact;
-    if (t->h_res->overflow <= t->rv.Kcap) {
-      float ms = 0;
+    if ((rc = readStatus(t, t->deferred))) return rc;
+    if (t->h_res->overflow > t->rv.Kcap) {
+      int k = t->rv.Kcap;
+      while (k < t->h_res->overflow) k *= 2;
+      CUDA_TRY(cudaMemsetAsync(&t->rv.st->overflow, 0, sizeof(int), t->stream));
+      if ((rc = allocElist(t, k))) return rc;
+      continue;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
+    if (t->deferred) {
+      t->chunksOnHost = t->h_res->nact == 0;
       cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
-      cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
-      *ll = t->h_res->ll;
+      *ll = NAN;
       return DMPC_OK;
     }
-    int k = t->rv.Kcap;
-    while (k < t->h_res->overflow) k *= 2;
-    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, sizeof(int), t->stream));
-    if ((rc = allocElist(t, k))) return rc;
+    if (t->h_res->nact != 0) {                      // some site rescaled: the real reduction
+      if (chain && (rc = launchChain(t))) return rc;
+      if ((rc = launchFinal(t, mode, 1))) return rc;
+      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+      if ((rc = readStatus(t, false))) return rc;
+    }
+    cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+    *ll = t->h_res->ll;
+    return DMPC_OK;
   }
   return fail(DMPC_ERR_CUDA, "rescale list kept overflowing");
 }
@@ -510,23 +535,19 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     if ((r2 = t->alloc(&t->rv.carryOut, (size_t)RMAX))) return r2;
     if ((r2 = t->alloc(&t->rv.sitell, (size_t)t->Sp))) return r2;
     if ((r2 = t->alloc(&t->rv.chunk, (size_t)t->nChunks))) return r2;
-    if ((r2 = t->alloc(&t->rv.ticket, (size_t)1))) return r2;
-    if ((r2 = t->alloc(&t->rv.overflow, (size_t)4))) return r2;      // [0] list overflow, [1] bad cells, [2] fused-clade violation
-    if ((r2 = t->alloc(&t->rv.nact, (size_t)1))) return r2;
-    if ((r2 = t->alloc(&t->rv.result, (size_t)1))) return r2;
+    if ((r2 = t->alloc(&t->rv.st, (size_t)1))) return r2;
     if ((r2 = allocElist(t, 8))) return r2;
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
-    CUDA_TRY(cudaMemsetAsync(t->rv.ticket, 0, sizeof(unsigned), t->stream));
-    CUDA_TRY(cudaMemsetAsync(t->rv.overflow, 0, 4 * sizeof(int), t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
     t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal;
     // alignment: [N][S] host rows -> [N][Sp] device rows; pad sites get the all-ones mask
     CUDA_TRY(cudaMemcpy2DAsync(t->d_tipmask, t->Sp, alignmentBin, t->S, t->S, t->N, cudaMemcpyHostToDevice, t->stream));
     {
       const size_t n = (size_t)t->N * t->Sp;
-      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->d_tipmask, t->N, t->S, t->Sp, t->rv.overflow + 1);
+      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
       t->st.kernel_launches++;
-      CUDA_TRY(cudaMemcpyAsync(&t->h_res->badCells, t->rv.overflow + 1, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(&t->h_res->badCells, &t->rv.st->badCells, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
       CUDA_TRY(cudaStreamSynchronize(t->stream));
       if (t->h_res->badCells)
         return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
@@ -797,15 +818,28 @@ int dmpc_shard_chain(dmpc_tree* t, const float* carryIn, float* carryOut) {
   const bool chain = t->quirk && t->R > 1;
   if (!chain) { for (int r = 0; r < t->R; r++) carryOut[r] = 0.0f; return DMPC_OK; }
   float in[RMAX] = {0};
-  for (int r = 0; r < t->R; r++) in[r] = carryIn[r];
+  bool zeroIn = true;
+  for (int r = 0; r < t->R; r++) { in[r] = carryIn[r]; zeroIn &= carryIn[r] == 0.0f; }
+  if (t->lastNact == 0) {
+    // no rescaled site in this shard: the vector passes through unchanged
+    for (int r = 0; r < t->R; r++) carryOut[r] = carryIn[r];
+    if (zeroIn && t->carryIsZero) return DMPC_OK;                 // the gather's optimistic chunk sums stand
+    CUDA_TRY(cudaMemcpyAsync(t->rv.carryIn, in, sizeof in, cudaMemcpyHostToDevice, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));                   // `in` is a stack temporary
+    t->carryIsZero = zeroIn; t->chunksOnHost = false;
+    return DMPC_OK;
+  }
   CUDA_TRY(cudaMemcpyAsync(t->rv.carryIn, in, sizeof in, cudaMemcpyHostToDevice, t->stream));
   if ((rc = launchChain(t))) return rc;
   float out[RMAX];
   CUDA_TRY(cudaMemcpyAsync(out, t->rv.carryOut, sizeof out, cudaMemcpyDeviceToHost, t->stream));
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   for (int r = 0; r < t->R; r++) carryOut[r] = out[r];
+  t->carryIsZero = zeroIn; t->chunksOnHost = false;
   return DMPC_OK;
 }
+
+int dmpc_shard_active(dmpc_tree* t) { return checkHandle(t) ? -1 : (t->lastNact != 0); }
 
 int dmpc_shard_num_chunks(dmpc_tree* t) { return checkHandle(t) ? -1 : t->nChunks; }
 
@@ -814,10 +848,15 @@ int dmpc_shard_finish(dmpc_tree* t, double* chunkSums) {
   if ((rc = checkHandle(t))) return rc;
   if ((rc = ensureDevice(t))) return rc;
   if (!chunkSums) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->chunksOnHost) {                                          // the gather already finished this shard
+    std::memcpy(chunkSums, t->h_chunks, (size_t)t->nChunks * sizeof(double));
+    return DMPC_OK;
+  }
   const bool chain = t->quirk && t->R > 1;
   if ((rc = launchFinal(t, chain ? 1 : 0, 0))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(chunkSums, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+  CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
   CUDA_TRY(cudaStreamSynchronize(t->stream));
+  std::memcpy(chunkSums, t->h_chunks, (size_t)t->nChunks * sizeof(double));
   return DMPC_OK;
 }
 

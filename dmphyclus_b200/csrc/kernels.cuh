@@ -28,6 +28,7 @@ constexpr int TILE = 256;       // sites per block of the pruning kernel = flag 
 constexpr int PT = 128;         // threads of a pruning block
 constexpr int SPT = TILE / PT;  // sites per pruning thread
 constexpr int CHUNK = 256;      // sites per deterministic reduction chunk
+static_assert(TILE == CHUNK, "k_root_gather finishes one reduction chunk per block");
 
 struct DevView {
   double* part[2];
@@ -44,6 +45,16 @@ struct DevView {
   __device__ __forceinline__ uint8_t* flagOf(int slot) const { return slot ? flag[1] : flag[0]; }
 };
 
+struct DevStatus {
+  double ll;                    // the log-likelihood (valid when the kernel that owns the last ticket reduced)
+  int overflow;                 // longest per-site exponent list seen, when it exceeds the capacity
+  int badCells;                 // alignment cells without any state
+  int violation;                // a fused clade may have rescaled (k_prune, fast mode)
+  int nact;                     // site tiles holding a rescaled site (set by root_gather)
+  unsigned ticket, ticket2;     // last-block detection of k_final / k_root_gather
+  int pad[2];
+};
+
 struct RootView {
   float* elist;                 // [Sp][Kcap][RP] per-site non-zero exponents in vertex-id order, zero padded
   int* kmax;                    // [Sp] rows used at each site (uncapped)
@@ -58,10 +69,7 @@ struct RootView {
   float* carryOut;              // [RMAX]
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [nChunks] sums of CHUNK consecutive sites
-  unsigned* ticket;
-  int* overflow;
-  int* nact;                    // number of site tiles holding a rescaled site (set by root_gather)
-  double* result;
+  DevStatus* st;                // everything the host reads back after an evaluation, in one copy
   int Kcap, RP, Q;              // Q = rows per chain staging chunk
 };
 
@@ -350,14 +358,29 @@ __global__ void k_prepare_masks(uint8_t* mask, int N, int S, int Sp, int* bad) {
   else if ((mask[i] & 0xF) == 0 || mask[i] > 0xF) atomicAdd(bad, 1);
 }
 
+// sum of n chunk sums in a fixed order (CHUNK strided accumulators, then a binary tree); 256 threads
+__device__ __forceinline__ double reduce_chunks_device(const double* chunk, int n, double* s_red) {
+  double acc = 0.0;
+  for (int cI = threadIdx.x; cI < n; cI += CHUNK) acc = __dadd_rn(acc, chunk[cI]);
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int d = CHUNK / 2; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + d]);
+    __syncthreads();
+  }
+  return s_red[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4a root_gather: per site tile, dot(root, limProbs) and the per-site list of non-zero rescale exponents in
 // vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
 // the flagged vertices of each 128-vertex window are compacted (in id order) into shared memory, then visited
 // four at a time so that their exponent loads overlap.
 template <int RP>
-__global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
+__global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, int mode) {
   __shared__ int s_list[TILE];
+  __shared__ double s_red[TILE];
+  __shared__ bool s_last;
   __shared__ int s_wcnt[TILE / 32];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int site = tile * TILE + tid;
@@ -365,14 +388,15 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
   const int R = v.R;
   const size_t Sp = (size_t)v.Sp;
   const int rootSlot = v.cur[0];
+  double rd[RP];
 #pragma unroll
   for (int r = 0; r < RP; r++)
     if (r < R) {
       double a0, a1, a2, a3;
       ld256(v.partOf(rootSlot) + ((size_t)r * Sp + site) * 4, a0, a1, a2, a3);
       // arma::dot (op_dot::direct_dot_arma): two interleaved accumulators
-      rv.rootdot[(size_t)r * Sp + site] =
-          __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
+      rd[r] = __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
+      rv.rootdot[(size_t)r * Sp + site] = rd[r];
     }
   int k[RP];
 #pragma unroll
@@ -427,12 +451,50 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv) {
     for (int r = 0; r < RP; r++)
       for (int j = min(k[r], rv.Kcap); j < kk; j++) myList[(size_t)j * RP + r] = 0.0f;   // zero padding: x + 0.0f == x
     rv.kmax[site] = kmax;
-    if (kmax > rv.Kcap) atomicMax(rv.overflow, kmax);
+    if (kmax > rv.Kcap) atomicMax(&rv.st->overflow, kmax);
   } else {
     rv.kmax[site] = 0;
   }
   const int anyActive = __syncthreads_or(valid && kmax > 0);
-  if (tid == 0 && anyActive) atomicAdd(rv.nact, 1);
+  // Optimistic finish: when no site of the whole alignment rescaled, the exponent vector never moves, every site's
+  // term is log(mean_r(rootdot_r * expf(ev_r))) with the entry vector ev, and this kernel can finish the evaluation
+  // by itself (same arithmetic and the same summation tree as k_final).  The host checks nact before trusting it.
+  double ll = 0.0;
+  if (valid) {
+    double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < RP; r++)
+      if (r < R) {
+        const float ev = mode == 1 ? rv.carryIn[r] : 0.0f;
+        const double w = (double)(float)exp((double)ev);
+        const double x = __dmul_rn(rd[r], w);
+        if (r & 1) a2 = __dadd_rn(a2, x); else a1 = __dadd_rn(a1, x);
+      }
+    ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)R), (double)0.0f);
+    rv.sitell[site] = ll;
+  }
+  s_red[tid] = ll;
+  __syncthreads();
+  for (int d = TILE / 2; d > 0; d >>= 1) {
+    if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    rv.chunk[tile] = s_red[0];
+    if (anyActive) atomicAdd(&rv.st->nact, 1);
+    __threadfence();
+    s_last = atomicAdd(&rv.st->ticket2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const bool quiet = *(volatile int*)&rv.st->nact == 0;
+    if (quiet) {
+      const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
+      if (tid == 0) rv.st->ll = tot;
+    }
+    if (tid == 0) rv.st->ticket2 = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -450,7 +512,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   __shared__ int s_total[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nth = blockDim.x;
   const int S = v.S, Q = rv.Q;
-  if (*rv.nact == 0) {                            // nothing rescaled: the vector never leaves its entry value
+  if (rv.st->nact == 0) {                         // nothing rescaled: the vector never leaves its entry value
     if (tid < RMAX) rv.carryOut[tid] = rv.carryIn[tid];
     return;
   }
@@ -603,18 +665,6 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
 // each 256-site chunk, chunk sums combined by reduce_chunks order (identical on host for the multi-GPU path).
 // mode 1: exponent vectors come from the chain; mode 0: each site folds its own list from zero (numRateCats == 1,
 // where the carry is always exactly zero, or the textbook reduction).
-__device__ __forceinline__ double reduce_chunks_device(const double* chunk, int n, double* s_red) {
-  double acc = 0.0;
-  for (int cI = threadIdx.x; cI < n; cI += CHUNK) acc = __dadd_rn(acc, chunk[cI]);
-  s_red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int d = CHUNK / 2; d > 0; d >>= 1) {
-    if (threadIdx.x < d) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + d]);
-    __syncthreads();
-  }
-  return s_red[0];
-}
-
 __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mode, int reduceAll) {
   __shared__ double s_red[CHUNK];
   __shared__ bool s_last;
@@ -624,7 +674,7 @@ __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mod
     float ev[RMAX];
     float mx = 0.0f;
     const int km = min(rv.kmax[s], rv.Kcap);
-    if (mode == 1 && *rv.nact == 0) {               // the chain kernel returned early: no site rescaled
+    if (mode == 1 && rv.st->nact == 0) {            // the chain kernel returned early: no site rescaled
 #pragma unroll
       for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = rv.carryIn[r];
     } else if (mode == 1) {
@@ -665,15 +715,15 @@ __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mod
   if (threadIdx.x == 0) {
     rv.chunk[blockIdx.x] = s_red[0];
     __threadfence();
-    s_last = atomicAdd(rv.ticket, 1u) == gridDim.x - 1;
+    s_last = atomicAdd(&rv.st->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (s_last && reduceAll) {
     __threadfence();
     const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
-    if (threadIdx.x == 0) { *rv.result = tot; *rv.ticket = 0; }
+    if (threadIdx.x == 0) { rv.st->ll = tot; rv.st->ticket = 0; }
   } else if (s_last && threadIdx.x == 0) {
-    *rv.ticket = 0;
+    rv.st->ticket = 0;
   }
 }
 

@@ -36,7 +36,8 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_ulonglong), ("last_active_tiles", C.c_int),
                 ("num_tips", C.c_int), ("num_loci", C.c_int), ("num_rate_cats", C.c_int),
                 ("last_algorithmic_bytes", C.c_ulonglong), ("last_stored_vertices", C.c_int),
-                ("last_fused_vertices", C.c_int), ("exact_mode", C.c_int)]
+                ("last_fused_vertices", C.c_int), ("exact_mode", C.c_int),
+                ("last_host_plan_us", C.c_double), ("last_host_submit_us", C.c_double), ("last_host_total_us", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,6 +70,7 @@ ABI = {
     "dmpc_get_site_logliks": (C.c_int, [_P, _dbl_p]),
     "dmpc_set_deferred": (C.c_int, [_P, C.c_int]),
     "dmpc_shard_chain": (C.c_int, [_P, _f32_p, _f32_p]),
+    "dmpc_shard_active": (C.c_int, [_P]),
     "dmpc_shard_num_chunks": (C.c_int, [_P]),
     "dmpc_shard_finish": (C.c_int, [_P, _dbl_p]),
     "dmpc_reduce_chunks": (C.c_double, [_dbl_p, C.c_int]),
@@ -279,7 +281,7 @@ class Engine:
 
     def shard_active(self, ptr) -> bool:
         """True when a site of this handle rescaled in the last evaluation (its chain is not the identity)."""
-        return self.stats(ptr)["last_active_tiles"] > 0
+        return self.lib.dmpc_shard_active(ptr) > 0
 
     def shard_finish(self, ptr) -> np.ndarray:
         n = self.lib.dmpc_shard_num_chunks(ptr)

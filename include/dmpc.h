@@ -132,6 +132,9 @@ typedef struct dmpc_stats {
                                partials written + stored operands read (32 B each) + 1 B per tip operand */
   int last_stored_vertices, last_fused_vertices;   /* vertices written to HBM / recomputed in registers */
   int exact_mode;           /* 1 once fused clades run with full rescale bookkeeping */
+  double last_host_plan_us;      /* host time of the last evaluation: building the plan (schedule, tasks, tokens) */
+  double last_host_submit_us;    /* ... uploading it and launching every kernel */
+  double last_host_total_us;     /* ... whole evaluate(), including the wait for the result */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
@@ -157,6 +160,7 @@ int dmpc_get_site_logliks(dmpc_tree* t, double* out);
  * With deferral on, the entry points above return logLik = NaN and leave the reduction to these calls. */
 int dmpc_set_deferred(dmpc_tree* t, int on);
 int dmpc_shard_chain(dmpc_tree* t, const float* carryIn, float* carryOut);
+int dmpc_shard_active(dmpc_tree* t);     /* 1 when a site of this handle rescaled in the last evaluation */
 int dmpc_shard_num_chunks(dmpc_tree* t);
 int dmpc_shard_finish(dmpc_tree* t, double* chunkSums);
 /* Host-side twin of the device's final reduction: adds n chunk sums in the same fixed order as the single-GPU
