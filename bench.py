@@ -39,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+emit = print
 METRIC = "node-site partial updates/sec"
 UNIT = "updates/s"
 
@@ -179,7 +180,7 @@ def run_reference(args, rank, world):
                                     "clusterFunArmadillo.cpp:4,38); it cannot use more host threads"},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def config_dict(args, n, s, k, r, world):
@@ -326,12 +327,15 @@ def run_ours(args, rank, world, local_rank):
                             "unfused_bytes_per_step": bytes_unfused,
                             "unfused_equivalent_gbs": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9},
                "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
+               "sharded_exchange": ({"in_kernel": eng.fast, "host_collectives": eng.collectives} if world > 1 else None),
                "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
                "levels": int(st1["last_levels"])}
         out.update(extras)
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
+        out_fast = (eng.fast, eng.collectives)
+        local.comm_close()
         dist.destroy_process_group()
 
 
@@ -389,6 +393,12 @@ def cpu_baseline(p, n, s, r):
 
 
 def main():
+    # the ONE JSON line goes to the real stdout; anything libraries print to stdout meanwhile (NCCL's version banner)
+    # is diverted to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global emit
+    emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -58,6 +58,16 @@ DeviceCtx g_ctx[64];
 
 }  // namespace
 
+struct dmpc_comm {
+  int device = 0, rank = 0, world = 1, width = 0;
+  void* local = nullptr;               // this rank's mailbox (cudaMalloc: IPC-shareable)
+  void* peer[CW] = {nullptr};          // every rank's mailbox as seen from here
+  unsigned* seq = nullptr;             // message counter (device)
+  bool connected = false;
+  size_t flagBytes() const { return 64; }
+  size_t bytes() const { return flagBytes() + (size_t)2 * CW * width * sizeof(double); }
+};
+
 struct dmpc_tree {
   HostTree ht;
   int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nReal = 0, nChunks = 0;
@@ -89,6 +99,7 @@ struct dmpc_tree {
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
+  dmpc_comm* comm = nullptr;
   int lastNact = 0;
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
@@ -329,6 +340,17 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
 }
 
 int launchGather(dmpc_tree* t, int mode) {
+  t->rv.exactMode = t->exact ? 1 : 0;
+  t->rv.comm.world = 1;
+  if (t->deferred && t->comm && t->comm->connected && t->comm->device == t->device && t->nChunks + 2 <= t->comm->width) {
+    const dmpc_comm& c = *t->comm;
+    CommView& cv = t->rv.comm;
+    cv.world = c.world; cv.rank = c.rank; cv.width = c.width; cv.seq = c.seq;
+    for (int p = 0; p < c.world; p++) {
+      cv.flag[p] = (unsigned*)c.peer[p];
+      cv.payload[p] = (double*)((char*)c.peer[p] + c.flagBytes());
+    }
+  }
   CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
   if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
@@ -457,7 +479,7 @@ int checkHandle(dmpc_tree* t) {
 extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
-  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 8; o->fuse_exact = 0;
+  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 8; o->fuse_exact = 0; o->comm = nullptr;
 }
 
 const char* dmpc_last_error(void) { return g_err.c_str(); }
@@ -508,6 +530,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
   t->quirk = o.quirk_carry != 0;
   t->deferred = o.deferred != 0;
+  t->comm = (dmpc_comm*)o.comm;
   t->siteBegin = o.site_begin; t->sitesTotal = o.sites_total ? o.sites_total : numLoci;
   t->rv.RP = numRateCats <= 4 ? 4 : 8;
 
@@ -857,6 +880,58 @@ int dmpc_shard_finish(dmpc_tree* t, double* chunkSums) {
   CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   std::memcpy(chunkSums, t->h_chunks, (size_t)t->nChunks * sizeof(double));
+  return DMPC_OK;
+}
+
+int dmpc_shard_fast_result(dmpc_tree* t, int* ok, double* logLik) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!ok || !logLik) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->rv.comm.world > 1 && t->h_res->xok == 2) return fail(DMPC_ERR_CUDA, "peer exchange timed out: a rank of the site-sharded run never answered");
+  *ok = t->rv.comm.world > 1 && t->h_res->xok == 1;
+  *logLik = *ok ? t->h_res->ll : NAN;
+  return DMPC_OK;
+}
+
+int dmpc_comm_create(int device, int rank, int world, int maxChunksPerRank, dmpc_comm** out, void* ipcHandle64) {
+  if (!out || !ipcHandle64 || world < 1 || world > CW || rank < 0 || rank >= world || maxChunksPerRank < 1)
+    return fail(DMPC_ERR_ARG, "dmpc_comm_create: world must be 1..8, rank in range, handle buffer non-null");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(device));
+  dmpc_comm* c = new dmpc_comm;
+  c->device = device; c->rank = rank; c->world = world; c->width = maxChunksPerRank + 2;
+  if (cudaMalloc(&c->local, c->bytes() + 64) != cudaSuccess) { delete c; return fail(DMPC_ERR_CUDA, "cudaMalloc of the mailbox failed"); }
+  CUDA_TRY(cudaMemset(c->local, 0, c->bytes() + 64));
+  c->seq = (unsigned*)((char*)c->local + c->bytes());          // counter lives behind the mailbox proper
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->local));
+  std::memcpy(ipcHandle64, &h, 64);
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = c;
+  return DMPC_OK;
+}
+
+int dmpc_comm_connect(dmpc_comm* c, const void* allHandles) {
+  if (!c || !allHandles) return fail(DMPC_ERR_ARG, "null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (int p = 0; p < c->world; p++) {
+    if (p == c->rank) { c->peer[p] = c->local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)allHandles + 64 * p, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(&c->peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->connected = true;
+  return DMPC_OK;
+}
+
+int dmpc_comm_destroy(dmpc_comm* c) {
+  if (!c) return DMPC_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < c->world; p++)
+    if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+  if (c->local) cudaFree(c->local);
+  delete c;
   return DMPC_OK;
 }
 

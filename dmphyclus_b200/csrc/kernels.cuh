@@ -52,7 +52,21 @@ struct DevStatus {
   int violation;                // a fused clade may have rescaled (k_prune, fast mode)
   int nact;                     // site tiles holding a rescaled site (set by root_gather)
   unsigned ticket, ticket2;     // last-block detection of k_final / k_root_gather
-  int pad[2];
+  int xok;                      // site-sharded runs: 1 = the in-kernel peer exchange produced ll, 0 = host protocol needed,
+                                //   2 = a peer never answered, -1 = no exchange attempted
+  int pad;
+};
+
+// Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access): every rank
+// owns a mailbox in its HBM that all peers can store into.  Layout of a mailbox: unsigned flag[CW] (sequence number
+// of the last message of each sender), then double payload[2][CW][width] (double-buffered by sequence parity):
+// payload[.][sender] = { has-rescaled-site, nChunks, chunk sums... }.
+constexpr int CW = 8;            // ranks
+struct CommView {
+  int world, rank, width;
+  unsigned* seq;                // this rank's message counter (device memory)
+  unsigned* flag[CW];           // flag arrays of every rank's mailbox (peer pointers)
+  double* payload[CW];          // payload areas of every rank's mailbox (peer pointers)
 };
 
 struct RootView {
@@ -71,6 +85,8 @@ struct RootView {
   double* chunk;                // [nChunks] sums of CHUNK consecutive sites
   DevStatus* st;                // everything the host reads back after an evaluation, in one copy
   int Kcap, RP, Q;              // Q = rows per chain staging chunk
+  CommView comm;                // comm.world > 1: k_root_gather also performs the cross-rank exchange
+  int exactMode;                // the prune kernels ran in exact mode (a raised violation flag is then stale)
 };
 
 __constant__ double c_P[2][RMAX][16];   // [set][rate][i*4+j], set 0 = between, 1 = within; P(i,j) row-major
@@ -489,6 +505,65 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
   if (s_last) {
     __threadfence();
     const bool quiet = *(volatile int*)&rv.st->nact == 0;
+    const CommView& cm = rv.comm;
+    const bool retry = *(volatile int*)&rv.st->overflow > rv.Kcap || (*(volatile int*)&rv.st->violation != 0 && !rv.exactMode);
+    if (cm.world > 1) {
+      // Fused collective: this rank's {rescaled?, nChunks, chunk sums} go straight into every peer's mailbox over
+      // NVLink; when no rank holds a rescaled site, each rank then adds ALL chunk sums in the fixed global order and
+      // has the log-likelihood without any host-side collective.  Skipped when the host is going to re-run this
+      // gather (list overflow, fused-clade violation), so that every rank sends exactly one message per evaluation.
+      if (retry) {
+        if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; }
+        return;
+      }
+      __shared__ unsigned s_seq;
+      __shared__ int s_bad;
+      if (tid == 0) { s_seq = *cm.seq + 1; s_bad = 0; }
+      __syncthreads();
+      const unsigned seq = s_seq;
+      const int buf = seq & 1, nCh = gridDim.x, msg = 2 + nCh;
+      for (int idx = tid; idx < cm.world * msg; idx += TILE) {
+        const int p = idx / msg, j = idx - p * msg;
+        const double val = j == 0 ? (quiet ? 0.0 : 1.0) : j == 1 ? (double)nCh : rv.chunk[j - 2];
+        *((volatile double*)cm.payload[p] + ((size_t)buf * CW + cm.rank) * cm.width + j) = val;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < cm.world) {
+        *((volatile unsigned*)cm.flag[tid] + cm.rank) = seq;                  // "message seq from me is complete"
+        const volatile unsigned* mine = (volatile unsigned*)cm.flag[cm.rank] + tid;
+        const long long t0 = clock64();
+        while ((int)(*mine - seq) < 0) {
+          if (clock64() - t0 > 40000000000LL) { s_bad = 1; break; }            // ~20 s: a peer died; do not hang the GPU
+          __nanosleep(200);
+        }
+      }
+      __syncthreads();
+      __threadfence_system();
+      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)buf * CW * cm.width;
+      bool anyActive = false;
+      for (int p = 0; p < cm.world; p++) anyActive |= in[(size_t)p * cm.width] != 0.0;
+      if (!s_bad && !anyActive) {
+        double acc = 0.0;
+        int base = 0;                                                          // global index of rank p's first chunk
+        for (int p = 0; p < cm.world; p++) {
+          const int cnt = (int)in[(size_t)p * cm.width + 1];
+          for (int c = ((tid - base) % CHUNK + CHUNK) % CHUNK; c < cnt; c += CHUNK) acc = __dadd_rn(acc, in[(size_t)p * cm.width + 2 + c]);
+          base += cnt;
+        }
+        s_red[tid] = acc;
+        __syncthreads();
+        for (int d = CHUNK / 2; d > 0; d >>= 1) {
+          if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
+          __syncthreads();
+        }
+        if (tid == 0) { rv.st->ll = s_red[0]; rv.st->xok = 1; }
+      } else if (tid == 0) {
+        rv.st->xok = s_bad ? 2 : 0;
+      }
+      if (tid == 0) { *cm.seq = seq; rv.st->ticket2 = 0; }
+      return;
+    }
     if (quiet) {
       const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
       if (tid == 0) rv.st->ll = tot;

@@ -26,7 +26,7 @@ class DmpcError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int),
-                ("fuse_tips", C.c_int), ("fuse_exact", C.c_int), ("deferred", C.c_int)]
+                ("fuse_tips", C.c_int), ("fuse_exact", C.c_int), ("comm", C.c_void_p), ("deferred", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -74,6 +74,10 @@ ABI = {
     "dmpc_shard_num_chunks": (C.c_int, [_P]),
     "dmpc_shard_finish": (C.c_int, [_P, _dbl_p]),
     "dmpc_reduce_chunks": (C.c_double, [_dbl_p, C.c_int]),
+    "dmpc_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P), C.c_void_p]),
+    "dmpc_comm_connect": (C.c_int, [_P, C.c_void_p]),
+    "dmpc_comm_destroy": (C.c_int, [_P]),
+    "dmpc_shard_fast_result": (C.c_int, [_P, C.POINTER(C.c_int), _dbl_p]),
 }
 
 
@@ -288,6 +292,32 @@ class Engine:
         out = np.empty(n, np.float64)
         self._check(self.lib.dmpc_shard_finish(ptr, _p(out, _dbl_p)))
         return out
+
+    def shard_fast_result(self, ptr):
+        """(True, logLik) when the reduction kernel's peer exchange finished the evaluation on the device."""
+        ok, ll = C.c_int(), C.c_double()
+        self._check(self.lib.dmpc_shard_fast_result(ptr, C.byref(ok), C.byref(ll)))
+        return bool(ok.value), ll.value
+
+    def comm_setup(self, rank: int, world: int, exchange, max_chunks: int = 4096) -> None:
+        """Create this rank's NVLink mailbox, swap IPC handles with the peers through `exchange` (a callable
+        bytes -> list of every rank's bytes, e.g. over torch.distributed) and attach it to later handles."""
+        comm = _P()
+        mine = C.create_string_buffer(64)
+        device = self.opts.device if self.opts.device >= 0 else 0
+        self._check(self.lib.dmpc_comm_create(device, rank, world, max_chunks, C.byref(comm), mine))
+        allh = b"".join(exchange(mine.raw))
+        if len(allh) != 64 * world:
+            raise RuntimeError("IPC handle exchange returned the wrong amount of data")
+        self._check(self.lib.dmpc_comm_connect(comm, allh))
+        self._comm = comm
+        self.opts.comm = comm.value
+
+    def comm_close(self) -> None:
+        if getattr(self, "_comm", None):
+            self.opts.comm = None
+            self._check(self.lib.dmpc_comm_destroy(self._comm))
+            self._comm = None
 
     def reduce_chunks(self, chunks) -> float:
         c = np.ascontiguousarray(chunks, dtype=np.float64)

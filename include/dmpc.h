@@ -55,6 +55,8 @@ typedef struct dmpc_options {
                         <= 1 stores every vertex).  Results do not depend on it */
   int fuse_exact;    /* 1: fused clades keep full per-vertex rescale bookkeeping from the start (the engine switches
                         to it by itself the first time a fused clade could have rescaled) */
+  void* comm;        /* dmpc_comm* of a site-sharded run (or NULL): deferred evaluations then exchange their chunk sums
+                        through NVLink peer mailboxes inside the reduction kernel */
   int deferred;      /* 1: start in deferred-reduction mode (see dmpc_set_deferred): dmpc_loglik_create prunes and
                         gathers but leaves the root reduction to dmpc_shard_chain / dmpc_shard_finish */
 } dmpc_options;
@@ -163,6 +165,19 @@ int dmpc_shard_chain(dmpc_tree* t, const float* carryIn, float* carryOut);
 int dmpc_shard_active(dmpc_tree* t);     /* 1 when a site of this handle rescaled in the last evaluation */
 int dmpc_shard_num_chunks(dmpc_tree* t);
 int dmpc_shard_finish(dmpc_tree* t, double* chunkSums);
+/* Peer mailboxes for the fused exchange (one process per GPU of ONE box, peer access over NVLink/NVSwitch).
+ *   dmpc_comm_create:  allocates this rank's mailbox (room for maxChunksPerRank chunk sums per sender) and returns the
+ *                      64-byte CUDA IPC handle other ranks open it with;
+ *   dmpc_comm_connect: opens the world mailboxes from their handles (allHandles = world x 64 bytes, in rank order);
+ * then pass the comm in dmpc_options.comm (with deferred = 1).  After each deferred evaluation
+ *   dmpc_shard_fast_result: *ok = 1 and *logLik set when the in-kernel exchange completed it (no rank held a rescaled
+ *                      site); *ok = 0: run the host protocol (dmpc_shard_chain / dmpc_shard_finish + a collective). */
+typedef struct dmpc_comm dmpc_comm;
+int dmpc_comm_create(int device, int rank, int world, int maxChunksPerRank, dmpc_comm** out, void* ipcHandle64);
+int dmpc_comm_connect(dmpc_comm* c, const void* allHandles);
+int dmpc_comm_destroy(dmpc_comm* c);
+int dmpc_shard_fast_result(dmpc_tree* t, int* ok, double* logLik);
+
 /* Host-side twin of the device's final reduction: adds n chunk sums in the same fixed order as the single-GPU
  * kernel (256 strided accumulators, then a binary tree), so 1-GPU and N-GPU totals agree bit for bit. */
 double dmpc_reduce_chunks(const double* chunkSums, int n);
