@@ -65,7 +65,9 @@ struct dmpc_comm {
   unsigned* seq = nullptr;             // message counter (device)
   bool connected = false;
   size_t flagBytes() const { return 64; }
-  size_t bytes() const { return flagBytes() + (size_t)2 * CW * width * sizeof(double); }
+  size_t payloadBytes() const { return (size_t)2 * CW * width * sizeof(double); }
+  size_t carryBytes() const { return (size_t)2 * CW * RMAX * sizeof(float); }
+  size_t bytes() const { return 2 * flagBytes() + payloadBytes() + carryBytes(); }   // flags, payload, chain flags, carry
 };
 
 struct dmpc_tree {
@@ -349,6 +351,8 @@ int launchGather(dmpc_tree* t, int mode) {
     for (int p = 0; p < c.world; p++) {
       cv.flag[p] = (unsigned*)c.peer[p];
       cv.payload[p] = (double*)((char*)c.peer[p] + c.flagBytes());
+      cv.cflag[p] = (unsigned*)((char*)c.peer[p] + c.flagBytes() + c.payloadBytes());
+      cv.carry[p] = (float*)((char*)c.peer[p] + 2 * c.flagBytes() + c.payloadBytes());
     }
   }
   CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
@@ -433,6 +437,23 @@ int rootStage(dmpc_tree* t, double* ll) {
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
+    if (t->deferred && t->rv.comm.world > 1) {
+      // peer mailboxes attached: the gather has exchanged; if some rank holds a rescaled site, the chain (vector handed
+      // from rank to rank through the mailboxes) and the final kernel (second exchange) finish on the device too
+      if (t->h_res->xok == -1) { *ll = NAN; return DMPC_OK; }     // fused-clade violation: evaluate() re-runs in exact mode
+      if (t->h_res->xok == 0) {
+        if (chain && (rc = launchChain(t))) return rc;
+        if ((rc = launchFinal(t, mode, 2))) return rc;
+        CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+        if ((rc = readStatus(t, false))) return rc;
+        t->carryIsZero = false;
+      }
+      t->chunksOnHost = false;
+      cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+      if (t->h_res->xok != 1) return fail(DMPC_ERR_CUDA, "peer exchange failed: a rank of the site-sharded run never answered");
+      *ll = t->h_res->ll;
+      return DMPC_OK;
+    }
     if (t->deferred) {
       t->chunksOnHost = t->h_res->nact == 0;
       cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;

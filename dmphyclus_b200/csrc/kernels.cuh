@@ -67,6 +67,8 @@ struct CommView {
   unsigned* seq;                // this rank's message counter (device memory)
   unsigned* flag[CW];           // flag arrays of every rank's mailbox (peer pointers)
   double* payload[CW];          // payload areas of every rank's mailbox (peer pointers)
+  unsigned* cflag[CW];          // same for the exponent-vector hand-off of the cross-locus chain:
+  float* carry[CW];             //   carry[2][CW][RMAX], flag value = sequence number of the evaluation
 };
 
 struct RootView {
@@ -387,6 +389,65 @@ __device__ __forceinline__ double reduce_chunks_device(const double* chunk, int 
   return s_red[0];
 }
 
+// The fused collective of a site-sharded run (called by the LAST block of k_root_gather / k_final, 256 threads).
+// This rank's {rescaled?, nChunks, chunk sums} go straight into every peer's mailbox over NVLink; once every peer's
+// message of the same sequence number has arrived, and no rank reports a rescaled site, each rank adds ALL chunk sums
+// in the fixed global order (the order of reduce_chunks_device over the concatenated list) and has the same
+// log-likelihood, bit for bit, as a single GPU would — without any host-side collective.
+// Returns 1 = ll written, 0 = some rank holds a rescaled site (the chain + final kernels must run), 2 = timeout.
+__device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bool quiet, double* s_red) {
+  __shared__ unsigned s_seq;
+  __shared__ int s_bad;
+  const CommView& cm = rv.comm;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_seq = *cm.seq + 1; s_bad = 0; }
+  __syncthreads();
+  const unsigned seq = s_seq;
+  const int buf = seq & 1, msg = 2 + nCh;
+  for (int idx = tid; idx < cm.world * msg; idx += CHUNK) {
+    const int p = idx / msg, j = idx - p * msg;
+    const double val = j == 0 ? (quiet ? 0.0 : 1.0) : j == 1 ? (double)nCh : rv.chunk[j - 2];
+    *((volatile double*)cm.payload[p] + ((size_t)buf * CW + cm.rank) * cm.width + j) = val;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < cm.world) {
+    *((volatile unsigned*)cm.flag[tid] + cm.rank) = seq;                  // "message seq from me is complete"
+    const volatile unsigned* mine = (volatile unsigned*)cm.flag[cm.rank] + tid;
+    const long long t0 = clock64();
+    while ((int)(*mine - seq) < 0) {
+      if (clock64() - t0 > 40000000000LL) { s_bad = 1; break; }            // ~20 s: a peer died; do not hang the GPU
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)buf * CW * cm.width;
+  bool anyActive = false;
+  for (int p = 0; p < cm.world; p++) anyActive |= in[(size_t)p * cm.width] != 0.0;
+  int res = s_bad ? 2 : 0;
+  if (!s_bad && !anyActive) {
+    double acc = 0.0;
+    int base = 0;                                                          // global index of rank p's first chunk
+    for (int p = 0; p < cm.world; p++) {
+      const int cnt = (int)in[(size_t)p * cm.width + 1];
+      for (int c = ((tid - base) % CHUNK + CHUNK) % CHUNK; c < cnt; c += CHUNK) acc = __dadd_rn(acc, in[(size_t)p * cm.width + 2 + c]);
+      base += cnt;
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int d = CHUNK / 2; d > 0; d >>= 1) {
+      if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
+      __syncthreads();
+    }
+    if (tid == 0) rv.st->ll = s_red[0];
+    res = 1;
+  }
+  __syncthreads();
+  if (tid == 0) *cm.seq = seq;
+  return res;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4a root_gather: per site tile, dot(root, limProbs) and the per-site list of non-zero rescale exponents in
 // vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
@@ -508,60 +569,14 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
     const CommView& cm = rv.comm;
     const bool retry = *(volatile int*)&rv.st->overflow > rv.Kcap || (*(volatile int*)&rv.st->violation != 0 && !rv.exactMode);
     if (cm.world > 1) {
-      // Fused collective: this rank's {rescaled?, nChunks, chunk sums} go straight into every peer's mailbox over
-      // NVLink; when no rank holds a rescaled site, each rank then adds ALL chunk sums in the fixed global order and
-      // has the log-likelihood without any host-side collective.  Skipped when the host is going to re-run this
-      // gather (list overflow, fused-clade violation), so that every rank sends exactly one message per evaluation.
+      // skipped when the host is going to re-run this gather (list overflow, fused-clade violation), so that every
+      // rank sends exactly one message per exchange
       if (retry) {
         if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; }
         return;
       }
-      __shared__ unsigned s_seq;
-      __shared__ int s_bad;
-      if (tid == 0) { s_seq = *cm.seq + 1; s_bad = 0; }
-      __syncthreads();
-      const unsigned seq = s_seq;
-      const int buf = seq & 1, nCh = gridDim.x, msg = 2 + nCh;
-      for (int idx = tid; idx < cm.world * msg; idx += TILE) {
-        const int p = idx / msg, j = idx - p * msg;
-        const double val = j == 0 ? (quiet ? 0.0 : 1.0) : j == 1 ? (double)nCh : rv.chunk[j - 2];
-        *((volatile double*)cm.payload[p] + ((size_t)buf * CW + cm.rank) * cm.width + j) = val;
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < cm.world) {
-        *((volatile unsigned*)cm.flag[tid] + cm.rank) = seq;                  // "message seq from me is complete"
-        const volatile unsigned* mine = (volatile unsigned*)cm.flag[cm.rank] + tid;
-        const long long t0 = clock64();
-        while ((int)(*mine - seq) < 0) {
-          if (clock64() - t0 > 40000000000LL) { s_bad = 1; break; }            // ~20 s: a peer died; do not hang the GPU
-          __nanosleep(200);
-        }
-      }
-      __syncthreads();
-      __threadfence_system();
-      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)buf * CW * cm.width;
-      bool anyActive = false;
-      for (int p = 0; p < cm.world; p++) anyActive |= in[(size_t)p * cm.width] != 0.0;
-      if (!s_bad && !anyActive) {
-        double acc = 0.0;
-        int base = 0;                                                          // global index of rank p's first chunk
-        for (int p = 0; p < cm.world; p++) {
-          const int cnt = (int)in[(size_t)p * cm.width + 1];
-          for (int c = ((tid - base) % CHUNK + CHUNK) % CHUNK; c < cnt; c += CHUNK) acc = __dadd_rn(acc, in[(size_t)p * cm.width + 2 + c]);
-          base += cnt;
-        }
-        s_red[tid] = acc;
-        __syncthreads();
-        for (int d = CHUNK / 2; d > 0; d >>= 1) {
-          if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
-          __syncthreads();
-        }
-        if (tid == 0) { rv.st->ll = s_red[0]; rv.st->xok = 1; }
-      } else if (tid == 0) {
-        rv.st->xok = s_bad ? 2 : 0;
-      }
-      if (tid == 0) { *cm.seq = seq; rv.st->ticket2 = 0; }
+      const int res = exchangeAndReduce(rv, gridDim.x, quiet, s_red);
+      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; }
       return;
     }
     if (quiet) {
@@ -587,7 +602,36 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   __shared__ int s_total[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nth = blockDim.x;
   const int S = v.S, Q = rv.Q;
-  if (rv.st->nact == 0) {                         // nothing rescaled: the vector never leaves its entry value
+  const CommView& cm = rv.comm;
+  const bool sharded = cm.world > 1;
+  if (sharded) {
+    // the chain crosses the site blocks in rank order: take the vector from the nearest earlier rank that holds a
+    // rescaled site (every rank learnt who does from the gather's exchange), or zeros when there is none
+    __shared__ int s_prev;
+    const unsigned seq = *cm.seq;
+    const int buf = seq & 1;
+    if (tid == 0) {
+      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)buf * CW * cm.width;
+      int prev = -1;
+      for (int p = 0; p < cm.rank; p++) if (in[(size_t)p * cm.width] != 0.0) prev = p;
+      if (prev >= 0) {
+        const volatile unsigned* f = (volatile unsigned*)cm.cflag[cm.rank] + prev;
+        const long long t0 = clock64();
+        while ((int)(*f - seq) < 0) { if (clock64() - t0 > 40000000000LL) { prev = -2; break; } __nanosleep(200); }
+      }
+      s_prev = prev;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (tid < RMAX) {
+      float x = 0.0f;
+      if (s_prev >= 0) x = *((volatile float*)cm.carry[cm.rank] + ((size_t)buf * CW + s_prev) * RMAX + tid);
+      rv.carryIn[tid] = x;
+    }
+    if (tid == 0 && s_prev == -2) rv.st->xok = 2;
+    __syncthreads();
+  }
+  if (rv.st->nact == 0) {                         // nothing rescaled here: the vector passes through unchanged
     if (tid < RMAX) rv.carryOut[tid] = rv.carryIn[tid];
     return;
   }
@@ -732,6 +776,17 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   if (tid == 0) {
 #pragma unroll
     for (int r = 0; r < RMAX; r++) if (r < RC) rv.carryOut[r] = c[r];
+    if (sharded) {                                  // hand the vector to every later rank
+      const unsigned seq = *cm.seq;
+      const int buf = seq & 1;
+      for (int p = cm.rank + 1; p < cm.world; p++) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++)
+          *((volatile float*)cm.carry[p] + ((size_t)buf * CW + cm.rank) * RMAX + r) = r < RC ? c[r] : 0.0f;
+      }
+      __threadfence_system();
+      for (int p = cm.rank + 1; p < cm.world; p++) *((volatile unsigned*)cm.cflag[p] + cm.rank) = seq;
+    }
   }
 }
 
@@ -793,7 +848,11 @@ __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mod
     s_last = atomicAdd(&rv.st->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && reduceAll) {
+  if (s_last && reduceAll == 2) {                   // site-sharded: second exchange, every shard is final now
+    __threadfence();
+    const int res = exchangeAndReduce(rv, gridDim.x, true, s_red);
+    if (threadIdx.x == 0) { rv.st->xok = res; rv.st->ticket = 0; }
+  } else if (s_last && reduceAll) {
     __threadfence();
     const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
     if (threadIdx.x == 0) { rv.st->ll = tot; rv.st->ticket = 0; }

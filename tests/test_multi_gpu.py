@@ -50,7 +50,8 @@ def _worker(rank, world, port, case, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [(300, 1500, 5, 3, "evolved", 41), (700, 1100, 6, 3, "iid", 42), (200, 700, 4, 1, "iid", 43)])
+@pytest.mark.parametrize("case", [(300, 1500, 5, 3, "evolved", 41), (700, 1100, 6, 3, "iid", 42), (200, 700, 4, 1, "iid", 43),
+                                  (400, 2300, 5, 3, "tiny", 44), (1024, 1300, 6, 3, "diverged", 45)])
 def test_sharded_matches_single_gpu_bitwise(case):
     import torch
     world = min(torch.cuda.device_count(), 4)
@@ -65,7 +66,6 @@ def test_sharded_matches_single_gpu_bitwise(case):
         for rank in range(world):
             got, want, fast, ncoll = ret[rank]
             assert got == want, (rank, got, want)
-            if case[4] == "evolved":
-                assert fast == len(got) and ncoll == 0       # nothing rescaled: every evaluation finished in-kernel
-            elif case[3] > 1:
-                assert ncoll > 0                             # the fp32 chain had to hop through the ranks
+            # every evaluation finished on the device: chunk sums (and, for the iid cases, the fp32 exponent vector of
+            # the cross-locus chain) travelled through the NVLink mailboxes, no host-side collective ran
+            assert fast == len(got) and ncoll == 0
