@@ -50,8 +50,8 @@ def _worker(rank, world, port, case, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [(300, 1500, 5, 3, "evolved", 41), (700, 1100, 6, 3, "iid", 42), (200, 700, 4, 1, "iid", 43),
-                                  (400, 2300, 5, 3, "tiny", 44), (1024, 1300, 6, 3, "diverged", 45)])
+@pytest.mark.parametrize("case", [(300, 2600, 5, 3, "evolved", 41), (700, 2600, 6, 3, "iid", 42), (200, 2700, 4, 1, "iid", 43),
+                                  (400, 2600, 5, 3, "tiny", 44), (1024, 2600, 6, 3, "diverged", 45)])
 def test_sharded_matches_single_gpu_bitwise(case):
     import torch
     world = min(torch.cuda.device_count(), 4)
