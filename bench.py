@@ -68,6 +68,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, data):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_prune launch from the newest committed ncu capture of this
+    workload (profiles/*_traffic.json, written by tools/ncu_summary.py), or None."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("workload") == workload and d.get("data") == data:
+            best = (d, os.path.basename(f))
+    if best is None:
+        return None, None
+    return best[0]["dram_bytes_per_launch"], best[1]
+
+
 def algorithmic_bytes(n, s, r):
     """per full evaluation, S*R*[(N-2)*32 + (N-1)*36] + S*N bytes (~68 B per update)."""
     return s * r * ((n - 2) * 32 + (n - 1) * 36) + s * n
@@ -274,6 +291,23 @@ def run_ours(args, rank, world, local_rank):
     bytes_unfused = algorithmic_bytes(n, s_local, r)
     achieved = bytes_eval * args.steps / (prune_ms * 1e-3) / 1e9
     dev_bytes = st1["device_bytes"]
+    # Roofline of the dominant kernel (k_prune).  `achieved` follows the contract: SURVEY.md §8(d)'s per-unit figure
+    # (68 B per node-site partial update: children read, partial + exponent written, every vertex stored) x the updates
+    # of the timed launches / their device time.  Small-clade fusion removes most of that traffic — about four fifths
+    # of the vertices are recomputed in registers and never touch HBM — so `achieved` can exceed the HBM peak; the bytes
+    # the kernel really has to move (`moved_*`, counted by the engine for the plan it ran) and the ncu DRAM traffic say
+    # by how much.  See DESIGN.md §3.
+    traffic, traffic_src = ncu_traffic(args.workload, args.data)
+    roofline = {"bound": "hbm", "kernel": "k_prune", "achieved": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9 / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_update": bytes_unfused / ((n - 1) * s_local * r),
+                "algorithmic_bytes_per_launch": bytes_unfused / max(1, st1["last_prune_launches"]),
+                "launches_per_step": int(st1["last_prune_launches"]), "kernel_ms_per_step": prune_ms / args.steps,
+                "kernel_share_of_step": prune_ms / ms,
+                "moved_bytes_per_update": bytes_eval / ((n - 1) * s_local * r), "moved_gbs": achieved,
+                "moved_frac_of_peak": achieved / peak,
+                "stored_vertices": int(st1["last_stored_vertices"]), "fused_vertices": int(st1["last_fused_vertices"])}
     kernel_name = "k_prune"
     eng.finalDeallocate(h)
 
@@ -316,16 +350,7 @@ def run_ours(args, rank, world, local_rank):
                        "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                        "call": "Engine.logLikCpp (dmpc_loglik_create) + finalDeallocate, alignment in pinned host memory"},
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": bytes_eval / max(1, st1["last_prune_launches"]),
-                            "launches_per_step": int(st1["last_prune_launches"]),
-                            "kernel_ms_per_step": prune_ms / args.steps,
-                            "kernel_share_of_step": prune_ms / ms, "frac_of_8000_spec": achieved / 8000.0,
-                            "stored_vertices": int(st1["last_stored_vertices"]), "fused_vertices": int(st1["last_fused_vertices"]),
-                            "bytes_per_update": bytes_eval / ((n - 1) * s_local * r),
-                            "unfused_bytes_per_step": bytes_unfused,
-                            "unfused_equivalent_gbs": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9},
+               "roofline": roofline,
                "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
                "sharded_exchange": ({"in_kernel": eng.fast, "host_collectives": eng.collectives} if world > 1 else None),
                "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),

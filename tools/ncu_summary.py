@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--report")
     ap.add_argument("--bench")
     ap.add_argument("--note", default="")
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--data", default="evolved")
     a = ap.parse_args()
     out = os.path.join(ROOT, "profiles")
     os.makedirs(out, exist_ok=True)
@@ -99,6 +101,18 @@ def main():
             for r in rows[2:]:
                 w.writerow([short(r[i]) if c == "Kernel Name" else r[i] for c, i in zip(cols, idx)])
         md += ["", f"`ncu --set full` capture: `{a.tag}_prune_metrics.csv` (per-launch DRAM bytes, throughput, occupancy)."]
+        # average DRAM traffic per k_prune launch over ONE evaluation's worth of captured launches
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ur, uw = scale[rows[1][ri]], scale[rows[1][wi]]
+        pr = [r for r in rows[2:] if "k_prune" in r[ki]]
+        if pr:
+            tot = sum(float(r[ri]) * ur + float(r[wi]) * uw for r in pr)
+            json.dump({"kernel": "k_prune", "workload": a.workload, "data": a.data, "launches_captured": len(pr),
+                       "dram_bytes_per_launch": tot / len(pr), "dram_bytes_total": tot,
+                       "source": f"ncu --set full, {os.path.basename(a.report)}"},
+                      open(os.path.join(out, f"{a.tag}_traffic.json"), "w"), indent=1)
+            md += [f"k_prune DRAM traffic: {tot / 1e6:.1f} MB over {len(pr)} captured launches = {tot / len(pr) / 1e6:.2f} MB per launch."]
     open(os.path.join(out, f"{a.tag}_kernel_share.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md))
 
