@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
+    ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
     ap.add_argument("--seed", type=int, default=2001)
     return ap.parse_args()
 
@@ -400,6 +401,52 @@ def extra_legs(args, eng, p, al, n, s, k, r):
     return out
 
 
+def proposal_sweep(args):
+    """BASELINE.json config 4: B split / merge proposals per dmpc_eval_proposals call on 5,000 seqs x 5,000 sites."""
+    import torch
+    from dmphyclus_b200 import build, synth
+    from dmphyclus_b200.engine import Engine
+    from dmphyclus_b200.phylo import Phylo
+    from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
+    build.build()
+    n, s, _, r = CONFIGS["config4"]
+    k = 1500                                  # many small clusters: enough distinct split / merge candidates
+    p = Problem(load_packaged(), n, s, k, r, args.data, args.tree, seed=args.seed)
+    eng = Engine(device=0, fuse_tips=args.fuse)
+    al = eng.getConvertedAlignment(list(synth.STATES), p.chars)
+    W, B = p.W[4], p.B[4]
+    h = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, n, s, 5, 5)["solutionPointer"]
+    phy = Phylo(p.edge, n)
+    cand = [("split", m) for m in p.mrcas if m > n]
+    groups = {}
+    for m in p.mrcas:
+        groups.setdefault(int(phy.parent[m]), []).append(m)
+    cand += [("merge", g[0], g[1]) for g in groups.values() if len(g) == 2]
+    depth = phy.depth()
+    rows = []
+    for bsz in (64, 128, 256, 512, 1024, 2048, 4096):
+        props = [cand[i % len(cand)] for i in range(bsz)]
+        upd = sum(int(depth[q[1]] if q[0] == "split" else depth[q[1]] - 1) + 1 for q in props) * s * r
+        eng.evalProposals(h, W, B, p.pi, props)
+        eng.timer_begin(h)
+        reps = 5
+        for _ in range(reps):
+            ll, nb = eng.evalProposals(h, W, B, p.pi, props)
+        ms = eng.timer_end(h) / reps
+        rows.append({"batch": bsz, "ms": ms, "proposals_per_s": bsz / ms * 1e3, "path_updates_per_s": upd / ms * 1e3, "batched": nb})
+    # the same proposals one at a time through the reference-style entry point
+    props = [cand[i % len(cand)] for i in range(64)]
+    eng.timer_begin(h)
+    for q in props:
+        eng.clusSplitMergeLogLik(h, W, B, [q[1]] if q[0] == "split" else [q[1], q[2]], 1, p.pi)
+        eng.RestorePreviousConfig(h, np.zeros((1, 2), np.int32), 5, 5, False, p.mrcas, True)
+    one = eng.timer_end(h) / len(props)
+    eng.finalDeallocate(h)
+    emit(json.dumps({"metric": "cluster proposals/sec", "unit": "proposals/s", "workload": f"config4: {n} seqs x {s} sites, {k} clusters, "
+                     f"{len(cand)} distinct split/merge candidates", "alignment": args.data, "sweep": rows,
+                     "one_by_one_ms_per_proposal": one, "one_by_one_proposals_per_s": 1e3 / one}))
+
+
 def cpu_baseline(p, n, s, r):
     from oracle.oracle import Oracle
     be, kind = cpu_reference_backend()
@@ -428,7 +475,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.proposal_sweep:
+        proposal_sweep(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

@@ -692,19 +692,10 @@ int dmpc_clus_split_merge_loglik(dmpc_tree* t, const double* withinTransMats, co
   return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
 }
 
-int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRows, int withinMatListIndex,
-                                 int betweenMatListIndex, int nniMove, const int32_t* clusterMRCAs,
-                                 int nClusterMRCAs, int splitMergeMove) {
-  int rc;
-  if ((rc = checkHandle(t))) return rc;
-  if ((rc = ensureDevice(t))) return rc;
+// RestoreIterVecAndExp (IntermediateNode.h:26-33): the vertices the last proposal touched go back to their previous slot
+static int rollbackTouched(dmpc_tree* t) {
   HostTree& ht = t->ht;
-  ht.withinIdx = withinMatListIndex; ht.betweenIdx = betweenMatListIndex;
-  if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
-    if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
-    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
-  }
-  int n = 0;                                      // RestoreIterVecAndExp, IntermediateNode.h:26-33
+  int n = 0;
   for (int v = ht.numTips; v < ht.numVerts; v++)
     if (ht.touched[v]) {
       ht.cur[v] ^= 1;
@@ -718,6 +709,22 @@ int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRow
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(t->stream));   // h_curList is reused by the next rollback
   }
+  return DMPC_OK;
+}
+
+int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRows, int withinMatListIndex,
+                                 int betweenMatListIndex, int nniMove, const int32_t* clusterMRCAs,
+                                 int nClusterMRCAs, int splitMergeMove) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  HostTree& ht = t->ht;
+  ht.withinIdx = withinMatListIndex; ht.betweenIdx = betweenMatListIndex;
+  if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
+    if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
+    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
+  }
+  if ((rc = rollbackTouched(t))) return rc;
   if (splitMergeMove) {
     if (nClusterMRCAs > 0 && !clusterMRCAs) return fail(DMPC_ERR_ARG, "null pointer");
     ht.associate(clusterMRCAs, nClusterMRCAs);
@@ -749,6 +756,123 @@ int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double
   t->ht.negateAllUpdateFlags();
   t->ht.invalidateAll();
   return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+}
+
+// Batch of split / merge proposals against the committed state (no reference counterpart).
+int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats, const double* limProbs,
+                        const dmpc_proposal* props, int nProps, double* logLikOut, int* nBatchedOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if ((rc = ensureDevice(t))) return rc;
+  if (!withinTransMats || !betweenTransMats || !limProbs || !props || !logLikOut || nProps < 0) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->deferred) return fail(DMPC_ERR_STATE, "dmpc_eval_proposals is not available on a site-sharded (deferred) handle");
+  HostTree& ht = t->ht;
+  if (!ht.solved[ht.root()]) return fail(DMPC_ERR_STATE, "the committed state has pending invalidations");
+  for (int i = 0; i < nProps; i++) {
+    const dmpc_proposal& q = props[i];
+    if (q.kind == DMPC_PROPOSAL_SPLIT) {
+      if (q.a <= ht.numTips || q.a > ht.numVerts) return fail(DMPC_ERR_ARG, "split: the cluster MRCA must be an internal vertex");
+    } else if (q.kind == DMPC_PROPOSAL_MERGE) {
+      if (q.a < 1 || q.a > ht.numVerts || q.b < 1 || q.b > ht.numVerts || q.a == q.b || ht.parent[q.a - 1] < 0 ||
+          ht.parent[q.a - 1] != ht.parent[q.b - 1])
+        return fail(DMPC_ERR_ARG, "merge: the two cluster MRCAs must be siblings");
+    } else {
+      return fail(DMPC_ERR_ARG, "unknown proposal kind");
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_constMutex);
+    if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
+  }
+  if ((rc = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return rc;
+  int nBatched = 0;
+  std::vector<uint8_t> needSeq(nProps, 1);
+  // the batched kernel assumes a resting exponent vector: nothing rescaled in the committed state, nothing may in a proposal
+  const bool batchable = !t->exact && t->lastNact == 0 && nProps > 0;
+  if (batchable) {
+    const size_t perProp = (size_t)t->R * t->Sp * sizeof(double);
+    const int maxBatch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nProps, ((size_t)2 << 30) / perProp));
+    HostTree::Plan pp;
+    std::vector<int> runStart;
+    std::vector<double> chunks;
+    std::vector<int> invalid;
+    for (int b0 = 0; b0 < nProps; b0 += maxBatch) {
+      const int nb = std::min(maxBatch, nProps - b0);
+      pp.tasks.clear(); pp.tokens.clear(); pp.tipList.clear();
+      runStart.assign(1, 0);
+      for (int i = b0; i < b0 + nb; i++) {
+        const dmpc_proposal& q = props[i];
+        if (q.kind == DMPC_PROPOSAL_SPLIT) {         // HandleSplit, AugTree.cpp:328-336, on a scratch copy of the flags
+          const int m = q.a - 1, k0 = ht.kids[2 * m], k1 = ht.kids[2 * m + 1];
+          const uint8_t w0 = ht.within[k0], w1 = ht.within[k1];
+          ht.within[k0] = 0; ht.within[k1] = 0;
+          ht.pathRun(m, pp);
+          ht.within[k0] = w0; ht.within[k1] = w1;
+        } else {                                     // HandleMerge, AugTree.cpp:338-346
+          const int a = q.a - 1, b = q.b - 1;
+          const uint8_t wa = ht.within[a], wb = ht.within[b];
+          ht.within[a] = 1; ht.within[b] = 1;
+          ht.pathRun(ht.parent[a], pp);
+          ht.within[a] = wa; ht.within[b] = wb;
+        }
+        runStart.push_back((int)pp.tasks.size());
+      }
+      Task* dT = nullptr; Token* dK = nullptr; int32_t* dL = nullptr; int* dR = nullptr; int* dI = nullptr;
+      double* dRoot = nullptr; double* dC = nullptr;
+      const size_t nT = pp.tasks.size(), nK = std::max<size_t>(1, pp.tokens.size()), nL = std::max<size_t>(1, pp.tipList.size());
+      CUDA_TRY(cudaMallocAsync((void**)&dT, nT * sizeof(Task), t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dK, nK * sizeof(Token), t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dL, nL * sizeof(int32_t), t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dR, (size_t)(nb + 1) * sizeof(int), t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dI, (size_t)nb * sizeof(int), t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dRoot, (size_t)nb * perProp, t->stream));
+      CUDA_TRY(cudaMallocAsync((void**)&dC, (size_t)nb * t->T * sizeof(double), t->stream));
+      CUDA_TRY(cudaMemcpyAsync(dT, pp.tasks.data(), nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
+      if (!pp.tokens.empty()) CUDA_TRY(cudaMemcpyAsync(dK, pp.tokens.data(), pp.tokens.size() * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+      if (!pp.tipList.empty()) CUDA_TRY(cudaMemcpyAsync(dL, pp.tipList.data(), pp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(dR, runStart.data(), (size_t)(nb + 1) * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemsetAsync(dI, 0, (size_t)nb * sizeof(int), t->stream));
+      k_prune_paths<<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, dT, dR, dK, dL, dRoot, dI);
+      k_paths_final<<<dim3((unsigned)nb, (unsigned)t->T), CHUNK, 0, t->stream>>>(t->S, t->Sp, t->R, dRoot, dC);
+      t->st.kernel_launches += 2;
+      CUDA_TRY(cudaGetLastError());
+      chunks.resize((size_t)nb * t->T);
+      invalid.resize(nb);
+      CUDA_TRY(cudaMemcpyAsync(chunks.data(), dC, chunks.size() * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(invalid.data(), dI, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+      CUDA_TRY(cudaStreamSynchronize(t->stream));    // also: the pageable host vectors above were the copy sources
+      for (void* q : {(void*)dT, (void*)dK, (void*)dL, (void*)dR, (void*)dI, (void*)dRoot, (void*)dC}) cudaFreeAsync(q, t->stream);
+      for (int i = 0; i < nb; i++)
+        if (!invalid[i]) {
+          logLikOut[b0 + i] = dmpc_reduce_chunks(chunks.data() + (size_t)i * t->T, t->T);
+          needSeq[b0 + i] = 0;
+          nBatched++;
+        }
+      t->st.updates += (unsigned long long)nT * t->S * t->R;
+    }
+  }
+  // whatever could not be batched (rescaling involved, exact mode): the ordinary proposal path, then an internal reject
+  for (int i = 0; i < nProps; i++) {
+    if (!needSeq[i]) continue;
+    const dmpc_proposal& q = props[i];
+    const std::vector<uint8_t> savedWithin = ht.within;
+    const int savedNact = t->lastNact;
+    ht.negateAllUpdateFlags();
+    if (q.kind == DMPC_PROPOSAL_SPLIT) {
+      const int m = q.a - 1;
+      ht.invalidateSolution(m);
+      ht.within[ht.kids[2 * m]] = 0; ht.within[ht.kids[2 * m + 1]] = 0;
+    } else {
+      ht.invalidateSolution(ht.parent[q.a - 1]);
+      ht.within[q.a - 1] = 1; ht.within[q.b - 1] = 1;
+    }
+    if ((rc = evaluate(t, withinTransMats, betweenTransMats, limProbs, &logLikOut[i]))) return rc;
+    if ((rc = rollbackTouched(t))) return rc;
+    ht.within = savedWithin;
+    t->lastNact = savedNact;
+  }
+  if (nBatchedOut) *nBatchedOut = nBatched;
+  return DMPC_OK;
 }
 
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {

@@ -295,6 +295,24 @@ struct HostTree {
     return k;
   }
 
+  // Proposal paths (dmpc_eval_proposals): the stored vertices from `s` (or its first stored ancestor) up to the root,
+  // bottom-up, appended to p as one run.  Nothing is mutated; the on-path operand of every task but the first is the
+  // previous task's output, forwarded in registers.  The parent of a stored vertex is stored, so the run is contiguous.
+  void pathRun(int s, Plan& p) {
+    computeTips();
+    int v = s;
+    while (fused(v)) v = parent[v];
+    int prev = -1;
+    for (; v != -1; prev = v, v = parent[v]) {
+      Task k = makeTask(v, 0, 0, p, false);
+      if (prev >= 0) {
+        if (kids[2 * v] == prev) k.flags = (k.flags & ~TF_C0SLOT) | TF_C0FWD;
+        else k.flags = (k.flags & ~TF_C1SLOT) | TF_C1FWD;
+      }
+      p.tasks.push_back(k);
+    }
+  }
+
   void plan(Plan& p) {
     p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
     p.storedReads = p.tipReads = p.fusedOps = 0;

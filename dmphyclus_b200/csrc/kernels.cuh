@@ -361,6 +361,190 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
   if (!EXACT && trig) *violation = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3 prune_paths: a BATCH of proposals per launch (dmpc_eval_proposals).  Proposal b is a run of tasks — the stored
+// vertices on the path from the vertex it changes up to the root; grid = (proposals, T, R).  The thread walks its
+// run bottom-up with the path partial in registers (TF_CxFWD operands), reading only the off-path siblings (stored
+// partials, tip masks, fused clades) and writing nothing but dot(root, pi) for its (proposal, rate, site).  The
+// committed state is not touched.  Any rescale (or possible rescale inside a fused clade) marks the proposal invalid;
+// the host evaluates those one by one through the ordinary path.
+__global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __restrict__ tasks, const int* __restrict__ runStart,
+                                                       const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
+                                                       double* __restrict__ rootdot, int* __restrict__ invalid) {
+  __shared__ __align__(16) double s_lut[2 * 64];
+  __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
+  __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
+  __shared__ __align__(16) int4 s_tok[3 * FUSE_MAX_TIPS + 4];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x, tile = blockIdx.y, r = blockIdx.z, R = v.R;
+  const int site0 = tile * TILE + tid;
+  const size_t Sp = (size_t)v.Sp;
+  bool bad = false;
+  s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];       // PT == 2 * 64
+  __syncthreads();
+  double prev[SPT][4];
+#pragma unroll
+  for (int u = 0; u < SPT; u++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) prev[u][k] = 0.0;
+
+  for (int ti = runStart[b]; ti < runStart[b + 1]; ti++) {
+    const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
+    const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
+    const int fl = tk0.w;
+    const int set = (fl & TF_WITHIN) ? 1 : 0;
+    const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
+    const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
+    const bool fwd0 = (fl & TF_C0FWD) != 0, fwd1 = (fl & TF_C1FWD) != 0;
+    const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site0) * 4;
+    const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site0) * 4;
+    const bool plain = !(fus0 | fus1);
+    const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff, ntok = n0 + n1;
+    unsigned ma[SPT], mb[SPT];
+    double a[SPT][4], bb[SPT][4];
+#pragma unroll
+    for (int u = 0; u < SPT; u++) {
+      if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT];
+      else if (!fus0 && !fwd0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
+      if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT];
+      else if (!fus1 && !fwd1) ld256(pb + (size_t)u * PT * 4, bb[u][0], bb[u][1], bb[u][2], bb[u][3]);
+    }
+    if (!plain) {
+      const int nTips = tk1.w;
+      for (int j = tid; j < nTips * (TILE / 4); j += PT) {
+        const int tipIdx = j / (TILE / 4), q = j - tipIdx * (TILE / 4);
+        const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + tipIdx) * Sp + tile * TILE + 4 * q;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + tipIdx * TILE + 4 * q);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (tid < ntok) s_tok[tid] = __ldg(reinterpret_cast<const int4*>(prog + tk1.x + tid));
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    double reg[SPT][4];
+    auto run = [&](int first, int n, int sp) {
+      for (int i = first; i < first + n; i++) {
+        const int4 t4 = s_tok[i];
+        const int op = t4.x & 7;
+        if (op == OP_SPILL) {
+#pragma unroll
+          for (int u = 0; u < SPT; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid + u * PT] = reg[u][k];
+          sp++;
+          continue;
+        }
+        const int tset = (t4.x & TOK_SET) ? 1 : 0;
+        const double* P = c_P[tset][r];
+        const double* lutr = s_lut + tset * 64;
+        if (op == OP_SLOTREG) sp--;
+#pragma unroll
+        for (int u = 0; u < SPT; u++) {
+          double x[4], y[4];
+          if (op == OP_CHERRY) {
+            const unsigned m0 = s_mask[t4.y * TILE + tid + u * PT], m1 = s_mask[t4.z * TILE + tid + u * PT];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
+          } else if (op == OP_REGTIP) {
+            const unsigned m1 = s_mask[t4.z * TILE + tid + u * PT];
+            matvec4(P, reg[u], x);
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
+          } else {
+            double z[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid + u * PT];
+            matvec4(P, z, x);
+            matvec4(P, reg[u], y);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) reg[u][k] = __dmul_rn(x[k], y[k]);
+          bad |= maybeBelow4(reg[u]);
+        }
+      }
+    };
+    if (fus0) {
+      run(0, n0, 0);
+      if (fus1) {
+#pragma unroll
+        for (int u = 0; u < SPT; u++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) s_stack[k * TILE + tid + u * PT] = reg[u][k];
+      }
+    }
+    if (fus1) run(n0, n1, 1);
+    const double* P = c_P[set][r];
+    const double* lutr = s_lut + set * 64;
+#pragma unroll
+    for (int u = 0; u < SPT; u++) {
+      double first[4], second[4], s4[4];
+      if (tip0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma[u] + k];
+      } else if (fus0) {
+        if (fus1) {
+          double z[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid + u * PT];
+          matvec4(P, z, first);
+        } else {
+          matvec4(P, reg[u], first);
+        }
+      } else if (fwd0) {
+        matvec4(P, prev[u], first);
+      } else {
+        matvec4(P, a[u], first);
+      }
+      if (tip1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb[u] + k];
+      } else if (fus1) {
+        matvec4(P, reg[u], second);
+      } else if (fwd1) {
+        matvec4(P, prev[u], second);
+      } else {
+        matvec4(P, bb[u], second);
+      }
+      float e = 0.0f;
+      combineExact(first, second, s4, e);
+      bad |= e != 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) prev[u][k] = s4[k];
+    }
+    if (!plain) __syncthreads();                   // s_mask / s_tok are reused by the next task
+  }
+#pragma unroll
+  for (int u = 0; u < SPT; u++)                    // arma::dot: two interleaved accumulators
+    rootdot[((size_t)b * R + r) * Sp + site0 + u * PT] =
+        __dadd_rn(__dadd_rn(__dmul_rn(prev[u][0], c_pi[0]), __dmul_rn(prev[u][2], c_pi[2])),
+                  __dadd_rn(__dmul_rn(prev[u][1], c_pi[1]), __dmul_rn(prev[u][3], c_pi[3])));
+  if (bad) invalid[b] = 1;
+}
+
+// per (proposal, 256-site chunk): the site terms with a resting exponent vector and their fixed-tree sum
+__global__ void __launch_bounds__(CHUNK) k_paths_final(int S, int Sp, int R, const double* __restrict__ rootdot, double* __restrict__ chunks) {
+  __shared__ double s_red[CHUNK];
+  const int b = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
+  const int s = tile * CHUNK + tid;
+  double ll = 0.0;
+  if (s < S) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int r = 0; r < R; r++) {
+      const double x = __dmul_rn(rootdot[((size_t)b * R + r) * Sp + s], 1.0);
+      if (r & 1) a2 = __dadd_rn(a2, x); else a1 = __dadd_rn(a1, x);
+    }
+    ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)R), 0.0);
+  }
+  s_red[tid] = ll;
+  __syncthreads();
+  for (int d = CHUNK / 2; d > 0; d >>= 1) {
+    if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) chunks[(size_t)b * gridDim.y + tile] = s_red[0];
+}
+
 // rollback: flip the slot bits of the vertices a rejected proposal touched (IntermediateNode.h:26-33)
 __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -18,7 +18,8 @@ struct Task {
 enum : int32_t {
   TF_OUTSLOT = 1, TF_C0TIP = 2, TF_C1TIP = 4, TF_C0SLOT = 8, TF_C1SLOT = 16,
   TF_WITHIN = 32,         // matrix set of this vertex = within-flag of its FIRST child (AugTree.cpp:125)
-  TF_C0FUSED = 64, TF_C1FUSED = 128
+  TF_C0FUSED = 64, TF_C1FUSED = 128,
+  TF_C0FWD = 256, TF_C1FWD = 512   // proposal paths: the operand is the output of the previous task of the run (registers)
 };
 
 // One step of a fused-clade program.  The evaluator is a stack machine per thread (= per site): REG holds the

@@ -62,6 +62,7 @@ ABI = {
     "dmpc_get_max_map_size_estimate": (C.c_double, [C.c_double, C.c_uint]),
     "dmpc_check_and_cull_map": (C.c_int, [_P, C.c_uint, C.c_float, _dbl_p, _dbl_p, _dbl_p]),
     "dmpc_recompute_all": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, _dbl_p]),
+    "dmpc_eval_proposals": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, C.c_void_p, C.c_int, _dbl_p, C.POINTER(C.c_int)]),
     "dmpc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dmpc_timer_begin": (C.c_int, [_P]),
     "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
@@ -239,6 +240,19 @@ class Engine:
         ll = C.c_double()
         self._check(self.lib.dmpc_recompute_all(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p), C.byref(ll)))
         return ll.value
+
+    def evalProposals(self, ptr, withinTransProbs, betweenTransProbs, limProbs, proposals):
+        """Batch of split / merge proposals against the committed state (left untouched).  `proposals`: iterable of
+        ("split", mrca) or ("merge", mrcaA, mrcaB), 1-based ids.  Returns (logLik array, number evaluated by the batched kernel)."""
+        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        arr = np.zeros((len(proposals), 3), np.int32)
+        for i, q in enumerate(proposals):
+            arr[i] = (0, q[1], 0) if q[0] == "split" else (1, q[1], q[2])
+        out = np.empty(len(proposals), np.float64)
+        nb = C.c_int()
+        self._check(self.lib.dmpc_eval_proposals(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p), arr.ctypes.data_as(C.c_void_p),
+                                                 len(proposals), _p(out, _dbl_p), C.byref(nb)))
+        return out, nb.value
 
     def stats(self, ptr) -> dict:
         s = Stats()

@@ -114,6 +114,20 @@ int dmpc_check_and_cull_map(dmpc_tree* t, unsigned allowedNumberOfElements, floa
 int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
                        const double* limProbs, double* logLikOut);
 
+/* A batch of cluster proposals evaluated against the COMMITTED state, which is left untouched: logLikOut[i] is what
+ * dmpc_clus_split_merge_loglik would return for proposal i (followed by a reject).  Proposals whose paths involve no
+ * rescaling are evaluated together — one launch walks every proposal's path to the root with the path partial in
+ * registers, reading only the off-path siblings; the rest goes through the ordinary path one by one.  *nBatchedOut =
+ * how many took the batched kernel.  Matrices must be the committed ones. */
+enum { DMPC_PROPOSAL_SPLIT = 0, DMPC_PROPOSAL_MERGE = 1 };
+typedef struct dmpc_proposal {
+  int32_t kind;   /* DMPC_PROPOSAL_SPLIT: a = cluster MRCA to split; DMPC_PROPOSAL_MERGE: a, b = sibling cluster MRCAs */
+  int32_t a, b;   /* 1-based vertex ids */
+} dmpc_proposal;
+int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const double* betweenTransMats,
+                        const double* limProbs, const dmpc_proposal* props, int nProps, double* logLikOut,
+                        int* nBatchedOut);
+
 /* Counters since creation: node-site-rate partial updates performed, kernels launched, seconds of device time of
  * the last evaluation (CUDA events on the engine's stream). */
 typedef struct dmpc_stats {

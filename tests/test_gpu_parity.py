@@ -290,3 +290,46 @@ def test_fused_vertices_are_readable(packaged, engine, oracle):
     for v in range(p.n, 2 * p.n - 1):
         assert np.array_equal(engine.partial(hg, v)[0], oracle.partial(ho, v)[0]), v
     engine.finalDeallocate(hg); oracle.finalDeallocate(ho)
+
+
+# ---------------------------------------------------------------------------------------------- proposal batches
+def _split_merge_candidates(p):
+    """Every legal split (clusters whose MRCA is internal) and merge (sibling cluster MRCAs) of the current clustering."""
+    from dmphyclus_b200.phylo import Phylo
+    phy = Phylo(p.edge, p.n)
+    props = [("split", m) for m in p.mrcas if m > p.n]
+    by_parent = {}
+    for m in p.mrcas:
+        by_parent.setdefault(int(phy.parent[m]), []).append(m)
+    props += [("merge", g[0], g[1]) for g in by_parent.values() if len(g) == 2]
+    return props
+
+
+@pytest.mark.parametrize("n,S,k,R,kind,fuse", [(300, 700, 24, 3, "evolved", 8), (300, 700, 24, 3, "evolved", 1), (64, 300, 9, 1, "evolved", 8),
+                                                (900, 300, 30, 3, "iid", 8), (500, 520, 40, 2, "evolved", 15)])
+def test_proposal_batch_equals_one_by_one(packaged, oracle, n, S, k, R, kind, fuse):
+    """dmpc_eval_proposals: B proposals per launch == the same proposals evaluated one at a time through
+    clusSplitMergeLogLik + RestorePreviousConfig (bitwise on the GPU, 1e-9 against the oracle); the committed state is
+    untouched.  The iid case rescales, so the batch has to fall back to the ordinary path."""
+    from dmphyclus_b200.engine import Engine
+    eng = Engine(fuse_tips=fuse)
+    p = Problem(packaged, n, S, k, R, kind, seed=n + k)
+    props = _split_merge_candidates(p)
+    assert len(props) >= 5
+    hg, l0 = p.create(eng)
+    ho, _ = p.create(oracle)
+    W, B = p.W[4], p.B[4]
+    got, nb = eng.evalProposals(hg, W, B, p.pi, props)
+    assert (nb == len(props)) if kind == "evolved" else (nb == 0)
+    one_by_one, want = [], []
+    for q in props:
+        ids = [q[1]] if q[0] == "split" else [q[1], q[2]]
+        for be, h, out in ((eng, hg, one_by_one), (oracle, ho, want)):
+            out.append(be.clusSplitMergeLogLik(h, W, B, ids, 1, p.pi))
+            be.RestorePreviousConfig(h, np.zeros((1, 2), np.int32), 5, 5, False, p.mrcas, True)
+    assert list(got) == one_by_one
+    assert np.all(np.abs(got - np.array(want)) <= TOL * np.abs(np.array(want)))
+    assert eng.recomputeAll(hg, W, B, p.pi) == l0                 # nothing moved
+    got2, _ = eng.evalProposals(hg, W, B, p.pi, props[:3])
+    assert list(got2) == one_by_one[:3]
+    eng.finalDeallocate(hg); oracle.finalDeallocate(ho)
