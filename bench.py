@@ -51,12 +51,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--data", default="evolved", choices=["evolved", "iid"])
+    ap.add_argument("--data", default="evolved", choices=["evolved", "iid", "matched"])
     ap.add_argument("--tree", default="random", choices=["random", "balanced", "caterpillar"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
+    ap.add_argument("--sweep-rates", type=int, default=1, help="rate categories of the proposal sweep (with 3, config 4's committed state has rescaled sites and the batch falls back to one-by-one evaluation)")
     ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
     ap.add_argument("--seed", type=int, default=2001)
     return ap.parse_args()
@@ -409,9 +410,12 @@ def proposal_sweep(args):
     from dmphyclus_b200.phylo import Phylo
     from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
     build.build()
-    n, s, _, r = CONFIGS["config4"]
-    k = 1500                                  # many small clusters: enough distinct split / merge candidates
-    p = Problem(load_packaged(), n, s, k, r, args.data, args.tree, seed=args.seed)
+    n, s, k, r = CONFIGS["config4"]
+    r = args.sweep_rates
+    # the batched kernel needs a committed state without rescaled sites: an alignment evolved under the matrices it
+    # is evaluated with ("matched") has none at this size; anything else falls back to one-by-one evaluation
+    data = "matched" if args.data == "evolved" else args.data
+    p = Problem(load_packaged(), n, s, k, r, data, args.tree, seed=args.seed)
     eng = Engine(device=0, fuse_tips=args.fuse)
     al = eng.getConvertedAlignment(list(synth.STATES), p.chars)
     W, B = p.W[4], p.B[4]
@@ -441,9 +445,10 @@ def proposal_sweep(args):
         eng.clusSplitMergeLogLik(h, W, B, [q[1]] if q[0] == "split" else [q[1], q[2]], 1, p.pi)
         eng.RestorePreviousConfig(h, np.zeros((1, 2), np.int32), 5, 5, False, p.mrcas, True)
     one = eng.timer_end(h) / len(props)
+    active = eng.stats(h)["last_active_tiles"]
     eng.finalDeallocate(h)
-    emit(json.dumps({"metric": "cluster proposals/sec", "unit": "proposals/s", "workload": f"config4: {n} seqs x {s} sites, {k} clusters, "
-                     f"{len(cand)} distinct split/merge candidates", "alignment": args.data, "sweep": rows,
+    emit(json.dumps({"committed_state_rescaled_tiles": active, "metric": "cluster proposals/sec", "unit": "proposals/s", "workload": f"config4: {n} seqs x {s} sites, {k} clusters, {r} rate categories, "
+                     f"{len(cand)} distinct split/merge candidates", "alignment": data, "sweep": rows,
                      "one_by_one_ms_per_proposal": one, "one_by_one_proposals_per_s": 1e3 / one}))
 
 

@@ -58,6 +58,8 @@ class Problem:
             self.chars = synth.iid_alignment(n, n_sites, rng)
         elif kind == "diverged":
             self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[9], self.B[9], self.mrcas, self.pi, rng)
+        elif kind == "matched":      # evolved under exactly the matrices it is evaluated with
+            self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[w_idx - 1], self.B[b_idx - 1], self.mrcas, self.pi, rng)
         elif kind == "evolved":
             self.chars = synth.evolve_alignment(self.edge, n, n_sites, self.W[4], self.B[9], self.mrcas, self.pi, rng)
         else:
