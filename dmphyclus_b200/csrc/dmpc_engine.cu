@@ -93,6 +93,20 @@ struct dmpc_tree {
   std::vector<void*> allocs;
   dmpc_stats st{};
   HostTree::Plan plan;
+  // what runPlan launches: the plan just built (d_tasks ...) or the cached full-evaluation plan replayed with a slot flip
+  const HostTree::Plan* runPlanMeta = nullptr;
+  const Task* runTasks = nullptr; const Token* runTokens = nullptr; const int32_t* runTips = nullptr;
+  int runFlip = 0;
+  struct {
+    bool valid = false;
+    int fuse = 0;
+    std::vector<int32_t> kids;
+    std::vector<uint8_t> within, cur;
+    HostTree::Plan meta;                 // level structure and counters (the big vectors stay empty)
+    Task* dTasks = nullptr; Token* dTokens = nullptr; int32_t* dTips = nullptr;
+    int metaTasks = 0;
+  } cache;
+  unsigned long long planCacheHits = 0;
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
   Token* d_tokens = nullptr;
   Token* h_tokens = nullptr;     // pinned
@@ -250,21 +264,21 @@ int rootStage(dmpc_tree* t, double* ll);
 constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
-  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, &t->rv.st->violation);
-  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->d_tokens, t->d_tipList, &t->rv.st->violation);
+  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);
+  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);
   return DMPC_OK;
 }
 
 // the level launches of the current plan (tasks, tokens and tip lists are already on the device)
 int runPlan(dmpc_tree* t) {
-  const HostTree::Plan& p = t->plan;
+  const HostTree::Plan& p = *t->runPlanMeta;
   const int nLevels = (int)p.levelStart.size() - 1;
   if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
   CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
   int launches = 0;
   for (int l = 0; l < nLevels;) {
     int n = p.levelStart[l + 1] - p.levelStart[l];
-    const Task* lt = t->d_tasks + p.levelStart[l];
+    const Task* lt = t->runTasks + p.levelStart[l];
     // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.x == 1)
     int l2 = l + 1;
     bool run = n <= NARROW_LEVEL;
@@ -299,31 +313,76 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   if ((rc = uploadConstants(t, within, between, pi))) return rc;
   HostTree& ht = t->ht;
   HostTree::Plan& p = t->plan;
-  ht.plan(p);
-  t->st.last_host_plan_us = usSince(h0);
-  const int nTasks = (int)p.tasks.size(), nTok = (int)p.tokens.size();
-  if (nTasks) {
-    for (int sl = 0; sl < 2; sl++)
-      if (p.uses[sl] && (rc = allocSlot(t, sl))) return rc;
-    std::memcpy(t->h_tasks, p.tasks.data(), (size_t)nTasks * sizeof(Task));
-    CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, (size_t)nTasks * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
-    if (nTok) {
-      std::memcpy(t->h_tokens, p.tokens.data(), (size_t)nTok * sizeof(Token));
-      CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, (size_t)nTok * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
-      std::memcpy(t->h_tipList, p.tipList.data(), p.tipList.size() * sizeof(int32_t));
-      CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+  const bool full = ht.allInvalid;
+  // A full re-evaluation of an unchanged tree (every MCMC iteration proposes new within-cluster matrices ->
+  // InvalidateAll) needs the same plan as the last one, with every slot toggled: replay the device-resident copy.
+  bool hit = false;
+  int flip = 0;
+  auto& cc = t->cache;
+  if (full && cc.valid && cc.fuse == ht.fuseTips && cc.kids == ht.kids && cc.within == ht.within) {
+    flip = ht.cur[ht.root()] ^ cc.cur[ht.root()];
+    hit = true;
+    for (int v = ht.numTips; v < ht.numVerts && hit; v++) hit = (ht.cur[v] ^ cc.cur[v]) == flip;
+  }
+  const HostTree::Plan* meta = &p;
+  if (hit) {
+    for (int v = ht.numTips; v < ht.numVerts; v++) { ht.cur[v] ^= 1; ht.touched[v] = 1; ht.solved[v] = 1; }
+    ht.allInvalid = false;
+    if ((rc = allocSlot(t, 0)) || (rc = allocSlot(t, 1))) return rc;
+    meta = &cc.meta;
+    t->runTasks = cc.dTasks; t->runTokens = cc.dTokens; t->runTips = cc.dTips; t->runFlip = flip;
+    t->planCacheHits++;
+  } else {
+    std::vector<uint8_t> curBefore;
+    if (full) curBefore = ht.cur;
+    ht.plan(p);
+    t->runTasks = t->d_tasks; t->runTokens = t->d_tokens; t->runTips = t->d_tipList; t->runFlip = 0;
+    const int nT = (int)p.tasks.size(), nK = (int)p.tokens.size();
+    if (nT) {
+      for (int sl = 0; sl < 2; sl++)
+        if (p.uses[sl] && (rc = allocSlot(t, sl))) return rc;
+      std::memcpy(t->h_tasks, p.tasks.data(), (size_t)nT * sizeof(Task));
+      CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, (size_t)nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
+      if (nK) {
+        std::memcpy(t->h_tokens, p.tokens.data(), (size_t)nK * sizeof(Token));
+        CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, (size_t)nK * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+        std::memcpy(t->h_tipList, p.tipList.data(), p.tipList.size() * sizeof(int32_t));
+        CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+      }
+    }
+    if (full && nT) {                                // remember it (device-to-device copies, stream-ordered)
+      int r2;
+      if (!cc.dTasks) {
+        if ((r2 = t->alloc(&cc.dTasks, (size_t)t->nInt)) || (r2 = t->alloc(&cc.dTokens, (size_t)2 * t->nInt)) ||
+            (r2 = t->alloc(&cc.dTips, (size_t)2 * t->nInt)))
+          return r2;
+      }
+      CUDA_TRY(cudaMemcpyAsync(cc.dTasks, t->d_tasks, (size_t)nT * sizeof(Task), cudaMemcpyDeviceToDevice, t->stream));
+      if (nK) {
+        CUDA_TRY(cudaMemcpyAsync(cc.dTokens, t->d_tokens, (size_t)nK * sizeof(Token), cudaMemcpyDeviceToDevice, t->stream));
+        CUDA_TRY(cudaMemcpyAsync(cc.dTips, t->d_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyDeviceToDevice, t->stream));
+      }
+      cc.kids = ht.kids; cc.within = ht.within; cc.cur = curBefore; cc.fuse = ht.fuseTips;
+      cc.meta.levelStart = p.levelStart;
+      cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps;
+      cc.meta.tasks.clear(); cc.metaTasks = nT;
+      cc.valid = true;
     }
   }
+  t->runPlanMeta = meta;
+  const int nTasks = hit ? cc.metaTasks : (int)p.tasks.size();
+  const long long storedReads = meta->storedReads, tipReads = meta->tipReads, fusedOps = meta->fusedOps;
+  t->st.last_host_plan_us = usSince(h0);
   if ((rc = runPlan(t))) return rc;
-  t->st.last_updates = (unsigned long long)(nTasks + p.fusedOps) * t->S * t->R;
+  t->st.last_updates = (unsigned long long)(nTasks + fusedOps) * t->S * t->R;
   t->st.updates += t->st.last_updates;
   t->st.evaluations++;
   // compulsory HBM traffic of this evaluation: stored partials written (32 B) and read (32 B per stored operand),
   // one mask byte per tip operand; exponents move only where something rescaled (not counted)
-  t->st.last_algorithmic_bytes = (unsigned long long)t->S * t->R * 32ull * (unsigned long long)(nTasks + p.storedReads) +
-                                 (unsigned long long)t->S * (unsigned long long)p.tipReads;
+  t->st.last_algorithmic_bytes = (unsigned long long)t->S * t->R * 32ull * (unsigned long long)(nTasks + storedReads) +
+                                 (unsigned long long)t->S * (unsigned long long)tipReads;
   t->st.last_stored_vertices = nTasks;
-  t->st.last_fused_vertices = (int)p.fusedOps;
+  t->st.last_fused_vertices = (int)fusedOps;
   const auto h1 = std::chrono::steady_clock::now();
   rc = rootStage(t, ll);
   t->st.last_host_submit_us = std::chrono::duration<double, std::micro>(h1 - h0).count() - t->st.last_host_plan_us;
@@ -929,6 +988,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
       CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, rp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
     }
     const dim3 grid(1, (unsigned)t->T, (unsigned)t->R);
+    t->runTokens = t->d_tokens; t->runTips = t->d_tipList; t->runFlip = 0;
     rc = launchPrune(t, grid, t->d_tasks, 1);
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());

@@ -60,6 +60,7 @@ struct HostTree {
   int fuseTips = 1;
   std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
   bool tipsValid = false;
+  bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
 
   bool isTip(int v) const { return v < numTips; }
   int internalIndex(int v) const { return v - numTips; }
@@ -141,7 +142,7 @@ struct HostTree {
 
   void negateAllUpdateFlags() { std::fill(touched.begin(), touched.end(), 0); }          // AugTree.cpp:368-374
   void invalidateSolution(int v) { for (; v != -1; v = parent[v]) solved[v] = 0; }        // IntermediateNode.cpp:5-13
-  void invalidateAll() { for (int v = numTips; v < numVerts; v++) solved[v] = 0; }        // AugTree.cpp:136-142
+  void invalidateAll() { for (int v = numTips; v < numVerts; v++) solved[v] = 0; allInvalid = true; }   // AugTree.cpp:136-142
   void invalidateBetween() {                                                              // AugTree.cpp:273-287
     std::vector<int> stack(1, root());
     while (!stack.empty()) {
@@ -314,6 +315,7 @@ struct HostTree {
   }
 
   void plan(Plan& p) {
+    allInvalid = false;
     p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
     p.storedReads = p.tipReads = p.fusedOps = 0;
     p.uses[0] = p.uses[1] = false;

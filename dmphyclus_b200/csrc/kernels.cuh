@@ -162,7 +162,9 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
 template <bool EXACT>
 __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restrict__ tasks, int nTasks,
                                                  const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                 int* violation) {
+                                                 int* violation, int flip) {
+  // `flip` (0/1) is XORed into every slot bit of the tasks and tokens: a cached full-evaluation plan is replayed with
+  // all slots toggled instead of being rebuilt and uploaded again
   // one thread = SPT sites (tid, tid + PT, ...) of one rate: what is uniform across the block — token decoding, the
   // P matrix elements, addresses — is paid once per SPT updates
   __shared__ __align__(16) double s_lut[2 * 64];                 // [set][mask][4] of this block's rate
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
   for (int ti = blockIdx.x; ti < nTasks; ti += gridDim.x) {
     const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
     const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
-    const int fl = tk0.w;
+    const int fl = tk0.w ^ (flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0);
     const int set = (fl & TF_WITHIN) ? 1 : 0;
     const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
     const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
           }
         }
         if (EXACT) {
-          const int tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+          const int tslot = ((t4.x & TOK_SLOT) ? 1 : 0) ^ flip;
           bool resc = false;
 #pragma unroll
           for (int u = 0; u < SPT; u++) resc |= e[u] != 0.0f;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
       // bookkeeping of the fused vertices, one token per thread: current slot, and (fast mode) "nothing rescaled"
       const int4 t4 = s_tok[tid];
       if ((t4.x & 7) != OP_SPILL) {
-        const int tslot = (t4.x & TOK_SLOT) ? 1 : 0;
+        const int tslot = ((t4.x & TOK_SLOT) ? 1 : 0) ^ flip;
         if (!EXACT) v.flagOf(tslot)[flagRow + t4.w] = 0;
         if (tile == 0 && r == 0) v.cur[t4.w] = (uint8_t)tslot;
       }
