@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
     ap.add_argument("--sweep-rates", type=int, default=1, help="rate categories of the proposal sweep (with 3, config 4's committed state has rescaled sites and the batch falls back to one-by-one evaluation)")
     ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
+    ap.add_argument("--strong", action="store_true", help="N > 1: split the workload's sites across the ranks (strong scaling) instead of giving every rank the full site count")
     ap.add_argument("--seed", type=int, default=2001)
     return ap.parse_args()
 
@@ -95,6 +96,8 @@ def algorithmic_bytes(n, s, r):
 def make_problem(args, world):
     from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
     n, s, k, r = CONFIGS[args.workload]
+    if args.strong:      # strong scaling: the workload's own site count, sharded
+        return Problem(load_packaged(), n, s, k, r, args.data, args.tree, seed=args.seed), (n, s // world, k, r)
     # weak scaling: every rank holds `s` sites of an alignment of s * world sites
     return Problem(load_packaged(), n, s * world, k, r, args.data, args.tree, seed=args.seed), (n, s, k, r)
 
@@ -202,10 +205,15 @@ def run_reference(args, rank, world):
     emit(json.dumps(out))
 
 
+def CONFIGS_SITES(args):
+    from dmphyclus_b200.workloads import CONFIGS
+    return CONFIGS[args.workload][1]
+
+
 def config_dict(args, n, s, k, r, world):
     return {"workload": f"{args.workload}: logLikFromClusInd-style full evaluation, {n} seqs x {s} sites per GPU, "
                         f"{k} clusters, {r} rate categories",
-            "tips": n, "sites_per_gpu": s, "sites_total": s * world, "clusters": k, "rate_categories": r,
+            "tips": n, "sites_per_gpu": s, "sites_total": (CONFIGS_SITES(args) if args.strong else s * world), "clusters": k, "rate_categories": r,
             "alignment": args.data, "tree": args.tree, "seed": args.seed,
             "matrices": "packaged withinClusTransProbs[[5]] / betweenClusTransProbs[[5]]",
             "l2": "inputs larger than L2 (partials of one evaluation >> 126 MB); no explicit flush",
@@ -225,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     p, (n, s, k, r) = make_problem(args, world)
-    S_total = s * world
+    S_total = p.S
     W, B = p.W[p.w_idx - 1], p.B[p.b_idx - 1]
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -345,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": config_dict(args, n, s, k, r, world),
                "clocks": sampler.summary(),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,

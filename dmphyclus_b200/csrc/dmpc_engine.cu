@@ -559,7 +559,7 @@ int checkHandle(dmpc_tree* t) {
 extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
-  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 8; o->fuse_exact = 0; o->comm = nullptr;
+  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 15; o->fuse_exact = 0; o->comm = nullptr;
 }
 
 const char* dmpc_last_error(void) { return g_err.c_str(); }

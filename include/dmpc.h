@@ -51,7 +51,7 @@ typedef struct dmpc_options {
   int site_begin;    /* this handle evaluates global sites [site_begin, site_begin + numLoci) of an alignment of */
   int sites_total;   /* sites_total sites (multi-GPU site sharding); single GPU: 0 and numLoci */
   int fuse_tips;     /* small-clade fusion: vertices with at most this many tips below them are never written to
-                        HBM but recomputed from the tip masks by their nearest stored ancestor (default 8, max 15;
+                        HBM but recomputed from the tip masks by their nearest stored ancestor (default and max 15;
                         <= 1 stores every vertex).  Results do not depend on it */
   int fuse_exact;    /* 1: fused clades keep full per-vertex rescale bookkeeping from the start (the engine switches
                         to it by itself the first time a fused clade could have rescaled) */
