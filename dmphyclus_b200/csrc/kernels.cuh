@@ -909,17 +909,27 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
     if (wid > 0) {
       if (ch + 1 < nchunks) stage(ch + 1, tid - 32, nth - 32, b ^ 1);
     } else if (tid == 0) {
-      const float4* const bufb = buf0 + (size_t)b * cap * V;
-      const unsigned char* const endb = end0 + (size_t)b * (cap / 4);
+      // The walker: ONE thread, because the chain is sequential by definition.  A lone warp retires an instruction
+      // every few cycles, so the loop is kept to the loads (explicit shared-space addresses, one running pointer),
+      // the RC additions per row and one flag test per group of 4 rows; two groups per trip so that the next group
+      // is already on its way from shared memory while the current one is added.
+      unsigned rowAddr = (unsigned)__cvta_generic_to_shared(buf0 + (size_t)b * cap * V);
+      unsigned endAddr = (unsigned)__cvta_generic_to_shared(end0 + (size_t)b * (cap / 4));
       int outIdx = meta0[2 * b];
-      const int nrows = meta0[2 * b + 1];
+      const int ngroups = meta0[2 * b + 1] >> 2;
+      float* co = rv.cout + (size_t)outIdx * RP;
+      float* mo = rv.mxo + outIdx;
       float4 x[4][V], y[4][V];
+      unsigned fx, fy;
+      auto loadGroup = [&](float4 (&g)[4][V], unsigned& f, unsigned ra, unsigned ea) {
 #pragma unroll
-      for (int j = 0; j < 4; j++)
+        for (int j = 0; j < 4; j++)
 #pragma unroll
-        for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)j * V + u];
-      unsigned fx = endb[0], fy;
-      // two groups per trip: while one group is being added, the next one is already on its way from shared memory
+          for (int u = 0; u < V; u++)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[j][u].x), "=f"(g[j][u].y), "=f"(g[j][u].z), "=f"(g[j][u].w)
+                         : "r"(ra + (unsigned)((j * V + u) * 16)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(ea));
+      };
       auto addGroup = [&](const float4 (&g)[4][V], unsigned flag) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -934,26 +944,20 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
           for (int r = 1; r < RC; r++) m = fmaxf(m, c[r]);
 #pragma unroll
           for (int r = 0; r < RC; r++) c[r] = __fsub_rn(c[r], m);
-          float* co = rv.cout + (size_t)outIdx * RP;
 #pragma unroll
           for (int r = 0; r < RC; r++) co[r] = c[r];
-          rv.mxo[outIdx] = m;
-          outIdx++;
+          *mo = m;
+          co += RP; mo++;
         }
       };
-      for (int q = 0; q < nrows; q += 8) {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-          for (int u = 0; u < V; u++) y[j][u] = bufb[(size_t)(q + 4 + j) * V + u];
-        fy = endb[(q >> 2) + 1];
+      constexpr unsigned GB = 4 * V * 16;         // bytes of one group of rows
+      if (ngroups > 0) loadGroup(x, fx, rowAddr, endAddr);
+      for (int g = 0; g < ngroups; g += 2) {
+        loadGroup(y, fy, rowAddr + GB, endAddr + 1);      // the spare group behind the last one makes this safe
         addGroup(x, fx);
-        if (q + 4 >= nrows) break;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-          for (int u = 0; u < V; u++) x[j][u] = bufb[(size_t)(q + 8 + j) * V + u];
-        fx = endb[(q >> 2) + 2];
+        if (g + 1 >= ngroups) break;
+        rowAddr += 2 * GB; endAddr += 2;
+        loadGroup(x, fx, rowAddr, endAddr);
         addGroup(y, fy);
       }
     }
