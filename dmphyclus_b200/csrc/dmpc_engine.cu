@@ -3,7 +3,7 @@
 // Each entry point mirrors one Rcpp-exported function of the reference
 // (/root/reference/src/clusterFunArmadillo.cpp:36-332): same call sequence
 // (NegateAllUpdateFlags -> mutate topology/flags -> ComputeLoglik), but the state lives in flat host arrays
-// (host_tree.hpp) plus dense HBM buffers, and ComputeLoglik is a level schedule of CUDA launches
+// (host_tree.hpp) plus dense HBM buffers, and ComputeLoglik is a level plan of CUDA launches
 // (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
 #include "../../include/dmpc.h"
 

@@ -1,17 +1,16 @@
 // kernels.cuh — sm_100a CUDA kernels of the Felsenstein-pruning likelihood engine.
 //
-// Data layout in HBM (per handle; SURVEY.md §8d "site-major structure-of-arrays"):
-//   tipmask  u8     [N][Sp]                 4-bit state masks, Sp = numLoci padded to a multiple of 128
-//   part[s]  f64x4  [N-1][R][Sp]            conditional-likelihood 4-vectors, one 32-byte element per
-//                                           (internal vertex, rate, site); two slots s = 0,1 so that a
-//                                           rejected proposal rolls back by flipping a per-vertex slot bit
-//   expo[s]  f32    [N-1][R][Sp]            per-vertex rescale exponents (IntermediateNode.cpp:63: a FLOAT)
-//   flag[s]  u8     [R][T][N]               1 when any site of the 128-site tile rescaled at that vertex for that rate;
-//                                           expo tiles whose flag is 0 are never written nor read
-// One thread owns one site of one vertex for all R rates: its child loads are 256-bit (LDG.E.256), consecutive
-// threads touch consecutive 32-byte elements, so every warp request is 1 KB fully coalesced.  Per update the
-// compulsory traffic is 2 x 32 B read (internal children; 1 B for a tip) + 32 B written: 68-96 B, against
-// ~70 fp64 operations — HBM-bound, no tensor cores (a 4x4 mat-vec has nothing to tile).
+// Data layout in HBM (per handle):
+//   tipmask  u8     [N][Sp]                 4-bit state masks, Sp = numLoci padded to a multiple of 256
+//   part[s]  f64x4  [N][R][Sp]              conditional-likelihood 4-vectors, one 32-byte element per (internal
+//                                           vertex, rate, site); row N-1 is scratch.  Two slots s = 0,1 so that a
+//                                           rejected proposal rolls back by flipping a per-vertex slot bit.  Rows
+//                                           of FUSED vertices (small clades, see k_prune) are never written.
+//   expo[s]  f32    [N][R][Sp]              per-vertex rescale exponents (IntermediateNode.cpp:63: a FLOAT)
+//   flag[s]  u8     [R][T][N]               1 when any site of the 256-site tile rescaled at that vertex for that
+//                                           rate; expo tiles whose flag is 0 are never written nor read
+// Consecutive threads touch consecutive 32-byte elements (LDG.E.256 / STG.E.256), so every warp request is 1 KB
+// fully coalesced.  There is no GEMM shape here (a 4x4 mat-vec per thread): no tensor cores, no TMA tiles.
 //
 // Arithmetic follows the reference's evaluation order with separately rounded products and sums
 // (__dmul_rn/__dadd_rn: never contracted into FMAs), so partials are bit-identical to the CPU oracle.
@@ -35,7 +34,7 @@ struct DevView {
   float* expo[2];
   uint8_t* flag[2];
   const uint8_t* tipmask;
-  uint8_t* cur;                 // [N-1] slot of each internal vertex, as seen by the root reduction
+  uint8_t* cur;                 // [N] slot of each internal vertex, as seen by the root reduction
   const double* lut;            // [2][R][16][4]: P * indicator(mask) for every 4-bit mask (tips)
   int N, S, Sp, R, T, nInt;      // nInt = rows of the per-vertex arrays: the N-1 internal vertices + 1 scratch row
   int nReal;                    // N-1: what the root reduction scans
@@ -778,8 +777,10 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
 // per-site values depend on the site order through a sequential chain of fp32 additions whose rounding has to
 // be reproduced bit for bit.  One block: every thread compacts the active sites (those
 // that rescaled anywhere), then thread 0 walks their exponent rows as ONE flat stream while the other warps
-// stage the next chunk of rows (and the end-of-site markers) in shared memory.  Categories beyond R ride along
-// as -inf so that the hot loop needs no guards.  When no site rescaled the kernel returns at once.
+// stage the next chunk of rows (and the end-of-site markers) in shared memory.  RC = number of rate categories
+// (compile time), RP = floats per row (4 or 8).  When no site rescaled the kernel returns at once.  In a
+// site-sharded run the vector entering this shard comes from an earlier rank's mailbox and the vector leaving it is
+// handed to the later ranks (CommView).
 template <int RP, int RC>
 __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   extern __shared__ float4 s_dyn[];

@@ -214,14 +214,26 @@ def build_ref() -> str | None:
     return lib if os.path.exists(lib) else None
 
 
+def build_shimtest() -> str | None:
+    """oracle/_ref/libshimtest.so: rpkg/src/clusterFunArmadillo.cpp (the drop-in Rcpp shim) compiled against the Rcpp
+    stand-in and linked to libdmpc.so, behind the same harness as the reference TUs.  Needs libdmpc.so built."""
+    lib = os.path.join(HERE, "_ref", "libshimtest.so")
+    try:
+        subprocess.check_call(["make", "-C", HERE, "shimtest"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        pass
+    return lib if os.path.exists(lib) else None
+
+
 class Reference:
     """The reference's own translation units (compiled against oracle/shim) behind the same
     interface as `Oracle`.  Single-threaded, memoised through its `std::map` dictionary."""
 
     name = "reference"
 
-    def __init__(self):
-        path = build_ref()
+    def __init__(self, path: str | None = None):
+        if path is None:
+            path = build_ref()
         if path is None:
             raise FileNotFoundError("oracle/_ref/libref.so is absent and /root/reference is not available to build it")
         self.lib = C.CDLL(path)

@@ -7,11 +7,23 @@
 // arrays, calls the reference's Rcpp-exported functions (clusterFunArmadillo.cpp:36-332) and reads
 // the results back.  It is the second, independent oracle used to pin oracle/dmpc_oracle.cpp
 // (tests/test_oracle_vs_ref.py) and the `cpu_baseline.kind == "reference"` arm of bench.py.
+// Built twice (oracle/Makefile):
+//   _ref/libref.so       with the reference's own translation units (default);
+//   _ref/libshimtest.so  -DHARNESS_DMPC: with rpkg/src/clusterFunArmadillo.cpp — this repository's drop-in replacement
+//                        of the reference's entry-point file — linked against libdmpc.so, so that the R-facing shim is
+//                        exercised end to end (fake R objects -> Rcpp-style marshalling -> C-ABI -> GPU) without R.
 #include <RcppArmadillo.h>
 #include <RcppGSL.h>
+#include <cstdlib>
 #include <cstring>
 
+#ifdef HARNESS_DMPC
+#include "dmpc.h"
+#else
 #include "AugTree.h"
+#endif
+
+namespace Rcpp { SEXPREC g_shim_nil(SEXPREC::NIL); }
 
 using namespace Rcpp;
 using namespace arma;
@@ -52,11 +64,16 @@ SEXP matList(const double* m, int R) {   // R column-major 4x4 matrices
   for (int r = 0; r < R; r++) { SEXP x = realVec(m + 16 * r, 16); x->nrow = 4; x->ncol = 4; l->list.push_back(x); }
   return l;
 }
+#ifdef HARNESS_DMPC
+typedef dmpc_tree TreeT;
+#else
+typedef AugTree TreeT;
+#endif
 struct Handle {
-  AugTree* tree;
-  SEXPREC ext;   // persistent external-pointer record handed to the reference on every call
-  int numRates;
-  Handle() : tree(0), ext(SEXPREC::EXTPTR), numRates(0) {}
+  TreeT* tree;
+  SEXPREC ext;   // persistent external-pointer record handed to the entry points on every call
+  int numRates, numTips, numLoci;
+  Handle() : tree(0), ext(SEXPREC::EXTPTR), numRates(0), numTips(0), numLoci(0) {}
 };
 void copyEdge(SEXP e, int* out) { for (size_t i = 0; i < e->real.size(); i++) out[i] = (int)e->real[i]; }
 std::string g_err;
@@ -114,11 +131,20 @@ void* ref_loglik_create(const int* edge, int nEdgeRows, const double* clusterMRC
       }
       al->list.push_back(row);
     }
+#ifdef HARNESS_DMPC
+    if (getenv("SHIM_FAST_MASKS")) {     // what getConvertedAlignment of the drop-in shim attaches: packed masks, column-major
+      SEXP raw = shim::alloc(SEXPREC::RAW);
+      raw->raw.resize((size_t)numTips * numLoci);
+      for (int i = 0; i < numTips; i++)
+        for (int j = 0; j < numLoci; j++) raw->raw[(size_t)i + (size_t)j * numTips] = tipmask[(size_t)i * numLoci + j];
+      al->attrs["dmpc_masks"] = raw;
+    }
+#endif
     List res = logLikCpp(e, m, pi, w, b, 1, List(al), (uint)numTips, (uint)numLoci, (uint)withinIdx, (uint)betweenIdx);
     Handle* h = new Handle;
-    h->tree = static_cast<AugTree*>(res[1]->ptr);
+    h->tree = static_cast<TreeT*>(res[1]->ptr);
     h->ext.ptr = h->tree;
-    h->numRates = numRates;
+    h->numRates = numRates; h->numTips = numTips; h->numLoci = numLoci;
     *logLik = res[0]->real[0];
     return h;
   } catch (std::exception& ex) { g_err = ex.what(); return 0; }
@@ -183,7 +209,9 @@ void ref_restore(void* hv, const int* edge, int nEdgeRows, int withinIdx, int be
 void ref_final_deallocate(void* hv) {
   Handle* h = (Handle*)hv;
   finalDeallocate(&h->ext);
+#ifndef HARNESS_DMPC
   delete h->tree;   // the reference leaks the AugTree itself (clusterFunArmadillo.cpp:288-294); the harness does not
+#endif
   delete h;
 }
 
@@ -197,6 +225,15 @@ void ref_check_and_cull_map(void* hv, unsigned allowed, float cullProportion, co
   checkAndCullMap(&h->ext, allowed, cullProportion, w, b, pi);
 }
 
+#ifdef HARNESS_DMPC
+// ---- introspection through the C-ABI
+double ref_loglik(void*) { return 0.0; }
+long ref_dictionary_size(void*) { return 0; }
+void ref_get_partial(void* hv, int node, double* sol, float* expo) { dmpc_get_partial(((Handle*)hv)->tree, node, sol, expo); }
+void ref_get_topology(void* hv, int* parent, int* child0, int* child1, int* within) {
+  dmpc_get_topology(((Handle*)hv)->tree, parent, child0, child1, within);
+}
+#else
 // ---- introspection for bit-level comparison with oracle/dmpc_oracle.cpp
 double ref_loglik(void* hv) { return ((Handle*)hv)->tree->GetLoglik(); }
 long ref_dictionary_size(void* hv) { return (long)((Handle*)hv)->tree->GetSolutionDictionary()->size(); }
@@ -224,5 +261,7 @@ void ref_get_topology(void* hv, int* parent, int* child0, int* child1, int* with
     within[i] = n->GetWithinParentBranch() ? 1 : 0;
   }
 }
+
+#endif
 
 }  // extern "C"

@@ -13,12 +13,14 @@
 #include <vector>
 
 struct SEXPREC {
-  enum Kind { NIL, REAL, INT, STR, LIST, EXTPTR } kind;
+  enum Kind { NIL, REAL, INT, STR, LIST, EXTPTR, RAW } kind;
   std::vector<double> real;
   std::vector<int> integer;
   std::vector<std::string> str;
   std::vector<SEXPREC*> list;
   std::vector<std::string> names;
+  std::vector<unsigned char> raw;
+  std::map<std::string, SEXPREC*> attrs;
   int nrow, ncol;
   void* ptr;
   explicit SEXPREC(Kind k) : kind(k), nrow(-1), ncol(-1), ptr(0) {}
@@ -45,10 +47,37 @@ class exception : public std::exception {
   virtual const char* what() const throw() { return msg_.c_str(); }
 };
 
+class NumericVector;
+class IntegerVector;
+class List;
+class RawVector;
+inline SEXP wrap(SEXP s);
+inline SEXP wrap(const NumericVector& v);
+inline SEXP wrap(const IntegerVector& v);
+inline SEXP wrap(const List& l);
+inline SEXP wrap(const RawVector& v);
+
+// obj.attr("name"): readable (missing -> NULL object) and assignable
+extern SEXPREC g_shim_nil;
+class AttrProxy {
+  SEXP obj_;
+  std::string name_;
+ public:
+  AttrProxy(SEXP o, const std::string& n) : obj_(o), name_(n) {}
+  operator SEXP() const { std::map<std::string, SEXP>::const_iterator it = obj_->attrs.find(name_); return it == obj_->attrs.end() ? &g_shim_nil : it->second; }
+  template <class T> AttrProxy& operator=(const T& v) { obj_->attrs[name_] = wrap(v); return *this; }
+};
+
 class NumericVector {
  public:
   SEXP s;
   NumericVector(SEXP x) : s(x) {}
+  NumericVector(int n) : s(shim::alloc(SEXPREC::REAL)) { s->real.assign(n, 0.0); }
+  template <class It> NumericVector(It b, It e) : s(shim::alloc(SEXPREC::REAL)) { for (; b != e; ++b) s->real.push_back((double)*b); }
+  template <class A, class B, class C, class D> static NumericVector create(A a, B b, C c, D d) {
+    NumericVector v(4); v.s->real[0] = (double)a; v.s->real[1] = (double)b; v.s->real[2] = (double)c; v.s->real[3] = (double)d; return v;
+  }
+  AttrProxy attr(const std::string& n) { return AttrProxy(s, n); }
   operator SEXP() const { return s; }
   int size() const { return (int)s->real.size(); }
   double& operator[](int i) { return s->real[i]; }
@@ -56,7 +85,12 @@ class NumericVector {
 class IntegerVector {
  public:
   SEXP s;
-  IntegerVector(SEXP x) : s(x) {}
+  IntegerVector(SEXP x) : s(x) {
+    if (x->kind == SEXPREC::REAL && x->integer.empty()) for (size_t i = 0; i < x->real.size(); i++) x->integer.push_back((int)x->real[i]);
+  }
+  template <class A, class B> static IntegerVector create(A a, B b) {
+    SEXP x = shim::alloc(SEXPREC::INT); x->integer.push_back((int)a); x->integer.push_back((int)b); return IntegerVector(x);
+  }
   operator SEXP() const { return s; }
   int size() const { return (int)s->integer.size(); }
   int& operator[](int i) { return s->integer[i]; }
@@ -92,6 +126,7 @@ class XPtr {
 
 // ---- wrap
 inline SEXP wrap(SEXP s) { return s; }
+inline SEXP wrap(int x) { SEXP s = shim::alloc(SEXPREC::INT); s->integer.push_back(x); return s; }
 inline SEXP wrap(double x) { SEXP s = shim::alloc(SEXPREC::REAL); s->real.push_back(x); return s; }
 template <class T> SEXP wrap(const XPtr<T>& p) { return static_cast<SEXP>(p); }
 template <class T>
@@ -117,19 +152,54 @@ class Named {
   template <class T> NamedValue operator=(const T& v) const { NamedValue nv; nv.name = n_; nv.val = wrap(v); return nv; }
 };
 
+class ListProxy {    // element of a list: readable as an object, assignable
+  SEXP l_;
+  int i_;
+ public:
+  ListProxy(SEXP l, int i) : l_(l), i_(i) {}
+  operator SEXP() const { return l_->list[i_]; }
+  SEXP operator->() const { return l_->list[i_]; }
+  template <class T> ListProxy& operator=(const T& v) { l_->list[i_] = wrap(v); return *this; }
+};
+
 class List {
  public:
   SEXP s;
   List() : s(shim::alloc(SEXPREC::LIST)) {}
   List(SEXP x) : s(x) {}
+  List(int n) : s(shim::alloc(SEXPREC::LIST)) { s->list.assign(n, &g_shim_nil); }
   operator SEXP() const { return s; }
   int size() const { return (int)s->list.size(); }
-  SEXP operator[](int i) const { return s->list[i]; }
+  ListProxy operator[](int i) const { return ListProxy(s, i); }
+  AttrProxy attr(const std::string& n) { return AttrProxy(s, n); }
   void push(const NamedValue& nv) { s->list.push_back(nv.val); s->names.push_back(nv.name); }
   static List create(const NamedValue& a) { List l; l.push(a); return l; }
   static List create(const NamedValue& a, const NamedValue& b) { List l; l.push(a); l.push(b); return l; }
   static List create(const NamedValue& a, const NamedValue& b, const NamedValue& c) { List l; l.push(a); l.push(b); l.push(c); return l; }
 };
+
+class RObject {
+  SEXP s_;
+ public:
+  RObject(SEXP s) : s_(s) {}
+  bool isNULL() const { return s_ == 0 || s_->kind == SEXPREC::NIL; }
+  operator SEXP() const { return s_; }
+};
+
+class RawVector {
+ public:
+  SEXP s;
+  explicit RawVector(size_t n) : s(shim::alloc(SEXPREC::RAW)) { s->raw.assign(n, 0); }
+  RawVector(SEXP x) : s(x) {}
+  unsigned char& operator[](size_t i) { return s->raw[i]; }
+  AttrProxy attr(const std::string& n) { return AttrProxy(s, n); }
+  operator SEXP() const { return s; }
+};
+
+inline SEXP wrap(const NumericVector& v) { return v.s; }
+inline SEXP wrap(const IntegerVector& v) { return v.s; }
+inline SEXP wrap(const List& l) { return l.s; }
+inline SEXP wrap(const RawVector& v) { return v.s; }
 
 // ---- as<>
 template <class T> struct Exporter;

@@ -77,7 +77,7 @@ List logLikCpp(IntegerMatrix& edgeMat, NumericVector& clusterMRCAs, NumericVecto
   // alignmentBin is getConvertedAlignment's value: list(numTips) of list(numLoci) of 0/1 vectors; the packed masks
   // ride along as attribute "dmpc_masks" (raw numTips x numLoci, column-major) when it came from this library.
   std::vector<uint8_t> masks((size_t)numTips * numLoci);
-  RObject packed = alignmentBin.attr("dmpc_masks");
+  RObject packed(alignmentBin.attr("dmpc_masks"));
   if (!packed.isNULL()) {
     RawVector raw(packed);
     for (uint i = 0; i < numTips; i++)

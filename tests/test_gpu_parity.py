@@ -333,3 +333,23 @@ def test_proposal_batch_equals_one_by_one(packaged, oracle, n, S, k, R, kind, fu
     got2, _ = eng.evalProposals(hg, W, B, p.pi, props[:3])
     assert list(got2) == one_by_one[:3]
     eng.finalDeallocate(hg); oracle.finalDeallocate(ho)
+
+
+# ---------------------------------------------------------------------------------------------- the R-facing shim
+@pytest.mark.parametrize("fast_masks", [False, True])
+def test_rcpp_shim_end_to_end(packaged, oracle, fast_masks, monkeypatch):
+    """rpkg/src/clusterFunArmadillo.cpp — the file a maintainer drops into the R package — compiled against the Rcpp
+    stand-in (there is no R here) and driven through fake R objects: list-of-lists alignment, column-major matrices,
+    1-based ids, external pointer, edge matrix returned as a numeric matrix.  Same scripted sequence as the oracle."""
+    from oracle.oracle import Reference, build_shimtest
+    path = build_shimtest()
+    if path is None:
+        pytest.skip("libshimtest.so not built")
+    if fast_masks:
+        monkeypatch.setenv("SHIM_FAST_MASKS", "1")     # the packed-mask attribute getConvertedAlignment attaches
+    else:
+        monkeypatch.delenv("SHIM_FAST_MASKS", raising=False)
+    shim = Reference(path)
+    for n, S, k, R, kind in ((40, 70, 5, 3, "evolved"), (500, 60, 6, 3, "iid")):
+        p = Problem(packaged, n, S, k, R, kind, seed=n)
+        compare_to_golden(run_script(shim, p), run_script(oracle, p), ll_tol=TOL, exact_partials=True)
