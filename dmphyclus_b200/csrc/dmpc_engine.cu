@@ -966,6 +966,71 @@ int dmpc_timer_end(dmpc_tree* t, double* msOut) {
   return DMPC_OK;
 }
 
+int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
+                        int fuseTips, int* out) {
+  if (!edge || !out || (nClusterMRCAs > 0 && !clusterMRCAs)) return fail(DMPC_ERR_ARG, "null pointer");
+  HostTree ht;
+  if (!ht.build(edge, nEdgeRows, numTips)) return fail(DMPC_ERR_ARG, ht.err);
+  ht.associate(clusterMRCAs, nClusterMRCAs);
+  ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
+  HostTree::Plan p;
+  ht.plan(p);
+  const int N = numTips, nInt = N - 1;
+  auto bad = [&](const std::string& m) { return fail(DMPC_ERR_STATE, "plan self-check: " + m); };
+  std::vector<int> computedAt(nInt, -1);          // level at which each internal vertex is computed
+  const int nLevels = (int)p.levelStart.size() - 1;
+  int maxDepth = 0, maxTips = 0, fusedCount = 0;
+  for (int l = 0; l < nLevels; l++)
+    for (int i = p.levelStart[l]; i < p.levelStart[l + 1]; i++) {
+      const Task& k = p.tasks[i];
+      if (k.out < 0 || k.out >= nInt) return bad("task output out of range");
+      if (computedAt[k.out] != -1) return bad("vertex computed twice");
+      const int n0 = k.ntok & 0xffff, n1 = (k.ntok >> 16) & 0xffff;
+      if (((k.flags & TF_C0FUSED) != 0) != (n0 > 0) || ((k.flags & TF_C1FUSED) != 0) != (n1 > 0)) return bad("fused flag without program");
+      if (k.prog < 0 || k.prog + n0 + n1 > (int)p.tokens.size()) return bad("token range");
+      if (k.tipOff < 0 || k.tipOff + k.nTips > (int)p.tipList.size()) return bad("tip list range");
+      if (k.nTips > 2 * FUSE_MAX_TIPS || n0 + n1 > 3 * FUSE_MAX_TIPS + 4) return bad("task exceeds the kernel's shared-memory staging");
+      maxTips = std::max(maxTips, k.nTips);
+      for (int c = 0; c < 2; c++) {               // stored operands must have been computed at a lower level
+        const int idx = c ? k.c1 : k.c0;
+        const bool tip = k.flags & (c ? TF_C1TIP : TF_C0TIP), fus = k.flags & (c ? TF_C1FUSED : TF_C0FUSED);
+        if (tip) { if (idx < 0 || idx >= N) return bad("tip operand out of range"); continue; }
+        if (idx < 0 || idx >= nInt) return bad("operand out of range");
+        if (!fus && (computedAt[idx] < 0 || computedAt[idx] >= l)) return bad("stored operand not computed at a lower level");
+      }
+      // run the programs symbolically: stack discipline, tips under each clade, every token's vertex new
+      int off = k.prog;
+      for (int c = 0; c < 2; c++) {
+        const int n = c ? n1 : n0;
+        if (!n) continue;
+        int sp = c && n0 ? 1 : 0, tipsSeen = 0;
+        bool haveReg = false;
+        for (int j = off; j < off + n; j++) {
+          const Token& t = p.tokens[j];
+          const int op = t.op & 7;
+          if (op == OP_SPILL) { if (!haveReg) return bad("spill without a value"); sp++; haveReg = false; maxDepth = std::max(maxDepth, sp); continue; }
+          if (t.vertex < 0 || t.vertex >= nInt || computedAt[t.vertex] != -1) return bad("fused vertex out of range or computed twice");
+          if (op == OP_CHERRY) { if (t.a < 0 || t.a >= k.nTips || t.b < 0 || t.b >= k.nTips) return bad("cherry tip index"); tipsSeen += 2; }
+          else if (op == OP_REGTIP) { if (!haveReg || t.b < 0 || t.b >= k.nTips) return bad("reg-tip without a value"); tipsSeen += 1; }
+          else if (op == OP_SLOTREG) { if (!haveReg || sp <= (c && n0 ? 1 : 0)) return bad("slot-reg without a spilled value"); sp--; }
+          else return bad("unknown opcode");
+          haveReg = true;
+          computedAt[t.vertex] = l;
+          fusedCount++;
+        }
+        if (sp != (c && n0 ? 1 : 0) || !haveReg) return bad("unbalanced program");
+        if (tipsSeen > ht.fuseTips) return bad("fused clade larger than the threshold");
+        off += n;
+      }
+      if (maxDepth > FUSE_DEPTH) return bad("stack deeper than FUSE_DEPTH");
+      computedAt[k.out] = l;
+    }
+  for (int v = 0; v < nInt; v++) if (computedAt[v] < 0) return bad("vertex never computed");
+  if (computedAt[0] != nLevels - 1) return bad("the root is not in the last level");
+  out[0] = (int)p.tasks.size(); out[1] = fusedCount; out[2] = nLevels; out[3] = (int)p.tokens.size(); out[4] = maxDepth; out[5] = maxTips;
+  return DMPC_OK;
+}
+
 int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   int rc;
   if ((rc = checkHandle(t))) return rc;

@@ -66,6 +66,7 @@ ABI = {
     "dmpc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dmpc_timer_begin": (C.c_int, [_P]),
     "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
+    "dmpc_plan_selfcheck": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "dmpc_get_partial": (C.c_int, [_P, C.c_int, _dbl_p, _f32_p]),
     "dmpc_get_topology": (C.c_int, [_P, _i32_p, _i32_p, _i32_p, _i32_p]),
     "dmpc_get_site_logliks": (C.c_int, [_P, _dbl_p]),

@@ -158,6 +158,15 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 int dmpc_timer_begin(dmpc_tree* t);
 int dmpc_timer_end(dmpc_tree* t, double* msOut);
 
+/* Host-only self-check of the plan builder (needs no GPU; used by the CPU test-suite): builds the topology, applies the
+ * cluster flags, plans a full evaluation with the given fusion threshold and verifies the invariants the kernels rely
+ * on — every internal vertex computed exactly once (as a stored task or a fused token), children before parents across
+ * levels, fused clades no larger than the threshold, stack depth within FUSE_DEPTH, tip lists and token ranges
+ * consistent.  out[0..5] = stored vertices, fused vertices, levels, tokens, max stack depth, max tips of a task's programs.
+ * Returns DMPC_OK or DMPC_ERR_STATE with the violated invariant in dmpc_last_error(). */
+int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
+                        int fuseTips, int* out);
+
 /* Introspection for parity tests: the committed partial of a vertex (0-based id >= numTips) as
  * sol [numLoci][R][4] and expo [numLoci][R] (the oracle's layout), and the topology/flags. */
 int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo);

@@ -79,3 +79,31 @@ def test_workload_shapes_match_baseline():
     from dmphyclus_b200.workloads import CONFIGS
     assert CONFIGS["config2"] == (1000, 10000, 20, 3) and CONFIGS["config3"] == (10000, 30000, 100, 3)
     assert CONFIGS["config4"][:2] == (5000, 5000) and CONFIGS["config5"][:2] == (100000, 1500)
+
+
+@pytest.mark.parametrize("shape", ["random", "balanced", "caterpillar"])
+@pytest.mark.parametrize("fuse", [1, 2, 3, 4, 8, 15])
+def test_plan_builder_invariants(shape, fuse):
+    """The host-side plan (stored tasks per level + fused-clade token programs) over many trees: every vertex
+    computed exactly once, children before parents, stack depth and staging sizes within what k_prune assumes."""
+    import ctypes as C
+    from dmphyclus_b200 import build
+    from dmphyclus_b200.engine import load_library
+    build.build()
+    lib = load_library()
+    for n in (2, 3, 5, 16, 17, 64, 257, 1000):
+        rng = np.random.default_rng(n * 31 + fuse)
+        e = synth.random_tree(n, rng, shape)
+        mrcas, _ = synth.pick_clusters(e, n, min(5, n))
+        edge = np.ascontiguousarray(e.T, dtype=np.int32).ravel()
+        m = np.asarray(mrcas, np.float64)
+        out = (C.c_int * 6)()
+        rc = lib.dmpc_plan_selfcheck(edge.ctypes.data_as(C.POINTER(C.c_int32)), len(edge) // 2, n,
+                                     m.ctypes.data_as(C.POINTER(C.c_double)), len(m), fuse, out)
+        assert rc == 0, (n, shape, fuse, lib.dmpc_last_error().decode())
+        stored, fused, levels, tokens, depth, tips = list(out)
+        assert stored + fused == n - 1 and depth <= 3 and tips <= 30
+        if fuse == 1:
+            assert fused == 0 and tokens == 0
+        if shape == "caterpillar" and n > 40:
+            assert stored >= n - 1 - fuse          # only the bottom of a caterpillar can be fused
