@@ -341,8 +341,8 @@ def run_ours(args, rank, world, local_rank):
     d2h = 8 + 4 + 4
 
     extras = {}
-    if not args.no_extras and world == 1:
-        extras = extra_legs(args, eng, p, al, n, s, k, r)
+    if not args.no_extras:
+        extras = extra_legs(args, eng, p, al, n, s, k, r, world)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -374,11 +374,13 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def extra_legs(args, eng, p, al, n, s, k, r):
+def extra_legs(args, eng, p, al, n, s, k, r, world=1):
     """Secondary numbers (not the headline): the rescale-stress alignment and MCMC iterations/sec."""
     from dmphyclus_b200 import chain, synth
     from dmphyclus_b200.workloads import Problem, load_packaged
     out = {}
+    if world > 1:
+        return mcmc_leg(args, eng, p, al, out, "site-sharded: every rank runs the same driver in lock-step")
     other = "iid" if args.data == "evolved" else "evolved"
     q = Problem(load_packaged(), n, s, k, r, other, args.tree, seed=args.seed)
     alq = eng.getConvertedAlignment(list(synth.STATES), q.chars)
@@ -398,14 +400,20 @@ def extra_legs(args, eng, p, al, n, s, k, r):
                              "prune_ms_per_step": pr / steps, "rescale_rows": st["exponent_capacity"],
                              "logLik": res["logLik"]}
     eng.finalDeallocate(h)
-    # MCMC iterations/sec: the reference's move schedule (.performStepPhylo) driven from the host mirror
+    return mcmc_leg(args, eng, p, al, out, "single GPU")
+
+
+def mcmc_leg(args, eng, p, al, out, how):
+    """MCMC iterations/sec: the reference's move schedule (.performStepPhylo) driven from the host mirror."""
+    from dmphyclus_b200 import chain
     cs = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
                              scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
-    iters = 5
+    iters = 10
     t0 = time.perf_counter()
     _, calls = chain.run_chain(eng, al, p.edge, p.clus, 100.0, cs, iters, seed=args.seed)
     dt = time.perf_counter() - t0
     out["mcmc"] = {"iterations_per_sec": iters / dt, "iterations": iters, "likelihood_calls": calls,
+                   "likelihood_calls_per_sec": calls / dt, "how": how,
                    "note": "host driver = Python mirror of .performStepPhylo (R in a deployment); includes the initial logLikCpp"}
     return out
 

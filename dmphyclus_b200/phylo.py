@@ -18,9 +18,21 @@ class Phylo:
         n_nodes = int(self.edge.max())
         self.parent = np.zeros(n_nodes + 1, np.int64)
         self.parent[self.edge[:, 1]] = self.edge[:, 0]
-        self.children = [[] for _ in range(n_nodes + 1)]
-        for p, c in self.edge:          # row order = child order (AddChild appends)
-            self.children[p].append(int(c))
+        # children in edge-row order (AddChild appends); strictly bifurcating, so two per internal node.  Vectorised:
+        # the MCMC driver rebuilds this view for every move.
+        order = np.argsort(self.edge[:, 0], kind="stable")
+        par_sorted, kid_sorted = self.edge[order, 0], self.edge[order, 1]
+        ch = np.zeros((n_nodes + 1, 2), np.int64)
+        if len(order) and np.all(par_sorted[0::2] == par_sorted[1::2]):
+            ch[par_sorted[0::2], 0] = kid_sorted[0::2]
+            ch[par_sorted[1::2], 1] = kid_sorted[1::2]
+            self.children = ch.tolist()
+            for t in range(self.n_tips + 1):
+                self.children[t] = []
+        else:                             # not bifurcating: generic path
+            self.children = [[] for _ in range(n_nodes + 1)]
+            for p, c in self.edge:
+                self.children[p].append(int(c))
         self.root = self.n_tips + 1
 
     def is_tip(self, v: int) -> bool:
