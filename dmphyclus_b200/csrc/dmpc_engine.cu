@@ -644,19 +644,22 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
     t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal;
-    // alignment: [N][S] host rows -> [N][Sp] device rows; pad sites get the all-ones mask
-    CUDA_TRY(cudaMemcpy2DAsync(t->d_tipmask, t->Sp, alignmentBin, t->S, t->S, t->N, cudaMemcpyHostToDevice, t->stream));
+    // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
+    // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
+    uint8_t* stage = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)t->N * t->S, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(stage, alignmentBin, (size_t)t->N * t->S, cudaMemcpyHostToDevice, t->stream));
     {
       const size_t n = (size_t)t->N * t->Sp;
-      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
+      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
       t->st.kernel_launches++;
-      CUDA_TRY(cudaMemcpyAsync(&t->h_res->badCells, &t->rv.st->badCells, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-      CUDA_TRY(cudaStreamSynchronize(t->stream));
-      if (t->h_res->badCells)
-        return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
-                                      " alignment cells hold no state (unknown symbol; clusterFunArmadillo.cpp:109)");
     }
-    return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+    CUDA_TRY(cudaFreeAsync(stage, t->stream));
+    int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+    if (rcEval == DMPC_OK && t->h_res->badCells)
+      return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
+                                    " alignment cells hold no state (unknown symbol; clusterFunArmadillo.cpp:109)");
+    return rcEval;
   };
   rc = body();
   if (rc != DMPC_OK) { std::string keepMsg = g_err; destroy(t); g_err = keepMsg; return rc; }

@@ -552,13 +552,19 @@ __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
   if (i < n) cur[idxAndSlot[i] >> 1] = (uint8_t)(idxAndSlot[i] & 1);
 }
 
-// pad sites get the all-ones mask; counts cells whose mask is 0 (unknown symbol)
-__global__ void k_prepare_masks(uint8_t* mask, int N, int S, int Sp, int* bad) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// the uploaded alignment ([N][S] bytes, contiguous) -> the padded device layout [N][Sp]; pad sites get the all-ones
+// mask; cells without any state (unknown symbol) or with stray high bits are counted and neutralised
+__global__ void k_prepare_masks(const uint8_t* __restrict__ in, uint8_t* __restrict__ mask, int N, int S, int Sp, int* bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * Sp) return;
-  int s = (int)(i % Sp);
-  if (s >= S) mask[i] = 0xF;
-  else if ((mask[i] & 0xF) == 0 || mask[i] > 0xF) atomicAdd(bad, 1);
+  const int s = (int)(i % Sp);
+  const size_t row = i / Sp;
+  uint8_t m = 0xF;
+  if (s < S) {
+    m = in[row * S + s];
+    if ((m & 0xF) == 0 || m > 0xF) { atomicAdd(bad, 1); m = 0xF; }
+  }
+  mask[i] = m;
 }
 
 // sum of n chunk sums in a fixed order (CHUNK strided accumulators, then a binary tree); 256 threads
