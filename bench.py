@@ -329,10 +329,14 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.mark = "e2e"
     t0 = time.perf_counter()
+    e2e_parts = np.zeros(4)
     for _ in range(e2e_steps):
         res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        sti = local.stats(res["solutionPointer"])
+        e2e_parts += (sti["create_setup_us"] * 1e-3, sti["create_upload_ms"], sti["last_eval_ms"], sti["last_host_total_us"] * 1e-3)
         eng.finalDeallocate(res["solutionPointer"])
     barrier()
+    e2e_parts /= e2e_steps
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     sampler.mark = "after"
     assert res["logLik"] == ll0, (res["logLik"], ll0)
@@ -358,6 +362,8 @@ def run_ours(args, rank, world, local_rank):
                "clocks": sampler.summary(),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                       "breakdown_ms": {"host_setup": e2e_parts[0], "upload_device": e2e_parts[1], "evaluation_device": e2e_parts[2],
+                                        "evaluate_call_host": e2e_parts[3]},
                        "call": "Engine.logLikCpp (dmpc_loglik_create) + finalDeallocate, alignment in pinned host memory"},
                "gpu_launches": int(launches),
                "roofline": roofline,

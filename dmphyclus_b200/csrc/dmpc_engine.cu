@@ -39,7 +39,7 @@ typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status bloc
 // a logLikFromClusInd-style create/evaluate/destroy cycle; handles borrow a pack and give it back.
 struct ResPack {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Task* h_tasks = nullptr;       // pinned
   int32_t* h_curList = nullptr;  // pinned
   Token* h_tokens = nullptr;     // pinned
@@ -77,7 +77,7 @@ struct dmpc_tree {
   int device = 0, siteBegin = 0, sitesTotal = 0;
   ResPack pack;
   cudaStream_t stream = nullptr;                       // = pack.stream
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DevView dv{};
   RootView rv{};
   uint8_t* d_tipmask = nullptr;
@@ -176,7 +176,7 @@ int acquirePack(dmpc_tree* t) {
   }
   t->h_chunks = p.h_chunks;
   t->stream = p.stream;
-  for (int i = 0; i < 5; i++) t->ev[i] = p.ev[i];
+  for (int i = 0; i < 7; i++) t->ev[i] = p.ev[i];
   t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens; t->h_tipList = p.h_tipList;
   return DMPC_OK;
 }
@@ -615,6 +615,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->rv.RP = numRateCats <= 4 ? 4 : 8;
 
   int rc = DMPC_OK;
+  const auto c0 = std::chrono::steady_clock::now();
   auto body = [&]() -> int {
     CUDA_TRY(cudaSetDevice(t->device));
     int r2;
@@ -647,6 +648,8 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
     // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
     uint8_t* stage = nullptr;
+    t->st.create_setup_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
+    CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
     CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)t->N * t->S, t->stream));
     CUDA_TRY(cudaMemcpyAsync(stage, alignmentBin, (size_t)t->N * t->S, cudaMemcpyHostToDevice, t->stream));
     {
@@ -655,7 +658,9 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
       t->st.kernel_launches++;
     }
     CUDA_TRY(cudaFreeAsync(stage, t->stream));
+    CUDA_TRY(cudaEventRecord(t->ev[6], t->stream));
     int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+    if (rcEval == DMPC_OK) { float ms = 0; cudaEventElapsedTime(&ms, t->ev[5], t->ev[6]); t->st.create_upload_ms = ms; }
     if (rcEval == DMPC_OK && t->h_res->badCells)
       return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
                                     " alignment cells hold no state (unknown symbol; clusterFunArmadillo.cpp:109)");

@@ -151,6 +151,8 @@ typedef struct dmpc_stats {
   double last_host_plan_us;      /* host time of the last evaluation: building the plan (schedule, tasks, tokens) */
   double last_host_submit_us;    /* ... uploading it and launching every kernel */
   double last_host_total_us;     /* ... whole evaluate(), including the wait for the result */
+  double create_setup_us;        /* dmpc_loglik_create: host time before the alignment upload is issued (tree, buffers) */
+  double create_upload_ms;       /* ... device time of the alignment upload + re-pitch (CUDA events) */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
