@@ -261,7 +261,7 @@ dmpc_tree* g_constOwner[64] = {nullptr};
 
 int rootStage(dmpc_tree* t, double* ll);
 
-constexpr int NARROW_LEVEL = 8;   // levels with at most this many tasks are chained into one launch
+constexpr int NARROW_LEVEL = 4;   // levels with at most this many tasks are chained into one launch
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
   if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdmpc.so")
+LIB_PATH = os.environ.get("DMPC_LIB_PATH", os.path.join(HERE, "libdmpc.so"))   # the override is for A/B builds of the kernels
 _dbl_p = C.POINTER(C.c_double)
 _i32_p = C.POINTER(C.c_int32)
 _u8_p = C.POINTER(C.c_uint8)
