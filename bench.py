@@ -369,6 +369,7 @@ def run_ours(args, rank, world, local_rank):
                "roofline": roofline,
                "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
                "sharded_exchange": ({"in_kernel": eng.fast, "host_collectives": eng.collectives} if world > 1 else None),
+               "chain": {"rescaled_sites": int(st1["last_chain_sites"]), "exponent_rows": int(st1["last_chain_rows"]), "rescaled_tiles": int(st1["last_active_tiles"])},
                "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
                "levels": int(st1["last_levels"])}
         out.update(extras)

@@ -116,6 +116,7 @@ struct dmpc_tree {
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
   dmpc_comm* comm = nullptr;
+  int chainGroup = 4;            // rows per group of the chain walker: 4 for long exponent lists, 1 for sparse ones
   int lastNact = 0;
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
@@ -207,7 +208,7 @@ int allocSlot(dmpc_tree* t, int slot) {
 int allocElist(dmpc_tree* t, int kcap) {
   // the previous list (if any) stays in the pool until the handle dies; growth is rare and geometric
   t->rv.Kcap = kcap;
-  t->rv.Q = std::max(512, (kcap + 3) & ~3);
+  t->rv.Q = std::max(512, (kcap + 3) & ~3);       // >= the padded length of any site's list, multiple of both group sizes
   t->st.exponent_capacity = kcap;
   return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
 }
@@ -422,30 +423,32 @@ int launchGather(dmpc_tree* t, int mode) {
   return DMPC_OK;
 }
 
-size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 8) rows of RP floats, 1 marker byte per group of 4 rows, metadata
+size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 8) rows of RP floats, 1 marker byte per group (<= per row), metadata
   const size_t cap = 2 * (size_t)t->rv.Q + 8;
-  return 2 * cap * t->rv.RP * sizeof(float) + 2 * (cap / 4) + 4 * sizeof(int) + 16;
+  return 2 * cap * t->rv.RP * sizeof(float) + 2 * cap + 4 * sizeof(int) + 16;
 }
 
-template <int RP, int RC>
+template <int RP, int RC, int G>
 int launchChainT(dmpc_tree* t, size_t smem) {
-  CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chain<RP, RC><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chain<RP, RC, G><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
   return DMPC_OK;
 }
+template <int RP, int RC>
+int launchChainG(dmpc_tree* t, size_t smem) { return t->chainGroup == 1 ? launchChainT<RP, RC, 1>(t, smem) : launchChainT<RP, RC, 4>(t, smem); }
 
 int launchChain(dmpc_tree* t) {
   const size_t smem = chainSmem(t);
   if (smem > 220 * 1024) return fail(DMPC_ERR_ARG, "rescale list too deep for the chain kernel's staging buffers");
   int rc = DMPC_OK;
   switch (t->R) {
-    case 2: rc = launchChainT<4, 2>(t, smem); break;
-    case 3: rc = launchChainT<4, 3>(t, smem); break;
-    case 4: rc = launchChainT<4, 4>(t, smem); break;
-    case 5: rc = launchChainT<8, 5>(t, smem); break;
-    case 6: rc = launchChainT<8, 6>(t, smem); break;
-    case 7: rc = launchChainT<8, 7>(t, smem); break;
-    default: rc = launchChainT<8, 8>(t, smem); break;
+    case 2: rc = launchChainG<4, 2>(t, smem); break;
+    case 3: rc = launchChainG<4, 3>(t, smem); break;
+    case 4: rc = launchChainG<4, 4>(t, smem); break;
+    case 5: rc = launchChainG<8, 5>(t, smem); break;
+    case 6: rc = launchChainG<8, 6>(t, smem); break;
+    case 7: rc = launchChainG<8, 7>(t, smem); break;
+    default: rc = launchChainG<8, 8>(t, smem); break;
   }
   if (rc) return rc;
   t->st.kernel_launches++;
@@ -467,7 +470,15 @@ int readStatus(dmpc_tree* t, bool withChunks) {
     CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   t->st.last_active_tiles = t->h_res->nact;
+  t->st.last_chain_sites = t->h_res->nact ? t->h_res->chainSites : 0;
+  t->st.last_chain_rows = t->h_res->nact ? t->h_res->chainRows : 0;
   t->lastNact = t->h_res->nact;
+  if (t->h_res->nact && t->h_res->chainSites > 0) {
+    // rows per rescaled site as the chain just saw them (padded to the group size): sparse lists walk faster one row at a time
+    const double avg = (double)t->h_res->chainRows / t->h_res->chainSites;
+    if (t->chainGroup == 4 && avg < 4.5) t->chainGroup = 1;
+    else if (t->chainGroup == 1 && avg > 6.0) t->chainGroup = 4;
+  }
   return DMPC_OK;
 }
 
@@ -948,6 +959,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
   *out = t->st;
   out->exact_mode = t->exact ? 1 : 0;
+  out->chain_group = t->chainGroup;
   out->num_tips = t->N; out->num_loci = t->S; out->num_rate_cats = t->R;
   return DMPC_OK;
 }

@@ -54,6 +54,8 @@ struct DevStatus {
   int xok;                      // site-sharded runs: 1 = the in-kernel peer exchange produced ll, 0 = host protocol needed,
                                 //   2 = a peer never answered, -1 = no exchange attempted
   int pad;
+  int chainSites, chainRows;    // what k_chain walked: rescaled sites and (padded) exponent rows
+  int pad2[2];
 };
 
 // Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access): every rank
@@ -787,7 +789,9 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
 // (compile time), RP = floats per row (4 or 8).  When no site rescaled the kernel returns at once.  In a
 // site-sharded run the vector entering this shard comes from an earlier rank's mailbox and the vector leaving it is
 // handed to the later ranks (CommView).
-template <int RP, int RC>
+// G = rows per group (4 for long lists, 1 when most rescaled sites hold a single row): a site's rows are padded to a
+// multiple of G with zero rows, the walker tests for the end of a site once per group.
+template <int RP, int RC, int G>
 __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   extern __shared__ float4 s_dyn[];
   constexpr int V = RP / 4;                       // float4 per row
@@ -830,12 +834,12 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   }
 
   // phase A: ordered compaction of the sites that rescaled anywhere (kmax > 0) + prefix of their row counts.
-  // A site's rows are padded to a multiple of 4 with zero rows (x + 0.0f == x), so that the walker consumes
-  // whole groups of 4 and a site can only end at a group boundary.
+  // A site's rows are padded to a multiple of G with zero rows (x + 0.0f == x), so that the walker consumes
+  // whole groups and a site can only end at a group boundary.
   int baseCnt = 0, baseRows = 0;
   for (int start = 0; start < S; start += nth) {
     const int s = start + tid;
-    const int km = s < S ? (min(rv.kmax[s], rv.Kcap) + 3) & ~3 : 0;
+    const int km = s < S ? (min(rv.kmax[s], rv.Kcap) + G - 1) / G * G : 0;
     const int actv = km > 0;
     int ic = actv, ir = km;                        // inclusive warp scans
 #pragma unroll
@@ -864,7 +868,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
     __syncthreads();
   }
   const int nact = baseCnt;
-  if (tid == 0) rv.rowoff[nact] = baseRows;
+  if (tid == 0) { rv.rowoff[nact] = baseRows; rv.st->chainSites = nact; rv.st->chainRows = baseRows; }
   __syncthreads();
   // staging chunks: chunk c = active sites whose row offset lies in [cQ, (c+1)Q); Q >= padded Kcap so no chunk is empty
   const int nchunks = nact ? rv.rowoff[nact - 1] / Q + 1 : 0;
@@ -879,23 +883,23 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
   // end-of-site marker per group of 4 rows, then per-buffer {first active index, rows}
   const int cap = 2 * Q + 8;
   float4* const buf0 = s_dyn;
-  unsigned char* const end0 = reinterpret_cast<unsigned char*>(s_dyn + (size_t)2 * cap * V);
-  int* const meta0 = reinterpret_cast<int*>(end0 + 2 * (cap / 4));
+  unsigned char* const end0 = reinterpret_cast<unsigned char*>(s_dyn + (size_t)2 * cap * V);   // one marker per group
+  int* const meta0 = reinterpret_cast<int*>(end0 + 2 * cap);
   float c[RC];
 #pragma unroll
   for (int r = 0; r < RC; r++) c[r] = rv.carryIn[r];
 
   auto stage = [&](int ch, int ltid, int nld, int b) {
     float4* const bufb = buf0 + (size_t)b * cap * V;
-    unsigned char* const endb = end0 + (size_t)b * (cap / 4);
+    unsigned char* const endb = end0 + (size_t)b * cap;
     const int i0 = rv.chunkStart[ch], i1 = rv.chunkStart[ch + 1];
     const int r0 = rv.rowoff[i0], nrows = rv.rowoff[i1] - r0, ns = i1 - i0;
     if (ltid == 0) { meta0[2 * b] = i0; meta0[2 * b + 1] = nrows; }
-    for (int q = ltid; q < nrows + 4; q += nld) {
+    for (int q = ltid; q < nrows + G; q += nld) {
       if (q >= nrows) {                           // the spare group: zeros, never an end
 #pragma unroll
         for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((q & 3) == 0) endb[q >> 2] = 0;
+        if (q % G == 0) endb[q / G] = 0;
         continue;
       }
       int lo = 0, hi = ns;                        // last k with rowoff[i0 + k] - r0 <= q
@@ -905,7 +909,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
       const float4* src = reinterpret_cast<const float4*>(rv.elist + ((size_t)site * rv.Kcap + j) * RP);
 #pragma unroll
       for (int u = 0; u < V; u++) bufb[(size_t)q * V + u] = j < km ? src[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((q & 3) == 0) endb[q >> 2] = (unsigned char)(q + 4 == rv.rowoff[i0 + lo + 1] - r0);
+      if (q % G == 0) endb[q / G] = (unsigned char)(q + G == rv.rowoff[i0 + lo + 1] - r0);
     }
   };
 
@@ -921,25 +925,25 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
       // the RC additions per row and one flag test per group of 4 rows; two groups per trip so that the next group
       // is already on its way from shared memory while the current one is added.
       unsigned rowAddr = (unsigned)__cvta_generic_to_shared(buf0 + (size_t)b * cap * V);
-      unsigned endAddr = (unsigned)__cvta_generic_to_shared(end0 + (size_t)b * (cap / 4));
+      unsigned endAddr = (unsigned)__cvta_generic_to_shared(end0 + (size_t)b * cap);
       int outIdx = meta0[2 * b];
-      const int ngroups = meta0[2 * b + 1] >> 2;
+      const int ngroups = meta0[2 * b + 1] / G;
       float* co = rv.cout + (size_t)outIdx * RP;
       float* mo = rv.mxo + outIdx;
-      float4 x[4][V], y[4][V];
+      float4 x[G][V], y[G][V];
       unsigned fx, fy;
-      auto loadGroup = [&](float4 (&g)[4][V], unsigned& f, unsigned ra, unsigned ea) {
+      auto loadGroup = [&](float4 (&g)[G][V], unsigned& f, unsigned ra, unsigned ea) {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < G; j++)
 #pragma unroll
           for (int u = 0; u < V; u++)
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[j][u].x), "=f"(g[j][u].y), "=f"(g[j][u].z), "=f"(g[j][u].w)
                          : "r"(ra + (unsigned)((j * V + u) * 16)));
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(ea));
       };
-      auto addGroup = [&](const float4 (&g)[4][V], unsigned flag) {
+      auto addGroup = [&](const float4 (&g)[G][V], unsigned flag) {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < G; j++)
 #pragma unroll
           for (int r = 0; r < RC; r++) {
             const float4 w = g[j][r >> 2];
@@ -957,7 +961,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
           co += RP; mo++;
         }
       };
-      constexpr unsigned GB = 4 * V * 16;         // bytes of one group of rows
+      constexpr unsigned GB = G * V * 16;         // bytes of one group of rows
       if (ngroups > 0) loadGroup(x, fx, rowAddr, endAddr);
       for (int g = 0; g < ngroups; g += 2) {
         loadGroup(y, fy, rowAddr + GB, endAddr + 1);      // the spare group behind the last one makes this safe

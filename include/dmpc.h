@@ -153,6 +153,8 @@ typedef struct dmpc_stats {
   double last_host_total_us;     /* ... whole evaluate(), including the wait for the result */
   double create_setup_us;        /* dmpc_loglik_create: host time before the alignment upload is issued (tree, buffers) */
   double create_upload_ms;       /* ... device time of the alignment upload + re-pitch (CUDA events) */
+  int last_chain_sites, last_chain_rows;   /* rescaled sites / exponent rows the sequential chain kernel walked */
+  int chain_group;          /* rows per group the chain walker will use next (4, or 1 for sparse exponent lists) */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which

@@ -353,3 +353,25 @@ def test_rcpp_shim_end_to_end(packaged, oracle, fast_masks, monkeypatch):
     for n, S, k, R, kind in ((40, 70, 5, 3, "evolved"), (500, 60, 6, 3, "iid")):
         p = Problem(packaged, n, S, k, R, kind, seed=n)
         compare_to_golden(run_script(shim, p), run_script(oracle, p), ll_tol=TOL, exact_partials=True)
+
+
+def test_chain_walker_group_sizes_agree(packaged, engine, oracle):
+    """The sequential exponent chain pads a site's rows to groups of 4 (long lists) or walks them one by one (sparse
+    lists); the engine switches after seeing the first evaluation.  Both must give the oracle's value."""
+    p = Problem(packaged, 1024, 900, 6, 3, "diverged", seed=3)       # few rescales per site -> the sparse walker
+    hg, l0 = p.create(engine)
+    ho, lo = p.create(oracle)
+    assert engine.stats(hg)["last_chain_sites"] > 0 and rel(l0, lo) < TOL
+    g_after_first = engine.stats(hg)["chain_group"]
+    l1 = engine.recomputeAll(hg, p.W[4], p.B[4], p.pi)
+    assert l1 == l0
+    a = engine.newBetweenTransProbsLogLik(hg, p.W[4], p.B[2], 1, 3, p.pi)
+    b = oracle.newBetweenTransProbsLogLik(ho, p.W[4], p.B[2], 1, 3, p.pi)
+    assert rel(a, b) < TOL
+    q = Problem(packaged, 900, 300, 5, 3, "iid", seed=4)             # ~12 rescales per site and rate -> groups of 4
+    hq, lq = q.create(engine)
+    hq2, lq2 = q.create(oracle)
+    assert rel(lq, lq2) < TOL and engine.recomputeAll(hq, q.W[4], q.B[4], q.pi) == lq
+    assert {g_after_first, engine.stats(hq)["chain_group"]} == {1, 4}
+    for be, h in ((engine, hg), (oracle, ho), (engine, hq), (oracle, hq2)):
+        be.finalDeallocate(h)
