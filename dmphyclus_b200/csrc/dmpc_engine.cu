@@ -107,6 +107,11 @@ struct dmpc_tree {
     int metaTasks = 0;
   } cache;
   unsigned long long planCacheHits = 0;
+  // the cached full-evaluation plan as CUDA graphs (one per slot flip): level launches + gather in ONE submission
+  struct { cudaGraphExec_t exec = nullptr; unsigned long long version = 0; } graphs[2];
+  unsigned long long graphVersion = 1;   // bumped whenever something baked into the captured kernel parameters changes
+  bool capturing = false, gatherPrelaunched = false;
+  unsigned long long graphReplays = 0;
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
   Token* d_tokens = nullptr;
   Token* h_tokens = nullptr;     // pinned
@@ -198,6 +203,7 @@ int ensureDevice(dmpc_tree* t) {
 int allocSlot(dmpc_tree* t, int slot) {
   if (t->dv.part[slot]) return DMPC_OK;
   int rc;
+  t->graphVersion++;
   const size_t n = (size_t)t->nInt * t->R * t->Sp;
   if ((rc = t->alloc(&t->dv.part[slot], n * 4))) return rc;
   if ((rc = t->alloc(&t->dv.expo[slot], n))) return rc;
@@ -208,6 +214,7 @@ int allocSlot(dmpc_tree* t, int slot) {
 int allocElist(dmpc_tree* t, int kcap) {
   // the previous list (if any) stays in the pool until the handle dies; growth is rare and geometric
   t->rv.Kcap = kcap;
+  t->graphVersion++;
   t->rv.Q = std::max(512, (kcap + 3) & ~3);       // >= the padded length of any site's list, multiple of both group sizes
   t->st.exponent_capacity = kcap;
   return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
@@ -261,8 +268,16 @@ std::mutex g_constMutex;
 dmpc_tree* g_constOwner[64] = {nullptr};
 
 int rootStage(dmpc_tree* t, double* ll);
+int launchGather(dmpc_tree* t, int mode);
 
 constexpr int NARROW_LEVEL = 4;   // levels with at most this many tasks are chained into one launch
+
+// timing events: inside a stream capture they become event-record nodes that record the (external) event on every replay
+int recordEv(dmpc_tree* t, int i) {
+  if (t->capturing) CUDA_TRY(cudaEventRecordWithFlags(t->ev[i], t->stream, cudaEventRecordExternal));
+  else CUDA_TRY(cudaEventRecord(t->ev[i], t->stream));
+  return DMPC_OK;
+}
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
   if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);
@@ -275,7 +290,8 @@ int runPlan(dmpc_tree* t) {
   const HostTree::Plan& p = *t->runPlanMeta;
   const int nLevels = (int)p.levelStart.size() - 1;
   if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
-  CUDA_TRY(cudaEventRecord(t->ev[0], t->stream));
+  int rcE;
+  if ((rcE = recordEv(t, 0))) return rcE;
   int launches = 0;
   for (int l = 0; l < nLevels;) {
     int n = p.levelStart[l + 1] - p.levelStart[l];
@@ -292,8 +308,8 @@ int runPlan(dmpc_tree* t) {
     t->st.kernel_launches++;
     launches++;
   }
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(t->ev[1], t->stream));
+  if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  if ((rcE = recordEv(t, 1))) return rcE;
   t->st.last_levels = nLevels;
   t->st.last_prune_launches = launches;
   return DMPC_OK;
@@ -368,13 +384,41 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
       cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps;
       cc.meta.tasks.clear(); cc.metaTasks = nT;
       cc.valid = true;
+      t->graphVersion++;
     }
   }
   t->runPlanMeta = meta;
   const int nTasks = hit ? cc.metaTasks : (int)p.tasks.size();
   const long long storedReads = meta->storedReads, tipReads = meta->tipReads, fusedOps = meta->fusedOps;
   t->st.last_host_plan_us = usSince(h0);
-  if ((rc = runPlan(t))) return rc;
+  const bool chainMode = t->quirk && t->R > 1;
+  if (hit && !t->deferred) {
+    // replay (or first capture) of the whole device-side sequence of this cached plan: levels + gather
+    auto& g = t->graphs[flip];
+    if (!g.exec || g.version != t->graphVersion) {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+      t->capturing = true;
+      int rcC = runPlan(t);
+      if (!rcC) rcC = launchGather(t, chainMode ? 1 : 0);
+      if (!rcC) rcC = recordEv(t, 2);
+      t->capturing = false;
+      const cudaError_t ce = cudaStreamEndCapture(t->stream, &graph);
+      if (rcC) { if (graph) cudaGraphDestroy(graph); return rcC; }
+      if (ce != cudaSuccess) return fail(DMPC_ERR_CUDA, std::string("stream capture: ") + cudaGetErrorString(ce));
+      const cudaError_t ci = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ci != cudaSuccess) return fail(DMPC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci));
+      g.version = t->graphVersion;
+    }
+    CUDA_TRY(cudaGraphLaunch(g.exec, t->stream));
+    t->gatherPrelaunched = true;
+    t->graphReplays++;
+    t->st.kernel_launches += t->st.last_prune_launches + 1;
+  } else if ((rc = runPlan(t))) {
+    return rc;
+  }
   t->st.last_updates = (unsigned long long)(nTasks + fusedOps) * t->S * t->R;
   t->st.updates += t->st.last_updates;
   t->st.evaluations++;
@@ -393,6 +437,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     // a fused clade may have rescaled: redo the same plan with the exact kernel (same tasks, same slots) and
     // keep that mode for the life of the handle
     t->exact = true;
+    t->graphVersion++;
     CUDA_TRY(cudaMemsetAsync(&t->rv.st->violation, 0, sizeof(int), t->stream));
     if ((rc = runPlan(t))) return rc;
     t->st.exact_mode = 1;
@@ -419,7 +464,7 @@ int launchGather(dmpc_tree* t, int mode) {
   if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   t->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
+  if (!t->capturing) CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
 }
 
@@ -495,8 +540,12 @@ int rootStage(dmpc_tree* t, double* ll) {
     t->carryIsZero = true;
   }
   for (int attempt = 0; attempt < 8; attempt++) {
-    if ((rc = launchGather(t, mode))) return rc;
-    CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+    if (t->gatherPrelaunched) {
+      t->gatherPrelaunched = false;               // the replayed graph already ran the gather (and recorded ev[2])
+    } else {
+      if ((rc = launchGather(t, mode))) return rc;
+      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+    }
     if ((rc = readStatus(t, t->deferred))) return rc;
     if (t->h_res->overflow > t->rv.Kcap) {
       int k = t->rv.Kcap;
@@ -546,6 +595,7 @@ int rootStage(dmpc_tree* t, double* ll) {
 void destroy(dmpc_tree* t) {
   if (!t) return;
   cudaSetDevice(t->device);
+  for (auto& g : t->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   if (t->stream) {
     for (void* p : t->allocs) cudaFreeAsync(p, t->stream);
     cudaStreamSynchronize(t->stream);                  // the pack (stream, pinned buffers) goes back idle
@@ -960,6 +1010,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   *out = t->st;
   out->exact_mode = t->exact ? 1 : 0;
   out->chain_group = t->chainGroup;
+  out->plan_cache_hits = t->planCacheHits; out->graph_replays = t->graphReplays;
   out->num_tips = t->N; out->num_loci = t->S; out->num_rate_cats = t->R;
   return DMPC_OK;
 }

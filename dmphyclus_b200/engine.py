@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("last_fused_vertices", C.c_int), ("exact_mode", C.c_int),
                 ("last_host_plan_us", C.c_double), ("last_host_submit_us", C.c_double), ("last_host_total_us", C.c_double),
                 ("create_setup_us", C.c_double), ("create_upload_ms", C.c_double),
-                ("last_chain_sites", C.c_int), ("last_chain_rows", C.c_int), ("chain_group", C.c_int)]
+                ("last_chain_sites", C.c_int), ("last_chain_rows", C.c_int), ("chain_group", C.c_int),
+                ("plan_cache_hits", C.c_ulonglong), ("graph_replays", C.c_ulonglong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

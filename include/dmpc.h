@@ -155,6 +155,8 @@ typedef struct dmpc_stats {
   double create_upload_ms;       /* ... device time of the alignment upload + re-pitch (CUDA events) */
   int last_chain_sites, last_chain_rows;   /* rescaled sites / exponent rows the sequential chain kernel walked */
   int chain_group;          /* rows per group the chain walker will use next (4, or 1 for sparse exponent lists) */
+  unsigned long long plan_cache_hits;   /* full evaluations that replayed the device-resident plan */
+  unsigned long long graph_replays;     /* ... of which submitted as one CUDA graph launch */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which

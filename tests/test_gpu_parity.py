@@ -375,3 +375,34 @@ def test_chain_walker_group_sizes_agree(packaged, engine, oracle):
     assert {g_after_first, engine.stats(hq)["chain_group"]} == {1, 4}
     for be, h in ((engine, hg), (oracle, ho), (engine, hq), (oracle, hq2)):
         be.finalDeallocate(h)
+
+
+def test_plan_cache_and_graph_replay(packaged, engine, oracle):
+    """Repeated full evaluations of an unchanged tree replay the cached plan (as one CUDA graph launch); proposals,
+    rollbacks and topology changes in between must invalidate or bypass it correctly."""
+    p = Problem(packaged, 300, 600, 6, 3, "evolved", seed=12)
+    hg, l0 = p.create(engine)
+    ho, _ = p.create(oracle)
+    W, B = p.W, p.B
+    for _ in range(4):
+        assert engine.recomputeAll(hg, W[4], B[4], p.pi) == l0
+    st = engine.stats(hg)
+    assert st["plan_cache_hits"] >= 3 and st["graph_replays"] >= 3
+    # new within-cluster matrices = full recompute through the cached plan, accepted, then rejected
+    for idx, keep in ((7, True), (2, False), (9, True)):
+        a = engine.newWithinTransProbsLogLik(hg, W[idx - 1], B[4], 1, idx, p.pi)
+        b = oracle.newWithinTransProbsLogLik(ho, W[idx - 1], B[4], 1, idx, p.pi)
+        assert rel(a, b) < TOL
+        if not keep:
+            for be, h in ((engine, hg), (oracle, ho)):
+                be.RestorePreviousConfig(h, np.zeros((1, 2), np.int32), 7, 5, False, p.mrcas, False)
+    # a topology change (accepted NNI) must not be served from the stale plan
+    m = [x for x in p.mrcas if x > p.n][0]
+    ra = engine.withinClusNNIlogLik(hg, W[8], B[4], m, 2, 1, p.pi)
+    rb = oracle.withinClusNNIlogLik(ho, W[8], B[4], m, 2, 1, p.pi)
+    assert np.array_equal(ra["edge"], rb["edge"]) and rel(ra["logLik"], rb["logLik"]) < TOL
+    a = engine.newWithinTransProbsLogLik(hg, W[0], B[4], 1, 1, p.pi)
+    b = oracle.newWithinTransProbsLogLik(ho, W[0], B[4], 1, 1, p.pi)
+    assert rel(a, b) < TOL
+    assert np.array_equal(engine.partial(hg, p.n)[0], oracle.partial(ho, p.n)[0])
+    engine.finalDeallocate(hg); oracle.finalDeallocate(ho)
