@@ -392,7 +392,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   const long long storedReads = meta->storedReads, tipReads = meta->tipReads, fusedOps = meta->fusedOps;
   t->st.last_host_plan_us = usSince(h0);
   const bool chainMode = t->quirk && t->R > 1;
-  if (hit && !t->deferred) {
+  if (hit) {
     // replay (or first capture) of the whole device-side sequence of this cached plan: levels + gather
     auto& g = t->graphs[flip];
     if (!g.exec || g.version != t->graphVersion) {
@@ -461,6 +461,8 @@ int launchGather(dmpc_tree* t, int mode) {
     }
   }
   CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
+  if (t->deferred && mode == 1)                  // site-sharded: the gather's optimistic finish assumes the vector enters as zeros
+    CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
   if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
   t->st.kernel_launches++;
@@ -535,10 +537,7 @@ int rootStage(dmpc_tree* t, double* ll) {
   int rc;
   const bool chain = t->quirk && t->R > 1;
   const int mode = chain ? 1 : 0;
-  if (t->deferred && chain) {
-    CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));   // optimistic: vector enters as zeros
-    t->carryIsZero = true;
-  }
+  if (t->deferred && chain) t->carryIsZero = true;   // launchGather zeroes the entry vector: optimistic pass
   for (int attempt = 0; attempt < 8; attempt++) {
     if (t->gatherPrelaunched) {
       t->gatherPrelaunched = false;               // the replayed graph already ran the gather (and recorded ev[2])
@@ -1171,6 +1170,7 @@ int dmpc_set_deferred(dmpc_tree* t, int on) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
   t->deferred = on != 0;
+  t->graphVersion++;
   return DMPC_OK;
 }
 
