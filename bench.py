@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
-    ap.add_argument("--sweep-rates", type=int, default=1, help="rate categories of the proposal sweep (with 3, config 4's committed state has rescaled sites and the batch falls back to one-by-one evaluation)")
+    ap.add_argument("--sweep-rates", type=int, default=3, help="rate categories of the proposal sweep")
     ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
     ap.add_argument("--strong", action="store_true", help="N > 1: split the workload's sites across the ranks (strong scaling) instead of giving every rank the full site count")
     ap.add_argument("--seed", type=int, default=2001)
@@ -435,9 +435,7 @@ def proposal_sweep(args):
     build.build()
     n, s, k, r = CONFIGS["config4"]
     r = args.sweep_rates
-    # the batched kernel needs a committed state without rescaled sites: an alignment evolved under the matrices it
-    # is evaluated with ("matched") has none at this size; anything else falls back to one-by-one evaluation
-    data = "matched" if args.data == "evolved" else args.data
+    data = args.data
     p = Problem(load_packaged(), n, s, k, r, data, args.tree, seed=args.seed)
     eng = Engine(device=0, fuse_tips=args.fuse)
     al = eng.getConvertedAlignment(list(synth.STATES), p.chars)

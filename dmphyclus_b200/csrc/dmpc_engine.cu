@@ -463,8 +463,8 @@ int launchGather(dmpc_tree* t, int mode) {
   CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
   if (t->deferred && mode == 1)                  // site-sharded: the gather's optimistic finish assumes the vector enters as zeros
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
-  if (t->rv.RP == 4) k_root_gather<4><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
-  else k_root_gather<8><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode);
+  if (t->rv.RP == 4) k_root_gather<4, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
+  else k_root_gather<8, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
   t->st.kernel_launches++;
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -475,27 +475,35 @@ size_t chainSmem(const dmpc_tree* t) {   // 2 buffers of (2Q + 8) rows of RP flo
   return 2 * cap * t->rv.RP * sizeof(float) + 2 * cap + 4 * sizeof(int) + 16;
 }
 
+// rvBatch != nullptr: one block per proposal of a batch (dmpc_eval_proposals), working on per-proposal copies
 template <int RP, int RC, int G>
-int launchChainT(dmpc_tree* t, size_t smem) {
-  CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chain<RP, RC, G><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+int launchChainT(dmpc_tree* t, size_t smem, const RootView* rvBatch, int nBatch) {
+  if (rvBatch) {
+    CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain<RP, RC, G, true><<<nBatch, 1024, smem, t->stream>>>(t->dv, *rvBatch);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_chain<RP, RC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chain<RP, RC, G, false><<<1, 1024, smem, t->stream>>>(t->dv, t->rv);
+  }
   return DMPC_OK;
 }
 template <int RP, int RC>
-int launchChainG(dmpc_tree* t, size_t smem) { return t->chainGroup == 1 ? launchChainT<RP, RC, 1>(t, smem) : launchChainT<RP, RC, 4>(t, smem); }
+int launchChainG(dmpc_tree* t, size_t smem, const RootView* rvBatch, int nBatch) {
+  return t->chainGroup == 1 ? launchChainT<RP, RC, 1>(t, smem, rvBatch, nBatch) : launchChainT<RP, RC, 4>(t, smem, rvBatch, nBatch);
+}
 
-int launchChain(dmpc_tree* t) {
+int launchChain(dmpc_tree* t, const RootView* rvBatch = nullptr, int nBatch = 0) {
   const size_t smem = chainSmem(t);
   if (smem > 220 * 1024) return fail(DMPC_ERR_ARG, "rescale list too deep for the chain kernel's staging buffers");
   int rc = DMPC_OK;
   switch (t->R) {
-    case 2: rc = launchChainG<4, 2>(t, smem); break;
-    case 3: rc = launchChainG<4, 3>(t, smem); break;
-    case 4: rc = launchChainG<4, 4>(t, smem); break;
-    case 5: rc = launchChainG<8, 5>(t, smem); break;
-    case 6: rc = launchChainG<8, 6>(t, smem); break;
-    case 7: rc = launchChainG<8, 7>(t, smem); break;
-    default: rc = launchChainG<8, 8>(t, smem); break;
+    case 2: rc = launchChainG<4, 2>(t, smem, rvBatch, nBatch); break;
+    case 3: rc = launchChainG<4, 3>(t, smem, rvBatch, nBatch); break;
+    case 4: rc = launchChainG<4, 4>(t, smem, rvBatch, nBatch); break;
+    case 5: rc = launchChainG<8, 5>(t, smem, rvBatch, nBatch); break;
+    case 6: rc = launchChainG<8, 6>(t, smem, rvBatch, nBatch); break;
+    case 7: rc = launchChainG<8, 7>(t, smem, rvBatch, nBatch); break;
+    default: rc = launchChainG<8, 8>(t, smem, rvBatch, nBatch); break;
   }
   if (rc) return rc;
   t->st.kernel_launches++;
@@ -504,7 +512,7 @@ int launchChain(dmpc_tree* t) {
 }
 
 int launchFinal(dmpc_tree* t, int mode, int reduceAll) {
-  k_final<<<t->nChunks, CHUNK, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll);
+  k_final<false><<<t->nChunks, CHUNK, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll, PathView{});
   t->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -914,21 +922,31 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
   if ((rc = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return rc;
   int nBatched = 0;
   std::vector<uint8_t> needSeq(nProps, 1);
-  // the batched kernel assumes a resting exponent vector: nothing rescaled in the committed state, nothing may in a proposal
-  const bool batchable = !t->exact && t->lastNact == 0 && nProps > 0;
+  // Batched path: per proposal, the path to the root is walked with the partial in registers (k_prune_paths), then the
+  // ordinary root reduction runs on per-proposal copies of its work arrays, reading the proposal's exponents for path
+  // vertices and the committed ones for everything else.  Exact-mode handles (fused clades that may rescale) and
+  // proposals that trip the fused-clade test or overflow the exponent lists go one by one below.
+  const bool chainMode = t->quirk && t->R > 1;
+  const bool batchable = !t->exact && nProps > 0;
   if (batchable) {
-    const size_t perProp = (size_t)t->R * t->Sp * sizeof(double);
-    const int maxBatch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nProps, ((size_t)2 << 30) / perProp));
+    constexpr int JCAP = 96;                       // longest path handled in a batch
+    const size_t Sp = (size_t)t->Sp, Kc = (size_t)t->rv.Kcap, RP = (size_t)t->rv.RP, R = (size_t)t->R, T = (size_t)t->T;
     HostTree::Plan pp;
     std::vector<int> runStart;
-    std::vector<double> chunks;
+    std::vector<int32_t> ids, pos;
+    std::vector<DevStatus> stat;
     std::vector<int> invalid;
-    for (int b0 = 0; b0 < nProps; b0 += maxBatch) {
-      const int nb = std::min(maxBatch, nProps - b0);
+    int b0 = 0;
+    while (b0 < nProps) {
+      // plan proposals until the batch's scratch would exceed ~3 GB
       pp.tasks.clear(); pp.tokens.clear(); pp.tipList.clear();
       runStart.assign(1, 0);
-      for (int i = b0; i < b0 + nb; i++) {
+      std::vector<int> member;                     // indices (into props) of this batch
+      int jmax = 1;
+      size_t bytes = 0;
+      for (int i = b0; i < nProps; i++) {
         const dmpc_proposal& q = props[i];
+        const size_t before = pp.tasks.size();
         if (q.kind == DMPC_PROPOSAL_SPLIT) {         // HandleSplit, AugTree.cpp:328-336, on a scratch copy of the flags
           const int m = q.a - 1, k0 = ht.kids[2 * m], k1 = ht.kids[2 * m + 1];
           const uint8_t w0 = ht.within[k0], w1 = ht.within[k1];
@@ -942,37 +960,83 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
           ht.pathRun(ht.parent[a], pp);
           ht.within[a] = wa; ht.within[b] = wb;
         }
+        const int len = (int)(pp.tasks.size() - before);
+        if (len > JCAP) { pp.tasks.resize(before); b0 = i + 1; if (member.empty()) continue; else { b0 = i; break; } }
+        const int jm = std::max(jmax, len);
+        const size_t per = (size_t)jm * R * Sp * 4 + (size_t)jm * R * T + R * Sp * 8 +            // pe, pf, rootdot
+                           Sp * Kc * RP * 4 + Sp * (4 * 4 + 4 + 8) + Sp * RP * 4 + T * 8 + 256;    // root work arrays
+        if (!member.empty() && per * (member.size() + 1) > ((size_t)3 << 30)) { pp.tasks.resize(before); b0 = i; break; }
+        jmax = jm; bytes = per * (member.size() + 1);
+        member.push_back(i);
         runStart.push_back((int)pp.tasks.size());
+        b0 = i + 1;
       }
-      Task* dT = nullptr; Token* dK = nullptr; int32_t* dL = nullptr; int* dR = nullptr; int* dI = nullptr;
-      double* dRoot = nullptr; double* dC = nullptr;
-      const size_t nT = pp.tasks.size(), nK = std::max<size_t>(1, pp.tokens.size()), nL = std::max<size_t>(1, pp.tipList.size());
-      CUDA_TRY(cudaMallocAsync((void**)&dT, nT * sizeof(Task), t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dK, nK * sizeof(Token), t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dL, nL * sizeof(int32_t), t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dR, (size_t)(nb + 1) * sizeof(int), t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dI, (size_t)nb * sizeof(int), t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dRoot, (size_t)nb * perProp, t->stream));
-      CUDA_TRY(cudaMallocAsync((void**)&dC, (size_t)nb * t->T * sizeof(double), t->stream));
+      const int nb = (int)member.size();
+      if (!nb) continue;
+      (void)bytes;
+      ids.assign((size_t)nb * jmax, INT32_MAX); pos.assign((size_t)nb * jmax, 0);
+      for (int i = 0; i < nb; i++) {
+        const int len = runStart[i + 1] - runStart[i];
+        std::vector<std::pair<int32_t, int32_t>> pr(len);
+        for (int j = 0; j < len; j++) pr[j] = {pp.tasks[runStart[i] + j].out, j};
+        std::sort(pr.begin(), pr.end());
+        for (int j = 0; j < len; j++) { ids[(size_t)i * jmax + j] = pr[j].first; pos[(size_t)i * jmax + j] = pr[j].second; }
+      }
+      // scratch (stream-ordered pool)
+      std::vector<void*> tmp;
+      auto dalloc = [&](size_t n) -> void* { void* q = nullptr; if (cudaMallocAsync(&q, std::max<size_t>(n, 16), t->stream) != cudaSuccess) return nullptr; tmp.push_back(q); return q; };
+      const size_t nT = pp.tasks.size(), nK = pp.tokens.size(), nL = pp.tipList.size();
+      Task* dT = (Task*)dalloc(nT * sizeof(Task)); Token* dK = (Token*)dalloc(nK * sizeof(Token)); int32_t* dL = (int32_t*)dalloc(nL * 4);
+      int* dR = (int*)dalloc((size_t)(nb + 1) * 4); int* dI = (int*)dalloc((size_t)nb * 4);
+      PathView pv{};
+      pv.JMAX = jmax;
+      int32_t* dIds = (int32_t*)dalloc(ids.size() * 4); int32_t* dPos = (int32_t*)dalloc(pos.size() * 4);
+      pv.ids = dIds; pv.pos = dPos;
+      pv.pe = (float*)dalloc((size_t)nb * jmax * R * Sp * 4);
+      pv.pf = (uint8_t*)dalloc((size_t)nb * jmax * R * T);
+      pv.rootdot = (double*)dalloc((size_t)nb * R * Sp * 8);
+      RootView rb = t->rv;
+      rb.comm.world = 1;
+      rb.elist = (float*)dalloc((size_t)nb * Sp * Kc * RP * 4);
+      rb.kmax = (int*)dalloc((size_t)nb * Sp * 4);
+      rb.act = (int*)dalloc((size_t)nb * Sp * 4);
+      rb.rowoff = (int*)dalloc((size_t)nb * (Sp + 1) * 4);
+      rb.posIncl = (int*)dalloc((size_t)nb * Sp * 4);
+      rb.chunkStart = (int*)dalloc((size_t)nb * (Sp + 2) * 4);
+      rb.cout = (float*)dalloc((size_t)nb * Sp * RP * 4);
+      rb.mxo = (float*)dalloc((size_t)nb * Sp * 4);
+      rb.carryOut = (float*)dalloc((size_t)nb * RMAX * 4);
+      rb.sitell = (double*)dalloc((size_t)nb * Sp * 8);
+      rb.chunk = (double*)dalloc((size_t)nb * T * 8);
+      rb.st = (DevStatus*)dalloc((size_t)nb * sizeof(DevStatus));
+      bool okAlloc = true;
+      for (void* q : tmp) okAlloc &= q != nullptr;
+      if (!okAlloc || tmp.size() != 22) { for (void* q : tmp) if (q) cudaFreeAsync(q, t->stream); return fail(DMPC_ERR_CUDA, "out of device memory for the proposal batch"); }
       CUDA_TRY(cudaMemcpyAsync(dT, pp.tasks.data(), nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
-      if (!pp.tokens.empty()) CUDA_TRY(cudaMemcpyAsync(dK, pp.tokens.data(), pp.tokens.size() * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
-      if (!pp.tipList.empty()) CUDA_TRY(cudaMemcpyAsync(dL, pp.tipList.data(), pp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
-      CUDA_TRY(cudaMemcpyAsync(dR, runStart.data(), (size_t)(nb + 1) * sizeof(int), cudaMemcpyHostToDevice, t->stream));
-      CUDA_TRY(cudaMemsetAsync(dI, 0, (size_t)nb * sizeof(int), t->stream));
-      k_prune_paths<<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, dT, dR, dK, dL, dRoot, dI);
-      k_paths_final<<<dim3((unsigned)nb, (unsigned)t->T), CHUNK, 0, t->stream>>>(t->S, t->Sp, t->R, dRoot, dC);
-      t->st.kernel_launches += 2;
+      if (nK) CUDA_TRY(cudaMemcpyAsync(dK, pp.tokens.data(), nK * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
+      if (nL) CUDA_TRY(cudaMemcpyAsync(dL, pp.tipList.data(), nL * 4, cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(dR, runStart.data(), (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(dIds, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(dPos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, t->stream));
+      CUDA_TRY(cudaMemsetAsync(dI, 0, (size_t)nb * 4, t->stream));
+      CUDA_TRY(cudaMemsetAsync(rb.st, 0, (size_t)nb * sizeof(DevStatus), t->stream));
+      const int mode = chainMode ? 1 : 0;
+      k_prune_paths<<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, dT, dR, dK, dL, pv, dI);
+      if (t->rv.RP == 4) k_root_gather<4, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
+      else k_root_gather<8, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
+      if (chainMode && (rc = launchChain(t, &rb, nb))) return rc;
+      k_final<true><<<dim3((unsigned)t->nChunks, (unsigned)nb), CHUNK, 0, t->stream>>>(t->dv, rb, mode, 1, pv);
+      t->st.kernel_launches += 3;
       CUDA_TRY(cudaGetLastError());
-      chunks.resize((size_t)nb * t->T);
-      invalid.resize(nb);
-      CUDA_TRY(cudaMemcpyAsync(chunks.data(), dC, chunks.size() * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
-      CUDA_TRY(cudaMemcpyAsync(invalid.data(), dI, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+      stat.resize(nb); invalid.resize(nb);
+      CUDA_TRY(cudaMemcpyAsync(stat.data(), rb.st, (size_t)nb * sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
+      CUDA_TRY(cudaMemcpyAsync(invalid.data(), dI, (size_t)nb * 4, cudaMemcpyDeviceToHost, t->stream));
       CUDA_TRY(cudaStreamSynchronize(t->stream));    // also: the pageable host vectors above were the copy sources
-      for (void* q : {(void*)dT, (void*)dK, (void*)dL, (void*)dR, (void*)dI, (void*)dRoot, (void*)dC}) cudaFreeAsync(q, t->stream);
+      for (void* q : tmp) cudaFreeAsync(q, t->stream);
       for (int i = 0; i < nb; i++)
-        if (!invalid[i]) {
-          logLikOut[b0 + i] = dmpc_reduce_chunks(chunks.data() + (size_t)i * t->T, t->T);
-          needSeq[b0 + i] = 0;
+        if (!invalid[i] && stat[i].overflow <= t->rv.Kcap) {
+          logLikOut[member[i]] = stat[i].ll;
+          needSeq[member[i]] = 0;
           nBatched++;
         }
       t->st.updates += (unsigned long long)nT * t->S * t->R;

@@ -305,7 +305,7 @@ struct HostTree {
     while (fused(v)) v = parent[v];
     int prev = -1;
     for (; v != -1; prev = v, v = parent[v]) {
-      Task k = makeTask(v, 0, 0, p, false);
+      Task k = makeTask(v, v - numTips, cur[v], p, false);   // nothing is written: `out` only names the vertex
       if (prev >= 0) {
         if (kids[2 * v] == prev) k.flags = (k.flags & ~TF_C0SLOT) | TF_C0FWD;
         else k.flags = (k.flags & ~TF_C1SLOT) | TF_C1FWD;

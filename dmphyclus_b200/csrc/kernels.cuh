@@ -92,6 +92,36 @@ struct RootView {
   int exactMode;                // the prune kernels ran in exact mode (a raised violation flag is then stale)
 };
 
+// Proposal batches (dmpc_eval_proposals): proposal b differs from the committed state only at the stored vertices of
+// its path to the root.  Their new exponents / tile flags / the new dot(root, pi) live in per-proposal scratch; the
+// batched root kernels (BATCH = true) read those for path vertices and the committed arrays for everything else, and
+// write per-proposal copies of the reduction's work arrays.
+struct PathView {
+  const int32_t* ids;           // [B][JMAX] internal indices of the path vertices, ascending, padded with INT_MAX
+  const int32_t* pos;           // [B][JMAX] position in the run of ids[.]
+  float* pe;                    // [B][JMAX][R][Sp] new exponents (written where the tile flag is set)
+  uint8_t* pf;                  // [B][JMAX][R][T] tile flags
+  double* rootdot;              // [B][R][Sp]
+  int JMAX;
+};
+__device__ __forceinline__ RootView forProposal(RootView rv, int b, int Sp, int T) {
+  const size_t sp = (size_t)Sp;
+  rv.elist += (size_t)b * sp * rv.Kcap * rv.RP;
+  rv.kmax += (size_t)b * sp;
+  rv.act += (size_t)b * sp;
+  rv.rowoff += (size_t)b * (sp + 1);
+  rv.posIncl += (size_t)b * sp;
+  rv.chunkStart += (size_t)b * (sp + 2);
+  rv.cout += (size_t)b * sp * rv.RP;
+  rv.mxo += (size_t)b * sp;
+  rv.carryOut += (size_t)b * RMAX;
+  rv.sitell += (size_t)b * sp;
+  rv.chunk += (size_t)b * T;
+  rv.st += b;
+  rv.comm.world = 1;
+  return rv;
+}
+
 __constant__ double c_P[2][RMAX][16];   // [set][rate][i*4+j], set 0 = between, 1 = within; P(i,j) row-major
 __constant__ double c_pi[4];
 
@@ -369,11 +399,12 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
 // vertices on the path from the vertex it changes up to the root; grid = (proposals, T, R).  The thread walks its
 // run bottom-up with the path partial in registers (TF_CxFWD operands), reading only the off-path siblings (stored
 // partials, tip masks, fused clades) and writing nothing but dot(root, pi) for its (proposal, rate, site).  The
-// committed state is not touched.  Any rescale (or possible rescale inside a fused clade) marks the proposal invalid;
-// the host evaluates those one by one through the ordinary path.
+// committed state is not touched.  The path vertices' new rescale exponents and tile flags go to per-proposal scratch
+// for the batched root reduction; a possible rescale inside a FUSED clade marks the proposal invalid (the host
+// evaluates those one by one through the ordinary path).
 __global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __restrict__ tasks, const int* __restrict__ runStart,
                                                        const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                       double* __restrict__ rootdot, int* __restrict__ invalid) {
+                                                       PathView pv, int* __restrict__ invalid) {
   __shared__ __align__(16) double s_lut[2 * 64];
   __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
   __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
@@ -479,6 +510,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __
     if (fus1) run(n0, n1, 1);
     const double* P = c_P[set][r];
     const double* lutr = s_lut + set * 64;
+    float eu[SPT];
 #pragma unroll
     for (int u = 0; u < SPT; u++) {
       double first[4], second[4], s4[4];
@@ -509,43 +541,31 @@ __global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __
       } else {
         matvec4(P, bb[u], second);
       }
-      float e = 0.0f;
-      combineExact(first, second, s4, e);
-      bad |= e != 0.0f;
+      eu[u] = 0.0f;
+      combineExact(first, second, s4, eu[u]);
 #pragma unroll
       for (int k = 0; k < 4; k++) prev[u][k] = s4[k];
     }
-    if (!plain) __syncthreads();                   // s_mask / s_tok are reused by the next task
+    {
+      // the path vertex's new exponents and tile flag, for the batched root reduction (also fences s_mask / s_tok reuse)
+      bool resc = false;
+#pragma unroll
+      for (int u = 0; u < SPT; u++) resc |= eu[u] != 0.0f;
+      const int any = __syncthreads_or(resc);
+      const int j = ti - runStart[b];
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < SPT; u++) pv.pe[(((size_t)b * pv.JMAX + j) * R + r) * Sp + site0 + u * PT] = eu[u];
+      }
+      if (tid == 0) pv.pf[(((size_t)b * pv.JMAX + j) * R + r) * v.T + tile] = (uint8_t)(any != 0);
+    }
   }
 #pragma unroll
   for (int u = 0; u < SPT; u++)                    // arma::dot: two interleaved accumulators
-    rootdot[((size_t)b * R + r) * Sp + site0 + u * PT] =
+    pv.rootdot[((size_t)b * R + r) * Sp + site0 + u * PT] =
         __dadd_rn(__dadd_rn(__dmul_rn(prev[u][0], c_pi[0]), __dmul_rn(prev[u][2], c_pi[2])),
                   __dadd_rn(__dmul_rn(prev[u][1], c_pi[1]), __dmul_rn(prev[u][3], c_pi[3])));
   if (bad) invalid[b] = 1;
-}
-
-// per (proposal, 256-site chunk): the site terms with a resting exponent vector and their fixed-tree sum
-__global__ void __launch_bounds__(CHUNK) k_paths_final(int S, int Sp, int R, const double* __restrict__ rootdot, double* __restrict__ chunks) {
-  __shared__ double s_red[CHUNK];
-  const int b = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
-  const int s = tile * CHUNK + tid;
-  double ll = 0.0;
-  if (s < S) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int r = 0; r < R; r++) {
-      const double x = __dmul_rn(rootdot[((size_t)b * R + r) * Sp + s], 1.0);
-      if (r & 1) a2 = __dadd_rn(a2, x); else a1 = __dadd_rn(a1, x);
-    }
-    ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)R), 0.0);
-  }
-  s_red[tid] = ll;
-  __syncthreads();
-  for (int d = CHUNK / 2; d > 0; d >>= 1) {
-    if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
-    __syncthreads();
-  }
-  if (tid == 0) chunks[(size_t)b * gridDim.y + tile] = s_red[0];
 }
 
 // rollback: flip the slot bits of the vertices a rejected proposal touched (IntermediateNode.h:26-33)
@@ -646,9 +666,12 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
 // vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
 // the flagged vertices of each 128-vertex window are compacted (in id order) into shared memory, then visited
 // four at a time so that their exponent loads overlap.
-template <int RP>
-__global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, int mode) {
+template <int RP, bool BATCH>
+__global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, int mode, PathView pv) {
+  const int pb = BATCH ? blockIdx.y : 0;           // proposal of a batch
+  const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   __shared__ int s_list[TILE];
+  __shared__ int s_listJ[BATCH ? TILE : 1];
   __shared__ double s_red[TILE];
   __shared__ bool s_last;
   __shared__ int s_wcnt[TILE / 32];
@@ -662,11 +685,15 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
 #pragma unroll
   for (int r = 0; r < RP; r++)
     if (r < R) {
-      double a0, a1, a2, a3;
-      ld256(v.partOf(rootSlot) + ((size_t)r * Sp + site) * 4, a0, a1, a2, a3);
-      // arma::dot (op_dot::direct_dot_arma): two interleaved accumulators
-      rd[r] = __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
-      rv.rootdot[(size_t)r * Sp + site] = rd[r];
+      if (BATCH) {
+        rd[r] = pv.rootdot[((size_t)pb * R + r) * Sp + site];     // k_prune_paths computed it from the proposal's root
+      } else {
+        double a0, a1, a2, a3;
+        ld256(v.partOf(rootSlot) + ((size_t)r * Sp + site) * 4, a0, a1, a2, a3);
+        // arma::dot (op_dot::direct_dot_arma): two interleaved accumulators
+        rd[r] = __dadd_rn(__dadd_rn(__dmul_rn(a0, c_pi[0]), __dmul_rn(a2, c_pi[2])), __dadd_rn(__dmul_rn(a1, c_pi[1]), __dmul_rn(a3, c_pi[3])));
+        rv.rootdot[(size_t)r * Sp + site] = rd[r];
+      }
     }
   int k[RP];
 #pragma unroll
@@ -678,10 +705,22 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
   for (int base = 0; base < v.nReal; base += TILE) {
     const int nd = base + tid;
     int slot = 0, rbits = 0;                     // rates for which this vertex rescaled somewhere in the tile
+    int pj = -1;                                 // BATCH: position in the proposal's run when nd is a path vertex
     if (nd < v.nReal) {
-      slot = v.cur[nd];
-      const uint8_t* fp = (slot ? f1 : f0) + nd;
-      for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
+      if (BATCH) {
+        const int32_t* ids = pv.ids + (size_t)pb * pv.JMAX;
+        int lo = 0, hi = pv.JMAX;                 // first index with ids[.] >= nd
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] < nd) lo = mid + 1; else hi = mid; }
+        if (lo < pv.JMAX && ids[lo] == nd) pj = pv.pos[(size_t)pb * pv.JMAX + lo];
+      }
+      if (pj >= 0) {
+        const uint8_t* fp = pv.pf + (((size_t)pb * pv.JMAX + pj) * R) * v.T + tile;
+        for (int r = 0; r < R; r++) rbits |= (fp[(size_t)r * v.T] != 0) << r;
+      } else {
+        slot = v.cur[nd];
+        const uint8_t* fp = (slot ? f1 : f0) + nd;
+        for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
+      }
     }
     const bool f = rbits != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, f);
@@ -690,7 +729,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
     int off = __popc(bal & ((1u << lane) - 1)), n = 0;
 #pragma unroll
     for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
-    if (f) s_list[off] = (nd << 9) | (slot << 8) | rbits;
+    if (f) { s_list[off] = (nd << 9) | (slot << 8) | rbits; if (BATCH) s_listJ[off] = pj; }
     __syncthreads();
     for (int i = 0; i < n; i += 4) {
       float e[4][RP];
@@ -698,6 +737,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
       for (int j = 0; j < 4; j++) {
         const int ent = s_list[min(i + j, n - 1)];
         const float* src = v.expoOf((ent >> 8) & 1) + (size_t)(ent >> 9) * R * Sp + site;
+        if (BATCH) { const int qj = s_listJ[min(i + j, n - 1)]; if (qj >= 0) src = pv.pe + (((size_t)pb * pv.JMAX + qj) * R) * Sp + site; }
 #pragma unroll
         for (int r = 0; r < RP; r++) e[j][r] = (((ent >> r) & 1) && i + j < n) ? src[r * Sp] : 0.0f;   // unflagged rows were never written
       }
@@ -791,8 +831,9 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv, in
 // handed to the later ranks (CommView).
 // G = rows per group (4 for long lists, 1 when most rescaled sites hold a single row): a site's rows are padded to a
 // multiple of G with zero rows, the walker tests for the end of a site once per group.
-template <int RP, int RC, int G>
-__global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
+template <int RP, int RC, int G, bool BATCH>
+__global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv0) {
+  const RootView rv = BATCH ? forProposal(rv0, blockIdx.x, v.Sp, v.T) : rv0;   // BATCH: one block per proposal
   extern __shared__ float4 s_dyn[];
   constexpr int V = RP / 4;                       // float4 per row
   __shared__ int s_scan[2][32];
@@ -996,7 +1037,11 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv) {
 // each 256-site chunk, chunk sums combined by reduce_chunks order (identical on host for the multi-GPU path).
 // mode 1: exponent vectors come from the chain; mode 0: each site folds its own list from zero (numRateCats == 1,
 // where the carry is always exactly zero, or the textbook reduction).
-__global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mode, int reduceAll) {
+template <bool BATCH>
+__global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv0, int mode, int reduceAll, PathView pv) {
+  const int pb = BATCH ? blockIdx.y : 0;
+  const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
+  const double* const rootdot = BATCH ? pv.rootdot + (size_t)pb * v.R * v.Sp : rv.rootdot;
   __shared__ double s_red[CHUNK];
   __shared__ bool s_last;
   const int s = blockIdx.x * CHUNK + threadIdx.x;
@@ -1031,7 +1076,7 @@ __global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv, int mod
     for (int r = 0; r < RMAX; r++)
       if (r < v.R) {
         const double w = (double)(float)exp((double)ev[r]);   // correctly rounded expf
-        const double x = __dmul_rn(rv.rootdot[(size_t)r * v.Sp + s], w);
+        const double x = __dmul_rn(rootdot[(size_t)r * v.Sp + s], w);
         if (r & 1) a2 = __dadd_rn(a2, x); else a1 = __dadd_rn(a1, x);
       }
     ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)v.R), (double)mx);
