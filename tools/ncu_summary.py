@@ -69,23 +69,25 @@ def main():
                "| kernel | launches | total us | share | avg us |", "|---|---|---|---|---|"]
         for k, (c, t) in tot.items():
             md.append(f"| {k} | {c} | {t / 1e3:.1f} | {100 * t / all_ns:.1f}% | {t / c / 1e3:.2f} |")
-        # one evaluation = from one k_final to the next
+        # one evaluation = from one root reduction to the next (k_final when something rescaled, else k_root_gather)
         finals = [i for i, l in enumerate(ls) if l[1].startswith("k_final")]
+        if len(finals) < 3:
+            finals = [i for i, l in enumerate(ls) if l[1].startswith("k_root_gather")]
         if len(finals) >= 3:
             seg = ls[finals[1] + 1:finals[2] + 1]
-            md += ["", "One evaluation (between two consecutive `k_final` launches):", "",
+            md += ["", "One evaluation (between two consecutive root reductions):", "",
                    "| kernel | grid | us |", "|---|---|---|"]
             for _, k, g, _, ns in seg:
                 md.append(f"| {k} | {g} | {ns / 1e3:.2f} |")
             st = sum(x[4] for x in seg)
             pr = sum(x[4] for x in seg if x[1].startswith("k_prune"))
-            md += ["", f"evaluation total {st / 1e3:.1f} us, of which k_prune_level {pr / 1e3:.1f} us = {100 * pr / st:.1f}%"]
+            md += ["", f"evaluation total {st / 1e3:.1f} us, of which k_prune {pr / 1e3:.1f} us = {100 * pr / st:.1f}%"]
     if a.bench and os.path.exists(a.bench):
         b = json.load(open(a.bench))
         r = b["roofline"]
         md += ["", "Live (CUDA events, `bench.py`, not under ncu):", "",
                f"* value {b['value']:.4g} {b['unit']}, {b['ms_per_step']:.4f} ms/step; e2e {b['e2e']['value']:.4g} ({b['e2e']['ms_per_step']:.3f} ms/step)",
-               f"* k_prune_level {r['kernel_ms_per_step']:.4f} ms/step = {100 * r['kernel_share_of_step']:.1f}% of the step; "
+               f"* k_prune {r['kernel_ms_per_step']:.4f} ms/step = {100 * r['kernel_share_of_step']:.1f}% of the step; "
                f"achieved {r['achieved']:.0f} GB/s = {r['frac']:.3f} of {r['peak']} GB/s ({r['peak_source']})",
                f"* clocks {b['clocks']}"]
     if a.report:
