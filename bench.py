@@ -168,6 +168,8 @@ def time_cpu(be, p, n_sites, reps=1):
         t0 = time.perf_counter()
         res = be.logLikCpp(p.edge, p.mrcas, p.pi, p.W[p.w_idx - 1], p.B[p.b_idx - 1], 1, al, p.n, n_sites, p.w_idx, p.b_idx)
         dt = time.perf_counter() - t0
+        if hasattr(be, "dictionary_size"):      # the reference memoises (node, site) solutions: how many were distinct
+            time_cpu.dictionary = be.dictionary_size(res["solutionPointer"])
         be.finalDeallocate(res["solutionPointer"])
         best = dt if best is None else min(best, dt)
     return best, res["logLik"]
@@ -192,12 +194,15 @@ def run_reference(args, rank, world):
     upd = (n - 1) * ns * r
     val = upd * args.steps / dt
     sample = f"first {ns} of {s} sites, all {n} tips, one logLikCpp per step (tree build + dictionary fill + pruning + reduction)"
+    lookups = (2 * n - 1) * ns
+    memo = getattr(time_cpu, "dictionary", None)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(args, n, s, k, r, 1),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                             "host_cores": os.cpu_count(),
+                            "dictionary_entries": memo, "dictionary_hit_rate": (1.0 - memo / lookups) if memo else None,
                             "note": "the reference's likelihood is single-threaded (OpenMP commented out, "
                                     "clusterFunArmadillo.cpp:4,38); it cannot use more host threads"},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -478,9 +483,11 @@ def cpu_baseline(p, n, s, r):
     be, kind = cpu_reference_backend()
     ns = min(s, 5000)
     dt, _ = time_cpu(be, p, ns)
+    memo = getattr(time_cpu, "dictionary", None)
     out = {"value": (n - 1) * ns * r / dt, "unit": UNIT, "cores": 1, "kind": kind,
            "sample": f"first {ns} of {s} sites, all {n} tips, one logLikCpp ({dt:.1f} s of CPU work)",
-           "host_cores": os.cpu_count()}
+           "host_cores": os.cpu_count(),
+           "dictionary_entries": memo, "dictionary_hit_rate": (1.0 - memo / ((2 * n - 1) * ns)) if memo else None}
     # the dense oracle port: 1 thread, and OpenMP over sites on every host core (what numLikThreads advertised)
     dt1, _ = time_cpu(Oracle(threads=1), p, s)
     nthr = os.cpu_count() or 1

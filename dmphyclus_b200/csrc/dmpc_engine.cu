@@ -266,6 +266,9 @@ int uploadConstants(dmpc_tree* t, const double* within, const double* between, c
 // constants are per-module: a second handle on the same device may have overwritten them
 std::mutex g_constMutex;
 dmpc_tree* g_constOwner[64] = {nullptr};
+// ... and because they are, evaluations of different handles on one device must not overlap: every call that launches
+// kernels holds the device's lock until its results are back (calls are synchronous anyway)
+std::mutex g_deviceMutex[64];
 
 int rootStage(dmpc_tree* t, double* ll);
 int launchGather(dmpc_tree* t, int mode);
@@ -318,6 +321,7 @@ int runPlan(dmpc_tree* t) {
 // ComputeLoglik (AugTree.cpp:289-326): prune the dirty levels, then reduce at the root.
 int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll) {
   int rc;
+  std::lock_guard<std::mutex> deviceLock(g_deviceMutex[t->device & 63]);
   if ((rc = ensureDevice(t))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_constMutex);
