@@ -283,8 +283,10 @@ int recordEv(dmpc_tree* t, int i) {
 }
 
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
-  if (t->exact) k_prune<true><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);
-  else k_prune<false><<<grid, PT, 0, t->stream>>>(t->dv, lt, nTasks, t->runTokens, t->runTips, &t->rv.st->violation, t->runFlip);
+  PruneArgs a{};
+  a.tasks = lt; a.nTasks = nTasks; a.prog = t->runTokens; a.tipList = t->runTips; a.violation = &t->rv.st->violation; a.flip = t->runFlip;
+  if (t->exact) k_prune<true, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
+  else k_prune<false, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
   return DMPC_OK;
 }
 
@@ -926,7 +928,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
   if ((rc = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return rc;
   int nBatched = 0;
   std::vector<uint8_t> needSeq(nProps, 1);
-  // Batched path: per proposal, the path to the root is walked with the partial in registers (k_prune_paths), then the
+  // Batched path: per proposal, the path to the root is walked with the partial in registers (k_prune<false, true>), then the
   // ordinary root reduction runs on per-proposal copies of its work arrays, reading the proposal's exponents for path
   // vertices and the committed ones for everything else.  Exact-mode handles (fused clades that may rescale) and
   // proposals that trip the fused-clade test or overflow the exponent lists go one by one below.
@@ -1025,7 +1027,11 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       CUDA_TRY(cudaMemsetAsync(dI, 0, (size_t)nb * 4, t->stream));
       CUDA_TRY(cudaMemsetAsync(rb.st, 0, (size_t)nb * sizeof(DevStatus), t->stream));
       const int mode = chainMode ? 1 : 0;
-      k_prune_paths<<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, dT, dR, dK, dL, pv, dI);
+      {
+        PruneArgs a{};
+        a.tasks = dT; a.prog = dK; a.tipList = dL; a.runStart = dR; a.invalid = dI; a.pv = pv;
+        k_prune<false, true><<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, a);
+      }
       if (t->rv.RP == 4) k_root_gather<4, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
       else k_root_gather<8, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
       if (chainMode && (rc = launchChain(t, &rb, nb))) return rc;

@@ -190,12 +190,32 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
   }
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restrict__ tasks, int nTasks,
-                                                 const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                 int* violation, int flip) {
-  // `flip` (0/1) is XORed into every slot bit of the tasks and tokens: a cached full-evaluation plan is replayed with
-  // all slots toggled instead of being rebuilt and uploaded again
+// PATHS = true is K3, the proposal-batch variant (dmpc_eval_proposals): blockIdx.x is a PROPOSAL, whose run of tasks —
+// the stored vertices on the path from the vertex it changes up to the root — the block walks bottom-up with the path
+// partial in registers (TF_CxFWD operands), reading only the off-path siblings (stored partials, tip masks, fused
+// clades) and writing nothing to the committed state: the path vertices' new rescale exponents and tile flags go to
+// per-proposal scratch for the batched root reduction, and dot(root, pi) for its (proposal, rate, site).  A possible
+// rescale inside a FUSED clade marks the proposal invalid (the host evaluates those one by one).
+struct PruneArgs {
+  const Task* tasks;
+  int nTasks;
+  const Token* prog;
+  const int32_t* tipList;
+  int* violation;               // fast mode: raised when a fused clade may have rescaled
+  int flip;                     // 0/1, XORed into every slot bit of the tasks and tokens: a cached full-evaluation plan is
+                                // replayed with all slots toggled instead of being rebuilt and uploaded again
+  const int* runStart;          // PATHS: [proposals + 1] task ranges
+  int* invalid;                 // PATHS: [proposals]
+  PathView pv;                  // PATHS: per-proposal outputs
+};
+
+template <bool EXACT, bool PATHS>
+__global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
+  static_assert(!(EXACT && PATHS), "proposal batches run in fast mode only");
+  const Task* __restrict__ tasks = pa_.tasks;
+  const Token* __restrict__ prog = pa_.prog;
+  const int32_t* __restrict__ tipList = pa_.tipList;
+  const int flip = PATHS ? 0 : pa_.flip;
   // one thread = SPT sites (tid, tid + PT, ...) of one rate: what is uniform across the block — token decoding, the
   // P matrix elements, addresses — is paid once per SPT updates
   __shared__ __align__(16) double s_lut[2 * 64];                 // [set][mask][4] of this block's rate
@@ -208,14 +228,19 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
   bool lutLoaded = false, trig = false;
+  double prev[PATHS ? SPT : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
+  const int tiBegin = PATHS ? pa_.runStart[blockIdx.x] : (int)blockIdx.x;
+  const int tiEnd = PATHS ? pa_.runStart[blockIdx.x + 1] : pa_.nTasks;
+  const int tiStep = PATHS ? 1 : (int)gridDim.x;
 
-  for (int ti = blockIdx.x; ti < nTasks; ti += gridDim.x) {
+  for (int ti = tiBegin; ti < tiEnd; ti += tiStep) {
     const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
     const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
     const int fl = tk0.w ^ (flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0);
     const int set = (fl & TF_WITHIN) ? 1 : 0;
     const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
     const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
+    const bool fwd0 = PATHS && (fl & TF_C0FWD) != 0, fwd1 = PATHS && (fl & TF_C1FWD) != 0;
     const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site0) * 4;
     const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site0) * 4;
     const bool plain = !(fus0 | fus1);
@@ -226,9 +251,9 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
 #pragma unroll
     for (int u = 0; u < SPT; u++) {
       if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT];
-      else if (!fus0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
+      else if (!fus0 && !fwd0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
       if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT];
-      else if (!fus1) ld256(pb + (size_t)u * PT * 4, b[u][0], b[u][1], b[u][2], b[u][3]);
+      else if (!fus1 && !fwd1) ld256(pb + (size_t)u * PT * 4, b[u][0], b[u][1], b[u][2], b[u][3]);
     }
     if (!plain) {
       // the masks of every tip the programs read (4 sites per cp.async) and the tokens themselves, into shared memory
@@ -333,7 +358,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
       }
     }
     if (fus1) run(n0, n1, 1);
-    if (!plain && tid < ntok) {
+    if (!PATHS && !plain && tid < ntok) {
       // bookkeeping of the fused vertices, one token per thread: current slot, and (fast mode) "nothing rescaled"
       const int4 t4 = s_tok[tid];
       if ((t4.x & 7) != OP_SPILL) {
@@ -365,169 +390,8 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, const Task* __restri
         } else {
           matvec4(P, reg[u], first);
         }
-      } else {
-        matvec4(P, a[u], first);
-      }
-      if (tip1) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) second[k] = lutr[4 * mb[u] + k];
-      } else if (fus1) {
-        matvec4(P, reg[u], second);
-      } else {
-        matvec4(P, b[u], second);
-      }
-      e[u] = 0.0f;
-      combineExact(first, second, s4, e[u]);
-      st256(v.partOf(os) + (o + (size_t)u * PT) * 4, s4[0], s4[1], s4[2], s4[3]);
-      rescaled |= e[u] != 0.0f;
-    }
-    const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_tok / s_stack reuse by the next task of a run
-    if (any) {
-#pragma unroll
-      for (int u = 0; u < SPT; u++) v.expoOf(os)[o + (size_t)u * PT] = e[u];
-    }
-    if (tid == 0) {
-      v.flagOf(os)[flagRow + tk0.x] = (uint8_t)(any != 0);
-      if (tile == 0 && r == 0) v.cur[tk0.x] = (uint8_t)os;
-    }
-  }
-  if (!EXACT && trig) *violation = 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3 prune_paths: a BATCH of proposals per launch (dmpc_eval_proposals).  Proposal b is a run of tasks — the stored
-// vertices on the path from the vertex it changes up to the root; grid = (proposals, T, R).  The thread walks its
-// run bottom-up with the path partial in registers (TF_CxFWD operands), reading only the off-path siblings (stored
-// partials, tip masks, fused clades) and writing nothing but dot(root, pi) for its (proposal, rate, site).  The
-// committed state is not touched.  The path vertices' new rescale exponents and tile flags go to per-proposal scratch
-// for the batched root reduction; a possible rescale inside a FUSED clade marks the proposal invalid (the host
-// evaluates those one by one through the ordinary path).
-__global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __restrict__ tasks, const int* __restrict__ runStart,
-                                                       const Token* __restrict__ prog, const int32_t* __restrict__ tipList,
-                                                       PathView pv, int* __restrict__ invalid) {
-  __shared__ __align__(16) double s_lut[2 * 64];
-  __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
-  __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
-  __shared__ __align__(16) int4 s_tok[3 * FUSE_MAX_TIPS + 4];
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x, tile = blockIdx.y, r = blockIdx.z, R = v.R;
-  const int site0 = tile * TILE + tid;
-  const size_t Sp = (size_t)v.Sp;
-  bool bad = false;
-  s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];       // PT == 2 * 64
-  __syncthreads();
-  double prev[SPT][4];
-#pragma unroll
-  for (int u = 0; u < SPT; u++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) prev[u][k] = 0.0;
-
-  for (int ti = runStart[b]; ti < runStart[b + 1]; ti++) {
-    const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
-    const int4 tk1 = __ldg(reinterpret_cast<const int4*>(tasks + ti) + 1);
-    const int fl = tk0.w;
-    const int set = (fl & TF_WITHIN) ? 1 : 0;
-    const bool tip0 = (fl & TF_C0TIP) != 0, tip1 = (fl & TF_C1TIP) != 0;
-    const bool fus0 = (fl & TF_C0FUSED) != 0, fus1 = (fl & TF_C1FUSED) != 0;
-    const bool fwd0 = (fl & TF_C0FWD) != 0, fwd1 = (fl & TF_C1FWD) != 0;
-    const double* pa = v.partOf(fl & TF_C0SLOT) + (((size_t)tk0.y * R + r) * Sp + site0) * 4;
-    const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site0) * 4;
-    const bool plain = !(fus0 | fus1);
-    const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff, ntok = n0 + n1;
-    unsigned ma[SPT], mb[SPT];
-    double a[SPT][4], bb[SPT][4];
-#pragma unroll
-    for (int u = 0; u < SPT; u++) {
-      if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT];
-      else if (!fus0 && !fwd0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
-      if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT];
-      else if (!fus1 && !fwd1) ld256(pb + (size_t)u * PT * 4, bb[u][0], bb[u][1], bb[u][2], bb[u][3]);
-    }
-    if (!plain) {
-      const int nTips = tk1.w;
-      for (int j = tid; j < nTips * (TILE / 4); j += PT) {
-        const int tipIdx = j / (TILE / 4), q = j - tipIdx * (TILE / 4);
-        const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + tipIdx) * Sp + tile * TILE + 4 * q;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + tipIdx * TILE + 4 * q);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (tid < ntok) s_tok[tid] = __ldg(reinterpret_cast<const int4*>(prog + tk1.x + tid));
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-    }
-    double reg[SPT][4];
-    auto run = [&](int first, int n, int sp) {
-      for (int i = first; i < first + n; i++) {
-        const int4 t4 = s_tok[i];
-        const int op = t4.x & 7;
-        if (op == OP_SPILL) {
-#pragma unroll
-          for (int u = 0; u < SPT; u++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid + u * PT] = reg[u][k];
-          sp++;
-          continue;
-        }
-        const int tset = (t4.x & TOK_SET) ? 1 : 0;
-        const double* P = c_P[tset][r];
-        const double* lutr = s_lut + tset * 64;
-        if (op == OP_SLOTREG) sp--;
-#pragma unroll
-        for (int u = 0; u < SPT; u++) {
-          double x[4], y[4];
-          if (op == OP_CHERRY) {
-            const unsigned m0 = s_mask[t4.y * TILE + tid + u * PT], m1 = s_mask[t4.z * TILE + tid + u * PT];
-#pragma unroll
-            for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
-          } else if (op == OP_REGTIP) {
-            const unsigned m1 = s_mask[t4.z * TILE + tid + u * PT];
-            matvec4(P, reg[u], x);
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
-          } else {
-            double z[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid + u * PT];
-            matvec4(P, z, x);
-            matvec4(P, reg[u], y);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) reg[u][k] = __dmul_rn(x[k], y[k]);
-          bad |= maybeBelow4(reg[u]);
-        }
-      }
-    };
-    if (fus0) {
-      run(0, n0, 0);
-      if (fus1) {
-#pragma unroll
-        for (int u = 0; u < SPT; u++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) s_stack[k * TILE + tid + u * PT] = reg[u][k];
-      }
-    }
-    if (fus1) run(n0, n1, 1);
-    const double* P = c_P[set][r];
-    const double* lutr = s_lut + set * 64;
-    float eu[SPT];
-#pragma unroll
-    for (int u = 0; u < SPT; u++) {
-      double first[4], second[4], s4[4];
-      if (tip0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) first[k] = lutr[4 * ma[u] + k];
-      } else if (fus0) {
-        if (fus1) {
-          double z[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid + u * PT];
-          matvec4(P, z, first);
-        } else {
-          matvec4(P, reg[u], first);
-        }
       } else if (fwd0) {
-        matvec4(P, prev[u], first);
+        matvec4(P, prev[PATHS ? u : 0], first);
       } else {
         matvec4(P, a[u], first);
       }
@@ -537,36 +401,53 @@ __global__ void __launch_bounds__(PT, 5) k_prune_paths(DevView v, const Task* __
       } else if (fus1) {
         matvec4(P, reg[u], second);
       } else if (fwd1) {
-        matvec4(P, prev[u], second);
+        matvec4(P, prev[PATHS ? u : 0], second);
       } else {
-        matvec4(P, bb[u], second);
+        matvec4(P, b[u], second);
       }
-      eu[u] = 0.0f;
-      combineExact(first, second, s4, eu[u]);
+      e[u] = 0.0f;
+      combineExact(first, second, s4, e[u]);
+      if (PATHS) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) prev[u][k] = s4[k];
+        for (int k = 0; k < 4; k++) prev[PATHS ? u : 0][k] = s4[k];
+      } else {
+        st256(v.partOf(os) + (o + (size_t)u * PT) * 4, s4[0], s4[1], s4[2], s4[3]);
+      }
+      rescaled |= e[u] != 0.0f;
     }
-    {
-      // the path vertex's new exponents and tile flag, for the batched root reduction (also fences s_mask / s_tok reuse)
-      bool resc = false;
-#pragma unroll
-      for (int u = 0; u < SPT; u++) resc |= eu[u] != 0.0f;
-      const int any = __syncthreads_or(resc);
-      const int j = ti - runStart[b];
+    const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_tok / s_stack reuse by the next task of a run
+    if (PATHS) {
+      const PathView& pv = pa_.pv;
+      const size_t row = ((size_t)blockIdx.x * pv.JMAX + (ti - tiBegin)) * R + r;
       if (any) {
 #pragma unroll
-        for (int u = 0; u < SPT; u++) pv.pe[(((size_t)b * pv.JMAX + j) * R + r) * Sp + site0 + u * PT] = eu[u];
+        for (int u = 0; u < SPT; u++) pv.pe[row * Sp + site0 + u * PT] = e[u];
       }
-      if (tid == 0) pv.pf[(((size_t)b * pv.JMAX + j) * R + r) * v.T + tile] = (uint8_t)(any != 0);
+      if (tid == 0) pv.pf[row * v.T + tile] = (uint8_t)(any != 0);
+    } else {
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < SPT; u++) v.expoOf(os)[o + (size_t)u * PT] = e[u];
+      }
+      if (tid == 0) {
+        v.flagOf(os)[flagRow + tk0.x] = (uint8_t)(any != 0);
+        if (tile == 0 && r == 0) v.cur[tk0.x] = (uint8_t)os;
+      }
     }
   }
+  if (PATHS) {
 #pragma unroll
-  for (int u = 0; u < SPT; u++)                    // arma::dot: two interleaved accumulators
-    pv.rootdot[((size_t)b * R + r) * Sp + site0 + u * PT] =
-        __dadd_rn(__dadd_rn(__dmul_rn(prev[u][0], c_pi[0]), __dmul_rn(prev[u][2], c_pi[2])),
-                  __dadd_rn(__dmul_rn(prev[u][1], c_pi[1]), __dmul_rn(prev[u][3], c_pi[3])));
-  if (bad) invalid[b] = 1;
+    for (int u = 0; u < SPT; u++)                  // arma::dot: two interleaved accumulators
+      pa_.pv.rootdot[((size_t)blockIdx.x * R + r) * Sp + site0 + u * PT] =
+          __dadd_rn(__dadd_rn(__dmul_rn(prev[PATHS ? u : 0][0], c_pi[0]), __dmul_rn(prev[PATHS ? u : 0][2], c_pi[2])),
+                    __dadd_rn(__dmul_rn(prev[PATHS ? u : 0][1], c_pi[1]), __dmul_rn(prev[PATHS ? u : 0][3], c_pi[3])));
+    if (trig) pa_.invalid[blockIdx.x] = 1;
+  } else if (!EXACT && trig) {
+    *pa_.violation = 1;
+  }
 }
+
+
 
 // rollback: flip the slot bits of the vertices a rejected proposal touched (IntermediateNode.h:26-33)
 __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
@@ -686,7 +567,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   for (int r = 0; r < RP; r++)
     if (r < R) {
       if (BATCH) {
-        rd[r] = pv.rootdot[((size_t)pb * R + r) * Sp + site];     // k_prune_paths computed it from the proposal's root
+        rd[r] = pv.rootdot[((size_t)pb * R + r) * Sp + site];     // k_prune<., PATHS> computed it from the proposal's root
       } else {
         double a0, a1, a2, a3;
         ld256(v.partOf(rootSlot) + ((size_t)r * Sp + site) * 4, a0, a1, a2, a3);
