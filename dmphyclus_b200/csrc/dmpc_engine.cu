@@ -294,24 +294,30 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
 int runPlan(dmpc_tree* t) {
   const HostTree::Plan& p = *t->runPlanMeta;
   const int nLevels = (int)p.levelStart.size() - 1;
-  if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 8.3M)");
+  if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 16.7M)");
   int rcE;
   if ((rcE = recordEv(t, 0))) return rcE;
   int launches = 0;
   for (int l = 0; l < nLevels;) {
     int n = p.levelStart[l + 1] - p.levelStart[l];
     const Task* lt = t->runTasks + p.levelStart[l];
-    // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.x == 1)
+    // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.z == 1)
     int l2 = l + 1;
     bool run = n <= NARROW_LEVEL;
     if (run) while (l2 < nLevels && p.levelStart[l2 + 1] - p.levelStart[l2] <= NARROW_LEVEL) l2++;
     if (run && l2 > l + 1) n = p.levelStart[l2] - p.levelStart[l]; else { run = false; l2 = l + 1; }
-    const dim3 grid(run ? 1u : (unsigned)n, (unsigned)t->T, (unsigned)t->R);
-    int rc = launchPrune(t, grid, lt, n);
-    if (rc) return rc;
+    // grid = (rate, site tile, task): blocks that share a task's masks and tokens are scheduled next to each other;
+    // gridDim.z is limited to 65535, wider levels go out in slices
+    for (int off = 0; off < n; off += 65535) {
+      const int m = run ? n : std::min(65535, n - off);
+      const dim3 grid((unsigned)t->R, (unsigned)t->T, run ? 1u : (unsigned)m);
+      int rc = launchPrune(t, grid, lt + off, m);
+      if (rc) return rc;
+      t->st.kernel_launches++;
+      launches++;
+      if (run) break;
+    }
     l = l2;
-    t->st.kernel_launches++;
-    launches++;
   }
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
   if ((rcE = recordEv(t, 1))) return rcE;
@@ -971,7 +977,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
         const int jm = std::max(jmax, len);
         const size_t per = (size_t)jm * R * Sp * 4 + (size_t)jm * R * T + R * Sp * 8 +            // pe, pf, rootdot
                            Sp * Kc * RP * 4 + Sp * (4 * 4 + 4 + 8) + Sp * RP * 4 + T * 8 + 256;    // root work arrays
-        if (!member.empty() && per * (member.size() + 1) > ((size_t)3 << 30)) { pp.tasks.resize(before); b0 = i; break; }
+        if (!member.empty() && (per * (member.size() + 1) > ((size_t)3 << 30) || member.size() >= 65535)) { pp.tasks.resize(before); b0 = i; break; }
         jmax = jm; bytes = per * (member.size() + 1);
         member.push_back(i);
         runStart.push_back((int)pp.tasks.size());
@@ -1030,7 +1036,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       {
         PruneArgs a{};
         a.tasks = dT; a.prog = dK; a.tipList = dL; a.runStart = dR; a.invalid = dI; a.pv = pv;
-        k_prune<false, true><<<dim3((unsigned)nb, (unsigned)t->T, (unsigned)t->R), PT, 0, t->stream>>>(t->dv, a);
+        k_prune<false, true><<<dim3((unsigned)t->R, (unsigned)t->T, (unsigned)nb), PT, 0, t->stream>>>(t->dv, a);
       }
       if (t->rv.RP == 4) k_root_gather<4, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
       else k_root_gather<8, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
@@ -1196,7 +1202,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
       std::memcpy(t->h_tipList, rp.tipList.data(), rp.tipList.size() * sizeof(int32_t));
       CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, rp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
     }
-    const dim3 grid(1, (unsigned)t->T, (unsigned)t->R);
+    const dim3 grid((unsigned)t->R, (unsigned)t->T, 1);
     t->runTokens = t->d_tokens; t->runTips = t->d_tipList; t->runFlip = 0;
     rc = launchPrune(t, grid, t->d_tasks, 1);
     if (rc) return rc;

@@ -141,7 +141,7 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
 // ------------------------------------------------------------------------------------------------
 // K2 prune: the dirty STORED vertices of one level x all sites x all rate categories.
 // Replaces IntermediateNode::ComputeSolutions/ComputeSolution (IntermediateNode.cpp:26-71) driven by
-// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (tasks of the level, 256-site tiles, R), 128 threads; one
+// AugTree::TrySolve (AugTree.cpp:114-134).  grid = (R, 256-site tiles, tasks of the level), 128 threads; one
 // thread owns two sites of one rate of its task: 256-bit child loads (or mask bytes), `sol = (P c0) % (P c1)` with
 // products and sums rounded separately in Armadillo's order, the reference's two rescale checks, 256-bit stores.
 //
@@ -158,7 +158,7 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
 // evaluation with EXACT = true, where every fused vertex gets the reference's full two-check treatment, a
 // block vote, and exponent rows — and keeps that mode for the handle.
 //
-// A launch covers one level (gridDim.x = its tasks) or, with gridDim.x == 1, a run of narrow levels whose tasks
+// A launch covers one level (gridDim.z = its tasks) or, with gridDim.z == 1, a run of narrow levels whose tasks
 // each block walks in order: a thread only ever reads partials of its own (site, rate), so the child -> parent
 // dependencies inside the run are plain program order.
 __device__ __forceinline__ void matvec4(const double* __restrict__ P, const double (&x)[4], double (&y)[4]) {
@@ -190,7 +190,7 @@ __device__ __forceinline__ void combineExact(const double (&first)[4], const dou
   }
 }
 
-// PATHS = true is K3, the proposal-batch variant (dmpc_eval_proposals): blockIdx.x is a PROPOSAL, whose run of tasks —
+// PATHS = true is K3, the proposal-batch variant (dmpc_eval_proposals): blockIdx.z is a PROPOSAL, whose run of tasks —
 // the stored vertices on the path from the vertex it changes up to the root — the block walks bottom-up with the path
 // partial in registers (TF_CxFWD operands), reading only the off-path siblings (stored partials, tip masks, fused
 // clades) and writing nothing to the committed state: the path vertices' new rescale exponents and tile flags go to
@@ -223,15 +223,15 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
   __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
   __shared__ __align__(16) int4 s_tok[3 * FUSE_MAX_TIPS + 4];
   const int tid = threadIdx.x;
-  const int tile = blockIdx.y, r = blockIdx.z, R = v.R;
+  const int tile = blockIdx.y, r = blockIdx.x, R = v.R;
   const int site0 = tile * TILE + tid;
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
   bool lutLoaded = false, trig = false;
   double prev[PATHS ? SPT : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
-  const int tiBegin = PATHS ? pa_.runStart[blockIdx.x] : (int)blockIdx.x;
-  const int tiEnd = PATHS ? pa_.runStart[blockIdx.x + 1] : pa_.nTasks;
-  const int tiStep = PATHS ? 1 : (int)gridDim.x;
+  const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : (int)blockIdx.z;
+  const int tiEnd = PATHS ? pa_.runStart[blockIdx.z + 1] : pa_.nTasks;
+  const int tiStep = PATHS ? 1 : (int)gridDim.z;
 
   for (int ti = tiBegin; ti < tiEnd; ti += tiStep) {
     const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
     const int any = __syncthreads_or(rescaled);      // also fences s_mask / s_tok / s_stack reuse by the next task of a run
     if (PATHS) {
       const PathView& pv = pa_.pv;
-      const size_t row = ((size_t)blockIdx.x * pv.JMAX + (ti - tiBegin)) * R + r;
+      const size_t row = ((size_t)blockIdx.z * pv.JMAX + (ti - tiBegin)) * R + r;
       if (any) {
 #pragma unroll
         for (int u = 0; u < SPT; u++) pv.pe[row * Sp + site0 + u * PT] = e[u];
@@ -438,10 +438,10 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
   if (PATHS) {
 #pragma unroll
     for (int u = 0; u < SPT; u++)                  // arma::dot: two interleaved accumulators
-      pa_.pv.rootdot[((size_t)blockIdx.x * R + r) * Sp + site0 + u * PT] =
+      pa_.pv.rootdot[((size_t)blockIdx.z * R + r) * Sp + site0 + u * PT] =
           __dadd_rn(__dadd_rn(__dmul_rn(prev[PATHS ? u : 0][0], c_pi[0]), __dmul_rn(prev[PATHS ? u : 0][2], c_pi[2])),
                     __dadd_rn(__dmul_rn(prev[PATHS ? u : 0][1], c_pi[1]), __dmul_rn(prev[PATHS ? u : 0][3], c_pi[3])));
-    if (trig) pa_.invalid[blockIdx.x] = 1;
+    if (trig) pa_.invalid[blockIdx.z] = 1;
   } else if (!EXACT && trig) {
     *pa_.violation = 1;
   }
