@@ -120,6 +120,7 @@ struct dmpc_tree {
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
+  int pendingCur = 0;            // slot bits of a rollback that the device has not seen yet (h_curList)
   dmpc_comm* comm = nullptr;
   int chainGroup = 4;            // rows per group of the chain walker: 4 for long exponent lists, 1 for sparse ones
   int lastNact = 0;
@@ -193,6 +194,20 @@ void releasePack(dmpc_tree* t) {
   g_ctx[t->device & 63].freePacks.push_back(t->pack);
   t->pack = ResPack{};
   t->stream = nullptr;
+}
+
+// RestoreIterVecAndExp (IntermediateNode.h:26-33): the vertices the last proposal touched go back to their previous slot.
+// The host state flips at once; the device copy of the slot bits (only the root reduction reads it) is brought up to date
+// by the next call that launches kernels, so that a reject costs no launch and no synchronisation of its own.
+int flushCur(dmpc_tree* t) {
+  if (!t->pendingCur) return DMPC_OK;
+  const int n = t->pendingCur;
+  t->pendingCur = 0;
+  CUDA_TRY(cudaMemcpyAsync(t->d_curList, t->h_curList, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+  k_set_cur<<<(n + 255) / 256, 256, 0, t->stream>>>(t->dv.cur, t->d_curList, n);
+  t->st.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
 }
 
 int ensureDevice(dmpc_tree* t) {
@@ -331,6 +346,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   int rc;
   std::lock_guard<std::mutex> deviceLock(g_deviceMutex[t->device & 63]);
   if ((rc = ensureDevice(t))) return rc;
+  if ((rc = flushCur(t))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_constMutex);
     if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
@@ -839,9 +855,13 @@ int dmpc_clus_split_merge_loglik(dmpc_tree* t, const double* withinTransMats, co
   return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
 }
 
-// RestoreIterVecAndExp (IntermediateNode.h:26-33): the vertices the last proposal touched go back to their previous slot
 static int rollbackTouched(dmpc_tree* t) {
   HostTree& ht = t->ht;
+  if (t->pendingCur) {                            // two rollbacks in a row: the pinned list is still waiting to be uploaded
+    int rc = flushCur(t);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+  }
   int n = 0;
   for (int v = ht.numTips; v < ht.numVerts; v++)
     if (ht.touched[v]) {
@@ -849,13 +869,7 @@ static int rollbackTouched(dmpc_tree* t) {
       ht.touched[v] = 0;
       t->h_curList[n++] = ((v - ht.numTips) << 1) | ht.cur[v];
     }
-  if (n) {
-    CUDA_TRY(cudaMemcpyAsync(t->d_curList, t->h_curList, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
-    k_set_cur<<<(n + 255) / 256, 256, 0, t->stream>>>(t->dv.cur, t->d_curList, n);
-    t->st.kernel_launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(t->stream));   // h_curList is reused by the next rollback
-  }
+  t->pendingCur = n;
   return DMPC_OK;
 }
 
@@ -932,6 +946,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
     if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
   }
   if ((rc = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return rc;
+  if ((rc = flushCur(t))) return rc;
   int nBatched = 0;
   std::vector<uint8_t> needSeq(nProps, 1);
   // Batched path: per proposal, the path to the root is walked with the partial in registers (k_prune<false, true>), then the
@@ -1189,6 +1204,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   HostTree& ht = t->ht;
   const int slot = ht.cur[vertex], idx = vertex - t->N;
   int partSlot = slot, partRow = idx;
+  if ((rc = flushCur(t))) return rc;
   ht.computeTips();
   if (ht.fused(vertex)) {
     // a fused vertex has no stored partial: replay its program (read-only) into the scratch row
