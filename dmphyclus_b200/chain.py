@@ -25,21 +25,26 @@ from .phylo import Phylo, cluster_mrcas
 
 # ---------------------------------------------------------------- priors (R/DMphyClusInterface.R:147-162)
 def _log_big_b(x) -> float:                       # .logBigB, DMphyClusSource.R:329-333
-    x = np.asarray(x, dtype=np.float64)
-    return float(sum(math.lgamma(v) for v in x) - math.lgamma(float(x.sum())))
+    x = [float(v) for v in x]
+    return sum(math.lgamma(v) for v in x) - math.lgamma(sum(x))
 
 
 def clusIndLogPrior(clusInd, alpha, k=None) -> float:
     """Dirichlet-multinomial log-prior of a cluster assignment vector (clusIndLogPrior, R API)."""
     counts = np.bincount(np.unique(np.asarray(clusInd), return_inverse=True)[1]).astype(np.float64)
+    return _log_prior_of_counts(counts, len(np.asarray(clusInd)), alpha, k)
+
+
+def _log_prior_of_counts(counts, n, alpha, k=None) -> float:
+    """clusIndLogPrior from table(clusInd) (counts in label order) and length(clusInd)."""
+    counts = [float(c) for c in counts]
     if k is None:
         k = len(counts)
-    alpha_vec = np.full(k, float(alpha)) if np.ndim(alpha) == 0 else np.asarray(alpha, dtype=np.float64)
+    alpha_vec = [float(alpha)] * k if np.ndim(alpha) == 0 else [float(a) for a in alpha]
     if len(counts) < k:
-        counts = np.concatenate([counts, np.zeros(k - len(counts))])
-    n = len(np.asarray(clusInd))
+        counts = counts + [0.0] * (k - len(counts))
     return (math.lgamma(n + 1) - sum(math.lgamma(c + 1) for c in counts)
-            + _log_big_b(alpha_vec + counts) - _log_big_b(alpha_vec))
+            + _log_big_b([a + c for a, c in zip(alpha_vec, counts)]) - _log_big_b(alpha_vec))
 
 
 def _dgamma_log(x, shape, scale) -> float:
@@ -77,6 +82,23 @@ class ChainSettings:
     maxMapSize: float | None = None
     cullProportion: float | None = None
 
+    def __post_init__(self):
+        # the lists the chain proposes from never change (DMphyClusInterface.R: withinTransMatAll / betweenTransMatAll),
+        # so every list is one read-only array object: a backend may convert it once and recognise it afterwards
+        def frozen(a):
+            a = np.array(a, dtype=np.float64)
+            a.setflags(write=False)
+            return a
+        self.limProbs = frozen(self.limProbs)
+        self._within = [frozen(m) for m in self.withinTransMatAll]
+        self._between = [frozen(m) for m in self.betweenTransMatAll]
+
+    def within(self, index: int) -> np.ndarray:      # withinTransMatAll[[index]], 1-based
+        return self._within[index - 1]
+
+    def between(self, index: int) -> np.ndarray:
+        return self._between[index - 1]
+
 
 @dataclass
 class ChainState:
@@ -92,6 +114,15 @@ class ChainState:
     extPointer: object = None
     clusterCounts: dict = field(default_factory=dict)   # names(clusterCounts) -> count
     n_loglik_calls: int = 0
+    _phylo: object = None                  # view of `edge`, rebuilt only when an accepted NNI replaced it
+    _phylo_edge: object = None
+
+    def phylo(self) -> Phylo:
+        """paraValues$phylogeny as a parent/children view.  R hands the same phylo object to every move until an NNI
+        is accepted; here the view is cached on the identity of the edge array for the same reason."""
+        if self._phylo is None or self._phylo_edge is not self.edge:
+            self._phylo, self._phylo_edge = Phylo(self.edge, self.n_tips), self.edge
+        return self._phylo
 
 
 def init_current_value(backend, alignmentBin, edge, clusInd, alpha, st: ChainSettings,
@@ -105,8 +136,8 @@ def init_current_value(backend, alignmentBin, edge, clusInd, alpha, st: ChainSet
     phy = Phylo(edge, n)
     clusInd = np.asarray(clusInd, dtype=np.int64)
     mrcas = cluster_mrcas(phy, clusInd)
-    res = backend.logLikCpp(edge, mrcas, st.limProbs, st.withinTransMatAll[withinMatListIndex - 1],
-                            st.betweenTransMatAll[betweenMatListIndex - 1], st.numLikThreads, alignmentBin, n, s,
+    res = backend.logLikCpp(edge, mrcas, st.limProbs, st.within(withinMatListIndex),
+                            st.between(betweenMatListIndex), st.numLikThreads, alignmentBin, n, s,
                             withinMatListIndex, betweenMatListIndex)
     cv = ChainState(edge=np.array(edge, dtype=np.int32), n_tips=n, clusInd=clusInd, alpha=float(alpha),
                     withinMatListIndex=withinMatListIndex, betweenMatListIndex=betweenMatListIndex,
@@ -122,14 +153,14 @@ def init_current_value(backend, alignmentBin, edge, clusInd, alpha, st: ChainSet
 # ---------------------------------------------------------------- moves
 def _update_trans_matrix(backend, cv: ChainState, st: ChainSettings, rng, between: bool):
     """.updateTransMatrix (DMphyClusSource.R:216-255)."""
-    all_list = st.betweenTransMatAll if between else st.withinTransMatAll
+    all_list = st._between if between else st._within
     new_index = int(rng.integers(1, len(all_list) + 1))           # sample.int(n, 1)
     if between:
-        new_ll = backend.newBetweenTransProbsLogLik(cv.extPointer, st.withinTransMatAll[cv.withinMatListIndex - 1],
+        new_ll = backend.newBetweenTransProbsLogLik(cv.extPointer, st.within(cv.withinMatListIndex),
                                                     all_list[new_index - 1], st.numLikThreads, new_index, st.limProbs)
     else:
         new_ll = backend.newWithinTransProbsLogLik(cv.extPointer, all_list[new_index - 1],
-                                                   st.betweenTransMatAll[cv.betweenMatListIndex - 1],
+                                                   st.between(cv.betweenMatListIndex),
                                                    st.numLikThreads, new_index, st.limProbs)
     cv.n_loglik_calls += 1
     if rng.random() < _exp(new_ll - cv.logLik):
@@ -163,8 +194,8 @@ def _nni_update(backend, cv, st, rng, call):
 
 def _update_between_phylo(backend, cv, st, rng):
     """.updateBetweenPhylo (DMphyClusSource.R:335-351)."""
-    w = st.withinTransMatAll[cv.withinMatListIndex - 1]
-    b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+    w = st.within(cv.withinMatListIndex)
+    b = st.between(cv.betweenMatListIndex)
     _nni_update(backend, cv, st, rng, lambda: backend.betweenClusNNIlogLik(
         cv.extPointer, w, b, cv.clusterNodeIndices, st.numMovesNNIbetween, st.numLikThreads, st.limProbs))
 
@@ -176,12 +207,14 @@ def _update_cluster_phylos(backend, cv, st, rng):
         select = [cv.clusterNodeIndices[i] for i in rng.choice(len(cv.clusterNodeIndices), size=k, replace=False)]
     else:
         select = list(cv.clusterNodeIndices)
-    original = Phylo(cv.edge, cv.n_tips)
+    # length(Descendants(originalPhylo, clusterMRCA)) = the size of that cluster: clusters are clades of the tree
+    # (DMphyClusInterface.R:228-249) and NNI moves keep every cluster's tip set and MRCA id (DMphyClusSource.R:396)
+    size_of = {m: cv.clusterCounts[k + 1] for k, m in enumerate(cv.clusterNodeIndices)}
     for mrca in select:
-        if len(original.descendants(mrca)) < 3:
+        if size_of[mrca] < 3:
             continue
-        w = st.withinTransMatAll[cv.withinMatListIndex - 1]
-        b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+        w = st.within(cv.withinMatListIndex)
+        b = st.between(cv.betweenMatListIndex)
         _nni_update(backend, cv, st, rng, lambda: backend.withinClusNNIlogLik(
             cv.extPointer, w, b, mrca, st.numMovesNNIwithin, st.numLikThreads, st.limProbs))
 
@@ -198,7 +231,7 @@ def _pairs_and_splits(phy: Phylo, mrcas, counts_gt1):
 
 def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
     """.splitJoinClusterMove / .performSplit / .performMerge (DMphyClusSource.R:100-214)."""
-    phy = Phylo(cv.edge, cv.n_tips)
+    phy = cv.phylo()
     pairs = _pairs_and_splits(phy, cv.clusterNodeIndices, None)[0] if len(cv.clusterNodeIndices) > 1 else []
     to_split = [k for k, c in cv.clusterCounts.items() if c > 1]
     num_moves = len(pairs) + len(to_split)
@@ -206,8 +239,8 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
         raise RuntimeError("No possible move. This is an error. Exiting...")
     selected = int(rng.integers(1, num_moves + 1))                # sample(1:numMoves, 1)
     split_move = selected > len(pairs)
-    w = st.withinTransMatAll[cv.withinMatListIndex - 1]
-    b = st.betweenTransMatAll[cv.betweenMatListIndex - 1]
+    w = st.within(cv.withinMatListIndex)
+    b = st.between(cv.betweenMatListIndex)
     if split_move:
         clus_number = to_split[selected - len(pairs) - 1]
         node = cv.clusterNodeIndices[clus_number - 1]
@@ -237,7 +270,7 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
     cv.n_loglik_calls += 1
     labels, cnt = np.unique(new_clus, return_counts=True)
     new_counts = {int(l): int(c) for l, c in zip(labels, cnt)}
-    new_lpp = (new_ll + clusIndLogPrior(new_clus, cv.alpha)
+    new_lpp = (new_ll + _log_prior_of_counts(cnt, len(new_clus), cv.alpha)
                + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
                + _dpois_log(int(new_clus.max()), st.poisRateNumClus))
     groups = {}
@@ -263,8 +296,9 @@ def _update_alpha(cv: ChainState, st: ChainSettings, rng):
     """.updateAlpha (DMphyClusSource.R:38-52)."""
     new_alpha = cv.alpha + (rng.random() - 0.5)
     new_alpha = new_alpha + abs(new_alpha - st.alphaMin) * (new_alpha < st.alphaMin)
-    new_lp = clusIndLogPrior(cv.clusInd, new_alpha) + _dgamma_log(new_alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
-    cur_lp = clusIndLogPrior(cv.clusInd, cv.alpha) + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+    counts = [cv.clusterCounts[k] for k in sorted(cv.clusterCounts)]          # table(clusInd)
+    new_lp = _log_prior_of_counts(counts, len(cv.clusInd), new_alpha) + _dgamma_log(new_alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
+    cur_lp = _log_prior_of_counts(counts, len(cv.clusInd), cv.alpha) + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
     pois = cv.logPostProb - cur_lp - cv.logLik
     if rng.random() < _exp(new_lp - cur_lp):
         cv.alpha = new_alpha
@@ -285,8 +319,8 @@ def perform_step_phylo(backend, cv: ChainState, st: ChainSettings, rng) -> Chain
     _update_alpha(cv, st, rng)
     if st.maxMapSize is not None:
         backend.checkAndCullMap(cv.extPointer, st.maxMapSize, st.cullProportion,
-                                st.withinTransMatAll[cv.withinMatListIndex - 1],
-                                st.betweenTransMatAll[cv.betweenMatListIndex - 1], st.limProbs)
+                                st.within(cv.withinMatListIndex),
+                                st.between(cv.betweenMatListIndex), st.limProbs)
     return cv
 
 

@@ -133,10 +133,37 @@ class Engine:
             self.opts.fuse_tips = int(fuse_tips)
         self.opts.fuse_exact = int(fuse_exact)
         self._shape = {}
+        self._mcache = {}
 
     def _check(self, rc):
         if rc != 0:
             raise DmpcError(rc, self.lib.dmpc_last_error().decode())
+
+    def _mp(self, m):
+        """Pointer to a transition-matrix list in the layout R passes (column-major 4x4 each).  Read-only arrays handed
+        in again (the MCMC driver proposes from a fixed set of lists) are converted once; the returned ctypes pointer
+        keeps its array alive."""
+        ent = self._mcache.get(id(m))
+        if ent is not None and ent[0] is m:
+            return ent[1]
+        ptr = _p(_mats(m), _dbl_p)
+        if isinstance(m, np.ndarray) and not m.flags.writeable:
+            if len(self._mcache) > 256:
+                self._mcache.clear()
+            self._mcache[id(m)] = (m, ptr)
+        return ptr
+
+    def _pp(self, pi):
+        ent = self._mcache.get(id(pi))
+        if ent is not None and ent[0] is pi:
+            return ent[1]
+        a = np.ascontiguousarray(pi, dtype=np.float64)
+        if a.shape != (4,):
+            raise ValueError("limProbs must have 4 entries")
+        ptr = _p(a, _dbl_p)
+        if isinstance(pi, np.ndarray) and not pi.flags.writeable:
+            self._mcache[id(pi)] = (pi, ptr)
+        return ptr
 
     # ------------------------------------------------------------------ the 11 entry points
     def getConvertedAlignment(self, equivVector, alignmentAlphaMat) -> np.ndarray:
@@ -173,48 +200,48 @@ class Engine:
 
     def newBetweenTransProbsLogLik(self, ptr, withinTransProbs, newBetweenTransProbs, numOpenMP,
                                    newBetweenMatListIndex, limProbs) -> float:
-        w, b, pi = _mats(withinTransProbs), _mats(newBetweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(newBetweenTransProbs), self._pp(limProbs)
         ll = C.c_double()
-        self._check(self.lib.dmpc_new_between_transprobs_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p),
-                                                                int(newBetweenMatListIndex), _p(pi, _dbl_p), C.byref(ll)))
+        self._check(self.lib.dmpc_new_between_transprobs_loglik(ptr, w, b,
+                                                                int(newBetweenMatListIndex), pi, C.byref(ll)))
         return ll.value
 
     def newWithinTransProbsLogLik(self, ptr, newWithinTransProbs, betweenTransProbs, numOpenMP,
                                   newWithinMatListIndex, limProbs) -> float:
-        w, b, pi = _mats(newWithinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(newWithinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         ll = C.c_double()
-        self._check(self.lib.dmpc_new_within_transprobs_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p),
-                                                               int(newWithinMatListIndex), _p(pi, _dbl_p), C.byref(ll)))
+        self._check(self.lib.dmpc_new_within_transprobs_loglik(ptr, w, b,
+                                                               int(newWithinMatListIndex), pi, C.byref(ll)))
         return ll.value
 
     def withinClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, MRCAofClusForNNI, numMovesNNI,
                             numOpenMP, limProbs):
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         n = self._shape[ptr][0]
-        edge = np.zeros(2 * (2 * n - 2), np.int32)
+        edge = np.empty(2 * (2 * n - 2), np.int32)
         ll = C.c_double()
-        self._check(self.lib.dmpc_within_clus_nni_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), int(MRCAofClusForNNI),
-                                                         int(numMovesNNI), _p(pi, _dbl_p), C.byref(ll), _p(edge, _i32_p)))
+        self._check(self.lib.dmpc_within_clus_nni_loglik(ptr, w, b, int(MRCAofClusForNNI),
+                                                         int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
         return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
 
     def betweenClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, clusterMRCAs, numMovesNNI,
                              numOpenMP, limProbs):
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
         n = self._shape[ptr][0]
-        edge = np.zeros(2 * (2 * n - 2), np.int32)
+        edge = np.empty(2 * (2 * n - 2), np.int32)
         ll = C.c_double()
-        self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(m, _dbl_p), len(m),
-                                                          int(numMovesNNI), _p(pi, _dbl_p), C.byref(ll), _p(edge, _i32_p)))
+        self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, w, b, _p(m, _dbl_p), len(m),
+                                                          int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
         return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
 
     def clusSplitMergeLogLik(self, ptr, withinTransProbs, betweenTransProbs, clusMRCAsToSplitOrMerge, numOpenMP,
                              limProbs) -> float:
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         m = np.ascontiguousarray(np.asarray(clusMRCAsToSplitOrMerge).ravel(), dtype=np.int32)
         ll = C.c_double()
-        self._check(self.lib.dmpc_clus_split_merge_loglik(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(m, _i32_p), len(m),
-                                                          _p(pi, _dbl_p), C.byref(ll)))
+        self._check(self.lib.dmpc_clus_split_merge_loglik(ptr, w, b, _p(m, _i32_p), len(m),
+                                                          pi, C.byref(ll)))
         return ll.value
 
     def RestorePreviousConfig(self, ptr, edgeMat, withinMatListIndex, betweenMatListIndex, NNImove, clusterMRCAs,
@@ -234,27 +261,27 @@ class Engine:
 
     def checkAndCullMap(self, ptr, allowedNumberOfElements, cullProportion, withinTransProbs, betweenTransProbs,
                         limProbs) -> None:
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         self._check(self.lib.dmpc_check_and_cull_map(ptr, int(allowedNumberOfElements), float(cullProportion),
-                                                     _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p)))
+                                                     w, b, pi))
 
     # ------------------------------------------------------------------ beyond the reference
     def recomputeAll(self, ptr, withinTransProbs, betweenTransProbs, limProbs) -> float:
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         ll = C.c_double()
-        self._check(self.lib.dmpc_recompute_all(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p), C.byref(ll)))
+        self._check(self.lib.dmpc_recompute_all(ptr, w, b, pi, C.byref(ll)))
         return ll.value
 
     def evalProposals(self, ptr, withinTransProbs, betweenTransProbs, limProbs, proposals):
         """Batch of split / merge proposals against the committed state (left untouched).  `proposals`: iterable of
         ("split", mrca) or ("merge", mrcaA, mrcaB), 1-based ids.  Returns (logLik array, number evaluated by the batched kernel)."""
-        w, b, pi = _mats(withinTransProbs), _mats(betweenTransProbs), np.ascontiguousarray(limProbs, np.float64)
+        w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
         arr = np.zeros((len(proposals), 3), np.int32)
         for i, q in enumerate(proposals):
             arr[i] = (0, q[1], 0) if q[0] == "split" else (1, q[1], q[2])
         out = np.empty(len(proposals), np.float64)
         nb = C.c_int()
-        self._check(self.lib.dmpc_eval_proposals(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(pi, _dbl_p), arr.ctypes.data_as(C.c_void_p),
+        self._check(self.lib.dmpc_eval_proposals(ptr, w, b, pi, arr.ctypes.data_as(C.c_void_p),
                                                  len(proposals), _p(out, _dbl_p), C.byref(nb)))
         return out, nb.value
 

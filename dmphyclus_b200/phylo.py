@@ -18,55 +18,66 @@ class Phylo:
         n_nodes = int(self.edge.max())
         self.parent = np.zeros(n_nodes + 1, np.int64)
         self.parent[self.edge[:, 1]] = self.edge[:, 0]
-        # children in edge-row order (AddChild appends); strictly bifurcating, so two per internal node.  Vectorised:
-        # the MCMC driver rebuilds this view for every move.
-        order = np.argsort(self.edge[:, 0], kind="stable")
-        par_sorted, kid_sorted = self.edge[order, 0], self.edge[order, 1]
-        ch = np.zeros((n_nodes + 1, 2), np.int64)
-        if len(order) and np.all(par_sorted[0::2] == par_sorted[1::2]):
-            ch[par_sorted[0::2], 0] = kid_sorted[0::2]
-            ch[par_sorted[1::2], 1] = kid_sorted[1::2]
-            self.children = ch.tolist()
-            for t in range(self.n_tips + 1):
-                self.children[t] = []
-        else:                             # not bifurcating: generic path
-            self.children = [[] for _ in range(n_nodes + 1)]
-            for p, c in self.edge:
-                self.children[p].append(int(c))
         self.root = self.n_tips + 1
+        self._children = None
+
+    @property
+    def children(self):
+        """children[v] in edge-row order (AddChild appends).  Built on first use: the MCMC driver rebuilds this view
+        after every accepted topology change but most moves only need `parent`."""
+        if self._children is None:
+            n_nodes = len(self.parent) - 1
+            order = np.argsort(self.edge[:, 0], kind="stable")
+            par_sorted, kid_sorted = self.edge[order, 0], self.edge[order, 1]
+            if len(order) and len(order) % 2 == 0 and np.all(par_sorted[0::2] == par_sorted[1::2]) \
+                    and (len(order) < 4 or np.all(par_sorted[0:-2:2] != par_sorted[2::2])):
+                # strictly bifurcating, so two per internal node: vectorised
+                ch = np.zeros((n_nodes + 1, 2), np.int64)
+                ch[par_sorted[0::2], 0] = kid_sorted[0::2]
+                ch[par_sorted[1::2], 1] = kid_sorted[1::2]
+                out = ch.tolist()
+                for t in range(self.n_tips + 1):
+                    out[t] = []
+            else:                             # not bifurcating: generic path
+                out = [[] for _ in range(n_nodes + 1)]
+                for p, c in self.edge:
+                    out[p].append(int(c))
+            self._children = out
+        return self._children
 
     def is_tip(self, v: int) -> bool:
         return v <= self.n_tips
 
     def descendants(self, v: int) -> np.ndarray:
         """Tip ids under v (phangorn::Descendants(type='tips')), in traversal order."""
-        out, stack = [], [v]
+        out, stack, ch, nt = [], [v], self.children, self.n_tips
         while stack:
             x = stack.pop()
-            if x <= self.n_tips:
+            if x <= nt:
                 out.append(x)
             else:
-                stack.extend(reversed(self.children[x]))
+                stack.extend(reversed(ch[x]))
         return np.array(out, dtype=np.int64)
 
     def subtree_sizes(self) -> np.ndarray:
         """Number of tips under every node."""
         size = np.zeros(len(self.parent), np.int64)
         size[1:self.n_tips + 1] = 1
+        ch = self.children
         for v in self.postorder():
             if v > self.n_tips:
-                size[v] = sum(size[c] for c in self.children[v])
+                size[v] = sum(size[c] for c in ch[v])
         return size
 
     def postorder(self):
-        out, stack = [], [(self.root, False)]
+        out, stack, ch = [], [(self.root, False)], self.children
         while stack:
             v, done = stack.pop()
             if done or v <= self.n_tips:
                 out.append(v)
             else:
                 stack.append((v, True))
-                for c in reversed(self.children[v]):
+                for c in reversed(ch[v]):
                     stack.append((c, False))
         return out
 

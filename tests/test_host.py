@@ -75,6 +75,33 @@ def test_chain_runs_and_is_reproducible(oracle, packaged):
     assert abs(r["logLik"] - last["logLik"]) <= 1e-12 * abs(last["logLik"])
 
 
+def test_chain_bookkeeping_invariants(oracle, packaged):
+    """What the driver's shortcuts rely on, checked after every iteration: clusterCounts is table(clusInd) with labels
+    1..K, cluster k's tips are exactly the tips below clusterNodeIndices[k] (so its size is the length of
+    phangorn::Descendants of its MRCA, DMphyClusSource.R:384-388), and the cached tree view follows accepted NNIs."""
+    p = Problem(packaged, 60, 40, 6, 3, "evolved", seed=15)
+    st = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
+                             scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
+    al = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    seen = {"n": 0, "edges": set()}
+
+    def check(it, cv):
+        labels, cnt = np.unique(cv.clusInd, return_counts=True)
+        assert list(labels) == list(range(1, len(labels) + 1)) == sorted(cv.clusterCounts)
+        assert [cv.clusterCounts[int(l)] for l in labels] == list(cnt)
+        phy = Phylo(cv.edge, cv.n_tips)
+        assert np.array_equal(cv.phylo().parent, phy.parent)
+        for k, m in enumerate(cv.clusterNodeIndices):
+            tips = np.sort(phy.descendants(m))
+            assert np.array_equal(tips, np.nonzero(cv.clusInd == k + 1)[0] + 1)
+            assert len(tips) == cv.clusterCounts[k + 1]
+        seen["n"] += 1
+        seen["edges"].add(cv.edge.tobytes())
+
+    chain.run_chain(oracle, al, p.edge, p.clus, 100.0, st, 25, seed=6, on_iter=check)
+    assert seen["n"] == 25 and len(seen["edges"]) > 1          # some NNI was accepted along the way
+
+
 def test_workload_shapes_match_baseline():
     from dmphyclus_b200.workloads import CONFIGS
     assert CONFIGS["config2"] == (1000, 10000, 20, 3) and CONFIGS["config3"] == (10000, 30000, 100, 3)
