@@ -416,17 +416,57 @@ def extra_legs(args, eng, p, al, n, s, k, r, world=1):
 
 
 def mcmc_leg(args, eng, p, al, out, how):
-    """MCMC iterations/sec: the reference's move schedule (.performStepPhylo) driven from the host mirror."""
+    """MCMC iterations/sec: the reference's move schedule (.performStepPhylo) driven from the host mirror, then a short
+    second pass that reads the engine's own counters after every likelihood call to say where a call's time goes."""
     from dmphyclus_b200 import chain
     cs = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
                              scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
-    iters = 10
+    iters = 30
+    marks = []
     t0 = time.perf_counter()
-    _, calls = chain.run_chain(eng, al, p.edge, p.clus, 100.0, cs, iters, seed=args.seed)
+    _, calls = chain.run_chain(eng, al, p.edge, p.clus, 100.0, cs, iters, seed=args.seed,
+                               on_iter=lambda it, cv: marks.append((time.perf_counter(), cv.n_loglik_calls)))
     dt = time.perf_counter() - t0
-    out["mcmc"] = {"iterations_per_sec": iters / dt, "iterations": iters, "likelihood_calls": calls,
-                   "likelihood_calls_per_sec": calls / dt, "how": how,
-                   "note": "host driver = Python mirror of .performStepPhylo (R in a deployment); includes the initial logLikCpp"}
+    # steady state: from the end of the first iteration (after handle creation, first plans and graph captures)
+    (ta, ca), (tb, cb) = marks[0], marks[-1]
+    out["mcmc"] = {"iterations_per_sec": (iters - 1) / (tb - ta), "iterations": iters, "likelihood_calls": calls,
+                   "likelihood_calls_per_sec": (cb - ca) / (tb - ta), "us_per_likelihood_call": (tb - ta) / (cb - ca) * 1e6,
+                   "iterations_per_sec_with_setup": iters / dt, "how": how,
+                   "note": "host driver = Python mirror of .performStepPhylo (R in a deployment); rate taken after the "
+                           "first iteration, *_with_setup includes the initial logLikCpp"}
+    if how != "single GPU":
+        return out
+
+    class Probe:
+        """The same backend, reading dmpc_stats after each likelihood entry point (slows the driver: diagnostics only)."""
+        KINDS = ("newBetweenTransProbsLogLik", "newWithinTransProbsLogLik", "withinClusNNIlogLik", "betweenClusNNIlogLik",
+                 "clusSplitMergeLogLik")
+
+        def __init__(self, be):
+            self.be, self.rows = be, {k: [] for k in self.KINDS}
+
+        def __getattr__(self, name):
+            f = getattr(self.be, name)
+            if name not in self.KINDS:
+                return f
+
+            def wrapped(ptr, *a, **kw):
+                w0 = time.perf_counter()
+                r = f(ptr, *a, **kw)
+                w1 = time.perf_counter()
+                st = self.be.stats(ptr)
+                self.rows[name].append(((w1 - w0) * 1e6, st["last_host_total_us"], st["last_host_plan_us"], st["last_host_submit_us"],
+                                        st["last_eval_ms"] * 1e3, st["last_prune_ms"] * 1e3, st["last_stored_vertices"],
+                                        st["last_fused_vertices"], st["last_walk_steps"], st["last_prune_launches"]))
+                return r
+            return wrapped
+
+    pr = Probe(eng)
+    chain.run_chain(pr, al, p.edge, p.clus, 100.0, cs, 6, seed=args.seed)
+    cols = ("wall_us", "engine_host_us", "plan_us", "submit_us", "device_eval_us", "device_prune_us", "stored_vertices",
+            "fused_vertices", "walk_steps", "prune_launches")
+    out["mcmc"]["per_call"] = {k: dict(zip(cols, [round(float(x), 2) for x in np.mean(np.array(v), axis=0)]), n=len(v))
+                               for k, v in pr.rows.items() if v}
     return out
 
 

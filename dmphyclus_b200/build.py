@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("dmpc_engine.cu", "kernels.cuh", "host_tree.hpp")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("dmpc_engine.cu", "kernels.cuh", "host_tree.hpp", "task.hpp")]
 HDR = os.path.join(ROOT, "include", "dmpc.h")
 LIB = os.path.join(HERE, "libdmpc.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

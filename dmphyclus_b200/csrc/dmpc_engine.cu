@@ -151,6 +151,7 @@ int acquirePack(dmpc_tree* t) {
       CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, t->device));
       unsigned long long keep = ~0ULL;                    // keep freed HBM cached in the pool between handles
       CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK_SMEM));
       cx.checked = true;
     }
     if (!cx.freePacks.empty()) { t->pack = cx.freePacks.back(); cx.freePacks.pop_back(); }
@@ -308,7 +309,8 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
 // the level launches of the current plan (tasks, tokens and tip lists are already on the device)
 int runPlan(dmpc_tree* t) {
   const HostTree::Plan& p = *t->runPlanMeta;
-  const int nLevels = (int)p.levelStart.size() - 1;
+  const int nAll = (int)p.levelStart.size() - 1;
+  const int nLevels = nAll - p.chainLevels;        // the trailing single-task levels go to k_walk as one chain
   if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 16.7M)");
   int rcE;
   if ((rcE = recordEv(t, 0))) return rcE;
@@ -334,10 +336,18 @@ int runPlan(dmpc_tree* t) {
     }
     l = l2;
   }
+  if (p.chainLevels) {
+    const int first = p.levelStart[nLevels], n = p.levelStart[nAll] - first;     // one task per level: n == chainLevels
+    k_walk<<<dim3((unsigned)t->R, (unsigned)t->T), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip);
+    t->st.kernel_launches++;
+    launches++;
+  }
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
   if ((rcE = recordEv(t, 1))) return rcE;
-  t->st.last_levels = nLevels;
+  t->st.last_levels = nAll;
   t->st.last_prune_launches = launches;
+  t->st.last_walk_steps = p.chainLevels;
+  t->st.last_materialised = p.materialised;
   return DMPC_OK;
 }
 
@@ -409,6 +419,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
       }
       cc.kids = ht.kids; cc.within = ht.within; cc.cur = curBefore; cc.fuse = ht.fuseTips;
       cc.meta.levelStart = p.levelStart;
+      cc.meta.chainLevels = p.chainLevels; cc.meta.materialised = p.materialised;
       cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps;
       cc.meta.tasks.clear(); cc.metaTasks = nT;
       cc.valid = true;
@@ -1132,17 +1143,27 @@ int dmpc_timer_end(dmpc_tree* t, double* msOut) {
 }
 
 int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
-                        int fuseTips, int* out) {
+                        int fuseTips, int dirtyVertex, int* out) {
   if (!edge || !out || (nClusterMRCAs > 0 && !clusterMRCAs)) return fail(DMPC_ERR_ARG, "null pointer");
   HostTree ht;
   if (!ht.build(edge, nEdgeRows, numTips)) return fail(DMPC_ERR_ARG, ht.err);
+  if (dirtyVertex != 0 && (dirtyVertex <= numTips || dirtyVertex > ht.numVerts)) return fail(DMPC_ERR_ARG, "dirtyVertex must be internal");
   ht.associate(clusterMRCAs, nClusterMRCAs);
   ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
   HostTree::Plan p;
   ht.plan(p);
+  const bool full = dirtyVertex == 0;
+  std::vector<uint8_t> dirty(ht.numVerts, 0);
+  if (!full) {                                    // a proposal: the path from dirtyVertex to the root (InvalidateSolution)
+    ht.negateAllUpdateFlags();
+    ht.invalidateSolution(dirtyVertex - 1);
+    for (int v = dirtyVertex - 1; v != -1; v = ht.parent[v]) dirty[v] = 1;
+    ht.plan(p);
+  }
   const int N = numTips, nInt = N - 1;
   auto bad = [&](const std::string& m) { return fail(DMPC_ERR_STATE, "plan self-check: " + m); };
   std::vector<int> computedAt(nInt, -1);          // level at which each internal vertex is computed
+  std::vector<uint8_t> asTask(nInt, 0), readStored(nInt, 0);
   const int nLevels = (int)p.levelStart.size() - 1;
   int maxDepth = 0, maxTips = 0, fusedCount = 0;
   for (int l = 0; l < nLevels; l++)
@@ -1156,12 +1177,18 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
       if (k.tipOff < 0 || k.tipOff + k.nTips > (int)p.tipList.size()) return bad("tip list range");
       if (k.nTips > 2 * FUSE_MAX_TIPS || n0 + n1 > 3 * FUSE_MAX_TIPS + 4) return bad("task exceeds the kernel's shared-memory staging");
       maxTips = std::max(maxTips, k.nTips);
-      for (int c = 0; c < 2; c++) {               // stored operands must have been computed at a lower level
+      for (int c = 0; c < 2; c++) {               // stored operands must have been computed at a lower level, or be clean
         const int idx = c ? k.c1 : k.c0;
         const bool tip = k.flags & (c ? TF_C1TIP : TF_C0TIP), fus = k.flags & (c ? TF_C1FUSED : TF_C0FUSED);
         if (tip) { if (idx < 0 || idx >= N) return bad("tip operand out of range"); continue; }
         if (idx < 0 || idx >= nInt) return bad("operand out of range");
-        if (!fus && (computedAt[idx] < 0 || computedAt[idx] >= l)) return bad("stored operand not computed at a lower level");
+        if (ht.kids[2 * (k.out + N) + c] != idx + N) return bad("operand is not the vertex's child");
+        if (fus) continue;
+        readStored[idx] = 1;
+        if (computedAt[idx] >= l) return bad("stored operand not computed at a lower level");
+        if (computedAt[idx] < 0 && (full || dirty[idx + N])) return bad("stored operand is dirty but not part of the plan");
+        ht.computeTips();
+        if (computedAt[idx] < 0 && ht.fused(idx + N)) return bad("a fused-size operand is read from HBM without having been materialised");
       }
       // run the programs symbolically: stack discipline, tips under each clade, every token's vertex new
       int off = k.prog;
@@ -1189,10 +1216,42 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
       }
       if (maxDepth > FUSE_DEPTH) return bad("stack deeper than FUSE_DEPTH");
       computedAt[k.out] = l;
+      asTask[k.out] = 1;
     }
-  for (int v = 0; v < nInt; v++) if (computedAt[v] < 0) return bad("vertex never computed");
-  if (computedAt[0] != nLevels - 1) return bad("the root is not in the last level");
+  if (full) { for (int v = 0; v < nInt; v++) if (computedAt[v] < 0) return bad("vertex never computed"); }
+  else { for (int v = N; v < ht.numVerts; v++) if (dirty[v] && computedAt[v - N] < 0) return bad("dirty vertex never computed"); }
+  if (nLevels > 0 && computedAt[0] != nLevels - 1) return bad("the root is not in the last level");
+  // the walked chain (k_walk): one task per trailing level, each consuming the previous one's output; no fused operands
+  // (materialised beforehand: level 0 of the plan holds exactly those clades)
+  if (p.chainLevels) {
+    if (p.chainLevels < CHAIN_MIN || p.chainLevels > nLevels) return bad("chain length");
+    const int first = nLevels - p.chainLevels;
+    for (int l = first; l < nLevels; l++) {
+      if (p.levelStart[l + 1] - p.levelStart[l] != 1) return bad("a chain level holds more than one task");
+      const Task& k = p.tasks[p.levelStart[l]];
+      if (k.flags & (TF_C0FUSED | TF_C1FUSED)) return bad("fused operand inside the chain");
+      const int fw = k.flags & (TF_C0FWD | TF_C1FWD);
+      if (l == first) { if (!(k.flags & TF_HEAD) || fw) return bad("chain head flags"); continue; }
+      if ((k.flags & TF_HEAD) || (fw != TF_C0FWD && fw != TF_C1FWD)) return bad("chain step flags");
+      const Task& pr = p.tasks[p.levelStart[l - 1]];
+      if ((fw == TF_C0FWD ? k.c0 : k.c1) != pr.out) return bad("forwarded operand is not the previous task's output");
+      if (fw == TF_C0FWD ? (k.flags & TF_C0TIP) : (k.flags & TF_C1TIP)) return bad("forwarded operand flagged as a tip");
+    }
+    for (int l = 0; l < first; l++)
+      for (int i = p.levelStart[l]; i < p.levelStart[l + 1]; i++)
+        if (p.tasks[i].flags & (TF_HEAD | TF_C0FWD | TF_C1FWD)) return bad("chain flags outside the chain");
+    ht.computeTips();
+    int nMat = 0;
+    for (int v = 0; v < nInt; v++)
+      if (asTask[v] && ht.fused(v + N)) { nMat++; if (computedAt[v] != 0 || !readStored[v]) return bad("materialised clade not in level 0 or never read"); }
+    if (nMat != p.materialised) return bad("materialised count");
+  } else {
+    for (const Task& k : p.tasks) if (k.flags & (TF_HEAD | TF_C0FWD | TF_C1FWD)) return bad("chain flags without a chain");
+    if (p.materialised) return bad("materialised clades without a chain");
+  }
+  for (int v = 0; v < ht.numVerts; v++) if (ht.mat[v]) return bad("materialisation marks left behind");
   out[0] = (int)p.tasks.size(); out[1] = fusedCount; out[2] = nLevels; out[3] = (int)p.tokens.size(); out[4] = maxDepth; out[5] = maxTips;
+  out[6] = p.chainLevels; out[7] = p.materialised;
   return DMPC_OK;
 }
 

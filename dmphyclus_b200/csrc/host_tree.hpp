@@ -60,6 +60,7 @@ struct HostTree {
   int fuseTips = 1;
   std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
   bool tipsValid = false;
+  std::vector<uint8_t> mat;              // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
   bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
 
   bool isTip(int v) const { return v < numTips; }
@@ -107,6 +108,7 @@ struct HostTree {
     solved.assign(numVerts, 0);
     touched.assign(numVerts, 0);
     cur.assign(numVerts, 1);             // first evaluation writes slot 0
+    mat.assign(numVerts, 0);
     for (int v = 0; v < numTips; v++) solved[v] = 1;
     rng.seed(0);
     if (!link(edge, nEdgeRows)) return false;
@@ -233,6 +235,8 @@ struct HostTree {
     std::vector<int32_t> tipList;                // tips read by the fused programs, task by task
     std::vector<int> levelStart;
     long long storedReads = 0, tipReads = 0, fusedOps = 0;
+    int chainLevels = 0;                         // trailing single-task levels that k_walk evaluates (0 or >= CHAIN_MIN)
+    int materialised = 0;                        // fused-size clades evaluated as stored tasks for that chain (level 0 of the plan)
     bool uses[2] = {false, false};               // slots this plan writes
     std::vector<int> pre, level, cnt, fill;      // scratch
   };
@@ -282,7 +286,7 @@ struct HostTree {
       int32_t& ref = j ? k.c1 : k.c0;
       if (isTip(c)) {
         ref = c; k.flags |= j ? TF_C1TIP : TF_C0TIP; p.tipReads++;
-      } else if (fused(c)) {
+      } else if (fused(c) && !mat[c]) {
         ref = c - numTips; k.flags |= j ? TF_C1FUSED : TF_C0FUSED;
         const int off = (int)p.tokens.size();
         emitClade(c, p, k.tipOff, mutate);
@@ -318,6 +322,7 @@ struct HostTree {
     allInvalid = false;
     p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
     p.storedReads = p.tipReads = p.fusedOps = 0;
+    p.chainLevels = p.materialised = 0;
     p.uses[0] = p.uses[1] = false;
     if (solved[root()]) { p.levelStart.push_back(0); return; }
     computeTips();
@@ -340,24 +345,42 @@ struct HostTree {
     }
     p.cnt.assign(maxLevel + 1, 0);
     for (int v : pre) p.cnt[level[v]]++;
-    p.levelStart.assign(maxLevel + 1, 0);   // level l (1-based) = tasks[levelStart[l-1] .. levelStart[l])
-    int acc = 0;
-    for (int l = 1; l <= maxLevel; l++) { p.levelStart[l - 1] = acc; acc += p.cnt[l]; }
-    p.levelStart[maxLevel] = acc;
+    // the trailing chain: levels chainL0..maxLevel hold one task each
+    int chainL0 = maxLevel + 1;
+    for (int l = maxLevel; l >= 1 && p.cnt[l] == 1; l--) chainL0 = l;
+    p.chainLevels = maxLevel - chainL0 + 1;
+    if (p.chainLevels < CHAIN_MIN) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
+    std::vector<int> matList;                // fused clades hanging off the chain: stored tasks of a leading level
+    if (p.chainLevels)
+      for (int v : pre)
+        if (level[v] >= chainL0)
+          for (int i = 0; i < 2; i++) { const int c = kids[2 * v + i]; if (!isTip(c) && fused(c)) { mat[c] = 1; matList.push_back(c); } }
+    p.materialised = (int)matList.size();
+    const int lead = matList.empty() ? 0 : 1;
+    p.levelStart.assign(maxLevel + lead + 1, 0);   // level l (1-based) = tasks[levelStart[l-1+lead] .. levelStart[l+lead])
+    int acc = (int)matList.size();
+    for (int l = 1; l <= maxLevel; l++) { p.levelStart[l - 1 + lead] = acc; acc += p.cnt[l]; }
+    p.levelStart[maxLevel + lead] = acc;
     p.fill.assign(p.levelStart.begin(), p.levelStart.end());
-    std::vector<int> order(pre.size());
-    for (int v : pre) order[p.fill[level[v] - 1]++] = v;
+    std::vector<int> order((size_t)acc);
+    for (size_t i = 0; i < matList.size(); i++) order[i] = matList[i];
+    for (int v : pre) order[p.fill[level[v] - 1 + lead]++] = v;
     p.tasks.resize(order.size());
     for (size_t i = 0; i < order.size(); i++) {
       const int v = order[i];
       const int outSlot = cur[v] ^ 1;
-      Task k = makeTask(v, v - numTips, outSlot, p, true);
+      Task k = makeTask(v, v - numTips, outSlot, p, true);   // materialised clades come first: the chain sees their new slot
+      if (level[v] >= chainL0) {                             // a chain task (materialised clades have level 0)
+        if (level[v] == chainL0) k.flags |= TF_HEAD;
+        else k.flags |= level[kids[2 * v]] == level[v] - 1 ? TF_C0FWD : TF_C1FWD;   // the one dirty vertex of the level below
+      }
       p.tasks[i] = k;
       p.uses[outSlot] = true;
       cur[v] = (uint8_t)outSlot;                      // ComputeSolutions: _previousIterVec <- current (:28) ...
       touched[v] = 1;                                 // ... _updateFlag = true (:34)
       solved[v] = 1;                                  // ... _isSolved = true (:33)
     }
+    for (int c : matList) mat[c] = 0;
   }
 };
 

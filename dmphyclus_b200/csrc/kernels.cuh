@@ -449,6 +449,155 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
 
 
 
+// ------------------------------------------------------------------------------------------------
+// K2w walk: the trailing CHAIN of a plan — levels that hold one task each, every task consuming the previous one's
+// output (a root path after a split / merge / NNI proposal; the spine of a caterpillar).  Evaluated level by level,
+// such a chain costs one global-memory round trip per vertex (store, dependent load of the next task's operands,
+// ~1.3 us measured); here one thread owns one (site, rate) for the whole chain, keeps the running partial in
+// registers, and everything that does NOT depend on the chain — the task descriptors and the off-chain operands
+// (stored partials, tip mask bytes; fused clades were materialised by the plan builder) — is fetched WALK_DEPTH steps
+// ahead with cp.async into a per-thread ring in shared memory (and WALK_PF steps ahead into L2), so that a step costs
+// its dependent arithmetic only: sol = (P prev) % (P sib) with the reference's two rescale checks
+// (IntermediateNode.cpp:53-66, same combineExact as k_prune), one 256-bit store of the vertex's partial.
+// grid = (R, site tiles), TILE threads.  Rescale bookkeeping keeps k_prune's format (exponent rows only for tiles
+// where some site rescaled, one flag byte per (rate, tile, vertex)) without a barrier per step: a thread that
+// rescales writes its own exponent at once and remembers the step in a bit mask; every WALK_WIN steps the block ORs
+// the masks, the other threads fill in their zeros for the steps that rescaled somewhere, and the flags are written.
+constexpr int WALK_DEPTH = 8;     // cp.async stages in flight per thread
+constexpr int WALK_CHUNK = 256;   // task descriptors staged in shared memory per pass
+constexpr int WALK_WIN = 32;      // steps per flag window (bits of the mask)
+constexpr int WALK_PF = 24;       // L2 prefetch distance in steps
+constexpr int WALK_SMEM = WALK_DEPTH * TILE * 32;   // dynamic shared memory: the ring, 32 B per thread and stage
+static_assert((WALK_DEPTH & (WALK_DEPTH - 1)) == 0 && WALK_CHUNK % WALK_WIN == 0 && WALK_WIN == 32, "walk geometry");
+
+__global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip) {
+  extern __shared__ __align__(32) double s_ring[];                 // [WALK_DEPTH][TILE][4]
+  __shared__ int4 s_desc[WALK_CHUNK];                              // {out, c0, c1, flags} of the staged tasks
+  __shared__ __align__(16) double s_lut[2 * 64];                   // [set][mask][4] of this block's rate
+  __shared__ unsigned s_win[3];
+  const int tid = threadIdx.x, r = blockIdx.x, tile = blockIdx.y, R = v.R;
+  const int site = tile * TILE + tid;
+  const size_t Sp = (size_t)v.Sp;
+  const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
+  const int slotMask = flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0;
+  if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
+  if (tid < 3) s_win[tid] = 0;
+  const unsigned ringMine = (unsigned)__cvta_generic_to_shared(s_ring) + (unsigned)tid * 32u;
+
+  // the off-chain operand of a step: a stored partial (32 B of this thread's site) or the word holding its tip mask byte
+  auto sibling = [&](const int4& d, bool& isTip) -> const void* {
+    const int fl = d.w ^ slotMask;
+    const bool fwd0 = (fl & (TF_C0FWD | TF_HEAD)) != 0;
+    const int sib = fwd0 ? d.z : d.y;
+    isTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
+    if (isTip) return v.tipmask + (size_t)sib * Sp + (size_t)(site & ~3);
+    return v.partOf(fl & (fwd0 ? TF_C1SLOT : TF_C0SLOT)) + (((size_t)sib * R + r) * Sp + site) * 4;
+  };
+  auto issue = [&](int k) {
+    bool isTip;
+    const void* src = sibling(s_desc[k], isTip);
+    const unsigned dst = ringMine + (unsigned)(k & (WALK_DEPTH - 1)) * (unsigned)(TILE * 32);
+    if (isTip) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"((const char*)src + 16) : "memory");
+    }
+  };
+
+  // the head: child 0 of the first task comes from memory and then plays the forwarded operand
+  double prev[4];
+  {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(tasks));
+    const int fl = d.w ^ slotMask;
+    if (fl & TF_C0TIP) {
+      const unsigned m = v.tipmask[(size_t)d.y * Sp + site];
+#pragma unroll
+      for (int k = 0; k < 4; k++) prev[k] = (m >> k) & 1u ? 1.0 : 0.0;   // P * indicator == the lookup table, bit for bit
+    } else {
+      ld256(v.partOf(fl & TF_C0SLOT) + (((size_t)d.y * R + r) * Sp + site) * 4, prev[0], prev[1], prev[2], prev[3]);
+    }
+  }
+
+  unsigned myMask = 0;              // steps of the current window at which this thread's site rescaled
+  int win = 0;
+  for (int c0 = 0; c0 < nSteps; c0 += WALK_CHUNK) {
+    const int cn = min(WALK_CHUNK, nSteps - c0);
+    __syncthreads();                // the previous chunk's descriptors are no longer needed (first pass: s_lut, s_win)
+    for (int j = tid; j < cn; j += TILE) s_desc[j] = __ldg(reinterpret_cast<const int4*>(tasks + c0 + j));
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WALK_DEPTH - 1; k++) {
+      if (k < cn) issue(k);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int k = 0; k < cn; k++) {
+      if (k + WALK_DEPTH - 1 < cn) issue(k + WALK_DEPTH - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (k + WALK_PF < cn) {
+        bool isTip;
+        const void* src = sibling(s_desc[k + WALK_PF], isTip);
+        if (isTip ? (tid & 127) == 0 : (tid & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+      }
+      asm volatile("cp.async.wait_group %0;" ::"n"(WALK_DEPTH - 1) : "memory");   // the group of step k has landed
+
+      const int4 d = s_desc[k];
+      const int fl = d.w ^ slotMask;
+      const bool fwd0 = (fl & (TF_C0FWD | TF_HEAD)) != 0;
+      const bool sibTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
+      const int set = (fl & TF_WITHIN) ? 1 : 0;
+      const double* P = c_P[set][r];
+      const double* mine = s_ring + ((size_t)(k & (WALK_DEPTH - 1)) * TILE + tid) * 4;
+      double ct[4], sb[4], s4[4];
+      matvec4(P, prev, ct);
+      if (sibTip) {
+        const unsigned w = *reinterpret_cast<const unsigned*>(mine);
+        const unsigned m = (w >> (8 * (tid & 3))) & 0xffu;
+        const double* lutr = s_lut + set * 64;
+#pragma unroll
+        for (int q = 0; q < 4; q++) sb[q] = lutr[4 * m + q];
+      } else {
+        const double x[4] = {mine[0], mine[1], mine[2], mine[3]};
+        matvec4(P, x, sb);
+      }
+      float e = 0.0f;
+      if (fwd0) combineExact(ct, sb, s4, e); else combineExact(sb, ct, s4, e);
+      const int os = (fl & TF_OUTSLOT) ? 1 : 0;
+      const size_t o = ((size_t)d.x * R + r) * Sp + site;
+      st256(v.partOf(os) + o * 4, s4[0], s4[1], s4[2], s4[3]);
+#pragma unroll
+      for (int q = 0; q < 4; q++) prev[q] = s4[q];
+      if (e != 0.0f) { v.expoOf(os)[o] = e; myMask |= 1u << (k & (WALK_WIN - 1)); }
+
+      if ((k & (WALK_WIN - 1)) == WALK_WIN - 1 || k == cn - 1) {
+        // end of a window: three rotating masks, so that one barrier per window orders set -> read -> reset
+        unsigned* sw = &s_win[win % 3];
+        if (myMask) atomicOr(sw, myMask);
+        __syncthreads();
+        const unsigned bm = *(volatile unsigned*)sw;
+        if (tid == 0) s_win[(win + 2) % 3] = 0;
+        const int w0 = k & ~(WALK_WIN - 1), cnt = k - w0 + 1;
+        unsigned z = bm & ~myMask;      // steps that rescaled somewhere in the tile but not at this site: exponent 0
+        while (z) {
+          const int b = __ffs(z) - 1;
+          z &= z - 1;
+          const int4 dz = s_desc[w0 + b];
+          const int oz = ((dz.w ^ slotMask) & TF_OUTSLOT) ? 1 : 0;
+          v.expoOf(oz)[((size_t)dz.x * R + r) * Sp + site] = 0.0f;
+        }
+        if (tid < cnt) {
+          const int4 dz = s_desc[w0 + tid];
+          const int oz = ((dz.w ^ slotMask) & TF_OUTSLOT) ? 1 : 0;
+          v.flagOf(oz)[flagRow + dz.x] = (uint8_t)((bm >> tid) & 1u);
+          if (tile == 0 && r == 0) v.cur[dz.x] = (uint8_t)oz;
+        }
+        myMask = 0;
+        win++;
+      }
+    }
+  }
+}
+
 // rollback: flip the slot bits of the vertices a rejected proposal touched (IntermediateNode.h:26-33)
 __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,8 +19,16 @@ enum : int32_t {
   TF_OUTSLOT = 1, TF_C0TIP = 2, TF_C1TIP = 4, TF_C0SLOT = 8, TF_C1SLOT = 16,
   TF_WITHIN = 32,         // matrix set of this vertex = within-flag of its FIRST child (AugTree.cpp:125)
   TF_C0FUSED = 64, TF_C1FUSED = 128,
-  TF_C0FWD = 256, TF_C1FWD = 512   // proposal paths: the operand is the output of the previous task of the run (registers)
+  TF_C0FWD = 256, TF_C1FWD = 512,  // proposal paths and walked chains: the operand is the output of the previous task
+                                   // of the run, forwarded in registers
+  TF_HEAD = 1024                   // first task of a walked chain: child 0 is read from memory, then plays the forwarded part
 };
+// A plan's trailing levels that hold ONE task each form a chain (every task consumes the previous one's output): a root
+// path, or the spine of a caterpillar.  With at least CHAIN_MIN of them the chain is handed to k_walk, which keeps the
+// running partial in registers and prefetches the off-chain operands many steps ahead, instead of paying a full
+// load -> compute -> store -> load round trip per level.  Fused clades hanging off the chain are MATERIALISED first:
+// evaluated once, in parallel, as ordinary stored tasks into their own (otherwise unused) rows.
+constexpr int CHAIN_MIN = 4;
 
 // One step of a fused-clade program.  The evaluator is a stack machine per thread (= per site): REG holds the
 // partial of the vertex computed last, the stack lives in shared memory.

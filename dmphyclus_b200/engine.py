@@ -40,7 +40,8 @@ class Stats(C.Structure):
                 ("last_host_plan_us", C.c_double), ("last_host_submit_us", C.c_double), ("last_host_total_us", C.c_double),
                 ("create_setup_us", C.c_double), ("create_upload_ms", C.c_double),
                 ("last_chain_sites", C.c_int), ("last_chain_rows", C.c_int), ("chain_group", C.c_int),
-                ("plan_cache_hits", C.c_ulonglong), ("graph_replays", C.c_ulonglong)]
+                ("plan_cache_hits", C.c_ulonglong), ("graph_replays", C.c_ulonglong),
+                ("last_walk_steps", C.c_int), ("last_materialised", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,7 +70,7 @@ ABI = {
     "dmpc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dmpc_timer_begin": (C.c_int, [_P]),
     "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
-    "dmpc_plan_selfcheck": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "dmpc_plan_selfcheck": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "dmpc_get_partial": (C.c_int, [_P, C.c_int, _dbl_p, _f32_p]),
     "dmpc_get_topology": (C.c_int, [_P, _i32_p, _i32_p, _i32_p, _i32_p]),
     "dmpc_get_site_logliks": (C.c_int, [_P, _dbl_p]),

@@ -157,6 +157,9 @@ typedef struct dmpc_stats {
   int chain_group;          /* rows per group the chain walker will use next (4, or 1 for sparse exponent lists) */
   unsigned long long plan_cache_hits;   /* full evaluations that replayed the device-resident plan */
   unsigned long long graph_replays;     /* ... of which submitted as one CUDA graph launch */
+  int last_walk_steps;      /* vertices of the last evaluation's trailing chain, evaluated by the walk kernel with the
+                               running partial in registers (0: no chain of at least 4 single-task levels) */
+  int last_materialised;    /* fused-size clades hanging off that chain, evaluated once as stored tasks beforehand */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
@@ -168,10 +171,14 @@ int dmpc_timer_end(dmpc_tree* t, double* msOut);
  * cluster flags, plans a full evaluation with the given fusion threshold and verifies the invariants the kernels rely
  * on — every internal vertex computed exactly once (as a stored task or a fused token), children before parents across
  * levels, fused clades no larger than the threshold, stack depth within FUSE_DEPTH, tip lists and token ranges
- * consistent.  out[0..5] = stored vertices, fused vertices, levels, tokens, max stack depth, max tips of a task's programs.
- * Returns DMPC_OK or DMPC_ERR_STATE with the violated invariant in dmpc_last_error(). */
+ * consistent; the trailing chain handed to the walk kernel is one task per level, each forwarding into the next, with
+ * the fused clades hanging off it materialised in level 0.  dirtyVertex = 0 checks the plan of a full evaluation;
+ * dirtyVertex = a 1-based internal vertex id checks the plan of the proposal that follows a full evaluation and
+ * invalidates that vertex and its ancestors (a split / merge / NNI root path).
+ * out[0..7] = stored vertices, fused vertices, levels, tokens, max stack depth, max tips of a task's programs, chain
+ * levels, materialised clades.  Returns DMPC_OK or DMPC_ERR_STATE with the violated invariant in dmpc_last_error(). */
 int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
-                        int fuseTips, int* out);
+                        int fuseTips, int dirtyVertex, int* out);
 
 /* Introspection for parity tests: the committed partial of a vertex (0-based id >= numTips) as
  * sol [numLoci][R][4] and expo [numLoci][R] (the oracle's layout), and the topology/flags. */

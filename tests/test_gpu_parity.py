@@ -292,6 +292,69 @@ def test_fused_vertices_are_readable(packaged, engine, oracle):
     engine.finalDeallocate(hg); oracle.finalDeallocate(ho)
 
 
+# ---------------------------------------------------------------------------------------------- walked chains
+@pytest.mark.parametrize("n,S,R,kind,fuse", [(3000, 300, 3, "iid", 15), (700, 520, 3, "evolved", 1), (1200, 257, 2, "diverged", 4)])
+def test_caterpillar_spine_is_walked(packaged, oracle, n, S, R, kind, fuse):
+    """A caterpillar's spine is one chain of single-task levels: k_walk evaluates it with the running partial in
+    registers (many descriptor chunks and flag windows, several site tiles, rescaling at most steps on iid data).
+    Partials bit-exact and exponents to the last bit at vertices all along the spine."""
+    from dmphyclus_b200.engine import Engine
+    eng = Engine(fuse_tips=fuse)
+    p = Problem(packaged, n, S, 4, R, kind, "caterpillar", seed=n + fuse)
+    hg, lg = p.create(eng)
+    ho, lo = p.create(oracle)
+    st = eng.stats(hg)
+    assert st["last_walk_steps"] >= n - 1 - 16 and st["last_walk_steps"] + st["last_materialised"] + 4 >= st["last_stored_vertices"]
+    assert rel(lg, lo) < TOL, (lg, lo)
+    for v in sorted({n, n + 1, n + 31, n + 32, n + 255, n + 256, n + 257, n + (n - 1) // 2, 2 * n - 20, 2 * n - 2}):
+        (sg, eg), (so, eo) = eng.partial(hg, v), oracle.partial(ho, v)
+        assert np.array_equal(sg, so), f"partials of vertex {v} differ"
+        assert np.allclose(eg, eo, rtol=2e-7, atol=0), f"exponents of vertex {v} differ"
+    assert eng.recomputeAll(hg, p.W[4], p.B[4], p.pi) == lg          # cached plan + graph replay of the same chain
+    a = eng.newBetweenTransProbsLogLik(hg, p.W[4], p.B[1], 1, 2, p.pi)
+    b = oracle.newBetweenTransProbsLogLik(ho, p.W[4], p.B[1], 1, 2, p.pi)
+    assert rel(a, b) < TOL
+    eng.finalDeallocate(hg); oracle.finalDeallocate(ho)
+
+
+@pytest.mark.parametrize("n,S,k,R,kind,fuse", [(1000, 300, 24, 3, "evolved", 15), (1000, 300, 24, 3, "iid", 8), (600, 260, 12, 1, "diverged", 15)])
+def test_root_path_proposals_are_walked(packaged, oracle, n, S, k, R, kind, fuse):
+    """Split / merge proposals dirty one root path: a chain.  The fused clades hanging off it are materialised (stored
+    for the occasion), the path is walked; accepted or rejected, every partial along the path, the rollback and the
+    next full evaluation agree with the oracle."""
+    from dmphyclus_b200.engine import Engine
+    from dmphyclus_b200.phylo import Phylo
+    eng = Engine(fuse_tips=fuse)
+    p = Problem(packaged, n, S, k, R, kind, seed=n + k + fuse)
+    hg, l0 = p.create(eng)
+    ho, _ = p.create(oracle)
+    W, B = p.W[4], p.B[4]
+    phy = Phylo(p.edge, p.n)
+    walked = mats = 0
+    props = _split_merge_candidates(p)
+    assert len(props) >= 6
+    for i, q in enumerate(props[:10]):
+        ids = [q[1]] if q[0] == "split" else [q[1], q[2]]
+        got = eng.clusSplitMergeLogLik(hg, W, B, ids, 1, p.pi)
+        want = oracle.clusSplitMergeLogLik(ho, W, B, ids, 1, p.pi)
+        assert rel(got, want) < TOL, (q, got, want)
+        st = eng.stats(hg)
+        walked += st["last_walk_steps"] > 0
+        mats += st["last_materialised"]
+        v = ids[0] if q[0] == "split" else int(phy.parent[ids[0]])
+        while v:                                            # every vertex of the dirtied path, stored or fused
+            (sg, eg), (so, eo) = eng.partial(hg, v), oracle.partial(ho, v)
+            assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=2e-7, atol=0), (q, v)
+            v = int(phy.parent[v])
+        for be, h in ((eng, hg), (oracle, ho)):
+            be.RestorePreviousConfig(h, np.zeros((1, 2), np.int32), 5, 5, False, p.mrcas, True)
+        if i % 3 == 2:
+            assert np.array_equal(eng.partial(hg, p.n)[0], oracle.partial(ho, p.n)[0])
+    assert walked > 0 and (fuse == 1 or mats > 0)
+    assert eng.recomputeAll(hg, W, B, p.pi) == l0
+    eng.finalDeallocate(hg); oracle.finalDeallocate(ho)
+
+
 # ---------------------------------------------------------------------------------------------- proposal batches
 def _split_merge_candidates(p):
     """Every legal split (clusters whose MRCA is internal) and merge (sibling cluster MRCAs) of the current clustering."""

@@ -111,26 +111,46 @@ def test_workload_shapes_match_baseline():
 @pytest.mark.parametrize("shape", ["random", "balanced", "caterpillar"])
 @pytest.mark.parametrize("fuse", [1, 2, 3, 4, 8, 15])
 def test_plan_builder_invariants(shape, fuse):
-    """The host-side plan (stored tasks per level + fused-clade token programs) over many trees: every vertex
-    computed exactly once, children before parents, stack depth and staging sizes within what k_prune assumes."""
+    """The host-side plan (stored tasks per level + fused-clade token programs + the walked chain) over many trees:
+    every vertex computed exactly once, children before parents, stack depth and staging sizes within what k_prune
+    assumes; the trailing chain is one task per level forwarding into the next, with the fused clades hanging off it
+    materialised in level 0.  Checked for full evaluations and for root-path proposals from many vertices."""
     import ctypes as C
     from dmphyclus_b200 import build
     from dmphyclus_b200.engine import load_library
     build.build()
     lib = load_library()
+    chains = mats = 0
     for n in (2, 3, 5, 16, 17, 64, 257, 1000):
         rng = np.random.default_rng(n * 31 + fuse)
         e = synth.random_tree(n, rng, shape)
         mrcas, _ = synth.pick_clusters(e, n, min(5, n))
         edge = np.ascontiguousarray(e.T, dtype=np.int32).ravel()
         m = np.asarray(mrcas, np.float64)
-        out = (C.c_int * 6)()
-        rc = lib.dmpc_plan_selfcheck(edge.ctypes.data_as(C.POINTER(C.c_int32)), len(edge) // 2, n,
-                                     m.ctypes.data_as(C.POINTER(C.c_double)), len(m), fuse, out)
-        assert rc == 0, (n, shape, fuse, lib.dmpc_last_error().decode())
-        stored, fused, levels, tokens, depth, tips = list(out)
+        out = (C.c_int * 8)()
+
+        def check(dirty):
+            rc = lib.dmpc_plan_selfcheck(edge.ctypes.data_as(C.POINTER(C.c_int32)), len(edge) // 2, n,
+                                         m.ctypes.data_as(C.POINTER(C.c_double)), len(m), fuse, dirty, out)
+            assert rc == 0, (n, shape, fuse, dirty, lib.dmpc_last_error().decode())
+            return list(out)
+
+        stored, fused, levels, tokens, depth, tips, chain_levels, materialised = check(0)
         assert stored + fused == n - 1 and depth <= 3 and tips <= 30
+        assert chain_levels == 0 or chain_levels >= 4
         if fuse == 1:
-            assert fused == 0 and tokens == 0
+            assert fused == 0 and tokens == 0 and materialised == 0
         if shape == "caterpillar" and n > 40:
             assert stored >= n - 1 - fuse          # only the bottom of a caterpillar can be fused
+            assert chain_levels >= stored - 2      # ... and its spine is one long chain
+        # proposals: the root path from a sample of internal vertices (InvalidateSolution, IntermediateNode.cpp:5-13)
+        internal = np.arange(n + 1, 2 * n)
+        for v in (internal if n <= 64 else rng.choice(internal, 48, replace=False)):
+            o = check(int(v))
+            assert o[6] == 0 or (o[6] >= 4 and o[6] <= o[2])
+            if o[6]:
+                assert o[6] + (1 if o[7] else 0) == o[2]      # a single path: everything but the materialised level is chain
+            chains += o[6] > 0
+            mats += o[7]
+    if fuse > 1 and shape == "random":
+        assert chains > 0 and mats > 0
