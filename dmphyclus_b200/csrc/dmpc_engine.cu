@@ -715,6 +715,8 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
   t->T = t->Sp / TILE;
   t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
+  // k_walk addresses partials by 32-bit element offsets (an element = one 32-byte 4-vector): fine up to 137 GB per slot
+  t->ht.walkChains = (unsigned long long)t->nInt * t->R * t->Sp < (1ull << 32);
   t->quirk = o.quirk_carry != 0;
   t->deferred = o.deferred != 0;
   t->comm = (dmpc_comm*)o.comm;

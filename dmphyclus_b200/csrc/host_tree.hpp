@@ -61,6 +61,7 @@ struct HostTree {
   std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
   bool tipsValid = false;
   std::vector<uint8_t> mat;              // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
+  bool walkChains = true;                // false: never hand a chain to k_walk (its 32-bit element offsets would overflow)
   bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
 
   bool isTip(int v) const { return v < numTips; }
@@ -349,7 +350,7 @@ struct HostTree {
     int chainL0 = maxLevel + 1;
     for (int l = maxLevel; l >= 1 && p.cnt[l] == 1; l--) chainL0 = l;
     p.chainLevels = maxLevel - chainL0 + 1;
-    if (p.chainLevels < CHAIN_MIN) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
+    if (p.chainLevels < CHAIN_MIN || !walkChains) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
     std::vector<int> matList;                // fused clades hanging off the chain: stored tasks of a leading level
     if (p.chainLevels)
       for (int v : pre)

@@ -173,17 +173,19 @@ __device__ __forceinline__ bool maybeBelow4(const double (&s)[4]) {       // con
   return __double2hiint(s[0]) < H && __double2hiint(s[1]) < H && __double2hiint(s[2]) < H && __double2hiint(s[3]) < H;
 }
 // IntermediateNode.cpp:53-66 for one category: first child, check, second child, check (the second OVERWRITES)
+// The exact test is guarded by the conservative high-word one: four independent integer compares instead of a chain of
+// four dependent fp64 compares on the common (no rescale) path.  below4 implies maybeBelow4 for every non-NaN input.
 __device__ __forceinline__ void combineExact(const double (&first)[4], const double (&second)[4], double (&s)[4], float& e) {
 #pragma unroll
   for (int i = 0; i < 4; i++) s[i] = first[i];                  // ones % y == y exactly
-  if (below4(s)) {
+  if (maybeBelow4(s) && below4(s)) {
     const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
     s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
     e = (float)log(m);
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) s[i] = __dmul_rn(s[i], second[i]);
-  if (below4(s)) {
+  if (maybeBelow4(s) && below4(s)) {
     const double m = fmax(fmax(s[0], s[1]), fmax(s[2], s[3]));
     s[0] = s[0] / m; s[1] = s[1] / m; s[2] = s[2] / m; s[3] = s[3] / m;
     e = (float)log(m);
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
 // ~1.3 us measured); here one thread owns one (site, rate) for the whole chain, keeps the running partial in
 // registers, and everything that does NOT depend on the chain — the task descriptors and the off-chain operands
 // (stored partials, tip mask bytes; fused clades were materialised by the plan builder) — is fetched WALK_DEPTH steps
-// ahead with cp.async into a per-thread ring in shared memory (and WALK_PF steps ahead into L2), so that a step costs
+// ahead with cp.async into a per-thread ring in shared memory, so that a step costs
 // its dependent arithmetic only: sol = (P prev) % (P sib) with the reference's two rescale checks
 // (IntermediateNode.cpp:53-66, same combineExact as k_prune), one 256-bit store of the vertex's partial.
 // grid = (R, site tiles), TILE threads.  Rescale bookkeeping keeps k_prune's format (exponent rows only for tiles
@@ -464,44 +466,47 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
 // rescales writes its own exponent at once and remembers the step in a bit mask; every WALK_WIN steps the block ORs
 // the masks, the other threads fill in their zeros for the steps that rescaled somewhere, and the flags are written.
 constexpr int WALK_DEPTH = 8;     // cp.async stages in flight per thread
-constexpr int WALK_CHUNK = 256;   // task descriptors staged in shared memory per pass
+constexpr int WALK_CHUNK = 256;   // steps whose descriptors are staged in shared memory per pass
 constexpr int WALK_WIN = 32;      // steps per flag window (bits of the mask)
-constexpr int WALK_PF = 24;       // L2 prefetch distance in steps
 constexpr int WALK_SMEM = WALK_DEPTH * TILE * 32;   // dynamic shared memory: the ring, 32 B per thread and stage
 static_assert((WALK_DEPTH & (WALK_DEPTH - 1)) == 0 && WALK_CHUNK % WALK_WIN == 0 && WALK_WIN == 32, "walk geometry");
+// a step as the walking threads see it: everything that is uniform across the block is worked out ONCE per step while
+// the chunk is staged (one thread per step), so that the per-step instruction stream of a walking warp — which is what
+// bounds a chain: a lone warp issues one dependent instruction every ~5 cycles — stays short.
+// x = element offset of the output row (vertex, this rate), y = element offset of the off-chain operand's row (stored)
+// or byte offset of its mask row (tip), z = flags, w = output vertex (for the flag / slot bookkeeping)
+enum : int { WF_OUTSLOT = 1, WF_SIBTIP = 2, WF_SIBSLOT = 4, WF_SET = 8, WF_FWD0 = 16 };
 
 __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip) {
   extern __shared__ __align__(32) double s_ring[];                 // [WALK_DEPTH][TILE][4]
-  __shared__ int4 s_desc[WALK_CHUNK];                              // {out, c0, c1, flags} of the staged tasks
+  __shared__ uint4 s_desc[WALK_CHUNK];
   __shared__ __align__(16) double s_lut[2 * 64];                   // [set][mask][4] of this block's rate
+  __shared__ __align__(16) double s_P[2 * 16];                     // both matrix sets of this block's rate
   __shared__ unsigned s_win[3];
   const int tid = threadIdx.x, r = blockIdx.x, tile = blockIdx.y, R = v.R;
-  const int site = tile * TILE + tid;
+  const unsigned site = (unsigned)(tile * TILE + tid);
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
   const int slotMask = flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0;
   if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
+  if (tid < 2 * 16) s_P[tid] = c_P[tid >> 4][r][tid & 15];
   if (tid < 3) s_win[tid] = 0;
   const unsigned ringMine = (unsigned)__cvta_generic_to_shared(s_ring) + (unsigned)tid * 32u;
+  double* const part0 = v.part[0];
+  double* const part1 = v.part[1];
+  const uint8_t* const maskMine = v.tipmask + (site & ~3u);        // the word holding this site's mask byte, row 0
 
-  // the off-chain operand of a step: a stored partial (32 B of this thread's site) or the word holding its tip mask byte
-  auto sibling = [&](const int4& d, bool& isTip) -> const void* {
-    const int fl = d.w ^ slotMask;
-    const bool fwd0 = (fl & (TF_C0FWD | TF_HEAD)) != 0;
-    const int sib = fwd0 ? d.z : d.y;
-    isTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
-    if (isTip) return v.tipmask + (size_t)sib * Sp + (size_t)(site & ~3);
-    return v.partOf(fl & (fwd0 ? TF_C1SLOT : TF_C0SLOT)) + (((size_t)sib * R + r) * Sp + site) * 4;
-  };
+  // the off-chain operand of step k of the staged chunk -> this thread's 32 bytes of ring stage k % WALK_DEPTH
   auto issue = [&](int k) {
-    bool isTip;
-    const void* src = sibling(s_desc[k], isTip);
+    const uint4 d = s_desc[k];
     const unsigned dst = ringMine + (unsigned)(k & (WALK_DEPTH - 1)) * (unsigned)(TILE * 32);
-    if (isTip) {
+    if (d.z & WF_SIBTIP) {
+      const uint8_t* src = maskMine + d.y;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
     } else {
+      const double* src = ((d.z & WF_SIBSLOT) ? part1 : part0) + (size_t)(d.y + site) * 4;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"((const char*)src + 16) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 2) : "memory");
     }
   };
 
@@ -519,12 +524,27 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
     }
   }
 
+  double P[16];                     // the matrix set of the current step, in registers; reloaded only when the set changes
+  int curSet = -1;
   unsigned myMask = 0;              // steps of the current window at which this thread's site rescaled
   int win = 0;
   for (int c0 = 0; c0 < nSteps; c0 += WALK_CHUNK) {
     const int cn = min(WALK_CHUNK, nSteps - c0);
-    __syncthreads();                // the previous chunk's descriptors are no longer needed (first pass: s_lut, s_win)
-    for (int j = tid; j < cn; j += TILE) s_desc[j] = __ldg(reinterpret_cast<const int4*>(tasks + c0 + j));
+    __syncthreads();                // the previous chunk's descriptors are no longer needed (first pass: s_lut, s_P, s_win)
+    for (int j = tid; j < cn; j += TILE) {
+      const int4 d = __ldg(reinterpret_cast<const int4*>(tasks + c0 + j));
+      const int fl = d.w ^ slotMask;
+      const bool fwd0 = (fl & (TF_C0FWD | TF_HEAD)) != 0;
+      const int sib = fwd0 ? d.z : d.y;
+      const bool sibTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
+      uint4 w;
+      w.x = (unsigned)(((size_t)d.x * R + r) * Sp);
+      w.y = sibTip ? (unsigned)((size_t)sib * Sp) : (unsigned)(((size_t)sib * R + r) * Sp);
+      w.z = ((fl & TF_OUTSLOT) ? WF_OUTSLOT : 0) | (sibTip ? WF_SIBTIP : 0) | ((fl & (fwd0 ? TF_C1SLOT : TF_C0SLOT)) ? WF_SIBSLOT : 0) |
+            ((fl & TF_WITHIN) ? WF_SET : 0) | (fwd0 ? WF_FWD0 : 0);
+      w.w = (unsigned)d.x;
+      s_desc[j] = w;
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < WALK_DEPTH - 1; k++) {
@@ -534,23 +554,18 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
     for (int k = 0; k < cn; k++) {
       if (k + WALK_DEPTH - 1 < cn) issue(k + WALK_DEPTH - 1);
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (k + WALK_PF < cn) {
-        bool isTip;
-        const void* src = sibling(s_desc[k + WALK_PF], isTip);
-        if (isTip ? (tid & 127) == 0 : (tid & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-      }
       asm volatile("cp.async.wait_group %0;" ::"n"(WALK_DEPTH - 1) : "memory");   // the group of step k has landed
 
-      const int4 d = s_desc[k];
-      const int fl = d.w ^ slotMask;
-      const bool fwd0 = (fl & (TF_C0FWD | TF_HEAD)) != 0;
-      const bool sibTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
-      const int set = (fl & TF_WITHIN) ? 1 : 0;
-      const double* P = c_P[set][r];
+      const uint4 d = s_desc[k];
+      const int set = (d.z & WF_SET) ? 1 : 0;
+      if (set != curSet) {          // uniform; rare (a root path crosses from within-cluster to between-cluster matrices once)
+        curSet = set;
+#pragma unroll
+        for (int q = 0; q < 16; q++) P[q] = s_P[set * 16 + q];
+      }
       const double* mine = s_ring + ((size_t)(k & (WALK_DEPTH - 1)) * TILE + tid) * 4;
       double ct[4], sb[4], s4[4];
-      matvec4(P, prev, ct);
-      if (sibTip) {
+      if (d.z & WF_SIBTIP) {
         const unsigned w = *reinterpret_cast<const unsigned*>(mine);
         const unsigned m = (w >> (8 * (tid & 3))) & 0xffu;
         const double* lutr = s_lut + set * 64;
@@ -560,14 +575,14 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
         const double x[4] = {mine[0], mine[1], mine[2], mine[3]};
         matvec4(P, x, sb);
       }
+      matvec4(P, prev, ct);
       float e = 0.0f;
-      if (fwd0) combineExact(ct, sb, s4, e); else combineExact(sb, ct, s4, e);
-      const int os = (fl & TF_OUTSLOT) ? 1 : 0;
-      const size_t o = ((size_t)d.x * R + r) * Sp + site;
-      st256(v.partOf(os) + o * 4, s4[0], s4[1], s4[2], s4[3]);
+      if (d.z & WF_FWD0) combineExact(ct, sb, s4, e); else combineExact(sb, ct, s4, e);
+      double* const outp = ((d.z & WF_OUTSLOT) ? part1 : part0) + (size_t)(d.x + site) * 4;
+      st256(outp, s4[0], s4[1], s4[2], s4[3]);
 #pragma unroll
       for (int q = 0; q < 4; q++) prev[q] = s4[q];
-      if (e != 0.0f) { v.expoOf(os)[o] = e; myMask |= 1u << (k & (WALK_WIN - 1)); }
+      if (e != 0.0f) { v.expoOf(d.z & WF_OUTSLOT)[(size_t)d.x + site] = e; myMask |= 1u << (k & (WALK_WIN - 1)); }
 
       if ((k & (WALK_WIN - 1)) == WALK_WIN - 1 || k == cn - 1) {
         // end of a window: three rotating masks, so that one barrier per window orders set -> read -> reset
@@ -581,15 +596,14 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
         while (z) {
           const int b = __ffs(z) - 1;
           z &= z - 1;
-          const int4 dz = s_desc[w0 + b];
-          const int oz = ((dz.w ^ slotMask) & TF_OUTSLOT) ? 1 : 0;
-          v.expoOf(oz)[((size_t)dz.x * R + r) * Sp + site] = 0.0f;
+          const uint4 dz = s_desc[w0 + b];
+          v.expoOf(dz.z & WF_OUTSLOT)[(size_t)dz.x + site] = 0.0f;
         }
         if (tid < cnt) {
-          const int4 dz = s_desc[w0 + tid];
-          const int oz = ((dz.w ^ slotMask) & TF_OUTSLOT) ? 1 : 0;
-          v.flagOf(oz)[flagRow + dz.x] = (uint8_t)((bm >> tid) & 1u);
-          if (tile == 0 && r == 0) v.cur[dz.x] = (uint8_t)oz;
+          const uint4 dz = s_desc[w0 + tid];
+          const int oz = dz.z & WF_OUTSLOT;
+          v.flagOf(oz)[flagRow + dz.w] = (uint8_t)((bm >> tid) & 1u);
+          if (tile == 0 && r == 0) v.cur[dz.w] = (uint8_t)oz;
         }
         myMask = 0;
         win++;
