@@ -7,6 +7,7 @@
 // (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
 #include "../../include/dmpc.h"
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -33,6 +34,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status block
+// a plan never holds more than one task per internal vertex, two tokens and two tip-list entries per fused vertex
+constexpr size_t PLAN_BYTES = sizeof(Task) + 2 * sizeof(Token) + 2 * sizeof(int32_t);
 
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
 // and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
@@ -40,11 +43,10 @@ typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status bloc
 struct ResPack {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  Task* h_tasks = nullptr;       // pinned
+  char* h_plan = nullptr;        // pinned: tasks | tokens | tip list of one evaluation, packed, uploaded in ONE copy
   int32_t* h_curList = nullptr;  // pinned
-  Token* h_tokens = nullptr;     // pinned
-  int32_t* h_tipList = nullptr;  // pinned
-  HostResult* h_res = nullptr;   // pinned
+  HostResult* h_res = nullptr;   // pinned + mapped: k_root_gather publishes the status block straight into it
+  HostResult* d_res = nullptr;   // ... its device-side address
   double* h_chunks = nullptr;    // pinned
   size_t cap = 0;                // internal vertices the pinned buffers can hold
   size_t chunkCap = 0;
@@ -82,8 +84,8 @@ struct dmpc_tree {
   RootView rv{};
   uint8_t* d_tipmask = nullptr;
   double* d_lut = nullptr;
-  Task* d_tasks = nullptr;
-  Task* h_tasks = nullptr;       // pinned
+  char* d_plan = nullptr;        // tasks | tokens | tip list of the current evaluation (PLAN_BYTES per internal vertex)
+  char* h_plan = nullptr;        // pinned
   int32_t* d_curList = nullptr;
   int32_t* h_curList = nullptr;  // pinned
   HostResult* h_res = nullptr;   // pinned
@@ -103,7 +105,8 @@ struct dmpc_tree {
     std::vector<int32_t> kids;
     std::vector<uint8_t> within, cur;
     HostTree::Plan meta;                 // level structure and counters (the big vectors stay empty)
-    Task* dTasks = nullptr; Token* dTokens = nullptr; int32_t* dTips = nullptr;
+    char* dPlan = nullptr;               // device copy of the packed plan
+    size_t offTok = 0, offTip = 0, bytes = 0;
     int metaTasks = 0;
   } cache;
   unsigned long long planCacheHits = 0;
@@ -113,10 +116,9 @@ struct dmpc_tree {
   bool capturing = false, gatherPrelaunched = false;
   unsigned long long graphReplays = 0;
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
-  Token* d_tokens = nullptr;
-  Token* h_tokens = nullptr;     // pinned
-  int32_t* d_tipList = nullptr;
-  int32_t* h_tipList = nullptr;  // pinned
+  size_t planOffTok = 0, planOffTip = 0, planBytes = 0;   // layout of the plan last packed into d_plan
+  unsigned pubExpected = 0;      // status publications k_root_gather has been asked for so far (see DevStatus::pubSeq)
+  bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
@@ -156,23 +158,22 @@ int acquirePack(dmpc_tree* t) {
     }
     if (!cx.freePacks.empty()) { t->pack = cx.freePacks.back(); cx.freePacks.pop_back(); }
   }
+  if (t->pack.h_res) std::memset(t->pack.h_res, 0, sizeof(HostResult));   // an idle pack: nothing is in flight; pubSeq restarts at 0
   ResPack& p = t->pack;
   if (!p.stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
     for (auto& e : p.ev) CUDA_TRY(cudaEventCreate(&e));
-    CUDA_TRY(cudaHostAlloc((void**)&p.h_res, sizeof(HostResult), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_res, sizeof(HostResult), cudaHostAllocMapped));
+    std::memset(p.h_res, 0, sizeof(HostResult));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&p.d_res, p.h_res, 0));
   }
   if (p.cap < (size_t)t->nInt) {
-    if (p.h_tasks) cudaFreeHost(p.h_tasks);
+    if (p.h_plan) cudaFreeHost(p.h_plan);
     if (p.h_curList) cudaFreeHost(p.h_curList);
-    if (p.h_tokens) cudaFreeHost(p.h_tokens);
-    if (p.h_tipList) cudaFreeHost(p.h_tipList);
-    p.h_tasks = nullptr; p.h_curList = nullptr; p.h_tokens = nullptr; p.h_tipList = nullptr; p.cap = 0;
+    p.h_plan = nullptr; p.h_curList = nullptr; p.cap = 0;
     const size_t cap = std::max<size_t>(1024, (size_t)t->nInt * 5 / 4);
-    CUDA_TRY(cudaHostAlloc((void**)&p.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_plan, cap * PLAN_BYTES, cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_curList, cap * sizeof(int32_t), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc((void**)&p.h_tokens, 2 * cap * sizeof(Token), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc((void**)&p.h_tipList, 2 * cap * sizeof(int32_t), cudaHostAllocDefault));
     p.cap = cap;
   }
   if (p.chunkCap < (size_t)t->nChunks) {
@@ -185,7 +186,8 @@ int acquirePack(dmpc_tree* t) {
   t->h_chunks = p.h_chunks;
   t->stream = p.stream;
   for (int i = 0; i < 7; i++) t->ev[i] = p.ev[i];
-  t->h_tasks = p.h_tasks; t->h_curList = p.h_curList; t->h_res = p.h_res; t->h_tokens = p.h_tokens; t->h_tipList = p.h_tipList;
+  t->h_plan = p.h_plan; t->h_curList = p.h_curList; t->h_res = p.h_res;
+  t->rv.hostSt = p.d_res;
   return DMPC_OK;
 }
 
@@ -227,12 +229,16 @@ int allocSlot(dmpc_tree* t, int slot) {
   return DMPC_OK;
 }
 
-int allocElist(dmpc_tree* t, int kcap) {
-  // the previous list (if any) stays in the pool until the handle dies; growth is rare and geometric
+void setElistGeometry(dmpc_tree* t, int kcap) {
   t->rv.Kcap = kcap;
   t->graphVersion++;
   t->rv.Q = std::max(512, (kcap + 3) & ~3);       // >= the padded length of any site's list, multiple of both group sizes
   t->st.exponent_capacity = kcap;
+}
+
+int allocElist(dmpc_tree* t, int kcap) {
+  // the previous list stays allocated until the handle dies; growth is rare and geometric
+  setElistGeometry(t, kcap);
   return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
 }
 
@@ -303,6 +309,26 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
   a.tasks = lt; a.nTasks = nTasks; a.prog = t->runTokens; a.tipList = t->runTips; a.violation = &t->rv.st->violation; a.flip = t->runFlip;
   if (t->exact) k_prune<true, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
   else k_prune<false, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
+  return DMPC_OK;
+}
+
+// tasks | tokens | tip list of a plan, packed into the pinned staging buffer and uploaded in ONE copy; sets what
+// runPlan / launchPrune read
+int uploadPlan(dmpc_tree* t, const HostTree::Plan& p) {
+  const size_t nT = p.tasks.size(), nK = p.tokens.size(), nL = p.tipList.size();
+  if (nT > (size_t)t->nInt || nK > 2 * (size_t)t->nInt || nL > 2 * (size_t)t->nInt)
+    return fail(DMPC_ERR_STATE, "plan larger than its staging buffer");
+  t->planOffTok = nT * sizeof(Task);
+  t->planOffTip = t->planOffTok + nK * sizeof(Token);
+  t->planBytes = t->planOffTip + nL * sizeof(int32_t);
+  if (nT) std::memcpy(t->h_plan, p.tasks.data(), nT * sizeof(Task));
+  if (nK) std::memcpy(t->h_plan + t->planOffTok, p.tokens.data(), nK * sizeof(Token));
+  if (nL) std::memcpy(t->h_plan + t->planOffTip, p.tipList.data(), nL * sizeof(int32_t));
+  if (t->planBytes) CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
+  t->runTasks = reinterpret_cast<const Task*>(t->d_plan);
+  t->runTokens = reinterpret_cast<const Token*>(t->d_plan + t->planOffTok);
+  t->runTips = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffTip);
+  t->runFlip = 0;
   return DMPC_OK;
 }
 
@@ -385,38 +411,26 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     ht.allInvalid = false;
     if ((rc = allocSlot(t, 0)) || (rc = allocSlot(t, 1))) return rc;
     meta = &cc.meta;
-    t->runTasks = cc.dTasks; t->runTokens = cc.dTokens; t->runTips = cc.dTips; t->runFlip = flip;
+    t->runTasks = reinterpret_cast<const Task*>(cc.dPlan);
+    t->runTokens = reinterpret_cast<const Token*>(cc.dPlan + cc.offTok);
+    t->runTips = reinterpret_cast<const int32_t*>(cc.dPlan + cc.offTip);
+    t->runFlip = flip;
     t->planCacheHits++;
   } else {
     std::vector<uint8_t> curBefore;
     if (full) curBefore = ht.cur;
     ht.plan(p);
-    t->runTasks = t->d_tasks; t->runTokens = t->d_tokens; t->runTips = t->d_tipList; t->runFlip = 0;
-    const int nT = (int)p.tasks.size(), nK = (int)p.tokens.size();
+    const int nT = (int)p.tasks.size();
     if (nT) {
       for (int sl = 0; sl < 2; sl++)
         if (p.uses[sl] && (rc = allocSlot(t, sl))) return rc;
-      std::memcpy(t->h_tasks, p.tasks.data(), (size_t)nT * sizeof(Task));
-      CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, (size_t)nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
-      if (nK) {
-        std::memcpy(t->h_tokens, p.tokens.data(), (size_t)nK * sizeof(Token));
-        CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, (size_t)nK * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
-        std::memcpy(t->h_tipList, p.tipList.data(), p.tipList.size() * sizeof(int32_t));
-        CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
-      }
     }
-    if (full && nT) {                                // remember it (device-to-device copies, stream-ordered)
+    if ((rc = uploadPlan(t, p))) return rc;
+    if (full && nT) {                                // remember it (one device-to-device copy, stream-ordered)
       int r2;
-      if (!cc.dTasks) {
-        if ((r2 = t->alloc(&cc.dTasks, (size_t)t->nInt)) || (r2 = t->alloc(&cc.dTokens, (size_t)2 * t->nInt)) ||
-            (r2 = t->alloc(&cc.dTips, (size_t)2 * t->nInt)))
-          return r2;
-      }
-      CUDA_TRY(cudaMemcpyAsync(cc.dTasks, t->d_tasks, (size_t)nT * sizeof(Task), cudaMemcpyDeviceToDevice, t->stream));
-      if (nK) {
-        CUDA_TRY(cudaMemcpyAsync(cc.dTokens, t->d_tokens, (size_t)nK * sizeof(Token), cudaMemcpyDeviceToDevice, t->stream));
-        CUDA_TRY(cudaMemcpyAsync(cc.dTips, t->d_tipList, p.tipList.size() * sizeof(int32_t), cudaMemcpyDeviceToDevice, t->stream));
-      }
+      if (!cc.dPlan && (r2 = t->alloc(&cc.dPlan, (size_t)t->nInt * PLAN_BYTES))) return r2;
+      CUDA_TRY(cudaMemcpyAsync(cc.dPlan, t->d_plan, t->planBytes, cudaMemcpyDeviceToDevice, t->stream));
+      cc.offTok = t->planOffTok; cc.offTip = t->planOffTip; cc.bytes = t->planBytes;
       cc.kids = ht.kids; cc.within = ht.within; cc.cur = curBefore; cc.fuse = ht.fuseTips;
       cc.meta.levelStart = p.levelStart;
       cc.meta.chainLevels = p.chainLevels; cc.meta.materialised = p.materialised;
@@ -453,6 +467,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     }
     CUDA_TRY(cudaGraphLaunch(g.exec, t->stream));
     t->gatherPrelaunched = true;
+    t->pubExpected++;
     t->graphReplays++;
     t->st.kernel_launches += t->st.last_prune_launches + 1;
   } else if ((rc = runPlan(t))) {
@@ -505,7 +520,7 @@ int launchGather(dmpc_tree* t, int mode) {
   if (t->rv.RP == 4) k_root_gather<4, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
   else k_root_gather<8, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
   t->st.kernel_launches++;
-  if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  if (!t->capturing) { CUDA_TRY(cudaGetLastError()); t->pubExpected++; }   // (a replayed graph counts its own gather)
   return DMPC_OK;
 }
 
@@ -558,11 +573,30 @@ int launchFinal(dmpc_tree* t, int mode, int reduceAll) {
 }
 
 // one D2H copy of everything the host needs after a batch of kernels, then the only synchronisation point
-int readStatus(dmpc_tree* t, bool withChunks) {
-  CUDA_TRY(cudaMemcpyAsync(t->h_res, t->rv.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
-  if (withChunks)
-    CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
-  CUDA_TRY(cudaStreamSynchronize(t->stream));
+// afterGather: the last kernel queued is k_root_gather, whose last block publishes the finished status block into the
+// mapped host mirror (DevStatus::pubSeq): the host polls for it — no copy queued behind the kernel, no stream
+// synchronisation, which together cost more than a root-path evaluation's kernels.  Otherwise (chain / final kernels ran,
+// or the chunk sums are wanted too): one D2H copy and the only synchronisation point.
+int readStatus(dmpc_tree* t, bool withChunks, bool afterGather) {
+  bool polled = false;
+  if (afterGather && !withChunks && t->rv.hostSt) {
+    const volatile unsigned* seq = &t->h_res->pubSeq;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 1;; spin++) {
+      if (*seq == t->pubExpected) { polled = true; break; }
+      if ((spin & 0x3fff) == 0) {
+        if (cudaStreamQuery(t->stream) != cudaErrorNotReady) { polled = *seq == t->pubExpected; break; }   // finished (or failed)
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0) break;
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!polled) {
+    CUDA_TRY(cudaMemcpyAsync(t->h_res, t->rv.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
+    if (withChunks)
+      CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+  }
   t->st.last_active_tiles = t->h_res->nact;
   t->st.last_chain_sites = t->h_res->nact ? t->h_res->chainSites : 0;
   t->st.last_chain_rows = t->h_res->nact ? t->h_res->chainRows : 0;
@@ -592,7 +626,7 @@ int rootStage(dmpc_tree* t, double* ll) {
       if ((rc = launchGather(t, mode))) return rc;
       CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
     }
-    if ((rc = readStatus(t, t->deferred))) return rc;
+    if ((rc = readStatus(t, t->deferred && !(t->rv.comm.world > 1), true))) return rc;
     if (t->h_res->overflow > t->rv.Kcap) {
       int k = t->rv.Kcap;
       while (k < t->h_res->overflow) k *= 2;
@@ -610,18 +644,18 @@ int rootStage(dmpc_tree* t, double* ll) {
         if (chain && (rc = launchChain(t))) return rc;
         if ((rc = launchFinal(t, mode, 2))) return rc;
         CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
-        if ((rc = readStatus(t, false))) return rc;
+        if ((rc = readStatus(t, false, false))) return rc;
         t->carryIsZero = false;
       }
       t->chunksOnHost = false;
-      cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+      t->evalTimePending = true;
       if (t->h_res->xok != 1) return fail(DMPC_ERR_CUDA, "peer exchange failed: a rank of the site-sharded run never answered");
       *ll = t->h_res->ll;
       return DMPC_OK;
     }
     if (t->deferred) {
       t->chunksOnHost = t->h_res->nact == 0;
-      cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+      t->evalTimePending = true;
       *ll = NAN;
       return DMPC_OK;
     }
@@ -629,9 +663,9 @@ int rootStage(dmpc_tree* t, double* ll) {
       if (chain && (rc = launchChain(t))) return rc;
       if ((rc = launchFinal(t, mode, 1))) return rc;
       CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
-      if ((rc = readStatus(t, false))) return rc;
+      if ((rc = readStatus(t, false, false))) return rc;
     }
-    cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]); t->st.last_eval_ms = ms;
+    t->evalTimePending = true;
     *ll = t->h_res->ll;
     return DMPC_OK;
   }
@@ -729,44 +763,62 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     CUDA_TRY(cudaSetDevice(t->device));
     int r2;
     if ((r2 = acquirePack(t))) return r2;
-    if ((r2 = t->alloc(&t->d_tipmask, (size_t)t->N * t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->d_lut, (size_t)2 * t->R * 64))) return r2;
-    if ((r2 = t->alloc(&t->d_tasks, (size_t)t->nInt))) return r2;
-    if ((r2 = t->alloc(&t->d_tokens, (size_t)2 * t->nInt))) return r2;
-    if ((r2 = t->alloc(&t->d_tipList, (size_t)2 * t->nInt))) return r2;
-    if ((r2 = t->alloc(&t->d_curList, (size_t)t->nInt))) return r2;
-    if ((r2 = t->alloc(&t->dv.cur, (size_t)t->nInt))) return r2;
-    if ((r2 = t->alloc(&t->rv.kmax, (size_t)t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.rootdot, (size_t)t->R * t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.act, (size_t)t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.rowoff, (size_t)t->Sp + 1))) return r2;
-    if ((r2 = t->alloc(&t->rv.posIncl, (size_t)t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.chunkStart, (size_t)t->Sp + 2))) return r2;
-    if ((r2 = t->alloc(&t->rv.cout, (size_t)t->Sp * t->rv.RP))) return r2;
-    if ((r2 = t->alloc(&t->rv.mxo, (size_t)t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.carryIn, (size_t)RMAX))) return r2;
-    if ((r2 = t->alloc(&t->rv.carryOut, (size_t)RMAX))) return r2;
-    if ((r2 = t->alloc(&t->rv.sitell, (size_t)t->Sp))) return r2;
-    if ((r2 = t->alloc(&t->rv.chunk, (size_t)t->nChunks))) return r2;
-    if ((r2 = t->alloc(&t->rv.st, (size_t)1))) return r2;
-    if ((r2 = allocElist(t, 8))) return r2;
+    // every buffer whose size is known now comes out of ONE stream-ordered allocation (a create / evaluate / destroy
+    // cycle, i.e. logLikFromClusInd, would otherwise spend more time in ~30 cudaMallocAsync / cudaFreeAsync calls than
+    // in the upload): alignment staging, masks, plan, root-reduction work arrays, slot 0 of the partials
+    struct { std::vector<std::pair<void*, size_t>> req; size_t total = 0; } ar;
+    auto want = [&](auto** p, size_t n) {
+      ar.total = (ar.total + 255) & ~(size_t)255;
+      ar.req.push_back({(void*)p, ar.total});
+      ar.total += n * sizeof(**p);
+    };
+    uint8_t* stage = nullptr;
+    const size_t nPart = (size_t)t->nInt * t->R * t->Sp;
+    want(&t->dv.part[0], nPart * 4);
+    want(&t->dv.expo[0], nPart);
+    want(&t->dv.flag[0], (size_t)t->R * t->T * t->nInt);
+    want(&t->d_tipmask, (size_t)t->N * t->Sp);
+    want(&stage, (size_t)t->N * t->S);
+    want(&t->d_lut, (size_t)2 * t->R * 64);
+    want(&t->d_plan, (size_t)t->nInt * PLAN_BYTES);
+    want(&t->d_curList, (size_t)t->nInt);
+    want(&t->dv.cur, (size_t)t->nInt);
+    want(&t->rv.kmax, (size_t)t->Sp);
+    want(&t->rv.rootdot, (size_t)t->R * t->Sp);
+    want(&t->rv.act, (size_t)t->Sp);
+    want(&t->rv.rowoff, (size_t)t->Sp + 1);
+    want(&t->rv.posIncl, (size_t)t->Sp);
+    want(&t->rv.chunkStart, (size_t)t->Sp + 2);
+    want(&t->rv.cout, (size_t)t->Sp * t->rv.RP);
+    want(&t->rv.mxo, (size_t)t->Sp);
+    want(&t->rv.carryIn, (size_t)RMAX);
+    want(&t->rv.carryOut, (size_t)RMAX);
+    want(&t->rv.sitell, (size_t)t->Sp);
+    want(&t->rv.chunk, (size_t)t->nChunks);
+    want(&t->rv.st, (size_t)1);
+    setElistGeometry(t, 8);
+    want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
+    {
+      void* base = nullptr;
+      CUDA_TRY(cudaMallocAsync(&base, ar.total, t->stream));
+      t->allocs.push_back(base);
+      t->st.device_bytes += ar.total;
+      for (auto& rq : ar.req) { void* q = (char*)base + rq.second; std::memcpy(rq.first, &q, sizeof q); }
+    }
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
     CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
     t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal;
     // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
     // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
-    uint8_t* stage = nullptr;
     t->st.create_setup_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
     CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
-    CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)t->N * t->S, t->stream));
     CUDA_TRY(cudaMemcpyAsync(stage, alignmentBin, (size_t)t->N * t->S, cudaMemcpyHostToDevice, t->stream));
     {
       const size_t n = (size_t)t->N * t->Sp;
       k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
       t->st.kernel_launches++;
     }
-    CUDA_TRY(cudaFreeAsync(stage, t->stream));
     CUDA_TRY(cudaEventRecord(t->ev[6], t->stream));
     int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
     if (rcEval == DMPC_OK) { float ms = 0; cudaEventElapsedTime(&ms, t->ev[5], t->ev[6]); t->st.create_upload_ms = ms; }
@@ -1114,6 +1166,13 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->evalTimePending) {                    // the evaluation's result was polled: its closing event may complete a moment later
+    t->evalTimePending = false;
+    float ms = 0;
+    if (ensureDevice(t) == DMPC_OK && cudaEventSynchronize(t->ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, t->ev[0], t->ev[2]) == cudaSuccess)
+      t->st.last_eval_ms = ms;
+  }
   *out = t->st;
   out->exact_mode = t->exact ? 1 : 0;
   out->chain_group = t->chainGroup;
@@ -1152,6 +1211,34 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
   if (dirtyVertex != 0 && (dirtyVertex <= numTips || dirtyVertex > ht.numVerts)) return fail(DMPC_ERR_ARG, "dirtyVertex must be internal");
   ht.associate(clusterMRCAs, nClusterMRCAs);
   ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
+  {
+    // tip counts: the one-pass version of link() (pre-ordered rows) and the incremental update of an NNI must agree with
+    // the full traversal
+    auto recount = [&](const char* what) -> bool {
+      if (!ht.tipsValid) return true;
+      const std::vector<int32_t> fast = ht.tips;
+      ht.tipsValid = false;
+      ht.computeTips();
+      if (fast != ht.tips) { fail(DMPC_ERR_STATE, std::string("plan self-check: tip counts after ") + what); return false; }
+      return true;
+    };
+    if (!recount("link")) return DMPC_ERR_STATE;
+    HostTree sc = ht;                              // a scratch copy takes a few NNI moves (RearrangeTreeNNI, AugTree.cpp:211-226)
+    std::vector<int> cand;
+    sc.nniCandidates(sc.root(), nullptr, cand);
+    for (int m = 0; m < 8 && !cand.empty(); m++) {
+      int two[2];
+      sc.twoVerticesForNNI(cand[sc.rng.uniform_int(cand.size())], nullptr, two);
+      sc.rearrangeNNI(two[0], two[1]);
+      const std::vector<int32_t> fast = sc.tips;
+      const bool was = sc.tipsValid;
+      sc.tipsValid = false;
+      sc.computeTips();
+      if (was && fast != sc.tips) return fail(DMPC_ERR_STATE, "plan self-check: tip counts after an NNI move");
+      cand.clear();
+      sc.nniCandidates(sc.root(), nullptr, cand);
+    }
+  }
   HostTree::Plan p;
   ht.plan(p);
   const bool full = dirtyVertex == 0;
@@ -1271,17 +1358,10 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
     // a fused vertex has no stored partial: replay its program (read-only) into the scratch row
     HostTree::Plan rp;
     const Task k = ht.makeTask(vertex, t->nReal, 0, rp, false);
-    t->h_tasks[0] = k;
-    CUDA_TRY(cudaMemcpyAsync(t->d_tasks, t->h_tasks, sizeof(Task), cudaMemcpyHostToDevice, t->stream));
-    if (!rp.tokens.empty()) {
-      std::memcpy(t->h_tokens, rp.tokens.data(), rp.tokens.size() * sizeof(Token));
-      CUDA_TRY(cudaMemcpyAsync(t->d_tokens, t->h_tokens, rp.tokens.size() * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
-      std::memcpy(t->h_tipList, rp.tipList.data(), rp.tipList.size() * sizeof(int32_t));
-      CUDA_TRY(cudaMemcpyAsync(t->d_tipList, t->h_tipList, rp.tipList.size() * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
-    }
+    rp.tasks.assign(1, k);
+    if ((rc = uploadPlan(t, rp))) return rc;
     const dim3 grid((unsigned)t->R, (unsigned)t->T, 1);
-    t->runTokens = t->d_tokens; t->runTips = t->d_tipList; t->runFlip = 0;
-    rc = launchPrune(t, grid, t->d_tasks, 1);
+    rc = launchPrune(t, grid, t->runTasks, 1);
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
     partSlot = 0; partRow = t->nReal;

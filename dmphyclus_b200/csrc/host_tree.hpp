@@ -60,6 +60,7 @@ struct HostTree {
   int fuseTips = 1;
   std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
   bool tipsValid = false;
+  std::vector<uint8_t> linkScratch;
   std::vector<uint8_t> mat;              // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
   bool walkChains = true;                // false: never hand a chain to k_walk (its 32-bit element offsets would overflow)
   bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
@@ -95,6 +96,22 @@ struct HostTree {
     }
     for (int v = numTips; v < numVerts; v++)
       if (nkids[v] != 2) { err = "the tree is not strictly bifurcating (IntermediateNode.cpp:59)"; return false; }
+    // Tips below every vertex in one reverse pass over the rows, valid when they come in pre-order (a vertex's own row
+    // before the rows of its children) — the order BuildEdgeMatrix emits (AugTree.cpp:228-251) and R hands back on every
+    // NNI rollback.  Any other order falls back to the traversal in computeTips().
+    tips.assign(numVerts, 0);
+    for (int v = 0; v < numTips; v++) tips[v] = 1;
+    std::vector<uint8_t>& pend = linkScratch;        // child rows of each vertex not folded in yet
+    pend.assign(numVerts, 0);
+    for (int v = numTips; v < numVerts; v++) pend[v] = 2;
+    bool ordered = true;
+    for (int k = nEdgeRows - 1; k >= 0 && ordered; k--) {
+      const int p = edge[k] - 1, c = edge[k + nEdgeRows] - 1;
+      if (pend[c] != 0) ordered = false;
+      tips[p] += tips[c];
+      pend[p]--;
+    }
+    tipsValid = ordered;
     return true;
   }
 
@@ -189,7 +206,11 @@ struct HostTree {
 
   // RearrangeTreeNNI (AugTree.cpp:211-226)
   void rearrangeNNI(int a, int b) {
-    tipsValid = false;
+    if (tipsValid) {                       // the two subtrees trade places: only their old ancestors' counts move
+      const int delta = tips[b] - tips[a];
+      for (int v = parent[a]; v != -1; v = parent[v]) tips[v] += delta;
+      for (int v = parent[b]; v != -1; v = parent[v]) tips[v] -= delta;
+    }
     removeChild(parent[a], a); addChild(parent[a], b);
     removeChild(parent[b], b); addChild(parent[b], a);
     std::swap(parent[a], parent[b]);
@@ -335,8 +356,8 @@ struct HostTree {
       pre.push_back(v);
       for (int i = 0; i < 2; i++) { int c = kids[2 * v + i]; if (!isTip(c) && !fused(c) && !solved[c]) stack.push_back(c); }
     }
-    std::vector<int>& level = p.level;
-    level.assign(numVerts, 0);             // height above the clean frontier; clean, fused vertices and tips = 0
+    std::vector<int>& level = p.level;     // height above the clean frontier; clean, fused vertices and tips = 0
+    if ((int)level.size() != numVerts) level.assign(numVerts, 0);   // all zero between calls (reset below for the dirty set)
     int maxLevel = 0;
     for (size_t i = pre.size(); i-- > 0;) {   // reverse pre-order visits children before parents
       int v = pre[i];
@@ -382,6 +403,7 @@ struct HostTree {
       solved[v] = 1;                                  // ... _isSolved = true (:33)
     }
     for (int c : matList) mat[c] = 0;
+    for (int v : pre) level[v] = 0;
   }
 };
 

@@ -16,6 +16,7 @@
 // (__dmul_rn/__dadd_rn: never contracted into FMAs), so partials are bit-identical to the CPU oracle.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "task.hpp"
@@ -55,8 +56,10 @@ struct DevStatus {
                                 //   2 = a peer never answered, -1 = no exchange attempted
   int pad;
   int chainSites, chainRows;    // what k_chain walked: rescaled sites and (padded) exponent rows
-  int pad2[2];
+  unsigned pubSeq;              // number of times k_root_gather has published this block to the host mirror
+  int pad2;
 };
+static_assert(sizeof(DevStatus) == 56, "status block = 14 words");
 
 // Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access): every rank
 // owns a mailbox in its HBM that all peers can store into.  Layout of a mailbox: unsigned flag[CW] (sequence number
@@ -87,6 +90,9 @@ struct RootView {
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [nChunks] sums of CHUNK consecutive sites
   DevStatus* st;                // everything the host reads back after an evaluation, in one copy
+  DevStatus* hostSt;            // mapped pinned mirror (or null): the gather's last block stores the finished block there
+                                // and bumps its pubSeq, so that the host can pick the result up by polling instead of
+                                // queueing a copy and synchronising the stream
   int Kcap, RP, Q;              // Q = rows per chain staging chunk
   CommView comm;                // comm.world > 1: k_root_gather also performs the cross-rank exchange
   int exactMode;                // the prune kernels ran in exact mode (a raised violation flag is then stale)
@@ -710,6 +716,20 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
 // vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
 // the flagged vertices of each 128-vertex window are compacted (in id order) into shared memory, then visited
 // four at a time so that their exponent loads overlap.
+// one thread, after every other write of the evaluation to *rv.st has been fenced: status block -> host mirror
+__device__ __forceinline__ void publishStatus(const RootView& rv) {
+  if (!rv.hostSt) return;
+  const unsigned seq = rv.st->pubSeq + 1;
+  rv.st->pubSeq = seq;
+  const volatile int* src = reinterpret_cast<const volatile int*>(rv.st);
+  volatile int* dst = reinterpret_cast<volatile int*>(rv.hostSt);
+  constexpr int SEQ_WORD = offsetof(DevStatus, pubSeq) / 4;
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(DevStatus) / 4); i++) if (i != SEQ_WORD) dst[i] = src[i];
+  __threadfence_system();                 // the payload is visible to the host before the sequence number is
+  dst[SEQ_WORD] = (int)seq;
+}
+
 template <int RP, bool BATCH>
 __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, int mode, PathView pv) {
   const int pb = BATCH ? blockIdx.y : 0;           // proposal of a batch
@@ -849,18 +869,18 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       // skipped when the host is going to re-run this gather (list overflow, fused-clade violation), so that every
       // rank sends exactly one message per exchange
       if (retry) {
-        if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; }
+        if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
         return;
       }
       const int res = exchangeAndReduce(rv, gridDim.x, quiet, s_red);
-      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; }
+      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
       return;
     }
     if (quiet) {
       const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
       if (tid == 0) rv.st->ll = tot;
     }
-    if (tid == 0) rv.st->ticket2 = 0;
+    if (tid == 0) { rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
   }
 }
 
