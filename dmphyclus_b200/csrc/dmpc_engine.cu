@@ -74,7 +74,7 @@ struct dmpc_comm {
 
 struct dmpc_tree {
   HostTree ht;
-  int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nReal = 0, nChunks = 0;
+  int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nReal = 0, nChunks = 0, nFlag = 0;
   bool quirk = true, deferred = false, alive = true;
   int device = 0, siteBegin = 0, sitesTotal = 0;
   ResPack pack;
@@ -225,7 +225,7 @@ int allocSlot(dmpc_tree* t, int slot) {
   const size_t n = (size_t)t->nInt * t->R * t->Sp;
   if ((rc = t->alloc(&t->dv.part[slot], n * 4))) return rc;
   if ((rc = t->alloc(&t->dv.expo[slot], n))) return rc;
-  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->R * t->T * t->nInt))) return rc;
+  if ((rc = t->alloc(&t->dv.flag[slot], (size_t)t->R * t->T * t->nFlag))) return rc;
   return DMPC_OK;
 }
 
@@ -744,6 +744,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->ht.withinIdx = withinMatListIndex; t->ht.betweenIdx = betweenMatListIndex;
   t->N = numTips; t->S = numLoci; t->R = numRateCats;
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
+  t->nFlag = (numTips + 15) & ~15;
   t->ht.fuseTips = std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
   t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
@@ -776,7 +777,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     const size_t nPart = (size_t)t->nInt * t->R * t->Sp;
     want(&t->dv.part[0], nPart * 4);
     want(&t->dv.expo[0], nPart);
-    want(&t->dv.flag[0], (size_t)t->R * t->T * t->nInt);
+    want(&t->dv.flag[0], (size_t)t->R * t->T * t->nFlag);
     want(&t->d_tipmask, (size_t)t->N * t->Sp);
     want(&stage, (size_t)t->N * t->S);
     want(&t->d_lut, (size_t)2 * t->R * 64);
@@ -808,7 +809,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
     CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
-    t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal;
+    t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal; t->dv.nFlag = t->nFlag;
     // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
     // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
     t->st.create_setup_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
@@ -1374,7 +1375,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   CUDA_TRY(cudaMemcpy(hs.data(), t->dv.part[partSlot] + (size_t)partRow * n * 4, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(he.data(), t->dv.expo[slot] + (size_t)idx * n, n * sizeof(float), cudaMemcpyDeviceToHost));
   for (int b = 0; b < t->R * t->T; b++)
-    CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nInt + idx, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&hf[b], t->dv.flag[slot] + (size_t)b * t->nFlag + idx, 1, cudaMemcpyDeviceToHost));
   for (int s = 0; s < t->S; s++)
     for (int r = 0; r < t->R; r++) {
       for (int k = 0; k < 4; k++) sol[((size_t)s * t->R + r) * 4 + k] = hs[((size_t)r * t->Sp + s) * 4 + k];

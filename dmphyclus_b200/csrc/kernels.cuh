@@ -7,7 +7,7 @@
 //                                           rejected proposal rolls back by flipping a per-vertex slot bit.  Rows
 //                                           of FUSED vertices (small clades, see k_prune) are never written.
 //   expo[s]  f32    [N][R][Sp]              per-vertex rescale exponents (IntermediateNode.cpp:63: a FLOAT)
-//   flag[s]  u8     [R][T][N]               1 when any site of the 256-site tile rescaled at that vertex for that
+//   flag[s]  u8     [R][T][N up to 16]      1 when any site of the 256-site tile rescaled at that vertex for that
 //                                           rate; expo tiles whose flag is 0 are never written nor read
 // Consecutive threads touch consecutive 32-byte elements (LDG.E.256 / STG.E.256), so every warp request is 1 KB
 // fully coalesced.  There is no GEMM shape here (a 4x4 mat-vec per thread): no tensor cores, no TMA tiles.
@@ -39,6 +39,8 @@ struct DevView {
   const double* lut;            // [2][R][16][4]: P * indicator(mask) for every 4-bit mask (tips)
   int N, S, Sp, R, T, nInt;      // nInt = rows of the per-vertex arrays: the N-1 internal vertices + 1 scratch row
   int nReal;                    // N-1: what the root reduction scans
+  int nFlag;                    // bytes of one (rate, tile) row of the flag arrays: nInt rounded up to 16, so that the root
+                                // reduction scans 16 vertices per 128-bit load
   // select instead of dynamic indexing: indexing a by-value kernel parameter array would spill it to local memory
   __device__ __forceinline__ double* partOf(int slot) const { return slot ? part[1] : part[0]; }
   __device__ __forceinline__ float* expoOf(int slot) const { return slot ? expo[1] : expo[0]; }
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
   const int tile = blockIdx.y, r = blockIdx.x, R = v.R;
   const int site0 = tile * TILE + tid;
   const size_t Sp = (size_t)v.Sp;
-  const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
+  const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   bool lutLoaded = false, trig = false;
   double prev[PATHS ? SPT : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
   const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : (int)blockIdx.z;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
   const int tid = threadIdx.x, r = blockIdx.x, tile = blockIdx.y, R = v.R;
   const unsigned site = (unsigned)(tile * TILE + tid);
   const size_t Sp = (size_t)v.Sp;
-  const size_t flagRow = ((size_t)r * v.T + tile) * v.nInt;
+  const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   const int slotMask = flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0;
   if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
   if (tid < 2 * 16) s_P[tid] = c_P[tid >> 4][r][tid & 15];
@@ -734,7 +736,8 @@ template <int RP, bool BATCH>
 __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, int mode, PathView pv) {
   const int pb = BATCH ? blockIdx.y : 0;           // proposal of a batch
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
-  __shared__ int s_list[TILE];
+  constexpr int NV = 16;                           // vertices per thread and pass of the (non-batch) flag scan
+  __shared__ int s_list[BATCH ? TILE : TILE * NV];
   __shared__ int s_listJ[BATCH ? TILE : 1];
   __shared__ double s_red[TILE];
   __shared__ bool s_last;
@@ -763,38 +766,12 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
 #pragma unroll
   for (int r = 0; r < RP; r++) k[r] = 0;
   float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
-  const size_t fstride = (size_t)v.T * v.nInt;                  // between the flag planes of consecutive rates
-  const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nInt : nullptr;
-  const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nInt : nullptr;
-  for (int base = 0; base < v.nReal; base += TILE) {
-    const int nd = base + tid;
-    int slot = 0, rbits = 0;                     // rates for which this vertex rescaled somewhere in the tile
-    int pj = -1;                                 // BATCH: position in the proposal's run when nd is a path vertex
-    if (nd < v.nReal) {
-      if (BATCH) {
-        const int32_t* ids = pv.ids + (size_t)pb * pv.JMAX;
-        int lo = 0, hi = pv.JMAX;                 // first index with ids[.] >= nd
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] < nd) lo = mid + 1; else hi = mid; }
-        if (lo < pv.JMAX && ids[lo] == nd) pj = pv.pos[(size_t)pb * pv.JMAX + lo];
-      }
-      if (pj >= 0) {
-        const uint8_t* fp = pv.pf + (((size_t)pb * pv.JMAX + pj) * R) * v.T + tile;
-        for (int r = 0; r < R; r++) rbits |= (fp[(size_t)r * v.T] != 0) << r;
-      } else {
-        slot = v.cur[nd];
-        const uint8_t* fp = (slot ? f1 : f0) + nd;
-        for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
-      }
-    }
-    const bool f = rbits != 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_wcnt[wid] = __popc(bal);
-    __syncthreads();
-    int off = __popc(bal & ((1u << lane) - 1)), n = 0;
-#pragma unroll
-    for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
-    if (f) { s_list[off] = (nd << 9) | (slot << 8) | rbits; if (BATCH) s_listJ[off] = pj; }
-    __syncthreads();
+  const size_t fstride = (size_t)v.T * v.nFlag;                 // between the flag planes of consecutive rates
+  const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nFlag : nullptr;
+  const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nFlag : nullptr;
+  // the flagged vertices of a pass, compacted in vertex-id order into s_list, are visited four at a time so that their
+  // exponent loads overlap
+  auto consume = [&](int n) {
     for (int i = 0; i < n; i += 4) {
       float e[4][RP];
 #pragma unroll
@@ -814,7 +791,101 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
             k[r]++;
           }
     }
-    __syncthreads();
+  };
+  if constexpr (!BATCH) {
+    // 16 vertices per thread and pass: the slot bytes and BOTH slots' flag bytes of every rate come in as independent
+    // 128-bit loads (one round trip per 4,096 vertices instead of two dependent ones per 256), the current slot's flags
+    // are selected bytewise.  A pass without any flag (the usual case) costs nothing more.
+    for (int base = 0; base < v.nReal; base += TILE * NV) {
+      const int v0 = base + tid * NV;
+      unsigned cw[4] = {0u, 0u, 0u, 0u}, any[4] = {0u, 0u, 0u, 0u}, sel[RP][4];
+#pragma unroll
+      for (int r = 0; r < RP; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) sel[r][q] = 0u;
+      if (v0 < v.nReal) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(v.cur + v0);
+        cw[0] = c4.x; cw[1] = c4.y; cw[2] = c4.z; cw[3] = c4.w;
+        uint4 a4[RP], b4[RP];
+#pragma unroll
+        for (int r = 0; r < RP; r++)
+          if (r < R) {
+            a4[r] = *reinterpret_cast<const uint4*>(f0 + (size_t)r * fstride + v0);
+            b4[r] = f1 ? *reinterpret_cast<const uint4*>(f1 + (size_t)r * fstride + v0) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        const int nValid = min(NV, v.nReal - v0);      // the scratch row (and the padding) is not a vertex
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int nb = min(4, max(0, nValid - 4 * q));                    // valid bytes of this word
+          const unsigned vm = nb >= 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
+          cw[q] &= 0x01010101u & vm;
+          const unsigned m = cw[q] * 0xffu;                                  // 0xff in the bytes whose vertex lives in slot 1
+#pragma unroll
+          for (int r = 0; r < RP; r++)
+            if (r < R) {
+              const unsigned a = q == 0 ? a4[r].x : q == 1 ? a4[r].y : q == 2 ? a4[r].z : a4[r].w;
+              const unsigned b = q == 0 ? b4[r].x : q == 1 ? b4[r].y : q == 2 ? b4[r].z : b4[r].w;
+              sel[r][q] = ((a & ~m) | (b & m)) & 0x01010101u & vm;
+              any[q] |= sel[r][q];
+            }
+        }
+      }
+      const int mine = __popc(any[0]) + __popc(any[1]) + __popc(any[2]) + __popc(any[3]);
+      int incl = mine;                              // inclusive scan over the block, in thread (= vertex) order
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int tq = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += tq; }
+      if (lane == 31) s_wcnt[wid] = incl;
+      __syncthreads();
+      int off = incl - mine, n = 0;
+#pragma unroll
+      for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
+      if (mine) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+          const int q = j >> 2, sh = 8 * (j & 3);
+          if ((any[q] >> sh) & 1u) {
+            int rbits = 0;
+#pragma unroll
+            for (int r = 0; r < RP; r++) rbits |= (int)((sel[r][q] >> sh) & 1u) << r;
+            s_list[off++] = ((v0 + j) << 9) | ((int)((cw[q] >> sh) & 1u) << 8) | rbits;
+          }
+        }
+      }
+      __syncthreads();
+      consume(n);
+      __syncthreads();
+    }
+  } else {
+    for (int base = 0; base < v.nReal; base += TILE) {
+      const int nd = base + tid;
+      int slot = 0, rbits = 0;                     // rates for which this vertex rescaled somewhere in the tile
+      int pj = -1;                                 // position in the proposal's run when nd is a path vertex
+      if (nd < v.nReal) {
+        const int32_t* ids = pv.ids + (size_t)pb * pv.JMAX;
+        int lo = 0, hi = pv.JMAX;                   // first index with ids[.] >= nd
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] < nd) lo = mid + 1; else hi = mid; }
+        if (lo < pv.JMAX && ids[lo] == nd) pj = pv.pos[(size_t)pb * pv.JMAX + lo];
+        if (pj >= 0) {
+          const uint8_t* fp = pv.pf + (((size_t)pb * pv.JMAX + pj) * R) * v.T + tile;
+          for (int r = 0; r < R; r++) rbits |= (fp[(size_t)r * v.T] != 0) << r;
+        } else {
+          slot = v.cur[nd];
+          const uint8_t* fp = (slot ? f1 : f0) + nd;
+          for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
+        }
+      }
+      const bool f = rbits != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) s_wcnt[wid] = __popc(bal);
+      __syncthreads();
+      int off = __popc(bal & ((1u << lane) - 1)), n = 0;
+#pragma unroll
+      for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
+      if (f) { s_list[off] = (nd << 9) | (slot << 8) | rbits; s_listJ[off] = pj; }
+      __syncthreads();
+      consume(n);
+      __syncthreads();
+    }
   }
   int kmax = 0;
 #pragma unroll
