@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
+    ap.add_argument("--mcmc-only", action="store_true", help="extra legs: only the MCMC one (skip the other alignment kind)")
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
     ap.add_argument("--sweep-rates", type=int, default=3, help="rate categories of the proposal sweep")
     ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
@@ -393,6 +394,8 @@ def extra_legs(args, eng, p, al, n, s, k, r, world=1):
     out = {}
     if world > 1:
         return mcmc_leg(args, eng, p, al, out, "site-sharded: every rank runs the same driver in lock-step")
+    if args.mcmc_only:
+        return mcmc_leg(args, eng, p, al, out, "single GPU")
     other = "iid" if args.data == "evolved" else "evolved"
     q = Problem(load_packaged(), n, s, k, r, other, args.tree, seed=args.seed)
     alq = eng.getConvertedAlignment(list(synth.STATES), q.chars)
