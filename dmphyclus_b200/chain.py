@@ -139,7 +139,7 @@ def init_current_value(backend, alignmentBin, edge, clusInd, alpha, st: ChainSet
     res = backend.logLikCpp(edge, mrcas, st.limProbs, st.within(withinMatListIndex),
                             st.between(betweenMatListIndex), st.numLikThreads, alignmentBin, n, s,
                             withinMatListIndex, betweenMatListIndex)
-    cv = ChainState(edge=np.array(edge, dtype=np.int32), n_tips=n, clusInd=clusInd, alpha=float(alpha),
+    cv = ChainState(edge=_frozen_edge(edge), n_tips=n, clusInd=clusInd, alpha=float(alpha),
                     withinMatListIndex=withinMatListIndex, betweenMatListIndex=betweenMatListIndex,
                     clusterNodeIndices=list(mrcas), logLik=res["logLik"], extPointer=res["solutionPointer"])
     cv.clusterCounts = {k: int((clusInd == k).sum()) for k in range(1, int(clusInd.max()) + 1)}
@@ -171,8 +171,20 @@ def _update_trans_matrix(backend, cv: ChainState, st: ChainSettings, rng, betwee
         cv.logPostProb = new_ll + (cv.logPostProb - cv.logLik)
         cv.logLik = new_ll
     else:
-        backend.RestorePreviousConfig(cv.extPointer, np.zeros((1, 2), np.int32), cv.withinMatListIndex,
+        backend.RestorePreviousConfig(cv.extPointer, _NO_EDGE, cv.withinMatListIndex,
                                       cv.betweenMatListIndex, False, cv.clusterNodeIndices, False)
+
+
+_NO_EDGE = np.zeros((1, 2), np.int32)            # matrix(0, 1, 1): what the R code passes when no NNI is rolled back
+_NO_EDGE.setflags(write=False)
+
+
+def _frozen_edge(edge) -> np.ndarray:
+    """paraValues$phylogeny$edge: replaced as a whole when an NNI is accepted, never edited in place — kept read-only so
+    that a backend (and the cached tree view) may recognise the same matrix when it comes back on a rollback."""
+    e = np.array(edge, dtype=np.int32)
+    e.setflags(write=False)
+    return e
 
 
 def _exp(x: float) -> float:
@@ -186,7 +198,7 @@ def _nni_update(backend, cv, st, rng, call):
     if rng.random() < _exp(new_ll - cv.logLik):
         cv.logPostProb = cv.logPostProb - cv.logLik + new_ll
         cv.logLik = new_ll
-        cv.edge = np.array(res["edge"], dtype=np.int32)
+        cv.edge = _frozen_edge(res["edge"])
     else:
         backend.RestorePreviousConfig(cv.extPointer, cv.edge, cv.withinMatListIndex, cv.betweenMatListIndex, True,
                                       cv.clusterNodeIndices, False)
@@ -288,7 +300,7 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
             cv.clusterCounts = {int(k): cv.clusterCounts[o] for k, o in zip(keys, sorted(cv.clusterCounts))}
             cv.clusInd = _relabel(cv.clusInd)
     else:
-        backend.RestorePreviousConfig(cv.extPointer, np.zeros((1, 2), np.int32), cv.withinMatListIndex,
+        backend.RestorePreviousConfig(cv.extPointer, _NO_EDGE, cv.withinMatListIndex,
                                       cv.betweenMatListIndex, False, cv.clusterNodeIndices, True)
 
 

@@ -584,6 +584,9 @@ int readStatus(dmpc_tree* t, bool withChunks, bool afterGather) {
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spin = 1;; spin++) {
       if (*seq == t->pubExpected) { polled = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
       if ((spin & 0x3fff) == 0) {
         if (cudaStreamQuery(t->stream) != cudaErrorNotReady) { polled = *seq == t->pubExpected; break; }   // finished (or failed)
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0) break;
@@ -1036,7 +1039,6 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       runStart.assign(1, 0);
       std::vector<int> member;                     // indices (into props) of this batch
       int jmax = 1;
-      size_t bytes = 0;
       for (int i = b0; i < nProps; i++) {
         const dmpc_proposal& q = props[i];
         const size_t before = pp.tasks.size();
@@ -1059,14 +1061,13 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
         const size_t per = (size_t)jm * R * Sp * 4 + (size_t)jm * R * T + R * Sp * 8 +            // pe, pf, rootdot
                            Sp * Kc * RP * 4 + Sp * (4 * 4 + 4 + 8) + Sp * RP * 4 + T * 8 + 256;    // root work arrays
         if (!member.empty() && (per * (member.size() + 1) > ((size_t)3 << 30) || member.size() >= 65535)) { pp.tasks.resize(before); b0 = i; break; }
-        jmax = jm; bytes = per * (member.size() + 1);
+        jmax = jm;
         member.push_back(i);
         runStart.push_back((int)pp.tasks.size());
         b0 = i + 1;
       }
       const int nb = (int)member.size();
       if (!nb) continue;
-      (void)bytes;
       ids.assign((size_t)nb * jmax, INT32_MAX); pos.assign((size_t)nb * jmax, 0);
       for (int i = 0; i < nb; i++) {
         const int len = runStart[i + 1] - runStart[i];

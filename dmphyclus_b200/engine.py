@@ -135,6 +135,7 @@ class Engine:
         self.opts.fuse_exact = int(fuse_exact)
         self._shape = {}
         self._mcache = {}
+        self._ecache = {}
 
     def _check(self, rc):
         if rc != 0:
@@ -153,6 +154,20 @@ class Engine:
                 self._mcache.clear()
             self._mcache[id(m)] = (m, ptr)
         return ptr
+
+    def _ep(self, e):
+        """Pointer + row count of an edge matrix in column-major int32 (what R passes).  A read-only array handed in again
+        (the committed phylogeny, on every rejected NNI) is converted once."""
+        ent = self._ecache.get(id(e))
+        if ent is not None and ent[0] is e:
+            return ent[1], ent[2]
+        arr = _edge(e)
+        ptr = _p(arr, _i32_p)
+        if isinstance(e, np.ndarray) and not e.flags.writeable:
+            if len(self._ecache) >= 4:
+                self._ecache.clear()
+            self._ecache[id(e)] = (e, ptr, len(arr) // 2)
+        return ptr, len(arr) // 2
 
     def _pp(self, pi):
         ent = self._mcache.get(id(pi))
@@ -247,9 +262,9 @@ class Engine:
 
     def RestorePreviousConfig(self, ptr, edgeMat, withinMatListIndex, betweenMatListIndex, NNImove, clusterMRCAs,
                               splitMergeMove) -> None:
-        e = _edge(edgeMat)
+        e, n_rows = self._ep(edgeMat)
         m = np.ascontiguousarray(np.asarray(clusterMRCAs).ravel(), dtype=np.int32)
-        self._check(self.lib.dmpc_restore_previous_config(ptr, _p(e, _i32_p), len(e) // 2, int(withinMatListIndex),
+        self._check(self.lib.dmpc_restore_previous_config(ptr, e, n_rows, int(withinMatListIndex),
                                                           int(betweenMatListIndex), int(bool(NNImove)), _p(m, _i32_p),
                                                           len(m), int(bool(splitMergeMove))))
 
