@@ -1210,7 +1210,7 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
   if (!edge || !out || (nClusterMRCAs > 0 && !clusterMRCAs)) return fail(DMPC_ERR_ARG, "null pointer");
   HostTree ht;
   if (!ht.build(edge, nEdgeRows, numTips)) return fail(DMPC_ERR_ARG, ht.err);
-  if (dirtyVertex != 0 && (dirtyVertex <= numTips || dirtyVertex > ht.numVerts)) return fail(DMPC_ERR_ARG, "dirtyVertex must be internal");
+  if (dirtyVertex > 0 && (dirtyVertex <= numTips || dirtyVertex > ht.numVerts)) return fail(DMPC_ERR_ARG, "dirtyVertex must be internal");
   ht.associate(clusterMRCAs, nClusterMRCAs);
   ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
   {
@@ -1245,10 +1245,23 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
   ht.plan(p);
   const bool full = dirtyVertex == 0;
   std::vector<uint8_t> dirty(ht.numVerts, 0);
-  if (!full) {                                    // a proposal: the path from dirtyVertex to the root (InvalidateSolution)
+  if (!full) {                                    // a proposal on top of the evaluated tree
     ht.negateAllUpdateFlags();
-    ht.invalidateSolution(dirtyVertex - 1);
-    for (int v = dirtyVertex - 1; v != -1; v = ht.parent[v]) dirty[v] = 1;
+    if (dirtyVertex > 0) {                        // split / merge: the path from dirtyVertex to the root (InvalidateSolution)
+      ht.invalidateSolution(dirtyVertex - 1);
+    } else if (dirtyVertex == -1) {               // new between-cluster matrices (AugTree.cpp:273-287)
+      ht.invalidateBetween();
+    } else {                                      // one NNI move anywhere in the tree: two root paths that meet (AugTree.cpp:211-226)
+      for (int i = 0; i < -dirtyVertex - 2; i++) ht.rng.next();      // -2, -3, ...: different picks from the Tausworthe stream
+      std::vector<int> cand;
+      ht.nniCandidates(ht.root(), nullptr, cand);
+      if (!cand.empty()) {
+        int two[2];
+        ht.twoVerticesForNNI(cand[ht.rng.uniform_int(cand.size())], nullptr, two);
+        ht.rearrangeNNI(two[0], two[1]);
+      }
+    }
+    for (int v = numTips; v < ht.numVerts; v++) dirty[v] = !ht.solved[v];   // what TrySolve recomputes (AugTree.cpp:114-134)
     ht.plan(p);
   }
   const int N = numTips, nInt = N - 1;

@@ -174,7 +174,9 @@ int dmpc_timer_end(dmpc_tree* t, double* msOut);
  * consistent; the trailing chain handed to the walk kernel is one task per level, each forwarding into the next, with
  * the fused clades hanging off it materialised in level 0.  dirtyVertex = 0 checks the plan of a full evaluation;
  * dirtyVertex = a 1-based internal vertex id checks the plan of the proposal that follows a full evaluation and
- * invalidates that vertex and its ancestors (a split / merge / NNI root path).
+ * invalidates that vertex and its ancestors (a split / merge root path); -1: the plan after new between-cluster
+ * matrices (the between part of the tree); -2, -3, ...: the plan after one NNI move (two root paths that meet), a
+ * different pick for each value.
  * out[0..7] = stored vertices, fused vertices, levels, tokens, max stack depth, max tips of a task's programs, chain
  * levels, materialised clades.  Returns DMPC_OK or DMPC_ERR_STATE with the violated invariant in dmpc_last_error(). */
 int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,

@@ -152,5 +152,11 @@ def test_plan_builder_invariants(shape, fuse):
                 assert o[6] + (1 if o[7] else 0) == o[2]      # a single path: everything but the materialised level is chain
             chains += o[6] > 0
             mats += o[7]
+        if n >= 5:
+            o = check(-1)                                     # new between-cluster matrices: the top of the tree
+            assert o[6] == 0 or o[6] >= 4
+            for pick in range(12):                            # NNI moves: two dirty paths that meet below the root
+                o = check(-2 - pick)
+                assert o[6] == 0 or (o[6] >= 4 and o[6] <= o[2])
     if fuse > 1 and shape == "random":
         assert chains > 0 and mats > 0
