@@ -259,15 +259,24 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
         if node <= cv.n_tips:
             raise RuntimeError("split of a cluster whose stored MRCA is a tip (single-cluster start): "
                                "the reference dereferences a null child here (AugTree.cpp:332)")
-        new_nodes = phy.children[node]
+        new_nodes = phy.kids(node)
         new_mrcas = list(cv.clusterNodeIndices)
         new_mrcas[clus_number - 1] = new_nodes[0]
         new_mrcas += new_nodes[1:]
         new_ll = backend.clusSplitMergeLogLik(cv.extPointer, w, b, [node], st.numLikThreads, st.limProbs)
-        new_clus = cv.clusInd.copy()
         numbers = [clus_number] + list(range(len(cv.clusterNodeIndices) + 1, len(new_mrcas) + 1))
-        for nd, num in zip(new_nodes, numbers):
-            new_clus[phy.descendants(nd) - 1] = num
+        parts = [phy.descendants(nd) for nd in new_nodes]         # the tips that change label (shortRecursive, :112-119)
+        # table(newClusInd) without building newClusInd: the split cluster's tips are exactly the tips below its MRCA's
+        # children, and the labels in use are 1..K (merges relabel), so K+1 is new and the keys stay sorted
+        new_counts = dict(cv.clusterCounts)
+        for num, tips in zip(numbers, parts):
+            new_counts[num] = len(tips)
+
+        def build_clus():
+            out = cv.clusInd.copy()
+            for num, tips in zip(numbers, parts):
+                out[tips - 1] = num
+            return out
     else:
         to_merge = pairs[selected - 1]
         new_mrca = int(phy.parent[to_merge[0]])                   # phangorn::mrca.phylo of siblings
@@ -277,14 +286,18 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
             replaced[k - 1] = new_mrca
         new_mrcas = list(dict.fromkeys(replaced))                 # unique(), first occurrence kept
         new_ll = backend.clusSplitMergeLogLik(cv.extPointer, w, b, to_merge, st.numLikThreads, st.limProbs)
-        new_clus = cv.clusInd.copy()
-        new_clus[np.isin(new_clus, numbers)] = min(numbers)
+        lowest = min(numbers)                                     # the merged cluster takes the lowest label, leaving a gap
+        new_counts = {k: c for k, c in cv.clusterCounts.items() if k == lowest or k not in numbers}
+        new_counts[lowest] = sum(cv.clusterCounts[k] for k in numbers)
+
+        def build_clus():
+            out = cv.clusInd.copy()
+            out[np.isin(out, numbers)] = lowest
+            return out
     cv.n_loglik_calls += 1
-    labels, cnt = np.unique(new_clus, return_counts=True)
-    new_counts = {int(l): int(c) for l, c in zip(labels, cnt)}
-    new_lpp = (new_ll + _log_prior_of_counts(cnt, len(new_clus), cv.alpha)
+    new_lpp = (new_ll + _log_prior_of_counts(list(new_counts.values()), len(cv.clusInd), cv.alpha)
                + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
-               + _dpois_log(int(new_clus.max()), st.poisRateNumClus))
+               + _dpois_log(max(new_counts), st.poisRateNumClus))
     groups = {}
     for m in new_mrcas:
         groups.setdefault(int(phy.parent[m]), []).append(m)
@@ -294,7 +307,7 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
     mh = ratio * _exp(new_lpp - cv.logPostProb)
     if rng.random() < mh:
         cv.logLik, cv.logPostProb = new_ll, new_lpp
-        cv.clusInd, cv.clusterCounts, cv.clusterNodeIndices = new_clus, new_counts, new_mrcas
+        cv.clusInd, cv.clusterCounts, cv.clusterNodeIndices = build_clus(), new_counts, new_mrcas   # newClusInd, only if kept
         if not split_move:
             keys = _relabel(np.array(sorted(cv.clusterCounts)))
             cv.clusterCounts = {int(k): cv.clusterCounts[o] for k, o in zip(keys, sorted(cv.clusterCounts))}

@@ -20,26 +20,44 @@ class Phylo:
         self.parent[self.edge[:, 1]] = self.edge[:, 0]
         self.root = self.n_tips + 1
         self._children = None
+        self._table = None
 
-    @property
-    def children(self):
-        """children[v] in edge-row order (AddChild appends).  Built on first use: the MCMC driver rebuilds this view
-        after every accepted topology change but most moves only need `parent`."""
-        if self._children is None:
+    def _child_table(self):
+        """[node][0..1] = its two children in edge-row order (0, 0 for tips), built with a handful of vector operations;
+        None when the tree is not strictly bifurcating.  The MCMC driver rebuilds this view after every accepted
+        topology change, and most moves look at a few vertices only."""
+        if self._table is None:
             n_nodes = len(self.parent) - 1
             order = np.argsort(self.edge[:, 0], kind="stable")
             par_sorted, kid_sorted = self.edge[order, 0], self.edge[order, 1]
             if len(order) and len(order) % 2 == 0 and np.all(par_sorted[0::2] == par_sorted[1::2]) \
                     and (len(order) < 4 or np.all(par_sorted[0:-2:2] != par_sorted[2::2])):
-                # strictly bifurcating, so two per internal node: vectorised
                 ch = np.zeros((n_nodes + 1, 2), np.int64)
                 ch[par_sorted[0::2], 0] = kid_sorted[0::2]
                 ch[par_sorted[1::2], 1] = kid_sorted[1::2]
-                out = ch.tolist()
-                for t in range(self.n_tips + 1):
-                    out[t] = []
+                self._table = ch
+            else:
+                self._table = False
+        return self._table if self._table is not False else None
+
+    def kids(self, v: int) -> list:
+        """phangorn::Children(phy, v) in edge-row order."""
+        t = self._child_table()
+        if t is None:
+            return self.children[v]
+        return [] if v <= self.n_tips else [int(t[v, 0]), int(t[v, 1])]
+
+    @property
+    def children(self):
+        """children[v] for every vertex, in edge-row order (AddChild appends), as lists."""
+        if self._children is None:
+            t = self._child_table()
+            if t is not None:
+                out = t.tolist()
+                for tip in range(self.n_tips + 1):
+                    out[tip] = []
             else:                             # not bifurcating: generic path
-                out = [[] for _ in range(n_nodes + 1)]
+                out = [[] for _ in range(len(self.parent))]
                 for p, c in self.edge:
                     out[p].append(int(c))
             self._children = out
@@ -50,7 +68,18 @@ class Phylo:
 
     def descendants(self, v: int) -> np.ndarray:
         """Tip ids under v (phangorn::Descendants(type='tips')), in traversal order."""
-        out, stack, ch, nt = [], [v], self.children, self.n_tips
+        out, stack, nt = [], [int(v)], self.n_tips
+        t = self._child_table()
+        if t is not None and self._children is None:      # a few vertices: index the table instead of listing every vertex
+            while stack:
+                x = stack.pop()
+                if x <= nt:
+                    out.append(x)
+                else:
+                    stack.append(int(t[x, 1]))
+                    stack.append(int(t[x, 0]))
+            return np.array(out, dtype=np.int64)
+        ch = self.children
         while stack:
             x = stack.pop()
             if x <= nt:
