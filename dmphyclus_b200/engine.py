@@ -238,7 +238,7 @@ class Engine:
         ll = C.c_double()
         self._check(self.lib.dmpc_within_clus_nni_loglik(ptr, w, b, int(MRCAofClusForNNI),
                                                          int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
-        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
+        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T}      # [E][2] view of the column-major buffer (owned by the result)
 
     def betweenClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, clusterMRCAs, numMovesNNI,
                              numOpenMP, limProbs):
@@ -249,7 +249,7 @@ class Engine:
         ll = C.c_double()
         self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, w, b, _p(m, _dbl_p), len(m),
                                                           int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
-        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T.copy()}
+        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T}      # [E][2] view of the column-major buffer (owned by the result)
 
     def clusSplitMergeLogLik(self, ptr, withinTransProbs, betweenTransProbs, clusMRCAsToSplitOrMerge, numOpenMP,
                              limProbs) -> float:
