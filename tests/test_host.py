@@ -102,6 +102,45 @@ def test_chain_bookkeeping_invariants(oracle, packaged):
     assert seen["n"] == 25 and len(seen["edges"]) > 1          # some NNI was accepted along the way
 
 
+def test_tree_view_fast_paths_agree():
+    """Phylo.kids / descendants (vectorised child table) against the list-of-lists view, on bifurcating trees of every
+    shape and on a tree with a polytomy (generic path)."""
+    for shape in ("random", "balanced", "caterpillar"):
+        rng = np.random.default_rng(5)
+        e = synth.random_tree(40, rng, shape)
+        a, b = Phylo(e, 40), Phylo(e, 40)
+        full = b.children                      # forces the list view on b
+        for v in range(1, 2 * 40):
+            assert a.kids(v) == full[v]
+            assert np.array_equal(a.descendants(v), b.descendants(v))
+        assert a._children is None             # the fast paths never built the full list
+    poly = np.array([[4, 1], [4, 2], [4, 3]])
+    p = Phylo(poly, 3)
+    assert p.kids(4) == [1, 2, 3] and list(p.descendants(4)) == [1, 2, 3]
+
+
+def test_wrapper_converts_read_only_inputs_once(packaged):
+    """engine.Engine marshals a transition-matrix list / edge matrix once when it is handed the same READ-ONLY array
+    again (the MCMC driver proposes from fixed lists and rolls back to one committed edge matrix); writable arrays are
+    converted on every call, so editing them in place is always seen."""
+    from dmphyclus_b200 import build
+    from dmphyclus_b200.engine import Engine
+    build.build()
+    eng = Engine()
+    w = np.array(packaged["within"][4])
+    p1 = eng._mp(w)
+    w[0, 0, 1] += 0.25
+    p2 = eng._mp(w)
+    assert p1._arr is not p2._arr and p2._arr[4] == w[0, 0, 1]          # column-major: P(0,1) sits at [0 + 4*1]
+    w.setflags(write=False)
+    assert eng._mp(w) is eng._mp(w)
+    edge = np.array([[4, 1], [4, 5], [5, 2], [5, 3]], dtype=np.int32)
+    (a, n), (b, _) = eng._ep(edge), eng._ep(edge)
+    assert n == 4 and a is not b
+    edge.setflags(write=False)
+    assert eng._ep(edge)[0] is eng._ep(edge)[0] and list(eng._ep(edge)[0]._arr) == [4, 4, 5, 5, 1, 5, 2, 3]
+
+
 def test_workload_shapes_match_baseline():
     from dmphyclus_b200.workloads import CONFIGS
     assert CONFIGS["config2"] == (1000, 10000, 20, 3) and CONFIGS["config3"] == (10000, 30000, 100, 3)
