@@ -1359,6 +1359,119 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
   return DMPC_OK;
 }
 
+// ---------------------------------------------------------------- host-only scheduling for the CPU test-suite
+struct dmpc_hostplan {
+  HostTree ht;
+  HostTree::Plan plan;
+};
+
+int dmpc_hp_create(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
+                   int fuseTips, dmpc_hostplan** out) {
+  if (!edge || !out || (nClusterMRCAs > 0 && !clusterMRCAs)) return fail(DMPC_ERR_ARG, "null pointer");
+  dmpc_hostplan* h = new dmpc_hostplan;
+  if (!h->ht.build(edge, nEdgeRows, numTips)) { std::string e = h->ht.err; delete h; return fail(DMPC_ERR_ARG, e); }
+  h->ht.associate(clusterMRCAs, nClusterMRCAs);
+  h->ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
+  *out = h;
+  return DMPC_OK;
+}
+
+int dmpc_hp_propose(dmpc_hostplan* h, int kind, const int32_t* args, int nArgs) {
+  if (!h || (nArgs > 0 && !args)) return fail(DMPC_ERR_ARG, "null pointer");
+  HostTree& ht = h->ht;
+  auto vertexOK = [&](int v1) { return v1 >= 1 && v1 <= ht.numVerts; };
+  ht.negateAllUpdateFlags();
+  switch (kind) {
+    case 0: ht.invalidateAll(); return DMPC_OK;                       // clusterFunArmadillo.cpp:142-164
+    case 1: ht.invalidateBetween(); return DMPC_OK;                   // :117-138
+    case 2: {                                                         // HandleSplit, AugTree.cpp:328-336
+      if (nArgs != 1 || !vertexOK(args[0]) || args[0] <= ht.numTips) return fail(DMPC_ERR_ARG, "split: one internal mrca");
+      const int m = args[0] - 1;
+      ht.invalidateSolution(m);
+      ht.within[ht.kids[2 * m]] = 0; ht.within[ht.kids[2 * m + 1]] = 0;
+      return DMPC_OK;
+    }
+    case 3: {                                                         // HandleMerge, AugTree.cpp:338-346
+      if (nArgs < 2) return fail(DMPC_ERR_ARG, "merge: at least two mrcas");
+      for (int i = 0; i < nArgs; i++) if (!vertexOK(args[i])) return fail(DMPC_ERR_ARG, "merge: mrca out of range");
+      if (ht.parent[args[0] - 1] < 0) return fail(DMPC_ERR_ARG, "cannot merge the root");
+      ht.invalidateSolution(ht.parent[args[0] - 1]);
+      for (int i = 0; i < nArgs; i++) ht.within[args[i] - 1] = 1;
+      return DMPC_OK;
+    }
+    case 4: case 5: {                                                 // clusterFunArmadillo.cpp:168-242
+      std::vector<long> mr;
+      int origin, numMoves;
+      if (kind == 4) {
+        if (nArgs != 2 || !vertexOK(args[0])) return fail(DMPC_ERR_ARG, "within NNI: {mrca, numMoves}");
+        origin = args[0] - 1; numMoves = args[1];
+      } else {
+        if (nArgs < 1) return fail(DMPC_ERR_ARG, "between NNI: {numMoves, mrcas...}");
+        origin = ht.root(); numMoves = args[0];
+        for (int i = 1; i < nArgs; i++) mr.push_back(args[i]);
+      }
+      const std::vector<long>* mp = kind == 5 ? &mr : nullptr;
+      std::vector<int> cand;
+      ht.nniCandidates(origin, mp, cand);
+      if (cand.empty()) return fail(DMPC_ERR_NO_MOVE, "no vertex admits a nearest-neighbour interchange here");
+      for (int m = 0; m < numMoves; m++) {
+        int two[2];
+        ht.twoVerticesForNNI(cand[ht.rng.uniform_int(cand.size())], mp, two);
+        ht.rearrangeNNI(two[0], two[1]);
+      }
+      return DMPC_OK;
+    }
+    default: return fail(DMPC_ERR_ARG, "unknown proposal kind");
+  }
+}
+
+int dmpc_hp_plan(dmpc_hostplan* h, int32_t* tasks, int taskCap, int32_t* tokens, int tokenCap, int32_t* tips, int tipCap,
+                 int32_t* levelStart, int levelCap, int32_t* counts) {
+  if (!h || !tasks || !tokens || !tips || !levelStart || !counts) return fail(DMPC_ERR_ARG, "null pointer");
+  static_assert(sizeof(Task) == 32 && sizeof(Token) == 16, "plan records are plain int32 tuples");
+  HostTree::Plan& p = h->plan;
+  h->ht.plan(p);
+  const int nL = (int)p.levelStart.size() - 1;
+  if ((int)p.tasks.size() > taskCap || (int)p.tokens.size() > tokenCap || (int)p.tipList.size() > tipCap || nL + 1 > levelCap)
+    return fail(DMPC_ERR_ARG, "dmpc_hp_plan: output capacity too small");
+  if (!p.tasks.empty()) std::memcpy(tasks, p.tasks.data(), p.tasks.size() * sizeof(Task));
+  if (!p.tokens.empty()) std::memcpy(tokens, p.tokens.data(), p.tokens.size() * sizeof(Token));
+  if (!p.tipList.empty()) std::memcpy(tips, p.tipList.data(), p.tipList.size() * sizeof(int32_t));
+  for (int l = 0; l <= nL; l++) levelStart[l] = p.levelStart[l];
+  counts[0] = (int)p.tasks.size(); counts[1] = (int)p.tokens.size(); counts[2] = (int)p.tipList.size();
+  counts[3] = nL; counts[4] = p.chainLevels; counts[5] = p.materialised;
+  return DMPC_OK;
+}
+
+int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nniMove, const int32_t* clusterMRCAs,
+                    int nClusterMRCAs, int splitMergeMove) {
+  if (!h) return fail(DMPC_ERR_ARG, "null pointer");
+  HostTree& ht = h->ht;
+  if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
+    if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
+    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
+  }
+  for (int v = ht.numTips; v < ht.numVerts; v++)  // RestoreIterVecAndExp, IntermediateNode.h:26-33
+    if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
+  if (splitMergeMove) {
+    if (nClusterMRCAs > 0 && !clusterMRCAs) return fail(DMPC_ERR_ARG, "null pointer");
+    ht.associate(clusterMRCAs, nClusterMRCAs);
+  }
+  return DMPC_OK;
+}
+
+int dmpc_hp_state(dmpc_hostplan* h, uint8_t* cur, uint8_t* within, int32_t* edgeOut) {
+  if (!h || !cur || !within || !edgeOut) return fail(DMPC_ERR_ARG, "null pointer");
+  for (int v = 0; v < h->ht.numVerts; v++) { cur[v] = h->ht.cur[v]; within[v] = h->ht.within[v]; }
+  h->ht.exportEdges(edgeOut);
+  return DMPC_OK;
+}
+
+int dmpc_hp_destroy(dmpc_hostplan* h) {
+  delete h;
+  return DMPC_OK;
+}
+
 int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   int rc;
   if ((rc = checkHandle(t))) return rc;

@@ -71,6 +71,12 @@ ABI = {
     "dmpc_timer_begin": (C.c_int, [_P]),
     "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
     "dmpc_plan_selfcheck": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "dmpc_hp_create": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.POINTER(_P)]),
+    "dmpc_hp_propose": (C.c_int, [_P, C.c_int, _i32_p, C.c_int]),
+    "dmpc_hp_plan": (C.c_int, [_P, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p]),
+    "dmpc_hp_restore": (C.c_int, [_P, _i32_p, C.c_int, C.c_int, _i32_p, C.c_int, C.c_int]),
+    "dmpc_hp_state": (C.c_int, [_P, _u8_p, _u8_p, _i32_p]),
+    "dmpc_hp_destroy": (C.c_int, [_P]),
     "dmpc_get_partial": (C.c_int, [_P, C.c_int, _dbl_p, _f32_p]),
     "dmpc_get_topology": (C.c_int, [_P, _i32_p, _i32_p, _i32_p, _i32_p]),
     "dmpc_get_site_logliks": (C.c_int, [_P, _dbl_p]),

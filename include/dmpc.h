@@ -182,6 +182,29 @@ int dmpc_timer_end(dmpc_tree* t, double* msOut);
 int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
                         int fuseTips, int dirtyVertex, int* out);
 
+/* Host-side scheduling WITHOUT a device, for the CPU test-suite (tests/plan_interpreter.py executes the plans it hands
+ * out with numpy under the kernels' semantics and compares with the oracle).  No arithmetic happens here: a dmpc_hostplan
+ * is the same topology / proposal state machine a dmpc_tree owns (host_tree.hpp), driven by the same steps the entry
+ * points take before they evaluate.
+ *   dmpc_hp_propose kind: 0 = InvalidateAll (new within-cluster matrices, recompute); 1 = new between-cluster matrices;
+ *     2 = split, args = {mrca}; 3 = merge, args = the sibling mrcas; 4 = within-cluster NNI, args = {mrca, numMoves};
+ *     5 = between-cluster NNI, args = {numMoves, clusterMRCAs...}.  All ids 1-based.
+ *   dmpc_hp_plan: the pending evaluation as tasks (8 int32 each, struct Task), tokens (4 int32 each), tip list and level
+ *     starts; counts = {tasks, tokens, tips, levels, chainLevels, materialised}.  Like an evaluation, it marks the planned
+ *     vertices solved and flips their slots.  Fails with DMPC_ERR_ARG when a capacity is too small.
+ *   dmpc_hp_restore: the host part of dmpc_restore_previous_config.
+ *   dmpc_hp_state: cur (slot of every vertex), within flags, and the edge matrix in BuildEdgeMatrix order. */
+typedef struct dmpc_hostplan dmpc_hostplan;
+int dmpc_hp_create(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
+                   int fuseTips, dmpc_hostplan** out);
+int dmpc_hp_propose(dmpc_hostplan* h, int kind, const int32_t* args, int nArgs);
+int dmpc_hp_plan(dmpc_hostplan* h, int32_t* tasks, int taskCap, int32_t* tokens, int tokenCap, int32_t* tips, int tipCap,
+                 int32_t* levelStart, int levelCap, int32_t* counts);
+int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nniMove, const int32_t* clusterMRCAs,
+                    int nClusterMRCAs, int splitMergeMove);
+int dmpc_hp_state(dmpc_hostplan* h, uint8_t* cur, uint8_t* within, int32_t* edgeOut);
+int dmpc_hp_destroy(dmpc_hostplan* h);
+
 /* Introspection for parity tests: the committed partial of a vertex (0-based id >= numTips) as
  * sol [numLoci][R][4] and expo [numLoci][R] (the oracle's layout), and the topology/flags. */
 int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo);

@@ -1,0 +1,108 @@
+"""Host logic of the engine on CPU: the plans its scheduler hands out (dmpc_hp_*, no device involved), executed by the
+numpy interpreter of tests/plan_interpreter.py, must reproduce the oracle's partial vectors BIT FOR BIT after every step of
+a scripted proposal sequence — full evaluations, new matrices, NNI moves (same Tausworthe picks, same edge matrices),
+splits and merges, accepted and rejected — for every fusion threshold and tree shape, including walked chains with
+materialised clades and rescaling inside fused clades."""
+import numpy as np
+import pytest
+
+from dmphyclus_b200.phylo import Phylo
+from dmphyclus_b200.workloads import Problem
+from plan_interpreter import PlanMachine
+
+NO_EDGE = np.zeros((1, 2), np.int32)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dmphyclus_b200 import build
+    from dmphyclus_b200.engine import load_library
+    build.build()
+    return load_library()
+
+
+def _compare(machine, oracle, ho, n, what, every=1):
+    cur, within, edge = machine.state()
+    topo = oracle.topology(ho)
+    assert np.array_equal(within.astype(np.int32), np.asarray(topo["within"], np.int32)), what
+    for v in range(n + 1, 2 * n, every):
+        (sg, eg), (so, eo) = machine.partial(v), oracle.partial(ho, v - 1)
+        assert np.array_equal(sg, so), f"{what}: partial of vertex {v}"
+        assert np.allclose(eg, eo, rtol=2e-7, atol=0), f"{what}: exponents of vertex {v}"
+    return edge
+
+
+@pytest.mark.parametrize("n,S,k,R,kind,shape,fuse,seed", [
+    (9, 40, 2, 3, "evolved", "random", 15, 1), (40, 48, 5, 3, "evolved", "random", 4, 2), (64, 33, 6, 1, "iid", "balanced", 8, 3),
+    (120, 24, 5, 2, "iid", "caterpillar", 15, 4), (120, 24, 5, 2, "iid", "caterpillar", 1, 5), (300, 20, 8, 3, "iid", "random", 15, 6),
+    (300, 20, 8, 3, "diverged", "random", 2, 7), (400, 16, 6, 3, "tiny", "random", 8, 8), (500, 12, 24, 3, "evolved", "random", 15, 9)])
+def test_interpreted_plans_reproduce_the_oracle(lib, oracle, packaged, n, S, k, R, kind, shape, fuse, seed):
+    p = Problem(packaged, n, S, k, R, kind, shape, seed=seed)
+    W, B, pi = p.W, p.B, p.pi
+    masks = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    ho = oracle.logLikCpp(p.edge, p.mrcas, pi, W[4], B[4], 1, masks, n, S, 5, 5)["solutionPointer"]
+    mc = PlanMachine(lib, p, masks, fuse)
+    every = 1 if n <= 130 else 7
+    try:
+        mc.set_matrices(W[4], B[4])
+        st = mc.evaluate()                                         # logLikCpp
+        assert st["tasks"] > 0 and (fuse > 1 or st["tokens"] == 0)
+        edge = _compare(mc, oracle, ho, n, "create", every)
+        assert np.array_equal(edge, np.asarray(p.edge, np.int32))          # BuildEdgeMatrix order = the synthetic tree's own
+        mrcas, w, b = list(p.mrcas), 5, 5
+        phy = Phylo(edge, n)
+        chains = mats = 0
+
+        def step(what, kind_, args, call, keep, nni=False, split_merge=False, new_w=None, new_b=None):
+            nonlocal edge, w, b, chains, mats
+            mc.propose(kind_, args)
+            mc.set_matrices(W[(new_w or w) - 1], B[(new_b or b) - 1])
+            res = call()
+            st = mc.evaluate()
+            chains += st["chain"] > 0
+            mats += st["materialised"]
+            new_edge = _compare(mc, oracle, ho, n, what, every)
+            if nni:
+                assert np.array_equal(new_edge, np.asarray(res["edge"], np.int32)), what
+            if keep:
+                edge, w, b = new_edge, new_w or w, new_b or b
+            else:
+                oracle.RestorePreviousConfig(ho, edge if nni else NO_EDGE, w, b, nni, mrcas, split_merge)
+                mc.restore(edge if nni else NO_EDGE, nni, mrcas, split_merge)
+                mc.set_matrices(W[w - 1], B[b - 1])
+                _compare(mc, oracle, ho, n, what + " (rolled back)", every)
+
+        if len(mrcas) > 1:
+            step("between matrices", 1, (), lambda: oracle.newBetweenTransProbsLogLik(ho, W[w - 1], B[1], 1, 2, pi), False, new_b=2)
+        step("within matrices", 0, (), lambda: oracle.newWithinTransProbsLogLik(ho, W[6], B[b - 1], 1, 7, pi), True, new_w=7)
+        big = [m for m in mrcas if m > n and len(phy.descendants(m)) >= 3]
+        for m in big[:3]:
+            step(f"within NNI at {m}", 4, (m, 1), lambda m=m: oracle.withinClusNNIlogLik(ho, W[w - 1], B[b - 1], m, 1, 1, pi), False, nni=True)
+        if len(mrcas) > 2:
+            step("between NNI", 5, [1] + mrcas, lambda: oracle.betweenClusNNIlogLik(ho, W[w - 1], B[b - 1], mrcas, 1, 1, pi), True, nni=True)
+        if big:
+            m = big[-1]
+            step(f"within NNI x2 at {m}", 4, (m, 2), lambda: oracle.withinClusNNIlogLik(ho, W[w - 1], B[b - 1], m, 2, 1, pi), True, nni=True)
+        phy = Phylo(edge, n)
+        for m in [x for x in mrcas if x > n][:4]:
+            step(f"split {m}", 2, (m,), lambda m=m: oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], [m], 1, pi), False, split_merge=True)
+        by_parent = {}
+        for m in mrcas:
+            by_parent.setdefault(int(phy.parent[m]), []).append(m)
+        for g in [g for g in by_parent.values() if len(g) == 2][:3]:
+            step(f"merge {g}", 3, g, lambda g=g: oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], g, 1, pi), False, split_merge=True)
+        splittable = [x for x in mrcas if x > n]
+        if splittable:                                             # a split that is kept, then the two halves merged again
+            m = splittable[-1]
+            kids = phy.kids(m)
+            step(f"split {m} kept", 2, (m,), lambda: oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], [m], 1, pi), True)
+            step("between matrices kept", 1, (), lambda: oracle.newBetweenTransProbsLogLik(ho, W[w - 1], B[8], 1, 9, pi), True, new_b=9)
+            step(f"merge {kids} kept", 3, kids, lambda: oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], kids, 1, pi), True)
+        step("final within matrices", 0, (), lambda: oracle.newWithinTransProbsLogLik(ho, W[2], B[b - 1], 1, 3, pi), True, new_w=3)
+        if shape == "caterpillar":
+            assert chains > 0
+        if n >= 300 and fuse > 2:
+            assert chains > 0 and mats > 0            # root paths were walked, with fused clades materialised off them
+    finally:
+        mc.close()
+        oracle.finalDeallocate(ho)
