@@ -106,3 +106,88 @@ def test_interpreted_plans_reproduce_the_oracle(lib, oracle, packaged, n, S, k, 
     finally:
         mc.close()
         oracle.finalDeallocate(ho)
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_proposal_sequences(lib, oracle, packaged, seed):
+    """Random shapes, sizes, fusion thresholds and 14 random moves each (matrices, within / between NNI with 1-3 swaps,
+    splits, merges; kept or rolled back at random): the interpreted plans track the oracle through the whole sequence."""
+    rng = np.random.default_rng(1000 + seed)
+    n, S = int(rng.integers(5, 260)), int(rng.integers(3, 20))
+    k, R = int(rng.integers(1, min(12, n // 2) + 1)), int(rng.integers(1, 4))
+    kind = str(rng.choice(["evolved", "iid", "diverged", "tiny"]))
+    shape, fuse = str(rng.choice(["random", "balanced", "caterpillar"])), int(rng.choice([1, 2, 3, 5, 8, 15]))
+    p = Problem(packaged, n, S, k, R, kind, shape, seed=seed)
+    W, B, pi = p.W, p.B, p.pi
+    masks = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    ho = oracle.logLikCpp(p.edge, p.mrcas, pi, W[4], B[4], 1, masks, n, S, 5, 5)["solutionPointer"]
+    mc = PlanMachine(lib, p, masks, fuse)
+    every = max(1, n // 40)
+    try:
+        mc.set_matrices(W[4], B[4])
+        mc.evaluate()
+        edge = _compare(mc, oracle, ho, n, "create", every)
+        mrcas, w, b = list(p.mrcas), 5, 5
+        for it in range(14):
+            phy = Phylo(edge, n)
+            move, keep = int(rng.integers(0, 6)), bool(rng.integers(0, 2))
+            nni = sm = False
+            new_w = new_b = new_mrcas = res = None
+            if move == 0:
+                new_w = int(rng.integers(1, 11))
+                mc.propose(0)
+                oracle.newWithinTransProbsLogLik(ho, W[new_w - 1], B[b - 1], 1, new_w, pi)
+            elif move == 1:
+                new_b = int(rng.integers(1, 11))
+                mc.propose(1)
+                oracle.newBetweenTransProbsLogLik(ho, W[w - 1], B[new_b - 1], 1, new_b, pi)
+            elif move == 2:
+                big = [m for m in mrcas if m > n and len(phy.descendants(m)) >= 3]
+                if not big:
+                    continue
+                m, nm, nni = int(rng.choice(big)), int(rng.integers(1, 4)), True
+                mc.propose(4, (m, nm))
+                res = oracle.withinClusNNIlogLik(ho, W[w - 1], B[b - 1], m, nm, 1, pi)
+            elif move == 3:
+                nm = int(rng.integers(1, 3))
+                try:
+                    mc.propose(5, [nm] + mrcas)
+                except RuntimeError:                                  # no candidate above the clusters: nothing was drawn
+                    continue
+                nni = True
+                res = oracle.betweenClusNNIlogLik(ho, W[w - 1], B[b - 1], mrcas, nm, 1, pi)
+            elif move == 4:
+                sp = [m for m in mrcas if m > n]
+                if not sp:
+                    continue
+                m, sm = int(rng.choice(sp)), True
+                mc.propose(2, (m,))
+                oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], [m], 1, pi)
+                new_mrcas = [x for x in mrcas if x != m] + phy.kids(m)
+            else:
+                by_parent = {}
+                for m in mrcas:
+                    by_parent.setdefault(int(phy.parent[m]), []).append(m)
+                pairs = [g for g in by_parent.values() if len(g) == 2]
+                if not pairs:
+                    continue
+                g, sm = pairs[int(rng.integers(0, len(pairs)))], True
+                mc.propose(3, g)
+                oracle.clusSplitMergeLogLik(ho, W[w - 1], B[b - 1], g, 1, pi)
+                new_mrcas = [x for x in mrcas if x not in g] + [int(phy.parent[g[0]])]
+            mc.set_matrices(W[(new_w or w) - 1], B[(new_b or b) - 1])
+            mc.evaluate()
+            new_edge = _compare(mc, oracle, ho, n, f"move {it} kind {move}", every)
+            if nni:
+                assert np.array_equal(new_edge, np.asarray(res["edge"], np.int32))
+            if keep:
+                edge, w, b = new_edge, new_w or w, new_b or b
+                mrcas = new_mrcas if new_mrcas is not None else mrcas
+            else:
+                oracle.RestorePreviousConfig(ho, edge if nni else NO_EDGE, w, b, nni, mrcas, sm)
+                mc.restore(edge if nni else NO_EDGE, nni, mrcas, sm)
+                mc.set_matrices(W[w - 1], B[b - 1])
+                _compare(mc, oracle, ho, n, f"move {it} rolled back", every)
+    finally:
+        mc.close()
+        oracle.finalDeallocate(ho)
