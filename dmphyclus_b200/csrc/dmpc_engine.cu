@@ -1042,19 +1042,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       for (int i = b0; i < nProps; i++) {
         const dmpc_proposal& q = props[i];
         const size_t before = pp.tasks.size();
-        if (q.kind == DMPC_PROPOSAL_SPLIT) {         // HandleSplit, AugTree.cpp:328-336, on a scratch copy of the flags
-          const int m = q.a - 1, k0 = ht.kids[2 * m], k1 = ht.kids[2 * m + 1];
-          const uint8_t w0 = ht.within[k0], w1 = ht.within[k1];
-          ht.within[k0] = 0; ht.within[k1] = 0;
-          ht.pathRun(m, pp);
-          ht.within[k0] = w0; ht.within[k1] = w1;
-        } else {                                     // HandleMerge, AugTree.cpp:338-346
-          const int a = q.a - 1, b = q.b - 1;
-          const uint8_t wa = ht.within[a], wb = ht.within[b];
-          ht.within[a] = 1; ht.within[b] = 1;
-          ht.pathRun(ht.parent[a], pp);
-          ht.within[a] = wa; ht.within[b] = wb;
-        }
+        ht.proposalRun(q.kind == DMPC_PROPOSAL_MERGE, q.a, q.b, pp);
         const int len = (int)(pp.tasks.size() - before);
         if (len > JCAP) { pp.tasks.resize(before); b0 = i + 1; if (member.empty()) continue; else { b0 = i; break; } }
         const int jm = std::max(jmax, len);
@@ -1440,6 +1428,30 @@ int dmpc_hp_plan(dmpc_hostplan* h, int32_t* tasks, int taskCap, int32_t* tokens,
   for (int l = 0; l <= nL; l++) levelStart[l] = p.levelStart[l];
   counts[0] = (int)p.tasks.size(); counts[1] = (int)p.tokens.size(); counts[2] = (int)p.tipList.size();
   counts[3] = nL; counts[4] = p.chainLevels; counts[5] = p.materialised;
+  return DMPC_OK;
+}
+
+int dmpc_hp_path(dmpc_hostplan* h, int kind, int a, int b, int32_t* tasks, int taskCap, int32_t* tokens, int tokenCap,
+                 int32_t* tips, int tipCap, int32_t* counts) {
+  if (!h || !tasks || !tokens || !tips || !counts) return fail(DMPC_ERR_ARG, "null pointer");
+  HostTree& ht = h->ht;
+  if (!ht.solved[ht.root()]) return fail(DMPC_ERR_STATE, "the committed state has pending invalidations");
+  if (kind == DMPC_PROPOSAL_SPLIT) {
+    if (a <= ht.numTips || a > ht.numVerts) return fail(DMPC_ERR_ARG, "split: the cluster MRCA must be an internal vertex");
+  } else if (kind == DMPC_PROPOSAL_MERGE) {
+    if (a < 1 || a > ht.numVerts || b < 1 || b > ht.numVerts || a == b || ht.parent[a - 1] < 0 || ht.parent[a - 1] != ht.parent[b - 1])
+      return fail(DMPC_ERR_ARG, "merge: the two cluster MRCAs must be siblings");
+  } else {
+    return fail(DMPC_ERR_ARG, "unknown proposal kind");
+  }
+  HostTree::Plan pp;
+  ht.proposalRun(kind == DMPC_PROPOSAL_MERGE, a, b, pp);
+  if ((int)pp.tasks.size() > taskCap || (int)pp.tokens.size() > tokenCap || (int)pp.tipList.size() > tipCap)
+    return fail(DMPC_ERR_ARG, "dmpc_hp_path: output capacity too small");
+  if (!pp.tasks.empty()) std::memcpy(tasks, pp.tasks.data(), pp.tasks.size() * sizeof(Task));
+  if (!pp.tokens.empty()) std::memcpy(tokens, pp.tokens.data(), pp.tokens.size() * sizeof(Token));
+  if (!pp.tipList.empty()) std::memcpy(tips, pp.tipList.data(), pp.tipList.size() * sizeof(int32_t));
+  counts[0] = (int)pp.tasks.size(); counts[1] = (int)pp.tokens.size(); counts[2] = (int)pp.tipList.size();
   return DMPC_OK;
 }
 

@@ -340,6 +340,25 @@ struct HostTree {
     }
   }
 
+  // One proposal of a batch (dmpc_eval_proposals) as a run: the cluster flags a split (HandleSplit, AugTree.cpp:328-336)
+  // or a merge (HandleMerge, :338-346) would set are applied to a scratch copy of the two flags involved, the path is
+  // planned, the flags are put back.  Ids are 1-based as in dmpc_proposal; the caller has validated them.
+  void proposalRun(bool merge, int a1, int b1, Plan& p) {
+    if (!merge) {
+      const int m = a1 - 1, k0 = kids[2 * m], k1 = kids[2 * m + 1];
+      const uint8_t w0 = within[k0], w1 = within[k1];
+      within[k0] = 0; within[k1] = 0;
+      pathRun(m, p);
+      within[k0] = w0; within[k1] = w1;
+    } else {
+      const int a = a1 - 1, b = b1 - 1;
+      const uint8_t wa = within[a], wb = within[b];
+      within[a] = 1; within[b] = 1;
+      pathRun(parent[a], p);
+      within[a] = wa; within[b] = wb;
+    }
+  }
+
   void plan(Plan& p) {
     allInvalid = false;
     p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();

@@ -74,6 +74,7 @@ ABI = {
     "dmpc_hp_create": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.POINTER(_P)]),
     "dmpc_hp_propose": (C.c_int, [_P, C.c_int, _i32_p, C.c_int]),
     "dmpc_hp_plan": (C.c_int, [_P, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p]),
+    "dmpc_hp_path": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p, C.c_int, _i32_p]),
     "dmpc_hp_restore": (C.c_int, [_P, _i32_p, C.c_int, C.c_int, _i32_p, C.c_int, C.c_int]),
     "dmpc_hp_state": (C.c_int, [_P, _u8_p, _u8_p, _i32_p]),
     "dmpc_hp_destroy": (C.c_int, [_P]),

@@ -192,6 +192,9 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
  *   dmpc_hp_plan: the pending evaluation as tasks (8 int32 each, struct Task), tokens (4 int32 each), tip list and level
  *     starts; counts = {tasks, tokens, tips, levels, chainLevels, materialised}.  Like an evaluation, it marks the planned
  *     vertices solved and flips their slots.  Fails with DMPC_ERR_ARG when a capacity is too small.
+ *   dmpc_hp_path: one proposal of a dmpc_eval_proposals batch (kind = DMPC_PROPOSAL_SPLIT / _MERGE, a, b as in
+ *     dmpc_proposal) as its run of tasks: the stored vertices of the path to the root, bottom-up, each forwarding into the
+ *     next; nothing is mutated.  counts = {tasks, tokens, tips}.
  *   dmpc_hp_restore: the host part of dmpc_restore_previous_config.
  *   dmpc_hp_state: cur (slot of every vertex), within flags, and the edge matrix in BuildEdgeMatrix order. */
 typedef struct dmpc_hostplan dmpc_hostplan;
@@ -200,6 +203,8 @@ int dmpc_hp_create(const int32_t* edge, int nEdgeRows, int numTips, const double
 int dmpc_hp_propose(dmpc_hostplan* h, int kind, const int32_t* args, int nArgs);
 int dmpc_hp_plan(dmpc_hostplan* h, int32_t* tasks, int taskCap, int32_t* tokens, int tokenCap, int32_t* tips, int tipCap,
                  int32_t* levelStart, int levelCap, int32_t* counts);
+int dmpc_hp_path(dmpc_hostplan* h, int kind, int a, int b, int32_t* tasks, int taskCap, int32_t* tokens, int tokenCap,
+                 int32_t* tips, int tipCap, int32_t* counts);
 int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nniMove, const int32_t* clusterMRCAs,
                     int nClusterMRCAs, int splitMergeMove);
 int dmpc_hp_state(dmpc_hostplan* h, uint8_t* cur, uint8_t* within, int32_t* edgeOut);

@@ -100,7 +100,7 @@ class PlanMachine:
     def _tip_term(self, tset, tip):
         return matvec(self.P[tset], self.ind[tip])
 
-    def _run_program(self, tokens, tips, flip=0):
+    def _run_program(self, tokens, tips, flip=0, store=True):
         stack, reg = [], None
         for op_word, a, b, vertex in tokens:
             op = op_word & 7
@@ -121,8 +121,9 @@ class PlanMachine:
             else:
                 raise AssertionError("unknown opcode")
             reg, e = combine_exact(first, second)
-            slot = (1 if op_word & TOK_SLOT else 0) ^ flip
-            self.val[slot][vertex], self.exp[slot][vertex] = reg, e
+            if store:
+                slot = (1 if op_word & TOK_SLOT else 0) ^ flip
+                self.val[slot][vertex], self.exp[slot][vertex] = reg, e
         assert not stack
         return reg
 
@@ -168,3 +169,39 @@ class PlanMachine:
                 prev = (out, sol)
         self.last = dict(tasks=n_t, levels=n_l, chain=chain, materialised=int(counts[5]), tokens=int(counts[1]))
         return self.last
+
+    def run_path(self, kind, a, b=0):
+        """One proposal of a dmpc_eval_proposals batch (k_prune<false, PATHS>): the run of stored vertices from the changed
+        vertex to the root, the path partial forwarded from task to task, only off-path operands read, NOTHING written.
+        Returns [(internal index, partial, exponents)] bottom-up."""
+        ct, ck, cl, _ = self.cap
+        tasks, tokens = np.zeros((ct, 8), np.int32), np.zeros((ck, 4), np.int32)
+        tips, counts = np.zeros(cl, np.int32), np.zeros(3, np.int32)
+        self._ok(self.lib.dmpc_hp_path(self.h, kind, a, b, _i32(tasks), ct, _i32(tokens), ck, _i32(tips), cl, _i32(counts)))
+        out, prev = [], None
+        for i in range(int(counts[0])):
+            vtx, c0, c1, fl, prog, ntok, tip_off, n_tips = [int(x) for x in tasks[i]]
+            tset = 1 if fl & TF_WITHIN else 0
+            my_tips = tips[tip_off:tip_off + n_tips]
+            n0 = ntok & 0xffff
+            assert not fl & TF_HEAD and bool(fl & (TF_C0FWD | TF_C1FWD)) == (i > 0) and (fl & (TF_C0FWD | TF_C1FWD)) != (TF_C0FWD | TF_C1FWD)
+            terms = []
+            for j, (c, is_tip, is_fused, slot_bit, fwd_bit) in enumerate((
+                    (c0, fl & TF_C0TIP, fl & TF_C0FUSED, fl & TF_C0SLOT, fl & TF_C0FWD),
+                    (c1, fl & TF_C1TIP, fl & TF_C1FUSED, fl & TF_C1SLOT, fl & TF_C1FWD))):
+                if is_tip:
+                    terms.append(self._tip_term(tset, c))
+                elif fwd_bit:
+                    assert prev[0] == c
+                    terms.append(matvec(self.P[tset], prev[1]))
+                elif is_fused:
+                    lo = prog + (n0 if j else 0)
+                    hi = lo + ((ntok >> 16) & 0xffff if j else n0)
+                    terms.append(matvec(self.P[tset], self._run_program([tuple(int(x) for x in t) for t in tokens[lo:hi]],
+                                                                        my_tips, store=False)))
+                else:
+                    terms.append(matvec(self.P[tset], self.val[1 if slot_bit else 0][c]))
+            sol, e = combine_exact(terms[0], terms[1])
+            prev = (vtx, sol)
+            out.append((vtx, sol, e))
+        return out

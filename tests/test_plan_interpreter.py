@@ -191,3 +191,40 @@ def test_random_proposal_sequences(lib, oracle, packaged, seed):
     finally:
         mc.close()
         oracle.finalDeallocate(ho)
+
+
+@pytest.mark.parametrize("n,S,k,R,kind,shape,fuse,seed", [
+    (64, 24, 9, 1, "evolved", "random", 8, 21), (300, 20, 24, 3, "evolved", "random", 15, 22), (300, 20, 24, 3, "iid", "random", 1, 23),
+    (200, 16, 12, 2, "tiny", "random", 8, 24), (150, 16, 10, 3, "iid", "caterpillar", 4, 25), (256, 12, 16, 3, "diverged", "balanced", 15, 26)])
+def test_proposal_runs_of_a_batch(lib, oracle, packaged, n, S, k, R, kind, shape, fuse, seed):
+    """dmpc_eval_proposals plans every split / merge of a batch as a run (HostTree::proposalRun, the function the product
+    calls): interpreted in the batch kernel's way — path partial forwarded, off-path operands from the committed state,
+    nothing written — every vertex of every proposal's path equals the oracle's after the same proposal, and the
+    committed state is untouched."""
+    p = Problem(packaged, n, S, k, R, kind, shape, seed=seed)
+    W, B, pi = p.W[4], p.B[4], p.pi
+    masks = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    ho = oracle.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, masks, n, S, 5, 5)["solutionPointer"]
+    mc = PlanMachine(lib, p, masks, fuse)
+    try:
+        mc.set_matrices(W, B)
+        mc.evaluate()
+        phy = Phylo(p.edge, n)
+        props = [(0, m, 0) for m in p.mrcas if m > n]
+        by_parent = {}
+        for m in p.mrcas:
+            by_parent.setdefault(int(phy.parent[m]), []).append(m)
+        props += [(1, g[0], g[1]) for g in by_parent.values() if len(g) == 2]
+        assert len(props) >= 2
+        for kind_, a, b in props:
+            run = mc.run_path(kind_, a, b)
+            oracle.clusSplitMergeLogLik(ho, W, B, [a] if kind_ == 0 else [a, b], 1, pi)
+            assert run and run[-1][0] == 0                                    # the run ends at the root
+            for idx, sol, e in run:
+                so, eo = oracle.partial(ho, idx + n)
+                assert np.array_equal(sol, so) and np.allclose(e, eo, rtol=2e-7, atol=0), (kind_, a, b, idx)
+            oracle.RestorePreviousConfig(ho, NO_EDGE, 5, 5, False, p.mrcas, True)
+        _compare(mc, oracle, ho, n, "after the batch", max(1, n // 50))      # the machine's committed state never moved
+    finally:
+        mc.close()
+        oracle.finalDeallocate(ho)
