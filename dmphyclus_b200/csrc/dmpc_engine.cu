@@ -66,6 +66,7 @@ struct dmpc_comm {
   void* peer[CW] = {nullptr};          // every rank's mailbox as seen from here
   unsigned* seq = nullptr;             // message counter (device)
   bool connected = false;
+  int maxChunks = 0;
   size_t flagBytes() const { return 64; }
   size_t payloadBytes() const { return (size_t)2 * CW * width * sizeof(double); }
   size_t carryBytes() const { return (size_t)2 * CW * RMAX * sizeof(float); }
@@ -111,7 +112,7 @@ struct dmpc_tree {
   } cache;
   unsigned long long planCacheHits = 0;
   // the cached full-evaluation plan as CUDA graphs (one per slot flip): level launches + gather in ONE submission
-  struct { cudaGraphExec_t exec = nullptr; unsigned long long version = 0; } graphs[2];
+  struct { cudaGraphExec_t exec = nullptr; unsigned long long version = 0; bool predicted = false; } graphs[2];
   unsigned long long graphVersion = 1;   // bumped whenever something baked into the captured kernel parameters changes
   bool capturing = false, gatherPrelaunched = false;
   unsigned long long graphReplays = 0;
@@ -126,6 +127,9 @@ struct dmpc_tree {
   dmpc_comm* comm = nullptr;
   int chainGroup = 4;            // rows per group of the chain walker: 4 for long exponent lists, 1 for sparse ones
   int lastNact = 0;
+  bool predictActive = false;    // the last evaluation saw a rescaled site: queue gather + cert + final without waiting for the gather
+  bool seqPredicted = false;     // what the root sequence in flight was launched with
+  int lastCert = 0, lastCertRate = -1, lastCertSites = 0;
   std::vector<int> lastTouched;  // internal indices the pending proposal flipped
 
   template <class Tp>
@@ -293,7 +297,7 @@ dmpc_tree* g_constOwner[64] = {nullptr};
 std::mutex g_deviceMutex[64];
 
 int rootStage(dmpc_tree* t, double* ll);
-int launchGather(dmpc_tree* t, int mode);
+int launchRootSequence(dmpc_tree* t);
 
 constexpr int NARROW_LEVEL = 4;   // levels with at most this many tasks are chained into one launch
 
@@ -448,13 +452,14 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   if (hit) {
     // replay (or first capture) of the whole device-side sequence of this cached plan: levels + gather
     auto& g = t->graphs[flip];
-    if (!g.exec || g.version != t->graphVersion) {
+    const bool predicted = chainMode && t->predictActive;
+    if (!g.exec || g.version != t->graphVersion || g.predicted != predicted) {
       if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
       cudaGraph_t graph = nullptr;
       CUDA_TRY(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
       t->capturing = true;
       int rcC = runPlan(t);
-      if (!rcC) rcC = launchGather(t, chainMode ? 1 : 0);
+      if (!rcC) rcC = launchRootSequence(t);
       if (!rcC) rcC = recordEv(t, 2);
       t->capturing = false;
       const cudaError_t ce = cudaStreamEndCapture(t->stream, &graph);
@@ -464,12 +469,14 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
       cudaGraphDestroy(graph);
       if (ci != cudaSuccess) return fail(DMPC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci));
       g.version = t->graphVersion;
+      g.predicted = predicted;
     }
+    t->seqPredicted = predicted;
     CUDA_TRY(cudaGraphLaunch(g.exec, t->stream));
     t->gatherPrelaunched = true;
     t->pubExpected++;
     t->graphReplays++;
-    t->st.kernel_launches += t->st.last_prune_launches + 1;
+    t->st.kernel_launches += t->st.last_prune_launches + (predicted ? 3 : 1);
   } else if ((rc = runPlan(t))) {
     return rc;
   }
@@ -500,27 +507,67 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   return DMPC_OK;
 }
 
-int launchGather(dmpc_tree* t, int mode) {
-  t->rv.exactMode = t->exact ? 1 : 0;
+// the peer mailboxes of a site-sharded run, as the root kernels see them (world = 1: no exchange)
+void attachComm(dmpc_tree* t) {
   t->rv.comm.world = 1;
-  if (t->deferred && t->comm && t->comm->connected && t->comm->device == t->device && t->nChunks + 2 <= t->comm->width) {
-    const dmpc_comm& c = *t->comm;
-    CommView& cv = t->rv.comm;
-    cv.world = c.world; cv.rank = c.rank; cv.width = c.width; cv.seq = c.seq;
-    for (int p = 0; p < c.world; p++) {
-      cv.flag[p] = (unsigned*)c.peer[p];
-      cv.payload[p] = (double*)((char*)c.peer[p] + c.flagBytes());
-      cv.cflag[p] = (unsigned*)((char*)c.peer[p] + c.flagBytes() + c.payloadBytes());
-      cv.carry[p] = (float*)((char*)c.peer[p] + 2 * c.flagBytes() + c.payloadBytes());
-    }
+  if (!(t->deferred && t->comm && t->comm->connected && t->comm->device == t->device)) return;
+  const dmpc_comm& c = *t->comm;
+  if (XHDR + t->nChunks + t->T * xrec(t->rv.RP) > c.width) return;       // the message would not fit: host protocol
+  CommView& cv = t->rv.comm;
+  cv.world = c.world; cv.rank = c.rank; cv.width = c.width; cv.seq = c.seq;
+  for (int p = 0; p < c.world; p++) {
+    cv.flag[p] = (unsigned*)c.peer[p];
+    cv.payload[p] = (double*)((char*)c.peer[p] + c.flagBytes());
+    cv.cflag[p] = (unsigned*)((char*)c.peer[p] + c.flagBytes() + c.payloadBytes());
+    cv.carry[p] = (float*)((char*)c.peer[p] + 2 * c.flagBytes() + c.payloadBytes());
   }
+}
+
+int launchGather(dmpc_tree* t, int mode, bool publish) {
+  t->rv.exactMode = t->exact ? 1 : 0;
+  t->rv.publishAtGather = publish ? 1 : 0;
+  attachComm(t);
   CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
   if (t->deferred && mode == 1)                  // site-sharded: the gather's optimistic finish assumes the vector enters as zeros
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
   if (t->rv.RP == 4) k_root_gather<4, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
   else k_root_gather<8, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
   t->st.kernel_launches++;
-  if (!t->capturing) { CUDA_TRY(cudaGetLastError()); t->pubExpected++; }   // (a replayed graph counts its own gather)
+  if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
+}
+
+// reduceAll: 0 = chunk sums only (host protocol of a sharded run), 1 = this handle's total, 2 = cross-rank exchange
+int launchFinal(dmpc_tree* t, int mode, int reduceAll, bool publish) {
+  k_final<false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll, publish ? 1 : 0, PathView{});
+  t->st.kernel_launches++;
+  if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  return DMPC_OK;
+}
+
+// k_cert + k_final(mode 2): the chain resolved by certificate, result published by the final kernel
+int launchCertFinal(dmpc_tree* t) {
+  const int reduceAll = t->rv.comm.world > 1 ? 2 : 1;
+  if (t->rv.RP == 4) k_cert<4, false><<<1, TILE, 0, t->stream>>>(t->dv, t->rv);
+  else k_cert<8, false><<<1, TILE, 0, t->stream>>>(t->dv, t->rv);
+  t->st.kernel_launches++;
+  if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  return launchFinal(t, 2, reduceAll, true);
+}
+
+// What follows the pruning of an evaluation.  Usually no site rescaled last time and the gather alone finishes (and
+// publishes); when the last evaluation did see rescaled sites, the certificate and the final kernel are queued behind
+// the gather at once — no host round trip in between — and the final kernel publishes.
+int launchRootSequence(dmpc_tree* t) {
+  const bool chain = t->quirk && t->R > 1;
+  attachComm(t);
+  const bool hostProtocol = t->deferred && t->rv.comm.world == 1;
+  const bool predicted = chain && !hostProtocol && t->predictActive;
+  t->seqPredicted = predicted;
+  int rc;
+  if ((rc = launchGather(t, chain ? 1 : 0, !predicted))) return rc;
+  if (predicted && (rc = launchCertFinal(t))) return rc;
+  if (!t->capturing) t->pubExpected++;             // (a replayed graph counts its own publication)
   return DMPC_OK;
 }
 
@@ -565,58 +612,63 @@ int launchChain(dmpc_tree* t, const RootView* rvBatch = nullptr, int nBatch = 0)
   return DMPC_OK;
 }
 
-int launchFinal(dmpc_tree* t, int mode, int reduceAll) {
-  k_final<false><<<t->nChunks, CHUNK, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll, PathView{});
-  t->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
-  return DMPC_OK;
-}
-
-// one D2H copy of everything the host needs after a batch of kernels, then the only synchronisation point
-// afterGather: the last kernel queued is k_root_gather, whose last block publishes the finished status block into the
-// mapped host mirror (DevStatus::pubSeq): the host polls for it — no copy queued behind the kernel, no stream
-// synchronisation, which together cost more than a root-path evaluation's kernels.  Otherwise (chain / final kernels ran,
-// or the chunk sums are wanted too): one D2H copy and the only synchronisation point.
-int readStatus(dmpc_tree* t, bool withChunks, bool afterGather) {
-  bool polled = false;
-  if (afterGather && !withChunks && t->rv.hostSt) {
+// The host's view of the status block after the kernels queued so far.
+// polled: the last kernel queued publishes the finished block into the mapped host mirror (DevStatus::pubSeq) and the
+// host polls for it — no copy queued behind the kernel, no stream synchronisation, which together cost more than a
+// root-path evaluation's kernels.  Otherwise (literal chain fallback, or the chunk sums are wanted too): one D2H copy
+// and the only synchronisation point.
+int readStatus(dmpc_tree* t, bool withChunks, bool polled) {
+  bool got = false;
+  if (polled && !withChunks && t->rv.hostSt) {
     const volatile unsigned* seq = &t->h_res->pubSeq;
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spin = 1;; spin++) {
-      if (*seq == t->pubExpected) { polled = true; break; }
+      if (*seq == t->pubExpected) { got = true; break; }
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
       if ((spin & 0x3fff) == 0) {
-        if (cudaStreamQuery(t->stream) != cudaErrorNotReady) { polled = *seq == t->pubExpected; break; }   // finished (or failed)
+        if (cudaStreamQuery(t->stream) != cudaErrorNotReady) { got = *seq == t->pubExpected; break; }   // finished (or failed)
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0) break;
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
   }
-  if (!polled) {
+  if (!got) {
     CUDA_TRY(cudaMemcpyAsync(t->h_res, t->rv.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
     if (withChunks)
       CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
   }
   t->st.last_active_tiles = t->h_res->nact;
-  t->st.last_chain_sites = t->h_res->nact ? t->h_res->chainSites : 0;
-  t->st.last_chain_rows = t->h_res->nact ? t->h_res->chainRows : 0;
   t->lastNact = t->h_res->nact;
-  if (t->h_res->nact && t->h_res->chainSites > 0) {
-    // rows per rescaled site as the chain just saw them (padded to the group size): sparse lists walk faster one row at a time
-    const double avg = (double)t->h_res->chainRows / t->h_res->chainSites;
-    if (t->chainGroup == 4 && avg < 4.5) t->chainGroup = 1;
-    else if (t->chainGroup == 1 && avg > 6.0) t->chainGroup = 4;
-  }
   return DMPC_OK;
 }
 
+// bookkeeping once an evaluation's chain is resolved: what walked what (dmpc_stats), and how k_chain should group rows
+void noteChain(dmpc_tree* t, bool anyActive) {
+  const HostResult& h = *t->h_res;
+  t->lastCert = anyActive ? h.cert : CERT_NONE;
+  t->lastCertRate = t->lastCert == CERT_OK ? h.certRate : -1;
+  t->lastCertSites = t->lastCert == CERT_OK ? h.certL0 : 0;
+  t->st.last_chain_sites = anyActive && h.nact ? h.chainSites : 0;
+  t->st.last_chain_rows = anyActive && h.nact ? h.chainRows : 0;
+  t->st.last_cert = t->lastCert; t->st.last_cert_rate = t->lastCertRate;
+  if (t->lastCert == CERT_LITERAL && h.nact && h.chainSites > 0) {
+    // rows per rescaled site as the chain just saw them (padded to the group size): sparse lists walk faster one row at a time
+    const double avg = (double)h.chainRows / h.chainSites;
+    if (t->chainGroup == 4 && avg < 4.5) t->chainGroup = 1;
+    else if (t->chainGroup == 1 && avg > 6.0) t->chainGroup = 4;
+  }
+}
+
 // ComputeLoglik's reduction (AugTree.cpp:296-325).  k_root_gather finishes the evaluation by itself when no site
-// rescaled anywhere (the usual case); only otherwise do the chain and the final kernel run.
-// Deferred (site-sharded) mode: stops after the gather; the chunk sums it produced — valid when this shard holds no
-// rescaled site and the exponent vector enters as zeros — are already on the host for dmpc_shard_finish.
+// rescaled anywhere; otherwise k_cert resolves the cross-locus chain by certificate and k_final adds the terms up
+// (both queued behind the gather already when the previous evaluation had rescaled sites); only when the certificate
+// does not hold do the literal chain kernel and a second final pass run.
+// Deferred (site-sharded) mode without peer mailboxes: stops after the gather; the chunk sums it produced — valid when
+// this shard holds no rescaled site and the exponent vector enters as zeros — are already on the host for
+// dmpc_shard_finish.
 int rootStage(dmpc_tree* t, double* ll) {
   int rc;
   const bool chain = t->quirk && t->R > 1;
@@ -624,12 +676,14 @@ int rootStage(dmpc_tree* t, double* ll) {
   if (t->deferred && chain) t->carryIsZero = true;   // launchGather zeroes the entry vector: optimistic pass
   for (int attempt = 0; attempt < 8; attempt++) {
     if (t->gatherPrelaunched) {
-      t->gatherPrelaunched = false;               // the replayed graph already ran the gather (and recorded ev[2])
+      t->gatherPrelaunched = false;               // the replayed graph already ran the root sequence (and recorded ev[2])
     } else {
-      if ((rc = launchGather(t, mode))) return rc;
+      if ((rc = launchRootSequence(t))) return rc;
       CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
     }
-    if ((rc = readStatus(t, t->deferred && !(t->rv.comm.world > 1), true))) return rc;
+    const bool sharded = t->rv.comm.world > 1;
+    const bool hostProtocol = t->deferred && !sharded;
+    if ((rc = readStatus(t, hostProtocol, true))) return rc;
     if (t->h_res->overflow > t->rv.Kcap) {
       int k = t->rv.Kcap;
       while (k < t->h_res->overflow) k *= 2;
@@ -639,36 +693,41 @@ int rootStage(dmpc_tree* t, double* ll) {
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
-    if (t->deferred && t->rv.comm.world > 1) {
-      // peer mailboxes attached: the gather has exchanged; if some rank holds a rescaled site, the chain (vector handed
-      // from rank to rank through the mailboxes) and the final kernel (second exchange) finish on the device too
-      if (t->h_res->xok == -1) { *ll = NAN; return DMPC_OK; }     // fused-clade violation: evaluate() re-runs in exact mode
-      if (t->h_res->xok == 0) {
-        if (chain && (rc = launchChain(t))) return rc;
-        if ((rc = launchFinal(t, mode, 2))) return rc;
+    t->evalTimePending = true;
+    if (hostProtocol) {
+      t->chunksOnHost = t->h_res->nact == 0;
+      *ll = NAN;
+      return DMPC_OK;
+    }
+    if (sharded && t->h_res->xok == -1) { *ll = NAN; return DMPC_OK; }     // fused-clade violation: evaluate() re-runs in exact mode
+    if (!sharded && !t->exact && t->h_res->violation) { *ll = NAN; return DMPC_OK; }   // same, single handle
+    // did any site (of any rank) rescale?  Sharded: the gather's exchange answered 1 when nobody did.
+    bool anyActive = sharded ? !(t->h_res->xok == 1 && t->h_res->cert == CERT_NONE) : t->h_res->nact != 0;
+    if (sharded && t->h_res->xok == 2) return fail(DMPC_ERR_CUDA, "peer exchange failed: a rank of the site-sharded run never answered");
+    if (!chain && anyActive) {
+      // textbook reduction / one rate category: every site folds its own exponent list
+      if ((rc = launchFinal(t, 0, sharded ? 2 : 1, false))) return rc;
+      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+      if ((rc = readStatus(t, false, false))) return rc;
+    } else if (anyActive) {
+      if (!t->seqPredicted) {                       // the gather ran alone: certificate + final now
+        if ((rc = launchCertFinal(t))) return rc;
+        t->pubExpected++;
+        CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+        if ((rc = readStatus(t, false, true))) return rc;
+      }
+      if (t->h_res->cert != CERT_OK) {              // no certificate: the literal chain (handed from rank to rank when sharded)
+        if ((rc = launchChain(t))) return rc;
+        if ((rc = launchFinal(t, 1, sharded ? 2 : 1, false))) return rc;
         CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
         if ((rc = readStatus(t, false, false))) return rc;
         t->carryIsZero = false;
       }
-      t->chunksOnHost = false;
-      t->evalTimePending = true;
-      if (t->h_res->xok != 1) return fail(DMPC_ERR_CUDA, "peer exchange failed: a rank of the site-sharded run never answered");
-      *ll = t->h_res->ll;
-      return DMPC_OK;
     }
-    if (t->deferred) {
-      t->chunksOnHost = t->h_res->nact == 0;
-      t->evalTimePending = true;
-      *ll = NAN;
-      return DMPC_OK;
-    }
-    if (t->h_res->nact != 0) {                      // some site rescaled: the real reduction
-      if (chain && (rc = launchChain(t))) return rc;
-      if ((rc = launchFinal(t, mode, 1))) return rc;
-      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
-      if ((rc = readStatus(t, false, false))) return rc;
-    }
-    t->evalTimePending = true;
+    noteChain(t, chain && anyActive);
+    t->predictActive = chain && anyActive;
+    t->chunksOnHost = false;
+    if (sharded && t->h_res->xok != 1) return fail(DMPC_ERR_CUDA, "peer exchange failed: a rank of the site-sharded run never answered");
     *ll = t->h_res->ll;
     return DMPC_OK;
   }
@@ -703,7 +762,8 @@ int checkHandle(dmpc_tree* t) {
 extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
-  o->device = -1; o->quirk_carry = 1; o->site_begin = 0; o->sites_total = 0; o->deferred = 0; o->fuse_tips = 15; o->fuse_exact = 0; o->comm = nullptr;
+  std::memset(o, 0, sizeof *o);
+  o->device = -1; o->quirk_carry = 1; o->fuse_tips = 15; o->chain_cert = 1;
 }
 
 const char* dmpc_last_error(void) { return g_err.c_str(); }
@@ -752,7 +812,9 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
   t->T = t->Sp / TILE;
-  t->nChunks = (numLoci + CHUNK - 1) / CHUNK;
+  t->nChunks = (numLoci + RCH - 1) / RCH;
+  t->rv.nChunks = t->nChunks;
+  t->rv.certOn = o.chain_cert != 0;
   // k_walk addresses partials by 32-bit element offsets (an element = one 32-byte 4-vector): fine up to 137 GB per slot
   t->ht.walkChains = (unsigned long long)t->nInt * t->R * t->Sp < (1ull << 32);
   t->quirk = o.quirk_carry != 0;
@@ -798,7 +860,8 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     want(&t->rv.carryIn, (size_t)RMAX);
     want(&t->rv.carryOut, (size_t)RMAX);
     want(&t->rv.sitell, (size_t)t->Sp);
-    want(&t->rv.chunk, (size_t)t->nChunks);
+    want(&t->rv.chunk, (size_t)t->T * CPT);
+    want(&t->rv.tileRec, (size_t)t->T * xrec(t->rv.RP));
     want(&t->rv.st, (size_t)1);
     setElistGeometry(t, 8);
     want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
@@ -1089,11 +1152,12 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       rb.mxo = (float*)dalloc((size_t)nb * Sp * 4);
       rb.carryOut = (float*)dalloc((size_t)nb * RMAX * 4);
       rb.sitell = (double*)dalloc((size_t)nb * Sp * 8);
-      rb.chunk = (double*)dalloc((size_t)nb * T * 8);
+      rb.chunk = (double*)dalloc((size_t)nb * T * CPT * 8);
+      rb.tileRec = (double*)dalloc((size_t)nb * T * xrec(t->rv.RP) * 8);
       rb.st = (DevStatus*)dalloc((size_t)nb * sizeof(DevStatus));
       bool okAlloc = true;
       for (void* q : tmp) okAlloc &= q != nullptr;
-      if (!okAlloc || tmp.size() != 22) { for (void* q : tmp) if (q) cudaFreeAsync(q, t->stream); return fail(DMPC_ERR_CUDA, "out of device memory for the proposal batch"); }
+      if (!okAlloc || tmp.size() != 23) { for (void* q : tmp) if (q) cudaFreeAsync(q, t->stream); return fail(DMPC_ERR_CUDA, "out of device memory for the proposal batch"); }
       CUDA_TRY(cudaMemcpyAsync(dT, pp.tasks.data(), nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
       if (nK) CUDA_TRY(cudaMemcpyAsync(dK, pp.tokens.data(), nK * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
       if (nL) CUDA_TRY(cudaMemcpyAsync(dL, pp.tipList.data(), nL * 4, cudaMemcpyHostToDevice, t->stream));
@@ -1110,14 +1174,32 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       }
       if (t->rv.RP == 4) k_root_gather<4, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
       else k_root_gather<8, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
-      if (chainMode && (rc = launchChain(t, &rb, nb))) return rc;
-      k_final<true><<<dim3((unsigned)t->nChunks, (unsigned)nb), CHUNK, 0, t->stream>>>(t->dv, rb, mode, 1, pv);
-      t->st.kernel_launches += 3;
-      CUDA_TRY(cudaGetLastError());
+      // root stage per proposal: quiet proposals were finished by the gather; the others take the certificate (mode 2) —
+      // and, if for some proposal it does not hold, the literal chain + final over the batch (mode 1) afterwards
       stat.resize(nb); invalid.resize(nb);
+      if (chainMode) {
+        if (t->rv.RP == 4) k_cert<4, true><<<nb, TILE, 0, t->stream>>>(t->dv, rb);
+        else k_cert<8, true><<<nb, TILE, 0, t->stream>>>(t->dv, rb);
+        k_final<true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, 2, 1, 0, pv);
+        t->st.kernel_launches += 4;
+      } else {
+        k_final<true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, 0, 1, 0, pv);
+        t->st.kernel_launches += 3;
+      }
+      CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaMemcpyAsync(stat.data(), rb.st, (size_t)nb * sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
       CUDA_TRY(cudaMemcpyAsync(invalid.data(), dI, (size_t)nb * 4, cudaMemcpyDeviceToHost, t->stream));
       CUDA_TRY(cudaStreamSynchronize(t->stream));    // also: the pageable host vectors above were the copy sources
+      bool needLiteral = false;
+      for (int i = 0; i < nb; i++) needLiteral |= chainMode && stat[i].nact != 0 && stat[i].cert == CERT_LITERAL && stat[i].overflow <= t->rv.Kcap;
+      if (needLiteral) {
+        if ((rc = launchChain(t, &rb, nb))) return rc;
+        k_final<true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, 1, 1, 0, pv);
+        t->st.kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(stat.data(), rb.st, (size_t)nb * sizeof(DevStatus), cudaMemcpyDeviceToHost, t->stream));
+        CUDA_TRY(cudaStreamSynchronize(t->stream));
+      }
       for (void* q : tmp) cudaFreeAsync(q, t->stream);
       for (int i = 0; i < nb; i++)
         if (!invalid[i] && stat[i].overflow <= t->rv.Kcap) {
@@ -1594,7 +1676,7 @@ int dmpc_shard_finish(dmpc_tree* t, double* chunkSums) {
     return DMPC_OK;
   }
   const bool chain = t->quirk && t->R > 1;
-  if ((rc = launchFinal(t, chain ? 1 : 0, 0))) return rc;
+  if ((rc = launchFinal(t, chain ? 1 : 0, 0, false))) return rc;
   CUDA_TRY(cudaMemcpyAsync(t->h_chunks, t->rv.chunk, (size_t)t->nChunks * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   std::memcpy(chunkSums, t->h_chunks, (size_t)t->nChunks * sizeof(double));
@@ -1617,7 +1699,9 @@ int dmpc_comm_create(int device, int rank, int world, int maxChunksPerRank, dmpc
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CUDA_TRY(cudaSetDevice(device));
   dmpc_comm* c = new dmpc_comm;
-  c->device = device; c->rank = rank; c->world = world; c->width = maxChunksPerRank + 2;
+  c->device = device; c->rank = rank; c->world = world; c->maxChunks = maxChunksPerRank;
+  // a message: header, chunk sums, and (when a site rescaled) one certificate record per 256-site tile
+  c->width = XHDR + maxChunksPerRank + ((maxChunksPerRank + CPT - 1) / CPT + 1) * XREC_MAX;
   if (cudaMalloc(&c->local, c->bytes() + 64) != cudaSuccess) { delete c; return fail(DMPC_ERR_CUDA, "cudaMalloc of the mailbox failed"); }
   CUDA_TRY(cudaMemset(c->local, 0, c->bytes() + 64));
   c->seq = (unsigned*)((char*)c->local + c->bytes());          // counter lives behind the mailbox proper
@@ -1654,13 +1738,13 @@ int dmpc_comm_destroy(dmpc_comm* c) {
 }
 
 double dmpc_reduce_chunks(const double* chunkSums, int n) {
-  volatile double acc[CHUNK];
-  for (int tI = 0; tI < CHUNK; tI++) {
+  volatile double acc[RED];
+  for (int tI = 0; tI < RED; tI++) {
     double a = 0.0;
-    for (int c = tI; c < n; c += CHUNK) { volatile double x = a + chunkSums[c]; a = x; }
+    for (int c = tI; c < n; c += RED) { volatile double x = a + chunkSums[c]; a = x; }
     acc[tI] = a;
   }
-  for (int d = CHUNK / 2; d > 0; d >>= 1)
+  for (int d = RED / 2; d > 0; d >>= 1)
     for (int tI = 0; tI < d; tI++) acc[tI] = acc[tI] + acc[tI + d];
   return acc[0];
 }

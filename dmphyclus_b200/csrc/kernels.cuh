@@ -27,8 +27,11 @@ constexpr int RMAX = 8;         // rate categories supported (the packaged data 
 constexpr int TILE = 256;       // sites per block of the pruning kernel = flag granularity
 constexpr int PT = 128;         // threads of a pruning block
 constexpr int SPT = TILE / PT;  // sites per pruning thread
-constexpr int CHUNK = 256;      // sites per deterministic reduction chunk
-static_assert(TILE == CHUNK, "k_root_gather finishes one reduction chunk per block");
+constexpr int RCH = 64;         // sites per deterministic reduction chunk: site blocks of a sharded run are multiples of it,
+                                // so that chunk boundaries — and the summation tree — do not depend on the number of ranks
+constexpr int CPT = TILE / RCH; // reduction chunks per site tile
+constexpr int RED = 256;        // strided accumulators of the final sum over the chunk sums (reduce_chunks)
+static_assert(TILE % RCH == 0 && RED == TILE, "the root kernels reduce CPT chunks per block with TILE threads");
 
 struct DevView {
   double* part[2];
@@ -52,28 +55,40 @@ struct DevStatus {
   int overflow;                 // longest per-site exponent list seen, when it exceeds the capacity
   int badCells;                 // alignment cells without any state
   int violation;                // a fused clade may have rescaled (k_prune, fast mode)
-  int nact;                     // site tiles holding a rescaled site (set by root_gather)
+  int nact;                     // site tiles holding a rescaled site (set by k_root_gather)
   unsigned ticket, ticket2;     // last-block detection of k_final / k_root_gather
   int xok;                      // site-sharded runs: 1 = the in-kernel peer exchange produced ll, 0 = host protocol needed,
                                 //   2 = a peer never answered, -1 = no exchange attempted
-  int pad;
-  int chainSites, chainRows;    // what k_chain walked: rescaled sites and (padded) exponent rows
-  unsigned pubSeq;              // number of times k_root_gather has published this block to the host mirror
-  int pad2;
+  int cert;                     // chain mode: CERT_* — how k_cert resolved the cross-locus exponent chain
+  int chainSites, chainRows;    // what the literal walker (k_chain, or k_cert's prefix) walked: rescaled sites and rows
+  unsigned pubSeq;              // number of times a root kernel has published this block to the host mirror
+  int certL0;                   // rescaled sites of the literal prefix (tiles 0 .. certTile)
+  int certRate;                 // the dominant rate category of the certified regime
+  int certTile;                 // last (global) site tile of the literal prefix; every later tile is certified
 };
-static_assert(sizeof(DevStatus) == 56, "status block = 14 words");
+static_assert(sizeof(DevStatus) == 64, "status block = 16 words");
+enum : int {
+  CERT_NONE = 0,                // k_cert has not run (or had nothing to do: no site rescaled anywhere)
+  CERT_OK = 1,                  // every tile behind the literal prefix is certified: k_final uses the closed form there
+  CERT_LITERAL = 2              // the certificate does not hold (or the prefix is too long): k_chain + k_final(mode 1)
+};
 
-// Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access): every rank
-// owns a mailbox in its HBM that all peers can store into.  Layout of a mailbox: unsigned flag[CW] (sequence number
-// of the last message of each sender), then double payload[2][CW][width] (double-buffered by sequence parity):
-// payload[.][sender] = { has-rescaled-site, nChunks, chunk sums... }.
+// Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access — or several shards
+// of one process): every rank owns a mailbox in its HBM that all peers can store into.  Layout of a mailbox: unsigned
+// flag[CW] (sequence number of the last message of each sender), then double payload[2][CW][width] (double-buffered by
+// sequence parity): payload[.][sender] = { flags, nChunks, nTiles, 0, chunk sums[nChunks], tile records[nTiles][XREC] }.
 constexpr int CW = 8;            // ranks
+constexpr int XHDR = 4;          // doubles in front of the chunk sums of a message
+enum : int { XF_ACTIVE = 1 };    // message flags
+// tile record of the chain certificate (see k_cert): nAct, ops, absSum, 0, S_r[RP], maxPre[RP][RP]
+__host__ __device__ constexpr int xrec(int RP) { return 4 + RP + RP * RP; }
+constexpr int XREC_MAX = xrec(RMAX);
 struct CommView {
   int world, rank, width;
   unsigned* seq;                // this rank's message counter (device memory)
   unsigned* flag[CW];           // flag arrays of every rank's mailbox (peer pointers)
   double* payload[CW];          // payload areas of every rank's mailbox (peer pointers)
-  unsigned* cflag[CW];          // same for the exponent-vector hand-off of the cross-locus chain:
+  unsigned* cflag[CW];          // same for the exponent-vector hand-off of the literal cross-locus chain:
   float* carry[CW];             //   carry[2][CW][RMAX], flag value = sequence number of the evaluation
 };
 
@@ -90,13 +105,17 @@ struct RootView {
   float* carryIn;               // [RMAX] exponent vector entering this shard (zeros on a single GPU)
   float* carryOut;              // [RMAX]
   double* sitell;               // [Sp] rateAveragedLogLiks
-  double* chunk;                // [nChunks] sums of CHUNK consecutive sites
+  double* chunk;                // [T * CPT] sums of RCH consecutive sites (the first nChunks are real)
+  double* tileRec;              // [T][xrec(RP)] per-tile records of the chain certificate (k_root_gather -> k_cert)
+  int nChunks;                  // ceil(S / RCH)
+  int publishAtGather;          // 1: the gather's last block publishes the status (nothing is queued behind it)
+  int certOn;                   // 0: k_cert always answers CERT_LITERAL (tests compare both paths)
   DevStatus* st;                // everything the host reads back after an evaluation, in one copy
-  DevStatus* hostSt;            // mapped pinned mirror (or null): the gather's last block stores the finished block there
+  DevStatus* hostSt;            // mapped pinned mirror (or null): the last root kernel stores the finished block there
                                 // and bumps its pubSeq, so that the host can pick the result up by polling instead of
                                 // queueing a copy and synchronising the stream
   int Kcap, RP, Q;              // Q = rows per chain staging chunk
-  CommView comm;                // comm.world > 1: k_root_gather also performs the cross-rank exchange
+  CommView comm;                // comm.world > 1: the root kernels also perform the cross-rank exchange
   int exactMode;                // the prune kernels ran in exact mode (a raised violation flag is then stale)
 };
 
@@ -124,7 +143,8 @@ __device__ __forceinline__ RootView forProposal(RootView rv, int b, int Sp, int 
   rv.mxo += (size_t)b * sp;
   rv.carryOut += (size_t)b * RMAX;
   rv.sitell += (size_t)b * sp;
-  rv.chunk += (size_t)b * T;
+  rv.chunk += (size_t)b * T * CPT;
+  rv.tileRec += (size_t)b * T * xrec(rv.RP);
   rv.st += b;
   rv.comm.world = 1;
   return rv;
@@ -641,26 +661,40 @@ __global__ void k_prepare_masks(const uint8_t* __restrict__ in, uint8_t* __restr
   mask[i] = m;
 }
 
-// sum of n chunk sums in a fixed order (CHUNK strided accumulators, then a binary tree); 256 threads
+// sum of n chunk sums in a fixed order (RED strided accumulators, then a binary tree); RED threads
 __device__ __forceinline__ double reduce_chunks_device(const double* chunk, int n, double* s_red) {
   double acc = 0.0;
-  for (int cI = threadIdx.x; cI < n; cI += CHUNK) acc = __dadd_rn(acc, chunk[cI]);
+  for (int cI = threadIdx.x; cI < n; cI += RED) acc = __dadd_rn(acc, chunk[cI]);
   s_red[threadIdx.x] = acc;
   __syncthreads();
-  for (int d = CHUNK / 2; d > 0; d >>= 1) {
+  for (int d = RED / 2; d > 0; d >>= 1) {
     if (threadIdx.x < d) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + d]);
     __syncthreads();
   }
   return s_red[0];
 }
 
-// The fused collective of a site-sharded run (called by the LAST block of k_root_gather / k_final, 256 threads).
-// This rank's {rescaled?, nChunks, chunk sums} go straight into every peer's mailbox over NVLink; once every peer's
-// message of the same sequence number has arrived, and no rank reports a rescaled site, each rank adds ALL chunk sums
-// in the fixed global order (the order of reduce_chunks_device over the concatenated list) and has the same
-// log-likelihood, bit for bit, as a single GPU would — without any host-side collective.
-// Returns 1 = ll written, 0 = some rank holds a rescaled site (the chain + final kernels must run), 2 = timeout.
-__device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bool quiet, double* s_red) {
+// per-site terms of one tile (TILE threads) -> its CPT chunk sums: a fixed binary tree inside each run of RCH sites
+__device__ __forceinline__ void tile_chunk_sums(double ll, double* s_red, double* chunkOut) {
+  const int tid = threadIdx.x;
+  s_red[tid] = ll;
+  __syncthreads();
+  for (int d = RCH / 2; d > 0; d >>= 1) {
+    if ((tid & (RCH - 1)) < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
+    __syncthreads();
+  }
+  if ((tid & (RCH - 1)) == 0) chunkOut[tid / RCH] = s_red[tid];
+}
+
+// The fused collective of a site-sharded run (called by the LAST block of k_root_gather / k_final, TILE threads).
+// This rank's {flags, nChunks, nTiles, chunk sums, tile records} go straight into every peer's mailbox over NVLink;
+// once every peer's message of the same sequence number has arrived, and no rank reports a rescaled site, each rank adds
+// ALL chunk sums in the fixed global order (the order of reduce_chunks_device over the concatenated list) and has the
+// same log-likelihood, bit for bit, as a single GPU would — without any host-side collective.  The tile records
+// (recs != nullptr: nTiles x XR doubles) are what k_cert needs from every rank when some site did rescale.
+// Returns 1 = ll written, 0 = some rank holds a rescaled site (k_cert + k_final must run), 2 = timeout.
+__device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bool quiet, double* s_red, const double* recs,
+                                                 int nTiles, int XR) {
   __shared__ unsigned s_seq;
   __shared__ int s_bad;
   const CommView& cm = rv.comm;
@@ -668,10 +702,12 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
   if (tid == 0) { s_seq = *cm.seq + 1; s_bad = 0; }
   __syncthreads();
   const unsigned seq = s_seq;
-  const int buf = seq & 1, msg = 2 + nCh;
-  for (int idx = tid; idx < cm.world * msg; idx += CHUNK) {
+  const int nRec = recs ? nTiles * XR : 0;
+  const int buf = seq & 1, msg = XHDR + nCh + nRec;
+  for (int idx = tid; idx < cm.world * msg; idx += TILE) {
     const int p = idx / msg, j = idx - p * msg;
-    const double val = j == 0 ? (quiet ? 0.0 : 1.0) : j == 1 ? (double)nCh : rv.chunk[j - 2];
+    const double val = j == 0 ? (quiet ? 0.0 : (double)XF_ACTIVE) : j == 1 ? (double)nCh : j == 2 ? (double)(recs ? nTiles : 0) : j == 3 ? 0.0
+                       : j < XHDR + nCh ? rv.chunk[j - XHDR] : recs[j - XHDR - nCh];
     *((volatile double*)cm.payload[p] + ((size_t)buf * CW + cm.rank) * cm.width + j) = val;
   }
   __threadfence_system();
@@ -682,7 +718,7 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
     const long long t0 = clock64();
     while ((int)(*mine - seq) < 0) {
       if (clock64() - t0 > 40000000000LL) { s_bad = 1; break; }            // ~20 s: a peer died; do not hang the GPU
-      __nanosleep(200);
+      __nanosleep(100);
     }
   }
   __syncthreads();
@@ -696,12 +732,12 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
     int base = 0;                                                          // global index of rank p's first chunk
     for (int p = 0; p < cm.world; p++) {
       const int cnt = (int)in[(size_t)p * cm.width + 1];
-      for (int c = ((tid - base) % CHUNK + CHUNK) % CHUNK; c < cnt; c += CHUNK) acc = __dadd_rn(acc, in[(size_t)p * cm.width + 2 + c]);
+      for (int c = ((tid - base) % RED + RED) % RED; c < cnt; c += RED) acc = __dadd_rn(acc, in[(size_t)p * cm.width + XHDR + c]);
       base += cnt;
     }
     s_red[tid] = acc;
     __syncthreads();
-    for (int d = CHUNK / 2; d > 0; d >>= 1) {
+    for (int d = RED / 2; d > 0; d >>= 1) {
       if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
       __syncthreads();
     }
@@ -742,6 +778,8 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   __shared__ double s_red[TILE];
   __shared__ bool s_last;
   __shared__ int s_wcnt[TILE / 32];
+  __shared__ double s_x[TILE / 32][RP + 3];
+  __shared__ double s_y[TILE / 32][RP * RP];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int site = tile * TILE + tid;
   const bool valid = site < v.S;
@@ -763,8 +801,9 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       }
     }
   int k[RP];
+  double sd[RP];                                   // this site's exponent sums, one per rate (for the certificate only)
 #pragma unroll
-  for (int r = 0; r < RP; r++) k[r] = 0;
+  for (int r = 0; r < RP; r++) { k[r] = 0; sd[r] = 0.0; }
   float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
   const size_t fstride = (size_t)v.T * v.nFlag;                 // between the flag planes of consecutive rates
   const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nFlag : nullptr;
@@ -789,6 +828,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
           if (e[j][r] != 0.0f) {
             if (k[r] < rv.Kcap && valid) myList[(size_t)k[r] * RP + r] = e[j][r];
             k[r]++;
+            sd[r] += (double)e[j][r];
           }
     }
   };
@@ -918,14 +958,66 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
     ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)R), (double)0.0f);
     rv.sitell[site] = ll;
   }
-  s_red[tid] = ll;
-  __syncthreads();
-  for (int d = TILE / 2; d > 0; d >>= 1) {
-    if (tid < d) s_red[tid] = __dadd_rn(s_red[tid], s_red[tid + d]);
-    __syncthreads();
+  tile_chunk_sums(ll, s_red, rv.chunk + (size_t)tile * CPT);
+  if (mode == 1) {
+    // The tile's record for the chain certificate (k_cert): with E_r = running sums of the sites' exponent sums,
+    //   S_r = the tile's total, maxPre[d][r] = max over the tile's sites (and 0) of (E_r - E_d) relative to the tile's
+    //   entry, nAct / ops / absSum = what bounds the fp32 rounding the literal chain would commit inside the tile.
+    constexpr int XR = xrec(RP);
+    double* const rec = rv.tileRec + (size_t)tile * XR;
+    if (!anyActive) {
+      for (int i = tid; i < XR; i += TILE) rec[i] = 0.0;
+    } else {
+      const bool actS = valid && kmax > 0;
+      double pre[RP], ab = 0.0;
+#pragma unroll
+      for (int r = 0; r < RP; r++) { pre[r] = (actS && r < R) ? sd[r] : 0.0; ab += fabs(pre[r]); }
+      double ops = actS ? (double)(kmax + 1) : 0.0, na = actS ? 1.0 : 0.0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int r = 0; r < RP; r++) { const double y = __shfl_up_sync(0xffffffffu, pre[r], d); if (lane >= d) pre[r] += y; }
+        ab += __shfl_xor_sync(0xffffffffu, ab, d); ops += __shfl_xor_sync(0xffffffffu, ops, d); na += __shfl_xor_sync(0xffffffffu, na, d);
+      }
+      if (lane == 31) {
+#pragma unroll
+        for (int r = 0; r < RP; r++) s_x[wid][r] = pre[r];
+        s_x[wid][RP] = ab; s_x[wid][RP + 1] = ops; s_x[wid][RP + 2] = na;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < TILE / 32; w++)
+        if (w < wid) {
+#pragma unroll
+          for (int r = 0; r < RP; r++) pre[r] += s_x[w][r];
+        }
+#pragma unroll
+      for (int d = 0; d < RP; d++)
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+          double mx = (d < R && r < R && d != r) ? fmax(0.0, pre[r] - pre[d]) : 0.0;
+#pragma unroll
+          for (int q = 16; q > 0; q >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, q));
+          if (lane == 0) s_y[wid][d * RP + r] = mx;
+        }
+      __syncthreads();
+      if (tid < RP * RP) {
+        double mx = 0.0;
+#pragma unroll
+        for (int w = 0; w < TILE / 32; w++) mx = fmax(mx, s_y[w][tid]);
+        rec[4 + RP + tid] = mx;
+      } else if (tid < RP * RP + RP + 3) {
+        const int j = tid - RP * RP;                 // 0..RP-1: S_r; RP: absSum; RP+1: ops; RP+2: nAct
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < TILE / 32; w++) acc += s_x[w][j];
+        if (j < RP) rec[4 + j] = acc; else if (j == RP) rec[2] = acc; else if (j == RP + 1) rec[1] = acc; else rec[0] = acc;
+      } else if (tid == RP * RP + RP + 3) {
+        rec[3] = 0.0;
+      }
+    }
   }
   if (tid == 0) {
-    rv.chunk[tile] = s_red[0];
     if (anyActive) atomicAdd(&rv.st->nact, 1);
     __threadfence();
     s_last = atomicAdd(&rv.st->ticket2, 1u) == gridDim.x - 1;
@@ -936,22 +1028,24 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
     const bool quiet = *(volatile int*)&rv.st->nact == 0;
     const CommView& cm = rv.comm;
     const bool retry = *(volatile int*)&rv.st->overflow > rv.Kcap || (*(volatile int*)&rv.st->violation != 0 && !rv.exactMode);
+    const bool pub = !BATCH && rv.publishAtGather;
+    if (tid == 0) rv.st->cert = CERT_NONE;
     if (cm.world > 1) {
       // skipped when the host is going to re-run this gather (list overflow, fused-clade violation), so that every
       // rank sends exactly one message per exchange
       if (retry) {
-        if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
+        if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
         return;
       }
-      const int res = exchangeAndReduce(rv, gridDim.x, quiet, s_red);
-      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
+      const int res = exchangeAndReduce(rv, rv.nChunks, quiet, s_red, (mode == 1 && !quiet) ? rv.tileRec : nullptr, gridDim.x, xrec(RP));
+      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
       return;
     }
     if (quiet) {
-      const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
+      const double tot = reduce_chunks_device(rv.chunk, rv.nChunks, s_red);
       if (tid == 0) rv.st->ll = tot;
     }
-    if (tid == 0) { rv.st->ticket2 = 0; if (!BATCH) publishStatus(rv); }
+    if (tid == 0) { rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
   }
 }
 
@@ -1168,77 +1262,337 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv0) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4c final: rateAveragedLogLiks (AugTree.cpp:317-323) per site, then a deterministic sum: fixed tree inside
-// each 256-site chunk, chunk sums combined by reduce_chunks order (identical on host for the multi-GPU path).
-// mode 1: exponent vectors come from the chain; mode 0: each site folds its own list from zero (numRateCats == 1,
-// where the carry is always exactly zero, or the textbook reduction).
+// K4b' cert: the chain WITHOUT walking it, wherever that can be proven exact.
+//
+// The literal chain (k_chain; AugTree.cpp:306-323) keeps an fp32 vector c, adds every site's exponents to it (vertex
+// order), subtracts its maximum m, and the site's term is log(mean_r(rootdot_r * expf(c_r))) + m.  In exact arithmetic
+// c_r = E_r - max_q E_q with E the running sums of the sites' exponent sums.  Rescale exponents are ~ -345 each and
+// the rate categories do not rescale equally often, so after a few rescaled sites ONE category d leads by far more
+// than 104 — and from then on expf(c_r) == 0.0f exactly for every r != d, c_d == 0.0f exactly, and the term of a site
+// is log(rootdot_d / R) + (fp32 sum, from zero, of that site's own category-d exponents): no history at all.
+// The certificate proves, tile by tile, that the literal fp32 chain is in that regime:
+//   * since the maximum entry of c is exactly 0, every c_r equals a DIFFERENCE c_r - c_d*, and differences only pick up
+//     the roundings of the additions and subtractions themselves — (2K+1) * 2^-24 * |value| per site with K rows —
+//     which add up (no amplification).  B(t) = kappa * sum_{t' <= t} 2^-22 * ops(t') * (gap at entry + abs sums + 1)
+//     bounds |c_r - (E_r - E_d)| anywhere up to the end of tile t (kappa = exp(2^-22 * total ops) covers B feeding
+//     back into the magnitudes);
+//   * tile t is certified for d when for every r != d:  (E_r - E_d at entry) + maxPre[d][r](t) + B(t) < -128.
+// All tiles behind the last uncertified one take the closed form in k_final; tiles 0 .. certTile (always including
+// tile 0: the chain starts from zeros) are walked literally here, by one thread, from rows staged in shared memory —
+// typically a few dozen sites.  If the regime never establishes itself (two categories neck and neck, tiny trees) or
+// the prefix is long, the answer is CERT_LITERAL and the host runs k_chain as before.  One block per evaluation
+// (BATCH: per proposal).  In a site-sharded run every rank holds every rank's tile records (the gather's exchange) and
+// reaches the same verdict; the literal prefix must then lie inside rank 0's block.
+constexpr int CERT_ROWCAP = 1024;    // rows of one literal tile staged in shared memory (more: read from global memory)
+constexpr int CERT_MAXLIT = 2048;    // rescaled sites the literal prefix may hold
+
+template <int RP, bool BATCH>
+__global__ void __launch_bounds__(TILE) k_cert(DevView v, RootView rv0) {
+  const RootView rv = BATCH ? forProposal(rv0, blockIdx.x, v.Sp, v.T) : rv0;
+  constexpr int XR = xrec(RP);
+  constexpr int V = RP / 4;
+  __shared__ double s_w[TILE / 32][RP + 2];
+  __shared__ double s_tot[RP + 2];
+  __shared__ long long s_key[TILE / 32];
+  __shared__ int s_base[CW + 1];
+  __shared__ const volatile double* s_rec[CW];
+  __shared__ float4 s_rows[CERT_ROWCAP * V];
+  __shared__ int s_cnt[TILE], s_site[TILE];
+  __shared__ int s_scan[2][TILE / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, R = v.R;
+  const CommView& cm = rv.comm;
+  const bool sharded = cm.world > 1;
+  DevStatus* const st = rv.st;
+  const bool retry = st->overflow > rv.Kcap || (st->violation != 0 && !rv.exactMode);
+  if (retry || (!sharded && st->nact == 0) || (sharded && st->xok != 0)) return;     // cert stays CERT_NONE
+  if (tid == 0) {
+    if (sharded) {
+      const unsigned seq = *cm.seq;                                   // the gather's exchange
+      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)(seq & 1) * CW * cm.width;
+      int b = 0;
+      for (int p = 0; p < cm.world; p++) {
+        const volatile double* m = in + (size_t)p * cm.width;
+        const int nT = (int)m[2];
+        s_base[p] = b;
+        // a quiet rank sends no records; its tile count is then unknown here, and irrelevant: zero records change nothing
+        s_rec[p] = nT > 0 ? m + XHDR + (int)m[1] : nullptr;
+        b += nT;
+      }
+      for (int p = cm.world; p <= CW; p++) s_base[p] = b;
+    } else {
+      s_base[0] = 0;
+      for (int p = 1; p <= CW; p++) s_base[p] = v.T;
+      s_rec[0] = rv.tileRec;
+    }
+  }
+  __syncthreads();
+  const int nRanks = sharded ? cm.world : 1;
+  const int Ttot = s_base[nRanks];
+  auto recOf = [&](int g) -> const volatile double* {
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < CW; q++) if (q < nRanks && g >= s_base[q]) p = q;
+    return s_rec[p] + (size_t)(g - s_base[p]) * XR;
+  };
+  // block-wide sums / scans of RP + 2 doubles at once (one barrier pair)
+  auto blockTotals = [&](double (&x)[RP + 2]) {
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1)
+#pragma unroll
+      for (int i = 0; i < RP + 2; i++) x[i] += __shfl_xor_sync(0xffffffffu, x[i], q);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < RP + 2; i++) s_w[wid][i] = x[i];
+    }
+    __syncthreads();
+    if (tid < RP + 2) { double a = 0.0; for (int w = 0; w < TILE / 32; w++) a += s_w[w][tid]; s_tot[tid] = a; }
+    __syncthreads();
+  };
+  // pass 1: totals -> the dominant category and kappa
+  {
+    double x[RP + 2];
+#pragma unroll
+    for (int i = 0; i < RP + 2; i++) x[i] = 0.0;
+    for (int g = tid; g < Ttot; g += TILE) {
+      const volatile double* rec = recOf(g);
+#pragma unroll
+      for (int r = 0; r < RP; r++) x[r] += rec[4 + r];
+      x[RP] += rec[1];
+    }
+    blockTotals(x);
+  }
+  int dom = 0;
+  for (int r = 1; r < R; r++) if (s_tot[r] > s_tot[dom]) dom = r;
+  const double kappa = exp(s_tot[RP] * 0x1p-22) * (1.0 + 1e-9);
+  __syncthreads();
+  // pass 2: per tile, entry sums (exclusive scan), the rounding bound (inclusive scan), the verdict
+  double carry[RP + 2];                           // running: E_r, sum of u*g, active sites
+#pragma unroll
+  for (int i = 0; i < RP + 2; i++) carry[i] = 0.0;
+  long long best = -1;                            // (last uncertified tile) << 32 | active sites up to and including it
+  for (int base = 0; base < Ttot; base += TILE) {
+    const int g = base + tid;
+    const bool in = g < Ttot;
+    const volatile double* rec = in ? recOf(g) : nullptr;
+    double Sr[RP], ops = 0.0, ab = 0.0, na = 0.0;
+#pragma unroll
+    for (int r = 0; r < RP; r++) Sr[r] = in ? rec[4 + r] : 0.0;
+    if (in) { na = rec[0]; ops = rec[1]; ab = rec[2]; }
+    // inclusive scans of S_r and nAct
+    double incl[RP + 1];
+#pragma unroll
+    for (int r = 0; r < RP; r++) incl[r] = Sr[r];
+    incl[RP] = na;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+      for (int i = 0; i < RP + 1; i++) { const double y = __shfl_up_sync(0xffffffffu, incl[i], d); if (lane >= d) incl[i] += y; }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < RP + 1; i++) s_w[wid][i] = incl[i];
+    }
+    __syncthreads();
+    double tot[RP + 1];
+#pragma unroll
+    for (int i = 0; i < RP + 1; i++) {
+      tot[i] = 0.0;
+#pragma unroll
+      for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][i]; if (w < wid) incl[i] += q; tot[i] += q; }
+    }
+    __syncthreads();
+    double entry[RP], emax = -1e300, emin = 1e300;
+#pragma unroll
+    for (int r = 0; r < RP; r++)
+      if (r < R) { entry[r] = carry[r] + incl[r] - Sr[r]; emax = fmax(emax, entry[r]); emin = fmin(emin, entry[r]); }
+    double ug = in ? 0x1p-22 * ops * ((emax - emin) + ab + 1.0) : 0.0;
+    double ugi = ug;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, ugi, d); if (lane >= d) ugi += y; }
+    if (lane == 31) s_w[wid][RP + 1] = ugi;
+    __syncthreads();
+    double ugTot = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][RP + 1]; if (w < wid) ugi += q; ugTot += q; }
+    const double B = kappa * (carry[RP] + ugi);
+    bool bad = false;
+    if (in) {
+#pragma unroll
+      for (int r = 0; r < RP; r++)
+        if (r < R && r != dom) bad |= !(entry[r] - entry[dom] + rec[4 + RP + dom * RP + r] + B < -128.0);
+    }
+    long long key = bad ? (((long long)g << 32) | (long long)(unsigned)(carry[RP + 1] + incl[RP])) : -1;
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, key, q); key = o > key ? o : key; }
+    if (lane == 0) s_key[wid] = key;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) best = s_key[w] > best ? s_key[w] : best;
+#pragma unroll
+    for (int r = 0; r < RP; r++) carry[r] += tot[r];
+    carry[RP] += ugTot;
+    carry[RP + 1] += tot[RP];
+    __syncthreads();
+  }
+  const int tb = (int)(best >> 32), L0 = (int)(best & 0xffffffffLL);
+  const bool ok = rv.certOn && best >= 0 && L0 <= CERT_MAXLIT && tb < s_base[1];
+  const int myBase = sharded ? s_base[cm.rank] : 0;
+  if (tid == 0) {
+    st->cert = ok ? CERT_OK : CERT_LITERAL;
+    st->certRate = dom;
+    st->certTile = tb - myBase;                   // local tile index: every local tile above it is certified
+    st->certL0 = L0;
+    if (ok) { st->chainSites = 0; st->chainRows = 0; }
+  }
+  if (!ok || (sharded && cm.rank != 0)) return;
+
+  // the literal prefix: tiles 0 .. tb of this (first) block of sites, one tile per pass
+  float c[RP];
+#pragma unroll
+  for (int r = 0; r < RP; r++) c[r] = 0.0f;
+  int actBase = 0, rowsWalked = 0;
+  for (int lt = 0; lt <= tb && lt < v.T; lt++) {
+    const int s = lt * TILE + tid;
+    const int km = s < v.S ? min(rv.kmax[s], rv.Kcap) : 0;
+    const int actv = km > 0;
+    int ic = actv, ir = km;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tc = __shfl_up_sync(0xffffffffu, ic, d), tr = __shfl_up_sync(0xffffffffu, ir, d);
+      if (lane >= d) { ic += tc; ir += tr; }
+    }
+    if (lane == 31) { s_scan[0][wid] = ic; s_scan[1][wid] = ir; }
+    __syncthreads();
+    int nA = 0, nR = 0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) { if (w < wid) { ic += s_scan[0][w]; ir += s_scan[1][w]; } nA += s_scan[0][w]; nR += s_scan[1][w]; }
+    if (s < v.S) rv.posIncl[s] = actBase + ic;
+    const bool staged = nR <= CERT_ROWCAP;
+    if (actv) {
+      s_cnt[ic - 1] = km; s_site[ic - 1] = s;
+      if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(rv.elist + (size_t)s * rv.Kcap * RP);
+        for (int j = 0; j < km * V; j++) s_rows[(size_t)(ir - km) * V + j] = src[j];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int q = 0;
+      for (int i = 0; i < nA; i++) {
+        const int cnt = s_cnt[i];
+        const float* rows = staged ? reinterpret_cast<const float*>(s_rows) + (size_t)q * RP : rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
+        for (int j = 0; j < cnt; j++)
+#pragma unroll
+          for (int r = 0; r < RP; r++) if (r < R) c[r] = __fadd_rn(c[r], rows[j * RP + r]);
+        q += cnt;
+        float m = c[0];
+#pragma unroll
+        for (int r = 1; r < RP; r++) if (r < R) m = fmaxf(m, c[r]);
+        float* co = rv.cout + (size_t)(actBase + i) * RP;
+#pragma unroll
+        for (int r = 0; r < RP; r++) if (r < R) { c[r] = __fsub_rn(c[r], m); co[r] = c[r]; }
+        rv.mxo[actBase + i] = m;
+      }
+    }
+    actBase += nA; rowsWalked += nR;
+    __syncthreads();
+  }
+  if (tid == 0) { st->chainSites = actBase; st->chainRows = rowsWalked; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c final: rateAveragedLogLiks (AugTree.cpp:317-323) per site, then a deterministic sum: a fixed tree inside each
+// RCH-site chunk, chunk sums combined in reduce_chunks order (identical on the host for the multi-GPU path).
+// mode 0: each site folds its own list from zero (numRateCats == 1, where the carry is always exactly zero, or the
+//         textbook reduction);
+// mode 1: exponent vectors come from the literal chain (k_chain);
+// mode 2: queued behind k_root_gather + k_cert without a host round trip: nothing to do unless the verdict is CERT_OK;
+//         then the tiles of the literal prefix read k_cert's vectors (as in mode 1) and every later tile takes the closed
+//         form of the certified regime (see k_cert).
+// publish: the last thread standing stores the status block into the host mirror (the host polls for it).
 template <bool BATCH>
-__global__ void __launch_bounds__(CHUNK) k_final(DevView v, RootView rv0, int mode, int reduceAll, PathView pv) {
+__global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mode, int reduceAll, int publish, PathView pv) {
   const int pb = BATCH ? blockIdx.y : 0;
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   const double* const rootdot = BATCH ? pv.rootdot + (size_t)pb * v.R * v.Sp : rv.rootdot;
-  __shared__ double s_red[CHUNK];
+  __shared__ double s_red[TILE];
   __shared__ bool s_last;
-  const int s = blockIdx.x * CHUNK + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x * TILE + tid;
+  int dom = -1;                                      // >= 0: this tile takes the closed form with that category
+  if (mode == 2) {
+    const bool retry = rv.st->overflow > rv.Kcap || (rv.st->violation != 0 && !rv.exactMode);
+    if (retry || rv.st->cert != CERT_OK) {
+      if (publish && !BATCH && blockIdx.x == 0 && tid == 0) publishStatus(rv);
+      return;
+    }
+    if ((int)blockIdx.x > rv.st->certTile) dom = rv.st->certRate;
+  }
   double ll = 0.0;
   if (s < v.S) {
     float ev[RMAX];
     float mx = 0.0f;
     const int km = min(rv.kmax[s], rv.Kcap);
-    if (mode == 1 && rv.st->nact == 0) {            // the chain kernel returned early: no site rescaled
+    double w[RMAX];
+    if (dom >= 0) {
+      // certified: expf(c_r) == 0 for r != dom, c_dom == 0 when the site begins, so its maximum is the fp32 sum of its own
+      // category-dom exponents (zero padding rows add +0.0f)
+      for (int j = 0; j < km; j++) mx = __fadd_rn(mx, rv.elist[((size_t)s * rv.Kcap + j) * rv.RP + dom]);
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = rv.carryIn[r];
-    } else if (mode == 1) {
-      const int p = rv.posIncl[s];
-#pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = p ? rv.cout[(size_t)(p - 1) * rv.RP + r] : rv.carryIn[r];
-      if (km > 0) mx = rv.mxo[p - 1];
+      for (int r = 0; r < RMAX; r++) w[r] = r == dom ? 1.0 : 0.0;
     } else {
+      if (mode >= 1 && rv.st->nact == 0) {          // the chain kernel returned early: no site rescaled
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) ev[r] = 0.0f;
-      for (int j = 0; j < km; j++)
+        for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = rv.carryIn[r];
+      } else if (mode >= 1) {
+        const int p = rv.posIncl[s];
 #pragma unroll
-        for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = __fadd_rn(ev[r], rv.elist[((size_t)s * rv.Kcap + j) * rv.RP + r]);
-      mx = ev[0];
+        for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = p ? rv.cout[(size_t)(p - 1) * rv.RP + r] : rv.carryIn[r];
+        if (km > 0) mx = rv.mxo[p - 1];
+      } else {
 #pragma unroll
-      for (int r = 1; r < RMAX; r++) if (r < v.R) mx = fmaxf(mx, ev[r]);
+        for (int r = 0; r < RMAX; r++) ev[r] = 0.0f;
+        for (int j = 0; j < km; j++)
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = __fsub_rn(ev[r], mx);
+          for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = __fadd_rn(ev[r], rv.elist[((size_t)s * rv.Kcap + j) * rv.RP + r]);
+        mx = ev[0];
+#pragma unroll
+        for (int r = 1; r < RMAX; r++) if (r < v.R) mx = fmaxf(mx, ev[r]);
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) if (r < v.R) ev[r] = __fsub_rn(ev[r], mx);
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) if (r < v.R) w[r] = (double)(float)exp((double)ev[r]);   // correctly rounded expf
     }
     // mean(likProp % exp(ev)): expf on the fp32 vector, promoted to double; two interleaved accumulators
     double a1 = 0.0, a2 = 0.0;
 #pragma unroll
     for (int r = 0; r < RMAX; r++)
       if (r < v.R) {
-        const double w = (double)(float)exp((double)ev[r]);   // correctly rounded expf
-        const double x = __dmul_rn(rootdot[(size_t)r * v.Sp + s], w);
+        const double x = __dmul_rn(rootdot[(size_t)r * v.Sp + s], w[r]);
         if (r & 1) a2 = __dadd_rn(a2, x); else a1 = __dadd_rn(a1, x);
       }
     ll = __dadd_rn(log(__dadd_rn(a1, a2) / (double)v.R), (double)mx);
     rv.sitell[s] = ll;
   }
-  s_red[threadIdx.x] = ll;
-  __syncthreads();
-  for (int d = CHUNK / 2; d > 0; d >>= 1) {
-    if (threadIdx.x < d) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + d]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    rv.chunk[blockIdx.x] = s_red[0];
+  tile_chunk_sums(ll, s_red, rv.chunk + (size_t)blockIdx.x * CPT);
+  if (tid == 0) {
     __threadfence();
     s_last = atomicAdd(&rv.st->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && reduceAll == 2) {                   // site-sharded: second exchange, every shard is final now
-    __threadfence();
-    const int res = exchangeAndReduce(rv, gridDim.x, true, s_red);
-    if (threadIdx.x == 0) { rv.st->xok = res; rv.st->ticket = 0; }
-  } else if (s_last && reduceAll) {
-    __threadfence();
-    const double tot = reduce_chunks_device(rv.chunk, gridDim.x, s_red);
-    if (threadIdx.x == 0) { rv.st->ll = tot; rv.st->ticket = 0; }
-  } else if (s_last && threadIdx.x == 0) {
+  if (!s_last) return;
+  __threadfence();
+  if (reduceAll == 2) {                             // site-sharded: second exchange, every shard is final now
+    const int res = exchangeAndReduce(rv, rv.nChunks, true, s_red, nullptr, 0, 0);
+    if (tid == 0) rv.st->xok = res;
+  } else if (reduceAll) {
+    const double tot = reduce_chunks_device(rv.chunk, rv.nChunks, s_red);
+    if (tid == 0) rv.st->ll = tot;
+  }
+  if (tid == 0) {
     rv.st->ticket = 0;
+    __threadfence();
+    if (publish && !BATCH) publishStatus(rv);
   }
 }
 

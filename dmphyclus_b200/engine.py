@@ -26,7 +26,8 @@ class DmpcError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("quirk_carry", C.c_int), ("site_begin", C.c_int), ("sites_total", C.c_int),
-                ("fuse_tips", C.c_int), ("fuse_exact", C.c_int), ("comm", C.c_void_p), ("deferred", C.c_int)]
+                ("fuse_tips", C.c_int), ("fuse_exact", C.c_int), ("comm", C.c_void_p), ("deferred", C.c_int),
+                ("chain_cert", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * 8)]
 
 
 class Stats(C.Structure):
@@ -41,7 +42,8 @@ class Stats(C.Structure):
                 ("create_setup_us", C.c_double), ("create_upload_ms", C.c_double),
                 ("last_chain_sites", C.c_int), ("last_chain_rows", C.c_int), ("chain_group", C.c_int),
                 ("plan_cache_hits", C.c_ulonglong), ("graph_replays", C.c_ulonglong),
-                ("last_walk_steps", C.c_int), ("last_materialised", C.c_int)]
+                ("last_walk_steps", C.c_int), ("last_materialised", C.c_int),
+                ("last_cert", C.c_int), ("last_cert_rate", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -129,7 +131,7 @@ class Engine:
     name = "cuda"
 
     def __init__(self, device: int = -1, quirk_carry: bool = True, site_begin: int = 0, sites_total: int = 0,
-                 fuse_tips: int | None = None, fuse_exact: bool = False):
+                 fuse_tips: int | None = None, fuse_exact: bool = False, chain_cert: bool = True):
         self.lib = load_library()
         self.opts = Options()
         self.lib.dmpc_default_options(C.byref(self.opts))
@@ -140,6 +142,7 @@ class Engine:
         if fuse_tips is not None:
             self.opts.fuse_tips = int(fuse_tips)
         self.opts.fuse_exact = int(fuse_exact)
+        self.opts.chain_cert = int(chain_cert)
         self._shape = {}
         self._mcache = {}
         self._ecache = {}

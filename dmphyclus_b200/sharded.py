@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 
-CHUNK = 256   # sites per deterministic reduction chunk (dmphyclus_b200/csrc/kernels.cuh)
+CHUNK = 64    # sites per deterministic reduction chunk (RCH in dmphyclus_b200/csrc/kernels.cuh)
 
 
 def shard_range(sites_total: int, rank: int, world: int) -> tuple[int, int]:

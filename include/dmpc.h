@@ -59,6 +59,11 @@ typedef struct dmpc_options {
                         through NVLink peer mailboxes inside the reduction kernel */
   int deferred;      /* 1: start in deferred-reduction mode (see dmpc_set_deferred): dmpc_loglik_create prunes and
                         gathers but leaves the root reduction to dmpc_shard_chain / dmpc_shard_finish */
+  int chain_cert;    /* 1 (default): where it can be PROVEN that the reference's sequential fp32 exponent chain is in its
+                        one-dominant-category regime, the per-site terms are computed in parallel from the closed form
+                        (bit-identical); 0: always walk the chain literally (tests compare the two) */
+  int n_devices;     /* > 1: single-process multi-GPU — the handle shards its sites over devices[0 .. n_devices) */
+  int devices[8];    /*      and every entry point fans out to the shards (the R shim reads DMPC_DEVICES) */
 } dmpc_options;
 void dmpc_default_options(dmpc_options* o);
 
@@ -160,6 +165,9 @@ typedef struct dmpc_stats {
   int last_walk_steps;      /* vertices of the last evaluation's trailing chain, evaluated by the walk kernel with the
                                running partial in registers (0: no chain of at least 4 single-task levels) */
   int last_materialised;    /* fused-size clades hanging off that chain, evaluated once as stored tasks beforehand */
+  int last_cert;            /* how the cross-locus exponent chain of the last evaluation was resolved: 0 = no site
+                               rescaled, 1 = by certificate (last_chain_sites = its literal prefix), 2 = walked literally */
+  int last_cert_rate;       /* the dominant rate category of the certified regime (-1: none) */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which

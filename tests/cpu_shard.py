@@ -1,9 +1,9 @@
 """CPU stand-in for one rank's evaluator in the site-sharded path: the oracle prunes this rank's site block, and the
-shard protocol of include/dmpc.h (chain from a carry, per-256-site chunk sums) is restated in numpy from
+shard protocol of include/dmpc.h (chain from a carry, per-64-site chunk sums) is restated in numpy from
 AugTree.cpp:296-323.  Lets the rank-to-rank exchange of dmphyclus_b200/sharded.py run under gloo without a GPU."""
 import numpy as np
 
-CHUNK = 256
+CHUNK = 64
 
 
 class OracleShard:

@@ -420,9 +420,12 @@ def test_rcpp_shim_end_to_end(packaged, oracle, fast_masks, monkeypatch):
         compare_to_golden(run_script(shim, p), run_script(oracle, p), ll_tol=TOL, exact_partials=True)
 
 
-def test_chain_walker_group_sizes_agree(packaged, engine, oracle):
+def test_chain_walker_group_sizes_agree(packaged, oracle):
     """The sequential exponent chain pads a site's rows to groups of 4 (long lists) or walks them one by one (sparse
-    lists); the engine switches after seeing the first evaluation.  Both must give the oracle's value."""
+    lists); the engine switches after seeing the first evaluation.  Both must give the oracle's value.  (The chain
+    certificate is switched off here: this is about the literal walker, k_chain.)"""
+    from dmphyclus_b200.engine import Engine
+    engine = Engine(chain_cert=False)
     p = Problem(packaged, 1024, 900, 6, 3, "diverged", seed=3)       # few rescales per site -> the sparse walker
     hg, l0 = p.create(engine)
     ho, lo = p.create(oracle)

@@ -68,9 +68,17 @@ def test_two_rank_site_sharding_matches_single_process(case):
 
 def test_shard_ranges_are_chunk_aligned_and_cover():
     from dmphyclus_b200.sharded import CHUNK, shard_range
+    from dmphyclus_b200.workloads import CONFIGS
+    assert CHUNK == 64          # RCH of dmphyclus_b200/csrc/kernels.cuh: decoupled from the 256-site prune tile
     for S in (1, 255, 256, 257, 10000, 30000, 1500):
         for world in (1, 2, 4, 8):
             rs = [shard_range(S, r, world) for r in range(world)]
             assert rs[0][0] == 0 and rs[-1][1] == S
             for (b0, e0), (b1, e1) in zip(rs, rs[1:]):
                 assert e0 == b1 and (b1 % CHUNK == 0 or b1 == S)
+    # every BASELINE config can run at 1, 2, 4 and 8 GPUs: no rank is left without sites (config 5 has only 1,500)
+    for name, (_, S, _, _) in CONFIGS.items():
+        for world in (1, 2, 4, 8):
+            for r in range(world):
+                b, e = shard_range(S, r, world)
+                assert e > b, (name, world, r)
