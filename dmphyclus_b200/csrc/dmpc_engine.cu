@@ -7,8 +7,13 @@
 // (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
 #include "../../include/dmpc.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -66,6 +71,7 @@ struct dmpc_comm {
   void* peer[CW] = {nullptr};          // every rank's mailbox as seen from here
   unsigned* seq = nullptr;             // message counter (device)
   bool connected = false;
+  bool ipc = true;                     // peers were opened through CUDA IPC handles (false: shards of one process)
   int maxChunks = 0;
   size_t flagBytes() const { return 64; }
   size_t payloadBytes() const { return (size_t)2 * CW * width * sizeof(double); }
@@ -73,7 +79,10 @@ struct dmpc_comm {
   size_t bytes() const { return 2 * flagBytes() + payloadBytes() + carryBytes(); }   // flags, payload, chain flags, carry
 };
 
+struct Group;
 struct dmpc_tree {
+  Group* grp = nullptr;          // set on the LEADER of a single-process multi-device handle: entry points fan out to its shards
+  bool isShard = false;          // a shard of such a handle: the leader holds the device locks
   HostTree ht;
   int N = 0, S = 0, Sp = 0, R = 0, T = 0, nInt = 0, nReal = 0, nChunks = 0, nFlag = 0;
   bool quirk = true, deferred = false, alive = true;
@@ -92,6 +101,7 @@ struct dmpc_tree {
   HostResult* h_res = nullptr;   // pinned
   double hP[2][RMAX][16];
   double hPi[4];
+  double wCol[RMAX * 16], bCol[RMAX * 16];   // the matrix lists as they last came in (column-major), for re-uploads
   bool constantsValid = false;
   std::vector<void*> allocs;
   dmpc_stats st{};
@@ -267,7 +277,9 @@ int uploadConstants(dmpc_tree* t, const double* within, const double* between, c
         if (!(row <= 1.0 + 1e-9)) t->exact = true;
       }
   std::memcpy(t->hP, P, sizeof P);
-  std::memcpy(t->hPi, pi, sizeof t->hPi);
+  std::memmove(t->hPi, pi, sizeof t->hPi);
+  std::memmove(t->wCol, within, (size_t)t->R * 16 * sizeof(double));
+  std::memmove(t->bCol, between, (size_t)t->R * 16 * sizeof(double));
   // tip lookup: P * indicator(mask), summed in gemv_emul_tinysq order (adding +0.0 terms is exact)
   std::vector<double> lut((size_t)2 * t->R * 64);
   for (int set = 0; set < 2; set++)
@@ -295,6 +307,10 @@ dmpc_tree* g_constOwner[64] = {nullptr};
 // ... and because they are, evaluations of different handles on one device must not overlap: every call that launches
 // kernels holds the device's lock until its results are back (calls are synchronous anyway)
 std::mutex g_deviceMutex[64];
+void claimConstants(dmpc_tree* t) {
+  std::lock_guard<std::mutex> lk(g_constMutex);
+  if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
+}
 
 int rootStage(dmpc_tree* t, double* ll);
 int launchRootSequence(dmpc_tree* t);
@@ -384,13 +400,11 @@ int runPlan(dmpc_tree* t) {
 // ComputeLoglik (AugTree.cpp:289-326): prune the dirty levels, then reduce at the root.
 int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll) {
   int rc;
-  std::lock_guard<std::mutex> deviceLock(g_deviceMutex[t->device & 63]);
+  std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
+  if (!t->isShard) deviceLock.lock();            // (the leader of a multi-device handle holds the locks of all its devices)
   if ((rc = ensureDevice(t))) return rc;
   if ((rc = flushCur(t))) return rc;
-  {
-    std::lock_guard<std::mutex> lk(g_constMutex);
-    if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
-  }
+  claimConstants(t);
   const auto h0 = std::chrono::steady_clock::now();
   auto usSince = [](std::chrono::steady_clock::time_point a) {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count();
@@ -760,6 +774,197 @@ int checkHandle(dmpc_tree* t) {
 
 // ================================================================================== C ABI
 extern "C" {
+static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
+                      const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
+                      int numRateCats, const uint8_t* alignmentBin, size_t alignPitch, int numTips, int numLoci,
+                      int withinMatListIndex, int betweenMatListIndex, const dmpc_options& o, bool isShard,
+                      dmpc_tree** treeOut, double* logLikOut);
+}
+
+// ================================================================================== single-process multi-device handles
+// One dmpc_tree (the LEADER, which owns no device memory) over n shard handles, each holding a contiguous block of
+// sites on its own device: what `DMPC_DEVICES=0,1,...` gives an R session, which is one process (R/DMphyClusInterface.R:71
+// stays unchanged).  Every entry point fans out to the shards — one host thread each, because the shards' root kernels
+// wait for one another inside the fused NVLink exchange — and all shards return the same log-likelihood, bit for bit
+// the single-device value.  The mailboxes are the ones of the process-per-GPU path (dmpc_comm), reached through peer
+// access instead of CUDA IPC.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has = false, done = false, quit = false;
+  int rc = 0;
+  std::string err;
+  void loop() {
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m);
+      cv.wait(lk, [&] { return has || quit; });
+      if (quit) return;
+      auto j = job;
+      lk.unlock();
+      const int r = j();
+      lk.lock();
+      rc = r; err = r ? g_err : std::string();
+      has = false; done = true;
+      cv.notify_all();
+    }
+  }
+};
+
+struct Group {
+  std::vector<dmpc_tree*> shards;
+  std::vector<dmpc_comm*> comms;
+  std::vector<std::unique_ptr<Worker>> workers;    // workers[i] serves shards[i + 1]; shard 0 runs on the calling thread
+  std::vector<int> begin, end;                     // site blocks
+  std::vector<int> lockDevices;                    // sorted, unique
+  int S = 0;
+};
+
+namespace {
+
+// fn(shard index, shard) on every shard at once; the device locks of all the group's devices are held meanwhile
+int groupRun(Group* g, const std::function<int(int, dmpc_tree*)>& fn) {
+  for (int d : g->lockDevices) g_deviceMutex[d & 63].lock();
+  const int n = (int)g->shards.size();
+  for (int i = 1; i < n; i++) {
+    Worker& w = *g->workers[i - 1];
+    std::lock_guard<std::mutex> lk(w.m);
+    w.job = [&fn, i, g] { return fn(i, g->shards[i]); };
+    w.has = true; w.done = false;
+    w.cv.notify_all();
+  }
+  int rc = fn(0, g->shards[0]);
+  std::string err = rc ? g_err : std::string();
+  for (int i = 1; i < n; i++) {
+    Worker& w = *g->workers[i - 1];
+    std::unique_lock<std::mutex> lk(w.m);
+    w.cv.wait(lk, [&] { return w.done; });
+    if (w.rc && !rc) { rc = w.rc; err = w.err; }
+  }
+  for (auto it = g->lockDevices.rbegin(); it != g->lockDevices.rend(); ++it) g_deviceMutex[*it & 63].unlock();
+  if (rc) g_err = err;
+  return rc;
+}
+
+// a likelihood entry point on every shard; all shards must come back with the same value (they reduce the same chunk
+// sums in the same order)
+int groupLoglik(Group* g, double* logLikOut, const std::function<int(int, dmpc_tree*, double*)>& fn) {
+  std::vector<double> ll(g->shards.size(), NAN);
+  const int rc = groupRun(g, [&](int i, dmpc_tree* sh) { return fn(i, sh, &ll[i]); });
+  if (rc) return rc;
+  for (size_t i = 1; i < ll.size(); i++)
+    if (std::memcmp(&ll[i], &ll[0], sizeof(double))) return fail(DMPC_ERR_STATE, "the shards of a multi-device handle disagree on the log-likelihood");
+  *logLikOut = ll[0];
+  return DMPC_OK;
+}
+
+void destroyGroup(dmpc_tree* leader) {
+  Group* g = leader->grp;
+  if (g) {
+    for (auto& w : g->workers) {
+      { std::lock_guard<std::mutex> lk(w->m); w->quit = true; }
+      w->cv.notify_all();
+      if (w->th.joinable()) w->th.join();
+    }
+    for (dmpc_tree* sh : g->shards) destroy(sh);
+    for (dmpc_comm* c : g->comms) dmpc_comm_destroy(c);
+    delete g;
+  }
+  delete leader;
+}
+
+// contiguous site block of shard r of n: multiples of RCH sites, so that the chunk boundaries — and the summation
+// tree — do not depend on the number of shards (same rule as dmphyclus_b200/sharded.py::shard_range)
+void shardRange(int S, int r, int n, int* b, int* e) {
+  long per = ((long)S + n - 1) / n;
+  per = (per + RCH - 1) / RCH * RCH;
+  *b = (int)std::min<long>(S, r * per);
+  *e = (int)std::min<long>(S, *b + per);
+}
+
+int createGroup(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs, const double* limProbs,
+                const double* withinTransMats, const double* betweenTransMats, int numRateCats, const uint8_t* alignmentBin,
+                int numTips, int numLoci, int withinMatListIndex, int betweenMatListIndex, const dmpc_options& o, int nDev,
+                dmpc_tree** treeOut, double* logLikOut) {
+  if (o.n_devices > CW) return fail(DMPC_ERR_ARG, "at most 8 devices per handle");
+  if (o.deferred || o.comm) return fail(DMPC_ERR_ARG, "n_devices > 1 excludes the process-per-GPU options (deferred, comm)");
+  for (int i = 0; i < o.n_devices; i++)
+    if (o.devices[i] < 0 || o.devices[i] >= nDev) return fail(DMPC_ERR_ARG, "dmpc_options.devices: no such CUDA device");
+  // shards that would own no site are left out (short alignments)
+  int n = o.n_devices;
+  while (n > 1) { int b, e; shardRange(numLoci, n - 1, n, &b, &e); if (e > b) break; n--; }
+  dmpc_tree* leader = new dmpc_tree;
+  Group* g = new Group;
+  leader->grp = g;
+  leader->N = numTips; leader->S = numLoci; leader->R = numRateCats; leader->device = o.devices[0];
+  g->S = numLoci;
+  auto bail = [&](int rc) { const std::string keep = g_err; destroyGroup(leader); g_err = keep; return rc; };
+  int maxChunks = 1;
+  for (int r = 0; r < n; r++) {
+    int b, e;
+    shardRange(numLoci, r, n, &b, &e);
+    g->begin.push_back(b); g->end.push_back(e);
+    maxChunks = std::max(maxChunks, (e - b + RCH - 1) / RCH);
+    if (std::find(g->lockDevices.begin(), g->lockDevices.end(), o.devices[r]) == g->lockDevices.end()) g->lockDevices.push_back(o.devices[r]);
+  }
+  std::sort(g->lockDevices.begin(), g->lockDevices.end());
+  // peer access between the devices, then one mailbox per shard, addressed directly
+  for (int a : g->lockDevices)
+    for (int b : g->lockDevices) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) return bail(fail(DMPC_ERR_CUDA, "devices of a multi-device handle need peer access to one another"));
+      cudaSetDevice(a);
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(b, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return bail(fail(DMPC_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe)));
+      cudaGetLastError();
+    }
+  for (int r = 0; r < n; r++) {
+    dmpc_comm* c = nullptr;
+    char handle[64];
+    const int rc = dmpc_comm_create(o.devices[r], r, n, maxChunks, &c, handle);
+    if (rc) return bail(rc);
+    c->ipc = false;
+    g->comms.push_back(c);
+  }
+  for (int r = 0; r < n; r++) {
+    for (int p2 = 0; p2 < n; p2++) g->comms[r]->peer[p2] = g->comms[p2]->local;
+    g->comms[r]->connected = true;
+  }
+  for (int r = 1; r < n; r++) {
+    g->workers.emplace_back(new Worker);
+    Worker* w = g->workers.back().get();
+    w->th = std::thread([w] { w->loop(); });
+  }
+  g->shards.assign(n, nullptr);
+  // the shards are created together as well: their first evaluation already meets in the exchange
+  std::vector<double> ll(n, NAN);
+  std::vector<dmpc_tree*> made(n, nullptr);
+  const int rc = [&]() {
+    g->shards.assign(n, leader);                    // placeholders (never dereferenced by the jobs below)
+    return groupRun(g, [&](int r, dmpc_tree*) {
+      dmpc_options so = o;
+      so.n_devices = 0; so.device = o.devices[r]; so.deferred = 1; so.comm = g->comms[r];
+      so.site_begin = g->begin[r]; so.sites_total = numLoci;
+      return createImpl(edge, nEdgeRows, clusterMRCAs, nClusterMRCAs, limProbs, withinTransMats, betweenTransMats, numRateCats,
+                        alignmentBin + g->begin[r], (size_t)numLoci, numTips, g->end[r] - g->begin[r], withinMatListIndex,
+                        betweenMatListIndex, so, true, &made[r], &ll[r]);
+    });
+  }();
+  g->shards.clear();
+  for (dmpc_tree* sh : made) if (sh) g->shards.push_back(sh);
+  if (rc) return bail(rc);
+  for (int r = 1; r < n; r++)
+    if (std::memcmp(&ll[r], &ll[0], sizeof(double))) return bail(fail(DMPC_ERR_STATE, "the shards of a multi-device handle disagree on the log-likelihood"));
+  *logLikOut = ll[0];
+  *treeOut = leader;
+  return DMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 void dmpc_default_options(dmpc_options* o) {
   std::memset(o, 0, sizeof *o);
@@ -784,23 +989,15 @@ long dmpc_convert_alignment(const char* chars, long nCells, const char* states, 
   return bad;
 }
 
-int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
-                       const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
-                       int numRateCats, const uint8_t* alignmentBin, int numTips, int numLoci,
-                       int withinMatListIndex, int betweenMatListIndex, const dmpc_options* opts,
-                       dmpc_tree** treeOut, double* logLikOut) {
-  if (!edge || !limProbs || !withinTransMats || !betweenTransMats || !alignmentBin || !treeOut || !logLikOut ||
-      (nClusterMRCAs > 0 && !clusterMRCAs))
-    return fail(DMPC_ERR_ARG, "null pointer");
-  if (numRateCats < 1 || numRateCats > RMAX) return fail(DMPC_ERR_ARG, "numRateCats must be in 1..8");
-  if (numTips < 2 || numLoci < 1) return fail(DMPC_ERR_ARG, "need at least 2 tips and 1 locus");
-  dmpc_options o;
-  dmpc_default_options(&o);
-  if (opts) o = *opts;
-  int nDev = 0;
-  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
-    return fail(DMPC_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+// one handle on one device.  alignmentBin holds this handle's numLoci columns of every tip, rows alignPitch bytes apart
+// (the whole alignment's row length when the handle is a shard of a multi-device handle)
+static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
+                      const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
+                      int numRateCats, const uint8_t* alignmentBin, size_t alignPitch, int numTips, int numLoci,
+                      int withinMatListIndex, int betweenMatListIndex, const dmpc_options& o, bool isShard,
+                      dmpc_tree** treeOut, double* logLikOut) {
   dmpc_tree* t = new dmpc_tree;
+  t->isShard = isShard;
   if (o.device < 0) { if (cudaGetDevice(&t->device) != cudaSuccess) t->device = 0; } else t->device = o.device;
   if (!t->ht.build(edge, nEdgeRows, numTips)) { std::string e = t->ht.err; delete t; return fail(DMPC_ERR_ARG, e); }
   t->ht.associate(clusterMRCAs, nClusterMRCAs);
@@ -880,7 +1077,7 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
     // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
     t->st.create_setup_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
     CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
-    CUDA_TRY(cudaMemcpyAsync(stage, alignmentBin, (size_t)t->N * t->S, cudaMemcpyHostToDevice, t->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(stage, (size_t)t->S, alignmentBin, alignPitch, (size_t)t->S, (size_t)t->N, cudaMemcpyHostToDevice, t->stream));
     {
       const size_t n = (size_t)t->N * t->Sp;
       k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
@@ -901,11 +1098,39 @@ int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* cluster
   return DMPC_OK;
 }
 
+int dmpc_loglik_create(const int32_t* edge, int nEdgeRows, const double* clusterMRCAs, int nClusterMRCAs,
+                       const double* limProbs, const double* withinTransMats, const double* betweenTransMats,
+                       int numRateCats, const uint8_t* alignmentBin, int numTips, int numLoci,
+                       int withinMatListIndex, int betweenMatListIndex, const dmpc_options* opts,
+                       dmpc_tree** treeOut, double* logLikOut) {
+  if (!edge || !limProbs || !withinTransMats || !betweenTransMats || !alignmentBin || !treeOut || !logLikOut ||
+      (nClusterMRCAs > 0 && !clusterMRCAs))
+    return fail(DMPC_ERR_ARG, "null pointer");
+  if (numRateCats < 1 || numRateCats > RMAX) return fail(DMPC_ERR_ARG, "numRateCats must be in 1..8");
+  if (numTips < 2 || numLoci < 1) return fail(DMPC_ERR_ARG, "need at least 2 tips and 1 locus");
+  dmpc_options o;
+  dmpc_default_options(&o);
+  if (opts) o = *opts;
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return fail(DMPC_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+  if (o.n_devices > 1)
+    return createGroup(edge, nEdgeRows, clusterMRCAs, nClusterMRCAs, limProbs, withinTransMats, betweenTransMats, numRateCats,
+                       alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex, o, nDev, treeOut, logLikOut);
+  return createImpl(edge, nEdgeRows, clusterMRCAs, nClusterMRCAs, limProbs, withinTransMats, betweenTransMats, numRateCats,
+                    alignmentBin, (size_t)numLoci, numTips, numLoci, withinMatListIndex, betweenMatListIndex, o, false, treeOut,
+                    logLikOut);
+}
+
 int dmpc_new_between_transprobs_loglik(dmpc_tree* t, const double* withinTransMats, const double* newBetweenTransMats,
                                        int newBetweenMatListIndex, const double* limProbs, double* logLikOut) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!withinTransMats || !newBetweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp)
+    return groupLoglik(t->grp, logLikOut, [&](int, dmpc_tree* sh, double* ll) {
+      return dmpc_new_between_transprobs_loglik(sh, withinTransMats, newBetweenTransMats, newBetweenMatListIndex, limProbs, ll);
+    });
   t->ht.negateAllUpdateFlags();
   t->ht.betweenIdx = newBetweenMatListIndex;
   t->ht.invalidateBetween();
@@ -917,6 +1142,10 @@ int dmpc_new_within_transprobs_loglik(dmpc_tree* t, const double* newWithinTrans
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!newWithinTransMats || !betweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp)
+    return groupLoglik(t->grp, logLikOut, [&](int, dmpc_tree* sh, double* ll) {
+      return dmpc_new_within_transprobs_loglik(sh, newWithinTransMats, betweenTransMats, newWithinMatListIndex, limProbs, ll);
+    });
   t->ht.negateAllUpdateFlags();
   t->ht.withinIdx = newWithinMatListIndex;
   t->ht.invalidateAll();
@@ -948,6 +1177,14 @@ int dmpc_within_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, con
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !edgeOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp) {
+    // every shard draws the same NNI picks from its own Tausworthe stream and exports the same edge matrix
+    std::vector<std::vector<int32_t>> e2(t->grp->shards.size());
+    return groupLoglik(t->grp, logLikOut, [&](int i, dmpc_tree* sh, double* ll) {
+      if (i) e2[i].resize((size_t)4 * (sh->N - 1));
+      return dmpc_within_clus_nni_loglik(sh, withinTransMats, betweenTransMats, mrcaOfClusForNNI, numMovesNNI, limProbs, ll, i ? e2[i].data() : edgeOut);
+    });
+  }
   if (mrcaOfClusForNNI < 1 || mrcaOfClusForNNI > t->ht.numVerts) return fail(DMPC_ERR_ARG, "MRCAofClusForNNI out of range");
   return nniCommon(t, withinTransMats, betweenTransMats, mrcaOfClusForNNI - 1, nullptr, numMovesNNI, limProbs, logLikOut, edgeOut);
 }
@@ -959,6 +1196,14 @@ int dmpc_between_clus_nni_loglik(dmpc_tree* t, const double* withinTransMats, co
   if ((rc = checkHandle(t))) return rc;
   if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !edgeOut || (nClusterMRCAs > 0 && !clusterMRCAs))
     return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp) {
+    std::vector<std::vector<int32_t>> e2(t->grp->shards.size());
+    return groupLoglik(t->grp, logLikOut, [&](int i, dmpc_tree* sh, double* ll) {
+      if (i) e2[i].resize((size_t)4 * (sh->N - 1));
+      return dmpc_between_clus_nni_loglik(sh, withinTransMats, betweenTransMats, clusterMRCAs, nClusterMRCAs, numMovesNNI, limProbs, ll,
+                                          i ? e2[i].data() : edgeOut);
+    });
+  }
   std::vector<long> m(nClusterMRCAs);
   for (int i = 0; i < nClusterMRCAs; i++) m[i] = (long)clusterMRCAs[i];
   return nniCommon(t, withinTransMats, betweenTransMats, t->ht.root(), &m, numMovesNNI, limProbs, logLikOut, edgeOut);
@@ -969,6 +1214,10 @@ int dmpc_clus_split_merge_loglik(dmpc_tree* t, const double* withinTransMats, co
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut || !mrcas || n < 1) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp)
+    return groupLoglik(t->grp, logLikOut, [&](int, dmpc_tree* sh, double* ll) {
+      return dmpc_clus_split_merge_loglik(sh, withinTransMats, betweenTransMats, mrcas, n, limProbs, ll);
+    });
   HostTree& ht = t->ht;
   for (int i = 0; i < n; i++)
     if (mrcas[i] < 1 || mrcas[i] > ht.numVerts) return fail(DMPC_ERR_ARG, "cluster MRCA out of range");
@@ -1010,6 +1259,11 @@ int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRow
                                  int nClusterMRCAs, int splitMergeMove) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp)
+    return groupRun(t->grp, [&](int, dmpc_tree* sh) {
+      return dmpc_restore_previous_config(sh, edge, nEdgeRows, withinMatListIndex, betweenMatListIndex, nniMove, clusterMRCAs, nClusterMRCAs,
+                                          splitMergeMove);
+    });
   if ((rc = ensureDevice(t))) return rc;
   HostTree& ht = t->ht;
   ht.withinIdx = withinMatListIndex; ht.betweenIdx = betweenMatListIndex;
@@ -1028,7 +1282,7 @@ int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRow
 int dmpc_final_deallocate(dmpc_tree* t) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
-  destroy(t);
+  if (t->grp) destroyGroup(t); else destroy(t);
   return DMPC_OK;
 }
 
@@ -1046,6 +1300,8 @@ int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!withinTransMats || !betweenTransMats || !limProbs || !logLikOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp)
+    return groupLoglik(t->grp, logLikOut, [&](int, dmpc_tree* sh, double* ll) { return dmpc_recompute_all(sh, withinTransMats, betweenTransMats, limProbs, ll); });
   t->ht.negateAllUpdateFlags();
   t->ht.invalidateAll();
   return evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
@@ -1056,6 +1312,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
                         const dmpc_proposal* props, int nProps, double* logLikOut, int* nBatchedOut) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp) return fail(DMPC_ERR_STATE, "dmpc_eval_proposals is not available on a multi-device handle");
   if ((rc = ensureDevice(t))) return rc;
   if (!withinTransMats || !betweenTransMats || !limProbs || !props || !logLikOut || nProps < 0) return fail(DMPC_ERR_ARG, "null pointer");
   if (t->deferred) return fail(DMPC_ERR_STATE, "dmpc_eval_proposals is not available on a site-sharded (deferred) handle");
@@ -1073,10 +1330,9 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       return fail(DMPC_ERR_ARG, "unknown proposal kind");
     }
   }
-  {
-    std::lock_guard<std::mutex> lk(g_constMutex);
-    if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
-  }
+  // the matrices live in module-level __constant__ memory: no other handle may launch on this device meanwhile
+  std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63]);
+  claimConstants(t);
   if ((rc = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return rc;
   if ((rc = flushCur(t))) return rc;
   int nBatched = 0;
@@ -1210,7 +1466,10 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       t->st.updates += (unsigned long long)nT * t->S * t->R;
     }
   }
-  // whatever could not be batched (rescaling involved, exact mode): the ordinary proposal path, then an internal reject
+  // whatever could not be batched (rescaling involved, exact mode): the ordinary proposal path, then an internal reject.
+  // These evaluations reuse the rollback slots, which is why the call must not sit between a proposal and its
+  // dmpc_restore_previous_config (see the header).
+  deviceLock.unlock();                             // evaluate() takes it again
   for (int i = 0; i < nProps; i++) {
     if (!needSeq[i]) continue;
     const dmpc_proposal& q = props[i];
@@ -1238,6 +1497,25 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp) {
+    // counters add up over the shards; times are those of the slowest shard; shapes are the whole alignment's
+    Group* g = t->grp;
+    for (size_t i = 0; i < g->shards.size(); i++) {
+      dmpc_stats s1;
+      if ((rc = dmpc_get_stats(g->shards[i], &s1))) return rc;
+      if (i == 0) { *out = s1; continue; }
+      out->updates += s1.updates; out->kernel_launches += s1.kernel_launches; out->last_updates += s1.last_updates;
+      out->device_bytes += s1.device_bytes; out->last_algorithmic_bytes += s1.last_algorithmic_bytes;
+      out->last_active_tiles += s1.last_active_tiles; out->last_chain_sites += s1.last_chain_sites; out->last_chain_rows += s1.last_chain_rows;
+      out->last_eval_ms = std::max(out->last_eval_ms, s1.last_eval_ms); out->last_prune_ms = std::max(out->last_prune_ms, s1.last_prune_ms);
+      out->last_host_total_us = std::max(out->last_host_total_us, s1.last_host_total_us);
+      out->create_upload_ms = std::max(out->create_upload_ms, s1.create_upload_ms);
+      out->exponent_capacity = std::max(out->exponent_capacity, s1.exponent_capacity);
+      out->exact_mode |= s1.exact_mode;
+    }
+    out->num_loci = g->S;
+    return DMPC_OK;
+  }
   if (t->evalTimePending) {                    // the evaluation's result was polled: its closing event may complete a moment later
     t->evalTimePending = false;
     float ms = 0;
@@ -1256,6 +1534,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
 int dmpc_timer_begin(dmpc_tree* t) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp) { for (dmpc_tree* sh : t->grp->shards) if ((rc = dmpc_timer_begin(sh))) return rc; return DMPC_OK; }
   if ((rc = ensureDevice(t))) return rc;
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   CUDA_TRY(cudaEventRecord(t->ev[3], t->stream));
@@ -1265,8 +1544,14 @@ int dmpc_timer_begin(dmpc_tree* t) {
 int dmpc_timer_end(dmpc_tree* t, double* msOut) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
-  if ((rc = ensureDevice(t))) return rc;
   if (!msOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp) {                                    // the slowest shard's device time
+    double worst = 0.0;
+    for (dmpc_tree* sh : t->grp->shards) { double ms; if ((rc = dmpc_timer_end(sh, &ms))) return rc; worst = std::max(worst, ms); }
+    *msOut = worst;
+    return DMPC_OK;
+  }
+  if ((rc = ensureDevice(t))) return rc;
   CUDA_TRY(cudaEventRecord(t->ev[4], t->stream));
   CUDA_TRY(cudaEventSynchronize(t->ev[4]));
   float ms = 0;
@@ -1569,8 +1854,19 @@ int dmpc_hp_destroy(dmpc_hostplan* h) {
 int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp) {                                    // the shards' site blocks side by side
+    Group* g = t->grp;
+    if (!sol || !expo) return fail(DMPC_ERR_ARG, "null pointer");
+    for (size_t i = 0; i < g->shards.size(); i++)
+      if ((rc = dmpc_get_partial(g->shards[i], vertex, sol + (size_t)g->begin[i] * t->R * 4, expo + (size_t)g->begin[i] * t->R))) return rc;
+    return DMPC_OK;
+  }
   if ((rc = ensureDevice(t))) return rc;
   if (vertex < t->N || vertex >= t->ht.numVerts || !sol || !expo) return fail(DMPC_ERR_ARG, "vertex must be internal");
+  std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
+  if (!t->isShard) deviceLock.lock();
+  claimConstants(t);
+  if (!t->constantsValid && (rc = uploadConstants(t, &t->wCol[0], &t->bCol[0], t->hPi))) return rc;
   HostTree& ht = t->ht;
   const int slot = ht.cur[vertex], idx = vertex - t->N;
   int partSlot = slot, partRow = idx;
@@ -1608,6 +1904,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
 int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* child1, int32_t* within) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp) return dmpc_get_topology(t->grp->shards[0], parent, child0, child1, within);
   for (int v = 0; v < t->ht.numVerts; v++) {
     parent[v] = t->ht.parent[v];
     child0[v] = t->ht.kids[2 * v]; child1[v] = t->ht.kids[2 * v + 1];
@@ -1619,6 +1916,11 @@ int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* c
 int dmpc_get_site_logliks(dmpc_tree* t, double* out) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp) {
+    for (size_t i = 0; i < t->grp->shards.size(); i++)
+      if ((rc = dmpc_get_site_logliks(t->grp->shards[i], out + t->grp->begin[i]))) return rc;
+    return DMPC_OK;
+  }
   if ((rc = ensureDevice(t))) return rc;
   CUDA_TRY(cudaStreamSynchronize(t->stream));
   CUDA_TRY(cudaMemcpy(out, t->rv.sitell, (size_t)t->S * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1628,6 +1930,7 @@ int dmpc_get_site_logliks(dmpc_tree* t, double* out) {
 int dmpc_set_deferred(dmpc_tree* t, int on) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (t->grp || t->isShard) return fail(DMPC_ERR_STATE, "a multi-device handle runs its own exchange");
   t->deferred = on != 0;
   t->graphVersion++;
   return DMPC_OK;
@@ -1731,7 +2034,7 @@ int dmpc_comm_destroy(dmpc_comm* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (int p = 0; p < c->world; p++)
-    if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    if (c->ipc && p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
   if (c->local) cudaFree(c->local);
   delete c;
   return DMPC_OK;

@@ -131,7 +131,7 @@ class Engine:
     name = "cuda"
 
     def __init__(self, device: int = -1, quirk_carry: bool = True, site_begin: int = 0, sites_total: int = 0,
-                 fuse_tips: int | None = None, fuse_exact: bool = False, chain_cert: bool = True):
+                 fuse_tips: int | None = None, fuse_exact: bool = False, chain_cert: bool = True, devices=None):
         self.lib = load_library()
         self.opts = Options()
         self.lib.dmpc_default_options(C.byref(self.opts))
@@ -143,6 +143,13 @@ class Engine:
             self.opts.fuse_tips = int(fuse_tips)
         self.opts.fuse_exact = int(fuse_exact)
         self.opts.chain_cert = int(chain_cert)
+        if devices is not None and len(devices) > 1:
+            # single-process multi-GPU: one handle whose sites are sharded over these devices (a device may repeat)
+            if len(devices) > 8:
+                raise ValueError("at most 8 devices per handle")
+            self.opts.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                self.opts.devices[i] = int(d)
         self._shape = {}
         self._mcache = {}
         self._ecache = {}

@@ -123,7 +123,10 @@ int dmpc_recompute_all(dmpc_tree* t, const double* withinTransMats, const double
  * dmpc_clus_split_merge_loglik would return for proposal i (followed by a reject).  Proposals whose paths involve no
  * rescaling are evaluated together — one launch walks every proposal's path to the root with the path partial in
  * registers, reading only the off-path siblings; the rest goes through the ordinary path one by one.  *nBatchedOut =
- * how many took the batched kernel.  Matrices must be the committed ones. */
+ * how many took the batched kernel.  Matrices must be the committed ones.  Call it only when no proposal is waiting
+ * for its dmpc_restore_previous_config: the one-by-one path reuses the rollback slots (a proposal made before the call
+ * can no longer be restored afterwards), and a fused clade that turns out to rescale switches the handle to exact
+ * mode for good (dmpc_stats.exact_mode), exactly as an ordinary proposal would. */
 enum { DMPC_PROPOSAL_SPLIT = 0, DMPC_PROPOSAL_MERGE = 1 };
 typedef struct dmpc_proposal {
   int32_t kind;   /* DMPC_PROPOSAL_SPLIT: a = cluster MRCA to split; DMPC_PROPOSAL_MERGE: a, b = sibling cluster MRCAs */

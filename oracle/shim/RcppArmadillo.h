@@ -192,9 +192,15 @@ class RawVector {
   explicit RawVector(size_t n) : s(shim::alloc(SEXPREC::RAW)) { s->raw.assign(n, 0); }
   RawVector(SEXP x) : s(x) {}
   unsigned char& operator[](size_t i) { return s->raw[i]; }
+  long size() const { return (long)s->raw.size(); }
   AttrProxy attr(const std::string& n) { return AttrProxy(s, n); }
   operator SEXP() const { return s; }
 };
+}  // namespace Rcpp
+// R's type tags, as far as the drop-in shim asks for them
+#define RAWSXP 24
+inline int TYPEOF(SEXP s) { return s == 0 || s->kind == SEXPREC::NIL ? 0 : s->kind == SEXPREC::RAW ? RAWSXP : -1; }
+namespace Rcpp {
 
 inline SEXP wrap(const NumericVector& v) { return v.s; }
 inline SEXP wrap(const IntegerVector& v) { return v.s; }

@@ -17,6 +17,7 @@
 #include "dmpc.h"
 
 using namespace Rcpp;
+typedef unsigned int uint;      // the reference's signatures spell it this way (glibc's <sys/types.h> typedef; restated for other libcs)
 
 namespace {
 
@@ -65,6 +66,21 @@ dmpc_options optionsFromEnv() {       // the R signature has no room for options
   dmpc_default_options(&o);
   if (const char* d = std::getenv("DMPC_DEVICE")) o.device = std::atoi(d);
   if (const char* q = std::getenv("DMPC_QUIRK_CARRY")) o.quirk_carry = std::atoi(q);
+  // DMPC_DEVICES=0,1,...,7: single-process multi-GPU — one handle whose sites are sharded over these devices; R stays
+  // one process and DMphyClusChain's signature (R/DMphyClusInterface.R:71) stays what it is
+  if (const char* l = std::getenv("DMPC_DEVICES")) {
+    int n = 0;
+    const char* p = l;
+    while (*p && n < 8) {
+      char* end = NULL;
+      const long d = std::strtol(p, &end, 10);
+      if (end == p) break;
+      o.devices[n++] = (int)d;
+      p = end;
+      while (*p == ',' || *p == ' ') p++;
+    }
+    if (n > 1) o.n_devices = n; else if (n == 1) o.device = o.devices[0];
+  }
   return o;
 }
 
@@ -78,11 +94,35 @@ List logLikCpp(IntegerMatrix& edgeMat, NumericVector& clusterMRCAs, NumericVecto
   // ride along as attribute "dmpc_masks" (raw numTips x numLoci, column-major) when it came from this library.
   std::vector<uint8_t> masks((size_t)numTips * numLoci);
   RObject packed(alignmentBin.attr("dmpc_masks"));
-  if (!packed.isNULL()) {
+  auto maskOfCell = [&](uint i, uint j) -> uint8_t {
+    List row(alignmentBin[i]);
+    IntegerVector ind(row[j]);
+    uint8_t m = 0;
+    for (int k = 0; k < ind.size() && k < 4; k++) m |= (uint8_t)((ind[k] != 0) << k);
+    return m;
+  };
+  // The attribute is trusted only when it still describes THIS list: raw, numTips x numLoci, and equal to the list on a
+  // spread of probe cells (R's `[[<-` keeps attributes, so an edited alignmentBin could otherwise be evaluated with
+  // stale masks).  Anything else falls back to the list itself.
+  bool usePacked = false;
+  if (!packed.isNULL() && TYPEOF(packed) == RAWSXP && (size_t)alignmentBin.size() == (size_t)numTips) {
     RawVector raw(packed);
-    for (uint i = 0; i < numTips; i++)
-      for (uint j = 0; j < numLoci; j++) masks[(size_t)i * numLoci + j] = raw[(size_t)i + (size_t)j * numTips];
-  } else {
+    RObject dim(raw.attr("dim"));
+    if (!dim.isNULL()) {
+      IntegerVector d(dim);
+      usePacked = d.size() == 2 && (uint)d[0] == numTips && (uint)d[1] == numLoci && (size_t)raw.size() == (size_t)numTips * numLoci;
+    }
+    const size_t cells = (size_t)numTips * numLoci, probes = cells < 257 ? cells : 257;
+    for (size_t q = 0; usePacked && q < probes; q++) {
+      const size_t c = probes == cells ? q : (q * (cells - 1)) / (probes - 1);
+      const uint i = (uint)(c / numLoci), j = (uint)(c % numLoci);
+      if (List(alignmentBin[i]).size() != (int)numLoci || raw[(size_t)i + (size_t)j * numTips] != maskOfCell(i, j)) usePacked = false;
+    }
+    if (usePacked)
+      for (uint i = 0; i < numTips; i++)
+        for (uint j = 0; j < numLoci; j++) masks[(size_t)i * numLoci + j] = raw[(size_t)i + (size_t)j * numTips];
+  }
+  if (!usePacked) {
     for (uint i = 0; i < numTips; i++) {
       List row(alignmentBin[i]);
       for (uint j = 0; j < numLoci; j++) {
@@ -111,11 +151,18 @@ SEXP getConvertedAlignment(SEXP& equivVector, CharacterMatrix& alignmentAlphaMat
   std::vector<std::string> states = as<std::vector<std::string> >(equivVector);
   if (states.size() != 4) stop("4-state DNA only");
   char st[4];
-  for (int j = 0; j < 4; j++) st[j] = states[j][0];
+  for (int j = 0; j < 4; j++) {
+    if (states[j].size() != 1) stop("state labels must be single characters");
+    st[j] = states[j][0];
+  }
   const int n = alignmentAlphaMat.nrow(), s = alignmentAlphaMat.ncol();
   std::vector<char> chars((size_t)n * s);
   for (int i = 0; i < n; i++)
-    for (int j = 0; j < s; j++) chars[(size_t)i * s + j] = std::string(alignmentAlphaMat(i, j))[0];
+    for (int j = 0; j < s; j++) {
+      // a multi-character cell matches no key of the reference's string-keyed map (clusterFunArmadillo.cpp:64-93): unknown
+      const std::string cell(alignmentAlphaMat(i, j));
+      chars[(size_t)i * s + j] = cell.size() == 1 ? cell[0] : '?';
+    }
   std::vector<uint8_t> masks(chars.size());
   dmpc_convert_alignment(chars.data(), (long)chars.size(), st, masks.data());
   // R-visible shape of the reference (list of lists of 0/1 vectors; an unknown symbol gives an empty vector)

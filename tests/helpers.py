@@ -1,4 +1,5 @@
 """Shared helpers of the parity tests."""
+import numpy as np
 from dmphyclus_b200.workloads import Problem  # noqa: F401
 
 
@@ -47,3 +48,29 @@ def compare_to_golden(got, expected, ll_tol, exact_partials=True):
             assert np.allclose(g, e, rtol=2e-7, atol=0), k
         else:
             assert np.array_equal(g, e), k
+
+
+def recompute(be, h, W, B, w_idx, pi):
+    """InvalidateAll + ComputeLoglik: the engine's recomputeAll, or the same thing through the reference's entry point."""
+    if hasattr(be, "recomputeAll"):
+        return be.recomputeAll(h, W, B, pi)
+    return be.newWithinTransProbsLogLik(h, W, B, 1, w_idx, pi)
+
+
+def scripted_moves(be, h, p, keep):
+    """A short scripted sequence over every kind of proposal; returns the log-likelihoods."""
+    W, B = p.W, p.B
+    out = []
+    none = np.zeros((1, 2), np.int32)
+    out.append(recompute(be, h, W[4], B[4], 5, p.pi))
+    out.append(be.newBetweenTransProbsLogLik(h, W[4], B[1], 1, 2, p.pi))
+    if not keep:
+        be.RestorePreviousConfig(h, none, 5, 5, False, p.mrcas, False)
+    out.append(be.newWithinTransProbsLogLik(h, W[6], B[1 if keep else 4], 1, 7, p.pi))
+    m = [x for x in p.mrcas if x > p.n][0]
+    out.append(be.clusSplitMergeLogLik(h, W[6], B[1 if keep else 4], [m], 1, p.pi))
+    be.RestorePreviousConfig(h, none, 7, 2 if keep else 5, False, p.mrcas, True)
+    r = be.withinClusNNIlogLik(h, W[6], B[1 if keep else 4], m, 1, 1, p.pi)
+    out.append(r["logLik"])
+    out.append(recompute(be, h, W[6], B[1 if keep else 4], 7, p.pi))
+    return out

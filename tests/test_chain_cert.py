@@ -5,7 +5,7 @@ every per-site term) and the oracle within 1e-9; where the certificate does not 
 import numpy as np
 import pytest
 
-from helpers import Problem, rel
+from helpers import Problem, rel, scripted_moves as _moves
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -14,32 +14,6 @@ TOL = 1e-9
 def _pair():
     from dmphyclus_b200.engine import Engine
     return Engine(chain_cert=True), Engine(chain_cert=False)
-
-
-def _recompute(be, h, W, B, w_idx, pi):
-    """InvalidateAll + ComputeLoglik: the engine's recomputeAll, or the same thing through the reference's entry point."""
-    if hasattr(be, "recomputeAll"):
-        return be.recomputeAll(h, W, B, pi)
-    return be.newWithinTransProbsLogLik(h, W, B, 1, w_idx, pi)
-
-
-def _moves(be, h, p, keep):
-    """A short scripted sequence over every kind of proposal; returns the log-likelihoods."""
-    W, B = p.W, p.B
-    out = []
-    none = np.zeros((1, 2), np.int32)
-    out.append(_recompute(be, h, W[4], B[4], 5, p.pi))
-    out.append(be.newBetweenTransProbsLogLik(h, W[4], B[1], 1, 2, p.pi))
-    if not keep:
-        be.RestorePreviousConfig(h, none, 5, 5, False, p.mrcas, False)
-    out.append(be.newWithinTransProbsLogLik(h, W[6], B[1 if keep else 4], 1, 7, p.pi))
-    m = [x for x in p.mrcas if x > p.n][0]
-    out.append(be.clusSplitMergeLogLik(h, W[6], B[1 if keep else 4], [m], 1, p.pi))
-    be.RestorePreviousConfig(h, none, 7, 2 if keep else 5, False, p.mrcas, True)
-    r = be.withinClusNNIlogLik(h, W[6], B[1 if keep else 4], m, 1, 1, p.pi)
-    out.append(r["logLik"])
-    out.append(_recompute(be, h, W[6], B[1 if keep else 4], 7, p.pi))
-    return out
 
 
 @pytest.mark.parametrize("n,S,k,R,kind,seed,expect", [
