@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py — throughput of the Felsenstein-pruning likelihood path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2] [--data evolved|iid]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3] [--data evolved|iid]
 
 One "step" = one full evaluation of the likelihood (InvalidateAll + ComputeLoglik: every internal vertex of the
 tree re-pruned at every site and rate category, then the root reduction) on one batch of synthetic input.  The
 metric is BASELINE.json's: node-site partial updates/sec, one update = one 4-state conditional-likelihood vector
-for one (internal vertex, site, rate category).
+for one (internal vertex, site, rate category); `mcmc` carries its second half, MCMC iterations/sec.
+
+Workload: config 3 (10,000 sequences x 30,000 sites, 100 clusters, 3 rate categories — the shape BASELINE.json's
+target is quoted on; it fits one B200: 66 GB).  N > 1 (launched by torchrun, one rank per GPU): the SAME 30,000 sites
+are split over the ranks (strong scaling; `--weak` gives every rank the full site count instead); the ranks meet only
+in the root reduction, inside the kernel, over NVLink peer mailboxes.  `also_config2` repeats the device-resident and
+end-to-end numbers on round 1's headline shape (1,000 x 10,000).
 
   value      device-resident: the alignment, tree and buffers already live in HBM; K x dmpc_recompute_all, timed
              with CUDA events on the engine's own stream, max over ranks.
   e2e        the same evaluation through the reference-facing call (`logLikCpp` = dmpc_loglik_create, then
              `finalDeallocate`) from pinned HOST buffers: tree build, alignment upload, pruning, reduction and
              the read-back of the log-likelihood all inside the timed region (wall clock around synchronous calls).
-  roofline   k_prune_level (the dominant kernel): algorithmic bytes of the timed launches / their device time
-             (CUDA events around the level launches of every evaluation), against MEASURED_PEAKS.json's HBM copy rate.
+  roofline   k_prune (the dominant kernel).  Small-clade fusion keeps ~88 % of the vertices out of HBM, so the kernel is
+             bound by the rate at which the fp64 pipe retires separately-rounded DMUL / DADD (the reference's evaluation
+             order forbids FMA): achieved = the DMUL + DADD the timed launches had to issue / their device time
+             (CUDA events around the level launches), peak = tools/fp64_peak.cu measured on this GPU in this run.
+             `hbm_equiv` keeps the algorithmic-bytes view (68 B per update) against MEASURED_PEAKS.json.
   cpu_baseline  the reference's own translation units (oracle/_ref, single-threaded — its OpenMP is commented
-             out) on a bounded sample of the same alignment, on this box's host cores.
-
-N > 1 (launched by torchrun, one rank per GPU): sites are sharded, every rank holds `sites` columns (weak scaling);
-the ranks meet only in the root reduction (dmphyclus_b200/sharded.py).
+             out) on a bounded sample of the same alignment, on this box's host cores; plus the
+             reference-driven MCMC rate on a bounded sample.
 
 `--impl reference` times the reference's CPU implementation (oracle/_ref/libref.so, else the oracle port) on the
 same workload and prints the same JSON line with "impl": "reference".
@@ -50,19 +57,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--workload", default="config3")
     ap.add_argument("--data", default="evolved", choices=["evolved", "iid", "matched"])
     ap.add_argument("--tree", default="random", choices=["random", "balanced", "caterpillar"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the iid / MCMC extra legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the MCMC / config 2 / other-alignment extra legs")
+    ap.add_argument("--all-extras", action="store_true", help="also run the rescale-stress (other alignment kind) leg")
     ap.add_argument("--mcmc-only", action="store_true", help="extra legs: only the MCMC one (skip the other alignment kind)")
     ap.add_argument("--fuse", type=int, default=None, help="small-clade fusion threshold (tips); default = library default")
     ap.add_argument("--sweep-rates", type=int, default=3, help="rate categories of the proposal sweep")
     ap.add_argument("--proposal-sweep", action="store_true", help="config 4: batches of 64..4096 split/merge proposals per launch")
-    ap.add_argument("--strong", action="store_true", help="N > 1: split the workload's sites across the ranks (strong scaling) instead of giving every rank the full site count")
+    ap.add_argument("--weak", action="store_true", help="N > 1: give every rank the workload's full site count (weak scaling) instead of splitting the workload's sites across the ranks (strong scaling, the default: BASELINE.json's target is config 3 over 8 GPUs)")
     ap.add_argument("--seed", type=int, default=2001)
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.strong = not args.weak
+    return args
 
 
 def peaks():
@@ -70,6 +80,21 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak(device):
+    """DMUL + DADD per second of this GPU, measured now by tools/fp64_peak.cu (built by __graft_entry__.build())."""
+    import ctypes
+    lib = os.path.join(ROOT, "tools", "libfp64peak.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared",
+                               "-Xcompiler", "-fPIC", "-o", lib, os.path.join(ROOT, "tools", "fp64_peak.cu")])
+    L = ctypes.CDLL(lib)
+    L.fp64_issue_peak.restype = ctypes.c_double
+    L.fp64_issue_peak.argtypes = [ctypes.c_int, ctypes.c_int]
+    v = L.fp64_issue_peak(device, 5)
+    return v if v > 0 else None
 
 
 def ncu_traffic(workload, data):
@@ -97,7 +122,7 @@ def algorithmic_bytes(n, s, r):
 def make_problem(args, world):
     from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
     n, s, k, r = CONFIGS[args.workload]
-    if args.strong:      # strong scaling: the workload's own site count, sharded
+    if args.strong or world == 1:      # strong scaling: the workload's own site count, sharded
         return Problem(load_packaged(), n, s, k, r, args.data, args.tree, seed=args.seed), (n, s // world, k, r)
     # weak scaling: every rank holds `s` sites of an alignment of s * world sites
     return Problem(load_packaged(), n, s * world, k, r, args.data, args.tree, seed=args.seed), (n, s, k, r)
@@ -176,16 +201,53 @@ def time_cpu(be, p, n_sites, reps=1):
     return best, res["logLik"]
 
 
+def reference_sample_sites(be, p, s, budget_s):
+    """Sites of a bounded sample: the reference's cost is calibrated on 16 columns and the sample sized for ~budget_s
+    of CPU work (/1.5: its std::map look-ups slow down as the dictionary grows)."""
+    t_probe, _ = time_cpu(be, p, 16)
+    per_site = t_probe / 16
+    return int(max(16, min(s, budget_s / per_site / 1.5))), per_site
+
+
+def reference_mcmc(p, s, per_site, budget_s=16.0):
+    """MCMC iterations/sec of the reference's own likelihood code under the same driver (`chain.run_chain`, the mirror of
+    `.performStepPhylo`, /root/reference/R/DMphyClusSource.R:1-26), on a bounded sample of sites: a full-size iteration
+    of config 3 would take minutes.  The sample is sized for ~budget_s; the rate it would have on all sites is
+    extrapolated linearly in the site count (its work per likelihood call is per site; the memo dictionary makes it
+    somewhat sub-linear, so the estimate flatters the reference)."""
+    from dmphyclus_b200 import chain, synth
+    from oracle.oracle import Reference
+    try:
+        be = Reference()
+        kind = "reference"
+    except Exception:
+        from oracle.oracle import Oracle
+        be, kind = Oracle(), "port"
+    iters = 2
+    m = int(max(16, min(s, budget_s / (iters + 1) / 5.0 / per_site)))   # an iteration costs ~5 full evaluations of the sample
+    al = be.getConvertedAlignment(list(synth.STATES), p.chars[:, :m])
+    cs = chain.ChainSettings(limProbs=p.pi, withinTransMatAll=p.W, betweenTransMatAll=p.B, shapeForAlpha=1000,
+                             scaleForAlpha=0.1, alphaMin=10, poisRateNumClus=2, numSplitMergeMoves=3)
+    marks = []
+    t0 = time.perf_counter()
+    _, calls = chain.run_chain(be, al, p.edge, p.clus, 100.0, cs, iters, seed=2001,
+                               on_iter=lambda it, cv: marks.append((time.perf_counter(), cv.n_loglik_calls)))
+    rate = (len(marks) - 1) / (marks[-1][0] - marks[0][0]) if len(marks) > 1 else iters / (time.perf_counter() - t0)
+    return {"iterations_per_sec": rate, "kind": kind, "cores": 1, "iterations": iters, "likelihood_calls": calls,
+            "sample": f"first {m} of {s} sites, all {p.n} tips, {iters} iterations of the .performStepPhylo mirror "
+                      f"(rate after the first iteration)",
+            "iterations_per_sec_all_sites_estimate": rate * m / s,
+            "estimate": "sample rate x sample sites / all sites (work per call is per site)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     p, (n, s, k, r) = make_problem(args, 1)
     be, kind = cpu_reference_backend()
-    # calibrate, then size the per-step sample so that the whole run stays within ~90 s
-    t_probe, _ = time_cpu(be, p, 64)
-    per_site = t_probe / 64
-    budget = 90.0 / max(1, args.steps + args.warmup)
-    ns = int(max(64, min(s, budget / per_site / 1.5)))      # /1.5: std::map lookups slow down as it grows
+    # size the per-step sample so that the whole run stays within ~75 s, and a step within ~4 s
+    budget = min(4.0, 75.0 / max(1, args.steps + args.warmup))
+    ns, per_site = reference_sample_sites(be, p, s, budget)
     for _ in range(args.warmup):
         time_cpu(be, p, ns)
     t0 = time.perf_counter()
@@ -194,13 +256,18 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     upd = (n - 1) * ns * r
     val = upd * args.steps / dt
-    sample = f"first {ns} of {s} sites, all {n} tips, one logLikCpp per step (tree build + dictionary fill + pruning + reduction)"
+    sample = (f"first {ns} of {s} sites, all {n} tips, one logLikCpp per step (tree build + dictionary fill + pruning + "
+              f"reduction); the reference memoises (node, site) solutions, so its rate per update rises a little with the "
+              f"number of sites")
     lookups = (2 * n - 1) * ns
     memo = getattr(time_cpu, "dictionary", None)
+    cfg = config_dict(args, n, s, k, r, 1)
+    cfg["reference_sample"] = sample
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+           "scaling": "strong" if args.strong else "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict(args, n, s, k, r, 1),
+           "config": cfg,
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                             "host_cores": os.cpu_count(),
                             "dictionary_entries": memo, "dictionary_hit_rate": (1.0 - memo / lookups) if memo else None,
@@ -208,6 +275,8 @@ def run_reference(args, rank, world):
                                     "clusterFunArmadillo.cpp:4,38); it cannot use more host threads"},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_extras:
+        out["mcmc"] = reference_mcmc(p, s, per_site)
     emit(json.dumps(out))
 
 
@@ -275,6 +344,17 @@ def run_ours(args, rank, world, local_rank):
     # ---------------------------------------------------------------- device-resident leg
     res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
     h, ll0 = res["solutionPointer"], res["logLik"]
+    single_ll = None
+    if world > 1 and rank == 0:
+        # the sharded value must be the single-GPU value, bit for bit: one evaluation of the whole alignment on this
+        # rank's device (one slot of partials: 33 GB for config 3), outside every timed region
+        one = Engine(device=local_rank, fuse_tips=args.fuse)
+        full = one.getConvertedAlignment(list(synth.STATES), p.chars)
+        r1 = one.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, full, p.n, S_total, p.w_idx, p.b_idx)
+        single_ll = r1["logLik"]
+        one.finalDeallocate(r1["solutionPointer"])
+        del full
+        assert single_ll == ll0, ("sharded log-likelihood differs from the single-GPU one", ll0, single_ll)
     sampler.mark = "warm"
     for _ in range(max(3, args.warmup)):
         ll = eng.recomputeAll(h, W, B, p.pi)
@@ -314,16 +394,29 @@ def run_ours(args, rank, world, local_rank):
     # the kernel really has to move (`moved_*`, counted by the engine for the plan it ran) and the ncu DRAM traffic say
     # by how much.  See DESIGN.md §3.
     traffic, traffic_src = ncu_traffic(args.workload, args.data)
-    roofline = {"bound": "hbm", "kernel": "k_prune", "achieved": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9 / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_update": bytes_unfused / ((n - 1) * s_local * r),
-                "algorithmic_bytes_per_launch": bytes_unfused / max(1, st1["last_prune_launches"]),
+    # ... which is why the roof that binds is the fp64 pipe's DMUL / DADD issue rate (no FMA: the reference's evaluation
+    # order rounds products and sums separately), measured on this GPU right now by tools/fp64_peak.cu
+    ops_eval = st1["last_fp64_ops"]
+    pk64 = fp64_peak(local_rank)
+    tfl = ops_eval * args.steps / (prune_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64_issue", "kernel": "k_prune", "achieved": tfl, "peak": (pk64 / 1e12 if pk64 else None),
+                "unit": "TFLOP/s", "frac": (tfl / (pk64 / 1e12) if pk64 else None),
+                "peak_source": "tools/fp64_peak.cu on this GPU, this run: DMUL + DADD per second, 8 independent chains per "
+                               "thread, every SM at full occupancy (FMA is not available to this kernel)",
+                "fp64_ops_per_update": ops_eval / ((n - 1) * s_local * r),
+                "fp64_ops_per_launch": ops_eval / max(1, st1["last_prune_launches"]),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "launches_per_step": int(st1["last_prune_launches"]), "kernel_ms_per_step": prune_ms / args.steps,
                 "kernel_share_of_step": prune_ms / ms,
-                "moved_bytes_per_update": bytes_eval / ((n - 1) * s_local * r), "moved_gbs": achieved,
-                "moved_frac_of_peak": achieved / peak,
-                "stored_vertices": int(st1["last_stored_vertices"]), "fused_vertices": int(st1["last_fused_vertices"])}
+                "stored_vertices": int(st1["last_stored_vertices"]), "fused_vertices": int(st1["last_fused_vertices"]),
+                "hbm_equiv": {"achieved": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": bytes_unfused * args.steps / (prune_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                              "algorithmic_bytes_per_update": bytes_unfused / ((n - 1) * s_local * r),
+                              "algorithmic_bytes_per_launch": bytes_unfused / max(1, st1["last_prune_launches"]),
+                              "moved_bytes_per_update": bytes_eval / ((n - 1) * s_local * r), "moved_gbs": achieved,
+                              "moved_frac_of_peak": achieved / peak,
+                              "note": "algorithmic bytes = every vertex stored (68 B per update); small-clade fusion "
+                                      "never moves most of them, so frac > 1 is not a bandwidth fraction"}}
     kernel_name = "k_prune"
     eng.finalDeallocate(h)
 
@@ -358,7 +451,10 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(p, n, s, r)
+        cpu = cpu_baseline(p, n, s, r, with_mcmc=not args.no_extras)
+        if cpu.get("mcmc") and extras.get("mcmc"):
+            extras["mcmc"]["vs_reference_all_sites_estimate"] = (extras["mcmc"]["iterations_per_sec"] /
+                                                                  cpu["mcmc"]["iterations_per_sec_all_sites_estimate"])
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -375,8 +471,11 @@ def run_ours(args, rank, world, local_rank):
                "roofline": roofline,
                "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
                "sharded_exchange": ({"in_kernel": eng.fast, "host_collectives": eng.collectives} if world > 1 else None),
-               "chain": {"rescaled_sites": int(st1["last_chain_sites"]), "exponent_rows": int(st1["last_chain_rows"]), "rescaled_tiles": int(st1["last_active_tiles"])},
-               "cpu_baseline": cpu, "logLik": ll0, "device_bytes": int(dev_bytes),
+               "chain": {"resolved_by": {0: "no site rescaled", 1: "certificate", 2: "literal walk"}.get(int(st1["last_cert"])),
+                         "walked_sites": int(st1["last_chain_sites"]), "walked_rows": int(st1["last_chain_rows"]),
+                         "rescaled_tiles": int(st1["last_active_tiles"]), "dominant_rate": int(st1["last_cert_rate"])},
+               "cpu_baseline": cpu, "logLik": ll0, "single_gpu_logLik_equal": (None if single_ll is None else bool(single_ll == ll0)),
+               "device_bytes": int(dev_bytes),
                "levels": int(st1["last_levels"])}
         out.update(extras)
         emit(json.dumps(out))
@@ -395,6 +494,10 @@ def extra_legs(args, eng, p, al, n, s, k, r, world=1):
     if world > 1:
         return mcmc_leg(args, eng, p, al, out, "site-sharded: every rank runs the same driver in lock-step")
     if args.mcmc_only:
+        return mcmc_leg(args, eng, p, al, out, "single GPU")
+    if args.workload != "config2":
+        out["also_config2"] = config2_leg(args, eng)
+    if not args.all_extras:
         return mcmc_leg(args, eng, p, al, out, "single GPU")
     other = "iid" if args.data == "evolved" else "evolved"
     q = Problem(load_packaged(), n, s, k, r, other, args.tree, seed=args.seed)
@@ -416,6 +519,39 @@ def extra_legs(args, eng, p, al, n, s, k, r, world=1):
                              "logLik": res["logLik"]}
     eng.finalDeallocate(h)
     return mcmc_leg(args, eng, p, al, out, "single GPU")
+
+
+def config2_leg(args, eng):
+    """Round 1's headline shape (1,000 x 10,000, 20 clusters): device-resident and end-to-end, same definitions."""
+    import torch
+    from dmphyclus_b200 import synth
+    from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
+    n, s, k, r = CONFIGS["config2"]
+    q = Problem(load_packaged(), n, s, k, r, args.data, args.tree, seed=args.seed)
+    masks = eng.getConvertedAlignment(list(synth.STATES), q.chars)
+    pinned = torch.empty(masks.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = masks
+    alq = pinned.numpy()
+    W, B = q.W[4], q.B[4]
+    res = eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)
+    h = res["solutionPointer"]
+    for _ in range(5):
+        eng.recomputeAll(h, W, B, q.pi)
+    steps = 50
+    eng.timer_begin(h)
+    for _ in range(steps):
+        eng.recomputeAll(h, W, B, q.pi)
+    ms = eng.timer_end(h) / steps
+    eng.finalDeallocate(h)
+    for _ in range(3):
+        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+    t0 = time.perf_counter()
+    for _ in range(20):
+        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+    e2e = (time.perf_counter() - t0) / 20 * 1e3
+    upd = (n - 1) * s * r
+    return {"workload": f"config2: {n} seqs x {s} sites, {k} clusters, {r} rate categories", "value": upd / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "e2e_value": upd / (e2e * 1e-3), "e2e_ms_per_step": e2e, "logLik": res["logLik"]}
 
 
 def mcmc_leg(args, eng, p, al, out, how):
@@ -521,10 +657,10 @@ def proposal_sweep(args):
                      "one_by_one_ms_per_proposal": one, "one_by_one_proposals_per_s": 1e3 / one}))
 
 
-def cpu_baseline(p, n, s, r):
+def cpu_baseline(p, n, s, r, with_mcmc=True):
     from oracle.oracle import Oracle
     be, kind = cpu_reference_backend()
-    ns = min(s, 5000)
+    ns, per_site = reference_sample_sites(be, p, s, 12.0)
     dt, _ = time_cpu(be, p, ns)
     memo = getattr(time_cpu, "dictionary", None)
     out = {"value": (n - 1) * ns * r / dt, "unit": UNIT, "cores": 1, "kind": kind,
@@ -532,11 +668,14 @@ def cpu_baseline(p, n, s, r):
            "host_cores": os.cpu_count(),
            "dictionary_entries": memo, "dictionary_hit_rate": (1.0 - memo / ((2 * n - 1) * ns)) if memo else None}
     # the dense oracle port: 1 thread, and OpenMP over sites on every host core (what numLikThreads advertised)
-    dt1, _ = time_cpu(Oracle(threads=1), p, s)
+    nd = int(min(s, max(256, 4.0e8 // ((n - 1) * r))))        # ~8 s single-threaded, a few GB of host memory
+    dt1, _ = time_cpu(Oracle(threads=1), p, nd)
     nthr = os.cpu_count() or 1
-    dtn, _ = time_cpu(Oracle(threads=nthr), p, s)
-    out["port_dense_1thread"] = {"value": (n - 1) * s * r / dt1, "unit": UNIT, "cores": 1, "sample": f"all {s} sites"}
-    out["port_dense_openmp"] = {"value": (n - 1) * s * r / dtn, "unit": UNIT, "cores": nthr, "sample": f"all {s} sites"}
+    dtn, _ = time_cpu(Oracle(threads=nthr), p, nd)
+    out["port_dense_1thread"] = {"value": (n - 1) * nd * r / dt1, "unit": UNIT, "cores": 1, "sample": f"first {nd} of {s} sites"}
+    out["port_dense_openmp"] = {"value": (n - 1) * nd * r / dtn, "unit": UNIT, "cores": nthr, "sample": f"first {nd} of {s} sites"}
+    if with_mcmc:
+        out["mcmc"] = reference_mcmc(p, s, per_site)
     return out
 
 

@@ -32,5 +32,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_fp64_peak(force: bool = False) -> str:
+    """tools/libfp64peak.so: the DMUL / DADD issue-rate microbenchmark bench.py measures its roofline peak with."""
+    src = os.path.join(ROOT, "tools", "fp64_peak.cu")
+    lib = os.path.join(ROOT, "tools", "libfp64peak.so")
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(src):
+        return lib
+    res = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+                          "-o", lib, src], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return lib
+
+
 if __name__ == "__main__":
+    build_fp64_peak(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -452,7 +452,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
       cc.kids = ht.kids; cc.within = ht.within; cc.cur = curBefore; cc.fuse = ht.fuseTips;
       cc.meta.levelStart = p.levelStart;
       cc.meta.chainLevels = p.chainLevels; cc.meta.materialised = p.materialised;
-      cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps;
+      cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps; cc.meta.fp64Ops = p.fp64Ops;
       cc.meta.tasks.clear(); cc.metaTasks = nT;
       cc.valid = true;
       t->graphVersion++;
@@ -490,7 +490,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     t->gatherPrelaunched = true;
     t->pubExpected++;
     t->graphReplays++;
-    t->st.kernel_launches += t->st.last_prune_launches + (predicted ? 3 : 1);
+    t->st.kernel_launches += t->st.last_prune_launches + (predicted ? 2 : 1);
   } else if ((rc = runPlan(t))) {
     return rc;
   }
@@ -501,6 +501,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   // one mask byte per tip operand; exponents move only where something rescaled (not counted)
   t->st.last_algorithmic_bytes = (unsigned long long)t->S * t->R * 32ull * (unsigned long long)(nTasks + storedReads) +
                                  (unsigned long long)t->S * (unsigned long long)tipReads;
+  t->st.last_fp64_ops = (unsigned long long)meta->fp64Ops * t->S * t->R;
   t->st.last_stored_vertices = nTasks;
   t->st.last_fused_vertices = (int)fusedOps;
   const auto h1 = std::chrono::steady_clock::now();
@@ -559,14 +560,9 @@ int launchFinal(dmpc_tree* t, int mode, int reduceAll, bool publish) {
   return DMPC_OK;
 }
 
-// k_cert + k_final(mode 2): the chain resolved by certificate, result published by the final kernel
+// k_final(mode 2): the per-site terms under the certificate the gather's last block issued; publishes the result
 int launchCertFinal(dmpc_tree* t) {
-  const int reduceAll = t->rv.comm.world > 1 ? 2 : 1;
-  if (t->rv.RP == 4) k_cert<4, false><<<1, TILE, 0, t->stream>>>(t->dv, t->rv);
-  else k_cert<8, false><<<1, TILE, 0, t->stream>>>(t->dv, t->rv);
-  t->st.kernel_launches++;
-  if (!t->capturing) CUDA_TRY(cudaGetLastError());
-  return launchFinal(t, 2, reduceAll, true);
+  return launchFinal(t, 2, t->rv.comm.world > 1 ? 2 : 1, true);
 }
 
 // What follows the pruning of an evaluation.  Usually no site rescaled last time and the gather alone finishes (and
@@ -677,8 +673,8 @@ void noteChain(dmpc_tree* t, bool anyActive) {
 }
 
 // ComputeLoglik's reduction (AugTree.cpp:296-325).  k_root_gather finishes the evaluation by itself when no site
-// rescaled anywhere; otherwise k_cert resolves the cross-locus chain by certificate and k_final adds the terms up
-// (both queued behind the gather already when the previous evaluation had rescaled sites); only when the certificate
+// rescaled anywhere; otherwise the gather's last block resolves the cross-locus chain by certificate and k_final adds the terms up
+// (queued behind the gather already when the previous evaluation had rescaled sites); only when the certificate
 // does not hold do the literal chain kernel and a second final pass run.
 // Deferred (site-sharded) mode without peer mailboxes: stops after the gather; the chunk sums it produced — valid when
 // this shard holds no rescaled site and the exponent vector enters as zeros — are already on the host for
@@ -1434,10 +1430,8 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       // and, if for some proposal it does not hold, the literal chain + final over the batch (mode 1) afterwards
       stat.resize(nb); invalid.resize(nb);
       if (chainMode) {
-        if (t->rv.RP == 4) k_cert<4, true><<<nb, TILE, 0, t->stream>>>(t->dv, rb);
-        else k_cert<8, true><<<nb, TILE, 0, t->stream>>>(t->dv, rb);
         k_final<true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, 2, 1, 0, pv);
-        t->st.kernel_launches += 4;
+        t->st.kernel_launches += 3;
       } else {
         k_final<true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, 0, 1, 0, pv);
         t->st.kernel_launches += 3;
@@ -1505,7 +1499,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
       if ((rc = dmpc_get_stats(g->shards[i], &s1))) return rc;
       if (i == 0) { *out = s1; continue; }
       out->updates += s1.updates; out->kernel_launches += s1.kernel_launches; out->last_updates += s1.last_updates;
-      out->device_bytes += s1.device_bytes; out->last_algorithmic_bytes += s1.last_algorithmic_bytes;
+      out->device_bytes += s1.device_bytes; out->last_algorithmic_bytes += s1.last_algorithmic_bytes; out->last_fp64_ops += s1.last_fp64_ops;
       out->last_active_tiles += s1.last_active_tiles; out->last_chain_sites += s1.last_chain_sites; out->last_chain_rows += s1.last_chain_rows;
       out->last_eval_ms = std::max(out->last_eval_ms, s1.last_eval_ms); out->last_prune_ms = std::max(out->last_prune_ms, s1.last_prune_ms);
       out->last_host_total_us = std::max(out->last_host_total_us, s1.last_host_total_us);

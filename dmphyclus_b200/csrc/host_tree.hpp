@@ -257,6 +257,8 @@ struct HostTree {
     std::vector<int32_t> tipList;                // tips read by the fused programs, task by task
     std::vector<int> levelStart;
     long long storedReads = 0, tipReads = 0, fusedOps = 0;
+    long long fp64Ops = 0;                       // DMUL + DADD per (site, rate) of the whole plan: a 4x4 mat-vec is 16 + 12, the
+                                                 // product of the two child terms 4; a tip's term is a table look-up
     int chainLevels = 0;                         // trailing single-task levels that k_walk evaluates (0 or >= CHAIN_MIN)
     int materialised = 0;                        // fused-size clades evaluated as stored tasks for that chain (level 0 of the plan)
     bool uses[2] = {false, false};               // slots this plan writes
@@ -292,6 +294,7 @@ struct HostTree {
     t.vertex = u - numTips;
     p.tokens.push_back(t);
     p.fusedOps++;
+    p.fp64Ops += (t.op & 7) == OP_CHERRY ? 4 : (t.op & 7) == OP_REGTIP ? 32 : 60;
     p.uses[slot] = true;
     if (mutate) { cur[u] = (uint8_t)slot; touched[u] = 1; solved[u] = 1; }
   }
@@ -318,6 +321,7 @@ struct HostTree {
       }
     }
     k.nTips = (int)p.tipList.size() - k.tipOff;
+    p.fp64Ops += 4 + 28 * ((k.flags & TF_C0TIP ? 0 : 1) + (k.flags & TF_C1TIP ? 0 : 1));
     if (within[kids[2 * v]]) k.flags |= TF_WITHIN;      // AugTree.cpp:125: the FIRST child's flag picks the matrix set
     return k;
   }
@@ -362,7 +366,7 @@ struct HostTree {
   void plan(Plan& p) {
     allInvalid = false;
     p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
-    p.storedReads = p.tipReads = p.fusedOps = 0;
+    p.storedReads = p.tipReads = p.fusedOps = p.fp64Ops = 0;
     p.chainLevels = p.materialised = 0;
     p.uses[0] = p.uses[1] = false;
     if (solved[root()]) { p.levelStart.push_back(0); return; }

@@ -59,8 +59,8 @@ struct DevStatus {
   unsigned ticket, ticket2;     // last-block detection of k_final / k_root_gather
   int xok;                      // site-sharded runs: 1 = the in-kernel peer exchange produced ll, 0 = host protocol needed,
                                 //   2 = a peer never answered, -1 = no exchange attempted
-  int cert;                     // chain mode: CERT_* — how k_cert resolved the cross-locus exponent chain
-  int chainSites, chainRows;    // what the literal walker (k_chain, or k_cert's prefix) walked: rescaled sites and rows
+  int cert;                     // chain mode: CERT_* — how certify() resolved the cross-locus exponent chain
+  int chainSites, chainRows;    // what the literal walker (k_chain, or certify()'s prefix) walked: rescaled sites and rows
   unsigned pubSeq;              // number of times a root kernel has published this block to the host mirror
   int certL0;                   // rescaled sites of the literal prefix (tiles 0 .. certTile)
   int certRate;                 // the dominant rate category of the certified regime
@@ -68,7 +68,7 @@ struct DevStatus {
 };
 static_assert(sizeof(DevStatus) == 64, "status block = 16 words");
 enum : int {
-  CERT_NONE = 0,                // k_cert has not run (or had nothing to do: no site rescaled anywhere)
+  CERT_NONE = 0,                // certify() has not run (or had nothing to do: no site rescaled anywhere)
   CERT_OK = 1,                  // every tile behind the literal prefix is certified: k_final uses the closed form there
   CERT_LITERAL = 2              // the certificate does not hold (or the prefix is too long): k_chain + k_final(mode 1)
 };
@@ -80,7 +80,7 @@ enum : int {
 constexpr int CW = 8;            // ranks
 constexpr int XHDR = 4;          // doubles in front of the chunk sums of a message
 enum : int { XF_ACTIVE = 1 };    // message flags
-// tile record of the chain certificate (see k_cert): nAct, ops, absSum, 0, S_r[RP], maxPre[RP][RP]
+// tile record of the chain certificate (see certify): nAct, ops, absSum, 0, S_r[RP], maxPre[RP][RP]
 __host__ __device__ constexpr int xrec(int RP) { return 4 + RP + RP * RP; }
 constexpr int XREC_MAX = xrec(RMAX);
 struct CommView {
@@ -106,10 +106,10 @@ struct RootView {
   float* carryOut;              // [RMAX]
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [T * CPT] sums of RCH consecutive sites (the first nChunks are real)
-  double* tileRec;              // [T][xrec(RP)] per-tile records of the chain certificate (k_root_gather -> k_cert)
+  double* tileRec;              // [T][xrec(RP)] per-tile records of the chain certificate (k_root_gather -> certify)
   int nChunks;                  // ceil(S / RCH)
   int publishAtGather;          // 1: the gather's last block publishes the status (nothing is queued behind it)
-  int certOn;                   // 0: k_cert always answers CERT_LITERAL (tests compare both paths)
+  int certOn;                   // 0: certify() always answers CERT_LITERAL (tests compare both paths)
   DevStatus* st;                // everything the host reads back after an evaluation, in one copy
   DevStatus* hostSt;            // mapped pinned mirror (or null): the last root kernel stores the finished block there
                                 // and bumps its pubSeq, so that the host can pick the result up by polling instead of
@@ -684,6 +684,7 @@ __device__ __forceinline__ void tile_chunk_sums(double ll, double* s_red, double
     __syncthreads();
   }
   if ((tid & (RCH - 1)) == 0) chunkOut[tid / RCH] = s_red[tid];
+  __syncthreads();          // every chunk sum is written before the caller's thread 0 fences and takes its ticket
 }
 
 // The fused collective of a site-sharded run (called by the LAST block of k_root_gather / k_final, TILE threads).
@@ -691,8 +692,8 @@ __device__ __forceinline__ void tile_chunk_sums(double ll, double* s_red, double
 // once every peer's message of the same sequence number has arrived, and no rank reports a rescaled site, each rank adds
 // ALL chunk sums in the fixed global order (the order of reduce_chunks_device over the concatenated list) and has the
 // same log-likelihood, bit for bit, as a single GPU would — without any host-side collective.  The tile records
-// (recs != nullptr: nTiles x XR doubles) are what k_cert needs from every rank when some site did rescale.
-// Returns 1 = ll written, 0 = some rank holds a rescaled site (k_cert + k_final must run), 2 = timeout.
+// (recs != nullptr: nTiles x XR doubles) are what certify() needs from every rank when some site did rescale.
+// Returns 1 = ll written, 0 = some rank holds a rescaled site (certify + k_final must run), 2 = timeout.
 __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bool quiet, double* s_red, const double* recs,
                                                  int nTiles, int XR) {
   __shared__ unsigned s_seq;
@@ -750,6 +751,244 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
 }
 
 // ------------------------------------------------------------------------------------------------
+// certify: the chain WITHOUT walking it, wherever that can be proven exact.
+//
+// The literal chain (k_chain; AugTree.cpp:306-323) keeps an fp32 vector c, adds every site's exponents to it (vertex
+// order), subtracts its maximum m, and the site's term is log(mean_r(rootdot_r * expf(c_r))) + m.  In exact arithmetic
+// c_r = E_r - max_q E_q with E the running sums of the sites' exponent sums.  Rescale exponents are ~ -345 each and
+// the rate categories do not rescale equally often, so after a few rescaled sites ONE category d leads by far more
+// than 104 — and from then on expf(c_r) == 0.0f exactly for every r != d, c_d == 0.0f exactly, and the term of a site
+// is log(rootdot_d / R) + (fp32 sum, from zero, of that site's own category-d exponents): no history at all.
+// The certificate proves, tile by tile, that the literal fp32 chain is in that regime:
+//   * since the maximum entry of c is exactly 0, every c_r equals a DIFFERENCE c_r - c_d*, and differences only pick up
+//     the roundings of the additions and subtractions themselves — (2K+1) * 2^-24 * |value| per site with K rows —
+//     which add up (no amplification).  B(t) = kappa * sum_{t' <= t} 2^-22 * ops(t') * (gap at entry + abs sums + 1)
+//     bounds |c_r - (E_r - E_d)| anywhere up to the end of tile t (kappa = exp(2^-22 * total ops) covers B feeding
+//     back into the magnitudes);
+//   * tile t is certified for d when for every r != d:  (E_r - E_d at entry) + maxPre[d][r](t) + B(t) < -128.
+// All tiles behind the last uncertified one take the closed form in k_final; tiles 0 .. certTile (always including
+// tile 0: the chain starts from zeros) are walked literally here, by one thread, from rows staged in shared memory —
+// typically a few dozen sites.  If the regime never establishes itself (two categories neck and neck, tiny trees) or
+// the prefix is long, the answer is CERT_LITERAL and the host runs k_chain as before.  Runs in the LAST block of
+// k_root_gather (all tile records are complete then; in a sharded run, right after the exchange), TILE threads.  In a
+// site-sharded run every rank holds every rank's tile records (the gather's exchange) and reaches the same verdict; the
+// literal prefix must then lie inside rank 0's block.
+constexpr int CERT_MAXLIT = 2048;    // rescaled sites the literal prefix may hold
+
+// s_rows: 16 KB of shared memory lent by the caller (the literal prefix's rows are staged there)
+template <int RP>
+__device__ __forceinline__ void certify(const DevView& v, const RootView& rv, float4* s_rows) {
+  constexpr int XR = xrec(RP);
+  constexpr int V = RP / 4;
+  constexpr int CERT_ROWCAP = 1024 / V;    // rows of one literal tile staged in shared memory (more: read from global memory)
+  __shared__ double s_w[TILE / 32][RP + 2];
+  __shared__ double s_tot[RP + 2];
+  __shared__ long long s_key[TILE / 32];
+  __shared__ int s_base[CW + 1];
+  __shared__ const volatile double* s_rec[CW];
+  __shared__ int s_cnt[TILE], s_site[TILE];
+  __shared__ int s_scan[2][TILE / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, R = v.R;
+  const CommView& cm = rv.comm;
+  const bool sharded = cm.world > 1;
+  DevStatus* const st = rv.st;
+  const bool retry = *(volatile int*)&st->overflow > rv.Kcap || (*(volatile int*)&st->violation != 0 && !rv.exactMode);
+  if (retry || (!sharded && *(volatile int*)&st->nact == 0) || (sharded && *(volatile int*)&st->xok != 0)) return;   // cert stays CERT_NONE
+  if (tid == 0) {
+    if (sharded) {
+      const unsigned seq = *cm.seq;                                   // the gather's exchange
+      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)(seq & 1) * CW * cm.width;
+      int b = 0;
+      for (int p = 0; p < cm.world; p++) {
+        const volatile double* m = in + (size_t)p * cm.width;
+        const int nT = (int)m[2];
+        s_base[p] = b;
+        // a quiet rank sends no records; its tile count is then unknown here, and irrelevant: zero records change nothing
+        s_rec[p] = nT > 0 ? m + XHDR + (int)m[1] : nullptr;
+        b += nT;
+      }
+      for (int p = cm.world; p <= CW; p++) s_base[p] = b;
+    } else {
+      s_base[0] = 0;
+      for (int p = 1; p <= CW; p++) s_base[p] = v.T;
+      s_rec[0] = rv.tileRec;
+    }
+  }
+  __syncthreads();
+  const int nRanks = sharded ? cm.world : 1;
+  const int Ttot = s_base[nRanks];
+  auto recOf = [&](int g) -> const volatile double* {
+    int p = 0;
+#pragma unroll
+    for (int q = 1; q < CW; q++) if (q < nRanks && g >= s_base[q]) p = q;
+    return s_rec[p] + (size_t)(g - s_base[p]) * XR;
+  };
+  // block-wide sums / scans of RP + 2 doubles at once (one barrier pair)
+  auto blockTotals = [&](double (&x)[RP + 2]) {
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1)
+#pragma unroll
+      for (int i = 0; i < RP + 2; i++) x[i] += __shfl_xor_sync(0xffffffffu, x[i], q);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < RP + 2; i++) s_w[wid][i] = x[i];
+    }
+    __syncthreads();
+    if (tid < RP + 2) { double a = 0.0; for (int w = 0; w < TILE / 32; w++) a += s_w[w][tid]; s_tot[tid] = a; }
+    __syncthreads();
+  };
+  // pass 1: totals -> the dominant category and kappa
+  {
+    double x[RP + 2];
+#pragma unroll
+    for (int i = 0; i < RP + 2; i++) x[i] = 0.0;
+    for (int g = tid; g < Ttot; g += TILE) {
+      const volatile double* rec = recOf(g);
+#pragma unroll
+      for (int r = 0; r < RP; r++) x[r] += rec[4 + r];
+      x[RP] += rec[1];
+    }
+    blockTotals(x);
+  }
+  int dom = 0;
+  for (int r = 1; r < R; r++) if (s_tot[r] > s_tot[dom]) dom = r;
+  const double kappa = exp(s_tot[RP] * 0x1p-22) * (1.0 + 1e-9);
+  __syncthreads();
+  // pass 2: per tile, entry sums (exclusive scan), the rounding bound (inclusive scan), the verdict
+  double carry[RP + 2];                           // running: E_r, sum of u*g, active sites
+#pragma unroll
+  for (int i = 0; i < RP + 2; i++) carry[i] = 0.0;
+  long long best = -1;                            // (last uncertified tile) << 32 | active sites up to and including it
+  for (int base = 0; base < Ttot; base += TILE) {
+    const int g = base + tid;
+    const bool in = g < Ttot;
+    const volatile double* rec = in ? recOf(g) : nullptr;
+    double Sr[RP], ops = 0.0, ab = 0.0, na = 0.0;
+#pragma unroll
+    for (int r = 0; r < RP; r++) Sr[r] = in ? rec[4 + r] : 0.0;
+    if (in) { na = rec[0]; ops = rec[1]; ab = rec[2]; }
+    // inclusive scans of S_r and nAct
+    double incl[RP + 1];
+#pragma unroll
+    for (int r = 0; r < RP; r++) incl[r] = Sr[r];
+    incl[RP] = na;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+      for (int i = 0; i < RP + 1; i++) { const double y = __shfl_up_sync(0xffffffffu, incl[i], d); if (lane >= d) incl[i] += y; }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < RP + 1; i++) s_w[wid][i] = incl[i];
+    }
+    __syncthreads();
+    double tot[RP + 1];
+#pragma unroll
+    for (int i = 0; i < RP + 1; i++) {
+      tot[i] = 0.0;
+#pragma unroll
+      for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][i]; if (w < wid) incl[i] += q; tot[i] += q; }
+    }
+    __syncthreads();
+    double entry[RP], emax = -1e300, emin = 1e300;
+#pragma unroll
+    for (int r = 0; r < RP; r++)
+      if (r < R) { entry[r] = carry[r] + incl[r] - Sr[r]; emax = fmax(emax, entry[r]); emin = fmin(emin, entry[r]); }
+    double ug = in ? 0x1p-22 * ops * ((emax - emin) + ab + 1.0) : 0.0;
+    double ugi = ug;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, ugi, d); if (lane >= d) ugi += y; }
+    if (lane == 31) s_w[wid][RP + 1] = ugi;
+    __syncthreads();
+    double ugTot = 0.0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][RP + 1]; if (w < wid) ugi += q; ugTot += q; }
+    const double B = kappa * (carry[RP] + ugi);
+    bool bad = false;
+    if (in) {
+#pragma unroll
+      for (int r = 0; r < RP; r++)
+        if (r < R && r != dom) bad |= !(entry[r] - entry[dom] + rec[4 + RP + dom * RP + r] + B < -128.0);
+    }
+    long long key = bad ? (((long long)g << 32) | (long long)(unsigned)(carry[RP + 1] + incl[RP])) : -1;
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, key, q); key = o > key ? o : key; }
+    if (lane == 0) s_key[wid] = key;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) best = s_key[w] > best ? s_key[w] : best;
+#pragma unroll
+    for (int r = 0; r < RP; r++) carry[r] += tot[r];
+    carry[RP] += ugTot;
+    carry[RP + 1] += tot[RP];
+    __syncthreads();
+  }
+  const int tb = (int)(best >> 32), L0 = (int)(best & 0xffffffffLL);
+  const bool ok = rv.certOn && best >= 0 && L0 <= CERT_MAXLIT && tb < s_base[1];
+  const int myBase = sharded ? s_base[cm.rank] : 0;
+  if (tid == 0) {
+    st->cert = ok ? CERT_OK : CERT_LITERAL;
+    st->certRate = dom;
+    st->certTile = tb - myBase;                   // local tile index: every local tile above it is certified
+    st->certL0 = L0;
+    if (ok) { st->chainSites = 0; st->chainRows = 0; }
+  }
+  if (!ok || (sharded && cm.rank != 0)) return;
+
+  // the literal prefix: tiles 0 .. tb of this (first) block of sites, one tile per pass
+  float c[RP];
+#pragma unroll
+  for (int r = 0; r < RP; r++) c[r] = 0.0f;
+  int actBase = 0, rowsWalked = 0;
+  for (int lt = 0; lt <= tb && lt < v.T; lt++) {
+    const int s = lt * TILE + tid;
+    const int km = s < v.S ? min(rv.kmax[s], rv.Kcap) : 0;
+    const int actv = km > 0;
+    int ic = actv, ir = km;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tc = __shfl_up_sync(0xffffffffu, ic, d), tr = __shfl_up_sync(0xffffffffu, ir, d);
+      if (lane >= d) { ic += tc; ir += tr; }
+    }
+    if (lane == 31) { s_scan[0][wid] = ic; s_scan[1][wid] = ir; }
+    __syncthreads();
+    int nA = 0, nR = 0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; w++) { if (w < wid) { ic += s_scan[0][w]; ir += s_scan[1][w]; } nA += s_scan[0][w]; nR += s_scan[1][w]; }
+    if (s < v.S) rv.posIncl[s] = actBase + ic;
+    const bool staged = nR <= CERT_ROWCAP;
+    if (actv) {
+      s_cnt[ic - 1] = km; s_site[ic - 1] = s;
+      if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(rv.elist + (size_t)s * rv.Kcap * RP);
+        for (int j = 0; j < km * V; j++) s_rows[(size_t)(ir - km) * V + j] = src[j];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int q = 0;
+      for (int i = 0; i < nA; i++) {
+        const int cnt = s_cnt[i];
+        const float* rows = staged ? reinterpret_cast<const float*>(s_rows) + (size_t)q * RP : rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
+        for (int j = 0; j < cnt; j++)
+#pragma unroll
+          for (int r = 0; r < RP; r++) if (r < R) c[r] = __fadd_rn(c[r], rows[j * RP + r]);
+        q += cnt;
+        float m = c[0];
+#pragma unroll
+        for (int r = 1; r < RP; r++) if (r < R) m = fmaxf(m, c[r]);
+        float* co = rv.cout + (size_t)(actBase + i) * RP;
+#pragma unroll
+        for (int r = 0; r < RP; r++) if (r < R) { c[r] = __fsub_rn(c[r], m); co[r] = c[r]; }
+        rv.mxo[actBase + i] = m;
+      }
+    }
+    actBase += nA; rowsWalked += nR;
+    __syncthreads();
+  }
+  if (tid == 0) { st->chainSites = actBase; st->chainRows = rowsWalked; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4a root_gather: per site tile, dot(root, limProbs) and the per-site list of non-zero rescale exponents in
 // vertex-id order (the order AugTree.cpp:309-315 adds them in).  Only vertices whose tile flag is set are read:
 // the flagged vertices of each 128-vertex window are compacted (in id order) into shared memory, then visited
@@ -773,7 +1012,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   const int pb = BATCH ? blockIdx.y : 0;           // proposal of a batch
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   constexpr int NV = 16;                           // vertices per thread and pass of the (non-batch) flag scan
-  __shared__ int s_list[BATCH ? TILE : TILE * NV];
+  __shared__ __align__(16) int s_list[TILE * NV];   // (also lent to certify() as its 16 KB row stage)
   __shared__ int s_listJ[BATCH ? TILE : 1];
   __shared__ double s_red[TILE];
   __shared__ bool s_last;
@@ -960,7 +1199,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   }
   tile_chunk_sums(ll, s_red, rv.chunk + (size_t)tile * CPT);
   if (mode == 1) {
-    // The tile's record for the chain certificate (k_cert): with E_r = running sums of the sites' exponent sums,
+    // The tile's record for the chain certificate (certify): with E_r = running sums of the sites' exponent sums,
     //   S_r = the tile's total, maxPre[d][r] = max over the tile's sites (and 0) of (E_r - E_d) relative to the tile's
     //   entry, nAct / ops / absSum = what bounds the fp32 rounding the literal chain would commit inside the tile.
     constexpr int XR = xrec(RP);
@@ -1017,6 +1256,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       }
     }
   }
+  __syncthreads();                                 // the tile's record is complete
   if (tid == 0) {
     if (anyActive) atomicAdd(&rv.st->nact, 1);
     __threadfence();
@@ -1038,12 +1278,19 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
         return;
       }
       const int res = exchangeAndReduce(rv, rv.nChunks, quiet, s_red, (mode == 1 && !quiet) ? rv.tileRec : nullptr, gridDim.x, xrec(RP));
-      if (tid == 0) { rv.st->xok = res; rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
+      if (tid == 0) rv.st->xok = res;
+      __syncthreads();
+      if (res == 0 && mode == 1) certify<RP>(v, rv, reinterpret_cast<float4*>(s_list));
+      __syncthreads();
+      if (tid == 0) { rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
       return;
     }
     if (quiet) {
       const double tot = reduce_chunks_device(rv.chunk, rv.nChunks, s_red);
       if (tid == 0) rv.st->ll = tot;
+    } else if (mode == 1 && !retry) {
+      certify<RP>(v, rv, reinterpret_cast<float4*>(s_list));
+      __syncthreads();
     }
     if (tid == 0) { rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
   }
@@ -1262,252 +1509,14 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv0) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b' cert: the chain WITHOUT walking it, wherever that can be proven exact.
-//
-// The literal chain (k_chain; AugTree.cpp:306-323) keeps an fp32 vector c, adds every site's exponents to it (vertex
-// order), subtracts its maximum m, and the site's term is log(mean_r(rootdot_r * expf(c_r))) + m.  In exact arithmetic
-// c_r = E_r - max_q E_q with E the running sums of the sites' exponent sums.  Rescale exponents are ~ -345 each and
-// the rate categories do not rescale equally often, so after a few rescaled sites ONE category d leads by far more
-// than 104 — and from then on expf(c_r) == 0.0f exactly for every r != d, c_d == 0.0f exactly, and the term of a site
-// is log(rootdot_d / R) + (fp32 sum, from zero, of that site's own category-d exponents): no history at all.
-// The certificate proves, tile by tile, that the literal fp32 chain is in that regime:
-//   * since the maximum entry of c is exactly 0, every c_r equals a DIFFERENCE c_r - c_d*, and differences only pick up
-//     the roundings of the additions and subtractions themselves — (2K+1) * 2^-24 * |value| per site with K rows —
-//     which add up (no amplification).  B(t) = kappa * sum_{t' <= t} 2^-22 * ops(t') * (gap at entry + abs sums + 1)
-//     bounds |c_r - (E_r - E_d)| anywhere up to the end of tile t (kappa = exp(2^-22 * total ops) covers B feeding
-//     back into the magnitudes);
-//   * tile t is certified for d when for every r != d:  (E_r - E_d at entry) + maxPre[d][r](t) + B(t) < -128.
-// All tiles behind the last uncertified one take the closed form in k_final; tiles 0 .. certTile (always including
-// tile 0: the chain starts from zeros) are walked literally here, by one thread, from rows staged in shared memory —
-// typically a few dozen sites.  If the regime never establishes itself (two categories neck and neck, tiny trees) or
-// the prefix is long, the answer is CERT_LITERAL and the host runs k_chain as before.  One block per evaluation
-// (BATCH: per proposal).  In a site-sharded run every rank holds every rank's tile records (the gather's exchange) and
-// reaches the same verdict; the literal prefix must then lie inside rank 0's block.
-constexpr int CERT_ROWCAP = 1024;    // rows of one literal tile staged in shared memory (more: read from global memory)
-constexpr int CERT_MAXLIT = 2048;    // rescaled sites the literal prefix may hold
-
-template <int RP, bool BATCH>
-__global__ void __launch_bounds__(TILE) k_cert(DevView v, RootView rv0) {
-  const RootView rv = BATCH ? forProposal(rv0, blockIdx.x, v.Sp, v.T) : rv0;
-  constexpr int XR = xrec(RP);
-  constexpr int V = RP / 4;
-  __shared__ double s_w[TILE / 32][RP + 2];
-  __shared__ double s_tot[RP + 2];
-  __shared__ long long s_key[TILE / 32];
-  __shared__ int s_base[CW + 1];
-  __shared__ const volatile double* s_rec[CW];
-  __shared__ float4 s_rows[CERT_ROWCAP * V];
-  __shared__ int s_cnt[TILE], s_site[TILE];
-  __shared__ int s_scan[2][TILE / 32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, R = v.R;
-  const CommView& cm = rv.comm;
-  const bool sharded = cm.world > 1;
-  DevStatus* const st = rv.st;
-  const bool retry = st->overflow > rv.Kcap || (st->violation != 0 && !rv.exactMode);
-  if (retry || (!sharded && st->nact == 0) || (sharded && st->xok != 0)) return;     // cert stays CERT_NONE
-  if (tid == 0) {
-    if (sharded) {
-      const unsigned seq = *cm.seq;                                   // the gather's exchange
-      const volatile double* in = (volatile double*)cm.payload[cm.rank] + (size_t)(seq & 1) * CW * cm.width;
-      int b = 0;
-      for (int p = 0; p < cm.world; p++) {
-        const volatile double* m = in + (size_t)p * cm.width;
-        const int nT = (int)m[2];
-        s_base[p] = b;
-        // a quiet rank sends no records; its tile count is then unknown here, and irrelevant: zero records change nothing
-        s_rec[p] = nT > 0 ? m + XHDR + (int)m[1] : nullptr;
-        b += nT;
-      }
-      for (int p = cm.world; p <= CW; p++) s_base[p] = b;
-    } else {
-      s_base[0] = 0;
-      for (int p = 1; p <= CW; p++) s_base[p] = v.T;
-      s_rec[0] = rv.tileRec;
-    }
-  }
-  __syncthreads();
-  const int nRanks = sharded ? cm.world : 1;
-  const int Ttot = s_base[nRanks];
-  auto recOf = [&](int g) -> const volatile double* {
-    int p = 0;
-#pragma unroll
-    for (int q = 1; q < CW; q++) if (q < nRanks && g >= s_base[q]) p = q;
-    return s_rec[p] + (size_t)(g - s_base[p]) * XR;
-  };
-  // block-wide sums / scans of RP + 2 doubles at once (one barrier pair)
-  auto blockTotals = [&](double (&x)[RP + 2]) {
-#pragma unroll
-    for (int q = 16; q > 0; q >>= 1)
-#pragma unroll
-      for (int i = 0; i < RP + 2; i++) x[i] += __shfl_xor_sync(0xffffffffu, x[i], q);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < RP + 2; i++) s_w[wid][i] = x[i];
-    }
-    __syncthreads();
-    if (tid < RP + 2) { double a = 0.0; for (int w = 0; w < TILE / 32; w++) a += s_w[w][tid]; s_tot[tid] = a; }
-    __syncthreads();
-  };
-  // pass 1: totals -> the dominant category and kappa
-  {
-    double x[RP + 2];
-#pragma unroll
-    for (int i = 0; i < RP + 2; i++) x[i] = 0.0;
-    for (int g = tid; g < Ttot; g += TILE) {
-      const volatile double* rec = recOf(g);
-#pragma unroll
-      for (int r = 0; r < RP; r++) x[r] += rec[4 + r];
-      x[RP] += rec[1];
-    }
-    blockTotals(x);
-  }
-  int dom = 0;
-  for (int r = 1; r < R; r++) if (s_tot[r] > s_tot[dom]) dom = r;
-  const double kappa = exp(s_tot[RP] * 0x1p-22) * (1.0 + 1e-9);
-  __syncthreads();
-  // pass 2: per tile, entry sums (exclusive scan), the rounding bound (inclusive scan), the verdict
-  double carry[RP + 2];                           // running: E_r, sum of u*g, active sites
-#pragma unroll
-  for (int i = 0; i < RP + 2; i++) carry[i] = 0.0;
-  long long best = -1;                            // (last uncertified tile) << 32 | active sites up to and including it
-  for (int base = 0; base < Ttot; base += TILE) {
-    const int g = base + tid;
-    const bool in = g < Ttot;
-    const volatile double* rec = in ? recOf(g) : nullptr;
-    double Sr[RP], ops = 0.0, ab = 0.0, na = 0.0;
-#pragma unroll
-    for (int r = 0; r < RP; r++) Sr[r] = in ? rec[4 + r] : 0.0;
-    if (in) { na = rec[0]; ops = rec[1]; ab = rec[2]; }
-    // inclusive scans of S_r and nAct
-    double incl[RP + 1];
-#pragma unroll
-    for (int r = 0; r < RP; r++) incl[r] = Sr[r];
-    incl[RP] = na;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-#pragma unroll
-      for (int i = 0; i < RP + 1; i++) { const double y = __shfl_up_sync(0xffffffffu, incl[i], d); if (lane >= d) incl[i] += y; }
-    if (lane == 31) {
-#pragma unroll
-      for (int i = 0; i < RP + 1; i++) s_w[wid][i] = incl[i];
-    }
-    __syncthreads();
-    double tot[RP + 1];
-#pragma unroll
-    for (int i = 0; i < RP + 1; i++) {
-      tot[i] = 0.0;
-#pragma unroll
-      for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][i]; if (w < wid) incl[i] += q; tot[i] += q; }
-    }
-    __syncthreads();
-    double entry[RP], emax = -1e300, emin = 1e300;
-#pragma unroll
-    for (int r = 0; r < RP; r++)
-      if (r < R) { entry[r] = carry[r] + incl[r] - Sr[r]; emax = fmax(emax, entry[r]); emin = fmin(emin, entry[r]); }
-    double ug = in ? 0x1p-22 * ops * ((emax - emin) + ab + 1.0) : 0.0;
-    double ugi = ug;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, ugi, d); if (lane >= d) ugi += y; }
-    if (lane == 31) s_w[wid][RP + 1] = ugi;
-    __syncthreads();
-    double ugTot = 0.0;
-#pragma unroll
-    for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][RP + 1]; if (w < wid) ugi += q; ugTot += q; }
-    const double B = kappa * (carry[RP] + ugi);
-    bool bad = false;
-    if (in) {
-#pragma unroll
-      for (int r = 0; r < RP; r++)
-        if (r < R && r != dom) bad |= !(entry[r] - entry[dom] + rec[4 + RP + dom * RP + r] + B < -128.0);
-    }
-    long long key = bad ? (((long long)g << 32) | (long long)(unsigned)(carry[RP + 1] + incl[RP])) : -1;
-#pragma unroll
-    for (int q = 16; q > 0; q >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, key, q); key = o > key ? o : key; }
-    if (lane == 0) s_key[wid] = key;
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < TILE / 32; w++) best = s_key[w] > best ? s_key[w] : best;
-#pragma unroll
-    for (int r = 0; r < RP; r++) carry[r] += tot[r];
-    carry[RP] += ugTot;
-    carry[RP + 1] += tot[RP];
-    __syncthreads();
-  }
-  const int tb = (int)(best >> 32), L0 = (int)(best & 0xffffffffLL);
-  const bool ok = rv.certOn && best >= 0 && L0 <= CERT_MAXLIT && tb < s_base[1];
-  const int myBase = sharded ? s_base[cm.rank] : 0;
-  if (tid == 0) {
-    st->cert = ok ? CERT_OK : CERT_LITERAL;
-    st->certRate = dom;
-    st->certTile = tb - myBase;                   // local tile index: every local tile above it is certified
-    st->certL0 = L0;
-    if (ok) { st->chainSites = 0; st->chainRows = 0; }
-  }
-  if (!ok || (sharded && cm.rank != 0)) return;
-
-  // the literal prefix: tiles 0 .. tb of this (first) block of sites, one tile per pass
-  float c[RP];
-#pragma unroll
-  for (int r = 0; r < RP; r++) c[r] = 0.0f;
-  int actBase = 0, rowsWalked = 0;
-  for (int lt = 0; lt <= tb && lt < v.T; lt++) {
-    const int s = lt * TILE + tid;
-    const int km = s < v.S ? min(rv.kmax[s], rv.Kcap) : 0;
-    const int actv = km > 0;
-    int ic = actv, ir = km;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int tc = __shfl_up_sync(0xffffffffu, ic, d), tr = __shfl_up_sync(0xffffffffu, ir, d);
-      if (lane >= d) { ic += tc; ir += tr; }
-    }
-    if (lane == 31) { s_scan[0][wid] = ic; s_scan[1][wid] = ir; }
-    __syncthreads();
-    int nA = 0, nR = 0;
-#pragma unroll
-    for (int w = 0; w < TILE / 32; w++) { if (w < wid) { ic += s_scan[0][w]; ir += s_scan[1][w]; } nA += s_scan[0][w]; nR += s_scan[1][w]; }
-    if (s < v.S) rv.posIncl[s] = actBase + ic;
-    const bool staged = nR <= CERT_ROWCAP;
-    if (actv) {
-      s_cnt[ic - 1] = km; s_site[ic - 1] = s;
-      if (staged) {
-        const float4* src = reinterpret_cast<const float4*>(rv.elist + (size_t)s * rv.Kcap * RP);
-        for (int j = 0; j < km * V; j++) s_rows[(size_t)(ir - km) * V + j] = src[j];
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int q = 0;
-      for (int i = 0; i < nA; i++) {
-        const int cnt = s_cnt[i];
-        const float* rows = staged ? reinterpret_cast<const float*>(s_rows) + (size_t)q * RP : rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
-        for (int j = 0; j < cnt; j++)
-#pragma unroll
-          for (int r = 0; r < RP; r++) if (r < R) c[r] = __fadd_rn(c[r], rows[j * RP + r]);
-        q += cnt;
-        float m = c[0];
-#pragma unroll
-        for (int r = 1; r < RP; r++) if (r < R) m = fmaxf(m, c[r]);
-        float* co = rv.cout + (size_t)(actBase + i) * RP;
-#pragma unroll
-        for (int r = 0; r < RP; r++) if (r < R) { c[r] = __fsub_rn(c[r], m); co[r] = c[r]; }
-        rv.mxo[actBase + i] = m;
-      }
-    }
-    actBase += nA; rowsWalked += nR;
-    __syncthreads();
-  }
-  if (tid == 0) { st->chainSites = actBase; st->chainRows = rowsWalked; }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K4c final: rateAveragedLogLiks (AugTree.cpp:317-323) per site, then a deterministic sum: a fixed tree inside each
 // RCH-site chunk, chunk sums combined in reduce_chunks order (identical on the host for the multi-GPU path).
 // mode 0: each site folds its own list from zero (numRateCats == 1, where the carry is always exactly zero, or the
 //         textbook reduction);
 // mode 1: exponent vectors come from the literal chain (k_chain);
-// mode 2: queued behind k_root_gather + k_cert without a host round trip: nothing to do unless the verdict is CERT_OK;
-//         then the tiles of the literal prefix read k_cert's vectors (as in mode 1) and every later tile takes the closed
-//         form of the certified regime (see k_cert).
+// mode 2: queued behind k_root_gather (whose last block certifies) without a host round trip: nothing to do unless the verdict is CERT_OK;
+//         then the tiles of the literal prefix read certify()'s vectors (as in mode 1) and every later tile takes the closed
+//         form of the certified regime (see certify).
 // publish: the last thread standing stores the status block into the host mirror (the host polls for it).
 template <bool BATCH>
 __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mode, int reduceAll, int publish, PathView pv) {

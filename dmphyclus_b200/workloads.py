@@ -18,6 +18,7 @@ CONFIGS = {
     "config3": (10000, 30000, 100, 3),    # chain, site-sharded
     "config4": (5000, 5000, 50, 3),       # proposal-batch sweep
     "config5": (100000, 1500, 100, 3),    # wide-short, deep trees
+    "config3_shard8": (10000, 3776, 100, 3),   # what ONE rank of config 3 over 8 GPUs holds (profiling a rank's kernels on one GPU)
 }
 
 

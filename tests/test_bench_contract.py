@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--no-extras"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout
@@ -25,7 +25,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "node-site partial updates/sec" and d["unit"] == "updates/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1
-    assert "config2" in d["config"]["workload"] and d["config"]["tips"] == 1000 and d["config"]["sites_per_gpu"] == 10000
+    # the workload of our own arm: config 3, the shape BASELINE.json's target is quoted on; the bounded sample is stated
+    assert "config3" in d["config"]["workload"] and d["config"]["tips"] == 10000 and d["config"]["sites_per_gpu"] == 30000
+    assert "sites" in d["config"]["reference_sample"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and "sites" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
