@@ -365,9 +365,16 @@ def run_ours(args, rank, world, local_rank):
     sampler.mark = "timed"
     local.timer_begin(h)
     host_us = np.zeros(3)
+    tl_keys, tl_sum, tl_n = None, None, 0
     for _ in range(args.steps):
         eng.recomputeAll(h, W, B, p.pi)
         sti = local.stats(h)
+        tl = local.root_timeline(h)
+        if tl_keys is None:
+            tl_keys, tl_sum = list(tl), np.zeros(len(tl))
+        if all(v is not None for v in tl.values()):
+            tl_sum += [tl[k] for k in tl_keys]
+            tl_n += 1
         prune_ms += sti["last_prune_ms"]
         host_us += (sti["last_host_plan_us"], sti["last_host_submit_us"], sti["last_host_total_us"])
     ms = local.timer_end(h)
@@ -470,6 +477,7 @@ def run_ours(args, rank, world, local_rank):
                "gpu_launches": int(launches),
                "roofline": roofline,
                "host_us_per_step": {"plan": host_us[0], "submit": host_us[1], "evaluate_total": host_us[2]},
+               "root_stage_us": ({k: round(float(v), 2) for k, v in zip(tl_keys, tl_sum / tl_n)} if tl_n else None),
                "sharded_exchange": ({"in_kernel": eng.fast, "host_collectives": eng.collectives} if world > 1 else None),
                "chain": {"resolved_by": {0: "no site rescaled", 1: "certificate", 2: "literal walk"}.get(int(st1["last_cert"])),
                          "walked_sites": int(st1["last_chain_sites"]), "walked_rows": int(st1["last_chain_rows"]),
@@ -594,16 +602,20 @@ def mcmc_leg(args, eng, p, al, out, how):
                 r = f(ptr, *a, **kw)
                 w1 = time.perf_counter()
                 st = self.be.stats(ptr)
+                tl = self.be.root_timeline(ptr)
                 self.rows[name].append(((w1 - w0) * 1e6, st["last_host_total_us"], st["last_host_plan_us"], st["last_host_submit_us"],
                                         st["last_eval_ms"] * 1e3, st["last_prune_ms"] * 1e3, st["last_stored_vertices"],
-                                        st["last_fused_vertices"], st["last_walk_steps"], st["last_prune_launches"]))
+                                        st["last_fused_vertices"], st["last_walk_steps"], st["last_prune_launches"],
+                                        tl["gather"] or 0.0, tl["exchange_or_reduce"] or 0.0, tl["certificate"] or 0.0,
+                                        tl["gap_to_final"] or 0.0, tl["final_terms"] or 0.0, tl["final_exchange_or_reduce"] or 0.0))
                 return r
             return wrapped
 
     pr = Probe(eng)
     chain.run_chain(pr, al, p.edge, p.clus, 100.0, cs, 6, seed=args.seed)
     cols = ("wall_us", "engine_host_us", "plan_us", "submit_us", "device_eval_us", "device_prune_us", "stored_vertices",
-            "fused_vertices", "walk_steps", "prune_launches")
+            "fused_vertices", "walk_steps", "prune_launches", "root_gather_us", "root_reduce_us", "root_certificate_us",
+            "root_gap_us", "root_final_us", "root_final_reduce_us")
     out["mcmc"]["per_call"] = {k: dict(zip(cols, [round(float(x), 2) for x in np.mean(np.array(v), axis=0)]), n=len(v))
                                for k, v in pr.rows.items() if v}
     return out

@@ -1067,6 +1067,8 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     }
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
     CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
+    CUDA_TRY(cudaMemsetAsync(&t->rv.st->stamp[0], 0xff, sizeof(unsigned long long), t->stream));
+    CUDA_TRY(cudaMemsetAsync(&t->rv.st->stamp[4], 0xff, sizeof(unsigned long long), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
     t->dv.N = t->N; t->dv.S = t->S; t->dv.Sp = t->Sp; t->dv.R = t->R; t->dv.T = t->T; t->dv.nInt = t->nInt; t->dv.nReal = t->nReal; t->dv.nFlag = t->nFlag;
     // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
@@ -1156,14 +1158,17 @@ static int nniCommon(dmpc_tree* t, const double* w, const double* b, int origin,
   if (cand.empty())
     return fail(DMPC_ERR_NO_MOVE, "no vertex admits a nearest-neighbour interchange here (the reference calls "
                                   "gsl_rng_uniform_int(r, 0), clusterFunArmadillo.cpp:187)");
+  t->ht.beginNni();
+  int lastRoot = -1;
   for (int m = 0; m < numMoves; m++) {
     const int root = cand[t->ht.rng.uniform_int(cand.size())];
     int two[2];
     t->ht.twoVerticesForNNI(root, mrcas, two);
     t->ht.rearrangeNNI(two[0], two[1]);
+    lastRoot = root;
   }
   int rc = evaluate(t, w, b, pi, ll);
-  if (rc == DMPC_OK) t->ht.exportEdges(edgeOut);
+  if (rc == DMPC_OK) t->ht.exportProposed(edgeOut, numMoves == 1 ? lastRoot : -1);
   return rc;
 }
 
@@ -1265,7 +1270,7 @@ int dmpc_restore_previous_config(dmpc_tree* t, const int32_t* edge, int nEdgeRow
   ht.withinIdx = withinMatListIndex; ht.betweenIdx = betweenMatListIndex;
   if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
     if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
-    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
+    if (!ht.restoreTopology(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
   }
   if ((rc = rollbackTouched(t))) return rc;
   if (splitMergeMove) {
@@ -1525,6 +1530,22 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   return DMPC_OK;
 }
 
+int dmpc_get_root_timeline(dmpc_tree* t, double* usOut) {
+  int rc;
+  if ((rc = checkHandle(t))) return rc;
+  if (!usOut) return fail(DMPC_ERR_ARG, "null pointer");
+  if (t->grp) t = t->grp->shards[0];
+  const unsigned long long* s = t->h_res->stamp;
+  auto d = [&](int a, int b) { return (s[a] == ~0ull || s[b] == ~0ull || s[b] < s[a]) ? -1.0 : (double)(s[b] - s[a]) * 1e-3; };
+  usOut[0] = d(0, 1);   // gather: first block -> last block found
+  usOut[1] = d(1, 2);   // exchange (wait for the peers) / quiet reduction
+  usOut[2] = d(2, 3);   // certificate (+ literal prefix)
+  usOut[3] = t->seqPredicted || t->lastCert ? d(3, 4) : -1.0;   // gap until the final kernel's first block
+  usOut[4] = t->lastCert ? d(4, 5) : -1.0;   // final: per-site terms
+  usOut[5] = t->lastCert ? d(5, 6) : -1.0;   // final's exchange / reduction
+  return DMPC_OK;
+}
+
 int dmpc_timer_begin(dmpc_tree* t) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
@@ -1712,6 +1733,8 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
 struct dmpc_hostplan {
   HostTree ht;
   HostTree::Plan plan;
+  bool nniPending = false;       // dmpc_hp_propose made NNI swaps whose edge matrix dmpc_hp_state has not exported yet
+  int nniRoot = -1;
 };
 
 int dmpc_hp_create(const int32_t* edge, int nEdgeRows, int numTips, const double* clusterMRCAs, int nClusterMRCAs,
@@ -1763,11 +1786,16 @@ int dmpc_hp_propose(dmpc_hostplan* h, int kind, const int32_t* args, int nArgs) 
       std::vector<int> cand;
       ht.nniCandidates(origin, mp, cand);
       if (cand.empty()) return fail(DMPC_ERR_NO_MOVE, "no vertex admits a nearest-neighbour interchange here");
+      ht.beginNni();
+      h->nniRoot = -1;
       for (int m = 0; m < numMoves; m++) {
         int two[2];
-        ht.twoVerticesForNNI(cand[ht.rng.uniform_int(cand.size())], mp, two);
+        const int root = cand[ht.rng.uniform_int(cand.size())];
+        ht.twoVerticesForNNI(root, mp, two);
         ht.rearrangeNNI(two[0], two[1]);
+        h->nniRoot = numMoves == 1 ? root : -1;
       }
+      h->nniPending = true;
       return DMPC_OK;
     }
     default: return fail(DMPC_ERR_ARG, "unknown proposal kind");
@@ -1822,8 +1850,9 @@ int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nn
   HostTree& ht = h->ht;
   if (nniMove) {                                  // BuildTreeNoAssign, AugTree.cpp:88-101
     if (!edge || nEdgeRows != ht.numVerts - 1) return fail(DMPC_ERR_ARG, "edge matrix required for an NNI rollback");
-    if (!ht.link(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
+    if (!ht.restoreTopology(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
   }
+  h->nniPending = false;
   for (int v = ht.numTips; v < ht.numVerts; v++)  // RestoreIterVecAndExp, IntermediateNode.h:26-33
     if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
   if (splitMergeMove) {
@@ -1836,7 +1865,10 @@ int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nn
 int dmpc_hp_state(dmpc_hostplan* h, uint8_t* cur, uint8_t* within, int32_t* edgeOut) {
   if (!h || !cur || !within || !edgeOut) return fail(DMPC_ERR_ARG, "null pointer");
   for (int v = 0; v < h->ht.numVerts; v++) { cur[v] = h->ht.cur[v]; within[v] = h->ht.within[v]; }
-  h->ht.exportEdges(edgeOut);
+  // the same incremental export the NNI entry points use (a pending NNI proposal is exported once, like they do)
+  if (h->nniPending) { h->ht.exportProposed(edgeOut, h->nniRoot); h->nniPending = false; }
+  else if (h->ht.pendingNni && h->ht.pendingRoot >= 0 && h->ht.exportValid) { std::copy(h->ht.committedEdge.begin(), h->ht.committedEdge.end(), edgeOut); h->ht.exportSubtree(h->ht.pendingRoot, edgeOut, false); }
+  else h->ht.exportEdges(edgeOut);
   return DMPC_OK;
 }
 

@@ -64,6 +64,19 @@ struct HostTree {
   std::vector<uint8_t> mat;              // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
   bool walkChains = true;                // false: never hand a chain to k_walk (its 32-bit element offsets would overflow)
   bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
+  // --- O(touched) NNI bookkeeping.  R hands the committed edge matrix back on every rejected NNI move
+  // (RestorePreviousConfig -> BuildTreeNoAssign, AugTree.cpp:88-101, 348-366) and gets the proposed one from every NNI
+  // call (BuildEdgeMatrix, :228-251): both are O(N) in the reference.  Here the swaps of the pending proposal are
+  // logged; when the matrix R hands back IS the committed one (memcmp), the rollback undoes the log instead of
+  // relinking 2N-2 edges, and the proposed matrix is the committed one with only the rows of the rearranged subtree
+  // rewritten (a subtree's rows are contiguous in pre-order and a swap inside it keeps their number).
+  struct NniUndo { int a, b, pa, pb; int32_t ka[2], kb[2]; bool tipsMoved; };
+  std::vector<NniUndo> nniLog;           // swaps since the committed topology (the pending NNI proposal)
+  bool pendingNni = false;               // an NNI proposal has been evaluated and neither restored nor followed by another proposal
+  int pendingRoot = -1;                  // ... the vertex whose subtree it rearranged (-1: several moves, whole matrix re-exported)
+  std::vector<int32_t> committedEdge;    // R's edge matrix of the committed topology (column-major, 1-based); empty = unknown
+  std::vector<int32_t> rowOf;            // exportValid: row of each vertex's own edge in committedEdge
+  bool exportChecked = false, exportValid = false;   // committedEdge is (known to be) exportEdges() of the committed topology
 
   bool isTip(int v) const { return v < numTips; }
   int internalIndex(int v) const { return v - numTips; }
@@ -130,6 +143,8 @@ struct HostTree {
     for (int v = 0; v < numTips; v++) solved[v] = 1;
     rng.seed(0);
     if (!link(edge, nEdgeRows)) return false;
+    committedEdge.assign(edge, edge + 2 * (size_t)nEdgeRows);
+    exportChecked = exportValid = false; pendingNni = false; nniLog.clear();
     if (parent[root()] != -1) { err = "vertex numTips+1 must be the root"; return false; }
     // every vertex must hang below the root
     std::vector<int> stack(1, root());
@@ -160,7 +175,93 @@ struct HostTree {
     }
   }
 
-  void negateAllUpdateFlags() { std::fill(touched.begin(), touched.end(), 0); }          // AugTree.cpp:368-374
+  // AugTree.cpp:368-374.  Every proposal starts here, so an NNI proposal that was not restored has been ACCEPTED by now.
+  void negateAllUpdateFlags() {
+    std::fill(touched.begin(), touched.end(), 0);
+    if (pendingNni) commitPendingNni();
+  }
+  void commitPendingNni() {
+    const int nRows = numVerts - 1;
+    if (exportValid && pendingRoot >= 0) {
+      exportSubtree(pendingRoot, committedEdge.data(), true);      // the same rows the proposal handed to R
+    } else {
+      committedEdge.resize(2 * (size_t)nRows);
+      exportEdges(committedEdge.data());
+      indexRows();
+      exportChecked = exportValid = true;
+    }
+    pendingNni = false; pendingRoot = -1; nniLog.clear();
+  }
+  void indexRows() {
+    const int nRows = numVerts - 1;
+    rowOf.assign(numVerts, -1);
+    for (int k = 0; k < nRows; k++) rowOf[committedEdge[k + nRows] - 1] = k;
+  }
+  // before the swaps of an NNI proposal: make sure we know whether the committed matrix is our own pre-order export
+  void beginNni() {
+    nniLog.clear();
+    pendingRoot = -1;
+    if (exportChecked) return;
+    const int nRows = numVerts - 1;
+    std::vector<int32_t> tmp(2 * (size_t)nRows);
+    exportEdges(tmp.data());
+    exportValid = committedEdge.size() == tmp.size() && std::equal(tmp.begin(), tmp.end(), committedEdge.begin());
+    if (exportValid) indexRows();
+    exportChecked = true;
+  }
+  // the rows of sr's subtree, in pre-order, into `out` at the place they have in committedEdge
+  void exportSubtree(int sr, int32_t* out, bool reindex) {
+    const int nRows = numVerts - 1;
+    int line = parent[sr] == -1 ? 0 : rowOf[sr] + 1;
+    std::vector<int> stack;
+    stack.push_back(kids[2 * sr + 1]); stack.push_back(kids[2 * sr]);
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      out[line] = parent[v] + 1; out[line + nRows] = v + 1;
+      if (reindex) rowOf[v] = line;
+      line++;
+      if (!isTip(v)) { stack.push_back(kids[2 * v + 1]); stack.push_back(kids[2 * v]); }
+    }
+  }
+  // the edge matrix of the PROPOSED topology (after beginNni + the swaps): numMoves == 1 rearranged only subtreeRoot's subtree
+  void exportProposed(int32_t* out, int subtreeRoot) {
+    const int nRows = numVerts - 1;
+    pendingNni = true;
+    if (exportValid && subtreeRoot >= 0) {
+      std::copy(committedEdge.begin(), committedEdge.end(), out);
+      exportSubtree(subtreeRoot, out, false);
+      pendingRoot = subtreeRoot;
+    } else {
+      exportEdges(out);
+      pendingRoot = -1;
+    }
+    (void)nRows;
+  }
+  // RestorePreviousConfig's BuildTreeNoAssign (AugTree.cpp:88-101, 348-366) for a rejected NNI proposal
+  bool restoreTopology(const int32_t* edge, int nEdgeRows) {
+    const size_t n2 = 2 * (size_t)nEdgeRows;
+    if (pendingNni && !nniLog.empty() && committedEdge.size() == n2 && std::equal(edge, edge + n2, committedEdge.begin())) {
+      for (size_t i = nniLog.size(); i-- > 0;) {                 // the committed matrix: undo the swaps, newest first
+        const NniUndo& u = nniLog[i];
+        kids[2 * u.pa] = u.ka[0]; kids[2 * u.pa + 1] = u.ka[1];
+        kids[2 * u.pb] = u.kb[0]; kids[2 * u.pb + 1] = u.kb[1];
+        parent[u.a] = u.pa; parent[u.b] = u.pb;
+        if (u.tipsMoved) {
+          const int delta = tips[u.b] - tips[u.a];
+          for (int v = u.pa; v != -1; v = parent[v]) tips[v] -= delta;   // (parents are back in place: the chains rearrangeNNI walked)
+          for (int v = u.pb; v != -1; v = parent[v]) tips[v] += delta;
+        }
+      }
+      pendingNni = false; pendingRoot = -1; nniLog.clear();
+      return true;
+    }
+    pendingNni = false; pendingRoot = -1; nniLog.clear();
+    if (!link(edge, nEdgeRows)) return false;
+    committedEdge.assign(edge, edge + n2);
+    exportChecked = exportValid = false;
+    return true;
+  }
+
   void invalidateSolution(int v) { for (; v != -1; v = parent[v]) solved[v] = 0; }        // IntermediateNode.cpp:5-13
   void invalidateAll() { for (int v = numTips; v < numVerts; v++) solved[v] = 0; allInvalid = true; }   // AugTree.cpp:136-142
   void invalidateBetween() {                                                              // AugTree.cpp:273-287
@@ -206,6 +307,11 @@ struct HostTree {
 
   // RearrangeTreeNNI (AugTree.cpp:211-226)
   void rearrangeNNI(int a, int b) {
+    NniUndo u;
+    u.a = a; u.b = b; u.pa = parent[a]; u.pb = parent[b];
+    u.ka[0] = kids[2 * u.pa]; u.ka[1] = kids[2 * u.pa + 1]; u.kb[0] = kids[2 * u.pb]; u.kb[1] = kids[2 * u.pb + 1];
+    u.tipsMoved = tipsValid;
+    nniLog.push_back(u);
     if (tipsValid) {                       // the two subtrees trade places: only their old ancestors' counts move
       const int delta = tips[b] - tips[a];
       for (int v = parent[a]; v != -1; v = parent[v]) tips[v] += delta;

@@ -64,9 +64,18 @@ struct DevStatus {
   unsigned pubSeq;              // number of times a root kernel has published this block to the host mirror
   int certL0;                   // rescaled sites of the literal prefix (tiles 0 .. certTile)
   int certRate;                 // the dominant rate category of the certified regime
-  int certTile;                 // last (global) site tile of the literal prefix; every later tile is certified
+  int certTile;                 // last (local) site tile of the literal prefix; every later tile is certified
+  // %globaltimer stamps (ns) of the root stage, for the latency breakdown dmpc_get_root_timeline reports:
+  //   0 first gather block starts    1 gather's last block found    2 exchange / quiet reduction done    3 certificate done
+  //   4 first final block starts     5 final's last block found     6 final's exchange / reduction done
+  unsigned long long stamp[8];
 };
-static_assert(sizeof(DevStatus) == 64, "status block = 16 words");
+static_assert(sizeof(DevStatus) == 128, "status block = 32 words");
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 enum : int {
   CERT_NONE = 0,                // certify() has not run (or had nothing to do: no site rescaled anywhere)
   CERT_OK = 1,                  // every tile behind the literal prefix is certified: k_final uses the closed form there
@@ -1005,6 +1014,7 @@ __device__ __forceinline__ void publishStatus(const RootView& rv) {
   for (int i = 0; i < (int)(sizeof(DevStatus) / 4); i++) if (i != SEQ_WORD) dst[i] = src[i];
   __threadfence_system();                 // the payload is visible to the host before the sequence number is
   dst[SEQ_WORD] = (int)seq;
+  rv.st->stamp[0] = ~0ull; rv.st->stamp[4] = ~0ull;   // "first block" stamps are atomicMin'ed: re-armed for the next evaluation
 }
 
 template <int RP, bool BATCH>
@@ -1024,6 +1034,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   const bool valid = site < v.S;
   const int R = v.R;
   const size_t Sp = (size_t)v.Sp;
+  if (!BATCH && tid == 0) atomicMin(&rv.st->stamp[0], gtime());
   const int rootSlot = v.cur[0];
   double rd[RP];
 #pragma unroll
@@ -1269,7 +1280,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
     const CommView& cm = rv.comm;
     const bool retry = *(volatile int*)&rv.st->overflow > rv.Kcap || (*(volatile int*)&rv.st->violation != 0 && !rv.exactMode);
     const bool pub = !BATCH && rv.publishAtGather;
-    if (tid == 0) rv.st->cert = CERT_NONE;
+    if (tid == 0) { rv.st->cert = CERT_NONE; if (!BATCH) rv.st->stamp[1] = gtime(); }
     if (cm.world > 1) {
       // skipped when the host is going to re-run this gather (list overflow, fused-clade violation), so that every
       // rank sends exactly one message per exchange
@@ -1278,21 +1289,23 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
         return;
       }
       const int res = exchangeAndReduce(rv, rv.nChunks, quiet, s_red, (mode == 1 && !quiet) ? rv.tileRec : nullptr, gridDim.x, xrec(RP));
-      if (tid == 0) rv.st->xok = res;
+      if (tid == 0) { rv.st->xok = res; if (!BATCH) rv.st->stamp[2] = gtime(); }
       __syncthreads();
       if (res == 0 && mode == 1) certify<RP>(v, rv, reinterpret_cast<float4*>(s_list));
       __syncthreads();
-      if (tid == 0) { rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
+      if (tid == 0) { rv.st->ticket2 = 0; if (!BATCH) rv.st->stamp[3] = gtime(); __threadfence(); if (pub) publishStatus(rv); }
       return;
     }
     if (quiet) {
       const double tot = reduce_chunks_device(rv.chunk, rv.nChunks, s_red);
       if (tid == 0) rv.st->ll = tot;
-    } else if (mode == 1 && !retry) {
+    }
+    if (tid == 0 && !BATCH) rv.st->stamp[2] = gtime();
+    if (!quiet && mode == 1 && !retry) {
       certify<RP>(v, rv, reinterpret_cast<float4*>(s_list));
       __syncthreads();
     }
-    if (tid == 0) { rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
+    if (tid == 0) { rv.st->ticket2 = 0; if (!BATCH) rv.st->stamp[3] = gtime(); __threadfence(); if (pub) publishStatus(rv); }
   }
 }
 
@@ -1536,6 +1549,7 @@ __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mod
     }
     if ((int)blockIdx.x > rv.st->certTile) dom = rv.st->certRate;
   }
+  if (!BATCH && tid == 0) atomicMin(&rv.st->stamp[4], gtime());
   double ll = 0.0;
   if (s < v.S) {
     float ev[RMAX];
@@ -1591,6 +1605,7 @@ __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mod
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (!BATCH && tid == 0) rv.st->stamp[5] = gtime();
   if (reduceAll == 2) {                             // site-sharded: second exchange, every shard is final now
     const int res = exchangeAndReduce(rv, rv.nChunks, true, s_red, nullptr, 0, 0);
     if (tid == 0) rv.st->xok = res;
@@ -1600,6 +1615,7 @@ __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mod
   }
   if (tid == 0) {
     rv.st->ticket = 0;
+    if (!BATCH) rv.st->stamp[6] = gtime();
     __threadfence();
     if (publish && !BATCH) publishStatus(rv);
   }

@@ -70,6 +70,7 @@ ABI = {
     "dmpc_recompute_all": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, _dbl_p]),
     "dmpc_eval_proposals": (C.c_int, [_P, _dbl_p, _dbl_p, _dbl_p, C.c_void_p, C.c_int, _dbl_p, C.POINTER(C.c_int)]),
     "dmpc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "dmpc_get_root_timeline": (C.c_int, [_P, _dbl_p]),
     "dmpc_timer_begin": (C.c_int, [_P]),
     "dmpc_timer_end": (C.c_int, [_P, _dbl_p]),
     "dmpc_plan_selfcheck": (C.c_int, [_i32_p, C.c_int, C.c_int, _dbl_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -322,6 +323,13 @@ class Engine:
         s = Stats()
         self._check(self.lib.dmpc_get_stats(ptr, C.byref(s)))
         return s.as_dict()
+
+    def root_timeline(self, ptr) -> dict:
+        """Where the last evaluation's root stage spent its time on the device (microseconds; None = phase did not run)."""
+        out = np.zeros(6)
+        self._check(self.lib.dmpc_get_root_timeline(ptr, _p(out, _dbl_p)))
+        keys = ("gather", "exchange_or_reduce", "certificate", "gap_to_final", "final_terms", "final_exchange_or_reduce")
+        return {k: (None if v < 0 else float(v)) for k, v in zip(keys, out)}
 
     def timer_begin(self, ptr) -> None:
         self._check(self.lib.dmpc_timer_begin(ptr))

@@ -175,6 +175,12 @@ typedef struct dmpc_stats {
                                mat-vec = 16 + 12, the product of the two child terms = 4, tip terms come from a table */
 } dmpc_stats;
 int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out);
+/* Latency breakdown of the last evaluation's root stage from %globaltimer stamps the root kernels leave in the status
+ * block (microseconds; -1 where a phase did not run): usOut[0] gather, first block to last block; [1] the gather's
+ * cross-rank exchange (wait for the peers' messages) or the quiet reduction; [2] chain certificate + literal prefix;
+ * [3] gap until the final kernel's first block; [4] final kernel, per-site terms; [5] its exchange / reduction.
+ * (Multi-device handle: shard 0's.) */
+int dmpc_get_root_timeline(dmpc_tree* t, double* usOut);
 /* Device-side timing of a region of calls: CUDA events recorded on the engine's own stream (which
  * torch.cuda.Event cannot see).  end returns the elapsed milliseconds between the two records. */
 int dmpc_timer_begin(dmpc_tree* t);
