@@ -16,6 +16,7 @@
 #include <thread>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -327,8 +328,10 @@ int recordEv(dmpc_tree* t, int i) {
 int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
   PruneArgs a{};
   a.tasks = lt; a.nTasks = nTasks; a.prog = t->runTokens; a.tipList = t->runTips; a.violation = &t->rv.st->violation; a.flip = t->runFlip;
-  if (t->exact) k_prune<true, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
-  else k_prune<false, false><<<grid, PT, 0, t->stream>>>(t->dv, a);
+  // 2 sites per thread, 5 blocks per SM (96 registers): measured best on B200 — 4 sites per thread (168-212 registers,
+  // 12-16 warps per SM) is 1.3-1.6x slower, 6 blocks per SM (80 registers, spills) 1.05x (profiles/r02_prune_variants.md)
+  if (t->exact) k_prune<true, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
+  else k_prune<false, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
   return DMPC_OK;
 }
 
@@ -1427,7 +1430,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       {
         PruneArgs a{};
         a.tasks = dT; a.prog = dK; a.tipList = dL; a.runStart = dR; a.invalid = dI; a.pv = pv;
-        k_prune<false, true><<<dim3((unsigned)t->R, (unsigned)t->T, (unsigned)nb), PT, 0, t->stream>>>(t->dv, a);
+        k_prune<false, true, 2, 5><<<dim3((unsigned)t->R, (unsigned)t->T, (unsigned)nb), TILE / 2, 0, t->stream>>>(t->dv, a);
       }
       if (t->rv.RP == 4) k_root_gather<4, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);
       else k_root_gather<8, true><<<dim3((unsigned)t->T, (unsigned)nb), TILE, 0, t->stream>>>(t->dv, rb, mode, pv);

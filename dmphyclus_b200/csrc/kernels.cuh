@@ -248,15 +248,19 @@ struct PruneArgs {
   PathView pv;                  // PATHS: per-proposal outputs
 };
 
-template <bool EXACT, bool PATHS>
-__global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
+// SPT_ = sites per thread (the block has TILE / SPT_ threads): what is uniform across the block — token decoding, the P
+// matrix entries (LDCU), addresses — is paid once per SPT_ updates, and the SPT_ sites are independent instruction streams
+// for the scheduler; MINB = resident blocks per SM the register allocation aims at.
+template <bool EXACT, bool PATHS, int SPT_, int MINB>
+__global__ void __launch_bounds__(TILE / SPT_, MINB) k_prune(DevView v, PruneArgs pa_) {
+  constexpr int PT_ = TILE / SPT_;
   static_assert(!(EXACT && PATHS), "proposal batches run in fast mode only");
   const Task* __restrict__ tasks = pa_.tasks;
   const Token* __restrict__ prog = pa_.prog;
   const int32_t* __restrict__ tipList = pa_.tipList;
   const int flip = PATHS ? 0 : pa_.flip;
-  // one thread = SPT sites (tid, tid + PT, ...) of one rate: what is uniform across the block — token decoding, the
-  // P matrix elements, addresses — is paid once per SPT updates
+  // one thread = SPT_ sites (tid, tid + PT_, ...) of one rate: what is uniform across the block — token decoding, the
+  // P matrix elements, addresses — is paid once per SPT_ updates
   __shared__ __align__(16) double s_lut[2 * 64];                 // [set][mask][4] of this block's rate
   __shared__ __align__(16) double s_stack[FUSE_DEPTH * 4 * TILE];
   __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   bool lutLoaded = false, trig = false;
-  double prev[PATHS ? SPT : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
+  double prev[PATHS ? SPT_ : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
   const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : (int)blockIdx.z;
   const int tiEnd = PATHS ? pa_.runStart[blockIdx.z + 1] : pa_.nTasks;
   const int tiStep = PATHS ? 1 : (int)gridDim.z;
@@ -284,20 +288,20 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
     const double* pb = v.partOf(fl & TF_C1SLOT) + (((size_t)tk0.z * R + r) * Sp + site0) * 4;
     const bool plain = !(fus0 | fus1);
     const int n0 = tk1.y & 0xffff, n1 = (tk1.y >> 16) & 0xffff, ntok = n0 + n1;
-    unsigned ma[SPT], mb[SPT];
-    double a[SPT][4], b[SPT][4];
+    unsigned ma[SPT_], mb[SPT_];
+    double a[SPT_][4], b[SPT_][4];
     // every load this thread needs from HBM is issued here, before any arithmetic
 #pragma unroll
-    for (int u = 0; u < SPT; u++) {
-      if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT];
-      else if (!fus0 && !fwd0) ld256(pa + (size_t)u * PT * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
-      if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT];
-      else if (!fus1 && !fwd1) ld256(pb + (size_t)u * PT * 4, b[u][0], b[u][1], b[u][2], b[u][3]);
+    for (int u = 0; u < SPT_; u++) {
+      if (tip0) ma[u] = v.tipmask[(size_t)tk0.y * Sp + site0 + u * PT_];
+      else if (!fus0 && !fwd0) ld256(pa + (size_t)u * PT_ * 4, a[u][0], a[u][1], a[u][2], a[u][3]);
+      if (tip1) mb[u] = v.tipmask[(size_t)tk0.z * Sp + site0 + u * PT_];
+      else if (!fus1 && !fwd1) ld256(pb + (size_t)u * PT_ * 4, b[u][0], b[u][1], b[u][2], b[u][3]);
     }
     if (!plain) {
       // the masks of every tip the programs read (4 sites per cp.async) and the tokens themselves, into shared memory
       const int nTips = tk1.w;
-      for (int j = tid; j < nTips * (TILE / 4); j += PT) {
+      for (int j = tid; j < nTips * (TILE / 4); j += PT_) {
         const int tipIdx = j / (TILE / 4), q = j - tipIdx * (TILE / 4);
         const unsigned char* src = v.tipmask + (size_t)__ldg(tipList + tk1.z + tipIdx) * Sp + tile * TILE + 4 * q;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s_mask + tipIdx * TILE + 4 * q);
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
       if (tid < ntok) s_tok[tid] = __ldg(reinterpret_cast<const int4*>(prog + tk1.x + tid));
     }
     if (!lutLoaded && (!plain || tip0 || tip1)) {
-      s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];       // PT == 2 * 64
+      for (int i = tid; i < 2 * 64; i += PT_) s_lut[i] = v.lut[(size_t)((i >> 6) * R + r) * 64 + (i & 63)];
       lutLoaded = true;
       if (plain) __syncthreads();
     }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
       __syncthreads();
     }
 
-    double reg[SPT][4];
+    double reg[SPT_][4];
     // ---- the fused operands' programs
     auto run = [&](int first, int n, int sp) {
       for (int i = first; i < first + n; i++) {
@@ -324,9 +328,9 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
         const int op = t4.x & 7;
         if (op == OP_SPILL) {
 #pragma unroll
-          for (int u = 0; u < SPT; u++)
+          for (int u = 0; u < SPT_; u++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid + u * PT] = reg[u][k];
+            for (int k = 0; k < 4; k++) s_stack[(sp * 4 + k) * TILE + tid + u * PT_] = reg[u][k];
           sp++;
           continue;
         }
@@ -334,23 +338,23 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
         const double* P = c_P[tset][r];
         const double* lutr = s_lut + tset * 64;
         if (op == OP_SLOTREG) sp--;
-        float e[SPT];
+        float e[SPT_];
 #pragma unroll
-        for (int u = 0; u < SPT; u++) {
+        for (int u = 0; u < SPT_; u++) {
           double x[4], y[4];                     // x = term of the operand the token lists first, y = the other
           if (op == OP_CHERRY) {
-            const unsigned m0 = s_mask[t4.y * TILE + tid + u * PT], m1 = s_mask[t4.z * TILE + tid + u * PT];
+            const unsigned m0 = s_mask[t4.y * TILE + tid + u * PT_], m1 = s_mask[t4.z * TILE + tid + u * PT_];
 #pragma unroll
             for (int k = 0; k < 4; k++) { x[k] = lutr[4 * m0 + k]; y[k] = lutr[4 * m1 + k]; }
           } else if (op == OP_REGTIP) {
-            const unsigned m1 = s_mask[t4.z * TILE + tid + u * PT];
+            const unsigned m1 = s_mask[t4.z * TILE + tid + u * PT_];
             matvec4(P, reg[u], x);
 #pragma unroll
             for (int k = 0; k < 4; k++) y[k] = lutr[4 * m1 + k];
           } else {
             double z[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid + u * PT];
+            for (int k = 0; k < 4; k++) z[k] = s_stack[(sp * 4 + k) * TILE + tid + u * PT_];
             matvec4(P, z, x);
             matvec4(P, reg[u], y);
           }
@@ -377,11 +381,11 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
           const int tslot = ((t4.x & TOK_SLOT) ? 1 : 0) ^ flip;
           bool resc = false;
 #pragma unroll
-          for (int u = 0; u < SPT; u++) resc |= e[u] != 0.0f;
+          for (int u = 0; u < SPT_; u++) resc |= e[u] != 0.0f;
           const int any = __syncthreads_or(resc);
           if (any) {
 #pragma unroll
-            for (int u = 0; u < SPT; u++) v.expoOf(tslot)[((size_t)t4.w * R + r) * Sp + site0 + u * PT] = e[u];
+            for (int u = 0; u < SPT_; u++) v.expoOf(tslot)[((size_t)t4.w * R + r) * Sp + site0 + u * PT_] = e[u];
           }
           if (tid == 0) v.flagOf(tslot)[flagRow + t4.w] = (uint8_t)(any != 0);
         }
@@ -391,9 +395,9 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
       run(0, n0, 0);
       if (fus1) {
 #pragma unroll
-        for (int u = 0; u < SPT; u++)
+        for (int u = 0; u < SPT_; u++)
 #pragma unroll
-          for (int k = 0; k < 4; k++) s_stack[k * TILE + tid + u * PT] = reg[u][k];
+          for (int k = 0; k < 4; k++) s_stack[k * TILE + tid + u * PT_] = reg[u][k];
       }
     }
     if (fus1) run(n0, n1, 1);
@@ -412,10 +416,10 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
     const double* lutr = s_lut + set * 64;
     const int os = (fl & TF_OUTSLOT) ? 1 : 0;
     const size_t o = ((size_t)tk0.x * R + r) * Sp + site0;
-    float e[SPT];
+    float e[SPT_];
     bool rescaled = false;
 #pragma unroll
-    for (int u = 0; u < SPT; u++) {
+    for (int u = 0; u < SPT_; u++) {
       double first[4], second[4], s4[4];
       if (tip0) {
 #pragma unroll
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
         if (fus1) {
           double z[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid + u * PT];
+          for (int k = 0; k < 4; k++) z[k] = s_stack[k * TILE + tid + u * PT_];
           matvec4(P, z, first);
         } else {
           matvec4(P, reg[u], first);
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
 #pragma unroll
         for (int k = 0; k < 4; k++) prev[PATHS ? u : 0][k] = s4[k];
       } else {
-        st256(v.partOf(os) + (o + (size_t)u * PT) * 4, s4[0], s4[1], s4[2], s4[3]);
+        st256(v.partOf(os) + (o + (size_t)u * PT_) * 4, s4[0], s4[1], s4[2], s4[3]);
       }
       rescaled |= e[u] != 0.0f;
     }
@@ -460,13 +464,13 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
       const size_t row = ((size_t)blockIdx.z * pv.JMAX + (ti - tiBegin)) * R + r;
       if (any) {
 #pragma unroll
-        for (int u = 0; u < SPT; u++) pv.pe[row * Sp + site0 + u * PT] = e[u];
+        for (int u = 0; u < SPT_; u++) pv.pe[row * Sp + site0 + u * PT_] = e[u];
       }
       if (tid == 0) pv.pf[row * v.T + tile] = (uint8_t)(any != 0);
     } else {
       if (any) {
 #pragma unroll
-        for (int u = 0; u < SPT; u++) v.expoOf(os)[o + (size_t)u * PT] = e[u];
+        for (int u = 0; u < SPT_; u++) v.expoOf(os)[o + (size_t)u * PT_] = e[u];
       }
       if (tid == 0) {
         v.flagOf(os)[flagRow + tk0.x] = (uint8_t)(any != 0);
@@ -476,8 +480,8 @@ __global__ void __launch_bounds__(PT, 5) k_prune(DevView v, PruneArgs pa_) {
   }
   if (PATHS) {
 #pragma unroll
-    for (int u = 0; u < SPT; u++)                  // arma::dot: two interleaved accumulators
-      pa_.pv.rootdot[((size_t)blockIdx.z * R + r) * Sp + site0 + u * PT] =
+    for (int u = 0; u < SPT_; u++)                  // arma::dot: two interleaved accumulators
+      pa_.pv.rootdot[((size_t)blockIdx.z * R + r) * Sp + site0 + u * PT_] =
           __dadd_rn(__dadd_rn(__dmul_rn(prev[PATHS ? u : 0][0], c_pi[0]), __dmul_rn(prev[PATHS ? u : 0][2], c_pi[2])),
                     __dadd_rn(__dmul_rn(prev[PATHS ? u : 0][1], c_pi[1]), __dmul_rn(prev[PATHS ? u : 0][3], c_pi[3])));
     if (trig) pa_.invalid[blockIdx.z] = 1;
