@@ -1,0 +1,126 @@
+"""BASELINE.json configs 3, 4 and 5 at (or near) their full size against the dense CPU oracle on all host cores:
+log-likelihood within 1e-9, root partial vectors bit for bit, one proposal of every kind (the reference's move schedule,
+/root/reference/R/DMphyClusSource.R:1-26), NNI edge matrices identical.  Config 3 keeps all 10,000 tips and takes 4,096
+of its 30,000 sites (the oracle's partials would not fit the host otherwise) — the sites are what shards, the tips are
+what makes the rescale chain, 118-tile flag scans and 1,245 stored vertices meet; it also runs as a two-shard
+multi-device handle, i.e. through the in-kernel exchange, on a one-GPU box."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import Problem, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+NONE = np.zeros((1, 2), np.int32)
+
+
+def _host_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 16.0
+
+
+def _one_of_each(be_list, p, check_partials=True):
+    """The same calls on every backend; returns one list of log-likelihoods per backend.  Rejected moves are restored,
+    the within-cluster NNI is kept (topology change), then the root partial is compared."""
+    W, B, pi, n = p.W, p.B, p.pi, p.n
+    outs = [[] for _ in be_list]
+    edges = [[] for _ in be_list]
+    big = [m for m in p.mrcas if m > n]
+    from dmphyclus_b200.phylo import Phylo
+    phy = Phylo(p.edge, n)
+    groups = {}
+    for m in p.mrcas:
+        groups.setdefault(int(phy.parent[m]), []).append(m)
+    pair = next((g for g in groups.values() if len(g) == 2), None)
+    for (be, h), out, ed in zip(be_list, outs, edges):
+        out.append(be.newBetweenTransProbsLogLik(h, W[4], B[7], 1, 8, pi))
+        be.RestorePreviousConfig(h, NONE, 5, 5, False, p.mrcas, False)
+        out.append(be.clusSplitMergeLogLik(h, W[4], B[4], [big[0]], 1, pi))
+        be.RestorePreviousConfig(h, NONE, 5, 5, False, p.mrcas, True)
+        if pair:
+            out.append(be.clusSplitMergeLogLik(h, W[4], B[4], pair, 1, pi))
+            be.RestorePreviousConfig(h, NONE, 5, 5, False, p.mrcas, True)
+        r = be.betweenClusNNIlogLik(h, W[4], B[4], p.mrcas, 1, 1, pi)
+        out.append(r["logLik"]); ed.append(np.array(r["edge"]))
+        be.RestorePreviousConfig(h, p.edge, 5, 5, True, p.mrcas, False)
+        r = be.withinClusNNIlogLik(h, W[4], B[4], big[-1], 1, 1, pi)          # kept
+        out.append(r["logLik"]); ed.append(np.array(r["edge"]))
+        out.append(be.newWithinTransProbsLogLik(h, W[2], B[4], 1, 3, pi))     # InvalidateAll on the new topology, kept
+    return outs, edges
+
+
+def _compare(outs, edges):
+    ref = outs[-1]                                   # the oracle goes last
+    for o in outs[:-1]:
+        assert len(o) == len(ref)
+        assert all(rel(a, b) < TOL for a, b in zip(o, ref)), (o, ref)
+    for e in edges[:-1]:
+        assert all(np.array_equal(a, b) for a, b in zip(e, edges[-1]))
+
+
+def test_config3_all_tips(packaged):
+    from dmphyclus_b200.engine import Engine
+    from oracle.oracle import Oracle
+    p = Problem(packaged, 10000, 4096, 100, 3, "evolved", seed=2001)
+    eng, two, orc = Engine(), Engine(devices=[0, 0]), Oracle(threads=os.cpu_count() or 4)
+    hg, lg = p.create(eng)
+    ht, lt = p.create(two)
+    ho, lo = p.create(orc)
+    assert rel(lg, lo) < TOL and lt == lg, (lg, lt, lo)
+    st = eng.stats(hg)
+    assert st["last_cert"] == 1 and st["last_stored_vertices"] > 1000      # the rescale chain and the stored tree are exercised
+    outs, edges = _one_of_each([(eng, hg), (two, ht), (orc, ho)], p)
+    _compare(outs, edges)
+    assert outs[0] == outs[1]                                               # the sharded handle: bit for bit
+    sg, eg = eng.partial(hg, p.n)
+    so, eo = orc.partial(ho, p.n)
+    assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=2e-7, atol=0)
+    assert np.array_equal(two.partial(ht, p.n)[0], so)
+    for be, h in ((eng, hg), (two, ht), (orc, ho)):
+        be.finalDeallocate(h)
+
+
+def test_config4_full_size(packaged):
+    from dmphyclus_b200.engine import Engine
+    from oracle.oracle import Oracle
+    p = Problem(packaged, 5000, 5000, 50, 3, "evolved", seed=2001)
+    eng, orc = Engine(), Oracle(threads=os.cpu_count() or 4)
+    hg, lg = p.create(eng)
+    ho, lo = p.create(orc)
+    assert rel(lg, lo) < TOL, (lg, lo)
+    # the proposal batch of config 4 (dmpc_eval_proposals) against the oracle's one-by-one values
+    big = [m for m in p.mrcas if m > p.n][:12]
+    got, nb = eng.evalProposals(hg, p.W[4], p.B[4], p.pi, [("split", m) for m in big])
+    want = []
+    for m in big:
+        want.append(orc.clusSplitMergeLogLik(ho, p.W[4], p.B[4], [m], 1, p.pi))
+        orc.RestorePreviousConfig(ho, NONE, 5, 5, False, p.mrcas, True)
+    assert all(rel(a, b) < TOL for a, b in zip(got, want)), (got, want)
+    outs, edges = _one_of_each([(eng, hg), (orc, ho)], p)
+    _compare(outs, edges)
+    assert np.array_equal(eng.partial(hg, p.n)[0], orc.partial(ho, p.n)[0])
+    eng.finalDeallocate(hg); orc.finalDeallocate(ho)
+
+
+@pytest.mark.parametrize("shape", ["random", "balanced"])
+def test_config5_full_size(packaged, shape):
+    """100,000 tips x 1,500 sites.  (The caterpillar variant cannot be checked this way: the reference's recursive
+    traversal — and the oracle's, which restates it — overflows the stack at that depth; its spine is covered at 20,000
+    tips by test_caterpillar_spine_is_walked.)"""
+    from dmphyclus_b200.engine import Engine
+    from oracle.oracle import Oracle
+    S = 1500 if _host_gb() > 40 else 384            # the oracle keeps every partial: 16 GB of host memory at full size
+    p = Problem(packaged, 100000, S, 100, 3, "evolved", shape, seed=2001)
+    eng, orc = Engine(), Oracle(threads=os.cpu_count() or 4)
+    hg, lg = p.create(eng)
+    ho, lo = p.create(orc)
+    assert rel(lg, lo) < TOL, (lg, lo)
+    outs, edges = _one_of_each([(eng, hg), (orc, ho)], p)
+    _compare(outs, edges)
+    assert np.array_equal(eng.partial(hg, p.n)[0], orc.partial(ho, p.n)[0])
+    eng.finalDeallocate(hg); orc.finalDeallocate(ho)
