@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", f) for f in ("dmpc_engine.cu", "kernels.cuh", "host_tree.hpp", "task.hpp")]
 HDR = os.path.join(ROOT, "include", "dmpc.h")
+HDR_TEST = os.path.join(ROOT, "include", "dmpc_test.h")
 LIB = os.path.join(HERE, "libdmpc.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -20,7 +21,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    deps = SRC + [HDR]
+    deps = SRC + [HDR, HDR_TEST]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC[0]]

@@ -6,6 +6,7 @@
 // (host_tree.hpp) plus dense HBM buffers, and ComputeLoglik is a level plan of CUDA launches
 // (kernels.cuh).  There is no CPU arithmetic path: without a usable device every call fails.
 #include "../../include/dmpc.h"
+#include "../../include/dmpc_test.h"
 
 #include <algorithm>
 #include <atomic>
@@ -1011,8 +1012,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
   t->nChunks = (numLoci + RCH - 1) / RCH;
   t->rv.nChunks = t->nChunks;
   t->rv.certOn = o.chain_cert != 0;
-  // k_walk addresses partials by 32-bit element offsets (an element = one 32-byte 4-vector): fine up to 137 GB per slot
-  t->ht.walkChains = (unsigned long long)t->nInt * t->R * t->Sp < (1ull << 32);
+  t->ht.walkChains = true;      // (k_walk addresses rows, with 64-bit products at the point of use: no size limit)
   t->quirk = o.quirk_carry != 0;
   t->deferred = o.deferred != 0;
   t->comm = (dmpc_comm*)o.comm;

@@ -514,8 +514,9 @@ static_assert((WALK_DEPTH & (WALK_DEPTH - 1)) == 0 && WALK_CHUNK % WALK_WIN == 0
 // a step as the walking threads see it: everything that is uniform across the block is worked out ONCE per step while
 // the chunk is staged (one thread per step), so that the per-step instruction stream of a walking warp — which is what
 // bounds a chain: a lone warp issues one dependent instruction every ~5 cycles — stays short.
-// x = element offset of the output row (vertex, this rate), y = element offset of the off-chain operand's row (stored)
-// or byte offset of its mask row (tip), z = flags, w = output vertex (for the flag / slot bookkeeping)
+// x = output row (vertex * R + this rate), y = row of the off-chain operand (stored: vertex * R + rate; tip: the tip),
+// z = flags, w = output vertex (for the flag / slot bookkeeping).  Rows, not element offsets: the 64-bit product with
+// the row pitch is formed at the point of use, so no handle is too large for the walk
 enum : int { WF_OUTSLOT = 1, WF_SIBTIP = 2, WF_SIBSLOT = 4, WF_SET = 8, WF_FWD0 = 16 };
 
 __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip) {
@@ -542,10 +543,10 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
     const uint4 d = s_desc[k];
     const unsigned dst = ringMine + (unsigned)(k & (WALK_DEPTH - 1)) * (unsigned)(TILE * 32);
     if (d.z & WF_SIBTIP) {
-      const uint8_t* src = maskMine + d.y;
+      const uint8_t* src = maskMine + (size_t)d.y * Sp;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
     } else {
-      const double* src = ((d.z & WF_SIBSLOT) ? part1 : part0) + (size_t)(d.y + site) * 4;
+      const double* src = ((d.z & WF_SIBSLOT) ? part1 : part0) + ((size_t)d.y * Sp + site) * 4;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 2) : "memory");
     }
@@ -579,8 +580,8 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
       const int sib = fwd0 ? d.z : d.y;
       const bool sibTip = (fl & (fwd0 ? TF_C1TIP : TF_C0TIP)) != 0;
       uint4 w;
-      w.x = (unsigned)(((size_t)d.x * R + r) * Sp);
-      w.y = sibTip ? (unsigned)((size_t)sib * Sp) : (unsigned)(((size_t)sib * R + r) * Sp);
+      w.x = (unsigned)(d.x * R + r);
+      w.y = sibTip ? (unsigned)sib : (unsigned)(sib * R + r);
       w.z = ((fl & TF_OUTSLOT) ? WF_OUTSLOT : 0) | (sibTip ? WF_SIBTIP : 0) | ((fl & (fwd0 ? TF_C1SLOT : TF_C0SLOT)) ? WF_SIBSLOT : 0) |
             ((fl & TF_WITHIN) ? WF_SET : 0) | (fwd0 ? WF_FWD0 : 0);
       w.w = (unsigned)d.x;
@@ -619,11 +620,11 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
       matvec4(P, prev, ct);
       float e = 0.0f;
       if (d.z & WF_FWD0) combineExact(ct, sb, s4, e); else combineExact(sb, ct, s4, e);
-      double* const outp = ((d.z & WF_OUTSLOT) ? part1 : part0) + (size_t)(d.x + site) * 4;
+      double* const outp = ((d.z & WF_OUTSLOT) ? part1 : part0) + ((size_t)d.x * Sp + site) * 4;
       st256(outp, s4[0], s4[1], s4[2], s4[3]);
 #pragma unroll
       for (int q = 0; q < 4; q++) prev[q] = s4[q];
-      if (e != 0.0f) { v.expoOf(d.z & WF_OUTSLOT)[(size_t)d.x + site] = e; myMask |= 1u << (k & (WALK_WIN - 1)); }
+      if (e != 0.0f) { v.expoOf(d.z & WF_OUTSLOT)[(size_t)d.x * Sp + site] = e; myMask |= 1u << (k & (WALK_WIN - 1)); }
 
       if ((k & (WALK_WIN - 1)) == WALK_WIN - 1 || k == cn - 1) {
         // end of a window: three rotating masks, so that one barrier per window orders set -> read -> reset
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
           const int b = __ffs(z) - 1;
           z &= z - 1;
           const uint4 dz = s_desc[w0 + b];
-          v.expoOf(dz.z & WF_OUTSLOT)[(size_t)dz.x + site] = 0.0f;
+          v.expoOf(dz.z & WF_OUTSLOT)[(size_t)dz.x * Sp + site] = 0.0f;
         }
         if (tid < cnt) {
           const uint4 dz = s_desc[w0 + tid];

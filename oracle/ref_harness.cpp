@@ -18,6 +18,7 @@
 #include <cstring>
 
 #ifdef HARNESS_DMPC
+#include <Rcpp.h>
 #include "dmpc.h"
 #else
 #include "AugTree.h"
@@ -226,6 +227,29 @@ void ref_check_and_cull_map(void* hv, unsigned allowed, float cullProportion, co
 }
 
 #ifdef HARNESS_DMPC
+// ---- the SEXP-level glue of the R package skeleton (rpkg/src/RcppExports.cpp), compiled against the stand-in too
+extern "C" SEXP _DMphyClus_getMaxMapSizeEstimate(SEXP, SEXP);
+extern "C" void R_init_DMphyClus(DllInfo*);
+// one call through the registered SEXP entry point (host-only arithmetic: needs no GPU)
+double ref_glue_max_map_size_estimate(double mb, unsigned numRateCats) {
+  Scope sc;
+  SEXP r = _DMphyClus_getMaxMapSizeEstimate(wrap(mb), wrap((double)numRateCats));
+  return r->real.empty() ? -1.0 : r->real[0];
+}
+// the routine table R_init_DMphyClus registers: names separated by ';' and the argument counts
+int ref_registered_routines(char* names, int cap, int* nargs, int maxRoutines) {
+  DllInfo d; d.calls = 0;
+  R_init_DMphyClus(&d);
+  std::string all;
+  int n = 0;
+  for (const R_CallMethodDef* c = d.calls; c && c->name; c++) {
+    if (n < maxRoutines) nargs[n] = c->numArgs;
+    all += c->name; all += ';';
+    n++;
+  }
+  std::strncpy(names, all.c_str(), cap - 1); names[cap - 1] = 0;
+  return n;
+}
 // ---- introspection through the C-ABI
 double ref_loglik(void*) { return 0.0; }
 long ref_dictionary_size(void*) { return 0; }

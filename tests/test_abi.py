@@ -19,8 +19,8 @@ def lib():
     return load_library()
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "dmpc.h")).read()
+def declared_symbols(header="dmpc.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return set(re.findall(r"\b(dmpc_[a-z0-9_]+)\s*\(", src))
 
@@ -28,9 +28,12 @@ def declared_symbols():
 def test_header_symbols_exported_and_bound(lib):
     from dmphyclus_b200.engine import ABI
     syms = declared_symbols()
-    assert len(syms) >= 25
-    assert syms == set(ABI), syms ^ set(ABI)
-    for s in syms:
+    hooks = declared_symbols("dmpc_test.h")            # host-only test hooks: same library, separate header
+    assert len(syms) >= 25 and hooks and not (syms & hooks)
+    assert all(h.startswith(("dmpc_hp_", "dmpc_plan_selfcheck")) for h in hooks), hooks
+    assert not any(s.startswith("dmpc_hp_") for s in syms)        # the product header carries no test hook
+    assert syms | hooks == set(ABI), (syms | hooks) ^ set(ABI)
+    for s in syms | hooks:
         assert getattr(lib, s) is not None
 
 
