@@ -42,7 +42,9 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status block
 // a plan never holds more than one task per internal vertex, two tokens and two tip-list entries per fused vertex
-constexpr size_t PLAN_BYTES = sizeof(Task) + 2 * sizeof(Token) + 2 * sizeof(int32_t);
+// ... and at most one segment per task (+ the closing entry of the segment table: PLAN_SLACK)
+constexpr size_t PLAN_BYTES = sizeof(Task) + 2 * sizeof(Token) + 2 * sizeof(int32_t) + sizeof(int32_t);
+constexpr size_t PLAN_SLACK = 64;
 
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
 // and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
@@ -110,7 +112,7 @@ struct dmpc_tree {
   HostTree::Plan plan;
   // what runPlan launches: the plan just built (d_tasks ...) or the cached full-evaluation plan replayed with a slot flip
   const HostTree::Plan* runPlanMeta = nullptr;
-  const Task* runTasks = nullptr; const Token* runTokens = nullptr; const int32_t* runTips = nullptr;
+  const Task* runTasks = nullptr; const Token* runTokens = nullptr; const int32_t* runTips = nullptr; const int32_t* runSegs = nullptr;
   int runFlip = 0;
   struct {
     bool valid = false;
@@ -119,7 +121,7 @@ struct dmpc_tree {
     std::vector<uint8_t> within, cur;
     HostTree::Plan meta;                 // level structure and counters (the big vectors stay empty)
     char* dPlan = nullptr;               // device copy of the packed plan
-    size_t offTok = 0, offTip = 0, bytes = 0;
+    size_t offTok = 0, offTip = 0, offSeg = 0, bytes = 0;
     int metaTasks = 0;
   } cache;
   unsigned long long planCacheHits = 0;
@@ -129,7 +131,7 @@ struct dmpc_tree {
   bool capturing = false, gatherPrelaunched = false;
   unsigned long long graphReplays = 0;
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
-  size_t planOffTok = 0, planOffTip = 0, planBytes = 0;   // layout of the plan last packed into d_plan
+  size_t planOffTok = 0, planOffTip = 0, planOffSeg = 0, planBytes = 0;   // layout of the plan last packed into d_plan
   unsigned pubExpected = 0;      // status publications k_root_gather has been asked for so far (see DevStatus::pubSeq)
   bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
@@ -188,7 +190,7 @@ int acquirePack(dmpc_tree* t) {
     if (p.h_curList) cudaFreeHost(p.h_curList);
     p.h_plan = nullptr; p.h_curList = nullptr; p.cap = 0;
     const size_t cap = std::max<size_t>(1024, (size_t)t->nInt * 5 / 4);
-    CUDA_TRY(cudaHostAlloc((void**)&p.h_plan, cap * PLAN_BYTES, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&p.h_plan, cap * PLAN_BYTES + PLAN_SLACK, cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_curList, cap * sizeof(int32_t), cudaHostAllocDefault));
     p.cap = cap;
   }
@@ -317,7 +319,6 @@ void claimConstants(dmpc_tree* t) {
 int rootStage(dmpc_tree* t, double* ll);
 int launchRootSequence(dmpc_tree* t);
 
-constexpr int NARROW_LEVEL = 4;   // levels with at most this many tasks are chained into one launch
 
 // timing events: inside a stream capture they become event-record nodes that record the (external) event on every replay
 int recordEv(dmpc_tree* t, int i) {
@@ -326,9 +327,11 @@ int recordEv(dmpc_tree* t, int i) {
   return DMPC_OK;
 }
 
-int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
+// segs != nullptr: block column z walks the tasks [segs[z], segs[z + 1]) of `lt` in order; else task z (stride gridDim.z)
+int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks, const int32_t* segs = nullptr) {
   PruneArgs a{};
   a.tasks = lt; a.nTasks = nTasks; a.prog = t->runTokens; a.tipList = t->runTips; a.violation = &t->rv.st->violation; a.flip = t->runFlip;
+  a.segStart = segs;
   // 2 sites per thread, 5 blocks per SM (96 registers): measured best on B200 — 4 sites per thread (168-212 registers,
   // 12-16 warps per SM) is 1.3-1.6x slower, 6 blocks per SM (80 registers, spills) 1.05x (profiles/r02_prune_variants.md)
   if (t->exact) k_prune<true, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
@@ -339,19 +342,22 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks) {
 // tasks | tokens | tip list of a plan, packed into the pinned staging buffer and uploaded in ONE copy; sets what
 // runPlan / launchPrune read
 int uploadPlan(dmpc_tree* t, const HostTree::Plan& p) {
-  const size_t nT = p.tasks.size(), nK = p.tokens.size(), nL = p.tipList.size();
-  if (nT > (size_t)t->nInt || nK > 2 * (size_t)t->nInt || nL > 2 * (size_t)t->nInt)
+  const size_t nT = p.tasks.size(), nK = p.tokens.size(), nL = p.tipList.size(), nS = p.segStart.size();
+  if (nT > (size_t)t->nInt || nK > 2 * (size_t)t->nInt || nL > 2 * (size_t)t->nInt || nS > nT + 1)
     return fail(DMPC_ERR_STATE, "plan larger than its staging buffer");
   t->planOffTok = nT * sizeof(Task);
   t->planOffTip = t->planOffTok + nK * sizeof(Token);
-  t->planBytes = t->planOffTip + nL * sizeof(int32_t);
+  t->planOffSeg = t->planOffTip + nL * sizeof(int32_t);
+  t->planBytes = t->planOffSeg + nS * sizeof(int32_t);
   if (nT) std::memcpy(t->h_plan, p.tasks.data(), nT * sizeof(Task));
   if (nK) std::memcpy(t->h_plan + t->planOffTok, p.tokens.data(), nK * sizeof(Token));
   if (nL) std::memcpy(t->h_plan + t->planOffTip, p.tipList.data(), nL * sizeof(int32_t));
+  if (nS) std::memcpy(t->h_plan + t->planOffSeg, p.segStart.data(), nS * sizeof(int32_t));
   if (t->planBytes) CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
   t->runTasks = reinterpret_cast<const Task*>(t->d_plan);
   t->runTokens = reinterpret_cast<const Token*>(t->d_plan + t->planOffTok);
   t->runTips = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffTip);
+  t->runSegs = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffSeg);
   t->runFlip = 0;
   return DMPC_OK;
 }
@@ -365,26 +371,20 @@ int runPlan(dmpc_tree* t) {
   int rcE;
   if ((rcE = recordEv(t, 0))) return rcE;
   int launches = 0;
-  for (int l = 0; l < nLevels;) {
-    int n = p.levelStart[l + 1] - p.levelStart[l];
-    const Task* lt = t->runTasks + p.levelStart[l];
-    // a run of narrow levels goes into ONE launch whose blocks walk the tasks in order (gridDim.z == 1)
-    int l2 = l + 1;
-    bool run = n <= NARROW_LEVEL;
-    if (run) while (l2 < nLevels && p.levelStart[l2 + 1] - p.levelStart[l2] <= NARROW_LEVEL) l2++;
-    if (run && l2 > l + 1) n = p.levelStart[l2] - p.levelStart[l]; else { run = false; l2 = l + 1; }
-    // grid = (rate, site tile, task): blocks that share a task's masks and tokens are scheduled next to each other;
-    // gridDim.z is limited to 65535, wider levels go out in slices
-    for (int off = 0; off < n; off += 65535) {
-      const int m = run ? n : std::min(65535, n - off);
-      const dim3 grid((unsigned)t->R, (unsigned)t->T, run ? 1u : (unsigned)m);
-      int rc = launchPrune(t, grid, lt + off, m);
+  if ((int)p.unitSeg.size() != nLevels + 1) return fail(DMPC_ERR_STATE, "plan: launch units and segment table disagree");
+  for (int l = 0; l < nLevels; l++) {
+    // one launch per unit (the materialised clades, then the rounds): grid = (rate, site tile, segment) — blocks that
+    // share a task's masks and tokens are scheduled next to each other; gridDim.z is limited to 65535, wider units go
+    // out in slices.  Segment boundaries are task indices of the whole plan, so every slice gets the plan's task array.
+    const int s0 = p.unitSeg[l], nSeg = p.unitSeg[l + 1] - s0;
+    for (int off = 0; off < nSeg; off += 65535) {
+      const int m = std::min(65535, nSeg - off);
+      const dim3 grid((unsigned)t->R, (unsigned)t->T, (unsigned)m);
+      int rc = launchPrune(t, grid, t->runTasks, 0, t->runSegs + s0 + off);
       if (rc) return rc;
       t->st.kernel_launches++;
       launches++;
-      if (run) break;
     }
-    l = l2;
   }
   if (p.chainLevels) {
     const int first = p.levelStart[nLevels], n = p.levelStart[nAll] - first;     // one task per level: n == chainLevels
@@ -424,18 +424,35 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   auto& cc = t->cache;
   if (full && cc.valid && cc.fuse == ht.fuseTips && cc.kids == ht.kids && cc.within == ht.within) {
     flip = ht.cur[ht.root()] ^ cc.cur[ht.root()];
-    hit = true;
-    for (int v = ht.numTips; v < ht.numVerts && hit; v++) hit = (ht.cur[v] ^ cc.cur[v]) == flip;
+    // every internal vertex's slot bit must differ from the cached plan's by the same flip: eight vertices per compare
+    const uint8_t* a = ht.cur.data() + ht.numTips;
+    const uint8_t* b = cc.cur.data() + ht.numTips;
+    const size_t n = (size_t)(ht.numVerts - ht.numTips);
+    const uint64_t want = flip ? 0x0101010101010101ull : 0ull;
+    uint64_t diff = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t x, y; std::memcpy(&x, a + i, 8); std::memcpy(&y, b + i, 8); diff |= (x ^ y) ^ want; }
+    for (; i < n; i++) diff |= (uint64_t)((a[i] ^ b[i]) ^ flip);
+    hit = diff == 0;
   }
   const HostTree::Plan* meta = &p;
   if (hit) {
-    for (int v = ht.numTips; v < ht.numVerts; v++) { ht.cur[v] ^= 1; ht.touched[v] = 1; ht.solved[v] = 1; }
+    {
+      uint8_t* c = ht.cur.data() + ht.numTips;
+      const size_t n = (size_t)(ht.numVerts - ht.numTips);
+      size_t i = 0;
+      for (; i + 8 <= n; i += 8) { uint64_t x; std::memcpy(&x, c + i, 8); x ^= 0x0101010101010101ull; std::memcpy(c + i, &x, 8); }
+      for (; i < n; i++) c[i] ^= 1;
+      std::fill(ht.touched.begin() + ht.numTips, ht.touched.end(), (uint8_t)1);
+      std::fill(ht.solved.begin() + ht.numTips, ht.solved.end(), (uint8_t)1);
+    }
     ht.allInvalid = false;
     if ((rc = allocSlot(t, 0)) || (rc = allocSlot(t, 1))) return rc;
     meta = &cc.meta;
     t->runTasks = reinterpret_cast<const Task*>(cc.dPlan);
     t->runTokens = reinterpret_cast<const Token*>(cc.dPlan + cc.offTok);
     t->runTips = reinterpret_cast<const int32_t*>(cc.dPlan + cc.offTip);
+    t->runSegs = reinterpret_cast<const int32_t*>(cc.dPlan + cc.offSeg);
     t->runFlip = flip;
     t->planCacheHits++;
   } else {
@@ -450,11 +467,11 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     if ((rc = uploadPlan(t, p))) return rc;
     if (full && nT) {                                // remember it (one device-to-device copy, stream-ordered)
       int r2;
-      if (!cc.dPlan && (r2 = t->alloc(&cc.dPlan, (size_t)t->nInt * PLAN_BYTES))) return r2;
+      if (!cc.dPlan && (r2 = t->alloc(&cc.dPlan, (size_t)t->nInt * PLAN_BYTES + PLAN_SLACK))) return r2;
       CUDA_TRY(cudaMemcpyAsync(cc.dPlan, t->d_plan, t->planBytes, cudaMemcpyDeviceToDevice, t->stream));
-      cc.offTok = t->planOffTok; cc.offTip = t->planOffTip; cc.bytes = t->planBytes;
+      cc.offTok = t->planOffTok; cc.offTip = t->planOffTip; cc.offSeg = t->planOffSeg; cc.bytes = t->planBytes;
       cc.kids = ht.kids; cc.within = ht.within; cc.cur = curBefore; cc.fuse = ht.fuseTips;
-      cc.meta.levelStart = p.levelStart;
+      cc.meta.levelStart = p.levelStart; cc.meta.unitSeg = p.unitSeg;
       cc.meta.chainLevels = p.chainLevels; cc.meta.materialised = p.materialised;
       cc.meta.storedReads = p.storedReads; cc.meta.tipReads = p.tipReads; cc.meta.fusedOps = p.fusedOps; cc.meta.fp64Ops = p.fp64Ops;
       cc.meta.tasks.clear(); cc.metaTasks = nT;
@@ -531,7 +548,7 @@ void attachComm(dmpc_tree* t) {
   t->rv.comm.world = 1;
   if (!(t->deferred && t->comm && t->comm->connected && t->comm->device == t->device)) return;
   const dmpc_comm& c = *t->comm;
-  if (XHDR + t->nChunks + t->T * xrec(t->rv.RP) > c.width) return;       // the message would not fit: host protocol
+  if (XHDR + t->nChunks + t->T * CPT * xrec(t->rv.RP) > c.width) return;       // the message would not fit: host protocol
   CommView& cv = t->rv.comm;
   cv.world = c.world; cv.rank = c.rank; cv.width = c.width; cv.seq = c.seq;
   for (int p = 0; p < c.world; p++) {
@@ -706,7 +723,7 @@ int rootStage(dmpc_tree* t, double* ll) {
       continue;
     }
     float ms = 0;
-    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms;
+    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms; t->st.prune_ms_total += ms;
     t->evalTimePending = true;
     if (hostProtocol) {
       t->chunksOnHost = t->h_res->nact == 0;
@@ -1006,6 +1023,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
   t->nFlag = (numTips + 15) & ~15;
   t->ht.fuseTips = std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
+  if (const char* gc = std::getenv("DMPC_GROUP_COST")) t->ht.groupCost = std::max(0, std::atoi(gc));   // experiments: 0 = one launch per level
   t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;
   t->T = t->Sp / TILE;
@@ -1042,7 +1060,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     want(&t->d_tipmask, (size_t)t->N * t->Sp);
     want(&stage, (size_t)t->N * t->S);
     want(&t->d_lut, (size_t)2 * t->R * 64);
-    want(&t->d_plan, (size_t)t->nInt * PLAN_BYTES);
+    want(&t->d_plan, (size_t)t->nInt * PLAN_BYTES + PLAN_SLACK);
     want(&t->d_curList, (size_t)t->nInt);
     want(&t->dv.cur, (size_t)t->nInt);
     want(&t->rv.kmax, (size_t)t->Sp);
@@ -1057,7 +1075,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     want(&t->rv.carryOut, (size_t)RMAX);
     want(&t->rv.sitell, (size_t)t->Sp);
     want(&t->rv.chunk, (size_t)t->T * CPT);
-    want(&t->rv.tileRec, (size_t)t->T * xrec(t->rv.RP));
+    want(&t->rv.tileRec, (size_t)t->T * CPT * xrec(t->rv.RP));
     want(&t->rv.st, (size_t)1);
     setElistGeometry(t, 8);
     want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
@@ -1413,7 +1431,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       rb.carryOut = (float*)dalloc((size_t)nb * RMAX * 4);
       rb.sitell = (double*)dalloc((size_t)nb * Sp * 8);
       rb.chunk = (double*)dalloc((size_t)nb * T * CPT * 8);
-      rb.tileRec = (double*)dalloc((size_t)nb * T * xrec(t->rv.RP) * 8);
+      rb.tileRec = (double*)dalloc((size_t)nb * T * CPT * xrec(t->rv.RP) * 8);
       rb.st = (DevStatus*)dalloc((size_t)nb * sizeof(DevStatus));
       bool okAlloc = true;
       for (void* q : tmp) okAlloc &= q != nullptr;
@@ -1510,6 +1528,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
       out->device_bytes += s1.device_bytes; out->last_algorithmic_bytes += s1.last_algorithmic_bytes; out->last_fp64_ops += s1.last_fp64_ops;
       out->last_active_tiles += s1.last_active_tiles; out->last_chain_sites += s1.last_chain_sites; out->last_chain_rows += s1.last_chain_rows;
       out->last_eval_ms = std::max(out->last_eval_ms, s1.last_eval_ms); out->last_prune_ms = std::max(out->last_prune_ms, s1.last_prune_ms);
+      out->prune_ms_total = std::max(out->prune_ms_total, s1.prune_ms_total);
       out->last_host_total_us = std::max(out->last_host_total_us, s1.last_host_total_us);
       out->create_upload_ms = std::max(out->create_upload_ms, s1.create_upload_ms);
       out->exponent_capacity = std::max(out->exponent_capacity, s1.exponent_capacity);
@@ -1639,7 +1658,21 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
   }
   const int N = numTips, nInt = N - 1;
   auto bad = [&](const std::string& m) { return fail(DMPC_ERR_STATE, "plan self-check: " + m); };
-  std::vector<int> computedAt(nInt, -1);          // level at which each internal vertex is computed
+  std::vector<int> computedAt(nInt, -1);          // launch unit in which each internal vertex is computed
+  std::vector<int> computedSeg(nInt, -1), computedPos(nInt, -1), segOfTask(p.tasks.size(), -1);
+  // segments: contiguous, covering exactly the tasks below the chain, each inside one launch unit
+  {
+    const int nUnits = (int)p.levelStart.size() - 1 - p.chainLevels;
+    if ((int)p.unitSeg.size() != nUnits + 1 || p.segStart.empty() || p.segStart.front() != 0) return bad("segment table shape");
+    for (int u = 0; u < nUnits; u++) {
+      if (p.unitSeg[u + 1] < p.unitSeg[u] || p.unitSeg[u + 1] >= (int)p.segStart.size()) return bad("unit -> segment range");
+      if (p.segStart[p.unitSeg[u]] != p.levelStart[u] || p.segStart[p.unitSeg[u + 1]] != p.levelStart[u + 1]) return bad("segments do not tile their launch unit");
+      for (int sg = p.unitSeg[u]; sg < p.unitSeg[u + 1]; sg++) {
+        if (p.segStart[sg + 1] <= p.segStart[sg]) return bad("empty segment");
+        for (int i = p.segStart[sg]; i < p.segStart[sg + 1]; i++) segOfTask[i] = sg;
+      }
+    }
+  }
   std::vector<uint8_t> asTask(nInt, 0), readStored(nInt, 0);
   const int nLevels = (int)p.levelStart.size() - 1;
   int maxDepth = 0, maxTips = 0, fusedCount = 0;
@@ -1662,7 +1695,9 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
         if (ht.kids[2 * (k.out + N) + c] != idx + N) return bad("operand is not the vertex's child");
         if (fus) continue;
         readStored[idx] = 1;
-        if (computedAt[idx] >= l) return bad("stored operand not computed at a lower level");
+        // a stored operand comes from an earlier launch, or from an earlier task of the SAME segment (one block walks it)
+        if (computedAt[idx] > l || (computedAt[idx] == l && !(computedSeg[idx] == segOfTask[i] && segOfTask[i] >= 0 && computedPos[idx] < i)))
+          return bad("stored operand not computed before its reader");
         if (computedAt[idx] < 0 && (full || dirty[idx + N])) return bad("stored operand is dirty but not part of the plan");
         ht.computeTips();
         if (computedAt[idx] < 0 && ht.fused(idx + N)) return bad("a fused-size operand is read from HBM without having been materialised");
@@ -1692,7 +1727,7 @@ int dmpc_plan_selfcheck(const int32_t* edge, int nEdgeRows, int numTips, const d
         off += n;
       }
       if (maxDepth > FUSE_DEPTH) return bad("stack deeper than FUSE_DEPTH");
-      computedAt[k.out] = l;
+      computedAt[k.out] = l; computedSeg[k.out] = segOfTask[i]; computedPos[k.out] = i;
       asTask[k.out] = 1;
     }
   if (full) { for (int v = 0; v < nInt; v++) if (computedAt[v] < 0) return bad("vertex never computed"); }
@@ -2032,8 +2067,8 @@ int dmpc_comm_create(int device, int rank, int world, int maxChunksPerRank, dmpc
   CUDA_TRY(cudaSetDevice(device));
   dmpc_comm* c = new dmpc_comm;
   c->device = device; c->rank = rank; c->world = world; c->maxChunks = maxChunksPerRank;
-  // a message: header, chunk sums, and (when a site rescaled) one certificate record per 256-site tile
-  c->width = XHDR + maxChunksPerRank + ((maxChunksPerRank + CPT - 1) / CPT + 1) * XREC_MAX;
+  // a message: header, chunk sums, and (when a site rescaled) one certificate record per 64-site chunk
+  c->width = XHDR + maxChunksPerRank + (maxChunksPerRank + CPT) * XREC_MAX;
   if (cudaMalloc(&c->local, c->bytes() + 64) != cudaSuccess) { delete c; return fail(DMPC_ERR_CUDA, "cudaMalloc of the mailbox failed"); }
   CUDA_TRY(cudaMemset(c->local, 0, c->bytes() + 64));
   c->seq = (unsigned*)((char*)c->local + c->bytes());          // counter lives behind the mailbox proper

@@ -361,7 +361,11 @@ struct HostTree {
     std::vector<Task> tasks;
     std::vector<Token> tokens;
     std::vector<int32_t> tipList;                // tips read by the fused programs, task by task
-    std::vector<int> levelStart;
+    std::vector<int> levelStart;                 // task range of every LAUNCH UNIT: [materialised clades], the rounds, then one
+                                                 // unit per chain level (k_walk takes those together)
+    std::vector<int> segStart;                   // task range of every segment (group) of the non-chain units, in task order
+    std::vector<int> unitSeg;                    // first segment of each non-chain unit (+ end): unit u = segments
+                                                 // [unitSeg[u], unitSeg[u+1]), one block column (gridDim.z) each
     long long storedReads = 0, tipReads = 0, fusedOps = 0;
     long long fp64Ops = 0;                       // DMUL + DADD per (site, rate) of the whole plan: a 4x4 mat-vec is 16 + 12, the
                                                  // product of the two child terms 4; a tip's term is a table look-up
@@ -369,6 +373,7 @@ struct HostTree {
     int materialised = 0;                        // fused-size clades evaluated as stored tasks for that chain (level 0 of the plan)
     bool uses[2] = {false, false};               // slots this plan writes
     std::vector<int> pre, level, cnt, fill;      // scratch
+    std::vector<int> grp, gRound, gCost, gHead, gNext, gTail;   // scratch of the path grouping
   };
 
   // mutate = false: introspection replay — tokens address the CURRENT slots and no state changes
@@ -469,13 +474,25 @@ struct HostTree {
     }
   }
 
+  // Groups.  Evaluated level by level, every level of the dirty tree costs a launch plus a full load -> compute ->
+  // store round trip, and the upper levels of a tree hold a handful of tasks each: with few site tiles per GPU (a
+  // site-sharded run) the device idles through two dozen dependent launches.  Instead the dirty stored vertices are
+  // split into vertical PATHS: a vertex joins the path of the child whose path started later (higher round), or opens a
+  // new round when both children's rounds are equal — the Strahler numbering of the dirty tree, so the number of
+  // rounds is ~log4 of the number of stored vertices instead of the tree's height.  One launch per round; one block
+  // column (gridDim.z) per path, walking its tasks bottom-up in program order: a thread only ever reads partials of its
+  // own (site, rate), so inside a path the child -> parent dependency is the thread's own store followed by its own load.
+  // groupCost caps the serial work of a path (stored vertex = 2 units, fused vertex = 1); 0 = one task per segment and
+  // one launch per level (the round-1 schedule, kept for comparison).
+  int groupCost = 128;
+
   void plan(Plan& p) {
     allInvalid = false;
-    p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear();
+    p.tasks.clear(); p.tokens.clear(); p.tipList.clear(); p.levelStart.clear(); p.segStart.clear(); p.unitSeg.clear();
     p.storedReads = p.tipReads = p.fusedOps = p.fp64Ops = 0;
     p.chainLevels = p.materialised = 0;
     p.uses[0] = p.uses[1] = false;
-    if (solved[root()]) { p.levelStart.push_back(0); return; }
+    if (solved[root()]) { p.levelStart.push_back(0); p.segStart.push_back(0); p.unitSeg.push_back(0); return; }
     computeTips();
     std::vector<int>& pre = p.pre;
     pre.clear();
@@ -501,21 +518,84 @@ struct HostTree {
     for (int l = maxLevel; l >= 1 && p.cnt[l] == 1; l--) chainL0 = l;
     p.chainLevels = maxLevel - chainL0 + 1;
     if (p.chainLevels < CHAIN_MIN || !walkChains) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
-    std::vector<int> matList;                // fused clades hanging off the chain: stored tasks of a leading level
+    std::vector<int> matList;                // fused clades hanging off the chain: stored tasks of a leading unit
     if (p.chainLevels)
       for (int v : pre)
         if (level[v] >= chainL0)
           for (int i = 0; i < 2; i++) { const int c = kids[2 * v + i]; if (!isTip(c) && fused(c)) { mat[c] = 1; matList.push_back(c); } }
     p.materialised = (int)matList.size();
-    const int lead = matList.empty() ? 0 : 1;
-    p.levelStart.assign(maxLevel + lead + 1, 0);   // level l (1-based) = tasks[levelStart[l-1+lead] .. levelStart[l+lead])
-    int acc = (int)matList.size();
-    for (int l = 1; l <= maxLevel; l++) { p.levelStart[l - 1 + lead] = acc; acc += p.cnt[l]; }
-    p.levelStart[maxLevel + lead] = acc;
-    p.fill.assign(p.levelStart.begin(), p.levelStart.end());
-    std::vector<int> order((size_t)acc);
-    for (size_t i = 0; i < matList.size(); i++) order[i] = matList[i];
-    for (int v : pre) order[p.fill[level[v] - 1 + lead]++] = v;
+
+    // ---- the vertices below the chain, grouped into paths and rounds
+    std::vector<int>& grp = p.grp;           // group of each dirty stored vertex below the chain
+    if ((int)grp.size() != numVerts) grp.assign(numVerts, -1);
+    std::vector<int>&gRound = p.gRound, &gCost = p.gCost, &gHead = p.gHead, &gNext = p.gNext, &gTail = p.gTail;
+    gRound.clear(); gCost.clear(); gHead.clear(); gTail.clear();
+    if ((int)gNext.size() != numVerts) gNext.assign(numVerts, -1);   // members of a group: linked list, bottom-up
+    int nRounds = 0;
+    for (size_t i = pre.size(); i-- > 0;) {
+      const int v = pre[i];
+      if (level[v] >= chainL0) continue;
+      int cost = 2, best = -1, other = -1;
+      for (int j = 0; j < 2; j++) {
+        const int c = kids[2 * v + j];
+        if (isTip(c)) continue;
+        if (fused(c)) { cost += tips[c] - 1; continue; }
+        if (level[c] == 0) continue;         // clean stored child: already in HBM
+        const int g = grp[c];
+        if (best < 0) best = g;
+        else if (gRound[g] > gRound[best] || (gRound[g] == gRound[best] && gCost[g] > gCost[best])) { other = best; best = g; }
+        else other = g;
+      }
+      int round = 0;
+      if (other >= 0) round = gRound[other] + 1;                                        // the path not taken closes below v
+      // v extends the path of its later child — unless both children's paths are of the same round: pulling one of them
+      // (all of it) into the next round would make two independent subtrees run one after the other
+      const bool join = groupCost > 0 && best >= 0 && gCost[best] + cost <= groupCost && (other < 0 || gRound[best] >= round);
+      if (join) {
+        gCost[best] += cost;
+        gNext[gTail[best]] = v; gTail[best] = v;
+        grp[v] = best;
+        nRounds = std::max(nRounds, gRound[best] + 1);
+      } else {
+        if (best >= 0) round = std::max(round, gRound[best] + 1);
+        grp[v] = (int)gRound.size();
+        gRound.push_back(round); gCost.push_back(cost); gHead.push_back(v); gTail.push_back(v);
+        nRounds = std::max(nRounds, round + 1);
+      }
+    }
+    const int nGroups = (int)gRound.size();
+    // task order: materialised clades (one segment each), then round by round, group by group, bottom-up; then the chain
+    std::vector<int> order;
+    order.reserve(pre.size() + matList.size());
+    p.unitSeg.push_back(0);
+    for (int c : matList) { p.segStart.push_back((int)order.size()); order.push_back(c); }
+    if (!matList.empty()) { p.levelStart.push_back(0); p.unitSeg.push_back((int)p.segStart.size()); }
+    {
+      std::vector<int>& cnt = p.cnt;          // groups per round, then their order
+      cnt.assign(nRounds + 1, 0);
+      for (int g = 0; g < nGroups; g++) cnt[gRound[g] + 1]++;
+      for (int r = 0; r < nRounds; r++) cnt[r + 1] += cnt[r];
+      std::vector<int>& byRound = p.fill;
+      byRound.assign(nGroups, 0);
+      std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+      for (int g = 0; g < nGroups; g++) byRound[pos[gRound[g]]++] = g;
+      for (int r = 0; r < nRounds; r++) {
+        p.levelStart.push_back((int)order.size());
+        for (int q = cnt[r]; q < cnt[r + 1]; q++) {
+          p.segStart.push_back((int)order.size());
+          for (int v = gHead[byRound[q]]; v != -1; v = gNext[v]) order.push_back(v);
+        }
+        p.unitSeg.push_back((int)p.segStart.size());
+      }
+    }
+    p.segStart.push_back((int)order.size());
+    if (p.chainLevels) {
+      const size_t base = order.size();
+      order.resize(base + p.chainLevels);
+      for (int v : pre) if (level[v] >= chainL0) order[base + (level[v] - chainL0)] = v;
+      for (int l = 0; l < p.chainLevels; l++) p.levelStart.push_back((int)base + l);
+    }
+    p.levelStart.push_back((int)order.size());
     p.tasks.resize(order.size());
     for (size_t i = 0; i < order.size(); i++) {
       const int v = order[i];
@@ -532,7 +612,7 @@ struct HostTree {
       solved[v] = 1;                                  // ... _isSolved = true (:33)
     }
     for (int c : matList) mat[c] = 0;
-    for (int v : pre) level[v] = 0;
+    for (int v : pre) { level[v] = 0; grp[v] = -1; gNext[v] = -1; }
   }
 };
 

@@ -62,9 +62,9 @@ struct DevStatus {
   int cert;                     // chain mode: CERT_* — how certify() resolved the cross-locus exponent chain
   int chainSites, chainRows;    // what the literal walker (k_chain, or certify()'s prefix) walked: rescaled sites and rows
   unsigned pubSeq;              // number of times a root kernel has published this block to the host mirror
-  int certL0;                   // rescaled sites of the literal prefix (tiles 0 .. certTile)
+  int certL0;                   // rescaled sites of the literal prefix (chunks 0 .. certTile)
   int certRate;                 // the dominant rate category of the certified regime
-  int certTile;                 // last (local) site tile of the literal prefix; every later tile is certified
+  int certTile;                 // last (local) RCH-site chunk of the literal prefix; every later chunk is certified
   // %globaltimer stamps (ns) of the root stage, for the latency breakdown dmpc_get_root_timeline reports:
   //   0 first gather block starts    1 gather's last block found    2 exchange / quiet reduction done    3 certificate done
   //   4 first final block starts     5 final's last block found     6 final's exchange / reduction done
@@ -85,7 +85,7 @@ enum : int {
 // Peer mailboxes of a site-sharded run (one process per GPU of the box, NVLink/NVSwitch peer access — or several shards
 // of one process): every rank owns a mailbox in its HBM that all peers can store into.  Layout of a mailbox: unsigned
 // flag[CW] (sequence number of the last message of each sender), then double payload[2][CW][width] (double-buffered by
-// sequence parity): payload[.][sender] = { flags, nChunks, nTiles, 0, chunk sums[nChunks], tile records[nTiles][XREC] }.
+// sequence parity): payload[.][sender] = { flags, nChunks, nRecords, 0, chunk sums[nChunks], chunk records[nRecords][XREC] }.
 constexpr int CW = 8;            // ranks
 constexpr int XHDR = 4;          // doubles in front of the chunk sums of a message
 enum : int { XF_ACTIVE = 1 };    // message flags
@@ -115,7 +115,7 @@ struct RootView {
   float* carryOut;              // [RMAX]
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [T * CPT] sums of RCH consecutive sites (the first nChunks are real)
-  double* tileRec;              // [T][xrec(RP)] per-tile records of the chain certificate (k_root_gather -> certify)
+  double* tileRec;              // [T * CPT][xrec(RP)] per-chunk records of the chain certificate (k_root_gather -> certify)
   int nChunks;                  // ceil(S / RCH)
   int publishAtGather;          // 1: the gather's last block publishes the status (nothing is queued behind it)
   int certOn;                   // 0: certify() always answers CERT_LITERAL (tests compare both paths)
@@ -153,7 +153,7 @@ __device__ __forceinline__ RootView forProposal(RootView rv, int b, int Sp, int 
   rv.carryOut += (size_t)b * RMAX;
   rv.sitell += (size_t)b * sp;
   rv.chunk += (size_t)b * T * CPT;
-  rv.tileRec += (size_t)b * T * xrec(rv.RP);
+  rv.tileRec += (size_t)b * T * CPT * xrec(rv.RP);
   rv.st += b;
   rv.comm.world = 1;
   return rv;
@@ -195,9 +195,9 @@ __device__ __forceinline__ double row4(const double* Pi, double x0, double x1, d
 // evaluation with EXACT = true, where every fused vertex gets the reference's full two-check treatment, a
 // block vote, and exponent rows — and keeps that mode for the handle.
 //
-// A launch covers one level (gridDim.z = its tasks) or, with gridDim.z == 1, a run of narrow levels whose tasks
-// each block walks in order: a thread only ever reads partials of its own (site, rate), so the child -> parent
-// dependencies inside the run are plain program order.
+// A launch covers one ROUND of the plan (host_tree.hpp: the dirty tree split into vertical paths, Strahler-numbered):
+// block column z walks the tasks of path z bottom-up in order — a thread only ever reads partials of its own (site,
+// rate), so the child -> parent dependencies inside a path are plain program order (its own store, then its own load).
 __device__ __forceinline__ void matvec4(const double* __restrict__ P, const double (&x)[4], double (&y)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) y[i] = row4(P + 4 * i, x[0], x[1], x[2], x[3]);
@@ -244,6 +244,8 @@ struct PruneArgs {
   int flip;                     // 0/1, XORed into every slot bit of the tasks and tokens: a cached full-evaluation plan is
                                 // replayed with all slots toggled instead of being rebuilt and uploaded again
   const int* runStart;          // PATHS: [proposals + 1] task ranges
+  const int32_t* segStart;      // !PATHS: block column z walks the tasks [segStart[z], segStart[z + 1]) in order (null: task z,
+                                // stride gridDim.z)
   int* invalid;                 // PATHS: [proposals]
   PathView pv;                  // PATHS: per-proposal outputs
 };
@@ -272,9 +274,10 @@ __global__ void __launch_bounds__(TILE / SPT_, MINB) k_prune(DevView v, PruneArg
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   bool lutLoaded = false, trig = false;
   double prev[PATHS ? SPT_ : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
-  const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : (int)blockIdx.z;
-  const int tiEnd = PATHS ? pa_.runStart[blockIdx.z + 1] : pa_.nTasks;
-  const int tiStep = PATHS ? 1 : (int)gridDim.z;
+  const bool segs = !PATHS && pa_.segStart != nullptr;
+  const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : segs ? pa_.segStart[blockIdx.z] : (int)blockIdx.z;
+  const int tiEnd = PATHS ? pa_.runStart[blockIdx.z + 1] : segs ? pa_.segStart[blockIdx.z + 1] : pa_.nTasks;
+  const int tiStep = (PATHS || segs) ? 1 : (int)gridDim.z;
 
   for (int ti = tiBegin; ti < tiEnd; ti += tiStep) {
     const int4 tk0 = __ldg(reinterpret_cast<const int4*>(tasks + ti));
@@ -824,7 +827,7 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
       for (int p = cm.world; p <= CW; p++) s_base[p] = b;
     } else {
       s_base[0] = 0;
-      for (int p = 1; p <= CW; p++) s_base[p] = v.T;
+      for (int p = 1; p <= CW; p++) s_base[p] = v.T * CPT;
       s_rec[0] = rv.tileRec;
     }
   }
@@ -942,7 +945,7 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
   if (tid == 0) {
     st->cert = ok ? CERT_OK : CERT_LITERAL;
     st->certRate = dom;
-    st->certTile = tb - myBase;                   // local tile index: every local tile above it is certified
+    st->certTile = tb - myBase;                   // local chunk index: every local chunk above it is certified
     st->certL0 = L0;
     if (ok) { st->chainSites = 0; st->chainRows = 0; }
   }
@@ -953,9 +956,10 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
 #pragma unroll
   for (int r = 0; r < RP; r++) c[r] = 0.0f;
   int actBase = 0, rowsWalked = 0;
-  for (int lt = 0; lt <= tb && lt < v.T; lt++) {
+  const int litEnd = min(v.S, (tb + 1) * RCH);    // sites [0, litEnd) are walked
+  for (int lt = 0; lt * TILE < litEnd; lt++) {
     const int s = lt * TILE + tid;
-    const int km = s < v.S ? min(rv.kmax[s], rv.Kcap) : 0;
+    const int km = s < litEnd ? min(rv.kmax[s], rv.Kcap) : 0;
     const int actv = km > 0;
     int ic = actv, ir = km;
 #pragma unroll
@@ -968,7 +972,7 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
     int nA = 0, nR = 0;
 #pragma unroll
     for (int w = 0; w < TILE / 32; w++) { if (w < wid) { ic += s_scan[0][w]; ir += s_scan[1][w]; } nA += s_scan[0][w]; nR += s_scan[1][w]; }
-    if (s < v.S) rv.posIncl[s] = actBase + ic;
+    if (s < litEnd) rv.posIncl[s] = actBase + ic;
     const bool staged = nR <= CERT_ROWCAP;
     if (actv) {
       s_cnt[ic - 1] = km; s_site[ic - 1] = s;
@@ -982,10 +986,21 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
       int q = 0;
       for (int i = 0; i < nA; i++) {
         const int cnt = s_cnt[i];
-        const float* rows = staged ? reinterpret_cast<const float*>(s_rows) + (size_t)q * RP : rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
-        for (int j = 0; j < cnt; j++)
+        if (staged) {                               // (two loops: the staged one compiles to shared-memory loads)
+          for (int j = 0; j < cnt; j++) {
+            float4 w[V];
 #pragma unroll
-          for (int r = 0; r < RP; r++) if (r < R) c[r] = __fadd_rn(c[r], rows[j * RP + r]);
+            for (int u = 0; u < V; u++) w[u] = s_rows[(size_t)(q + j) * V + u];
+#pragma unroll
+            for (int r = 0; r < RP; r++)
+              if (r < R) { const float4 x = w[r >> 2]; c[r] = __fadd_rn(c[r], (r & 3) == 0 ? x.x : (r & 3) == 1 ? x.y : (r & 3) == 2 ? x.z : x.w); }
+          }
+        } else {
+          const float* rows = rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
+          for (int j = 0; j < cnt; j++)
+#pragma unroll
+            for (int r = 0; r < RP; r++) if (r < R) c[r] = __fadd_rn(c[r], rows[j * RP + r]);
+        }
         q += cnt;
         float m = c[0];
 #pragma unroll
@@ -1219,9 +1234,10 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
     //   S_r = the tile's total, maxPre[d][r] = max over the tile's sites (and 0) of (E_r - E_d) relative to the tile's
     //   entry, nAct / ops / absSum = what bounds the fp32 rounding the literal chain would commit inside the tile.
     constexpr int XR = xrec(RP);
-    double* const rec = rv.tileRec + (size_t)tile * XR;
+    static_assert(RCH == 64 && TILE / 32 == 2 * CPT, "a chunk record is built from two warps");
+    double* const rec = rv.tileRec + (size_t)tile * CPT * XR;
     if (!anyActive) {
-      for (int i = tid; i < XR; i += TILE) rec[i] = 0.0;
+      for (int i = tid; i < CPT * XR; i += TILE) rec[i] = 0.0;
     } else {
       const bool actS = valid && kmax > 0;
       double pre[RP], ab = 0.0;
@@ -1240,12 +1256,10 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
         s_x[wid][RP] = ab; s_x[wid][RP + 1] = ops; s_x[wid][RP + 2] = na;
       }
       __syncthreads();
+      if (wid & 1) {                                 // prefix relative to the chunk's first site
 #pragma unroll
-      for (int w = 0; w < TILE / 32; w++)
-        if (w < wid) {
-#pragma unroll
-          for (int r = 0; r < RP; r++) pre[r] += s_x[w][r];
-        }
+        for (int r = 0; r < RP; r++) pre[r] += s_x[wid - 1][r];
+      }
 #pragma unroll
       for (int d = 0; d < RP; d++)
 #pragma unroll
@@ -1256,19 +1270,17 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
           if (lane == 0) s_y[wid][d * RP + r] = mx;
         }
       __syncthreads();
-      if (tid < RP * RP) {
-        double mx = 0.0;
-#pragma unroll
-        for (int w = 0; w < TILE / 32; w++) mx = fmax(mx, s_y[w][tid]);
-        rec[4 + RP + tid] = mx;
-      } else if (tid < RP * RP + RP + 3) {
-        const int j = tid - RP * RP;                 // 0..RP-1: S_r; RP: absSum; RP+1: ops; RP+2: nAct
-        double acc = 0.0;
-#pragma unroll
-        for (int w = 0; w < TILE / 32; w++) acc += s_x[w][j];
-        if (j < RP) rec[4 + j] = acc; else if (j == RP) rec[2] = acc; else if (j == RP + 1) rec[1] = acc; else rec[0] = acc;
-      } else if (tid == RP * RP + RP + 3) {
-        rec[3] = 0.0;
+      constexpr int PER = RP * RP + RP + 4;          // maxPre[RP][RP], S_r[RP], absSum, ops, nAct, pad
+      for (int idx = tid; idx < CPT * PER; idx += TILE) {
+        const int q = idx / PER, j = idx - q * PER;
+        double* const rq = rec + (size_t)q * XR;
+        if (j < RP * RP) rq[4 + RP + j] = fmax(s_y[2 * q][j], s_y[2 * q + 1][j]);
+        else if (j == PER - 1) rq[3] = 0.0;
+        else {
+          const int jj = j - RP * RP;                // 0..RP-1: S_r; RP: absSum; RP+1: ops; RP+2: nAct
+          const double acc = s_x[2 * q][jj] + s_x[2 * q + 1][jj];
+          if (jj < RP) rq[4 + jj] = acc; else if (jj == RP) rq[2] = acc; else if (jj == RP + 1) rq[1] = acc; else rq[0] = acc;
+        }
       }
     }
   }
@@ -1293,7 +1305,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
         if (tid == 0) { rv.st->xok = -1; rv.st->ticket2 = 0; __threadfence(); if (pub) publishStatus(rv); }
         return;
       }
-      const int res = exchangeAndReduce(rv, rv.nChunks, quiet, s_red, (mode == 1 && !quiet) ? rv.tileRec : nullptr, gridDim.x, xrec(RP));
+      const int res = exchangeAndReduce(rv, rv.nChunks, quiet, s_red, (mode == 1 && !quiet) ? rv.tileRec : nullptr, gridDim.x * CPT, xrec(RP));
       if (tid == 0) { rv.st->xok = res; if (!BATCH) rv.st->stamp[2] = gtime(); }
       __syncthreads();
       if (res == 0 && mode == 1) certify<RP>(v, rv, reinterpret_cast<float4*>(s_list));
@@ -1552,7 +1564,7 @@ __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mod
       if (publish && !BATCH && blockIdx.x == 0 && tid == 0) publishStatus(rv);
       return;
     }
-    if ((int)blockIdx.x > rv.st->certTile) dom = rv.st->certRate;
+    if (s / RCH > rv.st->certTile) dom = rv.st->certRate;       // (per site: the prefix may end inside this tile)
   }
   if (!BATCH && tid == 0) atomicMin(&rv.st->stamp[4], gtime());
   double ll = 0.0;

@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("last_chain_sites", C.c_int), ("last_chain_rows", C.c_int), ("chain_group", C.c_int),
                 ("plan_cache_hits", C.c_ulonglong), ("graph_replays", C.c_ulonglong),
                 ("last_walk_steps", C.c_int), ("last_materialised", C.c_int),
-                ("last_cert", C.c_int), ("last_cert_rate", C.c_int), ("last_fp64_ops", C.c_ulonglong)]
+                ("last_cert", C.c_int), ("last_cert_rate", C.c_int), ("prune_ms_total", C.c_double), ("last_fp64_ops", C.c_ulonglong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

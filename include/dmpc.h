@@ -171,6 +171,8 @@ typedef struct dmpc_stats {
   int last_cert;            /* how the cross-locus exponent chain of the last evaluation was resolved: 0 = no site
                                rescaled, 1 = by certificate (last_chain_sites = its literal prefix), 2 = walked literally */
   int last_cert_rate;       /* the dominant rate category of the certified regime (-1: none) */
+  double prune_ms_total;    /* device time of the pruning launches of every evaluation so far (CUDA events on the engine's
+                               stream around the round launches; read without a synchronisation once the result is in) */
   unsigned long long last_fp64_ops;   /* DMUL + DADD instructions (per lane) the last evaluation's pruning had to issue: a 4x4
                                mat-vec = 16 + 12, the product of the two child terms = 4, tip terms come from a table */
 } dmpc_stats;
