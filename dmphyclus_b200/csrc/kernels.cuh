@@ -798,9 +798,6 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
   constexpr int XR = xrec(RP);
   constexpr int V = RP / 4;
   constexpr int CERT_ROWCAP = 1024 / V;    // rows of one literal tile staged in shared memory (more: read from global memory)
-  __shared__ double s_w[TILE / 32][RP + 2];
-  __shared__ double s_tot[RP + 2];
-  __shared__ long long s_key[TILE / 32];
   __shared__ int s_base[CW + 1];
   __shared__ const volatile double* s_rec[CW];
   __shared__ int s_cnt[TILE], s_site[TILE];
@@ -840,93 +837,78 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
     for (int q = 1; q < CW; q++) if (q < nRanks && g >= s_base[q]) p = q;
     return s_rec[p] + (size_t)(g - s_base[p]) * XR;
   };
-  // block-wide sums / scans of RP + 2 doubles at once (one barrier pair)
-  auto blockTotals = [&](double (&x)[RP + 2]) {
+  // One record per thread and pass, loaded once (ld.global.cg: the mailbox is written by peers) and kept in registers.
+  // The leader d of a record is whoever leads at its ENTRY: a certified record ends with everyone else 128 behind d, so
+  // the next record's leader is d again — the certified suffix has one leader, and no pass over the totals is needed.
+  // Likewise kappa only has to cover the operations up to the record it is applied to.
+  __shared__ double s_w[TILE / 32][RP + 3];
+  __shared__ long long s_key[TILE / 32];
+  __shared__ int s_res[4];
+  double carry[RP + 3];                           // running: E_r, rescaled sites, ops, sum of u*g
 #pragma unroll
-    for (int q = 16; q > 0; q >>= 1)
+  for (int i = 0; i < RP + 3; i++) carry[i] = 0.0;
+  long long best = -1;                            // (last uncertified record) << 32 | rescaled sites up to and including it
+  for (int base = 0; base < Ttot; base += TILE) {
+    const int g = base + tid;
+    const bool in = g < Ttot;
+    const double* rec = in ? const_cast<const double*>(recOf(g)) : nullptr;
+    double x[RP + 3], Sr[RP], ab = 0.0;           // x: S_r, nAct, ops, (then) u*g — scanned inclusively
 #pragma unroll
-      for (int i = 0; i < RP + 2; i++) x[i] += __shfl_xor_sync(0xffffffffu, x[i], q);
-    if (lane == 0) {
+    for (int r = 0; r < RP; r++) { Sr[r] = in ? __ldcg(rec + 4 + r) : 0.0; x[r] = Sr[r]; }
+    x[RP] = in ? __ldcg(rec + 0) : 0.0;
+    x[RP + 1] = in ? __ldcg(rec + 1) : 0.0;
+    if (in) ab = __ldcg(rec + 2);
+    const double opsMine = x[RP + 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+      for (int i = 0; i < RP + 2; i++) { const double y = __shfl_up_sync(0xffffffffu, x[i], d); if (lane >= d) x[i] += y; }
+    if (lane == 31) {
 #pragma unroll
       for (int i = 0; i < RP + 2; i++) s_w[wid][i] = x[i];
     }
     __syncthreads();
-    if (tid < RP + 2) { double a = 0.0; for (int w = 0; w < TILE / 32; w++) a += s_w[w][tid]; s_tot[tid] = a; }
-    __syncthreads();
-  };
-  // pass 1: totals -> the dominant category and kappa
-  {
-    double x[RP + 2];
+    double tot[RP + 3];
 #pragma unroll
-    for (int i = 0; i < RP + 2; i++) x[i] = 0.0;
-    for (int g = tid; g < Ttot; g += TILE) {
-      const volatile double* rec = recOf(g);
-#pragma unroll
-      for (int r = 0; r < RP; r++) x[r] += rec[4 + r];
-      x[RP] += rec[1];
-    }
-    blockTotals(x);
-  }
-  int dom = 0;
-  for (int r = 1; r < R; r++) if (s_tot[r] > s_tot[dom]) dom = r;
-  const double kappa = exp(s_tot[RP] * 0x1p-22) * (1.0 + 1e-9);
-  __syncthreads();
-  // pass 2: per tile, entry sums (exclusive scan), the rounding bound (inclusive scan), the verdict
-  double carry[RP + 2];                           // running: E_r, sum of u*g, active sites
-#pragma unroll
-  for (int i = 0; i < RP + 2; i++) carry[i] = 0.0;
-  long long best = -1;                            // (last uncertified tile) << 32 | active sites up to and including it
-  for (int base = 0; base < Ttot; base += TILE) {
-    const int g = base + tid;
-    const bool in = g < Ttot;
-    const volatile double* rec = in ? recOf(g) : nullptr;
-    double Sr[RP], ops = 0.0, ab = 0.0, na = 0.0;
-#pragma unroll
-    for (int r = 0; r < RP; r++) Sr[r] = in ? rec[4 + r] : 0.0;
-    if (in) { na = rec[0]; ops = rec[1]; ab = rec[2]; }
-    // inclusive scans of S_r and nAct
-    double incl[RP + 1];
-#pragma unroll
-    for (int r = 0; r < RP; r++) incl[r] = Sr[r];
-    incl[RP] = na;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-#pragma unroll
-      for (int i = 0; i < RP + 1; i++) { const double y = __shfl_up_sync(0xffffffffu, incl[i], d); if (lane >= d) incl[i] += y; }
-    if (lane == 31) {
-#pragma unroll
-      for (int i = 0; i < RP + 1; i++) s_w[wid][i] = incl[i];
-    }
-    __syncthreads();
-    double tot[RP + 1];
-#pragma unroll
-    for (int i = 0; i < RP + 1; i++) {
+    for (int i = 0; i < RP + 2; i++) {
       tot[i] = 0.0;
 #pragma unroll
-      for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][i]; if (w < wid) incl[i] += q; tot[i] += q; }
+      for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][i]; if (w < wid) x[i] += q; tot[i] += q; }
+      x[i] += carry[i];
     }
-    __syncthreads();
-    double entry[RP], emax = -1e300, emin = 1e300;
+    // what enters this record, who leads there, and this record's share of the rounding bound
+    double emax = -1e300, emin = 1e300, edom = 0.0;
+    int dom = 0;
 #pragma unroll
     for (int r = 0; r < RP; r++)
-      if (r < R) { entry[r] = carry[r] + incl[r] - Sr[r]; emax = fmax(emax, entry[r]); emin = fmin(emin, entry[r]); }
-    double ug = in ? 0x1p-22 * ops * ((emax - emin) + ab + 1.0) : 0.0;
-    double ugi = ug;
+      if (r < R) {
+        const double e = x[r] - Sr[r];
+        if (e > emax) { emax = e; dom = r; edom = e; }
+        emin = fmin(emin, e);
+      }
+    double mp[RP];                                // maxPre[dom][.]: issued now, needed after the second scan
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, ugi, d); if (lane >= d) ugi += y; }
-    if (lane == 31) s_w[wid][RP + 1] = ugi;
+    for (int r = 0; r < RP; r++) mp[r] = (in && r < R) ? __ldcg(rec + 4 + RP + dom * RP + r) : 0.0;
+    if (in) rv.act[g] = dom;                      // (scratch: the compaction of the literal prefix comes later)
+    double ug = in ? 0x1p-22 * opsMine * ((emax - emin) + ab + 1.0) : 0.0;
+    const double ugMine = ug;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const double y = __shfl_up_sync(0xffffffffu, ug, d); if (lane >= d) ug += y; }
+    if (lane == 31) s_w[wid][RP + 2] = ug;
     __syncthreads();
-    double ugTot = 0.0;
+    tot[RP + 2] = 0.0;
 #pragma unroll
-    for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][RP + 1]; if (w < wid) ugi += q; ugTot += q; }
-    const double B = kappa * (carry[RP] + ugi);
+    for (int w = 0; w < TILE / 32; w++) { const double q = s_w[w][RP + 2]; if (w < wid) ug += q; tot[RP + 2] += q; }
+    ug += carry[RP + 2];
+    (void)ugMine;
+    const double B = exp(x[RP + 1] * 0x1p-22) * (1.0 + 1e-9) * ug;
     bool bad = false;
     if (in) {
 #pragma unroll
       for (int r = 0; r < RP; r++)
-        if (r < R && r != dom) bad |= !(entry[r] - entry[dom] + rec[4 + RP + dom * RP + r] + B < -128.0);
+        if (r < R && r != dom) bad |= !((x[r] - Sr[r]) - edom + mp[r] + B < -128.0);
     }
-    long long key = bad ? (((long long)g << 32) | (long long)(unsigned)(carry[RP + 1] + incl[RP])) : -1;
+    long long key = bad ? (((long long)g << 32) | (long long)(unsigned)x[RP]) : -1;
 #pragma unroll
     for (int q = 16; q > 0; q >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, key, q); key = o > key ? o : key; }
     if (lane == 0) s_key[wid] = key;
@@ -934,13 +916,19 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
 #pragma unroll
     for (int w = 0; w < TILE / 32; w++) best = s_key[w] > best ? s_key[w] : best;
 #pragma unroll
-    for (int r = 0; r < RP; r++) carry[r] += tot[r];
-    carry[RP] += ugTot;
-    carry[RP + 1] += tot[RP];
+    for (int i = 0; i < RP + 3; i++) carry[i] += tot[i];
     __syncthreads();
   }
-  const int tb = (int)(best >> 32), L0 = (int)(best & 0xffffffffLL);
-  const bool ok = rv.certOn && best >= 0 && L0 <= CERT_MAXLIT && tb < s_base[1];
+  if (tid == 0) {
+    const int tb0 = (int)(best >> 32), L00 = (int)(best & 0xffffffffLL);
+    __threadfence_block();
+    s_res[0] = tb0; s_res[1] = L00;
+    s_res[2] = (tb0 + 1 < Ttot) ? *(volatile int*)&rv.act[tb0 + 1] : 0;      // the leader of the certified suffix
+    s_res[3] = (rv.certOn && best >= 0 && L00 <= CERT_MAXLIT && tb0 < s_base[1]) ? 1 : 0;
+  }
+  __syncthreads();
+  const int tb = s_res[0], L0 = s_res[1], dom = s_res[2];
+  const bool ok = s_res[3] != 0;
   const int myBase = sharded ? s_base[cm.rank] : 0;
   if (tid == 0) {
     st->cert = ok ? CERT_OK : CERT_LITERAL;
@@ -983,18 +971,28 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
     }
     __syncthreads();
     if (tid == 0) {
+      // the walker: the next site's row count and first row are fetched before the current site's dependent chain
+      // (additions, maximum, subtraction) is worked through
       int q = 0;
+      int cntN = nA > 0 ? s_cnt[0] : 0;
+      float4 first[V];
+#pragma unroll
+      for (int u = 0; u < V; u++) first[u] = s_rows[u];
       for (int i = 0; i < nA; i++) {
-        const int cnt = s_cnt[i];
+        const int cnt = cntN;
+        cntN = s_cnt[min(i + 1, TILE - 1)];
         if (staged) {                               // (two loops: the staged one compiles to shared-memory loads)
           for (int j = 0; j < cnt; j++) {
             float4 w[V];
 #pragma unroll
-            for (int u = 0; u < V; u++) w[u] = s_rows[(size_t)(q + j) * V + u];
+            for (int u = 0; u < V; u++) w[u] = j == 0 ? first[u] : s_rows[(size_t)(q + j) * V + u];
 #pragma unroll
             for (int r = 0; r < RP; r++)
               if (r < R) { const float4 x = w[r >> 2]; c[r] = __fadd_rn(c[r], (r & 3) == 0 ? x.x : (r & 3) == 1 ? x.y : (r & 3) == 2 ? x.z : x.w); }
           }
+          const int qn = min(q + cnt, CERT_ROWCAP - 1);
+#pragma unroll
+          for (int u = 0; u < V; u++) first[u] = s_rows[(size_t)qn * V + u];
         } else {
           const float* rows = rv.elist + (size_t)s_site[i] * rv.Kcap * RP;
           for (int j = 0; j < cnt; j++)
