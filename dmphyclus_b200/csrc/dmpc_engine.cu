@@ -51,6 +51,8 @@ constexpr size_t PLAN_SLACK = 64;
 // a logLikFromClusInd-style create/evaluate/destroy cycle; handles borrow a pack and give it back.
 struct ResPack {
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;   // the alignment upload of logLikCpp runs here, slab by slab, ahead of the pruning
+  cudaEvent_t slabEv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* h_plan = nullptr;        // pinned: tasks | tokens | tip list of one evaluation, packed, uploaded in ONE copy
   int32_t* h_curList = nullptr;  // pinned
@@ -134,6 +136,9 @@ struct dmpc_tree {
   size_t planOffTok = 0, planOffTip = 0, planOffSeg = 0, planBytes = 0;   // layout of the plan last packed into d_plan
   unsigned pubExpected = 0;      // status publications k_root_gather has been asked for so far (see DevStatus::pubSeq)
   bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
+  // logLikCpp only: the alignment is uploaded in slabs of site tiles on the copy stream while the slabs already on the
+  // device are pruned (one-shot; the first evaluation consumes it)
+  struct { int n = 0; const uint8_t* src = nullptr; size_t pitch = 0; uint8_t* stage = nullptr; } slabs;
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
@@ -180,7 +185,9 @@ int acquirePack(dmpc_tree* t) {
   ResPack& p = t->pack;
   if (!p.stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.copyStream, cudaStreamNonBlocking));
     for (auto& e : p.ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto& e : p.slabEv) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc((void**)&p.h_res, sizeof(HostResult), cudaHostAllocMapped));
     std::memset(p.h_res, 0, sizeof(HostResult));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&p.d_res, p.h_res, 0));
@@ -362,16 +369,15 @@ int uploadPlan(dmpc_tree* t, const HostTree::Plan& p) {
   return DMPC_OK;
 }
 
-// the level launches of the current plan (tasks, tokens and tip lists are already on the device)
-int runPlan(dmpc_tree* t) {
+// the pruning launches of the current plan over the site tiles [dv.tileOff, dv.tileOff + tiles): one per round, then the
+// walked chain (tasks, tokens, tip lists and segments are already on the device)
+int launchRounds(dmpc_tree* t, int tiles, int* launchesOut) {
   const HostTree::Plan& p = *t->runPlanMeta;
   const int nAll = (int)p.levelStart.size() - 1;
   const int nLevels = nAll - p.chainLevels;        // the trailing single-task levels go to k_walk as one chain
-  if (t->T > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 16.7M)");
-  int rcE;
-  if ((rcE = recordEv(t, 0))) return rcE;
-  int launches = 0;
+  if (tiles > 65535) return fail(DMPC_ERR_ARG, "too many site tiles for one launch (numLoci > 16.7M)");
   if ((int)p.unitSeg.size() != nLevels + 1) return fail(DMPC_ERR_STATE, "plan: launch units and segment table disagree");
+  int launches = 0;
   for (int l = 0; l < nLevels; l++) {
     // one launch per unit (the materialised clades, then the rounds): grid = (rate, site tile, segment) — blocks that
     // share a task's masks and tokens are scheduled next to each other; gridDim.z is limited to 65535, wider units go
@@ -379,7 +385,7 @@ int runPlan(dmpc_tree* t) {
     const int s0 = p.unitSeg[l], nSeg = p.unitSeg[l + 1] - s0;
     for (int off = 0; off < nSeg; off += 65535) {
       const int m = std::min(65535, nSeg - off);
-      const dim3 grid((unsigned)t->R, (unsigned)t->T, (unsigned)m);
+      const dim3 grid((unsigned)t->R, (unsigned)tiles, (unsigned)m);
       int rc = launchPrune(t, grid, t->runTasks, 0, t->runSegs + s0 + off);
       if (rc) return rc;
       t->st.kernel_launches++;
@@ -388,13 +394,51 @@ int runPlan(dmpc_tree* t) {
   }
   if (p.chainLevels) {
     const int first = p.levelStart[nLevels], n = p.levelStart[nAll] - first;     // one task per level: n == chainLevels
-    k_walk<<<dim3((unsigned)t->R, (unsigned)t->T), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip);
+    k_walk<<<dim3((unsigned)t->R, (unsigned)tiles), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip);
     t->st.kernel_launches++;
     launches++;
   }
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
+  *launchesOut += launches;
+  return DMPC_OK;
+}
+
+int runPlan(dmpc_tree* t) {
+  const HostTree::Plan& p = *t->runPlanMeta;
+  int rcE, launches = 0;
+  if ((rcE = recordEv(t, 0))) return rcE;
+  if (t->slabs.n > 1 && !t->capturing) {
+    // logLikCpp: slab k of the alignment is copied (copy stream), re-pitched and pruned while slab k + 1 is on its way
+    const int nS = t->slabs.n, per = (t->T + nS - 1) / nS;
+    t->slabs.n = 0;                                // one-shot
+    CUDA_TRY(cudaEventRecord(t->ev[5], t->pack.copyStream));
+    for (int k = 0; k < nS; k++) {
+      const int t0 = k * per, t1 = std::min(t->T, t0 + per);
+      if (t1 <= t0) break;
+      const int c0 = t0 * TILE, c1 = std::min(t->S, t1 * TILE);      // real columns of the slab (pad columns have no source)
+      if (c1 > c0)
+        CUDA_TRY(cudaMemcpy2DAsync(t->slabs.stage + c0, (size_t)t->S, t->slabs.src + c0, t->slabs.pitch, (size_t)(c1 - c0), (size_t)t->N,
+                                   cudaMemcpyHostToDevice, t->pack.copyStream));
+      CUDA_TRY(cudaEventRecord(t->pack.slabEv[k], t->pack.copyStream));
+      if (k == nS - 1 || t1 == t->T) CUDA_TRY(cudaEventRecord(t->ev[6], t->pack.copyStream));
+      CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[k], 0));
+      {
+        const int p1 = t1 * TILE;                  // ... but the padded layout is filled up to the tile boundary
+        const size_t n = (size_t)t->N * (p1 - c0);
+        k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->slabs.stage, t->d_tipmask, t->N, t->S, t->Sp, c0, p1, &t->rv.st->badCells);
+        t->st.kernel_launches++;
+      }
+      t->dv.tileOff = t0;
+      const int rc = launchRounds(t, t1 - t0, &launches);
+      t->dv.tileOff = 0;
+      if (rc) return rc;
+    }
+  } else {
+    const int rc = launchRounds(t, t->T, &launches);
+    if (rc) return rc;
+  }
   if ((rcE = recordEv(t, 1))) return rcE;
-  t->st.last_levels = nAll;
+  t->st.last_levels = (int)p.levelStart.size() - 1;
   t->st.last_prune_launches = launches;
   t->st.last_walk_steps = p.chainLevels;
   t->st.last_materialised = p.materialised;
@@ -1095,16 +1139,35 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     // alignment: one contiguous upload, re-pitched to [N][Sp] (pad sites = all-ones mask) and validated on the device;
     // the bad-cell count comes back with the evaluation's status, so the upload costs no synchronisation of its own
     t->st.create_setup_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
-    CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
-    CUDA_TRY(cudaMemcpy2DAsync(stage, (size_t)t->S, alignmentBin, alignPitch, (size_t)t->S, (size_t)t->N, cudaMemcpyHostToDevice, t->stream));
-    {
-      const size_t n = (size_t)t->N * t->Sp;
-      k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, &t->rv.st->badCells);
-      t->st.kernel_launches++;
+    // the upload overlaps the pruning: site tiles go up in slabs on the copy stream, and every slab is re-pitched and
+    // pruned (all rounds of the plan) as soon as it has landed — the upload (PCIe) is the longer of the two
+    // how many slabs: every slab costs its own round launches (~20 us), and saves 1/n of the pruning from the critical
+    // path: n ~ sqrt(pruning time / 20 us), with the pruning estimated at 4.2 ps per node-site-rate update (measured:
+    // 2 slabs are best for 1,000 x 10,000, 8 for 10,000 x 30,000)
+    const double pruneUs = (double)t->nReal * t->S * t->R * 4.2e-6;
+    int nSlab = (int)std::lround(std::sqrt(pruneUs / 20.0));
+    nSlab = std::max(1, std::min({nSlab, 8, t->T / 4}));
+    if (const char* e = std::getenv("DMPC_UPLOAD_SLABS")) nSlab = std::max(1, std::min({8, std::atoi(e), t->T}));
+    if (nSlab > 1) {
+      // the copy stream must not run ahead of the allocation / memsets queued on the main stream
+      CUDA_TRY(cudaEventRecord(t->pack.slabEv[7], t->stream));
+      CUDA_TRY(cudaStreamWaitEvent(t->pack.copyStream, t->pack.slabEv[7], 0));
+      t->slabs.n = nSlab; t->slabs.src = alignmentBin; t->slabs.pitch = alignPitch; t->slabs.stage = stage;
+    } else {
+      CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
+      CUDA_TRY(cudaMemcpy2DAsync(stage, (size_t)t->S, alignmentBin, alignPitch, (size_t)t->S, (size_t)t->N, cudaMemcpyHostToDevice, t->stream));
+      {
+        const size_t n = (size_t)t->N * t->Sp;
+        k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, 0, t->Sp, &t->rv.st->badCells);
+        t->st.kernel_launches++;
+      }
+      CUDA_TRY(cudaEventRecord(t->ev[6], t->stream));
     }
-    CUDA_TRY(cudaEventRecord(t->ev[6], t->stream));
     int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
-    if (rcEval == DMPC_OK) { float ms = 0; cudaEventElapsedTime(&ms, t->ev[5], t->ev[6]); t->st.create_upload_ms = ms; }
+    if (rcEval == DMPC_OK) {                     // (the upload's closing event sits on the copy stream: it has long fired)
+      float ms = 0;
+      if (cudaEventSynchronize(t->ev[6]) == cudaSuccess && cudaEventElapsedTime(&ms, t->ev[5], t->ev[6]) == cudaSuccess) t->st.create_upload_ms = ms;
+    }
     if (rcEval == DMPC_OK && t->h_res->badCells)
       return fail(DMPC_ERR_ARG, std::to_string(t->h_res->badCells) +
                                     " alignment cells hold no state (unknown symbol; clusterFunArmadillo.cpp:109)");

@@ -44,6 +44,8 @@ struct DevView {
   int nReal;                    // N-1: what the root reduction scans
   int nFlag;                    // bytes of one (rate, tile) row of the flag arrays: nInt rounded up to 16, so that the root
                                 // reduction scans 16 vertices per 128-bit load
+  int tileOff;                  // first site tile of a pruning launch (0, except while logLikCpp prunes the alignment slab by
+                                // slab behind its upload)
   // select instead of dynamic indexing: indexing a by-value kernel parameter array would spill it to local memory
   __device__ __forceinline__ double* partOf(int slot) const { return slot ? part[1] : part[0]; }
   __device__ __forceinline__ float* expoOf(int slot) const { return slot ? expo[1] : expo[0]; }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(TILE / SPT_, MINB) k_prune(DevView v, PruneArg
   __shared__ __align__(16) unsigned char s_mask[2 * FUSE_MAX_TIPS * TILE];
   __shared__ __align__(16) int4 s_tok[3 * FUSE_MAX_TIPS + 4];
   const int tid = threadIdx.x;
-  const int tile = blockIdx.y, r = blockIdx.x, R = v.R;
+  const int tile = blockIdx.y + v.tileOff, r = blockIdx.x, R = v.R;
   const int site0 = tile * TILE + tid;
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
   __shared__ __align__(16) double s_lut[2 * 64];                   // [set][mask][4] of this block's rate
   __shared__ __align__(16) double s_P[2 * 16];                     // both matrix sets of this block's rate
   __shared__ unsigned s_win[3];
-  const int tid = threadIdx.x, r = blockIdx.x, tile = blockIdx.y, R = v.R;
+  const int tid = threadIdx.x, r = blockIdx.x, tile = blockIdx.y + v.tileOff, R = v.R;
   const unsigned site = (unsigned)(tile * TILE + tid);
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
@@ -665,11 +667,14 @@ __global__ void k_set_cur(uint8_t* cur, const int32_t* idxAndSlot, int n) {
 
 // the uploaded alignment ([N][S] bytes, contiguous) -> the padded device layout [N][Sp]; pad sites get the all-ones
 // mask; cells without any state (unknown symbol) or with stray high bits are counted and neutralised
-__global__ void k_prepare_masks(const uint8_t* __restrict__ in, uint8_t* __restrict__ mask, int N, int S, int Sp, int* bad) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * Sp) return;
-  const int s = (int)(i % Sp);
-  const size_t row = i / Sp;
+// (columns [c0, c1) of the padded layout: logLikCpp uploads and prepares the alignment slab by slab)
+__global__ void k_prepare_masks(const uint8_t* __restrict__ in, uint8_t* __restrict__ mask, int N, int S, int Sp, int c0, int c1, int* bad) {
+  const size_t w = (size_t)(c1 - c0);
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (size_t)N * w) return;
+  const int s = c0 + (int)(j % w);
+  const size_t row = j / w;
+  const size_t i = row * Sp + s;
   uint8_t m = 0xF;
   if (s < S) {
     m = in[row * S + s];
