@@ -580,6 +580,8 @@ struct HostTree {
       std::vector<int> pos(cnt.begin(), cnt.end() - 1);
       for (int g = 0; g < nGroups; g++) byRound[pos[gRound[g]]++] = g;
       for (int r = 0; r < nRounds; r++) {
+        // longest paths first (blocks are dispatched in segment order): the round's tail is then made of short ones
+        std::stable_sort(byRound.begin() + cnt[r], byRound.begin() + cnt[r + 1], [&](int a, int b) { return gCost[a] > gCost[b]; });
         p.levelStart.push_back((int)order.size());
         for (int q = cnt[r]; q < cnt[r + 1]; q++) {
           p.segStart.push_back((int)order.size());
