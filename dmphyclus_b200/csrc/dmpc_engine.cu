@@ -264,7 +264,9 @@ void setElistGeometry(dmpc_tree* t, int kcap) {
 int allocElist(dmpc_tree* t, int kcap) {
   // the previous list stays allocated until the handle dies; growth is rare and geometric
   setElistGeometry(t, kcap);
-  return t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
+  int rc = t->alloc(&t->rv.elist, (size_t)t->Sp * kcap * t->rv.RP);
+  if (rc) return rc;
+  return t->alloc(&t->rv.eid, (size_t)t->Sp * kcap * t->rv.RP);
 }
 
 // matrices arrive column-major from R (P(i,j) at [i + 4j]); constants hold them row-major
@@ -1123,6 +1125,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     want(&t->rv.st, (size_t)1);
     setElistGeometry(t, 8);
     want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
+    want(&t->rv.eid, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
     {
       void* base = nullptr;
       CUDA_TRY(cudaMallocAsync(&base, ar.total, t->stream));
@@ -1429,6 +1432,10 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
   const bool chainMode = t->quirk && t->R > 1;
   const bool batchable = !t->exact && nProps > 0;
   if (batchable) {
+    // the committed state's per-site exponent lists (with the vertex of every row), which the batched gather merges each
+    // proposal's path into: the handle's own lists are those of the LAST evaluation — possibly a rejected proposal — so
+    // they are rebuilt here (one ordinary gather over the committed state; nothing is published, nothing is read back)
+    if ((rc = launchGather(t, chainMode ? 1 : 0, false))) return rc;
     constexpr int JCAP = 96;                       // longest path handled in a batch
     const size_t Sp = (size_t)t->Sp, Kc = (size_t)t->rv.Kcap, RP = (size_t)t->rv.RP, R = (size_t)t->R, T = (size_t)t->T;
     HostTree::Plan pp;
@@ -1483,6 +1490,7 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       pv.rootdot = (double*)dalloc((size_t)nb * R * Sp * 8);
       RootView rb = t->rv;
       rb.comm.world = 1;
+      rb.baseElist = t->rv.elist; rb.baseEid = t->rv.eid; rb.baseKmax = t->rv.kmax;
       rb.elist = (float*)dalloc((size_t)nb * Sp * Kc * RP * 4);
       rb.kmax = (int*)dalloc((size_t)nb * Sp * 4);
       rb.act = (int*)dalloc((size_t)nb * Sp * 4);

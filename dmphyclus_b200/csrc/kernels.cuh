@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <limits.h>
 
 #include "task.hpp"
 
@@ -105,7 +106,11 @@ struct CommView {
 
 struct RootView {
   float* elist;                 // [Sp][Kcap][RP] per-site non-zero exponents in vertex-id order, zero padded
+  int* eid;                     // [Sp][Kcap][RP] the vertex (internal index) each of those rows belongs to (committed lists only)
   int* kmax;                    // [Sp] rows used at each site (uncapped)
+  const float* baseElist;       // proposal batches: the COMMITTED state's lists (elist / eid / kmax of the handle, refreshed
+  const int* baseEid;           //   by dmpc_eval_proposals), into which every proposal merges its path vertices' rows
+  const int* baseKmax;
   double* rootdot;              // [R][Sp] dot(root partial, limProbs)
   int* act;                     // [Sp] active (rescaled) sites, ascending
   int* rowoff;                  // [Sp+1] exclusive prefix of rows over active sites
@@ -1046,7 +1051,6 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   constexpr int NV = 16;                           // vertices per thread and pass of the (non-batch) flag scan
   __shared__ __align__(16) int s_list[TILE * NV];   // (also lent to certify() as its 16 KB row stage)
-  __shared__ int s_listJ[BATCH ? TILE : 1];
   __shared__ double s_red[TILE];
   __shared__ bool s_last;
   __shared__ int s_wcnt[TILE / 32];
@@ -1078,6 +1082,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
 #pragma unroll
   for (int r = 0; r < RP; r++) { k[r] = 0; sd[r] = 0.0; }
   float* const myList = rv.elist + (size_t)site * rv.Kcap * RP;
+  int* const myIds = BATCH ? nullptr : rv.eid + (size_t)site * rv.Kcap * RP;
   const size_t fstride = (size_t)v.T * v.nFlag;                 // between the flag planes of consecutive rates
   const uint8_t* f0 = v.flag[0] ? v.flag[0] + (size_t)tile * v.nFlag : nullptr;
   const uint8_t* f1 = v.flag[1] ? v.flag[1] + (size_t)tile * v.nFlag : nullptr;
@@ -1090,7 +1095,6 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       for (int j = 0; j < 4; j++) {
         const int ent = s_list[min(i + j, n - 1)];
         const float* src = v.expoOf((ent >> 8) & 1) + (size_t)(ent >> 9) * R * Sp + site;
-        if (BATCH) { const int qj = s_listJ[min(i + j, n - 1)]; if (qj >= 0) src = pv.pe + (((size_t)pb * pv.JMAX + qj) * R) * Sp + site; }
 #pragma unroll
         for (int r = 0; r < RP; r++) e[j][r] = (((ent >> r) & 1) && i + j < n) ? src[r * Sp] : 0.0f;   // unflagged rows were never written
       }
@@ -1099,7 +1103,10 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
 #pragma unroll
         for (int r = 0; r < RP; r++)
           if (e[j][r] != 0.0f) {
-            if (k[r] < rv.Kcap && valid) myList[(size_t)k[r] * RP + r] = e[j][r];
+            if (k[r] < rv.Kcap && valid) {
+              myList[(size_t)k[r] * RP + r] = e[j][r];
+              if (!BATCH) myIds[(size_t)k[r] * RP + r] = s_list[min(i + j, n - 1)] >> 9;
+            }
             k[r]++;
             sd[r] += (double)e[j][r];
           }
@@ -1169,35 +1176,50 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       __syncthreads();
     }
   } else {
-    for (int base = 0; base < v.nReal; base += TILE) {
-      const int nd = base + tid;
-      int slot = 0, rbits = 0;                     // rates for which this vertex rescaled somewhere in the tile
-      int pj = -1;                                 // position in the proposal's run when nd is a path vertex
-      if (nd < v.nReal) {
-        const int32_t* ids = pv.ids + (size_t)pb * pv.JMAX;
-        int lo = 0, hi = pv.JMAX;                   // first index with ids[.] >= nd
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] < nd) lo = mid + 1; else hi = mid; }
-        if (lo < pv.JMAX && ids[lo] == nd) pj = pv.pos[(size_t)pb * pv.JMAX + lo];
-        if (pj >= 0) {
-          const uint8_t* fp = pv.pf + (((size_t)pb * pv.JMAX + pj) * R) * v.T + tile;
-          for (int r = 0; r < R; r++) rbits |= (fp[(size_t)r * v.T] != 0) << r;
+    // Proposal batches: a proposal differs from the committed state only at the stored vertices of its path, so its
+    // per-site lists are the COMMITTED lists (rv.base*: vertex-id order, ids alongside) with the path vertices' rows
+    // dropped and their new exponents merged in by id — O(rows + path length) per site instead of a scan of every
+    // vertex's flags.
+    constexpr int PATH_CAP = 96;                   // = JCAP of dmpc_eval_proposals
+    __shared__ int s_pid[PATH_CAP], s_ppos[PATH_CAP];
+    __shared__ unsigned char s_pfl[PATH_CAP][RP];
+    const int J = min(pv.JMAX, PATH_CAP);
+    for (int j = tid; j < J; j += TILE) {
+      const int id = pv.ids[(size_t)pb * pv.JMAX + j], ps = pv.pos[(size_t)pb * pv.JMAX + j];
+      s_pid[j] = id; s_ppos[j] = ps;
+#pragma unroll
+      for (int r = 0; r < RP; r++)
+        s_pfl[j][r] = (id != INT_MAX && r < R) ? pv.pf[(((size_t)pb * pv.JMAX + ps) * R + r) * v.T + tile] : 0;
+    }
+    __syncthreads();
+    const float* const cl = rv.baseElist + (size_t)site * rv.Kcap * RP;
+    const int* const ci = rv.baseEid + (size_t)site * rv.Kcap * RP;
+    const int ckAll = rv.baseKmax[site], ck = min(ckAll, rv.Kcap);
+    if (valid && ckAll > rv.Kcap) atomicMax(&rv.st->overflow, ckAll);     // truncated committed list: evaluate this one alone
+#pragma unroll
+    for (int r = 0; r < RP; r++) {
+      if (r >= R) continue;
+      int i = 0, j = 0;
+      for (;;) {
+        int idc = INT_MAX;
+        float ec = 0.0f;
+        while (i < ck) { ec = cl[(size_t)i * RP + r]; if (ec != 0.0f) { idc = ci[(size_t)i * RP + r]; break; } i++; }
+        const int idp = j < J ? s_pid[j] : INT_MAX;
+        if (idc == INT_MAX && idp == INT_MAX) break;
+        float e;
+        if (idp <= idc) {                          // a path vertex: its new exponent replaces whatever the committed list held
+          if (idp == idc) i++;
+          e = s_pfl[j][r] ? pv.pe[(((size_t)pb * pv.JMAX + s_ppos[j]) * R + r) * Sp + site] : 0.0f;
+          j++;
         } else {
-          slot = v.cur[nd];
-          const uint8_t* fp = (slot ? f1 : f0) + nd;
-          for (int r = 0; r < R; r++) rbits |= (fp[r * fstride] != 0) << r;
+          e = ec; i++;
+        }
+        if (e != 0.0f) {
+          if (k[r] < rv.Kcap && valid) myList[(size_t)k[r] * RP + r] = e;
+          k[r]++;
+          sd[r] += (double)e;
         }
       }
-      const bool f = rbits != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, f);
-      if (lane == 0) s_wcnt[wid] = __popc(bal);
-      __syncthreads();
-      int off = __popc(bal & ((1u << lane) - 1)), n = 0;
-#pragma unroll
-      for (int w = 0; w < TILE / 32; w++) { if (w < wid) off += s_wcnt[w]; n += s_wcnt[w]; }
-      if (f) { s_list[off] = (nd << 9) | (slot << 8) | rbits; s_listJ[off] = pj; }
-      __syncthreads();
-      consume(n);
-      __syncthreads();
     }
   }
   int kmax = 0;
