@@ -43,7 +43,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 typedef dmpc::DevStatus HostResult;   // pinned mirror of the device status block
 // a plan never holds more than one task per internal vertex, two tokens and two tip-list entries per fused vertex
 // ... and at most one segment per task (+ the closing entry of the segment table: PLAN_SLACK)
-constexpr size_t PLAN_BYTES = sizeof(Task) + 2 * sizeof(Token) + 2 * sizeof(int32_t) + sizeof(int32_t);
+// ... and one pending rollback slot bit per vertex
+constexpr size_t PLAN_BYTES = sizeof(Task) + 2 * sizeof(Token) + 2 * sizeof(int32_t) + sizeof(int32_t) + sizeof(int32_t);
 constexpr size_t PLAN_SLACK = 64;
 
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
@@ -115,6 +116,7 @@ struct dmpc_tree {
   // what runPlan launches: the plan just built (d_tasks ...) or the cached full-evaluation plan replayed with a slot flip
   const HostTree::Plan* runPlanMeta = nullptr;
   const Task* runTasks = nullptr; const Token* runTokens = nullptr; const int32_t* runTips = nullptr; const int32_t* runSegs = nullptr;
+  const int32_t* runCur = nullptr; int runCurN = 0;   // pending rollback slot bits riding with the plan (first launch applies them)
   int runFlip = 0;
   struct {
     bool valid = false;
@@ -135,6 +137,8 @@ struct dmpc_tree {
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
   size_t planOffTok = 0, planOffTip = 0, planOffSeg = 0, planBytes = 0;   // layout of the plan last packed into d_plan
   unsigned pubExpected = 0;      // status publications k_root_gather has been asked for so far (see DevStatus::pubSeq)
+  bool timingOn = false;         // dmpc_get_stats has been called: keep the per-evaluation CUDA events of proposals too
+  bool timeThis = true;          // ... whether the evaluation in flight records them (full evaluations always do)
   bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
   // logLikCpp only: the alignment is uploaded in slabs of site tiles on the copy stream while the slabs already on the
   // device are pruned (one-shot; the first evaluation consumes it)
@@ -331,6 +335,7 @@ int launchRootSequence(dmpc_tree* t);
 
 // timing events: inside a stream capture they become event-record nodes that record the (external) event on every replay
 int recordEv(dmpc_tree* t, int i) {
+  if (!t->capturing && !t->timeThis) return DMPC_OK;      // small plans of a handle nobody asks for timings: no event records
   if (t->capturing) CUDA_TRY(cudaEventRecordWithFlags(t->ev[i], t->stream, cudaEventRecordExternal));
   else CUDA_TRY(cudaEventRecord(t->ev[i], t->stream));
   return DMPC_OK;
@@ -341,6 +346,8 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks, const int32
   PruneArgs a{};
   a.tasks = lt; a.nTasks = nTasks; a.prog = t->runTokens; a.tipList = t->runTips; a.violation = &t->rv.st->violation; a.flip = t->runFlip;
   a.segStart = segs;
+  a.curList = t->runCur; a.curN = t->runCurN;
+  t->runCurN = 0;                                  // the first launch of the evaluation takes them
   // 2 sites per thread, 5 blocks per SM (96 registers): measured best on B200 — 4 sites per thread (168-212 registers,
   // 12-16 warps per SM) is 1.3-1.6x slower, 6 blocks per SM (80 registers, spills) 1.05x (profiles/r02_prune_variants.md)
   if (t->exact) k_prune<true, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
@@ -350,7 +357,7 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks, const int32
 
 // tasks | tokens | tip list of a plan, packed into the pinned staging buffer and uploaded in ONE copy; sets what
 // runPlan / launchPrune read
-int uploadPlan(dmpc_tree* t, const HostTree::Plan& p) {
+int uploadPlan(dmpc_tree* t, const HostTree::Plan& p, bool withPending = false) {
   const size_t nT = p.tasks.size(), nK = p.tokens.size(), nL = p.tipList.size(), nS = p.segStart.size();
   if (nT > (size_t)t->nInt || nK > 2 * (size_t)t->nInt || nL > 2 * (size_t)t->nInt || nS > nT + 1)
     return fail(DMPC_ERR_STATE, "plan larger than its staging buffer");
@@ -362,11 +369,24 @@ int uploadPlan(dmpc_tree* t, const HostTree::Plan& p) {
   if (nK) std::memcpy(t->h_plan + t->planOffTok, p.tokens.data(), nK * sizeof(Token));
   if (nL) std::memcpy(t->h_plan + t->planOffTip, p.tipList.data(), nL * sizeof(int32_t));
   if (nS) std::memcpy(t->h_plan + t->planOffSeg, p.segStart.data(), nS * sizeof(int32_t));
+  // the slot bits of the last rollback that the device has not seen yet ride along, minus the vertices this plan rewrites
+  // (their new slot bit is written by the plan's own tasks): the first pruning launch applies them — no copy and no
+  // launch of their own
+  int nC = 0;
+  if (withPending && t->pendingCur && nT) {
+    int32_t* dst = reinterpret_cast<int32_t*>(t->h_plan + t->planBytes);
+    for (int i = 0; i < t->pendingCur; i++)
+      if (!t->ht.touched[(t->h_curList[i] >> 1) + t->ht.numTips]) dst[nC++] = t->h_curList[i];
+    t->pendingCur = 0;
+  }
+  const size_t offCur = t->planBytes;
+  t->planBytes += (size_t)nC * sizeof(int32_t);
   if (t->planBytes) CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
   t->runTasks = reinterpret_cast<const Task*>(t->d_plan);
   t->runTokens = reinterpret_cast<const Token*>(t->d_plan + t->planOffTok);
   t->runTips = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffTip);
   t->runSegs = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffSeg);
+  t->runCur = reinterpret_cast<const int32_t*>(t->d_plan + offCur); t->runCurN = nC;
   t->runFlip = 0;
   return DMPC_OK;
 }
@@ -396,7 +416,8 @@ int launchRounds(dmpc_tree* t, int tiles, int* launchesOut) {
   }
   if (p.chainLevels) {
     const int first = p.levelStart[nLevels], n = p.levelStart[nAll] - first;     // one task per level: n == chainLevels
-    k_walk<<<dim3((unsigned)t->R, (unsigned)tiles), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip);
+    k_walk<<<dim3((unsigned)t->R, (unsigned)tiles), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip, t->runCur, t->runCurN);
+    t->runCurN = 0;
     t->st.kernel_launches++;
     launches++;
   }
@@ -453,7 +474,6 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
   if (!t->isShard) deviceLock.lock();            // (the leader of a multi-device handle holds the locks of all its devices)
   if ((rc = ensureDevice(t))) return rc;
-  if ((rc = flushCur(t))) return rc;
   claimConstants(t);
   const auto h0 = std::chrono::steady_clock::now();
   auto usSince = [](std::chrono::steady_clock::time_point a) {
@@ -499,6 +519,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     t->runTokens = reinterpret_cast<const Token*>(cc.dPlan + cc.offTok);
     t->runTips = reinterpret_cast<const int32_t*>(cc.dPlan + cc.offTip);
     t->runSegs = reinterpret_cast<const int32_t*>(cc.dPlan + cc.offSeg);
+    t->runCurN = 0; t->pendingCur = 0;             // every slot bit is rewritten by this plan: a pending rollback is moot
     t->runFlip = flip;
     t->planCacheHits++;
   } else {
@@ -510,7 +531,8 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
       for (int sl = 0; sl < 2; sl++)
         if (p.uses[sl] && (rc = allocSlot(t, sl))) return rc;
     }
-    if ((rc = uploadPlan(t, p))) return rc;
+    if ((rc = uploadPlan(t, p, true))) return rc;
+    if (t->pendingCur && (rc = flushCur(t))) return rc;       // (an empty plan launches nothing that could carry the slot bits)
     if (full && nT) {                                // remember it (one device-to-device copy, stream-ordered)
       int r2;
       if (!cc.dPlan && (r2 = t->alloc(&cc.dPlan, (size_t)t->nInt * PLAN_BYTES + PLAN_SLACK))) return r2;
@@ -527,6 +549,9 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
   }
   t->runPlanMeta = meta;
   const int nTasks = hit ? cc.metaTasks : (int)p.tasks.size();
+  // a root-path proposal is a handful of microsecond kernels: three event records are a measurable share of its host
+  // time, so they are taken only when someone reads them (dmpc_get_stats) — full evaluations always carry them
+  t->timeThis = t->timingOn || full || nTasks > 256;
   const long long storedReads = meta->storedReads, tipReads = meta->tipReads, fusedOps = meta->fusedOps;
   t->st.last_host_plan_us = usSince(h0);
   const bool chainMode = t->quirk && t->R > 1;
@@ -609,7 +634,6 @@ int launchGather(dmpc_tree* t, int mode, bool publish) {
   t->rv.exactMode = t->exact ? 1 : 0;
   t->rv.publishAtGather = publish ? 1 : 0;
   attachComm(t);
-  CUDA_TRY(cudaMemsetAsync(&t->rv.st->nact, 0, sizeof(int), t->stream));
   if (t->deferred && mode == 1)                  // site-sharded: the gather's optimistic finish assumes the vector enters as zeros
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
   if (t->rv.RP == 4) k_root_gather<4, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
@@ -756,7 +780,7 @@ int rootStage(dmpc_tree* t, double* ll) {
       t->gatherPrelaunched = false;               // the replayed graph already ran the root sequence (and recorded ev[2])
     } else {
       if ((rc = launchRootSequence(t))) return rc;
-      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+      if (t->timeThis) CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
     }
     const bool sharded = t->rv.comm.world > 1;
     const bool hostProtocol = t->deferred && !sharded;
@@ -768,9 +792,13 @@ int rootStage(dmpc_tree* t, double* ll) {
       if ((rc = allocElist(t, k))) return rc;
       continue;
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms; t->st.prune_ms_total += ms;
-    t->evalTimePending = true;
+    if (t->timeThis) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]); t->st.last_prune_ms = ms; t->st.prune_ms_total += ms;
+      t->evalTimePending = true;
+    } else {
+      t->st.last_prune_ms = 0.0; t->st.last_eval_ms = 0.0;
+    }
     if (hostProtocol) {
       t->chunksOnHost = t->h_res->nact == 0;
       *ll = NAN;
@@ -784,19 +812,19 @@ int rootStage(dmpc_tree* t, double* ll) {
     if (!chain && anyActive) {
       // textbook reduction / one rate category: every site folds its own exponent list
       if ((rc = launchFinal(t, 0, sharded ? 2 : 1, false))) return rc;
-      CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+      if (t->timeThis) CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
       if ((rc = readStatus(t, false, false))) return rc;
     } else if (anyActive) {
       if (!t->seqPredicted) {                       // the gather ran alone: certificate + final now
         if ((rc = launchCertFinal(t))) return rc;
         t->pubExpected++;
-        CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+        if (t->timeThis) CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
         if ((rc = readStatus(t, false, true))) return rc;
       }
       if (t->h_res->cert != CERT_OK) {              // no certificate: the literal chain (handed from rank to rank when sharded)
         if ((rc = launchChain(t))) return rc;
         if ((rc = launchFinal(t, 1, sharded ? 2 : 1, false))) return rc;
-        CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
+        if (t->timeThis) CUDA_TRY(cudaEventRecord(t->ev[2], t->stream));
         if ((rc = readStatus(t, false, false))) return rc;
         t->carryIsZero = false;
       }
@@ -1123,6 +1151,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     want(&t->rv.chunk, (size_t)t->T * CPT);
     want(&t->rv.tileRec, (size_t)t->T * CPT * xrec(t->rv.RP));
     want(&t->rv.st, (size_t)1);
+    want(&t->rv.nactCtr, (size_t)1);
     setElistGeometry(t, 8);
     want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
     want(&t->rv.eid, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
@@ -1135,6 +1164,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     }
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
     CUDA_TRY(cudaMemsetAsync(t->rv.st, 0, sizeof(DevStatus), t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->rv.nactCtr, 0, sizeof(int), t->stream));
     CUDA_TRY(cudaMemsetAsync(&t->rv.st->stamp[0], 0xff, sizeof(unsigned long long), t->stream));
     CUDA_TRY(cudaMemsetAsync(&t->rv.st->stamp[4], 0xff, sizeof(unsigned long long), t->stream));
     t->dv.tipmask = t->d_tipmask; t->dv.lut = t->d_lut;
@@ -1588,6 +1618,7 @@ int dmpc_get_stats(dmpc_tree* t, dmpc_stats* out) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
   if (!out) return fail(DMPC_ERR_ARG, "null pointer");
+  t->timingOn = true;
   if (t->grp) {
     // counters add up over the shards; times are those of the slowest shard; shapes are the whole alignment's
     Group* g = t->grp;

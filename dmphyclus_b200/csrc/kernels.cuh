@@ -123,6 +123,8 @@ struct RootView {
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [T * CPT] sums of RCH consecutive sites (the first nChunks are real)
   double* tileRec;              // [T * CPT][xrec(RP)] per-chunk records of the chain certificate (k_root_gather -> certify)
+  int* nactCtr;                 // device-only: site tiles with a rescaled site, counted by the gather's blocks; its last block moves
+                                // the count into st->nact and re-arms the counter (no memset between evaluations)
   int nChunks;                  // ceil(S / RCH)
   int publishAtGather;          // 1: the gather's last block publishes the status (nothing is queued behind it)
   int certOn;                   // 0: certify() always answers CERT_LITERAL (tests compare both paths)
@@ -251,6 +253,8 @@ struct PruneArgs {
   int flip;                     // 0/1, XORed into every slot bit of the tasks and tokens: a cached full-evaluation plan is
                                 // replayed with all slots toggled instead of being rebuilt and uploaded again
   const int* runStart;          // PATHS: [proposals + 1] task ranges
+  const int32_t* curList;       // !PATHS, first launch of an evaluation: slot bits of the last rollback the device has not seen yet
+  int curN;                     //   ((internal index << 1) | slot; disjoint from what this plan writes), applied by block (0, 0, 0)
   const int32_t* segStart;      // !PATHS: block column z walks the tasks [segStart[z], segStart[z + 1]) in order (null: task z,
                                 // stride gridDim.z)
   int* invalid;                 // PATHS: [proposals]
@@ -281,6 +285,8 @@ __global__ void __launch_bounds__(TILE / SPT_, MINB) k_prune(DevView v, PruneArg
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   bool lutLoaded = false, trig = false;
   double prev[PATHS ? SPT_ : 1][4];               // PATHS: the previous task's output = the on-path operand of this one
+  if (!PATHS && pa_.curN > 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i < pa_.curN; i += PT_) v.cur[pa_.curList[i] >> 1] = (uint8_t)(pa_.curList[i] & 1);
   const bool segs = !PATHS && pa_.segStart != nullptr;
   const int tiBegin = PATHS ? pa_.runStart[blockIdx.z] : segs ? pa_.segStart[blockIdx.z] : (int)blockIdx.z;
   const int tiEnd = PATHS ? pa_.runStart[blockIdx.z + 1] : segs ? pa_.segStart[blockIdx.z + 1] : pa_.nTasks;
@@ -529,7 +535,7 @@ static_assert((WALK_DEPTH & (WALK_DEPTH - 1)) == 0 && WALK_CHUNK % WALK_WIN == 0
 // the row pitch is formed at the point of use, so no handle is too large for the walk
 enum : int { WF_OUTSLOT = 1, WF_SIBTIP = 2, WF_SIBSLOT = 4, WF_SET = 8, WF_FWD0 = 16 };
 
-__global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip) {
+__global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip, const int32_t* curList, int curN) {
   extern __shared__ __align__(32) double s_ring[];                 // [WALK_DEPTH][TILE][4]
   __shared__ uint4 s_desc[WALK_CHUNK];
   __shared__ __align__(16) double s_lut[2 * 64];                   // [set][mask][4] of this block's rate
@@ -540,6 +546,8 @@ __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restr
   const size_t Sp = (size_t)v.Sp;
   const size_t flagRow = ((size_t)r * v.T + tile) * v.nFlag;
   const int slotMask = flip ? (TF_OUTSLOT | TF_C0SLOT | TF_C1SLOT) : 0;
+  if (curN > 0 && blockIdx.x == 0 && blockIdx.y == 0)        // pending rollback slot bits (see PruneArgs::curList)
+    for (int i = tid; i < curN; i += TILE) v.cur[curList[i] >> 1] = (uint8_t)(curList[i] & 1);
   if (tid < 2 * 64) s_lut[tid] = v.lut[(size_t)((tid >> 6) * R + r) * 64 + (tid & 63)];
   if (tid < 2 * 16) s_P[tid] = c_P[tid >> 4][r][tid & 15];
   if (tid < 3) s_win[tid] = 0;
@@ -1311,13 +1319,17 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   }
   __syncthreads();                                 // the tile's record is complete
   if (tid == 0) {
-    if (anyActive) atomicAdd(&rv.st->nact, 1);
+    if (anyActive) atomicAdd(BATCH ? &rv.st->nact : rv.nactCtr, 1);
     __threadfence();
     s_last = atomicAdd(&rv.st->ticket2, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
+    if (!BATCH) {
+      if (tid == 0) { rv.st->nact = *(volatile int*)rv.nactCtr; *rv.nactCtr = 0; }
+      __syncthreads();
+    }
     const bool quiet = *(volatile int*)&rv.st->nact == 0;
     const CommView& cm = rv.comm;
     const bool retry = *(volatile int*)&rv.st->overflow > rv.Kcap || (*(volatile int*)&rv.st->violation != 0 && !rv.exactMode);
