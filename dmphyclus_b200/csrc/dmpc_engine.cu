@@ -1097,6 +1097,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
   t->nFlag = (numTips + 15) & ~15;
   t->ht.fuseTips = std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
+  if (const char* cm = std::getenv("DMPC_CHAIN_MIN")) t->ht.chainMin = std::max((int)CHAIN_MIN, std::atoi(cm));
   if (const char* gc = std::getenv("DMPC_GROUP_COST")) t->ht.groupCost = std::max(0, std::atoi(gc));   // experiments: 0 = one launch per level
   t->exact = o.fuse_exact != 0;
   t->Sp = (numLoci + TILE - 1) / TILE * TILE;

@@ -485,6 +485,8 @@ struct HostTree {
   // groupCost caps the serial work of a path (stored vertex = 2 units, fused vertex = 1); 0 = one task per segment and
   // one launch per level (the round-1 schedule, kept for comparison).
   int groupCost = 128;
+  int chainMin = CHAIN_MIN;              // trailing single-task levels are walked by k_walk from this length on; shorter ones are
+                                         // an ordinary path of the last round(s)
 
   void plan(Plan& p) {
     allInvalid = false;
@@ -517,7 +519,7 @@ struct HostTree {
     int chainL0 = maxLevel + 1;
     for (int l = maxLevel; l >= 1 && p.cnt[l] == 1; l--) chainL0 = l;
     p.chainLevels = maxLevel - chainL0 + 1;
-    if (p.chainLevels < CHAIN_MIN || !walkChains) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
+    if (p.chainLevels < chainMin || !walkChains) { p.chainLevels = 0; chainL0 = maxLevel + 1; }
     std::vector<int> matList;                // fused clades hanging off the chain: stored tasks of a leading unit
     if (p.chainLevels)
       for (int v : pre)

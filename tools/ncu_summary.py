@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+           "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 
@@ -47,7 +48,7 @@ def main():
     ap.add_argument("--report")
     ap.add_argument("--bench")
     ap.add_argument("--note", default="")
-    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--workload", default="config3")
     ap.add_argument("--data", default="evolved")
     a = ap.parse_args()
     out = os.path.join(ROOT, "profiles")
@@ -83,12 +84,12 @@ def main():
             pr = sum(x[4] for x in seg if x[1].startswith("k_prune"))
             md += ["", f"evaluation total {st / 1e3:.1f} us, of which k_prune {pr / 1e3:.1f} us = {100 * pr / st:.1f}%"]
     if a.bench and os.path.exists(a.bench):
-        b = json.load(open(a.bench))
+        b = json.loads(open(a.bench).read().strip().splitlines()[-1])
         r = b["roofline"]
         md += ["", "Live (CUDA events, `bench.py`, not under ncu):", "",
                f"* value {b['value']:.4g} {b['unit']}, {b['ms_per_step']:.4f} ms/step; e2e {b['e2e']['value']:.4g} ({b['e2e']['ms_per_step']:.3f} ms/step)",
                f"* k_prune {r['kernel_ms_per_step']:.4f} ms/step = {100 * r['kernel_share_of_step']:.1f}% of the step; "
-               f"achieved {r['achieved']:.0f} GB/s = {r['frac']:.3f} of {r['peak']} GB/s ({r['peak_source']})",
+               f"achieved {r['achieved']:.2f} {r['unit']} = {r['frac']:.3f} of {r['peak']:.2f} ({r['bound']}; {r['peak_source'][:60]}...)",
                f"* clocks {b['clocks']}"]
     if a.report:
         raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
