@@ -1153,6 +1153,8 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     want(&t->rv.tileRec, (size_t)t->T * CPT * xrec(t->rv.RP));
     want(&t->rv.st, (size_t)1);
     want(&t->rv.nactCtr, (size_t)1);
+    // one entry per certificate record of EVERY rank of a sharded run (ranks' blocks differ in size: the last one may be tiny)
+    want(&t->rv.certDom, std::max((size_t)t->T * CPT, (size_t)t->sitesTotal / RCH + (size_t)(CPT + 1) * CW + 8));
     setElistGeometry(t, 8);
     want(&t->rv.elist, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
     want(&t->rv.eid, (size_t)t->Sp * t->rv.Kcap * t->rv.RP);
@@ -1534,10 +1536,11 @@ int dmpc_eval_proposals(dmpc_tree* t, const double* withinTransMats, const doubl
       rb.sitell = (double*)dalloc((size_t)nb * Sp * 8);
       rb.chunk = (double*)dalloc((size_t)nb * T * CPT * 8);
       rb.tileRec = (double*)dalloc((size_t)nb * T * CPT * xrec(t->rv.RP) * 8);
+      rb.certDom = (int*)dalloc((size_t)nb * T * CPT * 4);
       rb.st = (DevStatus*)dalloc((size_t)nb * sizeof(DevStatus));
       bool okAlloc = true;
       for (void* q : tmp) okAlloc &= q != nullptr;
-      if (!okAlloc || tmp.size() != 23) { for (void* q : tmp) if (q) cudaFreeAsync(q, t->stream); return fail(DMPC_ERR_CUDA, "out of device memory for the proposal batch"); }
+      if (!okAlloc || tmp.size() != 24) { for (void* q : tmp) if (q) cudaFreeAsync(q, t->stream); return fail(DMPC_ERR_CUDA, "out of device memory for the proposal batch"); }
       CUDA_TRY(cudaMemcpyAsync(dT, pp.tasks.data(), nT * sizeof(Task), cudaMemcpyHostToDevice, t->stream));
       if (nK) CUDA_TRY(cudaMemcpyAsync(dK, pp.tokens.data(), nK * sizeof(Token), cudaMemcpyHostToDevice, t->stream));
       if (nL) CUDA_TRY(cudaMemcpyAsync(dL, pp.tipList.data(), nL * 4, cudaMemcpyHostToDevice, t->stream));

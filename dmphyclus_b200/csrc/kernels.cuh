@@ -123,6 +123,7 @@ struct RootView {
   double* sitell;               // [Sp] rateAveragedLogLiks
   double* chunk;                // [T * CPT] sums of RCH consecutive sites (the first nChunks are real)
   double* tileRec;              // [T * CPT][xrec(RP)] per-chunk records of the chain certificate (k_root_gather -> certify)
+  int* certDom;                 // [records of ALL ranks] scratch of certify(): the entry leader of every record
   int* nactCtr;                 // device-only: site tiles with a rescaled site, counted by the gather's blocks; its last block moves
                                 // the count into st->nact and re-arms the counter (no memset between evaluations)
   int nChunks;                  // ceil(S / RCH)
@@ -163,6 +164,7 @@ __device__ __forceinline__ RootView forProposal(RootView rv, int b, int Sp, int 
   rv.sitell += (size_t)b * sp;
   rv.chunk += (size_t)b * T * CPT;
   rv.tileRec += (size_t)b * T * CPT * xrec(rv.RP);
+  rv.certDom += (size_t)b * T * CPT;
   rv.st += b;
   rv.comm.world = 1;
   return rv;
@@ -907,7 +909,7 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
     double mp[RP];                                // maxPre[dom][.]: issued now, needed after the second scan
 #pragma unroll
     for (int r = 0; r < RP; r++) mp[r] = (in && r < R) ? __ldcg(rec + 4 + RP + dom * RP + r) : 0.0;
-    if (in) rv.act[g] = dom;                      // (scratch: the compaction of the literal prefix comes later)
+    if (in) rv.certDom[g] = dom;
     double ug = in ? 0x1p-22 * opsMine * ((emax - emin) + ab + 1.0) : 0.0;
     const double ugMine = ug;
 #pragma unroll
@@ -941,7 +943,7 @@ __device__ __forceinline__ void certify(const DevView& v, const RootView& rv, fl
     const int tb0 = (int)(best >> 32), L00 = (int)(best & 0xffffffffLL);
     __threadfence_block();
     s_res[0] = tb0; s_res[1] = L00;
-    s_res[2] = (tb0 + 1 < Ttot) ? *(volatile int*)&rv.act[tb0 + 1] : 0;      // the leader of the certified suffix
+    s_res[2] = (tb0 + 1 < Ttot) ? *(volatile int*)&rv.certDom[tb0 + 1] : 0;  // the leader of the certified suffix
     s_res[3] = (rv.certOn && best >= 0 && L00 <= CERT_MAXLIT && tb0 < s_base[1]) ? 1 : 0;
   }
   __syncthreads();
