@@ -74,3 +74,25 @@ def test_textbook_mode_unaffected(packaged, oracle):
     ho, lo = p.create(orc)
     assert rel(l, lo) < TOL and eng.stats(h)["last_cert"] == 0
     eng.finalDeallocate(h); orc.finalDeallocate(ho)
+
+
+def test_root_timeline_and_kernel_time_counters(packaged):
+    """dmpc_get_root_timeline (globaltimer stamps of the root kernels) and dmpc_stats.prune_ms_total (the pruning launches'
+    device time, accumulated without synchronisation): what bench.py builds its roofline and root-stage breakdown from."""
+    from dmphyclus_b200.engine import Engine
+    eng = Engine()
+    p = Problem(packaged, 10000, 600, 100, 3, "evolved", seed=31)
+    h, _ = p.create(eng)
+    s0 = eng.stats(h)
+    for _ in range(3):
+        eng.recomputeAll(h, p.W[4], p.B[4], p.pi)
+    s1 = eng.stats(h)
+    assert s1["prune_ms_total"] > s0["prune_ms_total"] > 0 and s1["last_prune_ms"] > 0
+    assert s1["last_fp64_ops"] > 20 * (p.n - 1) * p.S * p.R          # ~32 DMUL + DADD per update
+    tl = eng.root_timeline(h)
+    assert all(tl[k] is not None and 0 < tl[k] < 5000 for k in ("gather", "certificate", "final_terms")), tl
+    quiet = Problem(packaged, 60, 300, 4, 3, "evolved", seed=32)
+    hq, _ = quiet.create(eng)
+    tq = eng.root_timeline(hq)
+    assert tq["gather"] is not None and tq["final_terms"] is None       # nothing rescaled: the gather finished alone
+    eng.finalDeallocate(h); eng.finalDeallocate(hq)
