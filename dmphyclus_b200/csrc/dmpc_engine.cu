@@ -1888,6 +1888,9 @@ int dmpc_hp_create(const int32_t* edge, int nEdgeRows, int numTips, const double
   if (!h->ht.build(edge, nEdgeRows, numTips)) { std::string e = h->ht.err; delete h; return fail(DMPC_ERR_ARG, e); }
   h->ht.associate(clusterMRCAs, nClusterMRCAs);
   h->ht.fuseTips = std::max(1, std::min(fuseTips, (int)FUSE_MAX_TIPS));
+  // the same scheduler knobs a GPU handle reads (experiments; the CPU suite sweeps them)
+  if (const char* cm = std::getenv("DMPC_CHAIN_MIN")) h->ht.chainMin = std::max((int)CHAIN_MIN, std::atoi(cm));
+  if (const char* gc = std::getenv("DMPC_GROUP_COST")) h->ht.groupCost = std::max(0, std::atoi(gc));
   *out = h;
   return DMPC_OK;
 }

@@ -228,3 +228,50 @@ def test_proposal_runs_of_a_batch(lib, oracle, packaged, n, S, k, R, kind, shape
     finally:
         mc.close()
         oracle.finalDeallocate(ho)
+
+
+@pytest.mark.parametrize("group_cost,chain_min", [(0, 4), (6, 4), (1000, 4), (128, 1000000)])
+def test_scheduler_variants_give_the_same_partials(lib, oracle, packaged, monkeypatch, group_cost, chain_min):
+    """The plan builder's knobs — the cap on a path's serial work (0 = one launch per level, the round-1 schedule) and the
+    length from which a trailing chain goes to the walk kernel — only change HOW the dirty vertices are scheduled: a few
+    random proposal sequences under each setting must still track the oracle bit for bit."""
+    monkeypatch.setenv("DMPC_GROUP_COST", str(group_cost))
+    monkeypatch.setenv("DMPC_CHAIN_MIN", str(chain_min))
+    for seed in (3, 11, 29):
+        test_random_proposal_sequences(lib, oracle, packaged, seed)
+
+
+def test_edge_matrix_in_arbitrary_row_order(lib, oracle, packaged):
+    """The incremental edge export and the undo-log rollback of NNI moves rely on the committed edge matrix being the
+    engine's own pre-order export — which it checks, not assumes: with the rows of R's matrix in another order the first
+    NNI move re-exports the whole tree and a rollback relinks it, and everything still matches the oracle."""
+    rng = np.random.default_rng(5)
+    p = Problem(packaged, 90, 12, 6, 3, "iid", "random", seed=77)
+    perm = rng.permutation(len(p.edge))
+    p.edge = np.ascontiguousarray(p.edge[perm])
+    W, B, pi = p.W, p.B, p.pi
+    masks = oracle.getConvertedAlignment(list("atcg"), p.chars)
+    ho = oracle.logLikCpp(p.edge, p.mrcas, pi, W[4], B[4], 1, masks, p.n, p.S, 5, 5)["solutionPointer"]
+    mc = PlanMachine(lib, p, masks, 8)
+    try:
+        mc.set_matrices(W[4], B[4])
+        mc.evaluate()
+        _compare(mc, oracle, ho, p.n, "create")
+        edge = p.edge
+        big = [m for m in p.mrcas if m > p.n and len(Phylo(p.edge, p.n).descendants(m)) >= 3]
+        for it in range(8):
+            m, keep = int(big[it % len(big)]), it % 3 == 2
+            mc.propose(4, (m, 1 + it % 2))
+            res = oracle.withinClusNNIlogLik(ho, W[4], B[4], m, 1 + it % 2, 1, pi)
+            mc.evaluate()
+            new_edge = _compare(mc, oracle, ho, p.n, f"nni {it}")
+            assert np.array_equal(new_edge, np.asarray(res["edge"], np.int32))
+            if keep:
+                edge = new_edge
+            else:
+                oracle.RestorePreviousConfig(ho, edge, 5, 5, True, p.mrcas, False)
+                mc.restore(edge, True, p.mrcas, False)
+                _compare(mc, oracle, ho, p.n, f"nni {it} rolled back")
+    finally:
+        mc.close()
+        oracle.finalDeallocate(ho)
