@@ -773,7 +773,6 @@ void noteChain(dmpc_tree* t, bool anyActive) {
 int rootStage(dmpc_tree* t, double* ll) {
   int rc;
   const bool chain = t->quirk && t->R > 1;
-  const int mode = chain ? 1 : 0;
   if (t->deferred && chain) t->carryIsZero = true;   // launchGather zeroes the entry vector: optimistic pass
   for (int attempt = 0; attempt < 8; attempt++) {
     if (t->gatherPrelaunched) {

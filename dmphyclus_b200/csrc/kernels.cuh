@@ -92,7 +92,7 @@ enum : int {
 constexpr int CW = 8;            // ranks
 constexpr int XHDR = 4;          // doubles in front of the chunk sums of a message
 enum : int { XF_ACTIVE = 1 };    // message flags
-// tile record of the chain certificate (see certify): nAct, ops, absSum, 0, S_r[RP], maxPre[RP][RP]
+// record of the chain certificate, one per 64-site chunk (see certify): nAct, ops, absSum, 0, S_r[RP], maxPre[RP][RP]
 __host__ __device__ constexpr int xrec(int RP) { return 4 + RP + RP * RP; }
 constexpr int XREC_MAX = xrec(RMAX);
 struct CommView {
@@ -725,10 +725,10 @@ __device__ __forceinline__ void tile_chunk_sums(double ll, double* s_red, double
 }
 
 // The fused collective of a site-sharded run (called by the LAST block of k_root_gather / k_final, TILE threads).
-// This rank's {flags, nChunks, nTiles, chunk sums, tile records} go straight into every peer's mailbox over NVLink;
+// This rank's {flags, nChunks, nRecords, chunk sums, chunk records} go straight into every peer's mailbox over NVLink;
 // once every peer's message of the same sequence number has arrived, and no rank reports a rescaled site, each rank adds
 // ALL chunk sums in the fixed global order (the order of reduce_chunks_device over the concatenated list) and has the
-// same log-likelihood, bit for bit, as a single GPU would — without any host-side collective.  The tile records
+// same log-likelihood, bit for bit, as a single GPU would — without any host-side collective.  The chunk records
 // (recs != nullptr: nTiles x XR doubles) are what certify() needs from every rank when some site did rescale.
 // Returns 1 = ll written, 0 = some rank holds a rescaled site (certify + k_final must run), 2 = timeout.
 __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bool quiet, double* s_red, const double* recs,
@@ -807,8 +807,8 @@ __device__ __forceinline__ int exchangeAndReduce(const RootView& rv, int nCh, bo
 // tile 0: the chain starts from zeros) are walked literally here, by one thread, from rows staged in shared memory —
 // typically a few dozen sites.  If the regime never establishes itself (two categories neck and neck, tiny trees) or
 // the prefix is long, the answer is CERT_LITERAL and the host runs k_chain as before.  Runs in the LAST block of
-// k_root_gather (all tile records are complete then; in a sharded run, right after the exchange), TILE threads.  In a
-// site-sharded run every rank holds every rank's tile records (the gather's exchange) and reaches the same verdict; the
+// k_root_gather (all chunk records are complete then; in a sharded run, right after the exchange), TILE threads.  In a
+// site-sharded run every rank holds every rank's chunk records (the gather's exchange) and reaches the same verdict; the
 // literal prefix must then lie inside rank 0's block.
 constexpr int CERT_MAXLIT = 2048;    // rescaled sites the literal prefix may hold
 
@@ -1265,9 +1265,9 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
   }
   tile_chunk_sums(ll, s_red, rv.chunk + (size_t)tile * CPT);
   if (mode == 1) {
-    // The tile's record for the chain certificate (certify): with E_r = running sums of the sites' exponent sums,
-    //   S_r = the tile's total, maxPre[d][r] = max over the tile's sites (and 0) of (E_r - E_d) relative to the tile's
-    //   entry, nAct / ops / absSum = what bounds the fp32 rounding the literal chain would commit inside the tile.
+    // The records of the tile's four 64-site chunks for the chain certificate (certify): with E_r = running sums of the sites' exponent sums,
+    //   S_r = the chunk's total, maxPre[d][r] = max over the chunk's sites (and 0) of (E_r - E_d) relative to the chunk's
+    //   entry, nAct / ops / absSum = what bounds the fp32 rounding the literal chain would commit inside the chunk.
     constexpr int XR = xrec(RP);
     static_assert(RCH == 64 && TILE / 32 == 2 * CPT, "a chunk record is built from two warps");
     double* const rec = rv.tileRec + (size_t)tile * CPT * XR;
@@ -1319,7 +1319,7 @@ __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, i
       }
     }
   }
-  __syncthreads();                                 // the tile's record is complete
+  __syncthreads();                                 // the tile's records are complete
   if (tid == 0) {
     if (anyActive) atomicAdd(BATCH ? &rv.st->nact : rv.nactCtr, 1);
     __threadfence();
