@@ -15,6 +15,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <utility>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -137,6 +138,7 @@ struct dmpc_tree {
   bool exact = false;            // fused clades evaluated with per-vertex rescale bookkeeping (see k_prune_fused)
   size_t planOffTok = 0, planOffTip = 0, planOffSeg = 0, planBytes = 0;   // layout of the plan last packed into d_plan
   unsigned pubExpected = 0;      // status publications k_root_gather has been asked for so far (see DevStatus::pubSeq)
+  bool pdl = true;               // launch the kernels of an evaluation as programmatic dependents of one another (DMPC_PDL=0: off)
   bool timingOn = false;         // dmpc_get_stats has been called: keep the per-evaluation CUDA events of proposals too
   bool timeThis = true;          // ... whether the evaluation in flight records them (full evaluations always do)
   bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
@@ -329,6 +331,18 @@ void claimConstants(dmpc_tree* t) {
   if (g_constOwner[t->device & 63] != t) { t->constantsValid = false; g_constOwner[t->device & 63] = t; }
 }
 
+// kernel launch, optionally as a programmatic dependent of the previous kernel in the stream (kernels.cuh: pdl_wait)
+template <class... KArgs, class... Args>
+cudaError_t launchK(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 int rootStage(dmpc_tree* t, double* ll);
 int launchRootSequence(dmpc_tree* t);
 
@@ -350,8 +364,8 @@ int launchPrune(dmpc_tree* t, dim3 grid, const Task* lt, int nTasks, const int32
   t->runCurN = 0;                                  // the first launch of the evaluation takes them
   // 2 sites per thread, 5 blocks per SM (96 registers): measured best on B200 — 4 sites per thread (168-212 registers,
   // 12-16 warps per SM) is 1.3-1.6x slower, 6 blocks per SM (80 registers, spills) 1.05x (profiles/r02_prune_variants.md)
-  if (t->exact) k_prune<true, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
-  else k_prune<false, false, 2, 5><<<grid, TILE / 2, 0, t->stream>>>(t->dv, a);
+  if (t->exact) CUDA_TRY(launchK(k_prune<true, false, 2, 5>, grid, dim3(TILE / 2), 0, t->stream, t->pdl, t->dv, a));
+  else CUDA_TRY(launchK(k_prune<false, false, 2, 5>, grid, dim3(TILE / 2), 0, t->stream, t->pdl, t->dv, a));
   return DMPC_OK;
 }
 
@@ -416,7 +430,8 @@ int launchRounds(dmpc_tree* t, int tiles, int* launchesOut) {
   }
   if (p.chainLevels) {
     const int first = p.levelStart[nLevels], n = p.levelStart[nAll] - first;     // one task per level: n == chainLevels
-    k_walk<<<dim3((unsigned)t->R, (unsigned)tiles), TILE, WALK_SMEM, t->stream>>>(t->dv, t->runTasks + first, n, t->runFlip, t->runCur, t->runCurN);
+    CUDA_TRY(launchK(k_walk, dim3((unsigned)t->R, (unsigned)tiles), dim3(TILE), (size_t)WALK_SMEM, t->stream, t->pdl, t->dv, t->runTasks + first, n,
+                     t->runFlip, t->runCur, t->runCurN));
     t->runCurN = 0;
     t->st.kernel_launches++;
     launches++;
@@ -636,8 +651,10 @@ int launchGather(dmpc_tree* t, int mode, bool publish) {
   attachComm(t);
   if (t->deferred && mode == 1)                  // site-sharded: the gather's optimistic finish assumes the vector enters as zeros
     CUDA_TRY(cudaMemsetAsync(t->rv.carryIn, 0, RMAX * sizeof(float), t->stream));
-  if (t->rv.RP == 4) k_root_gather<4, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
-  else k_root_gather<8, false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, PathView{});
+  // (in a sharded run the memset above sits between the pruning and the gather: an ordinary dependency there)
+  const bool pdl = t->pdl && !(t->deferred && mode == 1);
+  if (t->rv.RP == 4) CUDA_TRY(launchK(k_root_gather<4, false>, dim3(t->T), dim3(TILE), 0, t->stream, pdl, t->dv, t->rv, mode, PathView{}));
+  else CUDA_TRY(launchK(k_root_gather<8, false>, dim3(t->T), dim3(TILE), 0, t->stream, pdl, t->dv, t->rv, mode, PathView{}));
   t->st.kernel_launches++;
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -645,7 +662,7 @@ int launchGather(dmpc_tree* t, int mode, bool publish) {
 
 // reduceAll: 0 = chunk sums only (host protocol of a sharded run), 1 = this handle's total, 2 = cross-rank exchange
 int launchFinal(dmpc_tree* t, int mode, int reduceAll, bool publish) {
-  k_final<false><<<t->T, TILE, 0, t->stream>>>(t->dv, t->rv, mode, reduceAll, publish ? 1 : 0, PathView{});
+  CUDA_TRY(launchK(k_final<false>, dim3(t->T), dim3(TILE), 0, t->stream, t->pdl, t->dv, t->rv, mode, reduceAll, publish ? 1 : 0, PathView{}));
   t->st.kernel_launches++;
   if (!t->capturing) CUDA_TRY(cudaGetLastError());
   return DMPC_OK;
@@ -1096,6 +1113,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
   t->nFlag = (numTips + 15) & ~15;
   t->ht.fuseTips = std::max(1, std::min(o.fuse_tips, (int)FUSE_MAX_TIPS));
+  if (const char* pe = std::getenv("DMPC_PDL")) t->pdl = std::atoi(pe) != 0;
   if (const char* cm = std::getenv("DMPC_CHAIN_MIN")) t->ht.chainMin = std::max((int)CHAIN_MIN, std::atoi(cm));
   if (const char* gc = std::getenv("DMPC_GROUP_COST")) t->ht.groupCost = std::max(0, std::atoi(gc));   // experiments: 0 = one launch per level
   t->exact = o.fuse_exact != 0;

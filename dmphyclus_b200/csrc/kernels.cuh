@@ -74,6 +74,14 @@ struct DevStatus {
   unsigned long long stamp[8];
 };
 static_assert(sizeof(DevStatus) == 128, "status block = 32 words");
+// Programmatic dependent launch: a kernel launched with the stream-serialisation attribute may be SCHEDULED while its
+// predecessor still runs; nothing the predecessor writes may be touched before pdl_wait() (a no-op for an ordinary
+// launch).  Every block signals at once that its successor may be scheduled: the successor's launch latency and block
+// ramp-up then overlap this grid's tail instead of following it.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -270,6 +278,7 @@ template <bool EXACT, bool PATHS, int SPT_, int MINB>
 __global__ void __launch_bounds__(TILE / SPT_, MINB) k_prune(DevView v, PruneArgs pa_) {
   constexpr int PT_ = TILE / SPT_;
   static_assert(!(EXACT && PATHS), "proposal batches run in fast mode only");
+  pdl_wait();
   const Task* __restrict__ tasks = pa_.tasks;
   const Token* __restrict__ prog = pa_.prog;
   const int32_t* __restrict__ tipList = pa_.tipList;
@@ -538,6 +547,7 @@ static_assert((WALK_DEPTH & (WALK_DEPTH - 1)) == 0 && WALK_CHUNK % WALK_WIN == 0
 enum : int { WF_OUTSLOT = 1, WF_SIBTIP = 2, WF_SIBSLOT = 4, WF_SET = 8, WF_FWD0 = 16 };
 
 __global__ void __launch_bounds__(TILE, 2) k_walk(DevView v, const Task* __restrict__ tasks, int nSteps, int flip, const int32_t* curList, int curN) {
+  pdl_wait();
   extern __shared__ __align__(32) double s_ring[];                 // [WALK_DEPTH][TILE][4]
   __shared__ uint4 s_desc[WALK_CHUNK];
   __shared__ __align__(16) double s_lut[2 * 64];                   // [set][mask][4] of this block's rate
@@ -1057,6 +1067,7 @@ __device__ __forceinline__ void publishStatus(const RootView& rv) {
 
 template <int RP, bool BATCH>
 __global__ void __launch_bounds__(TILE) k_root_gather(DevView v, RootView rv0, int mode, PathView pv) {
+  pdl_wait();
   const int pb = BATCH ? blockIdx.y : 0;           // proposal of a batch
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   constexpr int NV = 16;                           // vertices per thread and pass of the (non-batch) flag scan
@@ -1589,6 +1600,7 @@ __global__ void __launch_bounds__(1024) k_chain(DevView v, RootView rv0) {
 // publish: the last thread standing stores the status block into the host mirror (the host polls for it).
 template <bool BATCH>
 __global__ void __launch_bounds__(TILE) k_final(DevView v, RootView rv0, int mode, int reduceAll, int publish, PathView pv) {
+  pdl_wait();
   const int pb = BATCH ? blockIdx.y : 0;
   const RootView rv = BATCH ? forProposal(rv0, pb, v.Sp, v.T) : rv0;
   const double* const rootdot = BATCH ? pv.rootdot + (size_t)pb * v.R * v.Sp : rv.rootdot;
