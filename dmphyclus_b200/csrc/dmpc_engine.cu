@@ -1291,6 +1291,8 @@ static int nniCommon(dmpc_tree* t, const double* w, const double* b, int origin,
                      int numMoves, const double* pi, double* ll, int32_t* edgeOut) {
   t->ht.negateAllUpdateFlags();
   std::vector<int> cand;
+  if (mrcas) t->ht.markMrcas(*mrcas);
+  struct Unmark { HostTree& h; ~Unmark() { h.unmarkMrcas(); } } unmark{t->ht};
   t->ht.nniCandidates(origin, mrcas, cand);
   if (cand.empty())
     return fail(DMPC_ERR_NO_MOVE, "no vertex admits a nearest-neighbour interchange here (the reference calls "

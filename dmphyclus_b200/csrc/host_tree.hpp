@@ -274,7 +274,20 @@ struct HostTree {
     }
   }
 
-  bool inList(const std::vector<long>& l, long id1) const { return std::find(l.begin(), l.end(), id1) != l.end(); }
+  // membership in the cluster-MRCA list of a between-cluster NNI: a byte per vertex, filled once per call (the list has
+  // one entry per cluster and is consulted for every vertex above the clusters)
+  mutable std::vector<uint8_t> mrcaMark;
+  mutable const std::vector<long>* mrcaMarked = nullptr;
+  void markMrcas(const std::vector<long>& l) const {
+    mrcaMark.assign((size_t)numVerts + 2, 0);
+    for (long id1 : l) if (id1 >= 0 && id1 <= numVerts) mrcaMark[(size_t)id1] = 1;
+    mrcaMarked = &l;
+  }
+  void unmarkMrcas() const { mrcaMarked = nullptr; }
+  bool inList(const std::vector<long>& l, long id1) const {
+    if (mrcaMarked == &l) return id1 >= 0 && id1 <= numVerts && mrcaMark[(size_t)id1];
+    return std::find(l.begin(), l.end(), id1) != l.end();
+  }
 
   // GetNNIverticesWithin / Between (AugTree.cpp:144-209): pre-order list of vertices that have at least one
   // internal child (which, for the between variant, is not a cluster MRCA; the walk stops at cluster MRCAs).
