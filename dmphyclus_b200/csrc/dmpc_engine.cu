@@ -2232,6 +2232,13 @@ int dmpc_comm_destroy(dmpc_comm* c) {
   return DMPC_OK;
 }
 
+void dmpc_shard_range(int sitesTotal, int rank, int world, int* begin, int* end) {
+  int b = 0, e = 0;
+  if (sitesTotal > 0 && world > 0 && rank >= 0 && rank < world) shardRange(sitesTotal, rank, world, &b, &e);
+  if (begin) *begin = b;
+  if (end) *end = e;
+}
+
 double dmpc_reduce_chunks(const double* chunkSums, int n) {
   volatile double acc[RED];
   for (int tI = 0; tI < RED; tI++) {

@@ -90,6 +90,7 @@ ABI = {
     "dmpc_shard_num_chunks": (C.c_int, [_P]),
     "dmpc_shard_finish": (C.c_int, [_P, _dbl_p]),
     "dmpc_reduce_chunks": (C.c_double, [_dbl_p, C.c_int]),
+    "dmpc_shard_range": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dmpc_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P), C.c_void_p]),
     "dmpc_comm_connect": (C.c_int, [_P, C.c_void_p]),
     "dmpc_comm_destroy": (C.c_int, [_P]),

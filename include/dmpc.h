@@ -225,6 +225,12 @@ int dmpc_comm_connect(dmpc_comm* c, const void* allHandles);
 int dmpc_comm_destroy(dmpc_comm* c);
 int dmpc_shard_fast_result(dmpc_tree* t, int* ok, double* logLik);
 
+/* The contiguous block of sites [*begin, *end) that rank / shard `rank` of `world` owns in an alignment of sitesTotal sites:
+ * equal blocks, rounded up to the 64-site reduction chunk (so that chunk boundaries — and the summation tree — do not depend
+ * on the number of ranks); trailing ranks of a short alignment get an empty block.  This is the layout of a multi-device
+ * handle (dmpc_options.n_devices) and the one dmphyclus_b200/sharded.py uses for process-per-GPU runs. */
+void dmpc_shard_range(int sitesTotal, int rank, int world, int* begin, int* end);
+
 /* Host-side twin of the device's final reduction: adds n chunk sums in the same fixed order as the single-GPU
  * kernel (256 strided accumulators, then a binary tree), so 1-GPU and N-GPU totals agree bit for bit. */
 double dmpc_reduce_chunks(const double* chunkSums, int n);

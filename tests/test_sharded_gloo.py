@@ -82,3 +82,19 @@ def test_shard_ranges_are_chunk_aligned_and_cover():
             for r in range(world):
                 b, e = shard_range(S, r, world)
                 assert e > b, (name, world, r)
+
+
+def test_library_and_python_agree_on_the_shard_layout():
+    """dmpc_shard_range (the layout of a multi-device handle inside libdmpc) == sharded.shard_range (process per GPU)."""
+    import ctypes as C
+    from dmphyclus_b200 import build
+    from dmphyclus_b200.engine import load_library
+    from dmphyclus_b200.sharded import shard_range
+    build.build()
+    lib = load_library()
+    b, e = C.c_int(), C.c_int()
+    for S in list(range(1, 70)) + [127, 128, 129, 1499, 1500, 1501, 4095, 4096, 10000, 30000, 123457]:
+        for world in range(1, 9):
+            for r in range(world):
+                lib.dmpc_shard_range(S, r, world, C.byref(b), C.byref(e))
+                assert (b.value, e.value) == shard_range(S, r, world), (S, world, r)
