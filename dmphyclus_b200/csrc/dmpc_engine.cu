@@ -54,7 +54,7 @@ constexpr size_t PLAN_SLACK = 64;
 struct ResPack {
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;   // the alignment upload of logLikCpp runs here, slab by slab, ahead of the pruning
-  cudaEvent_t slabEv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t slabEv[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [8]: the plan upload of a slabbed create
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* h_plan = nullptr;        // pinned: tasks | tokens | tip list of one evaluation, packed, uploaded in ONE copy
   int32_t* h_curList = nullptr;  // pinned
@@ -145,6 +145,7 @@ struct dmpc_tree {
   // logLikCpp only: the alignment is uploaded in slabs of site tiles on the copy stream while the slabs already on the
   // device are pruned (one-shot; the first evaluation consumes it)
   struct { int n = 0; const uint8_t* src = nullptr; size_t pitch = 0; uint8_t* stage = nullptr; } slabs;
+  bool planOnCopyStream = false;   // the next uploadPlan goes through the copy stream (slabbed create: see createImpl)
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
   bool carryIsZero = true;
@@ -395,7 +396,16 @@ int uploadPlan(dmpc_tree* t, const HostTree::Plan& p, bool withPending = false) 
   }
   const size_t offCur = t->planBytes;
   t->planBytes += (size_t)nC * sizeof(int32_t);
-  if (t->planBytes) CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
+  if (t->planBytes && t->planOnCopyStream) {
+    // slab 0 of the alignment is in flight on the copy stream, and a copy queued on another stream is not served until
+    // that stream's copies run dry (measured): the plan takes its turn IN the copy stream, between slab 0 and slab 1
+    CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->pack.copyStream));
+    CUDA_TRY(cudaEventRecord(t->pack.slabEv[8], t->pack.copyStream));
+    CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[8], 0));
+  } else if (t->planBytes) {
+    CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
+  }
+  t->planOnCopyStream = false;
   t->runTasks = reinterpret_cast<const Task*>(t->d_plan);
   t->runTokens = reinterpret_cast<const Token*>(t->d_plan + t->planOffTok);
   t->runTips = reinterpret_cast<const int32_t*>(t->d_plan + t->planOffTip);
@@ -441,6 +451,18 @@ int launchRounds(dmpc_tree* t, int tiles, int* launchesOut) {
   return DMPC_OK;
 }
 
+// slab k of the alignment upload (site tiles [k * per, (k + 1) * per)) on the copy stream, and its event
+int queueSlab(dmpc_tree* t, int k) {
+  const int per = (t->T + t->slabs.n - 1) / t->slabs.n;
+  const int t0 = k * per, t1 = std::min(t->T, t0 + per);
+  const int c0 = t0 * TILE, c1 = std::min(t->S, t1 * TILE);      // real columns of the slab (pad columns have no source)
+  if (c1 > c0)
+    CUDA_TRY(cudaMemcpy2DAsync(t->slabs.stage + c0, (size_t)t->S, t->slabs.src + c0, t->slabs.pitch, (size_t)(c1 - c0), (size_t)t->N,
+                               cudaMemcpyHostToDevice, t->pack.copyStream));
+  CUDA_TRY(cudaEventRecord(t->pack.slabEv[k], t->pack.copyStream));
+  return DMPC_OK;
+}
+
 int runPlan(dmpc_tree* t) {
   const HostTree::Plan& p = *t->runPlanMeta;
   int rcE, launches = 0;
@@ -448,20 +470,15 @@ int runPlan(dmpc_tree* t) {
   if (t->slabs.n > 1 && !t->capturing) {
     // logLikCpp: slab k of the alignment is copied (copy stream), re-pitched and pruned while slab k + 1 is on its way
     const int nS = t->slabs.n, per = (t->T + nS - 1) / nS;
-    t->slabs.n = 0;                                // one-shot
-    CUDA_TRY(cudaEventRecord(t->ev[5], t->pack.copyStream));
     for (int k = 0; k < nS; k++) {
       const int t0 = k * per, t1 = std::min(t->T, t0 + per);
       if (t1 <= t0) break;
-      const int c0 = t0 * TILE, c1 = std::min(t->S, t1 * TILE);      // real columns of the slab (pad columns have no source)
-      if (c1 > c0)
-        CUDA_TRY(cudaMemcpy2DAsync(t->slabs.stage + c0, (size_t)t->S, t->slabs.src + c0, t->slabs.pitch, (size_t)(c1 - c0), (size_t)t->N,
-                                   cudaMemcpyHostToDevice, t->pack.copyStream));
-      CUDA_TRY(cudaEventRecord(t->pack.slabEv[k], t->pack.copyStream));
+      const int c0 = t0 * TILE;
+      if (k > 0) { const int rq = queueSlab(t, k); if (rq) return rq; }     // (slab 0 was queued by createImpl, ahead of the planning)
       if (k == nS - 1 || t1 == t->T) CUDA_TRY(cudaEventRecord(t->ev[6], t->pack.copyStream));
       CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[k], 0));
       {
-        const int p1 = t1 * TILE;                  // ... but the padded layout is filled up to the tile boundary
+        const int p1 = t1 * TILE;                  // the padded layout is filled up to the tile boundary
         const size_t n = (size_t)t->N * (p1 - c0);
         k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(t->slabs.stage, t->d_tipmask, t->N, t->S, t->Sp, c0, p1, &t->rv.st->badCells);
         t->st.kernel_launches++;
@@ -471,6 +488,7 @@ int runPlan(dmpc_tree* t) {
       t->dv.tileOff = 0;
       if (rc) return rc;
     }
+    t->slabs.n = 0;                                // one-shot
   } else {
     const int rc = launchRounds(t, t->T, &launches);
     if (rc) return rc;
@@ -484,10 +502,10 @@ int runPlan(dmpc_tree* t) {
 }
 
 // ComputeLoglik (AugTree.cpp:289-326): prune the dirty levels, then reduce at the root.
-int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll) {
+int evaluate(dmpc_tree* t, const double* within, const double* between, const double* pi, double* ll, bool lockHeld = false) {
   int rc;
   std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
-  if (!t->isShard) deviceLock.lock();            // (the leader of a multi-device handle holds the locks of all its devices)
+  if (!t->isShard && !lockHeld) deviceLock.lock();            // (the leader of a multi-device handle holds the locks of all its devices)
   if ((rc = ensureDevice(t))) return rc;
   claimConstants(t);
   const auto h0 = std::chrono::steady_clock::now();
@@ -860,6 +878,7 @@ void destroy(dmpc_tree* t) {
   cudaSetDevice(t->device);
   for (auto& g : t->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   if (t->stream) {
+    if (t->pack.copyStream) cudaStreamSynchronize(t->pack.copyStream);   // a create that failed may still have slabs in flight
     for (void* p : t->allocs) cudaFreeAsync(p, t->stream);
     cudaStreamSynchronize(t->stream);                  // the pack (stream, pinned buffers) goes back idle
   }
@@ -1106,8 +1125,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
   dmpc_tree* t = new dmpc_tree;
   t->isShard = isShard;
   if (o.device < 0) { if (cudaGetDevice(&t->device) != cudaSuccess) t->device = 0; } else t->device = o.device;
-  if (!t->ht.build(edge, nEdgeRows, numTips)) { std::string e = t->ht.err; delete t; return fail(DMPC_ERR_ARG, e); }
-  t->ht.associate(clusterMRCAs, nClusterMRCAs);
+  if (nEdgeRows != 2 * numTips - 2) { delete t; return fail(DMPC_ERR_ARG, "edge matrix must have 2*numTips-2 rows"); }
   t->ht.withinIdx = withinMatListIndex; t->ht.betweenIdx = betweenMatListIndex;
   t->N = numTips; t->S = numLoci; t->R = numRateCats;
   t->nReal = numTips - 1; t->nInt = numTips;      // rows of the per-vertex arrays: N-1 internal vertices + 1 scratch row
@@ -1201,14 +1219,31 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     int nSlab = (int)std::lround(std::sqrt(pruneUs / 20.0));
     nSlab = std::max(1, std::min({nSlab, 8, t->T / 4}));
     if (const char* e = std::getenv("DMPC_UPLOAD_SLABS")) nSlab = std::max(1, std::min({8, std::atoi(e), t->T}));
+    // the matrices go up first: once the alignment is under way, other copies wait for it (see uploadPlan).  They live in
+    // the device's constant bank, which this handle now holds until the evaluation's results are back
+    std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
+    if (!t->isShard) deviceLock.lock();
+    claimConstants(t);
+    if ((r2 = uploadConstants(t, withinTransMats, betweenTransMats, limProbs))) return r2;
     if (nSlab > 1) {
+      t->planOnCopyStream = true;
       // the copy stream must not run ahead of the allocation / memsets queued on the main stream
       CUDA_TRY(cudaEventRecord(t->pack.slabEv[7], t->stream));
       CUDA_TRY(cudaStreamWaitEvent(t->pack.copyStream, t->pack.slabEv[7], 0));
       t->slabs.n = nSlab; t->slabs.src = alignmentBin; t->slabs.pitch = alignPitch; t->slabs.stage = stage;
+      // slab 0 is queued now, before the host has even linked the tree: PCIe works on it while the host builds the tree
+      // and the plan (0.35 + 0.3 ms at 10,000 tips; a slab of 10,000 x 30,000 takes 0.7 ms).  Only slab 0: copies of all
+      // streams share one FIFO copy engine, and the plan (a copy as well) must not queue behind the whole alignment —
+      // with every slab queued here the pruning started only after the last one (measured: 10.9 ms instead of 7.0)
+      CUDA_TRY(cudaEventRecord(t->ev[5], t->pack.copyStream));
+      if ((r2 = queueSlab(t, 0))) return r2;
     } else {
       CUDA_TRY(cudaEventRecord(t->ev[5], t->stream));
-      CUDA_TRY(cudaMemcpy2DAsync(stage, (size_t)t->S, alignmentBin, alignPitch, (size_t)t->S, (size_t)t->N, cudaMemcpyHostToDevice, t->stream));
+      // (a 2-D copy is programmed row by row: 100,000 rows of 1,500 bytes ran at 11.7 GB/s, 13.1 ms for 150 MB)
+      if (alignPitch == (size_t)t->S)
+        CUDA_TRY(cudaMemcpyAsync(stage, alignmentBin, (size_t)t->N * t->S, cudaMemcpyHostToDevice, t->stream));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(stage, (size_t)t->S, alignmentBin, alignPitch, (size_t)t->S, (size_t)t->N, cudaMemcpyHostToDevice, t->stream));
       {
         const size_t n = (size_t)t->N * t->Sp;
         k_prepare_masks<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(stage, t->d_tipmask, t->N, t->S, t->Sp, 0, t->Sp, &t->rv.st->badCells);
@@ -1216,7 +1251,10 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
       }
       CUDA_TRY(cudaEventRecord(t->ev[6], t->stream));
     }
-    int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut);
+    // the tree is linked and validated while the alignment is in flight
+    if (!t->ht.build(edge, nEdgeRows, numTips)) return fail(DMPC_ERR_ARG, t->ht.err);
+    t->ht.associate(clusterMRCAs, nClusterMRCAs);
+    int rcEval = evaluate(t, withinTransMats, betweenTransMats, limProbs, logLikOut, true);
     if (rcEval == DMPC_OK) {                     // (the upload's closing event sits on the copy stream: it has long fired)
       float ms = 0;
       if (cudaEventSynchronize(t->ev[6]) == cudaSuccess && cudaEventElapsedTime(&ms, t->ev[5], t->ev[6]) == cudaSuccess) t->st.create_upload_ms = ms;

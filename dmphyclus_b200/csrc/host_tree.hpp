@@ -511,6 +511,9 @@ struct HostTree {
     computeTips();
     std::vector<int>& pre = p.pre;
     pre.clear();
+    if (p.tokens.capacity() == 0) {          // first (full) plan of a handle: no growth by doubling through 100,000s of entries
+      p.tokens.reserve((size_t)numTips + numTips / 4); p.tipList.reserve(numTips); pre.reserve(numTips);
+    }
     std::vector<int> stack(1, root());
     while (!stack.empty()) {
       int v = stack.back(); stack.pop_back();
