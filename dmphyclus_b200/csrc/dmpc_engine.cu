@@ -51,10 +51,11 @@ constexpr size_t PLAN_SLACK = 64;
 // Per-device cache of the host-side resources a handle needs (stream, events, pinned staging buffers).  Creating
 // and destroying them costs milliseconds (cudaHostAlloc/cudaFreeHost synchronise the device), which would dwarf
 // a logLikFromClusInd-style create/evaluate/destroy cycle; handles borrow a pack and give it back.
+constexpr int MAX_SLABS = 16;
 struct ResPack {
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;   // the alignment upload of logLikCpp runs here, slab by slab, ahead of the pruning
-  cudaEvent_t slabEv[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [8]: the plan upload of a slabbed create
+  cudaEvent_t slabEv[MAX_SLABS + 1] = {};   // [MAX_SLABS]: the plan upload of a slabbed create
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* h_plan = nullptr;        // pinned: tasks | tokens | tip list of one evaluation, packed, uploaded in ONE copy
   int32_t* h_curList = nullptr;  // pinned
@@ -144,7 +145,25 @@ struct dmpc_tree {
   bool evalTimePending = false;  // last_eval_ms still to be read from the events (done lazily: the result is polled)
   // logLikCpp only: the alignment is uploaded in slabs of site tiles on the copy stream while the slabs already on the
   // device are pruned (one-shot; the first evaluation consumes it)
-  struct { int n = 0; const uint8_t* src = nullptr; size_t pitch = 0; uint8_t* stage = nullptr; } slabs;
+  struct {
+    int n = 0; const uint8_t* src = nullptr; size_t pitch = 0; uint8_t* stage = nullptr;
+    int tile[MAX_SLABS + 2] = {0};           // slab k = site tiles [tile[k], tile[k + 1])
+    // Equal slabs.  Tried: sizes shrinking by 0.75 from slab to slab, so that the pruning left when the last byte has
+    // landed is that of a small slab — measured WORSE on 10,000 x 30,000 (6.96 against 6.44 ms end to end): the plan
+    // queues behind a slab 0 of 1.55 ms instead of 0.7, and the small late slabs prune at a fraction of the full rate.
+    void cut(int T, int nSlab) {
+      n = nSlab;
+      const double q = 1.0;
+      double sum = 0.0, w = 1.0, acc = 0.0;
+      for (int k = 0; k < n; k++, w *= q) sum += w;
+      w = 1.0;
+      for (int k = 0; k < n; k++, w *= q) {
+        tile[k] = k == 0 ? 0 : std::min(T - (n - k), std::max(tile[k - 1] + 1, (int)std::lround(T * acc / sum)));
+        acc += w;
+      }
+      tile[n] = T;
+    }
+  } slabs;
   bool planOnCopyStream = false;   // the next uploadPlan goes through the copy stream (slabbed create: see createImpl)
   double* h_chunks = nullptr;    // pinned: chunk sums of the last deferred evaluation
   bool chunksOnHost = false;     // ... and whether they are final (no rescaled site, zero entry vector)
@@ -400,8 +419,8 @@ int uploadPlan(dmpc_tree* t, const HostTree::Plan& p, bool withPending = false) 
     // slab 0 of the alignment is in flight on the copy stream, and a copy queued on another stream is not served until
     // that stream's copies run dry (measured): the plan takes its turn IN the copy stream, between slab 0 and slab 1
     CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->pack.copyStream));
-    CUDA_TRY(cudaEventRecord(t->pack.slabEv[8], t->pack.copyStream));
-    CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[8], 0));
+    CUDA_TRY(cudaEventRecord(t->pack.slabEv[MAX_SLABS], t->pack.copyStream));
+    CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[MAX_SLABS], 0));
   } else if (t->planBytes) {
     CUDA_TRY(cudaMemcpyAsync(t->d_plan, t->h_plan, t->planBytes, cudaMemcpyHostToDevice, t->stream));
   }
@@ -451,10 +470,9 @@ int launchRounds(dmpc_tree* t, int tiles, int* launchesOut) {
   return DMPC_OK;
 }
 
-// slab k of the alignment upload (site tiles [k * per, (k + 1) * per)) on the copy stream, and its event
+// slab k of the alignment upload on the copy stream, and its event
 int queueSlab(dmpc_tree* t, int k) {
-  const int per = (t->T + t->slabs.n - 1) / t->slabs.n;
-  const int t0 = k * per, t1 = std::min(t->T, t0 + per);
+  const int t0 = t->slabs.tile[k], t1 = t->slabs.tile[k + 1];
   const int c0 = t0 * TILE, c1 = std::min(t->S, t1 * TILE);      // real columns of the slab (pad columns have no source)
   if (c1 > c0)
     CUDA_TRY(cudaMemcpy2DAsync(t->slabs.stage + c0, (size_t)t->S, t->slabs.src + c0, t->slabs.pitch, (size_t)(c1 - c0), (size_t)t->N,
@@ -469,13 +487,12 @@ int runPlan(dmpc_tree* t) {
   if ((rcE = recordEv(t, 0))) return rcE;
   if (t->slabs.n > 1 && !t->capturing) {
     // logLikCpp: slab k of the alignment is copied (copy stream), re-pitched and pruned while slab k + 1 is on its way
-    const int nS = t->slabs.n, per = (t->T + nS - 1) / nS;
+    const int nS = t->slabs.n;
     for (int k = 0; k < nS; k++) {
-      const int t0 = k * per, t1 = std::min(t->T, t0 + per);
-      if (t1 <= t0) break;
+      const int t0 = t->slabs.tile[k], t1 = t->slabs.tile[k + 1];
       const int c0 = t0 * TILE;
       if (k > 0) { const int rq = queueSlab(t, k); if (rq) return rq; }     // (slab 0 was queued by createImpl, ahead of the planning)
-      if (k == nS - 1 || t1 == t->T) CUDA_TRY(cudaEventRecord(t->ev[6], t->pack.copyStream));
+      if (k == nS - 1) CUDA_TRY(cudaEventRecord(t->ev[6], t->pack.copyStream));
       CUDA_TRY(cudaStreamWaitEvent(t->stream, t->pack.slabEv[k], 0));
       {
         const int p1 = t1 * TILE;                  // the padded layout is filled up to the tile boundary
@@ -1218,7 +1235,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
     const double pruneUs = (double)t->nReal * t->S * t->R * 4.2e-6;
     int nSlab = (int)std::lround(std::sqrt(pruneUs / 20.0));
     nSlab = std::max(1, std::min({nSlab, 8, t->T / 4}));
-    if (const char* e = std::getenv("DMPC_UPLOAD_SLABS")) nSlab = std::max(1, std::min({8, std::atoi(e), t->T}));
+    if (const char* e = std::getenv("DMPC_UPLOAD_SLABS")) nSlab = std::max(1, std::min({MAX_SLABS, std::atoi(e), t->T}));
     // the matrices go up first: once the alignment is under way, other copies wait for it (see uploadPlan).  They live in
     // the device's constant bank, which this handle now holds until the evaluation's results are back
     std::unique_lock<std::mutex> deviceLock(g_deviceMutex[t->device & 63], std::defer_lock);
@@ -1230,7 +1247,7 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
       // the copy stream must not run ahead of the allocation / memsets queued on the main stream
       CUDA_TRY(cudaEventRecord(t->pack.slabEv[7], t->stream));
       CUDA_TRY(cudaStreamWaitEvent(t->pack.copyStream, t->pack.slabEv[7], 0));
-      t->slabs.n = nSlab; t->slabs.src = alignmentBin; t->slabs.pitch = alignPitch; t->slabs.stage = stage;
+      t->slabs.cut(t->T, nSlab); t->slabs.src = alignmentBin; t->slabs.pitch = alignPitch; t->slabs.stage = stage;
       // slab 0 is queued now, before the host has even linked the tree: PCIe works on it while the host builds the tree
       // and the plan (0.35 + 0.3 ms at 10,000 tips; a slab of 10,000 x 30,000 takes 0.7 ms).  Only slab 0: copies of all
       // streams share one FIFO copy engine, and the plan (a copy as well) must not queue behind the whole alignment —
