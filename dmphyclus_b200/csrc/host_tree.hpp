@@ -101,6 +101,7 @@ struct HostTree {
     tipsValid = false;
     std::fill(kids.begin(), kids.end(), -1);
     std::fill(nkids.begin(), nkids.end(), 0);
+    std::fill(parent.begin(), parent.end(), -1);
     for (int k = 0; k < nEdgeRows; k++) {
       int p = edge[k] - 1, c = edge[k + nEdgeRows] - 1;
       if (p < numTips || p >= numVerts || c < 0 || c >= numVerts || c == p) { err = "edge matrix entry out of range"; return false; }
@@ -145,6 +146,11 @@ struct HostTree {
     if (!link(edge, nEdgeRows)) return false;
     committedEdge.assign(edge, edge + 2 * (size_t)nEdgeRows);
     exportChecked = exportValid = false; pendingNni = false; nniLog.clear();
+    return checkRooted();
+  }
+
+  // after link(): one tree, rooted at vertex numTips+1, holding every vertex
+  bool checkRooted() {
     if (parent[root()] != -1) { err = "vertex numTips+1 must be the root"; return false; }
     // every vertex but the root is named as a child — with 2N-2 rows, exactly once (a child named twice would leave
     // another vertex hanging nowhere, and the traversal below would count the twice-named one twice)
@@ -264,7 +270,7 @@ struct HostTree {
       return true;
     }
     pendingNni = false; pendingRoot = -1; nniLog.clear();
-    if (!link(edge, nEdgeRows)) return false;
+    if (!link(edge, nEdgeRows) || !checkRooted()) return false;
     committedEdge.assign(edge, edge + n2);
     exportChecked = exportValid = false;
     return true;

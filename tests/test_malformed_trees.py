@@ -83,3 +83,27 @@ def test_malformed_trees_are_refused(lib):
     if len(keep_two(u)) == 2 and len(keep_two(w)) == 2:
         pass                                       # degrees intact: the connectivity check has to catch it
     assert refused(e, "cycle")
+
+
+def test_restore_refuses_a_malformed_matrix(lib):
+    """dmpc_restore_previous_config re-links the tree from the matrix R hands back (BuildTreeNoAssign,
+    /root/reference/src/AugTree.cpp:88-101): the same checks apply there."""
+    lib.dmpc_hp_restore.restype = C.c_int
+    lib.dmpc_hp_restore.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int]
+    rng = np.random.default_rng(13)
+    n = 16
+    good = np.asarray(synth.random_tree(n, rng, "random"))
+    e = np.ascontiguousarray(good.astype(np.int32).T).ravel()
+    h = C.c_void_p()
+    assert lib.dmpc_hp_create(e.ctypes.data_as(C.POINTER(C.c_int32)), len(e) // 2, n, None, 0, 15, C.byref(h)) == 0
+    other = np.asarray(synth.random_tree(n, rng, "random"))                      # a different, well-formed tree: accepted
+    o = np.ascontiguousarray(other.astype(np.int32).T).ravel()
+    assert lib.dmpc_hp_restore(h, o.ctypes.data_as(C.POINTER(C.c_int32)), len(o) // 2, 1, None, 0, 0) == 0
+    bad = good.copy()
+    tips_rows = np.flatnonzero(bad[:, 1] <= n)
+    bad[tips_rows[1], 1] = bad[tips_rows[0], 1]                                  # a tip named twice
+    b = np.ascontiguousarray(bad.astype(np.int32).T).ravel()
+    assert lib.dmpc_hp_restore(h, b.ctypes.data_as(C.POINTER(C.c_int32)), len(b) // 2, 1, None, 0, 0) != 0
+    assert b"single rooted tree" in lib.dmpc_last_error()
+    assert lib.dmpc_hp_restore(h, e.ctypes.data_as(C.POINTER(C.c_int32)), len(e) // 2, 1, None, 0, 0) == 0   # and recovers
+    lib.dmpc_hp_destroy(h)
