@@ -1249,9 +1249,9 @@ static int createImpl(const int32_t* edge, int nEdgeRows, const double* clusterM
       CUDA_TRY(cudaStreamWaitEvent(t->pack.copyStream, t->pack.slabEv[7], 0));
       t->slabs.cut(t->T, nSlab); t->slabs.src = alignmentBin; t->slabs.pitch = alignPitch; t->slabs.stage = stage;
       // slab 0 is queued now, before the host has even linked the tree: PCIe works on it while the host builds the tree
-      // and the plan (0.35 + 0.3 ms at 10,000 tips; a slab of 10,000 x 30,000 takes 0.7 ms).  Only slab 0: copies of all
-      // streams share one FIFO copy engine, and the plan (a copy as well) must not queue behind the whole alignment —
-      // with every slab queued here the pruning started only after the last one (measured: 10.9 ms instead of 7.0)
+      // and the plan (0.35 + 0.3 ms at 10,000 tips; a slab of 10,000 x 30,000 takes 0.7 ms).  Only slab 0: a copy
+      // queued on another stream is not served while the copy stream still has copies queued, and the plan is a copy
+      // as well — with every slab queued here the pruning started only after the last one (measured: 10.9 ms, not 7.0)
       CUDA_TRY(cudaEventRecord(t->ev[5], t->pack.copyStream));
       if ((r2 = queueSlab(t, 0))) return r2;
     } else {
