@@ -139,7 +139,7 @@ class Oracle:
         edge = np.zeros(2 * (2 * n - 2), np.int32)
         ll = self.lib.orc_within_nni(ptr, _p(w, _dbl_p), _p(b, _dbl_p), int(MRCAofClusForNNI), int(numMovesNNI),
                                      _p(pi, _dbl_p), _p(edge, _int_p))
-        if np.isnan(ll):
+        if np.isnan(ll) and not edge.any():      # (a NaN log-likelihood WITH an edge matrix is a result: total underflow)
             raise ValueError("no NNI move is possible in this cluster")
         return {"logLik": ll, "edge": edge.reshape(2, -1).T.copy()}
 
@@ -151,7 +151,7 @@ class Oracle:
         edge = np.zeros(2 * (2 * n - 2), np.int32)
         ll = self.lib.orc_between_nni(ptr, _p(w, _dbl_p), _p(b, _dbl_p), _p(m, _dbl_p), len(m), int(numMovesNNI),
                                       _p(pi, _dbl_p), _p(edge, _int_p))
-        if np.isnan(ll):
+        if np.isnan(ll) and not edge.any():
             raise ValueError("no NNI move is possible in the supporting tree")
         return {"logLik": ll, "edge": edge.reshape(2, -1).T.copy()}
 
