@@ -123,8 +123,8 @@ struct dmpc_tree {
   struct {
     bool valid = false;
     int fuse = 0;
-    std::vector<int32_t> kids;
-    std::vector<uint8_t> within, cur;
+    PooledVec<int32_t> kids;             // (recycled storage: a create / destroy cycle re-uses the blocks, host_tree.hpp)
+    PooledVec<uint8_t> within, cur;
     HostTree::Plan meta;                 // level structure and counters (the big vectors stay empty)
     char* dPlan = nullptr;               // device copy of the packed plan
     size_t offTok = 0, offTip = 0, offSeg = 0, bytes = 0;
@@ -573,7 +573,7 @@ int evaluate(dmpc_tree* t, const double* within, const double* between, const do
     t->runFlip = flip;
     t->planCacheHits++;
   } else {
-    std::vector<uint8_t> curBefore;
+    PooledVec<uint8_t> curBefore;
     if (full) curBefore = ht.cur;
     ht.plan(p);
     const int nT = (int)p.tasks.size();

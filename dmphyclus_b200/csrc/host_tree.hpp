@@ -9,7 +9,10 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <iterator>
+#include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "task.hpp"
@@ -43,25 +46,83 @@ struct TausRng {
   }
 };
 
+// A std::vector whose storage outlives it.  A logLikFromClusInd-style create / evaluate / destroy cycle allocates ~12 MB
+// of host vectors at 100,000 tips; blocks of that size go back to the operating system when they are freed (malloc trims
+// or unmaps them), so EVERY create paid the page faults of first touch again — about a third of its host time
+// (tools/host_bench.cpp).  The storage of a dying vector is parked instead (emptied, capacity kept), and a vector about
+// to grow beyond its capacity (assign / resize / reserve) first looks for a parked block that is large enough — the
+// smallest such one.  Contents never survive: a parked vector is empty, and every user assigns or clears before it reads.
+// Only the calls made on the PooledVec itself look into the pool; through a std::vector& it behaves like any vector.
+template <class T>
+struct PooledVec : std::vector<T> {
+  typedef std::vector<T> Base;
+  PooledVec() {}
+  PooledVec(const PooledVec& o) : Base() { want(o.size()); Base::operator=(o); }
+  PooledVec& operator=(const PooledVec& o) { want(o.size()); Base::operator=(o); return *this; }
+  PooledVec& operator=(const Base& o) { want(o.size()); Base::operator=(o); return *this; }
+  ~PooledVec() { park(); }
+  void assign(size_t n, const T& v) { want(n); Base::assign(n, v); }
+  template <class It, class = typename std::enable_if<!std::is_integral<It>::value>::type>
+  void assign(It first, It last) { want((size_t)std::distance(first, last)); Base::assign(first, last); }
+  void resize(size_t n) { want(n); Base::resize(n); }
+  void reserve(size_t n) { want(n); Base::reserve(n); }
+
+ private:
+  struct Pool { std::mutex m; std::vector<Base> free; };
+  static Pool& pool() { static Pool* p = new Pool; return *p; }       // never destroyed: handles may die after the statics
+  // bytes below which parking is pointless / above which a block is not worth holding on to; blocks kept per element type
+  static constexpr size_t KEEP_MIN = 64 * 1024, KEEP_MAX = (size_t)64 << 20, KEEP_MAX_VECS = 48;
+  // about to hold n elements: if that needs new storage, take the smallest parked block that fits (what this vector
+  // held so far moves along; its old block is parked in turn)
+  void want(size_t n) {
+    if (n <= this->capacity() || n * sizeof(T) < KEEP_MIN) return;
+    Base got;
+    {
+      Pool& p = pool();
+      std::lock_guard<std::mutex> lk(p.m);
+      size_t best = p.free.size();
+      for (size_t i = 0; i < p.free.size(); i++)
+        if (p.free[i].capacity() >= n && (best == p.free.size() || p.free[i].capacity() < p.free[best].capacity())) best = i;
+      if (best == p.free.size()) return;
+      got.swap(p.free[best]);
+      p.free[best].swap(p.free.back());
+      p.free.pop_back();
+    }
+    got.assign(this->begin(), this->end());      // (callers grow before they fill: this copies nothing in practice)
+    Base::swap(got);
+    PooledVec old;
+    old.Base::swap(got);                         // the block held so far: parked by old's destructor if it is worth it
+  }
+  void park() {
+    if (this->capacity() * sizeof(T) < KEEP_MIN || this->capacity() * sizeof(T) > KEEP_MAX) return;
+    this->clear();
+    Pool& p = pool();
+    std::lock_guard<std::mutex> lk(p.m);
+    if (p.free.size() >= KEEP_MAX_VECS) return;
+    p.free.emplace_back();
+    p.free.back().swap(*this);
+  }
+};
+
 struct HostTree {
   int numTips = 0, numVerts = 0;
-  std::vector<int32_t> parent;           // -1 for the root
-  std::vector<int32_t> kids;             // [2*v + i]: ordered children (-1 = absent); order = the reference's _children
-  std::vector<uint8_t> nkids;
-  std::vector<uint8_t> within;           // _withinParentBranch
-  std::vector<uint8_t> solved;           // _isSolved (tips: always 1)
-  std::vector<uint8_t> touched;          // _updateFlag
-  std::vector<uint8_t> cur;              // which of the two HBM slots holds the vertex's current partial
+  PooledVec<int32_t> parent;             // -1 for the root
+  PooledVec<int32_t> kids;               // [2*v + i]: ordered children (-1 = absent); order = the reference's _children
+  PooledVec<uint8_t> nkids;
+  PooledVec<uint8_t> within;             // _withinParentBranch
+  PooledVec<uint8_t> solved;             // _isSolved (tips: always 1)
+  PooledVec<uint8_t> touched;            // _updateFlag
+  PooledVec<uint8_t> cur;                // which of the two HBM slots holds the vertex's current partial
   int withinIdx = 0, betweenIdx = 0;
   TausRng rng;
   std::string err;
   // small-clade fusion: a vertex with at most fuseTips tips below it (and not the root) is never stored; it is
   // recomputed from the tip masks inside the task of its nearest stored ancestor.  1 = every vertex is stored.
   int fuseTips = 1;
-  std::vector<int32_t> tips;             // number of tips below each vertex (1 for a tip)
+  PooledVec<int32_t> tips;               // number of tips below each vertex (1 for a tip)
   bool tipsValid = false;
-  std::vector<uint8_t> linkScratch;
-  std::vector<uint8_t> mat;              // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
+  PooledVec<uint8_t> linkScratch;
+  PooledVec<uint8_t> mat;                // fused-size vertices the plan being built evaluates as stored tasks (see CHAIN_MIN)
   bool walkChains = true;                // false: never hand a chain to k_walk (its 32-bit element offsets would overflow)
   bool allInvalid = true;                // every internal vertex is unsolved (InvalidateAll, or nothing computed yet)
   // --- O(touched) NNI bookkeeping.  R hands the committed edge matrix back on every rejected NNI move
@@ -74,9 +135,11 @@ struct HostTree {
   std::vector<NniUndo> nniLog;           // swaps since the committed topology (the pending NNI proposal)
   bool pendingNni = false;               // an NNI proposal has been evaluated and neither restored nor followed by another proposal
   int pendingRoot = -1;                  // ... the vertex whose subtree it rearranged (-1: several moves, whole matrix re-exported)
-  std::vector<int32_t> committedEdge;    // R's edge matrix of the committed topology (column-major, 1-based); empty = unknown
-  std::vector<int32_t> rowOf;            // exportValid: row of each vertex's own edge in committedEdge
+  PooledVec<int32_t> committedEdge;      // R's edge matrix of the committed topology (column-major, 1-based); empty = unknown
+  PooledVec<int32_t> rowOf;              // exportValid: row of each vertex's own edge in committedEdge
   bool exportChecked = false, exportValid = false;   // committedEdge is (known to be) exportEdges() of the committed topology
+  bool linkOrdered = false;              // the rows link() last saw came in pre-order (a vertex's own row before its children's)
+  bool edgePreorder = false;             // ... and so do committedEdge's
 
   bool isTip(int v) const { return v < numTips; }
   int internalIndex(int v) const { return v - numTips; }
@@ -115,7 +178,7 @@ struct HostTree {
     // NNI rollback.  Any other order falls back to the traversal in computeTips().
     tips.assign(numVerts, 0);
     for (int v = 0; v < numTips; v++) tips[v] = 1;
-    std::vector<uint8_t>& pend = linkScratch;        // child rows of each vertex not folded in yet
+    PooledVec<uint8_t>& pend = linkScratch;          // child rows of each vertex not folded in yet
     pend.assign(numVerts, 0);
     for (int v = numTips; v < numVerts; v++) pend[v] = 2;
     bool ordered = true;
@@ -125,7 +188,7 @@ struct HostTree {
       tips[p] += tips[c];
       pend[p]--;
     }
-    tipsValid = ordered;
+    tipsValid = linkOrdered = ordered;
     return true;
   }
 
@@ -145,6 +208,7 @@ struct HostTree {
     rng.seed(0);
     if (!link(edge, nEdgeRows)) return false;
     committedEdge.assign(edge, edge + 2 * (size_t)nEdgeRows);
+    edgePreorder = linkOrdered;
     exportChecked = exportValid = false; pendingNni = false; nniLog.clear();
     return checkRooted();
   }
@@ -171,10 +235,33 @@ struct HostTree {
     return true;
   }
 
-  // AugTree::AssociateTransProbMatrices + BindMatrix (AugTree.cpp:30-57)
+  // AugTree::AssociateTransProbMatrices + BindMatrix (AugTree.cpp:30-57): every flag false, then for each cluster MRCA
+  // that is an internal vertex, all its descendants' parent branches are "within".
   template <class T>
   void associate(const T* mrcas, int n) {
     std::fill(within.begin(), within.end(), 0);
+    const int nRows = numVerts - 1;
+    // vertices the per-cluster traversal would visit: when the clusters cover little of the tree (a caterpillar cut
+    // into one clade and singletons) it is the cheaper of the two — it pays ~5x more per vertex than the pass per row
+    long covered = tipsValid ? 0 : nRows;
+    if (tipsValid)
+      for (int i = 0; i < n; i++) { const long m = (long)mrcas[i]; if (m > numTips && m <= numVerts) covered += 2L * tips[m - 1] - 2; }
+    if (edgePreorder && !pendingNni && nniLog.empty() && committedEdge.size() == 2 * (size_t)nRows && 5 * covered >= nRows) {
+      // The committed edge matrix IS the topology (no swap since it was linked, exported or restored), and lists every vertex's own row before the rows of its children
+      // (what BuildEdgeMatrix emits and R hands back): one pass down the rows — a child is within when its parent is a
+      // cluster MRCA or is within itself — instead of a traversal per cluster (100,000 tips: 1.5 -> 0.3 ms).  mat is
+      // all zero between plans and serves as the MRCA mark.
+      for (int i = 0; i < n; i++) { const long m = (long)mrcas[i]; if (m > numTips && m <= numVerts) mat[m - 1] = 1; }
+      const int32_t* pe = committedEdge.data();
+      const int32_t* ce = pe + nRows;
+      for (int k = 0; k < nRows; k++) { const int p = pe[k] - 1; within[ce[k] - 1] = within[p] | mat[p]; }
+      for (int i = 0; i < n; i++) { const long m = (long)mrcas[i]; if (m > numTips && m <= numVerts) mat[m - 1] = 0; }
+      return;
+    }
+    associateByTraversal(mrcas, n);
+  }
+  template <class T>
+  void associateByTraversal(const T* mrcas, int n) {
     std::vector<int> stack;
     for (int i = 0; i < n; i++) {
       long m = (long)mrcas[i];
@@ -204,6 +291,7 @@ struct HostTree {
       indexRows();
       exportChecked = exportValid = true;
     }
+    edgePreorder = true;                   // either way committedEdge is now this tree's own pre-order export
     pendingNni = false; pendingRoot = -1; nniLog.clear();
   }
   void indexRows() {
@@ -272,6 +360,7 @@ struct HostTree {
     pendingNni = false; pendingRoot = -1; nniLog.clear();
     if (!link(edge, nEdgeRows) || !checkRooted()) return false;
     committedEdge.assign(edge, edge + n2);
+    edgePreorder = linkOrdered;
     exportChecked = exportValid = false;
     return true;
   }
@@ -385,9 +474,9 @@ struct HostTree {
   // clades hanging off them, which are recomputed whenever their stored ancestor is.  Updates cur/touched/solved
   // the way ComputeSolutions does (IntermediateNode.cpp:28-34).
   struct Plan {
-    std::vector<Task> tasks;
-    std::vector<Token> tokens;
-    std::vector<int32_t> tipList;                // tips read by the fused programs, task by task
+    PooledVec<Task> tasks;
+    PooledVec<Token> tokens;
+    PooledVec<int32_t> tipList;                  // tips read by the fused programs, task by task
     std::vector<int> levelStart;                 // task range of every LAUNCH UNIT: [materialised clades], the rounds, then one
                                                  // unit per chain level (k_walk takes those together)
     std::vector<int> segStart;                   // task range of every segment (group) of the non-chain units, in task order
@@ -399,8 +488,8 @@ struct HostTree {
     int chainLevels = 0;                         // trailing single-task levels that k_walk evaluates (0 or >= CHAIN_MIN)
     int materialised = 0;                        // fused-size clades evaluated as stored tasks for that chain (level 0 of the plan)
     bool uses[2] = {false, false};               // slots this plan writes
-    std::vector<int> pre, level, cnt, fill;      // scratch
-    std::vector<int> grp, gRound, gCost, gHead, gNext, gTail;   // scratch of the path grouping
+    PooledVec<int> pre, level, cnt, fill;        // scratch
+    PooledVec<int> grp, gRound, gCost, gHead, gNext, gTail;   // scratch of the path grouping
   };
 
   // mutate = false: introspection replay — tokens address the CURRENT slots and no state changes
@@ -523,7 +612,7 @@ struct HostTree {
     p.uses[0] = p.uses[1] = false;
     if (solved[root()]) { p.levelStart.push_back(0); p.segStart.push_back(0); p.unitSeg.push_back(0); return; }
     computeTips();
-    std::vector<int>& pre = p.pre;
+    PooledVec<int>& pre = p.pre;
     pre.clear();
     if (p.tokens.capacity() == 0) {          // first (full) plan of a handle: no growth by doubling through 100,000s of entries
       p.tokens.reserve((size_t)numTips + numTips / 4); p.tipList.reserve(numTips); pre.reserve(numTips);
@@ -534,7 +623,7 @@ struct HostTree {
       pre.push_back(v);
       for (int i = 0; i < 2; i++) { int c = kids[2 * v + i]; if (!isTip(c) && !fused(c) && !solved[c]) stack.push_back(c); }
     }
-    std::vector<int>& level = p.level;     // height above the clean frontier; clean, fused vertices and tips = 0
+    PooledVec<int>& level = p.level;       // height above the clean frontier; clean, fused vertices and tips = 0
     if ((int)level.size() != numVerts) level.assign(numVerts, 0);   // all zero between calls (reset below for the dirty set)
     int maxLevel = 0;
     for (size_t i = pre.size(); i-- > 0;) {   // reverse pre-order visits children before parents
@@ -558,9 +647,9 @@ struct HostTree {
     p.materialised = (int)matList.size();
 
     // ---- the vertices below the chain, grouped into paths and rounds
-    std::vector<int>& grp = p.grp;           // group of each dirty stored vertex below the chain
+    PooledVec<int>& grp = p.grp;             // group of each dirty stored vertex below the chain
     if ((int)grp.size() != numVerts) grp.assign(numVerts, -1);
-    std::vector<int>&gRound = p.gRound, &gCost = p.gCost, &gHead = p.gHead, &gNext = p.gNext, &gTail = p.gTail;
+    PooledVec<int>&gRound = p.gRound, &gCost = p.gCost, &gHead = p.gHead, &gNext = p.gNext, &gTail = p.gTail;
     gRound.clear(); gCost.clear(); gHead.clear(); gTail.clear();
     if ((int)gNext.size() != numVerts) gNext.assign(numVerts, -1);   // members of a group: linked list, bottom-up
     int nRounds = 0;
@@ -603,11 +692,11 @@ struct HostTree {
     for (int c : matList) { p.segStart.push_back((int)order.size()); order.push_back(c); }
     if (!matList.empty()) { p.levelStart.push_back(0); p.unitSeg.push_back((int)p.segStart.size()); }
     {
-      std::vector<int>& cnt = p.cnt;          // groups per round, then their order
+      PooledVec<int>& cnt = p.cnt;            // groups per round, then their order
       cnt.assign(nRounds + 1, 0);
       for (int g = 0; g < nGroups; g++) cnt[gRound[g] + 1]++;
       for (int r = 0; r < nRounds; r++) cnt[r + 1] += cnt[r];
-      std::vector<int>& byRound = p.fill;
+      PooledVec<int>& byRound = p.fill;
       byRound.assign(nGroups, 0);
       std::vector<int> pos(cnt.begin(), cnt.end() - 1);
       for (int g = 0; g < nGroups; g++) byRound[pos[gRound[g]]++] = g;

@@ -19,7 +19,7 @@ def fuzzer(tmp_path_factory):
     if gxx is None:
         pytest.skip("no g++")
     exe = str(tmp_path_factory.mktemp("hostfuzz") / "host_fuzz")
-    res = subprocess.run([gxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+    res = subprocess.run([gxx, "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                           "-o", exe, SRC], capture_output=True, text=True)
     if res.returncode != 0 and "sanitize" in res.stderr and "cannot find" in res.stderr:
         pytest.skip("sanitizer runtimes are not installed")
@@ -27,11 +27,13 @@ def fuzzer(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("seed", [1, 2])
-def test_host_state_machine_under_sanitizers(fuzzer, seed):
-    res = subprocess.run([fuzzer, "--fuzz", "400", str(seed)], capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("seed,threads", [(1, 1), (2, 3)])
+def test_host_state_machine_under_sanitizers(fuzzer, seed, threads):
+    """threads > 1: several state machines at once on one recycled-storage pool (PooledVec, host_tree.hpp), as the shards
+    of a multi-device handle are created and destroyed on their worker threads."""
+    res = subprocess.run([fuzzer, "--fuzz", "250", str(seed), str(threads)], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert res.stdout.startswith("fuzz ok"), res.stdout + res.stderr
+    assert res.stdout.count("fuzz ok") == threads, res.stdout + res.stderr
 
 
 def test_host_timings_run(tmp_path):
@@ -40,7 +42,7 @@ def test_host_timings_run(tmp_path):
     if gxx is None:
         pytest.skip("no g++")
     exe = str(tmp_path / "host_bench")
-    subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, SRC], check=True)
+    subprocess.run([gxx, "-O2", "-std=c++17", "-pthread", "-o", exe, SRC], check=True)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "config5 100,000 tips, caterpillar" in res.stdout

@@ -1,7 +1,7 @@
 // host_bench.cpp — the engine's HOST side alone (csrc/host_tree.hpp: no CUDA), timed and fuzzed on a CPU box.
 //
 //   g++ -O2 -std=c++17 -o /tmp/host_bench tools/host_bench.cpp && /tmp/host_bench            (timings)
-//   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -o /tmp/host_fuzz tools/host_bench.cpp && /tmp/host_fuzz --fuzz 2000
+//   g++ -O1 -g -std=c++17 -pthread -fsanitize=address,undefined -o /tmp/host_fuzz tools/host_bench.cpp && /tmp/host_fuzz --fuzz 2000 1 4
 //
 // Timings: what logLikCpp spends on the host before the first pruning launch can be queued — link + validate the tree
 // (HostTree::build), cluster flags (associate), the plan of a full evaluation (plan) — and what a proposal costs
@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <thread>
 
 #include "../dmphyclus_b200/csrc/host_tree.hpp"
 
@@ -123,6 +124,22 @@ static void checkPlan(const HostTree& ht, const HostTree::Plan& p, const std::ve
   for (int v = N; v < ht.numVerts; v++) CHECK(ht.mat[v] == 0, "materialisation mark left behind");
 }
 
+// the one-pass flagging over the committed edge matrix against the per-cluster traversal, on an arbitrary MRCA list
+// (nested clades, tips and out-of-range ids included: both must treat them alike)
+static void checkAssociate(HostTree& ht, std::mt19937_64& rng) {
+  const std::vector<uint8_t> keep(ht.within.begin(), ht.within.end());
+  std::vector<double> ml;
+  const int k = 1 + (int)(rng() % 9);
+  for (int i = 0; i < k; i++) ml.push_back((double)(rng() % (ht.numVerts + 3)));
+  ht.associate(ml.data(), (int)ml.size());
+  const std::vector<uint8_t> fast(ht.within.begin(), ht.within.end());
+  std::fill(ht.within.begin(), ht.within.end(), 0);
+  ht.associateByTraversal(ml.data(), (int)ml.size());
+  CHECK(std::equal(fast.begin(), fast.end(), ht.within.begin()), "one-pass cluster flags differ from the traversal's");
+  for (int v = ht.numTips; v < ht.numVerts; v++) CHECK(ht.mat[v] == 0, "MRCA marks left behind");
+  std::copy(keep.begin(), keep.end(), ht.within.begin());
+}
+
 static void checkTips(HostTree& ht) {
   if (!ht.tipsValid) return;
   std::vector<int32_t> have = ht.tips;
@@ -131,15 +148,49 @@ static void checkTips(HostTree& ht) {
   CHECK(have == ht.tips, "incremental tip counts differ from a fresh traversal");
 }
 
+// PooledVec: storage is recycled, contents never are; copies are deep; small vectors stay out of the pool
+static void checkPool() {
+  const size_t big = 300000;
+  const int* block = nullptr;
+  {
+    PooledVec<int> a;
+    a.assign(big, 7);
+    block = a.data();
+    PooledVec<int> b(a), c;
+    c = a;
+    CHECK(b.data() != a.data() && c.data() != a.data() && b == a && c == a, "copies are deep");
+    b[5] = 9;
+    CHECK(a[5] == 7, "copies are deep");
+  }
+  {
+    PooledVec<int> d;
+    CHECK(d.empty() && d.capacity() == 0, "a fresh vector holds nothing until it grows");
+    d.assign(big, 3);                            // (single-threaded here: one of the three parked blocks comes back)
+    CHECK(d.capacity() >= big && d.size() == big, "assign");
+    for (size_t i = 0; i < big; i += 997) CHECK(d[i] == 3, "recycled storage must not leak old contents");
+    PooledVec<int> e;
+    e.resize(10);
+    e[3] = 1;
+    e.resize(big);                               // growth keeps what was there, like any vector
+    CHECK(e[3] == 1 && e[big - 1] == 0, "resize keeps the contents and zero-fills the rest");
+    std::vector<int> plain(5, 2);
+    e = plain;
+    CHECK(e.size() == 5 && e[4] == 2, "assignment from a plain vector");
+  }
+  (void)block;
+}
+
 static int fuzz(int rounds, uint64_t seed) {
   std::mt19937_64 rng(seed);
+  checkPool();
   long plans = 0, moves = 0;
   for (int r = 0; r < rounds; r++) {
-    const int n = 2 + (int)(rng() % (r % 16 == 0 ? 3000 : 120));
+    // (every 50th tree is large enough for its vectors to go through the recycled-storage pool)
+    const int n = r % 50 == 7 ? 20000 + (int)(rng() % 20000) : 2 + (int)(rng() % (r % 16 == 0 ? 3000 : 120));
     const int shape = (int)(rng() % 3);
     std::vector<int32_t> edge = makeTree(n, rng, shape);
     const int rows = 2 * n - 2;
-    if (rng() % 4 == 0) {                       // rows in another order: the traversal fallbacks
+    if (n <= 3000 && rng() % 4 == 0) {          // rows in another order: the traversal fallbacks
       std::vector<int> perm(rows);
       for (int i = 0; i < rows; i++) perm[i] = i;
       std::shuffle(perm.begin(), perm.end(), rng);
@@ -158,8 +209,9 @@ static int fuzz(int rounds, uint64_t seed) {
     ht.computeTips();
     std::vector<double> mr = makeClusters(ht, 1 + (int)(rng() % 12));
     ht.associate(mr.data(), (int)mr.size());
+    checkAssociate(ht, rng);
     HostTree::Plan p;
-    std::vector<uint8_t> before = ht.solved;
+    std::vector<uint8_t> before(ht.solved.begin(), ht.solved.end());
     ht.plan(p); plans++;
     checkPlan(ht, p, before);
     ht.negateAllUpdateFlags();
@@ -226,6 +278,7 @@ static int fuzz(int rounds, uint64_t seed) {
       const bool accept = rng() % 3 == 0;
       if (accept) {
         if (nni) committed = proposed;
+        if (rng() % 2) checkAssociate(ht, rng);      // (an accepted NNI is still pending here: the traversal path)
         continue;
       }
       // reject: RestorePreviousConfig
@@ -244,6 +297,7 @@ static int fuzz(int rounds, uint64_t seed) {
       for (int v = n; v < ht.numVerts; v++) if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
       CHECK(ht.cur == curBefore, "slot bits after the rollback");
       if (sm) ht.within = withinBefore;
+      checkAssociate(ht, rng);
       // (the reference leaves _isSolved as the proposal set it: everything planned is solved)
     }
   }
@@ -276,7 +330,17 @@ static int fuzz(int rounds, uint64_t seed) {
 }
 
 int main(int argc, char** argv) {
-  if (argc > 1 && !std::strcmp(argv[1], "--fuzz")) return fuzz(argc > 2 ? std::atoi(argv[2]) : 500, argc > 3 ? std::strtoull(argv[3], nullptr, 10) : 1);
+  if (argc > 1 && !std::strcmp(argv[1], "--fuzz")) {
+    // --fuzz ROUNDS [SEED [THREADS]]: several threads at once share the recycled-storage pool (PooledVec), as the shards
+    // of a multi-device handle do when they are created and destroyed on their worker threads
+    const int rounds = argc > 2 ? std::atoi(argv[2]) : 500, nThreads = argc > 4 ? std::atoi(argv[4]) : 1;
+    const uint64_t seed = argc > 3 ? std::strtoull(argv[3], nullptr, 10) : 1;
+    std::vector<std::thread> th;
+    for (int i = 1; i < nThreads; i++) th.emplace_back([=] { fuzz(rounds, seed + 1000u * i); });
+    const int rc = fuzz(rounds, seed);
+    for (auto& t : th) t.join();
+    return rc;
+  }
   struct Shape { const char* name; int n, k, shape; } shapes[] = {
       {"config2  1,000 tips, 20 clusters", 1000, 20, 0},     {"config4  5,000 tips, 50 clusters", 5000, 50, 0},
       {"config3 10,000 tips, 100 clusters", 10000, 100, 0},  {"config5 100,000 tips, random", 100000, 200, 0},
