@@ -119,6 +119,14 @@ def algorithmic_bytes(n, s, r):
     return s * r * ((n - 2) * 32 + (n - 1) * 36) + s * n
 
 
+def frozen(a):
+    """A read-only copy: the binding converts a read-only array it is handed again (matrix lists, limProbs — R hands the
+    same objects to every call) once instead of on every call (engine.Engine._mp)."""
+    a = np.array(a)
+    a.setflags(write=False)
+    return a
+
+
 def make_problem(args, world):
     from dmphyclus_b200.workloads import CONFIGS, Problem, load_packaged
     n, s, k, r = CONFIGS[args.workload]
@@ -309,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     p, (n, s, k, r) = make_problem(args, world)
     S_total = p.S
-    W, B = p.W[p.w_idx - 1], p.B[p.b_idx - 1]
+    W, B, pi = frozen(p.W[p.w_idx - 1]), frozen(p.B[p.b_idx - 1]), frozen(p.pi)
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -342,7 +350,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---------------------------------------------------------------- device-resident leg
-    res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+    res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
     h, ll0 = res["solutionPointer"], res["logLik"]
     single_ll = None
     if world > 1 and rank == 0:
@@ -350,14 +358,14 @@ def run_ours(args, rank, world, local_rank):
         # rank's device (one slot of partials: 33 GB for config 3), outside every timed region
         one = Engine(device=local_rank, fuse_tips=args.fuse)
         full = one.getConvertedAlignment(list(synth.STATES), p.chars)
-        r1 = one.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, full, p.n, S_total, p.w_idx, p.b_idx)
+        r1 = one.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, full, p.n, S_total, p.w_idx, p.b_idx)
         single_ll = r1["logLik"]
         one.finalDeallocate(r1["solutionPointer"])
         del full
         assert single_ll == ll0, ("sharded log-likelihood differs from the single-GPU one", ll0, single_ll)
     sampler.mark = "warm"
     for _ in range(max(3, args.warmup)):
-        ll = eng.recomputeAll(h, W, B, p.pi)
+        ll = eng.recomputeAll(h, W, B, pi)
     assert ll == ll0, (ll, ll0)          # a full re-evaluation is deterministic
     st0 = local.stats(h)
     prune_ms = 0.0
@@ -365,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.mark = "timed"
     local.timer_begin(h)
     for _ in range(args.steps):                     # the timed region: nothing but the K evaluations
-        eng.recomputeAll(h, W, B, p.pi)
+        eng.recomputeAll(h, W, B, pi)
     ms = local.timer_end(h)
     # k_prune's device time over exactly these K evaluations: the engine brackets every evaluation's pruning launches with
     # CUDA events on its own stream and adds the elapsed times up as the results come in (no extra synchronisation)
@@ -381,7 +389,7 @@ def run_ours(args, rank, world, local_rank):
     probe_steps = min(args.steps, 10)
     probe_ms = 0.0
     for _ in range(probe_steps):
-        eng.recomputeAll(h, W, B, p.pi)
+        eng.recomputeAll(h, W, B, pi)
         sti = local.stats(h)
         tl = local.root_timeline(h)
         if tl_keys is None:
@@ -438,14 +446,14 @@ def run_ours(args, rank, world, local_rank):
     # ---------------------------------------------------------------- end-to-end leg (host buffers in, scalar out)
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     for _ in range(3):
-        res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
         eng.finalDeallocate(res["solutionPointer"])
     barrier()
     sampler.mark = "e2e"
     t0 = time.perf_counter()
     e2e_parts = np.zeros(4)
     for _ in range(e2e_steps):
-        res = eng.logLikCpp(p.edge, p.mrcas, p.pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
         sti = local.stats(res["solutionPointer"])
         e2e_parts += (sti["create_setup_us"] * 1e-3, sti["create_upload_ms"], sti["last_eval_ms"], sti["last_host_total_us"] * 1e-3)
         eng.finalDeallocate(res["solutionPointer"])
@@ -548,22 +556,22 @@ def config2_leg(args, eng):
     pinned = torch.empty(masks.shape, dtype=torch.uint8, pin_memory=True)
     pinned.numpy()[...] = masks
     alq = pinned.numpy()
-    W, B = q.W[4], q.B[4]
-    res = eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)
+    W, B, pi = frozen(q.W[4]), frozen(q.B[4]), frozen(q.pi)
+    res = eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)
     h = res["solutionPointer"]
     for _ in range(5):
-        eng.recomputeAll(h, W, B, q.pi)
+        eng.recomputeAll(h, W, B, pi)
     steps = 50
     eng.timer_begin(h)
     for _ in range(steps):
-        eng.recomputeAll(h, W, B, q.pi)
+        eng.recomputeAll(h, W, B, pi)
     ms = eng.timer_end(h) / steps
     eng.finalDeallocate(h)
     for _ in range(3):
-        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
     t0 = time.perf_counter()
     for _ in range(20):
-        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, q.pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
     e2e = (time.perf_counter() - t0) / 20 * 1e3
     upd = (n - 1) * s * r
     return {"workload": f"config2: {n} seqs x {s} sites, {k} clusters, {r} rate categories", "value": upd / (ms * 1e-3),
