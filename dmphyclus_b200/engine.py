@@ -155,6 +155,7 @@ class Engine:
         self._shape = {}
         self._mcache = {}
         self._ecache = {}
+        self._lcache = {}
 
     def _check(self, rc):
         if rc != 0:
@@ -199,6 +200,34 @@ class Engine:
         if isinstance(pi, np.ndarray) and not pi.flags.writeable:
             self._mcache[id(pi)] = (pi, ptr)
         return ptr
+
+    def _lp(self, m, dtype, ptype):
+        """Pointer + length of an id list (cluster MRCAs) as a contiguous `dtype` array.  The MCMC driver hands the same
+        Python list to every call until a split / merge is accepted (paraValues$clusterNodeIndices): a list seen before is
+        converted once — recognised by identity AND by comparing it with a copy taken then (lists are mutable)."""
+        if type(m) is list:
+            ent = self._lcache.get((id(m), dtype))
+            if ent is not None and ent[0] is m and ent[1] == m:
+                return ent[2], ent[3]
+        arr = np.ascontiguousarray(np.asarray(m).ravel(), dtype=dtype)
+        ptr = _p(arr, ptype)
+        if type(m) is list:
+            if len(self._lcache) >= 64:
+                self._lcache.clear()
+            self._lcache[(id(m), dtype)] = (m, list(m), ptr, len(arr), arr)
+        return ptr, len(arr)
+
+    @staticmethod
+    def _edge_out(n_tips):
+        """Output buffer of an NNI entry point: (what to pass as int32*, the [E][2] view of it the result owns).  Small
+        matrices come as a ctypes array (no pointer object to build: 0.5 us against 2.7), large ones as numpy memory (not
+        zero-filled first)."""
+        n = 2 * (2 * n_tips - 2)
+        if n <= 16384:
+            buf = (C.c_int32 * n)()
+            return buf, np.frombuffer(buf, np.int32).reshape(2, -1).T
+        edge = np.empty(n, np.int32)
+        return _p(edge, _i32_p), edge.reshape(2, -1).T
 
     # ------------------------------------------------------------------ the 11 entry points
     def getConvertedAlignment(self, equivVector, alignmentAlphaMat) -> np.ndarray:
@@ -252,23 +281,21 @@ class Engine:
     def withinClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, MRCAofClusForNNI, numMovesNNI,
                             numOpenMP, limProbs):
         w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
-        n = self._shape[ptr][0]
-        edge = np.empty(2 * (2 * n - 2), np.int32)
+        buf, edge = self._edge_out(self._shape[ptr][0])
         ll = C.c_double()
         self._check(self.lib.dmpc_within_clus_nni_loglik(ptr, w, b, int(MRCAofClusForNNI),
-                                                         int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
-        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T}      # [E][2] view of the column-major buffer (owned by the result)
+                                                         int(numMovesNNI), pi, C.byref(ll), buf))
+        return {"logLik": ll.value, "edge": edge}      # [E][2] view of the column-major buffer (owned by the result)
 
     def betweenClusNNIlogLik(self, ptr, withinTransProbs, betweenTransProbs, clusterMRCAs, numMovesNNI,
                              numOpenMP, limProbs):
         w, b, pi = self._mp(withinTransProbs), self._mp(betweenTransProbs), self._pp(limProbs)
-        m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
-        n = self._shape[ptr][0]
-        edge = np.empty(2 * (2 * n - 2), np.int32)
+        m, n_m = self._lp(clusterMRCAs, np.float64, _dbl_p)
+        buf, edge = self._edge_out(self._shape[ptr][0])
         ll = C.c_double()
-        self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, w, b, _p(m, _dbl_p), len(m),
-                                                          int(numMovesNNI), pi, C.byref(ll), _p(edge, _i32_p)))
-        return {"logLik": ll.value, "edge": edge.reshape(2, -1).T}      # [E][2] view of the column-major buffer (owned by the result)
+        self._check(self.lib.dmpc_between_clus_nni_loglik(ptr, w, b, m, n_m,
+                                                          int(numMovesNNI), pi, C.byref(ll), buf))
+        return {"logLik": ll.value, "edge": edge}      # [E][2] view of the column-major buffer (owned by the result)
 
     def clusSplitMergeLogLik(self, ptr, withinTransProbs, betweenTransProbs, clusMRCAsToSplitOrMerge, numOpenMP,
                              limProbs) -> float:
@@ -282,10 +309,10 @@ class Engine:
     def RestorePreviousConfig(self, ptr, edgeMat, withinMatListIndex, betweenMatListIndex, NNImove, clusterMRCAs,
                               splitMergeMove) -> None:
         e, n_rows = self._ep(edgeMat)
-        m = np.ascontiguousarray(np.asarray(clusterMRCAs).ravel(), dtype=np.int32)
+        m, n_m = self._lp(clusterMRCAs, np.int32, _i32_p)
         self._check(self.lib.dmpc_restore_previous_config(ptr, e, n_rows, int(withinMatListIndex),
-                                                          int(betweenMatListIndex), int(bool(NNImove)), _p(m, _i32_p),
-                                                          len(m), int(bool(splitMergeMove))))
+                                                          int(betweenMatListIndex), int(bool(NNImove)), m,
+                                                          n_m, int(bool(splitMergeMove))))
 
     def finalDeallocate(self, ptr) -> None:
         self._shape.pop(ptr, None)
