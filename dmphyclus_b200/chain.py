@@ -36,14 +36,24 @@ def clusIndLogPrior(clusInd, alpha, k=None) -> float:
 
 
 def _log_prior_of_counts(counts, n, alpha, k=None) -> float:
-    """clusIndLogPrior from table(clusInd) (counts in label order) and length(clusInd)."""
+    """clusIndLogPrior from table(clusInd) (counts in label order) and length(clusInd):
+    `lgamma(n+1) - sum(lgamma(counts+1)) + .logBigB(alpha+counts) - .logBigB(alpha)`.  Every sum is the builtin `sum` over
+    the terms in cluster order, so the value does not depend on how the terms are produced (lists here: this runs five
+    times per MCMC iteration over all clusters)."""
+    lg = math.lgamma
     counts = [float(c) for c in counts]
     if k is None:
         k = len(counts)
-    alpha_vec = [float(alpha)] * k if np.ndim(alpha) == 0 else [float(a) for a in alpha]
     if len(counts) < k:
         counts = counts + [0.0] * (k - len(counts))
-    return (math.lgamma(n + 1) - sum(math.lgamma(c + 1) for c in counts)
+    if np.ndim(alpha) == 0:
+        a = float(alpha)
+        post = [a + c for c in counts]
+        return (lg(n + 1) - sum([lg(c + 1) for c in counts])
+                + (sum([lg(v) for v in post]) - lg(sum(post)))
+                - (sum([lg(a)] * k) - lg(sum([a] * k))))
+    alpha_vec = [float(a) for a in alpha]
+    return (lg(n + 1) - sum([lg(c + 1) for c in counts])
             + _log_big_b([a + c for a, c in zip(alpha_vec, counts)]) - _log_big_b(alpha_vec))
 
 
@@ -231,14 +241,33 @@ def _update_cluster_phylos(backend, cv, st, rng):
             cv.extPointer, w, b, mrca, st.numMovesNNIwithin, st.numLikThreads, st.limProbs))
 
 
+def _parents(phy: Phylo, mrcas) -> np.ndarray:
+    return phy.parent[np.asarray(mrcas, dtype=np.int64)]          # one vector look-up instead of one access per cluster
+
+
 def _pairs_and_splits(phy: Phylo, mrcas, counts_gt1):
     """Sibling cluster pairs (mergeable) grouped by parent in increasing parent id, as
-    split(clusterNodeIndices, f = parent) orders its factor levels (DMphyClusSource.R:157-165)."""
-    groups = {}
-    for m in mrcas:
-        groups.setdefault(int(phy.parent[m]), []).append(m)
-    pairs = [groups[p] for p in sorted(groups) if len(groups[p]) > 1]
+    split(clusterNodeIndices, f = parent) orders its factor levels (DMphyClusSource.R:157-165); within a group the
+    clusters keep their list order."""
+    par = _parents(phy, mrcas)
+    order = np.argsort(par, kind="stable")
+    sp = par[order]
+    same = np.nonzero(sp[1:] == sp[:-1])[0]                        # positions whose successor has the same parent
+    pairs, order = [], order.tolist()
+    i = 0
+    same = same.tolist()
+    while i < len(same):
+        j = i
+        while j + 1 < len(same) and same[j + 1] == same[j] + 1:    # (more than two clusters under one parent: not in a binary tree)
+            j += 1
+        pairs.append([mrcas[q] for q in order[same[i]:same[j] + 2]])
+        i = j + 1
     return pairs, counts_gt1
+
+
+def _num_pairs(phy: Phylo, mrcas) -> int:
+    """How many parents have more than one cluster MRCA hanging off them."""
+    return int(np.count_nonzero(np.unique(_parents(phy, mrcas), return_counts=True)[1] > 1))
 
 
 def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
@@ -298,10 +327,7 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
     new_lpp = (new_ll + _log_prior_of_counts(list(new_counts.values()), len(cv.clusInd), cv.alpha)
                + _dgamma_log(cv.alpha - st.alphaMin, st.shapeForAlpha, st.scaleForAlpha)
                + _dpois_log(max(new_counts), st.poisRateNumClus))
-    groups = {}
-    for m in new_mrcas:
-        groups.setdefault(int(phy.parent[m]), []).append(m)
-    num_pairs_new = sum(1 for g in groups.values() if len(g) > 1)
+    num_pairs_new = _num_pairs(phy, new_mrcas)
     num_splits_new = sum(1 for c in new_counts.values() if c > 1)
     ratio = num_moves / (num_pairs_new + num_splits_new)
     mh = ratio * _exp(new_lpp - cv.logPostProb)

@@ -199,3 +199,37 @@ def test_plan_builder_invariants(shape, fuse):
                 assert o[6] == 0 or (o[6] >= 4 and o[6] <= o[2])
     if fuse > 1 and shape == "random":
         assert chains > 0 and mats > 0
+
+
+def test_driver_helpers_against_their_plain_forms():
+    """The vectorised helpers of the driver mirror against the term-by-term forms they replace: sibling cluster pairs as
+    split(clusterNodeIndices, f = parent) gives them (/root/reference/R/DMphyClusSource.R:157-165), and the
+    Dirichlet-multinomial prior from the cluster counts (R/DMphyClusInterface.R:147-162)."""
+    from scipy.special import gammaln
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(8, 400))
+        edge = synth.random_tree(n, rng, ["random", "balanced", "caterpillar"][trial % 3])
+        phy = Phylo(edge, n)
+        k = int(rng.integers(1, 30))
+        mrcas = [int(x) for x in rng.choice(np.arange(1, 2 * n), size=min(k, 2 * n - 2), replace=False) if x != n + 1]
+        if not mrcas:
+            continue
+        groups = {}
+        for m in mrcas:
+            groups.setdefault(int(phy.parent[m]), []).append(m)
+        want = [groups[p] for p in sorted(groups) if len(groups[p]) > 1]
+        assert chain._pairs_and_splits(phy, mrcas, None)[0] == want
+        assert chain._num_pairs(phy, mrcas) == len(want)
+        counts = rng.integers(1, 50, size=len(mrcas)).astype(float)
+        alpha = float(rng.uniform(10.0, 120.0))
+        nn = int(counts.sum())
+        plain = (gammaln(nn + 1) - gammaln(counts + 1).sum() + (gammaln(alpha + counts).sum() - gammaln((alpha + counts).sum()))
+                 - (len(counts) * gammaln(alpha) - gammaln(len(counts) * alpha)))
+        got = chain._log_prior_of_counts(list(counts), nn, alpha)
+        assert abs(got - plain) <= 1e-10 * max(1.0, abs(plain))
+    # three clusters under one parent cannot happen in a binary tree, but the grouping must not lose one if it did
+    class Star:
+        parent = np.array([0, 9, 9, 9, 8, 8, 7, 0, 7, 7])
+    assert chain._pairs_and_splits(Star, [4, 1, 2, 5, 3, 6], None)[0] == [[4, 5], [1, 2, 3]]
+    assert chain._num_pairs(Star, [4, 1, 2, 5, 3, 6]) == 2
