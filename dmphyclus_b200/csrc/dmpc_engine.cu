@@ -2151,6 +2151,7 @@ int dmpc_get_partial(dmpc_tree* t, int vertex, double* sol, float* expo) {
 int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* child1, int32_t* within) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (!parent || !child0 || !child1 || !within) return fail(DMPC_ERR_ARG, "null pointer");
   if (t->grp) return dmpc_get_topology(t->grp->shards[0], parent, child0, child1, within);
   for (int v = 0; v < t->ht.numVerts; v++) {
     parent[v] = t->ht.parent[v];
@@ -2163,6 +2164,7 @@ int dmpc_get_topology(dmpc_tree* t, int32_t* parent, int32_t* child0, int32_t* c
 int dmpc_get_site_logliks(dmpc_tree* t, double* out) {
   int rc;
   if ((rc = checkHandle(t))) return rc;
+  if (!out) return fail(DMPC_ERR_ARG, "null pointer");
   if (t->grp) {
     for (size_t i = 0; i < t->grp->shards.size(); i++)
       if ((rc = dmpc_get_site_logliks(t->grp->shards[i], out + t->grp->begin[i]))) return rc;

@@ -11,13 +11,17 @@ data-path collective.  The root reduction is where ranks meet:
     the ranks all-gather (has-rescaled-site flag, chunk sums) in ONE collective; only when a rank before the last
     reports a rescaled site does the chain hop through those ranks in site order (one R-float broadcast per hop)
     before a second all-gather;
-  * each rank then reduces its sites to per-256-site chunk sums; the chunk sums are all-gathered and added in a
-    fixed order (`dmpc_reduce_chunks`), so the total is bit-identical for 1, 2, 4 or 8 ranks — which is what
+  * each rank then reduces its sites to per-64-site chunk sums (`CHUNK`); the chunk sums are all-gathered and added in
+    a fixed order (`dmpc_reduce_chunks`), so the total is bit-identical for 1, 2, 4 or 8 ranks — which is what
     keeps MCMC trajectories identical across GPU counts.
+
+With NVLink peer mailboxes attached (`Engine.comm_setup`, the normal case on a multi-GPU box) none of this happens on the
+host: the reduction kernels exchange chunk sums and certificate records themselves and `_reduce` only reads the result
+(`shard_fast_result`); the protocol above is the fallback, and what the CPU tests drive under gloo.
 
 All ranks run the same driver with the same RNG stream and make the same entry-point calls (SPMD); every
 rank gets the same log-likelihood back.  `torch.distributed` is plumbing only: payloads are R floats and
-S/256 doubles per evaluation.
+S/64 doubles per evaluation.
 """
 from __future__ import annotations
 

@@ -200,10 +200,10 @@ int dmpc_get_site_logliks(dmpc_tree* t, double* out);
 
 /* Multi-GPU site sharding (one handle per rank, contiguous site blocks).  With quirk_carry and R > 1 the
  * fp32 exponent chain crosses shard boundaries: a rank's chain starts from the previous rank's carry.
- *   dmpc_shard_begin:  runs the dirty-node pruning and the per-site gather for the pending evaluation of the
- *                      LAST entry-point call made with deferred reduction (see dmpc_set_deferred);
+ *   (an entry point called on a deferred handle — dmpc_options.deferred / dmpc_set_deferred — prunes the dirty
+ *   vertices and gathers the per-site quantities, and stops there unless peer mailboxes are attached;)
  *   dmpc_shard_chain:  runs this shard's chain from carryIn[R] (fp32) and returns carryOut[R];
- *   dmpc_shard_finish: returns the deterministic partial sums of this shard's sites in fixed 256-site chunks
+ *   dmpc_shard_finish: returns the deterministic partial sums of this shard's sites in fixed 64-site chunks
  *                      (chunkSums[nChunks]); the caller all-gathers them and adds them in chunk order, so the
  *                      total is bit-identical for any number of ranks.
  * With deferral on, the entry points above return logLik = NaN and leave the reduction to these calls. */
