@@ -288,13 +288,14 @@ def _split_join_cluster_move(backend, cv: ChainState, st: ChainSettings, rng):
         if node <= cv.n_tips:
             raise RuntimeError("split of a cluster whose stored MRCA is a tip (single-cluster start): "
                                "the reference dereferences a null child here (AugTree.cpp:332)")
-        new_nodes = phy.kids(node)
+        # Children(phylogeny, node) and the tips below each of them: the cluster IS the clade below its MRCA
+        # (DMphyClusInterface.R:228-249; every move keeps it so), hence its tips are the ones to sort by child
+        new_nodes, parts = phy.split_below(node, np.flatnonzero(cv.clusInd == clus_number) + 1)
         new_mrcas = list(cv.clusterNodeIndices)
         new_mrcas[clus_number - 1] = new_nodes[0]
         new_mrcas += new_nodes[1:]
         new_ll = backend.clusSplitMergeLogLik(cv.extPointer, w, b, [node], st.numLikThreads, st.limProbs)
         numbers = [clus_number] + list(range(len(cv.clusterNodeIndices) + 1, len(new_mrcas) + 1))
-        parts = [phy.descendants(nd) for nd in new_nodes]         # the tips that change label (shortRecursive, :112-119)
         # table(newClusInd) without building newClusInd: the split cluster's tips are exactly the tips below its MRCA's
         # children, and the labels in use are 1..K (merges relabel), so K+1 is new and the keys stay sorted
         new_counts = dict(cv.clusterCounts)

@@ -66,6 +66,31 @@ class Phylo:
             self._children = out
         return self._children
 
+    def split_below(self, node: int, tips) -> tuple[list, list]:
+        """phangorn::Children(phy, node) in edge-row order and, for each child, which of `tips` lie below it
+        (phangorn::Descendants(phy, child, "tips") restricted to `tips`, as an unordered set).  `tips` must all lie below
+        `node` — the tips of a cluster and its MRCA (R/DMphyClusSource.R:104-119) — which is checked.  Every tip climbs
+        towards `node` at once (a handful of vector operations per level of the clade), which needs no child table; small
+        trees, and views whose table exists anyway, take the plain traversal."""
+        if self._table is not None or len(self.parent) <= 8192:
+            # the child table exists already, or is cheap to build (it costs a sort of the edge rows: 0.4 ms at 10,000
+            # tips, after every accepted topology change): walk the two clades
+            kids = self.kids(node)
+            return kids, [self.descendants(k) for k in kids]
+        tips = np.asarray(tips, dtype=np.int64)
+        kids = self.edge[np.flatnonzero(self.edge[:, 0] == node), 1].tolist()
+        cur = tips.copy()
+        par = self.parent[cur]
+        for _ in range(len(self.parent)):
+            up = par != node
+            if not up.any():
+                break
+            cur = np.where(up, par, cur)
+            par = self.parent[cur]
+            if not par.all():                         # parent[root] = 0: a tip climbed past the root
+                raise ValueError(f"split_below: a tip does not lie below vertex {node}")
+        return kids, [tips[cur == k] for k in kids]
+
     def is_tip(self, v: int) -> bool:
         return v <= self.n_tips
 

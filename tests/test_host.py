@@ -233,3 +233,28 @@ def test_driver_helpers_against_their_plain_forms():
         parent = np.array([0, 9, 9, 9, 8, 8, 7, 0, 7, 7])
     assert chain._pairs_and_splits(Star, [4, 1, 2, 5, 3, 6], None)[0] == [[4, 5], [1, 2, 3]]
     assert chain._num_pairs(Star, [4, 1, 2, 5, 3, 6]) == 2
+
+
+def test_split_below_matches_children_and_descendants():
+    """Phylo.split_below (the tips of a clade sorted by the child of its root they hang under) against
+    Children + Descendants, on both of its paths: the traversal (small tree / table present) and the climb."""
+    rng = np.random.default_rng(8)
+    for n, shape in ((30, "random"), (700, "caterpillar"), (5000, "random"), (6000, "balanced")):
+        edge = synth.random_tree(n, rng, shape)
+        for trial in range(12):
+            ref = Phylo(edge, n)
+            node = int(rng.integers(n + 1, 2 * n))
+            tips = np.sort(ref.descendants(node))
+            want_kids = ref.kids(node)
+            want = [set(ref.descendants(k).tolist()) for k in want_kids]
+            phy = Phylo(edge, n)                                        # a fresh view: no table yet
+            kids, parts = phy.split_below(node, tips)
+            assert kids == want_kids and [set(p.tolist()) for p in parts] == want
+            assert sum(len(p) for p in parts) == len(tips)
+            if 2 * n > 8192:
+                assert phy._table is None                               # the climb built no table
+                with pytest.raises(ValueError):
+                    outside = np.setdiff1d(np.arange(1, n + 1), tips)
+                    if len(outside) == 0:
+                        raise ValueError("whole tree")
+                    phy.split_below(node, np.append(tips, outside[0]))  # a tip that is not below the vertex
