@@ -30,7 +30,9 @@ def test_script_bit_identical(oracle, reference, packaged, n, S, k, R, kind, sha
 
 
 @pytest.mark.parametrize("n,S,k,R,kind,iters,seed", [(6, 200, 2, 3, "evolved", 30, 1), (60, 40, 5, 3, "evolved", 15, 2),
-                                                     (700, 12, 8, 3, "iid", 6, 3)])
+                                                     (700, 12, 8, 3, "iid", 6, 3), (40, 30, 3, 1, "iid", 12, 4),
+                                                     (90, 25, 6, 2, "tiny", 10, 5), (250, 10, 4, 3, "diverged", 8, 6),
+                                                     (33, 64, 2, 2, "evolved", 20, 7)])
 def test_mcmc_trajectory_bit_identical(oracle, reference, packaged, n, S, k, R, kind, iters, seed):
     """The restated driver over both backends with one numpy stream: every sample identical, including the NNI picks
     drawn from the C++-side gsl_rng_taus stream."""
