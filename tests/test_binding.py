@@ -124,3 +124,20 @@ def test_edge_output_buffer_through_the_library(eng):
         assert np.array_equal(view, edge)                                    # synth emits pre-order rows: the export is the input
     finally:
         lib.dmpc_hp_destroy(h)
+
+
+def test_result_objects_of_the_nni_entry_points(mats, monkeypatch):
+    """The lines after the library call (building the R-style result list) — reached here by ignoring the status of a
+    NULL-handle call: `edge` is the [2N-2][2] view of the buffer that was handed to the library."""
+    w, b, pi = mats
+    eng = Engine()
+    monkeypatch.setattr(eng, "_check", lambda rc: None)
+    for n_tips in (50, 9000):
+        eng._shape[None] = (n_tips, 10, 3)
+        for res in (eng.withinClusNNIlogLik(None, w, b, n_tips + 2, 1, 1, pi),
+                    eng.betweenClusNNIlogLik(None, w, b, [n_tips + 2, n_tips + 3], 1, 1, pi)):
+            assert set(res) == {"logLik", "edge"} and isinstance(res["logLik"], float)
+            assert res["edge"].shape == (2 * n_tips - 2, 2) and res["edge"].dtype == np.int32
+            np.array(res["edge"], dtype=np.int32)            # what the driver does with it (chain._frozen_edge)
+    assert eng.RestorePreviousConfig(None, np.zeros((1, 2), np.int32), 5, 5, False, [3, 4], True) is None
+    assert isinstance(eng.clusSplitMergeLogLik(None, w, b, [7], 1, pi), float)
