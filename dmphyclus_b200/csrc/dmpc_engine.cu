@@ -1439,12 +1439,7 @@ static int rollbackTouched(dmpc_tree* t) {
     CUDA_TRY(cudaStreamSynchronize(t->stream));
   }
   int n = 0;
-  for (int v = ht.numTips; v < ht.numVerts; v++)
-    if (ht.touched[v]) {
-      ht.cur[v] ^= 1;
-      ht.touched[v] = 0;
-      t->h_curList[n++] = ((v - ht.numTips) << 1) | ht.cur[v];
-    }
+  ht.rollbackTouched([&](int v, int slot) { t->h_curList[n++] = ((v - ht.numTips) << 1) | slot; });
   t->pendingCur = n;
   return DMPC_OK;
 }
@@ -2074,8 +2069,7 @@ int dmpc_hp_restore(dmpc_hostplan* h, const int32_t* edge, int nEdgeRows, int nn
     if (!ht.restoreTopology(edge, nEdgeRows)) return fail(DMPC_ERR_ARG, ht.err);
   }
   h->nniPending = false;
-  for (int v = ht.numTips; v < ht.numVerts; v++)  // RestoreIterVecAndExp, IntermediateNode.h:26-33
-    if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
+  ht.rollbackTouched([](int, int) {});            // RestoreIterVecAndExp, IntermediateNode.h:26-33
   if (splitMergeMove) {
     if (nClusterMRCAs > 0 && !clusterMRCAs) return fail(DMPC_ERR_ARG, "null pointer");
     ht.associate(clusterMRCAs, nClusterMRCAs);

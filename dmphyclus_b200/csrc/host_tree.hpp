@@ -9,6 +9,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <iterator>
 #include <mutex>
 #include <string>
@@ -363,6 +364,25 @@ struct HostTree {
     edgePreorder = linkOrdered;
     exportChecked = exportValid = false;
     return true;
+  }
+
+  // RestoreIterVecAndExp (IntermediateNode.h:26-33) for every vertex the pending proposal touched: the vertex goes back
+  // to its other slot and its flag is cleared; f(v, slot) is told where it now lives.  A root-path proposal touches a
+  // few dozen of the internal vertices, so the flags are skipped eight at a time where none is set.
+  template <class F>
+  void rollbackTouched(F f) {
+    int v = numTips;
+    const uint8_t* tp = touched.data();
+    while (v < numVerts) {
+      if (v + 8 <= numVerts) {
+        uint64_t w;
+        std::memcpy(&w, tp + v, 8);
+        if (!w) { v += 8; continue; }
+      }
+      const int end = std::min(numVerts, v + 8);
+      for (; v < end; v++)
+        if (touched[v]) { cur[v] ^= 1; touched[v] = 0; f(v, (int)cur[v]); }
+    }
   }
 
   void invalidateSolution(int v) { for (; v != -1; v = parent[v]) solved[v] = 0; }        // IntermediateNode.cpp:5-13

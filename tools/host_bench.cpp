@@ -294,7 +294,14 @@ static int fuzz(int rounds, uint64_t seed) {
         CHECK(now == committed, "topology after the rollback is not the committed one");
         checkTips(ht);
       }
-      for (int v = n; v < ht.numVerts; v++) if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
+      {
+        // the eight-at-a-time rollback against the plain loop over every vertex
+        std::vector<int> want, got;
+        for (int v = n; v < ht.numVerts; v++) if (ht.touched[v]) want.push_back(2 * v + (ht.cur[v] ^ 1));
+        ht.rollbackTouched([&](int v, int slot) { got.push_back(2 * v + slot); });
+        CHECK(got == want, "rollbackTouched visits other vertices (or other slots) than the plain loop");
+        for (int v = 0; v < ht.numVerts; v++) CHECK(!ht.touched[v], "a touched flag survived the rollback");
+      }
       CHECK(ht.cur == curBefore, "slot bits after the rollback");
       if (sm) ht.within = withinBefore;
       checkAssociate(ht, rng);
@@ -401,7 +408,7 @@ int main(int argc, char** argv) {
       tn += us(t0);
       t0 = Clock::now();
       CHECK(ht.restoreTopology(committed.data(), rows), "restore");
-      for (int v = s.n; v < ht.numVerts; v++) if (ht.touched[v]) { ht.cur[v] ^= 1; ht.touched[v] = 0; }
+      ht.rollbackTouched([](int, int) {});
       tq += us(t0);
       done++;
     }
