@@ -318,6 +318,7 @@ def run_ours(args, rank, world, local_rank):
     p, (n, s, k, r) = make_problem(args, world)
     S_total = p.S
     W, B, pi = frozen(p.W[p.w_idx - 1]), frozen(p.B[p.b_idx - 1]), frozen(p.pi)
+    edge = frozen(np.asarray(p.edge, np.int32))
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -350,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---------------------------------------------------------------- device-resident leg
-    res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+    res = eng.logLikCpp(edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
     h, ll0 = res["solutionPointer"], res["logLik"]
     single_ll = None
     if world > 1 and rank == 0:
@@ -358,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
         # rank's device (one slot of partials: 33 GB for config 3), outside every timed region
         one = Engine(device=local_rank, fuse_tips=args.fuse)
         full = one.getConvertedAlignment(list(synth.STATES), p.chars)
-        r1 = one.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, full, p.n, S_total, p.w_idx, p.b_idx)
+        r1 = one.logLikCpp(edge, p.mrcas, pi, W, B, 1, full, p.n, S_total, p.w_idx, p.b_idx)
         single_ll = r1["logLik"]
         one.finalDeallocate(r1["solutionPointer"])
         del full
@@ -446,14 +447,14 @@ def run_ours(args, rank, world, local_rank):
     # ---------------------------------------------------------------- end-to-end leg (host buffers in, scalar out)
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     for _ in range(3):
-        res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        res = eng.logLikCpp(edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
         eng.finalDeallocate(res["solutionPointer"])
     barrier()
     sampler.mark = "e2e"
     t0 = time.perf_counter()
     e2e_parts = np.zeros(4)
     for _ in range(e2e_steps):
-        res = eng.logLikCpp(p.edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
+        res = eng.logLikCpp(edge, p.mrcas, pi, W, B, 1, al, p.n, s_local, p.w_idx, p.b_idx)
         sti = local.stats(res["solutionPointer"])
         e2e_parts += (sti["create_setup_us"] * 1e-3, sti["create_upload_ms"], sti["last_eval_ms"], sti["last_host_total_us"] * 1e-3)
         eng.finalDeallocate(res["solutionPointer"])
@@ -557,7 +558,8 @@ def config2_leg(args, eng):
     pinned.numpy()[...] = masks
     alq = pinned.numpy()
     W, B, pi = frozen(q.W[4]), frozen(q.B[4]), frozen(q.pi)
-    res = eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)
+    edge = frozen(np.asarray(q.edge, np.int32))
+    res = eng.logLikCpp(edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)
     h = res["solutionPointer"]
     for _ in range(5):
         eng.recomputeAll(h, W, B, pi)
@@ -568,10 +570,10 @@ def config2_leg(args, eng):
     ms = eng.timer_end(h) / steps
     eng.finalDeallocate(h)
     for _ in range(3):
-        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+        eng.finalDeallocate(eng.logLikCpp(edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
     t0 = time.perf_counter()
     for _ in range(20):
-        eng.finalDeallocate(eng.logLikCpp(q.edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
+        eng.finalDeallocate(eng.logLikCpp(edge, q.mrcas, pi, W, B, 1, alq, n, s, 5, 5)["solutionPointer"])
     e2e = (time.perf_counter() - t0) / 20 * 1e3
     upd = (n - 1) * s * r
     return {"workload": f"config2: {n} seqs x {s} sites, {k} clusters, {r} rate categories", "value": upd / (ms * 1e-3),

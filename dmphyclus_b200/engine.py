@@ -246,20 +246,22 @@ class Engine:
 
     def logLikCpp(self, edgeMat, clusterMRCAs, limProbsVec, withinTransMatList, betweenTransMatList, numOpenMP,
                   alignmentBin, numTips, numLoci, withinMatListIndex, betweenMatListIndex, deferred=False):
-        e = _edge(edgeMat)
-        m = np.asarray(clusterMRCAs, dtype=np.float64).ravel()
-        pi = np.ascontiguousarray(limProbsVec, dtype=np.float64)
-        w, b = _mats(withinTransMatList), _mats(betweenTransMatList)
+        # (read-only inputs handed in again — logLikFromClusInd called in a loop — are converted once: _ep, _mp, _pp)
+        e, n_rows = self._ep(edgeMat)
+        m, n_m = self._lp(clusterMRCAs, np.float64, _dbl_p)
+        pi = self._pp(limProbsVec)
+        w, b = self._mp(withinTransMatList), self._mp(betweenTransMatList)
+        n_rates = len(withinTransMatList)
         al = np.ascontiguousarray(alignmentBin, dtype=np.uint8)
-        if al.shape != (numTips, numLoci) or len(w) != len(b) or len(pi) != 4:
+        if al.shape != (numTips, numLoci) or n_rates != len(betweenTransMatList):
             raise ValueError("alignmentBin must be [numTips][numLoci]; matrix lists must have equal length")
         h, ll = _P(), C.c_double()
         self.opts.deferred = int(deferred)
-        self._check(self.lib.dmpc_loglik_create(_p(e, _i32_p), len(e) // 2, _p(m, _dbl_p), len(m), _p(pi, _dbl_p),
-                                                _p(w, _dbl_p), _p(b, _dbl_p), len(w) // 16, _p(al, _u8_p), numTips,
+        self._check(self.lib.dmpc_loglik_create(e, n_rows, m, n_m, pi,
+                                                w, b, n_rates, _p(al, _u8_p), numTips,
                                                 numLoci, int(withinMatListIndex), int(betweenMatListIndex),
                                                 C.byref(self.opts), C.byref(h), C.byref(ll)))
-        self._shape[h.value] = (numTips, numLoci, len(w) // 16)
+        self._shape[h.value] = (numTips, numLoci, n_rates)
         return {"logLik": ll.value, "solutionPointer": h.value, "alignmentBinPointer": None}
 
     def newBetweenTransProbsLogLik(self, ptr, withinTransProbs, newBetweenTransProbs, numOpenMP,

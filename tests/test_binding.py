@@ -141,3 +141,33 @@ def test_result_objects_of_the_nni_entry_points(mats, monkeypatch):
             np.array(res["edge"], dtype=np.int32)            # what the driver does with it (chain._frozen_edge)
     assert eng.RestorePreviousConfig(None, np.zeros((1, 2), np.int32), 5, 5, False, [3, 4], True) is None
     assert isinstance(eng.clusSplitMergeLogLik(None, w, b, [7], 1, pi), float)
+
+
+def test_loglikcpp_marshalling_with_cached_and_fresh_inputs(mats, packaged):
+    """logLikCpp converts read-only inputs once (a logLikFromClusInd-style loop hands the same objects in again) and
+    writeable ones every time; either way the call reaches the library, which — without a GPU — refuses with
+    DMPC_ERR_CUDA, and malformed inputs are refused before that."""
+    import torch
+    from dmphyclus_b200.workloads import Problem
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the refusal path is exercised on CPU-only boxes")
+    w, b, pi = mats
+    eng = Engine()
+    p = Problem(packaged, 12, 9, 3, 3, "iid", seed=4)
+    al = eng.getConvertedAlignment(list(synth.STATES), p.chars)
+    edge_ro = np.array(p.edge, np.int32)
+    edge_ro.setflags(write=False)
+    for edge in (edge_ro, edge_ro, np.array(p.edge), p.edge.tolist() if hasattr(p.edge, "tolist") else p.edge):
+        for mr in (p.mrcas, list(p.mrcas), np.asarray(p.mrcas, np.float64)):
+            with pytest.raises(DmpcError) as e:
+                eng.logLikCpp(edge, mr, pi, w, b, 1, al, p.n, p.S, 5, 5)
+            assert e.value.code == -2
+    assert len(eng._ecache) == 1                                   # the read-only edge matrix was converted once
+    with pytest.raises(ValueError):
+        eng.logLikCpp(edge_ro, p.mrcas, pi, w, b[:2], 1, al, p.n, p.S, 5, 5)          # lists of different length
+    with pytest.raises(ValueError):
+        eng.logLikCpp(edge_ro, p.mrcas, pi[:3], w, b, 1, al, p.n, p.S, 5, 5)          # limProbs
+    with pytest.raises(ValueError):
+        eng.logLikCpp(edge_ro, p.mrcas, pi, w, b, 1, al[:, :5], p.n, p.S, 5, 5)       # alignment shape
+    with pytest.raises(ValueError):
+        eng.logLikCpp(edge_ro, p.mrcas, pi, w[:, :3], b, 1, al, p.n, p.S, 5, 5)       # not 4x4 matrices
